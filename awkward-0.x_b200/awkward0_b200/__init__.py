@@ -1,0 +1,14 @@
+"""awkward0_b200 -- the awkward0 JaggedArray hot path on B200 (sm_100a): same Python API, CUDA kernels behind a
+ctypes C ABI, device-resident buffers, no CPU fallback.
+
+    from awkward0_b200 import JaggedArray
+    a = JaggedArray.fromcounts(counts, pt)          # host arrays are copied to HBM once
+    lead = a[a.argmax()]; sel = a[a > 20]; s = a.sum(); p = a.pairs()
+"""
+from ._lib import LIB_PATH, JaggedLibError  # noqa: F401  (fails loudly when the .so is missing)
+from .device import DeviceArray, asdevice  # noqa: F401
+from .table import Table  # noqa: F401
+from .jagged import JaggedArray  # noqa: F401
+
+__version__ = "0.1.0"
+__all__ = ["JaggedArray", "Table", "DeviceArray", "asdevice"]

@@ -1,0 +1,289 @@
+"""Device-resident 1-D arrays and the per-process runtime (workspace, stream, status read-back).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), the current CUDA stream and -- in
+sharded.py -- the NCCL communicator.  All arithmetic goes through libjagged_sm100a.so (see _lib.py).
+"""
+import ctypes
+
+import numpy
+import numpy.lib.mixins
+
+from . import _lib
+from ._lib import lib
+
+try:
+    import torch
+except ImportError as err:          # pragma: no cover
+    raise ImportError("awkward0_b200 needs PyTorch for device memory and streams") from err
+
+
+# ---- dtype tables ---------------------------------------------------------------------------------------------
+_NP2JG = {
+    numpy.dtype(numpy.float32): _lib.JG_F32, numpy.dtype(numpy.float64): _lib.JG_F64,
+    numpy.dtype(numpy.int32): _lib.JG_I32, numpy.dtype(numpy.int64): _lib.JG_I64,
+    numpy.dtype(numpy.bool_): _lib.JG_B8, numpy.dtype(numpy.uint8): _lib.JG_U8,
+    numpy.dtype(numpy.int8): _lib.JG_I8, numpy.dtype(numpy.int16): _lib.JG_I16,
+    numpy.dtype(numpy.uint16): _lib.JG_U16, numpy.dtype(numpy.uint32): _lib.JG_U32,
+    numpy.dtype(numpy.uint64): _lib.JG_U64,
+}
+_NP2TORCH = {
+    numpy.dtype(numpy.float32): torch.float32, numpy.dtype(numpy.float64): torch.float64,
+    numpy.dtype(numpy.int32): torch.int32, numpy.dtype(numpy.int64): torch.int64,
+    numpy.dtype(numpy.bool_): torch.bool, numpy.dtype(numpy.uint8): torch.uint8,
+    numpy.dtype(numpy.int8): torch.int8, numpy.dtype(numpy.int16): torch.int16,
+    numpy.dtype(numpy.uint16): torch.uint16, numpy.dtype(numpy.uint32): torch.uint32,
+    numpy.dtype(numpy.uint64): torch.uint64,
+}
+_TORCH2NP = dict((v, k) for k, v in _NP2TORCH.items())
+
+INDEXTYPE = numpy.dtype(numpy.int64)
+BOOLTYPE = numpy.dtype(numpy.bool_)
+
+
+def jg_code(dtype):
+    dtype = numpy.dtype(dtype)
+    try:
+        return _NP2JG[dtype]
+    except KeyError:
+        raise NotImplementedError("dtype {0} is not supported on the device (awkward0_b200 has no CPU fallback)".format(dtype))
+
+
+def torch_dtype(dtype):
+    dtype = numpy.dtype(dtype)
+    try:
+        return _NP2TORCH[dtype]
+    except KeyError:
+        raise NotImplementedError("dtype {0} is not supported on the device".format(dtype))
+
+
+# ---- runtime ----------------------------------------------------------------------------------------------------
+class _Runtime(object):
+    """Per-device scratch: the look-back workspace and the small status/total words kernels write."""
+
+    def __init__(self):
+        self._ws = {}
+
+    @staticmethod
+    def device():
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: awkward0_b200 runs on B200 only and has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    @staticmethod
+    def stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def workspace(self, n):
+        """(pointer, bytes) of a scratch buffer large enough for any call on n events."""
+        dev = self.device()
+        need = int(lib.jg_workspace_bytes(int(n)))
+        buf = self._ws.get(dev.index)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+            self._ws[dev.index] = buf
+        return ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel())
+
+    def scalars(self):
+        """A zeroed int64[8] on the device: [0] total, [1] status (low 32 bits), [2:6] info."""
+        return torch.zeros(8, dtype=torch.int64, device=self.device())
+
+    @staticmethod
+    def read(scal):
+        """One device->host read (synchronises the stream): returns (total, status, info[4])."""
+        host = scal.cpu().numpy()
+        return int(host[0]), int(host[1]) & 0xffffffff, host[2:6]
+
+
+runtime = _Runtime()
+
+
+def ptr(t, offset_items=0):
+    """Raw device pointer of a torch tensor (optionally advanced by whole items)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr() + offset_items * t.element_size())
+
+
+def empty(n, dtype):
+    return torch.empty(int(n), dtype=torch_dtype(dtype), device=runtime.device())
+
+
+# ---- DeviceArray --------------------------------------------------------------------------------------------------
+class DeviceArray(numpy.lib.mixins.NDArrayOperatorsMixin):
+    """A 1-D array resident in HBM with a numpy-like surface (dtype, len, slicing views, tolist, ufuncs).
+
+    It stands where the reference holds a ``numpy.ndarray`` (starts/stops/offsets/content/counts/parents and
+    every flat result such as ``a.sum()``).  Arithmetic on it runs the same CUDA kernels as JaggedArray content.
+    """
+
+    __array_priority__ = 50
+    __slots__ = ("_t", "_dtype")
+
+    def __init__(self, tensor, dtype=None):
+        if not isinstance(tensor, torch.Tensor):
+            raise TypeError("DeviceArray wraps a torch.Tensor; use asdevice() to convert")
+        if tensor.dim() != 1:
+            raise ValueError("DeviceArray is one-dimensional")
+        if not tensor.is_cuda:
+            raise ValueError("DeviceArray must live on a CUDA device (no CPU fallback)")
+        if not tensor.is_contiguous():
+            tensor = tensor.contiguous()
+        self._t = tensor
+        self._dtype = numpy.dtype(dtype) if dtype is not None else _TORCH2NP[tensor.dtype]
+
+    # -- numpy-like surface
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def shape(self):
+        return (int(self._t.shape[0]),)
+
+    @property
+    def ndim(self):
+        return 1
+
+    @property
+    def size(self):
+        return int(self._t.shape[0])
+
+    @property
+    def nbytes(self):
+        return int(self._t.numel() * self._t.element_size())
+
+    @property
+    def itemsize(self):
+        return int(self._t.element_size())
+
+    def __len__(self):
+        return int(self._t.shape[0])
+
+    @property
+    def tensor(self):
+        """The underlying torch tensor (zero-copy)."""
+        return self._t
+
+    def data_ptr(self, offset_items=0):
+        return ptr(self._t, offset_items)
+
+    def get(self):
+        """Copy to a host numpy array (device -> host)."""
+        if self._t.dtype in (torch.uint16, torch.uint32, torch.uint64):
+            return self._t.view(_NP2TORCH[numpy.dtype("i%d" % self.itemsize)]).cpu().numpy().view(self._dtype)
+        return self._t.cpu().numpy().astype(self._dtype, copy=False)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.get()
+        return out if dtype is None else out.astype(dtype, copy=False)
+
+    def tolist(self):
+        return self.get().tolist()
+
+    def copy(self):
+        return DeviceArray(self._t.clone(), self._dtype)
+
+    def view(self, dtype):
+        dtype = numpy.dtype(dtype)
+        if dtype.itemsize != self._dtype.itemsize:
+            raise ValueError("DeviceArray.view needs the same itemsize")
+        return DeviceArray(self._t.view(torch_dtype(dtype)), dtype)
+
+    def astype(self, dtype, copy=True):
+        dtype = numpy.dtype(dtype)
+        if dtype == self._dtype:
+            return self.copy() if copy else self
+        from . import _ufunc
+        return _ufunc.cast(self, dtype)
+
+    def __repr__(self):
+        n = len(self)
+        if n <= 8:
+            body = " ".join(str(x) for x in self.tolist())
+        else:
+            body = " ".join(str(x) for x in self[:3].tolist()) + " ... " + " ".join(str(x) for x in self[-3:].tolist())
+        return "<DeviceArray [{0}] {1} at cuda:{2}>".format(body, self._dtype, self._t.device.index)
+
+    def __getitem__(self, where):
+        if isinstance(where, slice):
+            start, stop, step = where.indices(len(self))
+            if step != 1:
+                raise NotImplementedError("DeviceArray slices must have step 1")
+            return DeviceArray(self._t[start:max(start, stop)], self._dtype)
+        if isinstance(where, (int, numpy.integer)):
+            n = len(self)
+            i = int(where)
+            if i < 0:
+                i += n
+            if not 0 <= i < n:
+                raise IndexError("index {0} is out of bounds for axis 0 with size {1}".format(where, n))
+            return self[i:i + 1].get()[0]
+        if isinstance(where, DeviceArray) and where.dtype.kind in "iu":
+            from . import _ufunc
+            return _ufunc.take(self, where)
+        raise NotImplementedError("DeviceArray supports integer, slice and integer-array indexing only")
+
+    def __bool__(self):
+        if len(self) == 1:
+            return bool(self.get()[0])
+        raise ValueError("The truth value of an array with more than one element is ambiguous. Use a.any() or a.all()")
+
+    # -- ufuncs and reductions run on the device
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        from . import _ufunc
+        for x in inputs:
+            if type(x).__name__ == "JaggedArray":       # let the jagged operand drive the broadcast
+                return NotImplemented
+        if "out" in kwargs:
+            raise NotImplementedError("in-place operations not supported")
+        if method != "__call__":
+            return NotImplemented
+        return _ufunc.flat_ufunc(ufunc, inputs)
+
+    def _reduce(self, op):
+        from . import _ufunc
+        return _ufunc.flat_reduce(self, op)
+
+    def sum(self):
+        return self._reduce(_lib.SUM)
+
+    def prod(self):
+        return self._reduce(_lib.PROD)
+
+    def min(self):
+        return self._reduce(_lib.MIN)
+
+    def max(self):
+        return self._reduce(_lib.MAX)
+
+    def any(self):
+        return self._reduce(_lib.ANY)
+
+    def all(self):
+        return self._reduce(_lib.ALL)
+
+
+def asdevice(x, dtype=None):
+    """Anything array-like -> DeviceArray (host data is copied host->device once)."""
+    if isinstance(x, DeviceArray):
+        return x if dtype is None or numpy.dtype(dtype) == x.dtype else x.astype(dtype)
+    if isinstance(x, torch.Tensor):
+        if x.dim() != 1:
+            raise ValueError("only one-dimensional device tensors are supported")
+        if not x.is_cuda:
+            x = x.to(runtime.device())
+        out = DeviceArray(x)
+        return out if dtype is None or numpy.dtype(dtype) == out.dtype else out.astype(dtype)
+    arr = numpy.asarray(x)
+    if dtype is not None:
+        arr = arr.astype(dtype, copy=False)
+    if arr.ndim != 1:
+        raise NotImplementedError("only one-dimensional arrays are supported on the device (got shape {0})".format(arr.shape))
+    np_dtype = arr.dtype
+    tdt = torch_dtype(np_dtype)
+    arr = numpy.ascontiguousarray(arr)
+    if np_dtype.kind == "u" and np_dtype.itemsize > 1:
+        host = torch.from_numpy(arr.view("i%d" % np_dtype.itemsize)).view(tdt)
+    else:
+        host = torch.from_numpy(arr)
+    return DeviceArray(host.to(runtime.device()), np_dtype)

@@ -1,0 +1,1136 @@
+"""GPU-resident JaggedArray with the awkward0 API (reference: awkward0/array/jagged.py, awkward0/array/base.py).
+
+Same method names, argument meaning and exceptions as ``awkward0.JaggedArray`` for the hot path named in
+BASELINE.json; every array operation is a hand-written sm_100a kernel reached through the C ABI of
+libjagged_sm100a.so (include/jagged_b200.h).  Buffers stay in HBM between calls: starts / stops / offsets /
+content / counts / parents and every flat result are ``DeviceArray`` objects (device.py); only ``tolist()``,
+``__array__``/``.get()`` and error checks move data to the host.  There is no CPU fallback: operations outside
+the hot path (last paragraph) raise NotImplementedError.
+
+Design differences from the reference that do not change results:
+  * the canonical layout is dense int64 ``offsets`` (an explicit flag instead of the pointer-alias test of
+    jagged.py:25-40); general starts/stops are accepted and compacted on first use (jagged.py:883-942);
+  * validity (jagged.py:469-477) is one fused kernel whose flags are read back together with offsets[0],
+    offsets[-1]; arrays produced by this library's own kernels are born valid;
+  * results whose reference layout is non-dense (argmin/argmax, jagged.py:1597-1600) are returned dense -- the
+    logical value (tolist(), counts, flatten()) is identical.
+"""
+import ctypes
+import numbers
+from collections import OrderedDict
+
+import numpy
+import numpy.lib.mixins
+
+from . import _lib, _ufunc
+from ._lib import call
+from .device import (BOOLTYPE, INDEXTYPE, DeviceArray, asdevice, empty, jg_code, runtime, torch, torch_dtype)
+from .table import Table
+
+
+def _vp(t, offset_items=0):
+    return ctypes.c_void_p(t.data_ptr() + offset_items * t.element_size()) if t is not None else ctypes.c_void_p(0)
+
+
+def _isintegertype(dtype):
+    return issubclass(numpy.dtype(dtype).type, numpy.integer)
+
+
+class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
+    """JaggedArray(starts, stops, content) on the device -- drop-in for awkward0.JaggedArray's hot path."""
+
+    # global switches, same names and defaults as base.py:28-31
+    allow_tonumpy = True
+    allow_iter = True
+    check_prop_valid = True
+    check_whole_valid = True
+
+    DEFAULTTYPE = numpy.dtype(numpy.float64)      # base.py:42-48
+    INDEXTYPE = INDEXTYPE
+    BOOLTYPE = BOOLTYPE
+    MASKTYPE = BOOLTYPE
+
+    __array_priority__ = 100
+
+    # class indirection (base.py:306-374): subclasses can substitute their own node classes
+    @property
+    def JaggedArray(self):
+        return JaggedArray
+
+    @property
+    def Table(self):
+        return Table
+
+    # ------------------------------------------------------------------------------------------------------
+    # classmethods that ARE the reference's kernels
+    # ------------------------------------------------------------------------------------------------------
+    @classmethod
+    def counts2offsets(cls, counts):
+        """jagged.py:42-47 -> jg_counts2offsets (single-pass decoupled-lookback scan).  Returns int64[N+1]."""
+        offsets, _, _ = cls._scan_counts(asdevice(counts), sync=False)
+        return offsets
+
+    @classmethod
+    def _scan_counts(cls, counts, sync=True):
+        if counts.dtype == numpy.int64 or counts.dtype == numpy.int32:
+            src = counts
+        elif counts.dtype == numpy.bool_ or counts.dtype == numpy.uint8:
+            src = counts
+        elif _isintegertype(counts.dtype):
+            src = counts.astype(numpy.int64)
+        else:
+            raise TypeError("counts must have integer dtype")
+        n = len(src)
+        offsets = empty(n + 1, INDEXTYPE)
+        scal = runtime.scalars()
+        ws, wsb = runtime.workspace(n)
+        call("jg_counts2offsets", src.data_ptr(), jg_code(src.dtype), n, _vp(offsets), _vp(scal), _vp(scal, 1), ws, wsb,
+             runtime.stream())
+        total, status = None, 0
+        if sync:
+            total, status, _ = runtime.read(scal)
+        return DeviceArray(offsets, INDEXTYPE), total, status
+
+    @classmethod
+    def offsets2parents(cls, offsets):
+        """jagged.py:49-54 -> jg_offsets2parents."""
+        offsets = cls._as_index64(asdevice(offsets))
+        n = len(offsets) - 1
+        if n < 0:
+            raise ValueError("offsets must be a non-empty array")
+        last = int(offsets[-1]) if n >= 0 else 0
+        return cls._parents_from(offsets, n, last)
+
+    @classmethod
+    def _parents_from(cls, off64, n, last):
+        out = empty(last, INDEXTYPE)
+        if last > 0:
+            call("jg_offsets2parents", off64.data_ptr(), n, _vp(out), runtime.stream())
+        return DeviceArray(out, INDEXTYPE)
+
+    @classmethod
+    def startsstops2parents(cls, starts, stops):
+        """jagged.py:56-71 -> jg_startsstops2parents."""
+        starts = cls._as_index64(asdevice(starts))
+        stops = cls._as_index64(asdevice(stops))
+        n = len(starts)
+        out_len = int(stops[:n].max()) if n > 0 else 0
+        out = empty(out_len, INDEXTYPE)
+        call("jg_startsstops2parents", starts.data_ptr(), stops.data_ptr(), n, _vp(out), out_len, runtime.stream())
+        return DeviceArray(out, INDEXTYPE)
+
+    @staticmethod
+    def _as_index64(x):
+        if x.dtype == numpy.int64:
+            return x
+        if not _isintegertype(x.dtype):
+            raise TypeError("offsets must have integer dtype")
+        return x.astype(numpy.int64)
+
+    @classmethod
+    def offsetsaliased(cls, starts, stops):
+        """jagged.py:25-40 -- are starts/stops the [:-1] / [1:] views of one offsets buffer?"""
+        if isinstance(starts, DeviceArray) and isinstance(stops, DeviceArray):
+            a, b = starts.tensor, stops.tensor
+            return (a.dtype == b.dtype and len(starts) == len(stops) and
+                    a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr() and
+                    b.data_ptr() == a.data_ptr() + a.element_size() and
+                    a.untyped_storage().nbytes() >= (a.storage_offset() + len(starts) + 1) * a.element_size())
+        if isinstance(starts, numpy.ndarray) and isinstance(stops, numpy.ndarray):
+            return (starts.base is not None and starts.base is stops.base and starts.ndim == 1 and stops.ndim == 1 and
+                    isinstance(starts.base, numpy.ndarray) and starts.base.ndim == 1 and
+                    starts.dtype == stops.dtype == starts.base.dtype and
+                    starts.ctypes.data == starts.base.ctypes.data and
+                    stops.ctypes.data == starts.base.ctypes.data + stops.dtype.itemsize and
+                    len(starts) == len(starts.base) - 1 and len(stops) == len(stops.base) - 1)
+        return False
+
+    # ------------------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------------------
+    def __init__(self, starts, stops, content):
+        self._reset()
+        self._content = self._tocontent(content)
+        if self.offsetsaliased(starts, stops):
+            if isinstance(starts, DeviceArray):
+                t = starts.tensor
+                base = DeviceArray(torch.as_strided(t, (len(starts) + 1,), (1,), t.storage_offset()), starts.dtype)
+            else:
+                base = asdevice(starts.base)
+            self._set_offsets(base)
+        else:
+            starts = asdevice(starts if not isinstance(starts, (list, tuple)) or len(starts) else numpy.zeros(0, INDEXTYPE))
+            stops = asdevice(stops if not isinstance(stops, (list, tuple)) or len(stops) else numpy.zeros(0, INDEXTYPE))
+            if self.check_prop_valid:
+                if not _isintegertype(starts.dtype):
+                    raise TypeError("starts must have integer dtype")
+                if not _isintegertype(stops.dtype):
+                    raise TypeError("stops must have integer dtype")
+            if len(starts) > len(stops):
+                raise ValueError("starts must have the same (or shorter) length than stops")
+            self._starts, self._stops = starts, stops[:len(starts)]
+            self._check_general()
+
+    def _reset(self):
+        self._starts = self._stops = self._offsets = self._off64 = None
+        self._counts = self._parents = None
+        self._isvalid = False
+        self._first = self._last = None      # host copies of offsets[0], offsets[-1]
+        self._pending_status = 0
+        self._rebased = None
+        self._general = None
+        self._maxcount = None
+
+    @classmethod
+    def _tocontent(cls, content):
+        if isinstance(content, (DeviceArray, Table, JaggedArray)):
+            return content
+        if isinstance(content, torch.Tensor):
+            return asdevice(content)
+        arr = numpy.asarray(content)
+        if arr.dtype == numpy.dtype(object) or arr.size == 0 and not isinstance(content, numpy.ndarray):
+            arr = numpy.asarray(content, dtype=cls.DEFAULTTYPE)
+        return asdevice(arr)
+
+    def _set_offsets(self, offsets):
+        """Adopt a dense offsets buffer (user dtype kept for the properties, int64 copy for the kernels)."""
+        if not _isintegertype(offsets.dtype):
+            raise TypeError("offsets must have integer dtype")
+        if len(offsets) == 0:
+            raise ValueError("offsets must be a non-empty array")
+        self._offsets = offsets
+        self._off64 = self._as_index64(offsets)
+        self._starts, self._stops = offsets[:-1], offsets[1:]
+        self._counts = self._parents = self._rebased = None
+        self._isvalid = False
+        self._first = self._last = None
+        if self.check_prop_valid or self.check_whole_valid:
+            self._run_validate()
+            if self.check_prop_valid and self._pending_status & _lib.ST_NEGATIVE_OFFSET:
+                raise ValueError("offsets must be a non-negative array")
+
+    def _content_len(self):
+        return len(self._content)
+
+    def _run_validate(self):
+        n = len(self._off64) - 1
+        scal = runtime.scalars()
+        call("jg_validate_offsets", self._off64.data_ptr(), n, self._content_len(), _vp(scal, 2), _vp(scal, 1),
+             runtime.stream())
+        _, status, info = runtime.read(scal)
+        self._pending_status = status
+        self._first, self._last = int(info[0]), int(info[1])
+        self._maxcount = int(info[2])
+
+    def _check_general(self):
+        """General starts/stops: validate, and adopt dense offsets when starts[1:] == stops[:-1] (jagged.py:358)."""
+        n = len(self._starts)
+        s64, e64 = self._as_index64(self._starts), self._as_index64(self._stops)
+        scal = runtime.scalars()
+        call("jg_validate_startsstops", s64.data_ptr(), e64.data_ptr(), n, self._content_len(), _vp(scal, 2),
+             _vp(scal, 1), runtime.stream())
+        _, status, info = runtime.read(scal)
+        if self.check_prop_valid and status & _lib.ST_NEGATIVE_OFFSET:
+            raise ValueError("starts must be a non-negative array")
+        self._pending_status = status
+        self._general = (s64, e64)
+        if not status & _lib.ST_NOT_OFFSETS and not status & _lib.ST_STOPS_LT_STARTS:
+            # offsets-compatible: build the dense offsets once (append(starts, stops[-1]), jagged.py:362)
+            off = empty(n + 1, INDEXTYPE)
+            if n > 0:
+                off[:n].copy_(s64.tensor)
+                off[n:].copy_(e64.tensor[n - 1:])
+            else:
+                off.zero_()
+            self._off64 = DeviceArray(off, INDEXTYPE)
+            self._offsets = self._off64 if self._starts.dtype == numpy.int64 else None
+            if n > 0:
+                first, last = self._off64[0], self._off64[-1]
+            else:
+                first = last = 0
+            self._first, self._last = int(first), int(last)
+
+    @classmethod
+    def _make(cls, off64, content, last, first=0):
+        """Internal constructor for arrays produced by this library's kernels (dense, valid, bounds known)."""
+        out = cls.__new__(cls)
+        out._reset()
+        out._content = content
+        out._offsets = out._off64 = off64
+        out._starts, out._stops = off64[:-1], off64[1:]
+        out._isvalid = True
+        out._first, out._last = first, last
+        return out
+
+    @classmethod
+    def fromiter(cls, iterable):
+        """Host-side builder (generate.py is out of scope): nested python lists -> counts + content -> device."""
+        rows = [list(x) for x in iterable]
+        counts = numpy.array([len(x) for x in rows], dtype=INDEXTYPE)
+        flat = [y for x in rows for y in x]
+        content = numpy.array(flat) if len(flat) else numpy.array([], dtype=cls.DEFAULTTYPE)
+        return cls.fromcounts(counts, content)
+
+    @classmethod
+    def fromoffsets(cls, offsets, content):
+        """jagged.py:142-153."""
+        offsets = asdevice(offsets if not isinstance(offsets, (list, tuple)) else numpy.asarray(offsets, dtype=INDEXTYPE))
+        if not _isintegertype(offsets.dtype):
+            raise TypeError("offsets must have integer dtype")
+        if len(offsets) == 0:
+            raise ValueError("offsets must be a non-empty array")
+        out = cls.__new__(cls)
+        out._reset()
+        out._content = cls._tocontent(content)
+        out._set_offsets(offsets)
+        return out
+
+    @classmethod
+    def fromcounts(cls, counts, content):
+        """jagged.py:155-166 -> jg_counts2offsets; negative counts / non-integer dtype raise like the reference."""
+        if isinstance(counts, (list, tuple)):
+            counts = numpy.asarray(counts, dtype=INDEXTYPE) if len(counts) else numpy.zeros(0, dtype=INDEXTYPE)
+        counts = asdevice(counts)
+        if not _isintegertype(counts.dtype) and counts.dtype != numpy.bool_:
+            raise TypeError("counts must have integer dtype")
+        if counts.dtype == numpy.bool_:
+            raise TypeError("counts must have integer dtype")
+        content = cls._tocontent(content)
+        offsets, total, status = cls._scan_counts(counts)
+        if status & _lib.ST_NEGATIVE_COUNT:
+            raise ValueError("counts must be a non-negative array")
+        out = cls._make(offsets, content, total)
+        out._counts = counts
+        out._isvalid = False
+        out._pending_status = _lib.ST_BEYOND_CONTENT if total > len(content) else 0
+        return out
+
+    def copy(self, starts=None, stops=None, content=None):
+        out = self.__class__.__new__(self.__class__)
+        out.__dict__.update(self.__dict__)
+        if content is not None:
+            out._content = self._tocontent(content)
+            out._isvalid = False
+        if starts is not None or stops is not None:
+            s = self._starts if starts is None else starts
+            e = self._stops if stops is None else stops
+            fresh = JaggedArray(s, e, out._content)
+            out.__dict__.update(fresh.__dict__)
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # validity
+    # ------------------------------------------------------------------------------------------------------
+    def _valid(self):
+        """jagged.py:469-492."""
+        if self._isvalid:
+            return
+        if self.check_whole_valid:
+            st = self._pending_status
+            if self._off64 is not None and self._general is None:
+                if self._first is None:
+                    self._run_validate()
+                    st = self._pending_status
+                if st & _lib.ST_NEGATIVE_OFFSET:
+                    raise ValueError("offsets must be a non-negative array")
+                if st & _lib.ST_NONMONOTONE:
+                    raise ValueError("offsets must be monatonically increasing")
+                if st & _lib.ST_BEYOND_CONTENT:
+                    raise ValueError("maximum offset {0} is beyond the length of the content ({1})".format(self._last, self._content_len()))
+            else:
+                if st & _lib.ST_STOPS_LT_STARTS:
+                    raise ValueError("stops must be greater than or equal to starts")
+                if st & _lib.ST_BEYOND_CONTENT:
+                    raise ValueError("maximum stop is beyond the length of the content ({0})".format(self._content_len()))
+        elif self._off64 is not None and self._first is None:
+            n = len(self._off64) - 1
+            self._first, self._last = int(self._off64[0]), int(self._off64[n])
+        self._isvalid = True
+
+    def valid(self, exception=False, message=False):
+        """base.py:174-188."""
+        try:
+            self._valid()
+        except Exception as err:
+            if exception:
+                raise err
+            elif message:
+                return "{0}: {1}".format(type(err), str(err))
+            else:
+                return False
+        else:
+            return None if message else True
+
+    def _canuseoffset(self):
+        self._valid()
+        return self._off64 is not None
+
+    @property
+    def iscompact(self):
+        return len(self._starts) == 0 or self._off64 is not None
+
+    def compact(self):
+        """jagged.py:1386-1398 -> counts, scan, jg_compact_gather."""
+        self._valid()
+        if self._off64 is not None:
+            return self
+        s64, e64 = self._general
+        n = len(s64)
+        counts = empty(n, INDEXTYPE)
+        call("jg_startsstops2counts", s64.data_ptr(), e64.data_ptr(), n, _vp(counts), runtime.stream())
+        offsets, total, _ = self._scan_counts(DeviceArray(counts, INDEXTYPE))
+        content = self._map_content(lambda c: self._compact_column(c, s64, offsets, n, total))
+        out = self._make(offsets, content, total)
+        out._counts = DeviceArray(counts, INDEXTYPE)
+        return out
+
+    @staticmethod
+    def _compact_column(col, s64, offsets, n, total):
+        out = empty(total, col.dtype)
+        if total > 0:
+            call("jg_compact_gather", col.data_ptr(), col.itemsize, s64.data_ptr(), offsets.data_ptr(), n, _vp(out),
+                 runtime.stream())
+        return DeviceArray(out, col.dtype)
+
+    def _map_content(self, fcn, content=None):
+        content = self._content if content is None else content
+        if isinstance(content, Table):
+            return content.map(fcn)
+        if isinstance(content, JaggedArray):
+            raise NotImplementedError("jagged-of-jagged content is outside the GPU hot path (no CPU fallback)")
+        return fcn(content)
+
+    def _dense(self):
+        """(compact array, off64, nevents, first, last): the form every kernel consumes."""
+        a = self.compact()
+        a._valid()
+        return a, a._off64, len(a._off64) - 1, a._first, a._last
+
+    # ------------------------------------------------------------------------------------------------------
+    # properties
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def starts(self):
+        return self._starts
+
+    @property
+    def stops(self):
+        return self._stops
+
+    @property
+    def content(self):
+        return self._content
+
+    @property
+    def offsets(self):
+        """jagged.py:352-365."""
+        self._valid()
+        if self._off64 is None:
+            raise ValueError("starts and stops are not compatible with a single offsets array")
+        if self._offsets is None:
+            self._offsets = self._off64.astype(self._starts.dtype) if self._starts.dtype != numpy.int64 else self._off64
+        return self._offsets
+
+    @property
+    def counts(self):
+        """jagged.py:383-388 -> jg_offsets2counts."""
+        if self._counts is None:
+            self._valid()
+            n = len(self._starts)
+            out = empty(n, INDEXTYPE)
+            if self._off64 is not None:
+                call("jg_offsets2counts", self._off64.data_ptr(), n, _vp(out), runtime.stream())
+            else:
+                s64, e64 = self._general
+                call("jg_startsstops2counts", s64.data_ptr(), e64.data_ptr(), n, _vp(out), runtime.stream())
+            counts = DeviceArray(out, INDEXTYPE)
+            if self._starts.dtype != numpy.int64:
+                counts = counts.astype(self._starts.dtype)
+            self._counts = counts
+        return self._counts
+
+    @property
+    def parents(self):
+        """jagged.py:408-416."""
+        if self._parents is None:
+            self._valid()
+            if self._off64 is not None:
+                self._parents = self._parents_from(self._off64, len(self._off64) - 1, self._last)
+            else:
+                self._parents = self.startsstops2parents(*self._general)
+        return self._parents
+
+    @property
+    def localindex(self):
+        """jagged.py:430-443 -> jg_localindex."""
+        a, off, n, first, last = self._dense()
+        out = empty(last - first, INDEXTYPE)
+        if last > first:
+            call("jg_localindex", off.data_ptr(), n, _vp(out), runtime.stream())
+        return self._make(a._rebased_offsets(), DeviceArray(out, INDEXTYPE), last - first)
+
+    def _rebased_offsets(self):
+        """offsets - offsets[0] (shared, not re-scanned, when offsets[0] == 0)."""
+        self._valid()
+        if self._first == 0:
+            return self._off64
+        if self._rebased is None:
+            self._rebased = _ufunc.binary(numpy.subtract, self._off64, numpy.int64(self._first))
+        return self._rebased
+
+    def _dense_content(self, content=None):
+        content = self._content if content is None else content
+        if self._first == 0 and self._last == len(content):
+            return content
+        return content[self._first:self._last]
+
+    def __len__(self):
+        return len(self._starts)
+
+    @property
+    def shape(self):
+        return (len(self._starts),)
+
+    @property
+    def ndim(self):
+        return 1
+
+    @property
+    def dtype(self):
+        return numpy.dtype(object)
+
+    @property
+    def type(self):
+        inner = self._content.type if isinstance(self._content, JaggedArray) else getattr(self._content, "dtype", "Table")
+        return "[0, {0}) -> [0, inf) -> {1}".format(len(self), inner)
+
+    @property
+    def nbytes(self):
+        head = self._off64.nbytes if self._off64 is not None else self._starts.nbytes + self._stops.nbytes
+        return head + self._content.nbytes
+
+    @property
+    def columns(self):
+        return self._content.columns if isinstance(self._content, Table) else []
+
+    def __getattr__(self, where):
+        if where.startswith("_"):
+            raise AttributeError(where)
+        content = self.__dict__.get("_content")
+        if isinstance(content, Table) and where in content:
+            return self[where]
+        raise AttributeError("no column named {0}".format(repr(where)))
+
+    @property
+    def i0(self):
+        return self["0"]
+
+    @property
+    def i1(self):
+        return self["1"]
+
+    @property
+    def i2(self):
+        return self["2"]
+
+    @property
+    def i3(self):
+        return self["3"]
+
+    @property
+    def i4(self):
+        return self["4"]
+
+    def unzip(self):
+        return tuple(self[n] for n in self.columns)
+
+    @classmethod
+    def zip(cls, columns1=None, *columns2, **columns3):
+        """Subset of jagged.py:1736-1849: jagged columns with identical counts -> one JaggedArray of records."""
+        table = OrderedDict()
+        if isinstance(columns1, dict):
+            table.update(columns1)
+            rowname = "Row"
+        elif columns1 is not None:
+            rowname = "tuple"
+            table["0"] = columns1
+            for i, x in enumerate(columns2):
+                table[str(i + 1)] = x
+        else:
+            rowname = "Row"
+        table.update(columns3)
+        first = None
+        for x in table.values():
+            if isinstance(x, JaggedArray):
+                first = x
+                break
+        if first is None:
+            raise TypeError("zip needs at least one JaggedArray")
+        a, off, n, _, last = first._dense()
+        contents = Table.named(rowname)
+        for name, x in table.items():
+            if isinstance(x, JaggedArray):
+                x = a._align(x)
+                contents[name] = x._dense_content()
+            else:
+                contents[name] = a.tojagged(x)._dense_content()
+        return cls._make(a._rebased_offsets(), contents, last - a._first)
+
+    # ------------------------------------------------------------------------------------------------------
+    # host conversions
+    # ------------------------------------------------------------------------------------------------------
+    def _checktonumpy(self):
+        if not self.allow_tonumpy:
+            raise RuntimeError("awkward0.array.base.AwkwardArray.allow_tonumpy is False; refusing to convert to Numpy")
+
+    def _host(self):
+        self._checktonumpy()
+        self._valid()
+        if self._off64 is not None:
+            off = self._off64.get()
+            starts, stops = off[:-1], off[1:]
+        else:
+            starts, stops = self._general[0].get(), self._general[1].get()
+        content = self._content
+        if isinstance(content, Table):
+            content = content._host_columns()
+        elif isinstance(content, JaggedArray):
+            content = content.tolist()
+        else:
+            content = content.get()
+        return starts, stops, content
+
+    def tolist(self):
+        """base.py:159-172."""
+        starts, stops, content = self._host()
+        istuple = isinstance(self._content, Table) and self._content.istuple
+
+        def rows(cols, a, b):
+            flat = OrderedDict()
+            for n, c in cols.items():
+                flat[n] = rows(c, a, b) if isinstance(c, dict) else c[a:b].tolist()
+            names = list(flat)
+            count = b - a
+            tup = istuple
+            return [tuple(flat[n][i] for n in names) if tup else dict((n, flat[n][i]) for n in names) for i in range(count)]
+
+        out = []
+        for a, b in zip(starts.tolist(), stops.tolist()):
+            if isinstance(content, dict):
+                out.append(rows(content, a, b))
+            elif isinstance(content, list):
+                out.append(content[a:b])
+            else:
+                out.append(content[a:b].tolist())
+        return out
+
+    def __iter__(self):
+        if not self.allow_iter:
+            raise RuntimeError("awkward0.array.base.AwkwardArray.allow_iter is False; refusing to iterate")
+        starts, stops, content = self._host()
+        if isinstance(content, dict):
+            raise NotImplementedError("iteration over Table content is not supported on the device")
+        for a, b in zip(starts.tolist(), stops.tolist()):
+            yield content[a:b]
+
+    def __array__(self, dtype=None, copy=None):
+        self._checktonumpy()
+        out = numpy.empty(len(self), dtype=object)
+        for i, x in enumerate(self):
+            out[i] = x
+        return out
+
+    def __str__(self):
+        n = len(self)
+        if n <= 6:
+            return "[{0}]".format(" ".join(str(x) for x in self.tolist()))
+        head, tail = self[:3].tolist(), self[n - 3:].tolist()
+        return "[{0} ... {1}]".format(" ".join(str(x) for x in head), " ".join(str(x) for x in tail))
+
+    def __repr__(self):
+        return "<JaggedArray {0} at 0x{1:012x}>".format(str(self), id(self))
+
+    def __bool__(self):
+        raise ValueError("The truth value of an array with more than one element is ambiguous. Use a.any() or a.all()")
+
+    # ------------------------------------------------------------------------------------------------------
+    # __getitem__
+    # ------------------------------------------------------------------------------------------------------
+    def __getitem__(self, where):
+        self._valid()
+        if isinstance(where, str):
+            if not isinstance(self._content, Table):
+                raise ValueError("no column named {0}".format(repr(where)))
+            out = self.copy()
+            out._content = self._content[where]
+            return out
+        if isinstance(where, tuple):
+            if len(where) == 0:
+                return self
+            if len(where) == 1:
+                where = where[0]
+            else:
+                raise NotImplementedError("multi-dimensional JaggedArray slicing is outside the GPU hot path (SURVEY.md section 8f-1)")
+
+        if isinstance(where, JaggedArray):
+            return self._getitem_jagged(where)
+
+        if isinstance(where, (int, numpy.integer)):
+            n = len(self)
+            i = int(where)
+            if i < 0:
+                i += n
+            if not 0 <= i < n:
+                raise IndexError("index {0} is out of bounds for axis 0 with size {1}".format(where, n))
+            if self._off64 is not None:
+                pair = self._off64[i:i + 2].get()
+                a, b = int(pair[0]), int(pair[1])
+            else:
+                a, b = int(self._general[0][i]), int(self._general[1][i])
+            return self._map_content(lambda c: c[a:b])
+
+        if isinstance(where, slice):
+            start, stop, step = where.indices(len(self))
+            if step != 1:
+                raise NotImplementedError("event slices with a step are outside the GPU hot path (SURVEY.md section 8f-1)")
+            stop = max(start, stop)
+            if self._off64 is not None:
+                sub = self._off64[start:stop + 1]
+                out = self.__class__.__new__(self.__class__)
+                out._reset()
+                out._content = self._content
+                out._offsets = out._off64 = sub
+                out._starts, out._stops = sub[:-1], sub[1:]
+                if start == 0 and stop == len(self):
+                    out._first, out._last = self._first, self._last
+                    out._isvalid = True
+                else:
+                    ends = numpy.concatenate([sub[:1].get(), sub[-1:].get()])
+                    out._first, out._last = int(ends[0]), int(ends[1])
+                    out._isvalid = True
+                return out
+            return JaggedArray(self._starts[start:stop], self._stops[start:stop], self._content)
+
+        raise NotImplementedError("event-level selection with flat boolean / integer arrays is outside the round-1 GPU hot path (SURVEY.md section 8f-1); no CPU fallback")
+
+    def _align(self, other):
+        """_tojagged(self.starts, self.stops) of jagged.py:573/971-973: `other` must have my counts."""
+        if len(other) != len(self):
+            raise ValueError("cannot fit contents of JaggedArray into the given starts and stops arrays")
+        b = other.compact()
+        b._valid()
+        a = self.compact()
+        a._valid()
+        if b._off64 is a._off64:
+            return b
+        if self.check_whole_valid:
+            scal = runtime.scalars()
+            call("jg_check_same_counts", a._off64.data_ptr(), b._off64.data_ptr(), len(a), _vp(scal, 1), runtime.stream())
+            _, status, _ = runtime.read(scal)
+            if status & _lib.ST_COUNTS_MISMATCH:
+                raise ValueError("cannot fit contents of JaggedArray into the given starts and stops arrays")
+        return b
+
+    def _getitem_jagged(self, head):
+        if isinstance(self._content, JaggedArray) and isinstance(head._content, JaggedArray):
+            return self.copy(content=self._content[head._content])
+        if not isinstance(head._content, DeviceArray):
+            raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
+        hdt = head._content.dtype
+        if _isintegertype(hdt):
+            return self._getitem_jagged_int(head)
+        if hdt == numpy.bool_:
+            return self._getitem_jagged_bool(head)
+        raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
+
+    def _getitem_jagged_bool(self, head):
+        """jagged.py:562-589 -> jg_mask_select (one pass: popcount, look-back scan, compaction)."""
+        a, off, n, first, last = self._dense()
+        head = a._align(head)
+        mask = head._content
+        mask_shift = head._first - first
+        new_offsets = empty(n + 1, INDEXTYPE)
+        scal = runtime.scalars()
+        ws, wsb = runtime.workspace(n)
+        columns = []
+
+        def select(col):
+            out = empty(last - first, col.dtype)
+            call("jg_mask_select", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
+                 _vp(out), _vp(new_offsets), _vp(scal), ws, wsb, runtime.stream())
+            columns.append(out)
+            return out
+
+        picked = a._map_content(select)
+        total, _, _ = runtime.read(scal)
+        content = a._map_content(lambda t: DeviceArray(t[:total], _TORCH_NP(t)), picked)
+        return self._make(DeviceArray(new_offsets, INDEXTYPE), content, total)
+
+    def _getitem_jagged_int(self, head):
+        """jagged.py:541-560 -> jg_index_gather."""
+        if len(head) != len(self):
+            raise ValueError("jagged array used as index has a different shape {0} from the jagged array it is selecting from {1}".format(head.shape, self.shape))
+        a, off, n, first, last = self._dense()
+        h, hoff, _, hfirst, hlast = head._dense()
+        index = h._content
+        if index.dtype not in (numpy.dtype(numpy.int64), numpy.dtype(numpy.int32)):
+            index = index.astype(numpy.int64)
+        scal = runtime.scalars()
+
+        def gather(col):
+            out = empty(hlast - hfirst, col.dtype)
+            if hlast > hfirst:
+                call("jg_index_gather", col.data_ptr(), col.itemsize, off.data_ptr(), index.data_ptr(),
+                     jg_code(index.dtype), hoff.data_ptr(), n, _vp(out), _vp(scal, 1), runtime.stream())
+            return DeviceArray(out, col.dtype)
+
+        content = a._map_content(gather)
+        _, status, _ = runtime.read(scal)
+        if status & _lib.ST_INDEX_OOB:
+            raise IndexError("jagged array used as index contains out-of-bounds values")
+        return self._make(h._rebased_offsets(), content, hlast - hfirst)
+
+    # ------------------------------------------------------------------------------------------------------
+    # broadcasting and ufuncs
+    # ------------------------------------------------------------------------------------------------------
+    def tojagged(self, data):
+        """jagged.py:840-881 -> jg_broadcast for flat[N]; scalars fill; jagged data must have the same counts."""
+        a, off, n, first, last = self._dense()
+        if isinstance(data, JaggedArray):
+            if len(data) != len(self):
+                raise ValueError("cannot broadcast JaggedArray to match JaggedArray with a different counts")
+            try:
+                b = a._align(data)
+            except ValueError:
+                raise ValueError("cannot broadcast JaggedArray to match JaggedArray with a different counts")
+            return self._make(a._rebased_offsets(), b._dense_content(), last - first)
+        if _ufunc.is_scalar(data) or (hasattr(data, "__len__") and len(data) == 1 and not isinstance(data, (str, bytes))):
+            value = numpy.asarray(data.get() if isinstance(data, DeviceArray) else data).reshape(-1)[0]
+            np_dtype = numpy.asarray(value).dtype
+            fill = torch.full((last - first,), value.item(), dtype=torch_dtype(np_dtype),
+                              device=runtime.device())
+            return self._make(a._rebased_offsets(), DeviceArray(fill, np_dtype), last - first)
+        flat = asdevice(data)
+        if len(flat) != n:
+            raise ValueError("cannot broadcast AwkwardArray to match JaggedArray with a different length")
+        out = empty(last - first, flat.dtype)
+        if last > first:
+            call("jg_broadcast", flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), runtime.stream())
+        return self._make(a._rebased_offsets(), DeviceArray(out, flat.dtype), last - first)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """jagged.py:944-1051."""
+        if "out" in kwargs:
+            raise NotImplementedError("in-place operations not supported")
+        if method != "__call__":
+            return NotImplemented
+        lead = None
+        for x in inputs:
+            if isinstance(x, JaggedArray):
+                lead = x
+        a, off, n, first, last = lead._dense()
+        if isinstance(a._content, (Table, JaggedArray)):
+            raise NotImplementedError("ufuncs on Table / nested content are outside the GPU hot path (no CPU fallback)")
+
+        operands, parent_side = [], None
+        for i, x in enumerate(inputs):
+            if isinstance(x, JaggedArray):
+                b = a._align(x) if x is not lead else a
+                if isinstance(b._content, (Table, JaggedArray)):
+                    raise NotImplementedError("ufuncs on Table / nested content are outside the GPU hot path")
+                operands.append(b._dense_content())
+            elif _ufunc.is_scalar(x):
+                operands.append(x)
+            else:
+                flat = asdevice(x) if not isinstance(x, DeviceArray) else x
+                if flat.shape != (n,):
+                    raise ValueError("cannot broadcast JaggedArray of shape {0} with array of shape {1}".format((n,), flat.shape))
+                if parent_side is not None:
+                    flat = a.tojagged(flat)._content      # a second flat operand: materialise its broadcast
+                else:
+                    parent_side = i
+                operands.append(flat)
+
+        if len(operands) == 1:
+            result = _ufunc.unary(ufunc, operands[0])
+        elif len(operands) == 2:
+            if parent_side is None:
+                result = _ufunc.binary(ufunc, operands[0], operands[1])
+            else:
+                other = operands[1 - parent_side]
+                if not isinstance(other, DeviceArray):
+                    # flat (op) scalar with no dense operand cannot happen: the jagged input is always dense
+                    raise TypeError("unexpected operand combination")
+                result = _ufunc.binary(ufunc, operands[0], operands[1], offsets=off, nevents=n, parent_side=parent_side)
+        else:
+            raise NotImplementedError("ufunc {0} with {1} operands is not implemented on the device".format(ufunc.__name__, len(operands)))
+        # fromcounts(stops - starts, result) (jagged.py:1045-1051): offsets rebased to zero, shared when possible
+        out = self._make(a._rebased_offsets(), result, last - first)
+        out._counts = a._counts
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # reducers (base.py:190-215 -> jagged.py:1459-1565)
+    # ------------------------------------------------------------------------------------------------------
+    def _reduce_out_dtype(self, op, dt):
+        if op in (_lib.ANY, _lib.ALL):
+            return BOOLTYPE
+        if op in (_lib.SUM, _lib.PROD):
+            if dt.kind == "b" or (dt.kind == "i" and dt.itemsize < 8):
+                return numpy.dtype(numpy.int64)
+            if dt.kind == "u" and dt.itemsize < 8:
+                return numpy.dtype(numpy.uint64)
+            return dt
+        if dt.kind == "b":
+            return numpy.dtype(numpy.float64)         # bool min/max take the identity's type (jagged.py:1530-1531)
+        return dt
+
+    def _reduce(self, op):
+        a, off, n, first, last = self._dense()
+        if isinstance(a._content, JaggedArray):
+            return self.copy(content=a._content._reduce(op))
+        if isinstance(a._content, Table):
+            out = Table.named(a._content.rowname)
+            for name in a._content.columns:
+                out[name] = a[name]._reduce(op)
+            return out
+        col = a._content
+        odt = self._reduce_out_dtype(op, col.dtype)
+        out = empty(n, odt)
+        if n > 0:
+            call("jg_segreduce", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out), len(col),
+                 runtime.stream())
+        return DeviceArray(out, odt)
+
+    def any(self):
+        return self._reduce(_lib.ANY)
+
+    def all(self):
+        return self._reduce(_lib.ALL)
+
+    def sum(self):
+        return self._reduce(_lib.SUM)
+
+    def prod(self):
+        return self._reduce(_lib.PROD)
+
+    def min(self):
+        return self._reduce(_lib.MIN)
+
+    def max(self):
+        return self._reduce(_lib.MAX)
+
+    def argmin(self):
+        return self._argminmax(True)
+
+    def argmax(self):
+        return self._argminmax(False)
+
+    def _argminmax(self, ismin, with_values=False):
+        """jagged.py:1581-1601 -> jg_segargminmax + jg_compact_nonneg (dense logical result)."""
+        a, off, n, first, last = self._dense()
+        if isinstance(a._content, JaggedArray):
+            return self.copy(content=a._content._argminmax(ismin))
+        if not isinstance(a._content, DeviceArray):
+            raise ValueError("cannot compute arg{0} because content is not one-dimensional".format("min" if ismin else "max"))
+        col = a._content
+        best = empty(n, INDEXTYPE)
+        out_offsets = empty(n + 1, INDEXTYPE)
+        out_index = empty(n, INDEXTYPE)
+        scal = runtime.scalars()
+        ws, wsb = runtime.workspace(n)
+        if n > 0:
+            call("jg_segargminmax", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0, _vp(best),
+                 ctypes.c_void_p(0), runtime.stream())
+        call("jg_compact_nonneg", _vp(best), n, _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
+        total, _, _ = runtime.read(scal)
+        return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
+
+    # ------------------------------------------------------------------------------------------------------
+    # flatten
+    # ------------------------------------------------------------------------------------------------------
+    def flatten(self, axis=0):
+        """jagged.py:1403-1429: dense layout -> a view of content (zero bytes moved)."""
+        if not isinstance(axis, (numbers.Integral, numpy.integer)) or axis < 0:
+            raise TypeError("axis must be a non-negative integer (can't count from the end)")
+        if axis != 0:
+            raise NotImplementedError("flatten(axis>0) needs jagged-of-jagged content, outside the GPU hot path")
+        if len(self) == 0:
+            return self._map_content(lambda c: c[0:0])
+        a, off, n, first, last = self._dense()
+        return a._map_content(lambda c: c[first:last])
+
+    # ------------------------------------------------------------------------------------------------------
+    # combinatorics (jagged.py:1070-1367)
+    # ------------------------------------------------------------------------------------------------------
+    def _comb_offsets(self, kind, k, off_a, off_b, n):
+        out_offsets = empty(n + 1, INDEXTYPE)
+        scal = runtime.scalars()
+        ws, wsb = runtime.workspace(n)
+        call("jg_comb_offsets", kind, k, off_a.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0),
+             n, _vp(out_offsets), _vp(scal), ws, wsb, runtime.stream())
+        total, _, _ = runtime.read(scal)
+        return DeviceArray(out_offsets, INDEXTYPE), total
+
+    def _comb_indices(self, kind, k, other=None, absolute=False):
+        a, off, n, first, last = self._dense()
+        off_b = None
+        if kind == _lib.COMB_CROSS:
+            b, off_b, nb, _, _ = other._dense()
+        poff, total = self._comb_offsets(kind, k, off, off_b, n)
+        ncols = k if kind == _lib.COMB_CHOOSE else 2
+        cols = [empty(total, INDEXTYPE) for _ in range(ncols)]
+        if total > 0:
+            arr = (ctypes.c_void_p * ncols)(*[c.data_ptr() for c in cols])
+            call("jg_comb_fill", kind, k, off.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0), n,
+                 poff.data_ptr(), arr, 1 if absolute else 0, runtime.stream())
+        table = Table.named("tuple", *[DeviceArray(c, INDEXTYPE) for c in cols])
+        return self._make(poff, table, total)
+
+    def _comb_values(self, kind, other=None):
+        a, off, n, first, last = self._dense()
+        if kind == _lib.COMB_CROSS:
+            b, off_b, nb, _, _ = other._dense()
+        else:
+            b, off_b = a, None
+        poff, total = self._comb_offsets(kind, 2, off, off_b, n)
+
+        def gather(col_a, col_b):
+            out_l, out_r = empty(total, col_a.dtype), empty(total, col_b.dtype)
+            if total > 0:
+                call("jg_comb_gather2", kind, off.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0),
+                     n, poff.data_ptr(), col_a.data_ptr(), col_a.itemsize, col_b.data_ptr(), col_b.itemsize,
+                     _vp(out_l), _vp(out_r), runtime.stream())
+            return DeviceArray(out_l, col_a.dtype), DeviceArray(out_r, col_b.dtype)
+
+        def both(col_a, col_b):
+            """(left tree, right tree) for one column (or Table of columns) of each side."""
+            if isinstance(col_a, JaggedArray) or isinstance(col_b, JaggedArray):
+                raise NotImplementedError("combinatorics over nested content are outside the GPU hot path")
+            if kind != _lib.COMB_CROSS:
+                if isinstance(col_a, Table):
+                    left, right = Table.named(col_a.rowname), Table.named(col_a.rowname)
+                    for name in col_a.columns:
+                        left._contents[name], right._contents[name] = both(col_a[name], col_a[name])
+                    return left, right
+                return gather(col_a, col_a)
+            leaves_a = list(_leaves(col_a))
+            leaves_b = list(_leaves(col_b))
+            m = max(len(leaves_a), len(leaves_b))
+            outs_a, outs_b = [], []
+            for i in range(m):
+                la = leaves_a[i] if i < len(leaves_a) else leaves_a[0]
+                lb = leaves_b[i] if i < len(leaves_b) else leaves_b[0]
+                l, r = gather(la, lb)
+                if i < len(leaves_a):
+                    outs_a.append(l)
+                if i < len(leaves_b):
+                    outs_b.append(r)
+            return _rebuild(col_a, iter(outs_a)), _rebuild(col_b, iter(outs_b))
+
+        left, right = both(a._content, b._content)
+        table = Table.named("tuple", left, right)
+        return self._make(poff, table, total)
+
+    def argpairs(self, nested=False):
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_indices(_lib.COMB_PAIRS, 2)
+
+    def pairs(self, nested=False):
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_values(_lib.COMB_PAIRS)
+
+    def argdistincts(self, nested=False):
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_indices(_lib.COMB_DISTINCTS, 2)
+
+    def distincts(self, nested=False):
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_values(_lib.COMB_DISTINCTS)
+
+    def argchoose(self, n):
+        """jagged.py:1223-1230: k-combinations in colexicographic order."""
+        if n > 5:
+            raise NotImplementedError
+        if n <= 1:
+            raise ValueError("Choosing 0 or 1 items is trivial")
+        return self._comb_indices(_lib.COMB_CHOOSE, int(n))
+
+    def choose(self, n):
+        """jagged.py:1232-1242."""
+        if n > 5:
+            raise NotImplementedError
+        if n <= 1:
+            raise ValueError("Choosing 0 or 1 items is trivial")
+        args = self._comb_indices(_lib.COMB_CHOOSE, int(n), absolute=True)
+        a = self.compact()
+        cols = [a._map_content(lambda c, idx=args._content[name]: _ufunc.take(c, idx)) for name in args._content.columns]
+        return self._make(args._off64, Table.named("tuple", *cols), args._last)
+
+    def _check_cross(self, other):
+        if not isinstance(other, JaggedArray):
+            raise TypeError("both arrays must be JaggedArrays")
+        if len(self) != len(other):
+            raise ValueError("both JaggedArrays must have the same length")
+
+    def argcross(self, other, nested=False):
+        self._valid()
+        self._check_cross(other)
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_indices(_lib.COMB_CROSS, 2, other=other)
+
+    def cross(self, other, nested=False):
+        self._valid()
+        self._check_cross(other)
+        if nested:
+            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
+        return self._comb_values(_lib.COMB_CROSS, other=other)
+
+    # ------------------------------------------------------------------------------------------------------
+    # outside the hot path: fail loudly (north_star: no CPU fallback)
+    # ------------------------------------------------------------------------------------------------------
+    def _notimpl(self, name):
+        raise NotImplementedError("JaggedArray.{0} is outside the GPU hot path (SURVEY.md section 8a/8f); no CPU fallback".format(name))
+
+    def __setitem__(self, where, what):
+        self._notimpl("__setitem__")
+
+    def regular(self):
+        self._notimpl("regular")
+
+    def argsort(self, ascending=False):
+        self._notimpl("argsort")
+
+    def pad(self, length, maskedwhen=True, clip=False, axis=0):
+        self._notimpl("pad")
+
+    def concatenate(self, arrays, axis=0):
+        self._notimpl("concatenate")
+
+
+def _rebuild(template, leaves):
+    if isinstance(template, Table):
+        out = Table.named(template.rowname)
+        for name in template.columns:
+            out._contents[name] = _rebuild(template[name], leaves)
+        return out
+    return next(leaves)
+
+
+def _leaves(content):
+    if isinstance(content, Table):
+        for name in content.columns:
+            for leaf in _leaves(content[name]):
+                yield leaf
+    else:
+        yield content
+
+
+def _TORCH_NP(t):
+    from .device import _TORCH2NP
+    return _TORCH2NP[t.dtype]

@@ -1,0 +1,131 @@
+"""A thin device Table: an ordered set of equal-length columns.
+
+Only what the JaggedArray hot path needs from the reference's awkward0/array/table.py: the result container of
+pairs/cross/distincts/choose (``Table.named("tuple", left, right)``, table.py:246-250), column access by name
+(table.py:587-600), ``flattentuple`` (table.py:791-820) and the record content produced by ``JaggedArray.zip``.
+Row objects, views and recarray I/O are host-side conveniences of the reference and are out of scope.
+"""
+from collections import OrderedDict
+
+from .device import DeviceArray, asdevice
+
+
+class Table(object):
+    def __init__(self, columns1=None, *columns2, **columns3):
+        self._contents = OrderedDict()
+        self.rowname = "Row"
+        seed = []
+        if isinstance(columns1, dict):
+            seed.extend(columns1.items())
+        elif columns1 is not None:
+            seed.append(("0", columns1))
+            for i, x in enumerate(columns2):
+                seed.append((str(i + 1), x))
+        seed.extend(columns3.items())
+        for n, x in seed:
+            self[n] = x
+
+    @classmethod
+    def named(cls, rowname, columns1=None, *columns2, **columns3):
+        out = cls(columns1, *columns2, **columns3)
+        out.rowname = rowname
+        return out
+
+    @property
+    def istuple(self):
+        return self.rowname == "tuple"
+
+    @property
+    def columns(self):
+        return list(self._contents)
+
+    def __len__(self):
+        for x in self._contents.values():
+            return len(x)
+        return 0
+
+    def __setitem__(self, where, what):
+        if not isinstance(where, str):
+            raise TypeError("Table columns are set by name")
+        if not isinstance(what, (DeviceArray, Table)) and type(what).__name__ != "JaggedArray":
+            what = asdevice(what)
+        if len(self._contents) != 0 and len(what) != len(self):
+            raise ValueError("column {0} has length {1}, table has length {2}".format(where, len(what), len(self)))
+        self._contents[where] = what
+
+    def __getitem__(self, where):
+        if isinstance(where, str):
+            try:
+                return self._contents[where]
+            except KeyError:
+                raise ValueError("no column named {0}".format(repr(where)))
+        if isinstance(where, slice):
+            out = Table.named(self.rowname)
+            for n, x in self._contents.items():
+                out._contents[n] = x[where]
+            return out
+        raise NotImplementedError("device Table supports column (str) and slice indexing only")
+
+    def __contains__(self, name):
+        return name in self._contents
+
+    def map(self, fcn):
+        """A new Table with fcn applied to every (leaf) column."""
+        out = Table.named(self.rowname)
+        for n, x in self._contents.items():
+            out._contents[n] = x.map(fcn) if isinstance(x, Table) else fcn(x)
+        return out
+
+    def flattentuple(self):
+        """table.py:791-820 -- splice nested tuple Tables into one tuple."""
+        if not self.istuple:
+            return self
+        flat = []
+        for x in self._contents.values():
+            if isinstance(x, Table) and x.istuple and getattr(x, "_splice", False):
+                flat.extend(x.flattentuple()._contents.values())
+            else:
+                flat.append(x)
+        out = Table.named("tuple")
+        for i, x in enumerate(flat):
+            out._contents[str(i)] = x
+        return out
+
+    @property
+    def i0(self):
+        return self["0"]
+
+    @property
+    def i1(self):
+        return self["1"]
+
+    @property
+    def i2(self):
+        return self["2"]
+
+    @property
+    def i3(self):
+        return self["3"]
+
+    @property
+    def i4(self):
+        return self["4"]
+
+    def __getattr__(self, name):
+        contents = self.__dict__.get("_contents")
+        if contents is not None and name in contents:
+            return contents[name]
+        raise AttributeError("no column named {0}".format(repr(name)))
+
+    def unzip(self):
+        return tuple(self._contents.values())
+
+    def _host_columns(self):
+        out = OrderedDict()
+        for n, x in self._contents.items():
+            out[n] = x._host_columns() if isinstance(x, Table) else x.get()
+        return out
+
+    @property
+    def nbytes(self):
+        return sum(x.nbytes for x in self._contents.values())

@@ -1,0 +1,247 @@
+// jg_comb.cu -- per-event combinatorics: pairs (i<=j), distincts (i<j), choose (k = 2..5, colexicographic) and
+// cross (rectangular) index generation, jagged.py:1070-1126, 1128-1221, 1302-1325.
+//
+// Phase 1 (jg_comb_offsets): per-event output count computed on the fly inside the look-back scan -> new offsets
+// and the grand total P.  Phase 2 (jg_comb_fill / jg_comb_gather2): one CTA per event tile; the output run of the
+// tile is walked element-parallel (coalesced 8-byte stores per column), each output finds its event by binary
+// search in the tile's on-chip output offsets and inverts the triangular / rectangular / combinatorial numbering
+// with integer-exact arithmetic (a floating-point estimate corrected by integer comparisons; the reference's
+// float64 closed forms are exact only up to n ~ 6000 for pairs, "1000 choose 3", "100 choose 4").
+//
+// Algorithmic traffic: 8(N+1) [x2 for cross] read, 8(N+1) + k*8*P written.
+#include "jg_scan.cuh"
+#include "jg_tile.cuh"
+
+namespace jg {
+
+// (i, j) of the k-th pair with i <= j in an event of n items; rows are i, row i holds n - i entries
+__device__ __forceinline__ void unrank_pairs(int64_t k, int64_t n, int64_t &i, int64_t &j) {
+    const double b = 2.0 * static_cast<double>(n) + 1.0;
+    int64_t r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    if (r < 0) r = 0;
+    if (r > n - 1) r = n - 1;
+    // L(r) = r*n - r(r-1)/2 = first index of row r
+    while (r + 1 < n && (r + 1) * n - ((r + 1) * r >> 1) <= k) ++r;
+    while (r > 0 && r * n - (r * (r - 1) >> 1) > k) --r;
+    i = r;
+    j = r + (k - (r * n - (r * (r - 1) >> 1)));
+}
+
+// (i, j) of the k-th pair with i < j; row i holds n - 1 - i entries
+__device__ __forceinline__ void unrank_distincts(int64_t k, int64_t n, int64_t &i, int64_t &j) {
+    const double b = 2.0 * static_cast<double>(n) - 1.0;
+    int64_t r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    if (r < 0) r = 0;
+    if (r > n - 2) r = n - 2;
+    // L(r) = r*(n-1) - r(r-1)/2
+    while (r + 1 < n - 1 && (r + 1) * (n - 1) - ((r + 1) * r >> 1) <= k) ++r;
+    while (r > 0 && r * (n - 1) - (r * (r - 1) >> 1) > k) --r;
+    i = r;
+    j = r + 1 + (k - (r * (n - 1) - (r * (r - 1) >> 1)));
+}
+
+__device__ __forceinline__ int64_t binom(int64_t c, int k) {
+    if (c < k) return 0;
+    switch (k) {
+        case 1: return c;
+        case 2: return c * (c - 1) / 2;
+        case 3: return c * (c - 1) * (c - 2) / 6;
+        case 4: return c * (c - 1) * (c - 2) * (c - 3) / 24;
+        default: return c * (c - 1) * (c - 2) * (c - 3) * (c - 4) / 120;
+    }
+}
+
+// combinatorial number system (colex order): largest c with C(c, k) <= m
+__device__ __forceinline__ int64_t largest_binom_le(int64_t m, int k, int64_t n) {
+    double est;
+    const double dm = static_cast<double>(m);
+    switch (k) {
+        case 2: est = 0.5 * (1.0 + sqrt(8.0 * dm + 1.0)); break;
+        case 3: est = cbrt(6.0 * dm) + 1.0; break;
+        case 4: est = sqrt(sqrt(24.0 * dm)) + 1.5; break;
+        default: est = pow(120.0 * dm, 0.2) + 2.0; break;
+    }
+    int64_t c = static_cast<int64_t>(est);
+    if (c < k - 1) c = k - 1;
+    if (c > n - 1) c = n - 1;
+    while (c + 1 <= n - 1 && binom(c + 1, k) <= m) ++c;
+    while (c > k - 1 && binom(c, k) > m) --c;
+    return c;
+}
+
+struct CombIndex {
+    int64_t v[5];
+};
+
+template <int KIND>
+__device__ __forceinline__ CombIndex unrank(int64_t m, int64_t na, int64_t nb, int k) {
+    CombIndex r;
+    if constexpr (KIND == JG_COMB_PAIRS) {
+        unrank_pairs(m, na, r.v[0], r.v[1]);
+    } else if constexpr (KIND == JG_COMB_DISTINCTS) {
+        unrank_distincts(m, na, r.v[0], r.v[1]);
+    } else if constexpr (KIND == JG_COMB_CROSS) {
+        r.v[0] = m / nb;
+        r.v[1] = m - r.v[0] * nb;
+    } else {
+        // columns are i1 < i2 < ... < ik; the largest index is found first
+        for (int q = k; q >= 2; --q) {
+            const int64_t c = largest_binom_le(m, q, na);
+            r.v[q - 1] = c;
+            m -= binom(c, q);
+        }
+        r.v[0] = m;
+    }
+    return r;
+}
+
+struct ColPtrs {
+    int64_t *p[5];
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kTileThreads)
+comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                 const int64_t *__restrict__ out_offsets, ColPtrs cols, int k, int absolute) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[kTileEvents + 1];
+    EventTile pt, ta, tb;
+    pt.load(s_po, out_offsets, n, blockIdx.x);
+    ta.load(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    const int ncols = (KIND == JG_COMB_CHOOSE) ? k : 2;
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
+        const int ev = pt.find_event(p);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, k);
+        const int64_t base_a = absolute ? s_oa[ev] : 0;
+        const int64_t base_b = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) : 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            if (c < ncols) __stcs(cols.p[c] + p, r.v[c] + ((c == 1 && KIND == JG_COMB_CROSS) ? base_b : base_a));
+        }
+    }
+}
+
+// fused value form: out_l[p] = content_a[start_a + i], out_r[p] = content_b[start_b + j]
+template <int KIND, typename VA, typename VB>
+__global__ void __launch_bounds__(kTileThreads)
+comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                    const int64_t *__restrict__ out_offsets, const VA *__restrict__ content_a,
+                    const VB *__restrict__ content_b, VA *__restrict__ out_l, VB *__restrict__ out_r) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[kTileEvents + 1];
+    EventTile pt, ta, tb;
+    pt.load(s_po, out_offsets, n, blockIdx.x);
+    ta.load(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
+        const int ev = pt.find_event(p);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
+        const int64_t sb = (KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev];
+        __stcs(out_l + p, __ldg(content_a + s_oa[ev] + r.v[0]));
+        __stcs(out_r + p, __ldg(content_b + sb + r.v[1]));
+    }
+}
+
+template <int KIND, typename VA>
+static int gather2_b(int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const void *ca,
+                     const void *cb, void *l, void *r, cudaStream_t s) {
+    const unsigned g = tile_grid(n);
+#define JG_G2(VB)                                                                                                   \
+    comb_gather2_kernel<KIND, VA, VB><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, static_cast<const VA *>(ca),         \
+                                                                 static_cast<const VB *>(cb), static_cast<VA *>(l),  \
+                                                                 static_cast<VB *>(r))
+    switch (itemsize_b) {
+        case 1: JG_G2(uint8_t); break;
+        case 2: JG_G2(uint16_t); break;
+        case 4: JG_G2(uint32_t); break;
+        case 8: JG_G2(uint64_t); break;
+        default: set_error("jg_comb_gather2: unsupported itemsize %d", itemsize_b); return -2;
+    }
+#undef JG_G2
+    return check_launch("comb_gather2_kernel");
+}
+
+template <int KIND>
+static int gather2_a(int itemsize_a, int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                     const void *ca, const void *cb, void *l, void *r, cudaStream_t s) {
+    switch (itemsize_a) {
+        case 1: return gather2_b<KIND, uint8_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 2: return gather2_b<KIND, uint16_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 4: return gather2_b<KIND, uint32_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 8: return gather2_b<KIND, uint64_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+    }
+    set_error("jg_comb_gather2: unsupported itemsize %d", itemsize_a);
+    return -2;
+}
+
+}  // namespace jg
+
+using namespace jg;
+
+extern "C" {
+
+int jg_comb_offsets(int kind, int k, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                    int64_t *out_offsets, int64_t *total, void *ws, size_t ws_bytes, void *stream) {
+    JG_REQUIRE(kind >= JG_COMB_PAIRS && kind <= JG_COMB_CROSS, "jg_comb_offsets: bad kind %d", kind);
+    JG_REQUIRE(kind != JG_COMB_CHOOSE || (k >= 2 && k <= 5), "jg_comb_offsets: choose needs 2 <= k <= 5");
+    JG_REQUIRE(kind != JG_COMB_CROSS || offsets_b != nullptr, "jg_comb_offsets: cross needs offsets_b");
+    ScanInComb in{offsets_a, kind == JG_COMB_CROSS ? offsets_b : nullptr, kind, k};
+    return launch_scan(in, n, out_offsets, total, nullptr, ws, ws_bytes, as_stream(stream));
+}
+
+int jg_comb_fill(int kind, int k, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                 const int64_t *out_offsets, int64_t *const *cols, int absolute, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const int ncols = kind == JG_COMB_CHOOSE ? k : 2;
+    JG_REQUIRE(ncols >= 2 && ncols <= 5, "jg_comb_fill: bad column count %d", ncols);
+    ColPtrs cp{};
+    for (int c = 0; c < ncols; ++c) cp.p[c] = cols[c];
+    const unsigned g = tile_grid(n);
+    switch (kind) {
+        case JG_COMB_PAIRS:
+            comb_fill_kernel<JG_COMB_PAIRS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
+            break;
+        case JG_COMB_DISTINCTS:
+            comb_fill_kernel<JG_COMB_DISTINCTS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
+            break;
+        case JG_COMB_CHOOSE:
+            comb_fill_kernel<JG_COMB_CHOOSE><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
+            break;
+        case JG_COMB_CROSS:
+            comb_fill_kernel<JG_COMB_CROSS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
+            break;
+        default:
+            set_error("jg_comb_fill: bad kind %d", kind);
+            return -2;
+    }
+    return check_launch("comb_fill_kernel");
+}
+
+int jg_comb_gather2(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, const int64_t *out_offsets,
+                    const void *content_a, int itemsize_a, const void *content_b, int itemsize_b, void *out_l,
+                    void *out_r, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    switch (kind) {
+        case JG_COMB_PAIRS:
+            return gather2_a<JG_COMB_PAIRS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+        case JG_COMB_DISTINCTS:
+            return gather2_a<JG_COMB_DISTINCTS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+        case JG_COMB_CROSS:
+            return gather2_a<JG_COMB_CROSS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+    }
+    set_error("jg_comb_gather2: bad kind %d", kind);
+    return -2;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// jg_offsets.cu -- offsets / counts / parents / localindex machinery (jagged.py:42-71, 352-443, 469-502).
+#include "jg_scan.cuh"
+#include "jg_tile.cuh"
+
+namespace jg {
+
+// ------------------------------------------------------------------------------------------------------------
+// counts = offsets[1:] - offsets[:-1]           (jagged.py:383-388)   traffic 8(n+1) + 8n
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+offsets2counts_kernel(const int64_t *__restrict__ offsets, int64_t n, int64_t *__restrict__ counts, bool aligned) {
+    // each thread produces two consecutive counts from three consecutive offsets
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 2;
+    for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            int64_t a, b, c;
+            if (aligned) {
+                longlong2 v = __ldg(reinterpret_cast<const longlong2 *>(offsets + i));
+                a = v.x;
+                b = v.y;
+            } else {
+                a = offsets[i];
+                b = offsets[i + 1];
+            }
+            c = __ldg(offsets + i + 2);
+            if (aligned) {
+                __stcs(reinterpret_cast<longlong2 *>(counts + i), make_longlong2(b - a, c - b));
+            } else {
+                counts[i] = b - a;
+                counts[i + 1] = c - b;
+            }
+        } else {
+            counts[i] = offsets[i + 1] - offsets[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+startsstops2counts_kernel(const int64_t *__restrict__ starts, const int64_t *__restrict__ stops, int64_t n,
+                          int64_t *__restrict__ counts) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        counts[i] = stops[i] - starts[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// _valid()   (jagged.py:120-127, 469-477)     traffic 8(n+1)
+// info = {offsets[0], offsets[n], max count, #non-empty}
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+validate_offsets_kernel(const int64_t *__restrict__ offsets, int64_t n, int64_t content_len,
+                        int64_t *__restrict__ info, int32_t *__restrict__ status) {
+    int32_t st = 0;
+    int64_t maxcount = 0, nonempty = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const int64_t a = offsets[i];
+        if (a < 0) st |= JG_ST_NEGATIVE_OFFSET;
+        if (a > content_len) st |= JG_ST_BEYOND_CONTENT;
+        if (i < n) {
+            const int64_t c = offsets[i + 1] - a;
+            if (c < 0) st |= JG_ST_NONMONOTONE;
+            maxcount = max(maxcount, c);
+            nonempty += (c > 0);
+        }
+    }
+    // block reduce
+    __shared__ int64_t s_max[8], s_cnt[8];
+    __shared__ int32_t s_st[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        maxcount = max(maxcount, __shfl_xor_sync(0xffffffffu, maxcount, d));
+        nonempty += __shfl_xor_sync(0xffffffffu, nonempty, d);
+        st |= __shfl_xor_sync(0xffffffffu, st, d);
+    }
+    if (lane == 0) {
+        s_max[warp] = maxcount;
+        s_cnt[warp] = nonempty;
+        s_st[warp] = st;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            maxcount = max(maxcount, s_max[w]);
+            nonempty += s_cnt[w];
+            st |= s_st[w];
+        }
+        if (st) atomicOr(status, st);
+        atomicMax(reinterpret_cast<long long *>(info + 2), static_cast<long long>(maxcount));
+        atomicAdd(reinterpret_cast<unsigned long long *>(info + 3), static_cast<unsigned long long>(nonempty));
+        if (blockIdx.x == 0) {
+            info[0] = offsets[0];
+            info[1] = offsets[n];
+        }
+    }
+}
+
+// info = {min start over non-empty (or 0), max stop over non-empty (or 0), max count, #non-empty}
+__global__ void __launch_bounds__(256)
+validate_startsstops_kernel(const int64_t *__restrict__ starts, const int64_t *__restrict__ stops, int64_t n,
+                            int64_t content_len, int64_t *__restrict__ info, int32_t *__restrict__ status) {
+    int32_t st = 0;
+    int64_t maxcount = 0, nonempty = 0, minstart = INT64_MAX, maxstop = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t a = starts[i], b = stops[i];
+        if (a < 0 || b < 0) st |= JG_ST_NEGATIVE_OFFSET;
+        if (b < a) st |= JG_ST_STOPS_LT_STARTS;
+        if (b != a) {
+            if (a >= content_len || b > content_len) st |= JG_ST_BEYOND_CONTENT;
+            minstart = min(minstart, a);
+            maxstop = max(maxstop, b);
+            nonempty += 1;
+            maxcount = max(maxcount, b - a);
+        }
+        if (i + 1 < n && starts[i + 1] != b) st |= JG_ST_NOT_OFFSETS;
+    }
+    if (st) atomicOr(status, st);
+    if (nonempty) {
+        atomicMin(reinterpret_cast<long long *>(info + 0), static_cast<long long>(minstart));
+        atomicMax(reinterpret_cast<long long *>(info + 1), static_cast<long long>(maxstop));
+        atomicMax(reinterpret_cast<long long *>(info + 2), static_cast<long long>(maxcount));
+        atomicAdd(reinterpret_cast<unsigned long long *>(info + 3), static_cast<unsigned long long>(nonempty));
+    }
+}
+
+__global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-element expansion kernels built on the event tile (jg_tile.cuh):
+//   parents[j] = i, localindex[j - o0] = j - offsets[i], broadcast out[j - o0] = flat[i]
+// ------------------------------------------------------------------------------------------------------------
+enum { EXPAND_PARENTS = 0, EXPAND_LOCALINDEX = 1, EXPAND_BROADCAST = 2 };
+
+template <int MODE, typename V>
+__global__ void __launch_bounds__(kTileThreads)
+expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out, const V *__restrict__ flat) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    EventTile tile;
+    tile.load(s_off, offsets, n, blockIdx.x);
+    const int64_t o0 = __ldg(offsets);
+    if (MODE == EXPAND_PARENTS && blockIdx.x == 0) {
+        // content below offsets[0] is unreachable: -1 (jagged.py:52-54)
+        for (int64_t j = threadIdx.x; j < o0; j += kTileThreads) out[j] = static_cast<V>(-1);
+    }
+    // element-parallel: every thread finds the event of its element by binary search in the tile's offsets
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
+        const int ev = tile.find_event(j);
+        if (MODE == EXPAND_PARENTS) {
+            out[j] = static_cast<V>(tile.event0 + ev);
+        } else if (MODE == EXPAND_LOCALINDEX) {
+            out[j - o0] = static_cast<V>(j - tile.off[ev]);
+        } else {
+            out[j - o0] = flat[tile.event0 + ev];
+        }
+    }
+}
+
+// general layout (jagged.py:56-71): out pre-filled with -1
+__global__ void __launch_bounds__(256)
+startsstops2parents_kernel(const int64_t *__restrict__ starts, const int64_t *__restrict__ stops, int64_t n,
+                           int64_t *__restrict__ out, int64_t out_len) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t b = min(stops[i], out_len);
+        for (int64_t j = starts[i]; j < b; ++j) out[j] = i;
+    }
+}
+
+// compact(): out[dense[i] + k] = content[starts[i] + k]   (jagged.py:883-942)
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+compact_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__ starts,
+                      const int64_t *__restrict__ dense, int64_t n, V *__restrict__ out) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    EventTile tile;
+    tile.load(s_off, dense, n, blockIdx.x);
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
+        const int ev = tile.find_event(j);
+        out[j] = content[starts[tile.event0 + ev] + (j - tile.off[ev])];
+    }
+}
+
+static inline int grid_for(int64_t work, int threads, int per_thread = 1) {
+    int64_t blocks = ceil_div(work, static_cast<int64_t>(threads) * per_thread);
+    int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace jg
+
+using namespace jg;
+
+extern "C" {
+
+int jg_counts2offsets(const void *counts, int counts_dtype, int64_t n, int64_t *offsets, int64_t *total,
+                      int32_t *status, void *ws, size_t ws_bytes, void *stream) {
+    JG_REQUIRE(n >= 0 && offsets != nullptr, "jg_counts2offsets: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(counts);
+    switch (counts_dtype) {
+        case JG_I64: {
+            ScanInArray<int64_t> in{static_cast<const int64_t *>(counts), (addr & 15) == 0};
+            return launch_scan(in, n, offsets, total, status, ws, ws_bytes, s);
+        }
+        case JG_I32: {
+            ScanInArray<int32_t> in{static_cast<const int32_t *>(counts), (addr & 7) == 0};
+            return launch_scan(in, n, offsets, total, status, ws, ws_bytes, s);
+        }
+        case JG_U8:
+        case JG_B8: {
+            ScanInArray<uint8_t> in{static_cast<const uint8_t *>(counts), false};
+            return launch_scan(in, n, offsets, total, status, ws, ws_bytes, s);
+        }
+    }
+    set_error("jg_counts2offsets: unsupported counts dtype %d", counts_dtype);
+    return -2;
+}
+
+int jg_offsets2counts(const int64_t *offsets, int64_t n, int64_t *counts, void *stream) {
+    if (n <= 0) return 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(offsets) | reinterpret_cast<uintptr_t>(counts)) & 15) == 0;
+    offsets2counts_kernel<<<grid_for(n, 256, 2), 256, 0, as_stream(stream)>>>(offsets, n, counts, aligned);
+    return check_launch("offsets2counts_kernel");
+}
+
+int jg_startsstops2counts(const int64_t *starts, const int64_t *stops, int64_t n, int64_t *counts, void *stream) {
+    if (n <= 0) return 0;
+    startsstops2counts_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(starts, stops, n, counts);
+    return check_launch("startsstops2counts_kernel");
+}
+
+int jg_validate_offsets(const int64_t *offsets, int64_t n, int64_t content_len, int64_t *info, int32_t *status,
+                        void *stream) {
+    JG_REQUIRE(n >= 0 && info && status, "jg_validate_offsets: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    cudaMemsetAsync(info, 0, 4 * sizeof(int64_t), s);
+    validate_offsets_kernel<<<grid_for(n + 1, 256, 4), 256, 0, s>>>(offsets, n, content_len, info, status);
+    return check_launch("validate_offsets_kernel");
+}
+
+int jg_validate_startsstops(const int64_t *starts, const int64_t *stops, int64_t n, int64_t content_len,
+                            int64_t *info, int32_t *status, void *stream) {
+    JG_REQUIRE(n >= 0 && info && status, "jg_validate_startsstops: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    fill_i64_kernel<<<1, 32, 0, s>>>(info, 1, INT64_MAX);
+    cudaMemsetAsync(info + 1, 0, 3 * sizeof(int64_t), s);
+    if (n > 0)
+        validate_startsstops_kernel<<<grid_for(n, 256, 2), 256, 0, s>>>(starts, stops, n, content_len, info, status);
+    return check_launch("validate_startsstops_kernel");
+}
+
+int jg_offsets2parents(const int64_t *offsets, int64_t n, int64_t *parents, void *stream) {
+    if (n <= 0) return 0;
+    expand_kernel<EXPAND_PARENTS, int64_t>
+        <<<tile_grid(n), kTileThreads, 0, as_stream(stream)>>>(offsets, n, parents, nullptr);
+    return check_launch("expand_kernel<parents>");
+}
+
+int jg_localindex(const int64_t *offsets, int64_t n, int64_t *out, void *stream) {
+    if (n <= 0) return 0;
+    expand_kernel<EXPAND_LOCALINDEX, int64_t>
+        <<<tile_grid(n), kTileThreads, 0, as_stream(stream)>>>(offsets, n, out, nullptr);
+    return check_launch("expand_kernel<localindex>");
+}
+
+int jg_startsstops2parents(const int64_t *starts, const int64_t *stops, int64_t n, int64_t *out, int64_t out_len,
+                           void *stream) {
+    cudaStream_t s = as_stream(stream);
+    if (out_len > 0) fill_i64_kernel<<<grid_for(out_len, 256), 256, 0, s>>>(out, out_len, -1);
+    if (n > 0) startsstops2parents_kernel<<<grid_for(n, 256), 256, 0, s>>>(starts, stops, n, out, out_len);
+    return check_launch("startsstops2parents_kernel");
+}
+
+int jg_compact_gather(const void *content, int itemsize, const int64_t *starts, const int64_t *dense_offsets,
+                      int64_t n, void *out, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1:
+            compact_gather_kernel<uint8_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), starts,
+                                                                     dense_offsets, n, static_cast<uint8_t *>(out));
+            break;
+        case 2:
+            compact_gather_kernel<uint16_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), starts,
+                                                                      dense_offsets, n, static_cast<uint16_t *>(out));
+            break;
+        case 4:
+            compact_gather_kernel<uint32_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), starts,
+                                                                      dense_offsets, n, static_cast<uint32_t *>(out));
+            break;
+        case 8:
+            compact_gather_kernel<uint64_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), starts,
+                                                                      dense_offsets, n, static_cast<uint64_t *>(out));
+            break;
+        default:
+            set_error("jg_compact_gather: unsupported itemsize %d", itemsize);
+            return -2;
+    }
+    return check_launch("compact_gather_kernel");
+}
+
+int jg_broadcast(const void *flat, int itemsize, const int64_t *offsets, int64_t n, void *out, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1:
+            expand_kernel<EXPAND_BROADCAST, uint8_t>
+                <<<g, kTileThreads, 0, s>>>(offsets, n, static_cast<uint8_t *>(out), static_cast<const uint8_t *>(flat));
+            break;
+        case 2:
+            expand_kernel<EXPAND_BROADCAST, uint16_t><<<g, kTileThreads, 0, s>>>(
+                offsets, n, static_cast<uint16_t *>(out), static_cast<const uint16_t *>(flat));
+            break;
+        case 4:
+            expand_kernel<EXPAND_BROADCAST, uint32_t><<<g, kTileThreads, 0, s>>>(
+                offsets, n, static_cast<uint32_t *>(out), static_cast<const uint32_t *>(flat));
+            break;
+        case 8:
+            expand_kernel<EXPAND_BROADCAST, uint64_t><<<g, kTileThreads, 0, s>>>(
+                offsets, n, static_cast<uint64_t *>(out), static_cast<const uint64_t *>(flat));
+            break;
+        default:
+            set_error("jg_broadcast: unsupported itemsize %d", itemsize);
+            return -2;
+    }
+    return check_launch("expand_kernel<broadcast>");
+}
+
+}  // extern "C"

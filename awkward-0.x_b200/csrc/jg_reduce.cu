@@ -1,0 +1,413 @@
+// jg_reduce.cu -- segmented reductions: the replacement for numpy ufunc.reduceat (jagged.py:1552-1563)
+// behind JaggedArray.sum/prod/min/max/any/all (base.py:193-215) and argmin/argmax (jagged.py:1567-1601).
+//
+// One CTA owns an event tile (512 events, jg_tile.cuh).  Per CTA, chosen on the device from the tile's own
+// element count (no host synchronisation, so the choice follows the count distribution tile by tile):
+//   * SHORT events (tile content fits the shared-memory stage): the content run of the whole tile is staged
+//     with one TMA bulk copy (UBLKCP) and each thread reduces whole events sequentially out of shared memory
+//     -- left to right, exactly the reference's order, so min/max/argmax ties and -0.0 behave identically;
+//   * LONG events (tile content exceeds the stage): warp-per-event -- the 32 lanes stride the event with
+//     coalesced loads and combine with shuffles (events >= kBlockEventMin elements are reduced by the whole
+//     CTA instead: block-per-event).
+// Semantics: NaN -> identity, empty -> identity, first-occurrence argmax,
+// "later element wins" on equal min/max (numpy's minimum/maximum loops), sum of a lone -0.0 stays -0.0.
+//
+// Algorithmic traffic: v*M + 8(N+1) read, v_out*N written.
+#include <math_constants.h>
+
+#include "jg_tile.cuh"
+
+namespace jg {
+
+template <typename T> struct IsFloat { static constexpr bool value = false; };
+template <> struct IsFloat<float> { static constexpr bool value = true; };
+template <> struct IsFloat<double> { static constexpr bool value = true; };
+
+template <typename T>
+__device__ __forceinline__ bool is_nan(T x) {
+    if constexpr (IsFloat<T>::value) return x != x;
+    else return false;
+}
+
+template <typename A> __device__ __forceinline__ A max_identity();
+template <> __device__ __forceinline__ float max_identity<float>() { return -CUDART_INF_F; }
+template <> __device__ __forceinline__ double max_identity<double>() { return -CUDART_INF; }
+template <> __device__ __forceinline__ int32_t max_identity<int32_t>() { return INT32_MIN; }
+template <> __device__ __forceinline__ int64_t max_identity<int64_t>() { return INT64_MIN; }
+template <> __device__ __forceinline__ uint8_t max_identity<uint8_t>() { return 0; }
+template <typename A> __device__ __forceinline__ A min_identity();
+template <> __device__ __forceinline__ float min_identity<float>() { return CUDART_INF_F; }
+template <> __device__ __forceinline__ double min_identity<double>() { return CUDART_INF; }
+template <> __device__ __forceinline__ int32_t min_identity<int32_t>() { return INT32_MAX; }
+template <> __device__ __forceinline__ int64_t min_identity<int64_t>() { return INT64_MAX; }
+template <> __device__ __forceinline__ uint8_t min_identity<uint8_t>() { return 255; }
+
+// Reduction functor: A = accumulator/output type, T = content type.
+template <int OP, typename T, typename A>
+struct Red {
+    __device__ static __forceinline__ A identity() {
+        if constexpr (OP == JG_SUM) return A(0);
+        else if constexpr (OP == JG_PROD) return A(1);
+        else if constexpr (OP == JG_MIN) return min_identity<A>();
+        else if constexpr (OP == JG_MAX) return max_identity<A>();
+        else if constexpr (OP == JG_ANY) return A(0);
+        else return A(1);
+    }
+    // content value -> accumulator domain (NaN -> identity, jagged.py:1524-1528; any/all: astype(bool))
+    __device__ static __forceinline__ A lift(T x) {
+        if (is_nan(x)) return identity();
+        if constexpr (OP == JG_ANY || OP == JG_ALL) return A(x != T(0));
+        else return static_cast<A>(x);
+    }
+    // acc (earlier elements) combined with x (a later element)
+    __device__ static __forceinline__ A combine(A acc, A x) {
+        if constexpr (OP == JG_SUM) return acc + x;
+        else if constexpr (OP == JG_PROD) return acc * x;
+        else if constexpr (OP == JG_MIN) return (acc < x) ? acc : x;      // equal -> later element
+        else if constexpr (OP == JG_MAX) return (acc > x) ? acc : x;
+        else if constexpr (OP == JG_ANY) return A(acc | x);
+        else return A(acc & x);
+    }
+};
+
+constexpr int kBlockEventMin = 1 << 15;   // events at least this long are reduced by the whole CTA
+
+// partial result of a lane/warp over a strided subset; `pos` = position of the element that produced a
+// min/max value (needed only to reproduce "later wins on ties" exactly for +-0.0)
+template <typename A>
+struct Partial {
+    A val;
+    int64_t pos;
+    bool has;
+};
+
+template <int OP, typename T, typename A>
+__device__ __forceinline__ Partial<A> merge(Partial<A> a, Partial<A> b) {
+    if (!b.has) return a;
+    if (!a.has) return b;
+    Partial<A> r;
+    r.has = true;
+    if constexpr (OP == JG_MIN || OP == JG_MAX) {
+        const bool a_better = (OP == JG_MIN) ? (a.val < b.val) : (a.val > b.val);
+        const bool b_better = (OP == JG_MIN) ? (b.val < a.val) : (b.val > a.val);
+        const bool take_a = a_better || (!b_better && a.pos > b.pos);
+        r.val = take_a ? a.val : b.val;
+        r.pos = take_a ? a.pos : b.pos;
+    } else {
+        r.val = Red<OP, T, A>::combine(a.val, b.val);
+        r.pos = 0;
+    }
+    return r;
+}
+
+template <int OP, typename T, typename A>
+__device__ __forceinline__ Partial<A> shuffle_merge(Partial<A> p) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Partial<A> o;
+        o.val = __shfl_xor_sync(0xffffffffu, p.val, d);
+        o.pos = __shfl_xor_sync(0xffffffffu, p.pos, d);
+        o.has = __shfl_xor_sync(0xffffffffu, static_cast<int>(p.has), d) != 0;
+        p = merge<OP, T, A>(p, o);
+    }
+    return p;
+}
+
+template <int OP, typename T, typename A>
+__device__ __forceinline__ Partial<A> strided_partial(const T *__restrict__ content, int64_t a, int64_t b, int first,
+                                                      int step) {
+    Partial<A> p;
+    p.has = false;
+    p.val = Red<OP, T, A>::identity();
+    p.pos = -1;
+    for (int64_t j = a + first; j < b; j += step) {
+        const A x = Red<OP, T, A>::lift(__ldcs(content + j));
+        if (!p.has) {
+            p.val = x;
+            p.pos = j;
+            p.has = true;
+        } else if constexpr (OP == JG_MIN || OP == JG_MAX) {
+            const bool keep = (OP == JG_MIN) ? (p.val < x) : (p.val > x);
+            if (!keep) {
+                p.val = x;
+                p.pos = j;
+            }
+        } else {
+            p.val = Red<OP, T, A>::combine(p.val, x);
+        }
+    }
+    return p;
+}
+
+template <int OP, typename T, typename A, int STAGE_BYTES>
+__global__ void __launch_bounds__(kTileThreads)
+segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
+                 A *__restrict__ out) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
+    __shared__ uint64_t s_bar;
+    __shared__ Partial<A> s_part[kTileThreads / kWarp];
+    using R = Red<OP, T, A>;
+
+    EventTile tile;
+    stage_init(&s_bar, 1);
+    tile.load(s_off, offsets, n, blockIdx.x);
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    const int64_t nbytes = (e1 - e0) * static_cast<int64_t>(sizeof(T));
+
+    if (nbytes <= STAGE_BYTES) {
+        // ---------------- SHORT: stage the tile's content run, thread-per-event out of shared memory --------
+        if (nbytes > 0) {
+            const uint32_t shift = stage_issue<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes), &s_bar);
+            stage_wait(&s_bar, 0);
+            const T *sm = reinterpret_cast<const T *>(s_stage + shift);
+            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+                const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
+                A acc = R::identity();
+                if (b > a) {
+                    acc = R::lift(sm[a]);
+                    for (int j = a + 1; j < b; ++j) acc = R::combine(acc, R::lift(sm[j]));
+                }
+                out[tile.event0 + ev] = acc;
+            }
+        } else {
+            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) out[tile.event0 + ev] = R::identity();
+        }
+        return;
+    }
+
+    // ---------------- LONG: warp-per-event (block-per-event for very long events) ---------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ev = warp; ev < tile.nev; ev += kTileThreads / kWarp) {
+        const int64_t a = s_off[ev], b = s_off[ev + 1];
+        if (b - a >= kBlockEventMin) continue;     // handled below by the whole CTA
+        Partial<A> p = strided_partial<OP, T, A>(content, a, b, lane, kWarp);
+        p = shuffle_merge<OP, T, A>(p);
+        if (lane == 0) out[tile.event0 + ev] = p.has ? p.val : R::identity();
+    }
+    for (int ev = 0; ev < tile.nev; ++ev) {
+        const int64_t a = s_off[ev], b = s_off[ev + 1];
+        if (b - a < kBlockEventMin) continue;
+        Partial<A> p = strided_partial<OP, T, A>(content, a, b, threadIdx.x, kTileThreads);
+        p = shuffle_merge<OP, T, A>(p);
+        __syncthreads();
+        if (lane == 0) s_part[warp] = p;
+        __syncthreads();
+        if (warp == 0) {
+            Partial<A> q;
+            if (lane < kTileThreads / kWarp) q = s_part[lane];
+            else { q.has = false; q.val = R::identity(); q.pos = -1; }
+            q = shuffle_merge<OP, T, A>(q);
+            if (lane == 0) out[tile.event0 + ev] = q.has ? q.val : R::identity();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// argmin / argmax: best[i] = local index of the FIRST extreme non-NaN element, -1 if the event has none.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct ArgPartial {
+    T val;
+    int64_t idx;    // local index, -1 = none
+};
+
+template <bool ISMIN, typename T>
+__device__ __forceinline__ ArgPartial<T> arg_merge(ArgPartial<T> a, ArgPartial<T> b) {
+    if (b.idx < 0) return a;
+    if (a.idx < 0) return b;
+    const bool a_better = ISMIN ? (a.val < b.val) : (a.val > b.val);
+    const bool b_better = ISMIN ? (b.val < a.val) : (b.val > a.val);
+    if (a_better) return a;
+    if (b_better) return b;
+    return a.idx < b.idx ? a : b;     // equal values: first occurrence
+}
+
+template <bool ISMIN, typename T>
+__device__ __forceinline__ ArgPartial<T> arg_shuffle(ArgPartial<T> p) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ArgPartial<T> o;
+        o.val = __shfl_xor_sync(0xffffffffu, p.val, d);
+        o.idx = __shfl_xor_sync(0xffffffffu, p.idx, d);
+        p = arg_merge<ISMIN, T>(p, o);
+    }
+    return p;
+}
+
+template <bool ISMIN, typename T>
+__device__ __forceinline__ ArgPartial<T> arg_strided(const T *__restrict__ content, int64_t a, int64_t b, int first,
+                                                     int step) {
+    ArgPartial<T> p;
+    p.idx = -1;
+    p.val = T(0);
+    for (int64_t j = a + first; j < b; j += step) {
+        const T x = __ldcs(content + j);
+        if (is_nan(x)) continue;
+        if (p.idx < 0 || (ISMIN ? (x < p.val) : (x > p.val))) {
+            p.val = x;
+            p.idx = j - a;
+        }
+    }
+    return p;
+}
+
+template <bool ISMIN, typename T, int STAGE_BYTES>
+__global__ void __launch_bounds__(kTileThreads)
+segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
+              int64_t *__restrict__ best, T *__restrict__ best_value) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
+    __shared__ uint64_t s_bar;
+    __shared__ ArgPartial<T> s_part[kTileThreads / kWarp];
+
+    EventTile tile;
+    stage_init(&s_bar, 1);
+    tile.load(s_off, offsets, n, blockIdx.x);
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    const int64_t nbytes = (e1 - e0) * static_cast<int64_t>(sizeof(T));
+
+    if (nbytes <= STAGE_BYTES) {
+        const T *sm = nullptr;
+        if (nbytes > 0) {
+            const uint32_t shift = stage_issue<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes), &s_bar);
+            stage_wait(&s_bar, 0);
+            sm = reinterpret_cast<const T *>(s_stage + shift);
+        }
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+            const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
+            int idx = -1;
+            T bv = T(0);
+            for (int j = a; j < b; ++j) {
+                const T x = sm[j];
+                if (is_nan(x)) continue;
+                if (idx < 0 || (ISMIN ? (x < bv) : (x > bv))) {
+                    bv = x;
+                    idx = j - a;
+                }
+            }
+            best[tile.event0 + ev] = idx;
+            if (best_value) best_value[tile.event0 + ev] = bv;
+        }
+        return;
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ev = warp; ev < tile.nev; ev += kTileThreads / kWarp) {
+        const int64_t a = s_off[ev], b = s_off[ev + 1];
+        if (b - a >= kBlockEventMin) continue;
+        ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, a, b, lane, kWarp));
+        if (lane == 0) {
+            best[tile.event0 + ev] = p.idx;
+            if (best_value) best_value[tile.event0 + ev] = p.val;
+        }
+    }
+    for (int ev = 0; ev < tile.nev; ++ev) {
+        const int64_t a = s_off[ev], b = s_off[ev + 1];
+        if (b - a < kBlockEventMin) continue;
+        ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, a, b, threadIdx.x, kTileThreads));
+        __syncthreads();
+        if (lane == 0) s_part[warp] = p;
+        __syncthreads();
+        if (warp == 0) {
+            ArgPartial<T> q;
+            if (lane < kTileThreads / kWarp) q = s_part[lane];
+            else { q.idx = -1; q.val = T(0); }
+            q = arg_shuffle<ISMIN, T>(q);
+            if (lane == 0) {
+                best[tile.event0 + ev] = q.idx;
+                if (best_value) best_value[tile.event0 + ev] = q.val;
+            }
+        }
+    }
+}
+
+template <typename T> struct StageBytes { static constexpr int value = sizeof(T) >= 8 ? 32768 : (sizeof(T) >= 4 ? 16384 : 8192); };
+
+template <int OP, typename T, typename A>
+static int launch_reduce(const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s) {
+    segreduce_kernel<OP, T, A, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
+        static_cast<const T *>(content), offsets, n, static_cast<A *>(out));
+    return check_launch("segreduce_kernel");
+}
+
+template <typename T, typename ASUM>
+static int dispatch_reduce(int op, const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s) {
+    switch (op) {
+        case JG_SUM: return launch_reduce<JG_SUM, T, ASUM>(content, offsets, n, out, s);
+        case JG_PROD: return launch_reduce<JG_PROD, T, ASUM>(content, offsets, n, out, s);
+        case JG_MIN: return launch_reduce<JG_MIN, T, T>(content, offsets, n, out, s);
+        case JG_MAX: return launch_reduce<JG_MAX, T, T>(content, offsets, n, out, s);
+        case JG_ANY: return launch_reduce<JG_ANY, T, uint8_t>(content, offsets, n, out, s);
+        case JG_ALL: return launch_reduce<JG_ALL, T, uint8_t>(content, offsets, n, out, s);
+    }
+    set_error("jg_segreduce: unsupported op %d", op);
+    return -2;
+}
+
+template <typename T>
+static int dispatch_arg(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *best,
+                        void *best_value, cudaStream_t s) {
+    if (is_min)
+        segarg_kernel<true, T, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
+            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value));
+    else
+        segarg_kernel<false, T, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
+            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value));
+    return check_launch("segarg_kernel");
+}
+
+}  // namespace jg
+
+using namespace jg;
+
+extern "C" {
+
+int jg_segreduce(const void *content, int dtype, const int64_t *offsets, int64_t n, int op, void *out,
+                 int64_t content_len, void *stream) {
+    (void)content_len;
+    JG_REQUIRE(n >= 0 && offsets && out, "jg_segreduce: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    switch (dtype) {
+        case JG_F32: return dispatch_reduce<float, float>(op, content, offsets, n, out, s);
+        case JG_F64: return dispatch_reduce<double, double>(op, content, offsets, n, out, s);
+        case JG_I32: return dispatch_reduce<int32_t, int64_t>(op, content, offsets, n, out, s);
+        case JG_I64: return dispatch_reduce<int64_t, int64_t>(op, content, offsets, n, out, s);
+        case JG_U8: return dispatch_reduce<uint8_t, uint64_t>(op, content, offsets, n, out, s);
+        case JG_B8:
+            // bool: sum/prod -> int64, any/all -> bool; min/max -> float64 with +-inf identities (jagged.py:1530)
+            switch (op) {
+                case JG_SUM: return launch_reduce<JG_SUM, uint8_t, int64_t>(content, offsets, n, out, s);
+                case JG_PROD: return launch_reduce<JG_PROD, uint8_t, int64_t>(content, offsets, n, out, s);
+                case JG_MIN: return launch_reduce<JG_MIN, uint8_t, double>(content, offsets, n, out, s);
+                case JG_MAX: return launch_reduce<JG_MAX, uint8_t, double>(content, offsets, n, out, s);
+                case JG_ANY: return launch_reduce<JG_ANY, uint8_t, uint8_t>(content, offsets, n, out, s);
+                case JG_ALL: return launch_reduce<JG_ALL, uint8_t, uint8_t>(content, offsets, n, out, s);
+            }
+            break;
+    }
+    set_error("jg_segreduce: unsupported dtype %d / op %d", dtype, op);
+    return -2;
+}
+
+int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min, int64_t *best,
+                    void *best_value, void *stream) {
+    JG_REQUIRE(n >= 0 && offsets && best, "jg_segargminmax: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    switch (dtype) {
+        case JG_F32: return dispatch_arg<float>(is_min, content, offsets, n, best, best_value, s);
+        case JG_F64: return dispatch_arg<double>(is_min, content, offsets, n, best, best_value, s);
+        case JG_I32: return dispatch_arg<int32_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_I64: return dispatch_arg<int64_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_U8:
+        case JG_B8: return dispatch_arg<uint8_t>(is_min, content, offsets, n, best, best_value, s);
+    }
+    set_error("jg_segargminmax: unsupported dtype %d", dtype);
+    return -2;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// jg_scan.cuh -- single-pass decoupled-lookback exclusive scan (int64 result) over a generated sequence.
+//
+// Replaces numpy.cumsum at jagged.py:46 (counts2offsets) and every later use of it (new offsets after a mask
+// :577, pair/cross counts :1075,:1095,:1164,:1311, argmax counts).  The input is a functor so the per-event
+// count can be computed on the fly (n(n+1)/2 from offsets, flags from best[] >= 0, ...) without a temporary.
+//
+// Layout: CTA = 256 threads = 8 warps; a tile is 4096 items; warp w owns 512 consecutive items as 8 rows of
+// 64; lane l of row r holds items (2l, 2l+1) of that row, so loads and stores are fully coalesced 128-bit
+// accesses (LDG.128 / STG.128 for int64) with no shared-memory transpose.  The in-warp scan is done with
+// shuffles on 32-bit partials when every item of the tile is < 2^19 (the common case: counts), else 64-bit.
+// Tiles take their index from an atomic ticket so that a tile only ever waits on tiles that already started.
+//
+// Algorithmic traffic: itemsize*n read + 8*(n+1) written (16n bytes for int64 counts).
+#pragma once
+
+#include "jg_common.cuh"
+
+namespace jg {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanRows = 8;
+constexpr int kScanTile = kScanThreads * kScanRows * 2;   // 4096 items
+
+// ---- input functors: load2(i, n, a, b) yields items i and i+1 (0 beyond n) ---------------------------------
+template <typename T>
+struct ScanInArray {
+    const T *p;
+    bool aligned;   // p is aligned to 2*sizeof(T)
+    __device__ __forceinline__ void load2(int64_t i, int64_t n, int64_t &a, int64_t &b) const {
+        a = 0;
+        b = 0;
+        if (i + 1 < n) {
+            if (aligned) {
+                if constexpr (sizeof(T) == 8) {
+                    longlong2 v = __ldcs(reinterpret_cast<const longlong2 *>(p + i));
+                    a = v.x;
+                    b = v.y;
+                } else if constexpr (sizeof(T) == 4) {
+                    int2 v = __ldcs(reinterpret_cast<const int2 *>(p + i));
+                    a = static_cast<T>(v.x);
+                    b = static_cast<T>(v.y);
+                } else {
+                    a = static_cast<int64_t>(p[i]);
+                    b = static_cast<int64_t>(p[i + 1]);
+                }
+            } else {
+                a = static_cast<int64_t>(p[i]);
+                b = static_cast<int64_t>(p[i + 1]);
+            }
+        } else if (i < n) {
+            a = static_cast<int64_t>(p[i]);
+        }
+    }
+};
+
+// counts of non-negative flags: item = (best[i] >= 0)
+struct ScanInNonNeg {
+    const int64_t *p;
+    __device__ __forceinline__ void load2(int64_t i, int64_t n, int64_t &a, int64_t &b) const {
+        a = (i < n) ? (p[i] >= 0) : 0;
+        b = (i + 1 < n) ? (p[i + 1] >= 0) : 0;
+    }
+};
+
+// combinatorics: item = f(count_a[, count_b])
+__device__ __forceinline__ int64_t comb_count(int kind, int k, int64_t na, int64_t nb) {
+    switch (kind) {
+        case JG_COMB_PAIRS: return (na * (na + 1)) >> 1;
+        case JG_COMB_DISTINCTS: return (na * (na - 1)) / 2;
+        case JG_COMB_CROSS: return na * nb;
+        default: {   // JG_COMB_CHOOSE, k = 2..5 (jagged.py:1152-1159)
+            if (k == 2) return na * (na - 1) / 2;
+            if (k == 3) return na * (na - 1) * (na - 2) / 6;
+            if (k == 4) return na * (na - 1) * (na - 2) * (na - 3) / 24;
+            return na * (na - 1) * (na - 2) * (na - 3) * (na - 4) / 120;
+        }
+    }
+}
+
+struct ScanInComb {
+    const int64_t *oa;
+    const int64_t *ob;
+    int kind, k;
+    __device__ __forceinline__ int64_t one(int64_t i) const {
+        int64_t na = oa[i + 1] - oa[i];
+        int64_t nb = ob ? (ob[i + 1] - ob[i]) : 0;
+        return comb_count(kind, k, na, nb);
+    }
+    __device__ __forceinline__ void load2(int64_t i, int64_t n, int64_t &a, int64_t &b) const {
+        a = (i < n) ? one(i) : 0;
+        b = (i + 1 < n) ? one(i + 1) : 0;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void scan_rows(const int64_t (&v)[kScanRows][2], T (&excl)[kScanRows], T &warp_total,
+                                          int lane) {
+    T incl[kScanRows];
+#pragma unroll
+    for (int r = 0; r < kScanRows; ++r) incl[r] = static_cast<T>(v[r][0]) + static_cast<T>(v[r][1]);
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+#pragma unroll
+        for (int r = 0; r < kScanRows; ++r) {
+            T o = __shfl_up_sync(0xffffffffu, incl[r], d);
+            if (lane >= d) incl[r] += o;
+        }
+    }
+    T run = 0;
+#pragma unroll
+    for (int r = 0; r < kScanRows; ++r) {
+        T rowtot = __shfl_sync(0xffffffffu, incl[r], 31);
+        excl[r] = run + incl[r] - (static_cast<T>(v[r][0]) + static_cast<T>(v[r][1]));
+        run += rowtot;
+    }
+    warp_total = run;
+}
+
+template <class In>
+__global__ void __launch_bounds__(kScanThreads)
+scan_lookback_kernel(In in, int64_t n, int64_t *__restrict__ out, int64_t *__restrict__ total,
+                     int32_t *__restrict__ status, LookbackWs *__restrict__ ws, uint32_t ntiles, bool out_aligned) {
+    __shared__ uint32_t s_tile;
+    __shared__ int64_t s_warp[kScanThreads / kWarp + 1];
+    __shared__ int64_t s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&ws->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t warp_item0 = static_cast<int64_t>(tile) * kScanTile + static_cast<int64_t>(warp) * (kScanRows * 64);
+
+    int64_t v[kScanRows][2];
+#pragma unroll
+    for (int r = 0; r < kScanRows; ++r) in.load2(warp_item0 + r * 64 + lane * 2, n, v[r][0], v[r][1]);
+
+    bool neg = false, big = false;
+#pragma unroll
+    for (int r = 0; r < kScanRows; ++r) {
+        neg |= (v[r][0] < 0) | (v[r][1] < 0);
+        big |= (static_cast<uint64_t>(v[r][0]) >= (1ull << 19)) | (static_cast<uint64_t>(v[r][1]) >= (1ull << 19));
+    }
+    if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
+    const bool wide = __syncthreads_or(big);
+
+    int64_t excl[kScanRows];
+    int64_t warp_total;
+    if (!wide) {
+        int32_t e32[kScanRows];
+        int32_t wt;
+        scan_rows<int32_t>(v, e32, wt, lane);
+#pragma unroll
+        for (int r = 0; r < kScanRows; ++r) excl[r] = e32[r];
+        warp_total = wt;
+    } else {
+        scan_rows<int64_t>(v, excl, warp_total, lane);
+    }
+    if (lane == 0) s_warp[warp] = warp_total;
+    __syncthreads();
+
+    if (warp == 0) {
+        constexpr int NW = kScanThreads / kWarp;
+        int64_t w = lane < NW ? s_warp[lane] : 0;
+        int64_t wi = warp_incl_scan_add(w, lane);
+        int64_t block_total = __shfl_sync(0xffffffffu, wi, NW - 1);
+        int64_t tile_base = lookback_exclusive_warp(ws->desc, tile, block_total);
+        if (lane < NW) s_warp[lane] = wi - w;
+        if (lane == 0) {
+            s_base = tile_base;
+            if (tile == ntiles - 1) {
+                out[n] = tile_base + block_total;
+                if (total) *total = tile_base + block_total;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t base = s_base + s_warp[warp];
+
+#pragma unroll
+    for (int r = 0; r < kScanRows; ++r) {
+        const int64_t i = warp_item0 + r * 64 + lane * 2;
+        const int64_t e0 = base + excl[r];
+        const int64_t e1 = e0 + v[r][0];
+        if (i + 1 < n) {
+            if (out_aligned) {
+                __stcs(reinterpret_cast<longlong2 *>(out + i), make_longlong2(e0, e1));
+            } else {
+                out[i] = e0;
+                out[i + 1] = e1;
+            }
+        } else if (i < n) {
+            out[i] = e0;
+        }
+    }
+}
+
+// Host launcher.  `out` has n+1 entries: out[i] = sum of items before i, out[n] = grand total.
+template <class In>
+int launch_scan(const In &in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws, size_t ws_bytes,
+                cudaStream_t stream) {
+    const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, kScanTile);
+    const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;
+    JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
+    JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
+    JG_REQUIRE(ntiles < (1ll << 31), "scan: too many tiles");
+    cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
+    if (e != cudaSuccess) {
+        set_error("scan: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    scan_lookback_kernel<In><<<static_cast<unsigned>(ntiles), kScanThreads, 0, stream>>>(
+        in, n, out, total, status, reinterpret_cast<LookbackWs *>(ws), static_cast<uint32_t>(ntiles), out_aligned);
+    return check_launch("scan_lookback_kernel");
+}
+
+}  // namespace jg

@@ -1,0 +1,104 @@
+// jg_tile.cuh -- the "event tile": a CTA owns kTileEvents consecutive events and keeps their offsets in
+// shared memory.  Everything that walks content event by event (reductions, mask, gathers, broadcasts,
+// combinatorics) is built on it, so content is always addressed through on-chip offsets.
+#pragma once
+
+#include "jg_common.cuh"
+
+namespace jg {
+
+constexpr int kTileThreads = 256;
+constexpr int kTileEvents = 512;
+
+struct EventTile {
+    int64_t *off;      // shared: off[0..nev]
+    int64_t event0;    // first event of this CTA
+    int nev;           // number of events in this CTA (<= kTileEvents)
+
+    // all threads of the CTA call this; `s_off` is a __shared__ int64_t[kTileEvents + 1]
+    __device__ __forceinline__ void load(int64_t *s_off, const int64_t *__restrict__ offsets, int64_t n,
+                                         int64_t tile_index) {
+        off = s_off;
+        event0 = tile_index * kTileEvents;
+        const int64_t left = n - event0;
+        nev = left < kTileEvents ? static_cast<int>(left) : kTileEvents;
+        for (int i = threadIdx.x; i <= nev; i += kTileThreads) s_off[i] = __ldg(offsets + event0 + i);
+        __syncthreads();
+    }
+    __device__ __forceinline__ int64_t first_element() const { return off[0]; }
+    __device__ __forceinline__ int64_t last_element() const { return off[nev]; }
+    // event (local index) that contains element j, first_element() <= j < last_element()
+    __device__ __forceinline__ int find_event(int64_t j) const {
+        int lo = 0, hi = nev - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (off[mid + 1] <= j) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    }
+};
+
+static inline unsigned tile_grid(int64_t n) { return static_cast<unsigned>(n <= 0 ? 1 : ceil_div(n, kTileEvents)); }
+
+}  // namespace jg
+
+namespace jg {
+
+// ---------------------------------------------------------------------------------------------------------
+// Staging a contiguous run of global memory into shared memory with the TMA engine (cp.async.bulk, SASS
+// UBLKCP): the 16-byte-aligned middle goes through ONE bulk copy issued by thread 0 and tracked by an
+// mbarrier; the (< 16 byte) unaligned head and tail are copied by ordinary loads.  Shared byte k mirrors
+// global byte (align_down(gaddr, 16) + k), so an element keeps its 16-byte phase and the returned `shift`
+// locates the first requested byte.
+//
+//   smem   : shared buffer, 16-byte aligned, capacity >= nbytes + 32
+//   g      : first requested global byte (element aligned)
+//   nbytes : number of requested bytes (> 0)
+//   bar    : one mbarrier per staged buffer, initialised with count 1 by thread 0 (see stage_init)
+// All threads of the CTA call stage_issue(); they later call stage_wait() before reading.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_init(uint64_t *bar, int nbars) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nbars; ++i) mbar_init(bar + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+template <int ELEM>
+__device__ __forceinline__ uint32_t stage_issue(unsigned char *smem, const unsigned char *g, uint32_t nbytes,
+                                                uint64_t *bar) {
+    const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+    const uint32_t shift = static_cast<uint32_t>(ga & 15);
+    const uintptr_t mid_begin = (ga + 15) & ~static_cast<uintptr_t>(15);
+    const uintptr_t mid_end = (ga + nbytes) & ~static_cast<uintptr_t>(15);
+    const uint32_t head = static_cast<uint32_t>(mid_begin > ga + nbytes ? nbytes : mid_begin - ga);
+    if (mid_end > mid_begin) {
+        const uint32_t mid = static_cast<uint32_t>(mid_end - mid_begin);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, mid);
+            bulk_g2s(smem + shift + head, reinterpret_cast<const void *>(mid_begin), mid, bar);
+        }
+        // tail elements
+        const uint32_t tail0 = head + mid;
+        for (uint32_t b = tail0 + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
+#pragma unroll
+            for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
+        }
+    } else if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, 0);   // nothing in flight: complete the phase immediately
+    }
+    for (uint32_t b = threadIdx.x * ELEM; b < head; b += blockDim.x * ELEM) {
+#pragma unroll
+        for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
+    }
+    return shift;
+}
+
+__device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t phase) {
+    mbar_wait(bar, phase);     // bulk bytes have landed (async proxy -> visible to waiting threads)
+    __syncthreads();           // head / tail written by other threads
+}
+
+}  // namespace jg

@@ -1,0 +1,194 @@
+/*
+ * jagged_b200.h -- C ABI of libjagged_sm100a.so: the awkward0 JaggedArray hot path on B200 (sm_100a).
+ *
+ * The reference (scikit-hep/awkward-0.x 0.15.5) is pure Python on numpy and has NO native interface; its
+ * "kernels" are the numpy primitives called from awkward0/array/jagged.py.  Each entry point below replaces
+ * one of those call sites (cited as jagged.py:LINE) and is what a ctypes binding inside the reference's own
+ * JaggedArray would call (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *   - every pointer is a RAW DEVICE pointer unless the parameter is documented as host;
+ *   - sizes and indices are int64_t (the reference's INDEXTYPE, base.py:44);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, re-entrant and
+ *     keeps no state between calls (the only global is the thread-local error string);
+ *   - the library never allocates or frees device memory: scratch comes from the caller (`ws`, `ws_bytes`,
+ *     size from jg_workspace_bytes), results go to caller-allocated buffers;
+ *   - return value: 0 = launched, <0 = argument / CUDA error (text in jg_last_error());
+ *   - data-dependent conditions (negative counts, non-monotone offsets, out-of-bounds jagged index, ...) are
+ *     OR-ed into a caller-provided device word `status` (JG_ST_* bits); the Python host reads it together
+ *     with the scan total and raises the reference's exception type and message.
+ *   - `dtype` arguments use the JG_* codes below; bool content is JG_B8 (one byte, 0/1).
+ */
+#ifndef JAGGED_B200_H
+#define JAGGED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+/* ---- dtype codes -------------------------------------------------------------------------------------- */
+enum {
+    JG_F32 = 0, JG_F64 = 1, JG_I32 = 2, JG_I64 = 3, JG_B8 = 4, JG_U8 = 5,
+    JG_I8 = 6, JG_I16 = 7, JG_U16 = 8, JG_U32 = 9, JG_U64 = 10
+};
+
+/* ---- status bits (device word written by kernels) ------------------------------------------------------ */
+enum {
+    JG_ST_NEGATIVE_COUNT  = 1,   /* fromcounts: "counts must be a non-negative array"        jagged.py:160 */
+    JG_ST_NEGATIVE_OFFSET = 2,   /* "offsets must be a non-negative array"                   jagged.py:126 */
+    JG_ST_NONMONOTONE     = 4,   /* "offsets must be monatonically increasing"               jagged.py:474 */
+    JG_ST_BEYOND_CONTENT  = 8,   /* "maximum offset {0} is beyond the length of the content" jagged.py:476 */
+    JG_ST_INDEX_OOB       = 16,  /* "jagged array used as index contains out-of-bounds"      jagged.py:555 */
+    JG_ST_COUNTS_MISMATCH = 32,  /* "cannot fit contents of JaggedArray into the given ..."  jagged.py:911 */
+    JG_ST_NOT_OFFSETS     = 64,  /* starts[1:] != stops[:-1]                                 jagged.py:358 */
+    JG_ST_STOPS_LT_STARTS = 128  /* "stops must be greater than or equal to starts"          jagged.py:501 */
+};
+
+/* ---- reducers (base.py:193-215) -------------------------------------------------------------------------- */
+enum { JG_SUM = 0, JG_PROD = 1, JG_MIN = 2, JG_MAX = 3, JG_ANY = 4, JG_ALL = 5, JG_COUNT_NONZERO = 6 };
+
+/* ---- elementwise ops (numpy ufuncs reached through __array_ufunc__, jagged.py:944-1051) ------------------- */
+enum {
+    JG_OP_ADD = 0, JG_OP_SUB = 1, JG_OP_MUL = 2, JG_OP_DIV = 3, JG_OP_FLOORDIV = 4, JG_OP_MOD = 5,
+    JG_OP_POW = 6, JG_OP_MAXIMUM = 7, JG_OP_MINIMUM = 8, JG_OP_ARCTAN2 = 9, JG_OP_HYPOT = 10,
+    JG_OP_GT = 16, JG_OP_GE = 17, JG_OP_LT = 18, JG_OP_LE = 19, JG_OP_EQ = 20, JG_OP_NE = 21,
+    JG_OP_AND = 24, JG_OP_OR = 25, JG_OP_XOR = 26,
+    JG_OP_NEG = 32, JG_OP_ABS = 33, JG_OP_SQRT = 34, JG_OP_EXP = 35, JG_OP_LOG = 36, JG_OP_SIN = 37,
+    JG_OP_COS = 38, JG_OP_TAN = 39, JG_OP_SINH = 40, JG_OP_COSH = 41, JG_OP_TANH = 42, JG_OP_SQUARE = 43,
+    JG_OP_NOT = 44, JG_OP_ISNAN = 45, JG_OP_CAST = 46, JG_OP_ISFINITE = 47, JG_OP_ARCSINH = 48,
+    JG_OP_FLOOR = 49, JG_OP_CEIL = 50, JG_OP_RINT = 51, JG_OP_SIGN = 52, JG_OP_LOG10 = 53, JG_OP_EXP2 = 54,
+    JG_OP_ARCSIN = 55, JG_OP_ARCCOS = 56, JG_OP_ARCTAN = 57, JG_OP_ISINF = 58, JG_OP_LOG2 = 59,
+    JG_OP_LOG1P = 60, JG_OP_EXPM1 = 61, JG_OP_RECIPROCAL = 62
+};
+
+/* how the second operand of a binary op is addressed */
+enum {
+    JG_RHS_ARRAY  = 0,   /* same length as lhs                                            */
+    JG_RHS_SCALAR = 1,   /* one value (taken from `scalar_f64` / `scalar_i64`)             */
+    JG_RHS_PARENT = 2    /* flat[N] broadcast through the events: rhs[parent(j)]  jagged.py:1003-1037 */
+};
+
+/* ---- combinatorics kinds ---------------------------------------------------------------------------------- */
+enum {
+    JG_COMB_PAIRS = 0,      /* i <= j, lexicographic             jagged.py:1070-1091 */
+    JG_COMB_DISTINCTS = 1,  /* i <  j, lexicographic             jagged.py:1093-1126 */
+    JG_COMB_CHOOSE = 2,     /* k = 2..5, colexicographic         jagged.py:1128-1221 */
+    JG_COMB_CROSS = 3       /* rectangular, left index slow      jagged.py:1302-1325 */
+};
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int         jg_version(void);
+const char *jg_last_error(void);                         /* thread-local, host string */
+int         jg_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* scratch bytes sufficient for any call on `n` events (scan descriptors + ticket); CUB-style two-phase API */
+size_t      jg_workspace_bytes(int64_t n);
+
+/* ---- offsets / parents machinery --------------------------------------------------------------------------- */
+/* jagged.py:42-47  counts2offsets: offsets[0]=0, offsets[1:]=cumsum(counts).  Single-pass decoupled-lookback
+ * scan.  counts_dtype in {JG_I32, JG_I64, JG_U8, JG_B8}; *total (device int64) receives offsets[n];
+ * JG_ST_NEGATIVE_COUNT is raised in *status for negative counts (jagged.py:160).                              */
+int jg_counts2offsets(const void *counts, int counts_dtype, int64_t n, int64_t *offsets, int64_t *total,
+                      int32_t *status, void *ws, size_t ws_bytes, void *stream);
+/* jagged.py:383-388  counts = stops - starts (offsets[1:] - offsets[:-1]) */
+int jg_offsets2counts(const int64_t *offsets, int64_t n, int64_t *counts, void *stream);
+/* general layout: counts[i] = stops[i] - starts[i] */
+int jg_startsstops2counts(const int64_t *starts, const int64_t *stops, int64_t n, int64_t *counts, void *stream);
+/* jagged.py:120-127,469-477  _valid(): non-negative, monotone, max <= content_len.
+ * info (device int64[4]) = {offsets[0], offsets[n], max count, number of non-empty events}.                    */
+int jg_validate_offsets(const int64_t *offsets, int64_t n, int64_t content_len, int64_t *info,
+                        int32_t *status, void *stream);
+/* jagged.py:358,495-502  general starts/stops: stops >= starts, bounds, and whether starts[1:] == stops[:-1].
+ * info (device int64[4]) = {min start of non-empty, max stop, max count, number of non-empty events}.          */
+int jg_validate_startsstops(const int64_t *starts, const int64_t *stops, int64_t n, int64_t content_len,
+                            int64_t *info, int32_t *status, void *stream);
+/* jagged.py:49-54  offsets2parents: parents[j] = i for offsets[i] <= j < offsets[i+1]; -1 below offsets[0].
+ * parents has offsets[n] entries (the caller knows offsets[n] from jg_validate_offsets / the scan total).      */
+int jg_offsets2parents(const int64_t *offsets, int64_t n, int64_t *parents, void *stream);
+/* jagged.py:430-437  localindex content: out[j - offsets[0]] = j - offsets[parent(j)]                          */
+int jg_localindex(const int64_t *offsets, int64_t n, int64_t *out, void *stream);
+/* jagged.py:56-71  startsstops2parents for a non-dense layout: out (length out_len) pre-filled with -1          */
+int jg_startsstops2parents(const int64_t *starts, const int64_t *stops, int64_t n, int64_t *out,
+                           int64_t out_len, void *stream);
+/* jagged.py:883-942 / 1386-1398  compact(): out[dense_offsets[i] + k] = content[starts[i] + k]                  */
+int jg_compact_gather(const void *content, int itemsize, const int64_t *starts, const int64_t *dense_offsets,
+                      int64_t n, void *out, void *stream);
+
+/* ---- segmented reductions ------------------------------------------------------------------------------------ */
+/* jagged.py:1459-1565 via base.py:193-215.  op in JG_SUM..JG_ALL.  NaN -> identity, empty -> identity.
+ * Output dtype follows numpy: sum/prod of B8/I32 -> I64 (U8 -> U64), min/max keep the dtype (B8 -> F64),
+ * any/all -> B8; the caller passes the matching out buffer.                                                      */
+int jg_segreduce(const void *content, int dtype, const int64_t *offsets, int64_t n, int op, void *out,
+                 int64_t content_len, void *stream);
+/* jagged.py:1567-1601  argmin/argmax, logical value: best[i] = local index of the first extreme non-NaN element,
+ * or -1 for an event with none.  Optionally also writes the extreme value itself (same dtype as content).        */
+int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                    int64_t *best, void *best_value, void *stream);
+/* turn best[] into the dense result: out_offsets[n+1] (0/1 counts scanned) and out_index[<=n]; *total = count.   */
+int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
+                      void *ws, size_t ws_bytes, void *stream);
+
+/* ---- jagged __getitem__ ---------------------------------------------------------------------------------------- */
+/* jagged.py:562-589  a[jagged_bool]: single pass (per-event popcount -> lookback scan -> compaction).
+ * mask and content are both addressed through `offsets` (absolute positions offsets[0]..offsets[n]);
+ * mask_shift = mask_offsets[0] - offsets[0] re-bases a mask whose content starts elsewhere.
+ * out must hold offsets[n]-offsets[0] items (upper bound); *total receives K.                                     */
+int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
+                   const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *total,
+                   void *ws, size_t ws_bytes, void *stream);
+/* counts of two layouts must agree (jagged.py:911-912): raises JG_ST_COUNTS_MISMATCH                               */
+int jg_check_same_counts(const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, int32_t *status,
+                         void *stream);
+/* jagged.py:541-560  a[jagged_int]: out[k] = content[offsets[p] + wrap(index[k])], p = event of k in
+ * index_offsets; negative wrap (:552-553); JG_ST_INDEX_OOB (:555-556).  index_dtype in {JG_I32, JG_I64}.          */
+int jg_index_gather(const void *content, int itemsize, const int64_t *offsets, const void *index,
+                    int index_dtype, const int64_t *index_offsets, int64_t n, void *out, int32_t *status,
+                    void *stream);
+/* plain gather out[k] = content[index[k]] (jagged.py:1294 content[left]); no bounds check beyond content_len      */
+int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_index, void *out, void *stream);
+
+/* ---- broadcasting and elementwise ufuncs ------------------------------------------------------------------------ */
+/* jagged.py:866-875  tojagged(flat): out[j - offsets[0]] = flat[parent(j)]                                          */
+int jg_broadcast(const void *flat, int itemsize, const int64_t *offsets, int64_t n, void *out, void *stream);
+/* jagged.py:1043  ufunc(lhs, rhs) on dense contents.  Operands are converted to `compute_dtype` on load, the op
+ * runs in that type, and the result is stored as `out_dtype` (comparisons -> JG_B8).  rhs_kind selects array /
+ * scalar / per-event broadcast (then `offsets`/`n` describe the events of lhs and lhs starts at offsets[0]).
+ * swap != 0 computes op(rhs, lhs) (reflected operators).                                                             */
+int jg_binary(int op, const void *lhs, int lhs_dtype, const void *rhs, int rhs_dtype, int rhs_kind,
+              double scalar_f64, int64_t scalar_i64, int swap, int compute_dtype, void *out, int out_dtype,
+              int64_t len, const int64_t *offsets, int64_t n, void *stream);
+int jg_unary(int op, const void *in, int in_dtype, int compute_dtype, void *out, int out_dtype, int64_t len,
+             void *stream);
+/* whole-array reduction of a flat device array to one value (for global totals before an NCCL all-reduce)          */
+int jg_flat_reduce(const void *in, int dtype, int64_t len, int op, void *out /* device, out dtype as segreduce */,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ---- combinatorics ------------------------------------------------------------------------------------------------ */
+/* single pass: per-event output count -> lookback scan -> index generation.
+ *   kind = JG_COMB_PAIRS / DISTINCTS / CHOOSE(k) / CROSS (offsets_b only for CROSS).
+ * Phase 1 (jg_comb_offsets): out_offsets[n+1] and *total = P (device).  Phase 2 (jg_comb_fill): writes k local
+ * index columns cols[c][P] (int64), or, if `absolute` != 0, indices with the event start added
+ * (jagged.py:1086-1087, 1319-1320).                                                                                   */
+int jg_comb_offsets(int kind, int k, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                    int64_t *out_offsets, int64_t *total, void *ws, size_t ws_bytes, void *stream);
+int jg_comb_fill(int kind, int k, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                 const int64_t *out_offsets, int64_t *const *cols /* host array of k device pointers */,
+                 int absolute, void *stream);
+/* fused value form (jagged.py:1294,1350): out_l[p] = content_a[start_a + i], out_r[p] = content_b[start_b + j]
+ * for kind in PAIRS / DISTINCTS / CROSS without materialising the index columns.                                     */
+int jg_comb_gather2(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                    const int64_t *out_offsets, const void *content_a, int itemsize_a, const void *content_b,
+                    int itemsize_b, void *out_l, void *out_r, void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAGGED_B200_H */
