@@ -87,6 +87,12 @@ def check(rc, what):
         raise JaggedLibError("{0} failed (rc={1}): {2}".format(what, rc, lib.jg_last_error().decode()))
 
 
+# kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
+LAUNCHES = [0]
+_KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2}
+
+
 def call(name, *args):
     """Call a C entry point that returns an int status and raise on failure."""
+    LAUNCHES[0] += _KERNELS.get(name, 1)
     check(getattr(lib, name)(*args), name)

@@ -1,0 +1,175 @@
+"""Event-range sharding of the JaggedArray hot path across GPUs (one process per GPU, torch.distributed).
+
+The path shards by independent units: no operation moves an element across an event boundary, which is the
+reference's own ChunkedArray model (awkward0/array/chunked.py:523-593, 602-658, 683-710 -- every op mapped
+chunk by chunk; tests/test_crosscut.py:86-89) and why counts are position independent
+(docs/classes.adoc:33-36).  Rank r owns a contiguous range of events with LOCAL offsets that start at 0; all
+kernels run locally with no data-path collective.  NCCL is used only for
+  * whole-array totals (sum of sums, global max/min, number selected, number of pairs): all_reduce of a few bytes;
+  * replicated per-event results on request: all_gather (sizes first when shards are unequal).
+
+Everything here works on whatever backend the process group uses: "nccl" with CUDA tensors in production,
+"gloo" with CPU tensors in the world_size-2 CPU tests (tests/test_sharded_gloo.py), where the local compute
+is supplied by the test.
+"""
+import numpy
+
+try:
+    import torch
+    import torch.distributed as dist
+except ImportError:          # pragma: no cover
+    torch = None
+    dist = None
+
+
+def event_range(nevents, rank, world):
+    """Contiguous, balanced event range [lo, hi) of `rank` (first nevents % world ranks get one more)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank {0} outside world of size {1}".format(rank, world))
+    base, extra = divmod(int(nevents), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def element_range(global_offsets, lo, hi):
+    """Content range [offsets[lo], offsets[hi]) of an event range (host-side, on the global offsets)."""
+    return int(global_offsets[lo]), int(global_offsets[hi])
+
+
+def local_shard(counts, content, rank, world, offsets=None):
+    """Slice host arrays (global counts, global dense content) into the shard of `rank`: (counts, content)."""
+    counts = numpy.asarray(counts)
+    lo, hi = event_range(len(counts), rank, world)
+    if offsets is None:
+        start = int(counts[:lo].sum())
+        stop = start + int(counts[lo:hi].sum())
+    else:
+        start, stop = element_range(offsets, lo, hi)
+    return counts[lo:hi], numpy.asarray(content)[start:stop]
+
+
+def _world(group=None):
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _device_for(group=None):
+    if dist is not None and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def _as_tensor(x, dtype, device):
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=dtype).reshape(-1)
+    if hasattr(x, "tensor"):                   # DeviceArray
+        return x.tensor.to(device=device, dtype=dtype).reshape(-1)
+    return torch.as_tensor(numpy.asarray(x), dtype=dtype, device=device).reshape(-1)
+
+
+def allreduce_totals(sums=(), maxima=(), minima=(), group=None):
+    """Whole-array totals across ranks: returns (sums, maxima, minima) as python floats / ints.
+
+    `sums` are added (sum of per-event sums, number selected, number of pairs ...), `maxima` / `minima`
+    are reduced with max / min.  Payloads are a few bytes: the cost is launch latency, not bandwidth.
+    """
+    world, _ = _world(group)
+    device = _device_for(group)
+    out = []
+    for values, op in ((sums, "sum"), (maxima, "max"), (minima, "min")):
+        values = list(values)
+        if not values:
+            out.append([])
+            continue
+        isint = all(isinstance(v, (int, numpy.integer)) for v in values)
+        t = torch.tensor(values, dtype=torch.int64 if isint else torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op],
+                            group=group)
+        out.append([v.item() for v in t.cpu()])
+    return tuple(out)
+
+
+def gather_per_event(local, group=None):
+    """Replicate a per-event result (one value per local event) on every rank, in global event order.
+
+    Equal shards use one all_gather; unequal shards exchange the sizes first and pad.  `local` is a
+    DeviceArray / torch tensor / numpy array; the result is a torch tensor on the group's device.
+    """
+    world, rank = _world(group)
+    device = _device_for(group)
+    if torch.is_tensor(local):
+        t = local.to(device).reshape(-1)
+    elif hasattr(local, "tensor"):
+        t = local.tensor.to(device).reshape(-1)
+    else:
+        t = torch.as_tensor(numpy.asarray(local), device=device).reshape(-1)
+    if world == 1:
+        return t
+    size = torch.tensor([t.numel()], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    biggest = max(sizes)
+    padded = torch.zeros(biggest, dtype=t.dtype, device=device)
+    padded[:t.numel()] = t
+    parts = [torch.empty(biggest, dtype=t.dtype, device=device) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+def global_offsets_base(local_total, group=None):
+    """Exclusive prefix over ranks of the local element totals: what to add to local offsets to get global ones."""
+    world, rank = _world(group)
+    device = _device_for(group)
+    if world == 1:
+        return 0
+    mine = torch.tensor([int(local_total)], dtype=torch.int64, device=device)
+    every = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    return int(sum(int(x.item()) for x in every[:rank]))
+
+
+class ShardedJaggedArray(object):
+    """This rank's shard of a jagged array plus the collectives that stitch whole-array answers together.
+
+    `local` is any object with the JaggedArray reducer surface (the device JaggedArray in production).
+    Per-event operations are simply forwarded to the shard (`s.local.sum()`, `s.local[s.local > 20]` ...).
+    """
+
+    def __init__(self, local, group=None):
+        self.local = local
+        self.group = group
+        self.world, self.rank = _world(group)
+
+    def __len__(self):
+        (total,), _, _ = allreduce_totals(sums=[int(len(self.local))], group=self.group)
+        return int(total)
+
+    def _scalar(self, x):
+        if hasattr(x, "get"):
+            x = x.get()
+        x = numpy.asarray(x).reshape(-1)
+        return x[0].item() if len(x) else 0
+
+    def total_sum(self):
+        """Sum over all events of the per-event sums."""
+        (tot,), _, _ = allreduce_totals(sums=[float(self._scalar(self.local.sum().sum()))], group=self.group)
+        return tot
+
+    def total_max(self):
+        _, (m,), _ = allreduce_totals(maxima=[float(self._scalar(self.local.max().max()))], group=self.group)
+        return m
+
+    def total_min(self):
+        _, _, (m,) = allreduce_totals(minima=[float(self._scalar(self.local.min().min()))], group=self.group)
+        return m
+
+    def total_content(self):
+        """Number of content elements over all shards."""
+        (tot,), _, _ = allreduce_totals(sums=[int(self._scalar(self.local.counts.sum()))], group=self.group)
+        return int(tot)
+
+    def gather(self, per_event):
+        return gather_per_event(per_event, group=self.group)

@@ -74,22 +74,18 @@ __device__ __forceinline__ uint32_t stage_issue(unsigned char *smem, const unsig
     const uintptr_t mid_begin = (ga + 15) & ~static_cast<uintptr_t>(15);
     const uintptr_t mid_end = (ga + nbytes) & ~static_cast<uintptr_t>(15);
     const uint32_t head = static_cast<uint32_t>(mid_begin > ga + nbytes ? nbytes : mid_begin - ga);
-    if (mid_end > mid_begin) {
-        const uint32_t mid = static_cast<uint32_t>(mid_end - mid_begin);
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, mid);
-            bulk_g2s(smem + shift + head, reinterpret_cast<const void *>(mid_begin), mid, bar);
-        }
-        // tail elements
-        const uint32_t tail0 = head + mid;
-        for (uint32_t b = tail0 + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
-#pragma unroll
-            for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
-        }
-    } else if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, 0);   // nothing in flight: complete the phase immediately
+    uint32_t mid = 0;
+    if (mid_end > mid_begin) mid = static_cast<uint32_t>(mid_end - mid_begin);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, mid);    // mid == 0: nothing in flight, the phase completes immediately
+        if (mid) bulk_g2s(smem + shift + head, reinterpret_cast<const void *>(mid_begin), mid, bar);
     }
+    // unaligned head (< 16 bytes) and tail (< 16 bytes) by ordinary loads
     for (uint32_t b = threadIdx.x * ELEM; b < head; b += blockDim.x * ELEM) {
+#pragma unroll
+        for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
+    }
+    for (uint32_t b = head + mid + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
 #pragma unroll
         for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
     }

@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py -- the JaggedArray hot-path sweep on B200 (BASELINE.json: "jagged elements/sec and HBM GB/s vs peak
+for sum/argmax/mask/pairs at 1/2/4/8 GPUs").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port), host cores
+
+Workload (config.workload): BASELINE.json configs[4] shard -- per GPU 125 M events (1 B events at 8 GPUs),
+Poisson(5) counts, float32 content Exp(25); one STEP = counts2offsets scan + segmented sum + argmax +
+(pt > 20) mask -> select -> flatten/counts, then the whole-array totals (NCCL all-reduce when N > 1).  Weak
+scaling: every rank owns the same number of events, no data-path collective.
+
+value  = content elements swept per second with inputs resident in HBM (CUDA events, max over ranks)
+e2e    = the same sweep through the public API from pinned HOST buffers (H2D inside the timed region, totals read back)
+roofline = dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline = the numpy oracle (a port of the reference's algorithm, oracle/jagged_oracle.py) on one host core,
+               bounded sample; `--impl reference` runs it on all host cores (one process per core, equal shards)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "awkward-0.x_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+THRESHOLD = 20.0
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic data
+# ----------------------------------------------------------------------------------------------------------------
+def make_shard(nevents, seed, mean=5.0, scale=25.0):
+    rng = np.random.default_rng(seed)
+    counts = rng.poisson(mean, nevents).astype(np.int64)
+    total = int(counts.sum())
+    pt = rng.standard_exponential(total, dtype=np.float32)
+    pt *= np.float32(scale)
+    return counts, pt
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm (numpy oracle port) on all host cores
+# ----------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(nevents, seed_base):
+    import multiprocessing
+    ident = multiprocessing.current_process()._identity
+    seed = seed_base + (ident[0] if ident else 0)
+    _W["data"] = make_shard(nevents, seed)
+
+
+def cpu_sweep(counts, pt):
+    """The same sweep with the reference's algorithm (numpy): returns (elements, checksum tuple)."""
+    from oracle import jagged_oracle as O
+    off = O.counts2offsets(counts)
+    s = O.reduce(off, pt, "sum")
+    aoff, aidx = O.argminmax(off, pt, False)
+    moff, mask = O.ufunc_broadcast(np.greater, off, pt, np.float32(THRESHOLD))
+    soff, sel = O.mask_select(off, pt, moff, mask)
+    flat = O.flatten(soff, sel)
+    c = O.offsets2counts(soff)
+    return len(pt), (float(s.sum(dtype=np.float64)), int(len(flat)), int(len(aidx)), int(c.sum()))
+
+
+def _worker_step(_):
+    counts, pt = _W["data"]
+    return cpu_sweep(counts, pt)[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_worker = args.ref_events_per_core
+    ctx = multiprocessing.get_context("fork")
+    pool = ctx.Pool(cores, initializer=_worker_init, initargs=(per_worker, 977))
+    try:
+        for _ in range(args.warmup):
+            pool.map(_worker_step, range(cores), chunksize=1)
+        t0 = time.perf_counter()
+        elements = 0
+        for _ in range(args.steps):
+            elements += sum(pool.map(_worker_step, range(cores), chunksize=1))
+        dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    value = elements / dt
+    line = {
+        "impl": "reference", "metric": "jagged elements/sec (offsets scan + sum + argmax + mask sweep)",
+        "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "events_per_step": per_worker * cores, "threshold": THRESHOLD},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port",
+                         "sample": "%d events per core x %d cores per step (Poisson(5), f32), numpy oracle port of "
+                                   "awkward0/array/jagged.py; the reference itself is pure Python and cannot travel "
+                                   "to the GPU box" % (per_worker, cores)},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+WORKLOAD_NAME = ("C5 sweep shard: 125M events/GPU (1B events at 8 GPUs), Poisson(5) counts, float32 Exp(25) content; "
+                 "step = counts2offsets + sum + argmax + (pt>20) mask-select + flatten/counts + global totals")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import awkward0_b200 as ak
+    from awkward0_b200 import _lib, sharded
+    from awkward0_b200.device import DeviceArray, empty, runtime
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    nev = args.events_per_gpu
+    counts_np, pt_np = make_shard(nev, 12345 + rank)
+    M = len(pt_np)
+    # pinned host staging (the e2e leg copies from here every step)
+    counts_pin = torch.empty(nev, dtype=torch.int64, pin_memory=True)
+    counts_pin.numpy()[:] = counts_np
+    pt_pin = torch.empty(M, dtype=torch.float32, pin_memory=True)
+    pt_pin.numpy()[:] = pt_np
+    del counts_np, pt_np
+
+    counts_dev = ak.asdevice(counts_pin)
+    pt_dev = ak.asdevice(pt_pin)
+    torch.cuda.synchronize()
+
+    def sweep(counts, content):
+        """One step through the public API.  Returns the whole-array totals (python numbers)."""
+        a = ak.JaggedArray.fromcounts(counts, content)          # scan (+ total/negative-count read-back)
+        s = a.sum()
+        lead = a.argmax()
+        sel = a[a > THRESHOLD]
+        flat = sel.flatten()
+        c = sel.counts
+        local_sum = float(s.sum())                               # device reduction, one 8-byte read
+        (gsum, gk, glead), _, _ = sharded.allreduce_totals(sums=[local_sum, float(len(flat)), float(len(lead.content))])
+        return gsum, gk, glead, len(c)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, out
+
+    # ---- warm-up, then the device-resident timed region
+    for _ in range(max(args.warmup, 3)):
+        totals = sweep(counts_dev, pt_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.LAUNCHES[0] = 0
+    ms_dev, totals = timed(lambda: sweep(counts_dev, pt_dev), args.steps)
+    launches = _lib.LAUNCHES[0]
+
+    # ---- e2e: pinned host -> device inside the timed region, totals read back
+    for _ in range(1):
+        sweep(counts_pin, pt_pin)
+    ms_e2e, totals_e2e = timed(lambda: sweep(counts_pin, pt_pin), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    Mt = torch.tensor([M], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(Mt)
+    M_all = float(Mt.item())
+    value = M_all * args.steps / (ms_dev * 1e-3)
+    e2e_value = M_all * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel roofline table (rank 0, device-resident, CUDA events around each C-ABI call)
+    ops = {}
+    if rank == 0:
+        ops = kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, nev, M, args)
+    peaks = load_peaks()
+    roof = None
+    if ops:
+        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_f32", "compact_nonneg", "greater_f32", "mask_select_f32", "offsets2counts"]
+        dom = max(step_ops, key=lambda k: ops[k]["ms"])
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peaks[0], "unit": "GB/s",
+                "frac": ops[dom]["gbs"] / peaks[0], "traffic": None, "peak_source": peaks[1],
+                "algorithmic_bytes": ops[dom]["bytes"], "ms": ops[dom]["ms"],
+                "step_share": ops[dom]["ms"] / sum(ops[k]["ms"] for k in step_ops)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": "jagged elements/sec (offsets scan + sum + argmax + mask sweep)", "value": value,
+            "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "events_per_gpu": nev, "content_elements_per_gpu": M,
+                       "threshold": THRESHOLD, "l2": "inputs (3.5 GB/GPU) are larger than L2; no flush needed",
+                       "parallelism": "event-range shards, %d rank(s)" % world},
+            "e2e": {"value": e2e_value, "unit": "elements/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(nev * 8 + M * 4), "d2h_bytes_per_step": 5 * 64,
+                    "note": "public API from pinned host buffers; results stay in HBM, totals are read back"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "totals": {"sum": totals[0], "selected": totals[1], "leading": totals[2]},
+            "roofline": roof, "cpu_baseline": cpu, "ops": ops,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M, args):
+    """CUDA-event time of every hot-path kernel on the resident shard; algorithmic bytes per SURVEY.md 8(d)."""
+    import ctypes
+    import torch
+    from awkward0_b200.jagged import _vp
+    reps = args.kernel_reps
+    peak = load_peaks()[0]
+    table = {}
+
+    def time_call(fn):
+        fn()
+        torch.cuda.synchronize()
+        best = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best.append(e0.elapsed_time(e1))
+        return float(np.mean(best)), float(min(best))
+
+    def add(name, nbytes, elements, fn):
+        ms, best = time_call(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        table[name] = {"ms": ms, "best_ms": best, "bytes": int(nbytes), "gbs": gbs, "frac": gbs / peak,
+                       "elements_per_s": elements / (ms * 1e-3)}
+
+    a = ak.JaggedArray.fromcounts(counts_dev, pt_dev)
+    off = a._off64
+    st = runtime.stream
+    ws, wsb = runtime.workspace(N)
+    scal = runtime.scalars()
+    v = 4
+
+    offsets_out = empty(N + 1, np.int64)
+    add("counts2offsets", 16 * N, N, lambda: _lib.call(
+        "jg_counts2offsets", counts_dev.data_ptr(), _lib.JG_I64, N, _vp(offsets_out), _vp(scal), _vp(scal, 1), ws, wsb, st()))
+    cnt = empty(N, np.int64)
+    add("offsets2counts", 16 * N, N, lambda: _lib.call("jg_offsets2counts", off.data_ptr(), N, _vp(cnt), st()))
+    info = runtime.scalars()
+    add("validate_offsets", 8 * N, N, lambda: _lib.call(
+        "jg_validate_offsets", off.data_ptr(), N, M, _vp(info, 2), _vp(info, 1), st()))
+    par = empty(M, np.int64)
+    add("offsets2parents", 8 * N + 8 * M, M, lambda: _lib.call("jg_offsets2parents", off.data_ptr(), N, _vp(par), st()))
+    add("localindex", 8 * N + 8 * M, M, lambda: _lib.call("jg_localindex", off.data_ptr(), N, _vp(par), st()))
+    del par
+    out32 = empty(N, np.float32)
+    for name, op in (("sum", _lib.SUM), ("max", _lib.MAX), ("min", _lib.MIN), ("prod", _lib.PROD)):
+        add("segreduce_%s_f32" % name, v * M + 8 * N + v * N, M, lambda op=op: _lib.call(
+            "jg_segreduce", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, op, _vp(out32), M, st()))
+    best = empty(N, np.int64)
+    add("segargmax_f32", v * M + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_segargminmax", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(best), ctypes.c_void_p(0), st()))
+    aoff, aidx = empty(N + 1, np.int64), empty(N, np.int64)
+    add("compact_nonneg", 8 * N + 8 * N + 8 * N, N, lambda: _lib.call(
+        "jg_compact_nonneg", _vp(best), N, _vp(aoff), _vp(aidx), _vp(scal), ws, wsb, st()))
+    mask = empty(M, np.bool_)
+    add("greater_f32", v * M + M, M, lambda: _lib.call(
+        "jg_binary", _lib.OP["GT"], pt_dev.data_ptr(), _lib.JG_F32, ctypes.c_void_p(0), 0, _lib.RHS_SCALAR,
+        ctypes.c_double(THRESHOLD), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(mask), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st()))
+    sel = empty(M, np.float32)
+    noff = empty(N + 1, np.int64)
+    _lib.call("jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(scal), ws, wsb, st())
+    K = int(scal.cpu()[0])
+    add("mask_select_f32", v * M + M + 8 * N + v * K + 8 * N, M, lambda: _lib.call(
+        "jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(scal), ws, wsb, st()))
+    del sel, mask
+    # leading-object gather a[a.argmax()]
+    lead = a.argmax()
+    Kl = len(lead.content)
+    gout = empty(Kl, np.float32)
+    add("index_gather_f32", 8 * Kl + 16 * N + v * Kl + v * Kl, Kl, lambda: _lib.call(
+        "jg_index_gather", pt_dev.data_ptr(), 4, off.data_ptr(), lead.content.data_ptr(), _lib.JG_I64,
+        lead._off64.data_ptr(), N, _vp(gout), _vp(scal, 1), st()))
+    del lead, gout
+    flat = ak.DeviceArray(out32)
+    bout = empty(M, np.float32)
+    add("broadcast_f32", v * N + 8 * N + v * M, M, lambda: _lib.call(
+        "jg_broadcast", flat.data_ptr(), 4, off.data_ptr(), N, _vp(bout), st()))
+    add("add_flat_f32", v * M + v * N + 8 * N + v * M, M, lambda: _lib.call(
+        "jg_binary", _lib.OP["ADD"], pt_dev.data_ptr(), _lib.JG_F32, flat.data_ptr(), _lib.JG_F32, _lib.RHS_PARENT,
+        ctypes.c_double(0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(bout), _lib.JG_F32, M, off.data_ptr(), N, st()))
+    del bout
+
+    # combinatorics on a dimuon-like shard (BASELINE configs[3]: Poisson(2) counts)
+    Nc = args.comb_events
+    rng = np.random.default_rng(4242)
+    mu_off = ak.JaggedArray.counts2offsets(ak.asdevice(rng.poisson(2.0, Nc).astype(np.int64)))
+    el_off = ak.JaggedArray.counts2offsets(ak.asdevice(rng.poisson(2.0, Nc).astype(np.int64)))
+    Mmu = int(mu_off[-1])
+    mu_pt = ak.asdevice(rng.exponential(20.0, Mmu).astype(np.float32))
+    Mel = int(el_off[-1])
+    el_pt = ak.asdevice(rng.exponential(20.0, Mel).astype(np.float32))
+    wsc, wscb = runtime.workspace(Nc)
+    for kind, name, ob in ((_lib.COMB_PAIRS, "pairs", None), (_lib.COMB_DISTINCTS, "distincts", None), (_lib.COMB_CROSS, "cross", el_off)):
+        poff = empty(Nc + 1, np.int64)
+        obp = ob.data_ptr() if ob is not None else ctypes.c_void_p(0)
+        nin = 8 * Nc * (2 if ob is not None else 1)
+        add("comb_offsets_" + name, nin + 8 * Nc, Nc, lambda: _lib.call(
+            "jg_comb_offsets", kind, 2, mu_off.data_ptr(), obp, Nc, _vp(poff), _vp(scal), wsc, wscb, st()))
+        P = int(scal.cpu()[0])
+        c0, c1 = empty(P, np.int64), empty(P, np.int64)
+        arr = (ctypes.c_void_p * 2)(c0.data_ptr(), c1.data_ptr())
+        add("arg" + name + "_fill", nin + 8 * Nc + 16 * P, P, lambda: _lib.call(
+            "jg_comb_fill", kind, 2, mu_off.data_ptr(), obp, Nc, _vp(poff), arr, 0, st()))
+        del c0, c1
+        l, r = empty(P, np.float32), empty(P, np.float32)
+        cb = el_pt if ob is not None else mu_pt
+        add(name + "_values_f32", nin + 8 * Nc + 4 * Mmu + (4 * Mel if ob is not None else 0) + 8 * P, P, lambda: _lib.call(
+            "jg_comb_gather2", kind, mu_off.data_ptr(), obp, Nc, _vp(poff), mu_pt.data_ptr(), 4, cb.data_ptr(), 4,
+            _vp(l), _vp(r), st()))
+        del l, r
+        table["arg" + name + "_fill"]["pairs"] = P
+    return table
+
+
+def cpu_baseline(args):
+    """Oracle port (numpy, 1 core) on a bounded sample of the same workload."""
+    n = args.cpu_events
+    counts, pt = make_shard(n, 12345)
+    cpu_sweep(counts[: n // 8], pt[: int(counts[: n // 8].sum())])     # warm numpy
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        elements, _ = cpu_sweep(counts, pt)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": elements / best, "unit": "elements/s", "cores": 1, "kind": "port",
+            "sample": "%d events (%d elements) of the same sweep, numpy oracle port of awkward0/array/jagged.py, "
+                      "best of 2; host has %d cores" % (n, elements, os.cpu_count() or 0),
+            "seconds": best}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--events-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--comb-events", type=int, default=50_000_000)
+    ap.add_argument("--cpu-events", type=int, default=4_000_000)
+    ap.add_argument("--ref-events-per-core", type=int, default=1_000_000)
+    ap.add_argument("--kernel-reps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

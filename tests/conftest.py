@@ -38,8 +38,9 @@ def same(a, b):
     if a.dtype != b.dtype or a.shape != b.shape:
         return False
     if a.dtype.kind == "f":
-        return bool(np.array_equal(a.view("u%d" % a.dtype.itemsize), b.view("u%d" % b.dtype.itemsize)) or
-                    (np.array_equal(np.isnan(a), np.isnan(b)) and
-                     np.array_equal(np.where(np.isnan(a), 0, a), np.where(np.isnan(b), 0, b)) and
-                     np.array_equal(np.signbit(a), np.signbit(b))))
+        if np.array_equal(a.view("u%d" % a.dtype.itemsize), b.view("u%d" % b.dtype.itemsize)):
+            return True
+        na, nb = np.isnan(a), np.isnan(b)      # NaN payload / sign bits are not part of the contract
+        return bool(np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb]) and
+                    np.array_equal(np.signbit(a[~na]), np.signbit(b[~nb])))
     return bool(np.array_equal(a, b))
