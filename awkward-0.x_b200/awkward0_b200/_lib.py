@@ -58,6 +58,7 @@ PROTOTYPES = {
     "jg_compact_gather": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "jg_segreduce": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "jg_segargminmax": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
+    "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_check_same_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
@@ -89,7 +90,8 @@ def check(rc, what):
 
 # kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
 LAUNCHES = [0]
-_KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2}
+_KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
+            "jg_mask_select": 3, "jg_segargminmax_dense": 3}
 
 
 def call(name, *args):

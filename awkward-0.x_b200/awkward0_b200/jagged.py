@@ -927,22 +927,19 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return self._argminmax(False)
 
     def _argminmax(self, ismin, with_values=False):
-        """jagged.py:1581-1601 -> jg_segargminmax + jg_compact_nonneg (dense logical result)."""
+        """jagged.py:1581-1601 -> jg_segargminmax_dense (one pass: arg-reduce, look-back scan, dense result)."""
         a, off, n, first, last = self._dense()
         if isinstance(a._content, JaggedArray):
             return self.copy(content=a._content._argminmax(ismin))
         if not isinstance(a._content, DeviceArray):
             raise ValueError("cannot compute arg{0} because content is not one-dimensional".format("min" if ismin else "max"))
         col = a._content
-        best = empty(n, INDEXTYPE)
         out_offsets = empty(n + 1, INDEXTYPE)
         out_index = empty(n, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
-        if n > 0:
-            call("jg_segargminmax", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0, _vp(best),
-                 ctypes.c_void_p(0), runtime.stream())
-        call("jg_compact_nonneg", _vp(best), n, _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
+        call("jg_segargminmax_dense", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
+             _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
         total, _, _ = runtime.read(scal)
         return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
 

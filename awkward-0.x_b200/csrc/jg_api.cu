@@ -61,11 +61,12 @@ int jg_device_info(int *sms, int *major, int *minor) {
     return 0;
 }
 
-// One 64-bit look-back descriptor per tile; the smallest tile any kernel uses is 256 events.
+// Scratch for any call on n events: either one look-back descriptor per scan tile, or (mask select, arg
+// compaction) two int64 arrays with one entry per 512-event tile plus the descriptors of the scan over them.
 size_t jg_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    size_t tiles = static_cast<size_t>(n / 256 + 2);
-    return 64 + tiles * 8 + 4096;
+    size_t tiles = static_cast<size_t>(n / 512 + 4);
+    return 3 * (tiles * 8 + 256) + 8192;
 }
 
 }  // extern "C"

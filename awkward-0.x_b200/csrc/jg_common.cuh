@@ -190,7 +190,11 @@ __device__ __forceinline__ int64_t lookback_exclusive(uint64_t *desc, uint32_t t
     return static_cast<int64_t>(excl);
 }
 
-// Warp-cooperative variant: the 32 lanes of one warp inspect 32 predecessors per round.
+// Warp-cooperative variant.  Every round the 32 lanes fetch kLookDepth x 32 predecessor descriptors with
+// independent loads (so one L2 round trip covers 256 tiles -- with ~900 tiles in flight on 148 SMs a
+// 32-per-round walk costs ~28 dependent L2 latencies per tile and dominates short tiles), then consume
+// them 32 at a time, nearest first.
+template <int kLookDepth = 1>
 __device__ __forceinline__ int64_t lookback_exclusive_warp(uint64_t *desc, uint32_t tile, int64_t aggregate) {
     const int lane = threadIdx.x & 31;
     const uint64_t agg = static_cast<uint64_t>(aggregate) & kValueMask;
@@ -200,21 +204,29 @@ __device__ __forceinline__ int64_t lookback_exclusive_warp(uint64_t *desc, uint3
     }
     if (lane == 0) st_relaxed_u64(&desc[tile], (kStateAggregate << 62) | agg);
     uint64_t excl = 0;
-    int64_t base = static_cast<int64_t>(tile) - 1;      // lane l looks at tile base - l
-    while (true) {
-        int64_t t = base - lane;
-        uint64_t w = (t >= 0) ? ld_relaxed_u64(&desc[t]) : (kStatePrefix << 62);
-        uint64_t st = w >> 62;
-        // all lanes up to the first PREFIX must be valid
-        unsigned invalid = __ballot_sync(0xffffffffu, st == kStateInvalid);
-        unsigned prefix = __ballot_sync(0xffffffffu, st == kStatePrefix);
-        int first_prefix = prefix ? (__ffs(prefix) - 1) : 32;
-        unsigned need = first_prefix >= 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);
-        if (invalid & need) continue;                   // something we need is not published yet
-        uint64_t contrib = (lane <= first_prefix) ? (w & kValueMask) : 0ull;
-        excl += warp_reduce_add(contrib);
-        if (prefix) break;
-        base -= 32;
+    int64_t base = static_cast<int64_t>(tile) - 1;      // group g, lane l looks at tile base - 32*g - l
+    bool done = false;
+    while (!done) {
+        uint64_t w[kLookDepth];
+#pragma unroll
+        for (int g = 0; g < kLookDepth; ++g) {
+            const int64_t t = base - 32 * g - lane;
+            w[g] = (t >= 0) ? ld_relaxed_u64(&desc[t]) : (kStatePrefix << 62);
+        }
+#pragma unroll
+        for (int g = 0; g < kLookDepth; ++g) {
+            if (done) break;
+            const uint64_t st = w[g] >> 62;
+            const unsigned invalid = __ballot_sync(0xffffffffu, st == kStateInvalid);
+            const unsigned prefix = __ballot_sync(0xffffffffu, st == kStatePrefix);
+            const int first_prefix = prefix ? (__ffs(prefix) - 1) : 32;
+            const unsigned need = first_prefix >= 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);
+            if (invalid & need) break;                  // a needed predecessor has not published: re-poll from here
+            const uint64_t contrib = (lane <= first_prefix) ? (w[g] & kValueMask) : 0ull;
+            excl += warp_reduce_add(contrib);
+            base -= 32;
+            if (prefix) done = true;
+        }
     }
     if (lane == 0) st_relaxed_u64(&desc[tile], (kStatePrefix << 62) | ((excl + agg) & kValueMask));
     return static_cast<int64_t>(excl);

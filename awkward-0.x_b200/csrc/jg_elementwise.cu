@@ -133,6 +133,94 @@ binary_flat_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__restr
     }
 }
 
+// Vectorised fast path: both operands already have the compute type C (or rhs is a scalar) and every pointer is
+// 16-byte aligned.  Each thread owns EPT = 16 consecutive elements: 128-bit loads, one 128-bit store per 16 bytes
+// of output (a comparison writes its 16 bool results with ONE STG.128 instead of 16 byte stores).
+template <typename T>
+union Vec16 {
+    int4 raw;
+    T v[16 / sizeof(T)];
+};
+
+template <typename T, int N>
+__device__ __forceinline__ void load_pack(const T *p, T (&dst)[N]) {
+    constexpr int PER = 16 / sizeof(T);          // elements per 128-bit access
+    static_assert(N % PER == 0, "pack size");
+#pragma unroll
+    for (int k = 0; k < N / PER; ++k) {
+        Vec16<T> q;
+        q.raw = __ldcs(reinterpret_cast<const int4 *>(p) + k);
+#pragma unroll
+        for (int e = 0; e < PER; ++e) dst[k * PER + e] = q.v[e];
+    }
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void store_pack(T *p, const T (&src)[N]) {
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int k = 0; k < N / PER; ++k) {
+        Vec16<T> q;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) q.v[e] = src[k * PER + e];
+        __stcs(reinterpret_cast<int4 *>(p) + k, q.raw);
+    }
+}
+
+template <class F, typename C>
+__global__ void __launch_bounds__(256)
+binary_vec_kernel(const C *__restrict__ lhs, const C *__restrict__ rhs, bool rhs_scalar, C scalar, int swap,
+                  typename F::Out *__restrict__ out, int64_t nchunks) {
+    using O = typename F::Out;
+    constexpr int EPT = 16;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        C a[EPT], b[EPT];
+        O r[EPT];
+        load_pack<C, EPT>(lhs + c * EPT, a);
+        if (rhs_scalar) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) b[e] = scalar;
+        } else {
+            load_pack<C, EPT>(rhs + c * EPT, b);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) r[e] = swap ? F::apply(b[e], a[e]) : F::apply(a[e], b[e]);
+        store_pack<O, EPT>(out + c * EPT, r);
+    }
+}
+
+template <class F, typename C>
+__global__ void __launch_bounds__(256)
+unary_vec_kernel(const C *__restrict__ in, typename F::Out *__restrict__ out, int64_t nchunks) {
+    using O = typename F::Out;
+    constexpr int EPT = 16;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        C a[EPT];
+        O r[EPT];
+        load_pack<C, EPT>(in + c * EPT, a);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) r[e] = F::apply(a[e]);
+        store_pack<O, EPT>(out + c * EPT, r);
+    }
+}
+
+template <typename C> struct DtypeOf;
+template <> struct DtypeOf<float> { static constexpr int value = JG_F32; };
+template <> struct DtypeOf<double> { static constexpr int value = JG_F64; };
+template <> struct DtypeOf<int32_t> { static constexpr int value = JG_I32; };
+template <> struct DtypeOf<int64_t> { static constexpr int value = JG_I64; };
+template <> struct DtypeOf<uint8_t> { static constexpr int value = JG_U8; };
+template <> struct DtypeOf<uint64_t> { static constexpr int value = JG_U64; };
+
+template <typename C>
+static inline bool same_type(int dt) {
+    return dt == DtypeOf<C>::value || (sizeof(C) == 1 && (dt == JG_B8 || dt == JG_U8));
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // rhs is flat[N]; lhs/out are dense contents starting at offsets[0]
 template <class F, typename C>
 __global__ void __launch_bounds__(kTileThreads)
@@ -177,8 +265,23 @@ static int launch_binary(const BinArgs &a) {
     C scalar;
     if constexpr (IsFp<C>::value) scalar = static_cast<C>(a.sf);
     else scalar = static_cast<C>(a.si);
-    binary_flat_kernel<F, C><<<ew_grid(a.len), 256, 0, a.s>>>(a.lhs, a.lhs_dt, a.rhs, a.rhs_dt, a.rhs_kind, scalar,
-                                                             a.swap, static_cast<O *>(a.out), a.len);
+    const bool rhs_scalar = a.rhs_kind == JG_RHS_SCALAR;
+    int64_t done = 0;
+    if (same_type<C>(a.lhs_dt) && (rhs_scalar || same_type<C>(a.rhs_dt)) && aligned16(a.lhs) && aligned16(a.out) &&
+        (rhs_scalar || aligned16(a.rhs)) && a.len >= 16) {
+        const int64_t nchunks = a.len / 16;
+        binary_vec_kernel<F, C><<<ew_grid(nchunks), 256, 0, a.s>>>(static_cast<const C *>(a.lhs),
+                                                                  static_cast<const C *>(a.rhs), rhs_scalar, scalar,
+                                                                  a.swap, static_cast<O *>(a.out), nchunks);
+        done = nchunks * 16;
+        if (done == a.len) return check_launch("binary_vec_kernel");
+    }
+    // scalar tail / unaligned / mixed-dtype operands
+    const char *lp = static_cast<const char *>(a.lhs) + done * dtype_size(a.lhs_dt);
+    const char *rp = rhs_scalar ? nullptr : static_cast<const char *>(a.rhs) + done * dtype_size(a.rhs_dt);
+    binary_flat_kernel<F, C><<<ew_grid(a.len - done), 256, 0, a.s>>>(lp, a.lhs_dt, rp, a.rhs_dt, a.rhs_kind, scalar,
+                                                                    a.swap, static_cast<O *>(a.out) + done,
+                                                                    a.len - done);
     return check_launch("binary_flat_kernel");
 }
 
@@ -286,7 +389,16 @@ unary_kernel(const void *__restrict__ in, int in_dt, typename F::Out *__restrict
 template <class F, typename C>
 static int launch_unary(const void *in, int in_dt, void *out, int64_t len, cudaStream_t s) {
     if (len <= 0) return 0;
-    unary_kernel<F, C><<<ew_grid(len), 256, 0, s>>>(in, in_dt, static_cast<typename F::Out *>(out), len);
+    using O = typename F::Out;
+    int64_t done = 0;
+    if (same_type<C>(in_dt) && aligned16(in) && aligned16(out) && len >= 16) {
+        const int64_t nchunks = len / 16;
+        unary_vec_kernel<F, C><<<ew_grid(nchunks), 256, 0, s>>>(static_cast<const C *>(in), static_cast<O *>(out), nchunks);
+        done = nchunks * 16;
+        if (done == len) return check_launch("unary_vec_kernel");
+    }
+    unary_kernel<F, C><<<ew_grid(len - done), 256, 0, s>>>(static_cast<const char *>(in) + done * dtype_size(in_dt), in_dt,
+                                                          static_cast<O *>(out) + done, len - done);
     return check_launch("unary_kernel");
 }
 

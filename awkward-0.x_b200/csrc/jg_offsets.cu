@@ -205,16 +205,11 @@ int jg_counts2offsets(const void *counts, int counts_dtype, int64_t n, int64_t *
                       int32_t *status, void *ws, size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets != nullptr, "jg_counts2offsets: bad arguments");
     cudaStream_t s = as_stream(stream);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(counts);
     switch (counts_dtype) {
-        case JG_I64: {
-            ScanInArray<int64_t> in{static_cast<const int64_t *>(counts), (addr & 15) == 0};
-            return launch_scan(in, n, offsets, total, status, ws, ws_bytes, s);
-        }
-        case JG_I32: {
-            ScanInArray<int32_t> in{static_cast<const int32_t *>(counts), (addr & 7) == 0};
-            return launch_scan(in, n, offsets, total, status, ws, ws_bytes, s);
-        }
+        case JG_I64:
+            return launch_scan_array(static_cast<const int64_t *>(counts), n, offsets, total, status, ws, ws_bytes, s);
+        case JG_I32:
+            return launch_scan_array(static_cast<const int32_t *>(counts), n, offsets, total, status, ws, ws_bytes, s);
         case JG_U8:
         case JG_B8: {
             ScanInArray<uint8_t> in{static_cast<const uint8_t *>(counts), false};

@@ -15,6 +15,7 @@
 // Algorithmic traffic: v*M + 8(N+1) read, v_out*N written.
 #include <math_constants.h>
 
+#include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -256,11 +257,13 @@ __device__ __forceinline__ ArgPartial<T> arg_strided(const T *__restrict__ conte
 template <bool ISMIN, typename T, int STAGE_BYTES>
 __global__ void __launch_bounds__(kTileThreads)
 segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
-              int64_t *__restrict__ best, T *__restrict__ best_value) {
+              int64_t *__restrict__ best, T *__restrict__ best_value, int64_t *__restrict__ tile_totals) {
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
     __shared__ uint64_t s_bar;
     __shared__ ArgPartial<T> s_part[kTileThreads / kWarp];
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
 
     EventTile tile;
     stage_init(&s_bar, 1);
@@ -276,6 +279,7 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
             stage_wait(&s_bar, 0);
             sm = reinterpret_cast<const T *>(s_stage + shift);
         }
+        int nvalid = 0;
         for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
             const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
             int idx = -1;
@@ -290,6 +294,13 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
             }
             best[tile.event0 + ev] = idx;
             if (best_value) best_value[tile.event0 + ev] = bv;
+            nvalid += (idx >= 0);
+        }
+        if (tile_totals) {
+            nvalid = warp_reduce_add(nvalid);
+            if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(&s_valid, nvalid);
+            __syncthreads();
+            if (threadIdx.x == 0) tile_totals[blockIdx.x] = s_valid;
         }
         return;
     }
@@ -302,6 +313,7 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
         if (lane == 0) {
             best[tile.event0 + ev] = p.idx;
             if (best_value) best_value[tile.event0 + ev] = p.val;
+            if (p.idx >= 0) atomicAdd(&s_valid, 1);
         }
     }
     for (int ev = 0; ev < tile.nev; ++ev) {
@@ -319,9 +331,53 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
             if (lane == 0) {
                 best[tile.event0 + ev] = q.idx;
                 if (best_value) best_value[tile.event0 + ev] = q.val;
+                if (q.idx >= 0) atomicAdd(&s_valid, 1);
             }
         }
     }
+    if (tile_totals) {
+        __syncthreads();
+        if (threadIdx.x == 0) tile_totals[blockIdx.x] = s_valid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dense form of argmin / argmax (jagged.py:1581-1601 logical value): segarg_kernel also counts, per event tile,
+// the events that have a result; the tile totals are scanned (tiny) and compact_best_kernel turns best[] into
+// out_offsets / out_index IN PLACE (best[] lives in the out_offsets buffer), with no cross-CTA waiting.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads)
+compact_best_kernel(int64_t *__restrict__ best_then_offsets, int64_t n, const int64_t *__restrict__ tile_bases,
+                    int64_t *__restrict__ out_index, uint32_t ntiles) {
+    __shared__ int32_t s_scan[kTileThreads / kWarp + 1];
+    const int64_t event0 = static_cast<int64_t>(blockIdx.x) * kTileEvents;
+    const int64_t i0 = event0 + threadIdx.x * 2;       // thread t finishes events 2t and 2t+1
+    int64_t b0 = -1, b1 = -1;
+    if (i0 + 1 < n) {
+        if ((reinterpret_cast<uintptr_t>(best_then_offsets) & 15) == 0) {
+            const longlong2 v = *reinterpret_cast<const longlong2 *>(best_then_offsets + i0);
+            b0 = v.x;
+            b1 = v.y;
+        } else {
+            b0 = best_then_offsets[i0];
+            b1 = best_then_offsets[i0 + 1];
+        }
+    } else if (i0 < n) {
+        b0 = best_then_offsets[i0];
+    }
+    const int has0 = b0 >= 0, has1 = b1 >= 0;
+    int32_t block_total;
+    const int32_t excl = block_excl_scan<int32_t, kTileThreads>(has0 + has1, s_scan, block_total);
+    const int64_t base = __ldg(tile_bases + blockIdx.x) + excl;
+    if (i0 < n) {
+        best_then_offsets[i0] = base;
+        if (has0) out_index[base] = b0;
+    }
+    if (i0 + 1 < n) {
+        best_then_offsets[i0 + 1] = base + has0;
+        if (has1) out_index[base + has0] = b1;
+    }
+    if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) best_then_offsets[n] = __ldg(tile_bases + ntiles);
 }
 
 template <typename T> struct StageBytes { static constexpr int value = sizeof(T) >= 8 ? 32768 : (sizeof(T) >= 4 ? 16384 : 8192); };
@@ -349,14 +405,37 @@ static int dispatch_reduce(int op, const void *content, const int64_t *offsets, 
 
 template <typename T>
 static int dispatch_arg(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *best,
-                        void *best_value, cudaStream_t s) {
+                        void *best_value, cudaStream_t s, int64_t *tile_totals = nullptr) {
     if (is_min)
         segarg_kernel<true, T, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
-            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value));
+            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value), tile_totals);
     else
         segarg_kernel<false, T, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
-            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value));
+            static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value), tile_totals);
     return check_launch("segarg_kernel");
+}
+
+template <typename T>
+static int dispatch_arg_dense(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *out_offsets,
+                              int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+    const int64_t ntiles = tile_grid(n);
+    // workspace: [totals: nt+2][bases: nt+2][scan descriptors]
+    const size_t arr = ((static_cast<size_t>(ntiles) + 2) * 8 + 255) & ~static_cast<size_t>(255);
+    const size_t scan_need = sizeof(LookbackWs) + static_cast<size_t>(ceil_div(ntiles, kScanTile) + 1) * 8;
+    JG_REQUIRE(ws != nullptr && ws_bytes >= 2 * arr + scan_need + 256,
+               "jg_segargminmax_dense: workspace too small (%zu < %zu)", ws_bytes, 2 * arr + scan_need + 256);
+    int64_t *totals = static_cast<int64_t *>(ws);
+    int64_t *bases = reinterpret_cast<int64_t *>(static_cast<char *>(ws) + arr);
+    void *scan_ws = static_cast<char *>(ws) + 2 * arr;
+    if (n == 0) cudaMemsetAsync(totals, 0, 8, s);
+    int rc = n > 0 ? dispatch_arg<T>(is_min, content, offsets, n, out_offsets, nullptr, s, totals) : 0;
+    if (rc) return rc;
+    ScanInArray<int64_t> in{totals, true};
+    rc = launch_scan(in, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
+    if (rc) return rc;
+    compact_best_kernel<<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(out_offsets, n, bases, out_index,
+                                                                                static_cast<uint32_t>(ntiles));
+    return check_launch("compact_best_kernel");
 }
 
 }  // namespace jg
@@ -407,6 +486,23 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
         case JG_B8: return dispatch_arg<uint8_t>(is_min, content, offsets, n, best, best_value, s);
     }
     set_error("jg_segargminmax: unsupported dtype %d", dtype);
+    return -2;
+}
+
+int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                          int64_t *out_offsets, int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes,
+                          void *stream) {
+    JG_REQUIRE(n >= 0 && offsets && out_offsets, "jg_segargminmax_dense: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    switch (dtype) {
+        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_U8:
+        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+    }
+    set_error("jg_segargminmax_dense: unsupported dtype %d", dtype);
     return -2;
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 
 #include "jg_common.cuh"
+#include "jg_tile.cuh"
 
 namespace jg {
 
@@ -192,6 +193,133 @@ scan_lookback_kernel(In in, int64_t n, int64_t *__restrict__ out, int64_t *__res
             out[i] = e0;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Array-input variant with the tile PARKED IN SHARED MEMORY: the tile (4096 items) is fetched with one TMA bulk
+// copy (UBLKCP), the 128 threads keep only a handful of registers, so 6-7 CTAs are resident per SM.  That
+// residency is what a look-back scan needs on B200: every tile waits ~6 us for the slowest of its predecessors
+// (profiles/r1_lookback_study.md), and only parked tiles -- not registers -- can cover that wait.
+// Measured 4.4 TB/s (vs 2.9 TB/s for the register-resident kernel above at 3 CTAs/SM).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kScanTmaThreads = 128;
+constexpr int kScanTmaItems = 32;                                   // per thread
+constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 4096 items
+
+template <typename T, typename S>     // T = stored item type, S = in-tile accumulator (int32 fast path / int64)
+__device__ __forceinline__ void scan_tma_rows(const T *sm, int valid, int wbase, int lane, int64_t run,
+                                              int64_t *__restrict__ out, int64_t i0, int64_t n, bool out_aligned) {
+    constexpr int ROWS = kScanTmaItems / 2;
+    S carry = 0;
+#pragma unroll 4
+    for (int r = 0; r < ROWS; ++r) {
+        const int p = wbase + r * 64 + lane * 2;
+        const S x = p < valid ? static_cast<S>(sm[p]) : S(0);
+        const S y = p + 1 < valid ? static_cast<S>(sm[p + 1]) : S(0);
+        const S s2 = x + y;
+        S incl = s2;
+#pragma unroll
+        for (int d = 1; d < kWarp; d <<= 1) {
+            const S o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int64_t e0 = run + static_cast<int64_t>(carry + incl - s2);
+        const int64_t i = i0 + p;
+        if (i + 1 < n) {
+            if (out_aligned) __stcs(reinterpret_cast<longlong2 *>(out + i), make_longlong2(e0, e0 + static_cast<int64_t>(x)));
+            else {
+                out[i] = e0;
+                out[i + 1] = e0 + static_cast<int64_t>(x);
+            }
+        } else if (i < n) {
+            out[i] = e0;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanTmaThreads)
+scan_tma_kernel(const T *__restrict__ in, int64_t n, int64_t *__restrict__ out, int64_t *__restrict__ total,
+                int32_t *__restrict__ status, LookbackWs *__restrict__ ws, uint32_t ntiles, bool out_aligned) {
+    constexpr int NW = kScanTmaThreads / kWarp;
+    __shared__ __align__(16) unsigned char s_raw[kScanTmaTile * sizeof(T) + 32];
+    __shared__ uint64_t s_bar;
+    __shared__ int64_t s_warp[NW + 1];
+    __shared__ int64_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const int64_t i0 = static_cast<int64_t>(tile) * kScanTmaTile;
+    const int64_t left = n - i0;
+    const int valid = left < kScanTmaTile ? static_cast<int>(left < 0 ? 0 : left) : kScanTmaTile;
+
+    stage_init(&s_bar, 1);
+    const T *sm = reinterpret_cast<const T *>(s_raw);
+    if (valid > 0) {
+        const uint32_t shift = stage_issue<sizeof(T)>(s_raw, reinterpret_cast<const unsigned char *>(in + i0),
+                                                      static_cast<uint32_t>(valid * sizeof(T)), &s_bar);
+        stage_wait(&s_bar, 0);
+        sm = reinterpret_cast<const T *>(s_raw + shift);
+    }
+    // phase A: warp sums + validity flags
+    const int wbase = warp * (kScanTmaItems * kWarp);
+    int64_t sum = 0;
+    bool neg = false, big = false;
+#pragma unroll 4
+    for (int r = 0; r < kScanTmaItems / 2; ++r) {
+        const int p = wbase + r * 64 + lane * 2;
+        const int64_t x = p < valid ? static_cast<int64_t>(sm[p]) : 0;
+        const int64_t y = p + 1 < valid ? static_cast<int64_t>(sm[p + 1]) : 0;
+        neg |= (x < 0) | (y < 0);
+        big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
+        sum += x + y;
+    }
+    if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
+    sum = warp_reduce_add(sum);
+    if (lane == 0) s_warp[warp] = sum;
+    const bool wide = __syncthreads_or(big);
+    if (warp == 0) {
+        int64_t w = lane < NW ? s_warp[lane] : 0;
+        int64_t wi = warp_incl_scan_add(w, lane);
+        const int64_t block_total = __shfl_sync(0xffffffffu, wi, NW - 1);
+        const int64_t tile_base = lookback_exclusive_warp<1>(ws->desc, tile, block_total);
+        if (lane < NW) s_warp[lane] = wi - w;
+        if (lane == 0) {
+            s_base = tile_base;
+            if (tile == ntiles - 1) {
+                out[n] = tile_base + block_total;
+                if (total) *total = tile_base + block_total;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t run = s_base + s_warp[warp];
+    if (wide) scan_tma_rows<T, int64_t>(sm, valid, wbase, lane, run, out, i0, n, out_aligned);
+    else scan_tma_rows<T, int32_t>(sm, valid, wbase, lane, run, out, i0, n, out_aligned);
+}
+
+template <typename T>
+int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws,
+                      size_t ws_bytes, cudaStream_t stream) {
+    const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, kScanTmaTile);
+    const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;
+    JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
+    JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
+    JG_REQUIRE(ntiles < (1ll << 31), "scan: too many tiles");
+    cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
+    if (e != cudaSuccess) {
+        set_error("scan: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(scan_tma_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
+    }
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    scan_tma_kernel<T><<<static_cast<unsigned>(ntiles), kScanTmaThreads, 0, stream>>>(
+        in, n, out, total, status, reinterpret_cast<LookbackWs *>(ws), static_cast<uint32_t>(ntiles), out_aligned);
+    return check_launch("scan_tma_kernel");
 }
 
 // Host launcher.  `out` has n+1 entries: out[i] = sum of items before i, out[n] = grand total.

@@ -1,56 +1,139 @@
 // jg_select.cu -- jagged __getitem__: boolean-mask compaction (jagged.py:562-589), integer gather
 // (jagged.py:541-560), plain take (jagged.py:1294) and the dense form of argmin/argmax results.
+#include <stdlib.h>
+
 #include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
 
 // ------------------------------------------------------------------------------------------------------------
-// a[jagged_bool] in ONE pass: per-event popcount -> block scan -> decoupled look-back across tiles ->
-// new offsets + compaction.  The tile's content run and mask run are staged with TMA bulk copies.
-// Algorithmic traffic: v*M + M + 8(N+1) read, v*K + 8(N+1) written.
+// a[jagged_bool]   (jagged.py:562-589)
+//
+// Three launches, none of which waits on another CTA (a single-pass decoupled look-back was measured first:
+// every tile ends up waiting ~6 us for the slowest of its predecessors, profiles/r1_lookback_study.md):
+//   1. mask_count_kernel : one WARP per event tile popcounts the tile's mask run (M bytes read) -> tile totals
+//   2. the look-back scan of jg_scan.cuh over the N/512 tile totals -> tile bases + grand total K (tiny)
+//   3. mask_fill_kernel  : the tile's content run and mask run are staged with TMA bulk copies (UBLKCP); the
+//      compaction is ELEMENT-parallel (a warp walks 32 consecutive positions: ballot + popc give each selected
+//      element its slot, so the global stores of a warp are consecutive); the per-event new offsets are read
+//      back from the on-chip per-position prefix.
+// Algorithmic traffic: v*M + M + 8(N+1) read, v*K + 8(N+1) written (the mask is read twice: +M actual).
 // ------------------------------------------------------------------------------------------------------------
-template <typename V, int STAGE_BYTES>
-__global__ void __launch_bounds__(kTileThreads)
-mask_select_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask, int64_t mask_shift,
-                   const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
-                   int64_t *__restrict__ new_offsets, int64_t *__restrict__ total, LookbackWs *__restrict__ ws,
-                   uint32_t ntiles) {
-    constexpr int kMaskBytes = STAGE_BYTES / sizeof(V);
-    __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_content[STAGE_BYTES + 32];
-    __shared__ __align__(16) unsigned char s_mask[kMaskBytes + 32];
-    __shared__ uint64_t s_bar[2];
-    __shared__ int32_t s_scan[kTileThreads / kWarp + 1];
-    __shared__ uint32_t s_tile;
-    __shared__ int64_t s_base;
+__device__ __forceinline__ int popcount_bytes16(int4 v) {
+    // bytes are 0/1 booleans (anything non-zero counts)
+    return __popc(__vcmpne4(v.x, 0) & 0x01010101u) + __popc(__vcmpne4(v.y, 0) & 0x01010101u) +
+           __popc(__vcmpne4(v.z, 0) & 0x01010101u) + __popc(__vcmpne4(v.w, 0) & 0x01010101u);
+}
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(&ws->ticket, 1u);
+constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
+
+__global__ void __launch_bounds__(kCountWarps * kWarp)
+mask_count_kernel(const uint8_t *__restrict__ mask, int64_t mask_shift, const int64_t *__restrict__ offsets,
+                  int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = static_cast<int64_t>(blockIdx.x) * kCountWarps + warp;
+    if (tile >= ntiles) return;
+    const int64_t ev0 = tile * kTileEvents;
+    const int64_t ev1 = min(n, ev0 + kTileEvents);
+    const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
+    const uint8_t *m = mask + e0 + mask_shift;
+    const int64_t len = e1 - e0;
+    int64_t cnt = 0;
+    // unaligned head, 16-byte body, tail
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    int64_t head = static_cast<int64_t>((16 - (addr & 15)) & 15);
+    if (head > len) head = len;
+    if (lane < head) cnt += (m[lane] != 0);
+    const int64_t nvec = (len - head) >> 4;
+    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
+    for (int64_t i = lane; i < nvec; i += kWarp) cnt += popcount_bytes16(__ldcs(mv + i));
+    const int64_t tail0 = head + (nvec << 4);
+    if (tail0 + lane < len) cnt += (m[tail0 + lane] != 0);
+    cnt = warp_reduce_add(cnt);
+    if (lane == 0) tile_totals[tile] = cnt;
+}
+
+template <typename V, int KM>     // KM = positions a tile may stage
+__global__ void __launch_bounds__(kTileThreads)
+mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask, int64_t mask_shift,
+                 const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
+                 int64_t *__restrict__ new_offsets, const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
+    constexpr int NW = kTileThreads / kWarp;
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
+    __shared__ __align__(16) unsigned char s_mask[KM + 32];
+    __shared__ uint16_t s_pfx[KM + 2];
+    __shared__ uint64_t s_bar[2];
+    __shared__ int32_t s_scan[NW + 1];
+
     stage_init(s_bar, 2);
-    const uint32_t tile_index = s_tile;
+    const uint32_t tile_index = blockIdx.x;
     EventTile tile;
     tile.load(s_off, offsets, n, tile_index);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t len = e1 - e0;
-    const bool staged = len > 0 && len <= kMaskBytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = __ldg(tile_bases + tile_index);
+    if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
 
-    const V *cv = content + e0;
-    const uint8_t *mv = mask + e0 + mask_shift;
-    if (staged) {
-        const uint32_t cs = stage_issue<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(cv),
-                                                   static_cast<uint32_t>(len * sizeof(V)), &s_bar[0]);
-        const uint32_t ms = stage_issue<1>(s_mask, mv, static_cast<uint32_t>(len), &s_bar[1]);
-        mbar_wait(&s_bar[0], 0);
-        mbar_wait(&s_bar[1], 0);
+    if (len <= KM) {
+        // ---------------- staged tile ----------------------------------------------------------------------
+        const int L = static_cast<int>(len);
+        const V *cv = nullptr;
+        const uint8_t *mv = nullptr;
+        if (L > 0) {
+            const uint32_t cs = stage_issue<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
+                                                       static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
+            const uint32_t ms = stage_issue<1>(s_mask, mask + e0 + mask_shift, static_cast<uint32_t>(L), &s_bar[1]);
+            mbar_wait(&s_bar[1], 0);
+            __syncthreads();
+            cv = reinterpret_cast<const V *>(s_content + cs);
+            mv = s_mask + ms;
+        }
+        // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
+        const int rows_total = (L + 31) >> 5;
+        const int rows_per_warp = (rows_total + NW - 1) / NW;
+        const int p_begin = min(L, warp * rows_per_warp * 32);
+        const int p_end = min(L, p_begin + rows_per_warp * 32);
+        // pass 1: selected per warp
+        int cnt = 0;
+        for (int p = p_begin + lane; p < p_end; p += 32) cnt += (mv[p] != 0);
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0) s_scan[warp] = cnt;
         __syncthreads();
-        cv = reinterpret_cast<const V *>(s_content + cs);
-        mv = s_mask + ms;
+        if (warp == 0) {
+            int w = lane < NW ? s_scan[lane] : 0;
+            int wi = warp_incl_scan_add(w, lane);
+            if (lane < NW) s_scan[lane] = wi - w;
+            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+        }
+        if (L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
+        __syncthreads();
+        // pass 2: compaction, consecutive lanes -> consecutive output slots
+        int run = s_scan[warp];
+        V *dst = out + base;
+        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+            const int p = p0 + lane;
+            const bool sel = p < p_end && mv[p] != 0;
+            const unsigned b = __ballot_sync(0xffffffffu, sel);
+            const int slot = run + __popc(b & ((1u << lane) - 1u));
+            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+            if (sel) dst[slot] = cv[p];
+            run += __popc(b);
+        }
+        __syncthreads();
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
+            new_offsets[tile.event0 + ev] = base + s_pfx[s_off[ev] - e0];
+        return;
     }
 
-    // thread t owns events 2t and 2t+1 (kTileEvents == 2 * kTileThreads)
-    const int ev0 = threadIdx.x * 2;
+    // ---------------- oversize tile (long events): straight from global memory ------------------------------
+    const V *cv = content + e0;
+    const uint8_t *mv = mask + e0 + mask_shift;
+    const int ev0 = threadIdx.x * 2;      // thread t owns events 2t and 2t+1
     int64_t a[2], b[2];
-    int32_t c[2] = {0, 0};
+    int64_t c[2] = {0, 0};
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int ev = ev0 + q;
@@ -58,25 +141,14 @@ mask_select_kernel(const V *__restrict__ content, const uint8_t *__restrict__ ma
         if (ev < tile.nev) {
             a[q] = s_off[ev] - e0;
             b[q] = s_off[ev + 1] - e0;
-            int32_t cnt = 0;
+            int64_t cnt = 0;
             for (int64_t j = a[q]; j < b[q]; ++j) cnt += (mv[j] != 0);
             c[q] = cnt;
         }
     }
-    int32_t block_total;
-    const int32_t excl = block_excl_scan<int32_t, kTileThreads>(c[0] + c[1], s_scan, block_total);
-    if (threadIdx.x < kWarp) {
-        const int64_t base = lookback_exclusive_warp(ws->desc, tile_index, block_total);
-        if (threadIdx.x == 0) {
-            s_base = base;
-            if (tile_index == ntiles - 1) {
-                new_offsets[n] = base + block_total;
-                if (total) *total = base + block_total;
-            }
-        }
-    }
-    __syncthreads();
-    const int64_t base = s_base;
+    __shared__ int64_t s_scan64[NW + 1];
+    int64_t block_total;
+    const int64_t excl = block_excl_scan<int64_t, kTileThreads>(c[0] + c[1], s_scan64, block_total);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int ev = ev0 + q;
@@ -159,22 +231,49 @@ static inline int flat_grid(int64_t work, int threads) {
     return static_cast<int>(blocks);
 }
 
-template <typename V, int STAGE>
+// workspace layout shared by the "tile totals -> tile bases" helpers: [totals: nt+1][bases: nt+1][scan ws]
+struct TileScanWs {
+    int64_t *totals;
+    int64_t *bases;
+    void *scan_ws;
+    size_t scan_ws_bytes;
+};
+
+static int carve_tile_ws(void *ws, size_t ws_bytes, int64_t ntiles, TileScanWs &o, const char *who) {
+    const size_t arr = (static_cast<size_t>(ntiles) + 2) * 8;
+    const size_t arr_al = (arr + 255) & ~static_cast<size_t>(255);
+    const size_t scan_need = sizeof(LookbackWs) + static_cast<size_t>(ceil_div(ntiles, kScanTile) + 1) * 8;
+    if (ws == nullptr || ws_bytes < 2 * arr_al + scan_need + 256) {
+        set_error("%s: workspace too small (%zu < %zu)", who, ws_bytes, 2 * arr_al + scan_need + 256);
+        return -2;
+    }
+    char *p = static_cast<char *>(ws);
+    o.totals = reinterpret_cast<int64_t *>(p);
+    o.bases = reinterpret_cast<int64_t *>(p + arr_al);
+    o.scan_ws = p + 2 * arr_al;
+    o.scan_ws_bytes = ws_bytes - 2 * arr_al;
+    return 0;
+}
+
+template <typename V, int KM>
 static int launch_mask_select(const void *content, const uint8_t *mask, int64_t mask_shift, const int64_t *offsets,
                               int64_t n, void *out, int64_t *new_offsets, int64_t *total, void *ws, size_t ws_bytes,
                               cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
-    const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;
-    JG_REQUIRE(ws != nullptr && ws_bytes >= need, "jg_mask_select: workspace too small (%zu < %zu)", ws_bytes, need);
-    cudaError_t e = cudaMemsetAsync(ws, 0, need, s);
-    if (e != cudaSuccess) {
-        set_error("jg_mask_select: cudaMemsetAsync: %s", cudaGetErrorString(e));
-        return -1;
-    }
-    mask_select_kernel<V, STAGE><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
-        static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets, total,
-        reinterpret_cast<LookbackWs *>(ws), static_cast<uint32_t>(ntiles));
-    return check_launch("mask_select_kernel");
+    TileScanWs t;
+    int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
+    if (rc) return rc;
+    mask_count_kernel<<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
+        mask, mask_shift, offsets, n, ntiles, t.totals);
+    rc = check_launch("mask_count_kernel");
+    if (rc) return rc;
+    ScanInArray<int64_t> in{t.totals, true};
+    rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
+    if (rc) return rc;
+    mask_fill_kernel<V, KM><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+        static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets, t.bases,
+        static_cast<uint32_t>(ntiles));
+    return check_launch("mask_fill_kernel");
 }
 
 template <typename V>
@@ -207,10 +306,10 @@ int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64
     JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
     cudaStream_t s = as_stream(stream);
     switch (itemsize) {
-        case 1: return launch_mask_select<uint8_t, 8192>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 2: return launch_mask_select<uint16_t, 8192>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 4: return launch_mask_select<uint32_t, 16384>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 8: return launch_mask_select<uint64_t, 32768>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
+        case 1: return launch_mask_select<uint8_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
+        case 2: return launch_mask_select<uint16_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
+        case 4: return launch_mask_select<uint32_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
+        case 8: return launch_mask_select<uint64_t, 3584>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
     }
     set_error("jg_mask_select: unsupported itemsize %d", itemsize);
     return -2;

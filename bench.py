@@ -269,7 +269,7 @@ def run_gpu(args):
     peaks = load_peaks()
     roof = None
     if ops:
-        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_f32", "compact_nonneg", "greater_f32", "mask_select_f32", "offsets2counts"]
+        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "greater_f32", "mask_select_f32", "offsets2counts"]
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
         roof = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peaks[0], "unit": "GB/s",
                 "frac": ops[dom]["gbs"] / peaks[0], "traffic": None, "peak_source": peaks[1],
@@ -367,6 +367,9 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     add("segargmax_f32", v * M + 8 * N + 8 * N, M, lambda: _lib.call(
         "jg_segargminmax", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(best), ctypes.c_void_p(0), st()))
     aoff, aidx = empty(N + 1, np.int64), empty(N, np.int64)
+    add("segargmax_dense_f32", v * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_segargminmax_dense", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(aoff), _vp(aidx), _vp(scal),
+        ws, wsb, st()))
     add("compact_nonneg", 8 * N + 8 * N + 8 * N, N, lambda: _lib.call(
         "jg_compact_nonneg", _vp(best), N, _vp(aoff), _vp(aidx), _vp(scal), ws, wsb, st()))
     mask = empty(M, np.bool_)

@@ -129,6 +129,11 @@ int jg_segreduce(const void *content, int dtype, const int64_t *offsets, int64_t
  * or -1 for an event with none.  Optionally also writes the extreme value itself (same dtype as content).        */
 int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
                     int64_t *best, void *best_value, void *stream);
+/* the same, fused with the compaction below: one pass from content to the dense result
+ * out_offsets[n+1] (scanned 0/1 counts), out_index[<= n] (allocate n), *total = number of events with a result. */
+int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                          int64_t *out_offsets, int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes,
+                          void *stream);
 /* turn best[] into the dense result: out_offsets[n+1] (0/1 counts scanned) and out_index[<=n]; *total = count.   */
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
                       void *ws, size_t ws_bytes, void *stream);

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Launch every hot-path kernel a few times on a 20 M-event shard (Poisson(5), f32): the command ncu profiles.
+
+    python profiles/prof_kernels.py [nevents]
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "awkward-0.x_b200")):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import awkward0_b200 as ak  # noqa: E402
+from awkward0_b200 import _lib  # noqa: E402
+from awkward0_b200.device import empty, runtime  # noqa: E402
+from awkward0_b200.jagged import _vp  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+rng = np.random.default_rng(1)
+counts = rng.poisson(5.0, N).astype(np.int64)
+M = int(counts.sum())
+pt = (rng.standard_exponential(M, dtype=np.float32) * np.float32(25.0))
+counts_d, pt_d = ak.asdevice(counts), ak.asdevice(pt)
+a = ak.JaggedArray.fromcounts(counts_d, pt_d)
+off = a._off64
+st = runtime.stream
+ws, wsb = runtime.workspace(N)
+scal = runtime.scalars()
+out_off = empty(N + 1, np.int64)
+f32 = empty(N, np.float32)
+i64a, i64b = empty(N + 1, np.int64), empty(N, np.int64)
+mask = empty(M, np.bool_)
+sel = empty(M, np.float32)
+par = empty(M, np.int64)
+for rep in range(3):
+    _lib.call("jg_counts2offsets", counts_d.data_ptr(), _lib.JG_I64, N, _vp(out_off), _vp(scal), _vp(scal, 1), ws, wsb, st())
+    _lib.call("jg_segreduce", pt_d.data_ptr(), _lib.JG_F32, off.data_ptr(), N, _lib.SUM, _vp(f32), M, st())
+    _lib.call("jg_segreduce", pt_d.data_ptr(), _lib.JG_F32, off.data_ptr(), N, _lib.MAX, _vp(f32), M, st())
+    _lib.call("jg_segargminmax_dense", pt_d.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(i64a), _vp(i64b), _vp(scal), ws, wsb, st())
+    _lib.call("jg_binary", _lib.OP["GT"], pt_d.data_ptr(), _lib.JG_F32, ctypes.c_void_p(0), 0, _lib.RHS_SCALAR,
+              ctypes.c_double(20.0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(mask), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st())
+    _lib.call("jg_mask_select", pt_d.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(i64a), _vp(scal), ws, wsb, st())
+    _lib.call("jg_offsets2counts", off.data_ptr(), N, _vp(i64b), st())
+    _lib.call("jg_offsets2parents", off.data_ptr(), N, _vp(par), st())
+    _lib.call("jg_broadcast", _vp(f32), 4, off.data_ptr(), N, _vp(sel), st())
+torch.cuda.synchronize()
+print("ok", N, M)
