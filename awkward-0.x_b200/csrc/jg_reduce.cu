@@ -60,6 +60,14 @@ struct Red {
         if constexpr (OP == JG_ANY || OP == JG_ALL) return A(x != T(0));
         else return static_cast<A>(x);
     }
+    // acc (earlier elements) followed by the raw content value x: combine(acc, lift(x)) in fewer instructions.
+    // For float min/max a single ordered comparison does both jobs: it is false for NaN (NaN is skipped, i.e.
+    // replaced by the identity) and true on equality (the later element wins, like numpy's loops).
+    __device__ static __forceinline__ A accumulate(A acc, T x) {
+        if constexpr (OP == JG_MIN && IsFloat<T>::value && sizeof(A) == sizeof(T)) return (static_cast<A>(x) <= acc) ? static_cast<A>(x) : acc;
+        else if constexpr (OP == JG_MAX && IsFloat<T>::value && sizeof(A) == sizeof(T)) return (static_cast<A>(x) >= acc) ? static_cast<A>(x) : acc;
+        else return combine(acc, lift(x));
+    }
     // acc (earlier elements) combined with x (a later element)
     __device__ static __forceinline__ A combine(A acc, A x) {
         if constexpr (OP == JG_SUM) return acc + x;
@@ -168,7 +176,10 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
                 A acc = R::identity();
                 if (b > a) {
                     acc = R::lift(sm[a]);
-                    for (int j = a + 1; j < b; ++j) acc = R::combine(acc, R::lift(sm[j]));
+                    // not unrolled on purpose: events are short (mean 5) and of different length per lane; an
+                    // unrolled loop with 8/4/2/1 remainder cascades makes a divergent warp execute every branch
+#pragma unroll 1
+                    for (int j = a + 1; j < b; ++j) acc = R::accumulate(acc, sm[j]);
                 }
                 out[tile.event0 + ev] = acc;
             }
@@ -284,10 +295,12 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
             const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
             int idx = -1;
             T bv = T(0);
+#pragma unroll 1
             for (int j = a; j < b; ++j) {
                 const T x = sm[j];
-                if (is_nan(x)) continue;
-                if (idx < 0 || (ISMIN ? (x < bv) : (x > bv))) {
+                // (x better than bv) is false for NaN; the first non-NaN value is always taken
+                const bool take = (ISMIN ? (x < bv) : (x > bv)) || (idx < 0 && !is_nan(x));
+                if (take) {
                     bv = x;
                     idx = j - a;
                 }

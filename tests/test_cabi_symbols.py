@@ -1,0 +1,56 @@
+"""not gpu: the C-ABI library loads and exports every symbol include/jagged_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "jagged_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_something():
+    names = declared_symbols()
+    assert len(names) >= 25 and "jg_counts2offsets" in names and "jg_mask_select" in names
+
+
+def test_library_exports_every_declared_symbol():
+    from awkward0_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header():
+    from awkward0_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == declared_symbols()
+
+
+def test_version_and_workspace_query_without_gpu():
+    from awkward0_b200 import _lib
+    assert _lib.lib.jg_version() >= 100
+    a, b = _lib.lib.jg_workspace_bytes(0), _lib.lib.jg_workspace_bytes(10**9)
+    assert 0 < a < b
+    assert isinstance(_lib.lib.jg_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import awkward0_b200 as ak
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ak.JaggedArray.fromcounts([1, 2], [1.0, 2.0, 3.0])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "awkward-0.x_b200")
+    pattern = re.compile(r"^\s*(from|import)\s+.*oracle", re.M)
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pattern.search(open(os.path.join(base, f)).read()), (base, f)

@@ -1,0 +1,282 @@
+"""-m gpu: the reference's own test cases (tests/test_jagged.py, tests/test_issues.py) and its exception contract
+ run against the CUDA JaggedArray, plus layouts and record content."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ak():
+    import awkward0_b200
+    return awkward0_b200
+
+
+CONTENT = [0.0, 1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9]
+
+
+def std(ak):
+    return ak.JaggedArray([0, 3, 3, 5], [3, 3, 5, 10], CONTENT)
+
+
+# ---- tests/test_jagged.py -----------------------------------------------------------------------------------
+def test_init_and_constructors(ak):        # test_jagged.py:20-38
+    J = ak.JaggedArray
+    want = [[0.0, 1.1, 2.2], [], [3.3, 4.4], [5.5, 6.6, 7.7, 8.8, 9.9]]
+    assert std(ak).tolist() == want
+    assert J.fromiter(want).tolist() == want
+    assert J.fromoffsets([0, 3, 3, 5, 10], CONTENT).tolist() == want
+    assert J.fromcounts([3, 0, 2, 5], CONTENT).tolist() == want
+    a = J([], [], [0.0, 1.1, 2.2, 3.3, 4.4])
+    assert a[:].tolist() == [] and len(a) == 0
+    assert isinstance(std(ak).nbytes, int)
+
+
+def test_introspection(ak):
+    a = ak.JaggedArray.fromcounts([3, 0, 2], np.arange(5, dtype=np.float32))
+    assert len(a) == 3 and a.shape == (3,) and a.ndim == 1 and a.dtype == np.dtype(object)
+    assert str(a.type) == "[0, 3) -> [0, inf) -> float32"
+    assert a.nbytes == 4 * 8 + 5 * 4
+    assert a.valid() is True
+    assert str(a) == "[[0.0, 1.0, 2.0] [] [3.0, 4.0]]"
+
+
+def test_tojagged(ak):                     # test_jagged.py:56-64
+    J = ak.JaggedArray
+    a = J.fromiter([[1], [2, 3], []])
+    assert a.tojagged(a).tolist() == a.tolist()
+    assert a.tojagged(np.array([3, 4, 5]) + 1).tolist() == [[4], [5, 5], []]
+    b = J.fromiter([[], []])
+    assert b.tojagged(b).tolist() == b.tolist()
+    assert a.tojagged(7).tolist() == [[7], [7, 7], []]
+
+
+def test_ufunc(ak):                        # test_jagged.py:151-154
+    a = std(ak)
+    assert (100 + a).tolist() == [[100.0, 101.1, 102.2], [], [103.3, 104.4], [105.5, 106.6, 107.7, 108.8, 109.9]]
+    assert (np.array([100, 200, 300, 400]) + a).tolist() == [[100.0, 101.1, 102.2], [], [303.3, 304.4], [405.5, 406.6, 407.7, 408.8, 409.9]]
+    assert (a + a).tolist() == [[0.0, 2.2, 4.4], [], [6.6, 8.8], [11.0, 13.2, 15.4, 17.6, 19.8]]
+    assert np.sqrt(a).content.get().tolist() == np.sqrt(np.array(CONTENT)).tolist()
+    assert (-a).tolist()[2] == [-3.3, -4.4]
+    assert ((a > 2) & (a < 8)).tolist() == [[False, False, True], [], [True, True], [True, True, True, False, False]]
+    assert (~(a > 2)).tolist()[0] == [True, True, False]
+
+
+def test_ufunc_dtypes_follow_numpy(ak):
+    f32 = ak.JaggedArray.fromcounts([2, 1], np.array([1, 2, 3], dtype=np.float32))
+    i32 = ak.JaggedArray.fromcounts([2, 1], np.array([1, 2, 3], dtype=np.int32))
+    assert (f32 + 1).content.dtype == np.float32 and (f32 + 1.5).content.dtype == np.float32
+    assert (f32 + np.float64(1)).content.dtype == np.float64
+    assert (f32 > 20).content.dtype == np.bool_
+    assert (i32 + 1).content.dtype == np.int32 and (i32 + 1.5).content.dtype == np.float64
+    assert (i32 / i32).content.dtype == np.float64 and (i32 // 2).content.get().tolist() == [0, 1, 1]
+    assert (i32 % 2).content.get().tolist() == [1, 0, 1] and (i32 ** 2).content.get().tolist() == [1, 4, 9]
+    assert (f32 * np.array([10.0, 100.0], dtype=np.float32)).content.get().tolist() == [10.0, 20.0, 300.0]
+
+
+def test_pairs_cross_distincts_loops(ak):  # test_jagged.py:214-252
+    J = ak.JaggedArray
+    for i in (0, 1, 2, 3, 7, 20, 49):
+        a = J.fromiter([[], [123], list(range(i)), []])
+        c = a.pairs()
+        assert c.counts.tolist() == [0, 1, i * (i + 1) // 2, 0]
+        left = sum([[x] * (i - x) for x in range(i)], [])
+        right = sum([list(range(x, i)) for x in range(i)], [])
+        lo, hi = int(c.offsets[2]), int(c.offsets[3])
+        assert c.i0.content[lo:hi].tolist() == left and c.i1.content[lo:hi].tolist() == right
+        d = a.distincts()
+        lo, hi = int(d.offsets[2]), int(d.offsets[3])
+        assert d.counts.tolist() == [0, 0, i * (i - 1) // 2, 0]
+        assert d.i0.content[lo:hi].tolist() == [x for x, y in zip(left, right) if x != y]
+        assert d.i1.content[lo:hi].tolist() == [y for x, y in zip(left, right) if x != y]
+    for i in (0, 1, 4, 9):
+        for j in (0, 1, 4):
+            a = J.fromiter([[], [123], list(range(i)), []])
+            b = J.fromiter([[], [456], list(range(j)), [999]])
+            c = a.cross(b)
+            assert c.counts.tolist() == [0, 1, i * j, 0]
+            lo, hi = int(c.offsets[2]), int(c.offsets[3])
+            assert c.i0.content[lo:hi].tolist() == np.repeat(range(i), j).tolist()
+            assert c.i1.content[lo:hi].tolist() == np.tile(range(j), i).tolist()
+
+
+def test_argchoose_colex(ak):              # test_jagged.py:254-338
+    import itertools
+    for k in (2, 3, 4, 5):
+        for n in (0, 1, 4, 5, 6, 9, 13):
+            a = ak.JaggedArray.fromiter([[], [1234], list(range(n)), []])
+            c = a.argchoose(k)
+            want = sorted(itertools.combinations(range(n), k), key=lambda t: tuple(reversed(t)))
+            assert c.tolist()[2] == want, (k, n)
+            assert c.tolist()[0] == [] and c.tolist()[1] == []
+    big = ak.JaggedArray.fromcounts([300], np.arange(300))
+    got = big.argchoose(3)
+    assert len(got.content) == 300 * 299 * 298 // 6
+    assert got.tolist()[0][-1] == (297, 298, 299)
+
+
+def test_pairs_tolist_and_choose_values(ak):
+    a = ak.JaggedArray.fromiter([[1.1, 2.2, 3.3], [], [4.4, 5.5]])
+    assert a.argdistincts().tolist() == [[(0, 1), (0, 2), (1, 2)], [], [(0, 1)]]
+    assert a.distincts().tolist() == [[(1.1, 2.2), (1.1, 3.3), (2.2, 3.3)], [], [(4.4, 5.5)]]
+    assert a.choose(2).tolist() == [[(1.1, 2.2), (1.1, 3.3), (2.2, 3.3)], [], [(4.4, 5.5)]]
+    assert a.pairs().tolist()[2] == [(4.4, 4.4), (4.4, 5.5), (5.5, 5.5)]
+
+
+def test_reducers_literals(ak):            # test_jagged.py:384-449
+    a = std(ak)
+    assert a.sum().tolist() == [3.3000000000000003, 0.0, 7.7, 38.5]
+    assert a.prod().tolist() == [0.0, 1.0, 14.52, 24350.911200000002]
+    assert a.min().tolist() == [0.0, np.inf, 3.3, 5.5]
+    assert a.max().tolist() == [2.2, -np.inf, 4.4, 9.9]
+    assert a.argmin().tolist() == [[0], [], [0], [0]]
+    assert a.argmax().tolist() == [[2], [], [1], [4]]
+    assert a.any().tolist() == [True, False, True, True] and a.all().tolist() == [False, True, True, True]
+
+
+def test_boolean_indexing(ak):             # test_jagged.py:583-590
+    J = ak.JaggedArray
+    array1, array2 = J.fromcounts([1], [0]), J.fromcounts([1], [0, 1])
+    indices1, indices2 = J.fromcounts([1], [True]), J.fromcounts([1], [True, False])
+    assert array1[indices1].tolist() == array1[indices2].tolist() == array2[indices1].tolist() == array2[indices2].tolist() == [[0]]
+
+
+def test_localindex_parents(ak):           # test_jagged.py:592-602
+    a = ak.JaggedArray.fromiter([[1.1, 2.2, 3.3, 4.4, 5.5], [], [6.6, 7.7, 8.8], [9.9]])
+    assert a.localindex.tolist() == [[0, 1, 2, 3, 4], [], [0, 1, 2], [0]]
+    assert a.parents.tolist() == [0, 0, 0, 0, 0, 2, 2, 2, 3]
+    b = ak.JaggedArray([5, 8], [5, 9], a.content)      # a[[False, True, False, True]]
+    assert b.localindex.tolist() == [[], [0]]
+    assert b.parents.tolist() == [-1, -1, -1, -1, -1, -1, -1, -1, 1]
+    assert b.tolist() == [[], [9.9]] and b.sum().tolist() == [0.0, 9.9]
+
+
+def test_issues(ak):                       # tests/test_issues.py:16-30
+    a = ak.JaggedArray.fromoffsets([2, 4, 4, 7], np.arange(10, dtype=np.float64))
+    assert a[a > 3].tolist() == [[], [], [4.0, 5.0, 6.0]]
+    assert a[a > 3].sum().tolist() == [0.0, 0.0, 15.0]
+    assert a[a > 100][1:].tolist() == [[], []]
+    assert a.flatten().tolist() == [2.0, 3.0, 4.0, 5.0, 6.0]
+    assert (a + np.array([10.0, 20.0, 30.0])).tolist() == [[12.0, 13.0], [], [34.0, 35.0, 36.0]]
+    assert a.pairs().tolist()[0] == [(2.0, 2.0), (2.0, 3.0), (3.0, 3.0)]
+
+
+def test_noncompact_layout(ak):            # test_jagged.py:499-502 style: starts/stops that are not dense
+    content = np.arange(12, dtype=np.float64)
+    a = ak.JaggedArray([0, 3, 7, 10], [3, 6, 10, 12], content)     # element 6 is skipped
+    assert a.tolist() == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0], [7.0, 8.0, 9.0], [10.0, 11.0]]
+    with pytest.raises(ValueError, match="starts and stops are not compatible with a single offsets array"):
+        a.offsets
+    assert a.iscompact is False
+    assert a.sum().tolist() == [3.0, 12.0, 24.0, 21.0]
+    assert a.counts.tolist() == [3, 3, 3, 2]
+    assert a.compact().offsets.tolist() == [0, 3, 6, 9, 11]
+    assert a.flatten().tolist() == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 7.0, 8.0, 9.0, 10.0, 11.0]
+    assert a[a > 4].tolist() == [[], [5.0], [7.0, 8.0, 9.0], [10.0, 11.0]]
+    assert a.argmax().tolist() == [[2], [2], [2], [1]]
+    rev = ak.JaggedArray([3, 0], [5, 3], content)                   # out-of-order events
+    assert rev.tolist() == [[3.0, 4.0], [0.0, 1.0, 2.0]] and rev.max().tolist() == [4.0, 2.0]
+
+
+def test_index_dtype_policy(ak):
+    a = ak.JaggedArray.fromoffsets(np.array([0, 2, 2, 5], dtype=np.int32), np.arange(5, dtype=np.float32))
+    assert a.offsets.dtype == np.int32 and a.counts.dtype == np.int32 and a.starts.dtype == np.int32
+    assert a.parents.dtype == np.int64 and a.localindex.content.dtype == np.int64
+    assert a.argmax().content.dtype == np.int64 and a.pairs().offsets.dtype == np.int64
+    assert a[a > 0].offsets.dtype == np.int64
+    assert a.sum().tolist() == [1.0, 0.0, 9.0]
+    c32 = ak.JaggedArray.fromcounts(np.array([2, 0, 3], dtype=np.int32), np.arange(5))
+    assert c32.offsets.dtype == np.int64 and c32.tolist() == [[0, 1], [], [2, 3, 4]]
+
+
+def test_records_zip_pairs(ak):            # BASELINE configs[3]: dimuon records
+    J = ak.JaggedArray
+    counts = [2, 0, 3]
+    pt = J.fromcounts(counts, np.array([10.0, 20.0, 30.0, 40.0, 50.0], dtype=np.float32))
+    eta = J.fromcounts(counts, np.array([0.1, 0.2, 0.3, 0.4, 0.5], dtype=np.float32))
+    mu = J.zip(pt=pt, eta=eta)
+    assert mu.columns == ["pt", "eta"] and mu.pt.tolist() == pt.tolist()
+    p = mu.distincts()
+    assert p.counts.tolist() == [1, 0, 3]
+    assert p.i0.pt.tolist() == [[10.0], [], [30.0, 30.0, 40.0]] and p.i1.pt.tolist() == [[20.0], [], [40.0, 50.0, 50.0]]
+    m = np.sqrt(2 * p.i0.pt * p.i1.pt * (np.cosh(p.i0.eta - p.i1.eta) - 1))
+    want = np.sqrt(2 * np.float32(10) * np.float32(20) * (np.cosh(np.float32(0.1) - np.float32(0.2)) - 1))
+    assert np.isclose(m.tolist()[0][0], want, rtol=1e-4)
+    el = J.zip(pt=J.fromcounts([1, 1, 0], np.array([5.0, 6.0], dtype=np.float32)))
+    x = mu.cross(el)
+    assert x.counts.tolist() == [2, 0, 0] and x.i0.pt.tolist()[0] == [10.0, 20.0] and x.i1.pt.tolist()[0] == [5.0, 5.0]
+    assert mu[mu.pt > 25].pt.tolist() == [[], [], [30.0, 40.0, 50.0]]
+    assert mu.sum()["pt"].tolist() == [30.0, 0.0, 120.0]
+
+
+def test_device_array_surface(ak):
+    a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
+    s = a.sum()
+    assert isinstance(s, ak.DeviceArray) and s.dtype == np.float32 and len(s) == 3
+    assert float(s.sum()) == 10.0 and float(s.max()) == 9.0 and float(s.min()) == 0.0
+    assert (s > 0).tolist() == [True, False, True] and bool((s >= 0).all()) and bool((s > 5).any())
+    assert (s * 2 + 1).tolist() == [3.0, 1.0, 19.0]
+    assert np.asarray(s).tolist() == [1.0, 0.0, 9.0]
+    assert a.counts[1] == 0 and a.counts[-1] == 3
+    assert a.content[a.argmax().content].tolist() == [1.0, 2.0]      # integer-array indexing on the device
+
+
+# ---- exception contract ------------------------------------------------------------------
+def test_exceptions(ak):
+    J = ak.JaggedArray
+    a = std(ak)
+    with pytest.raises(TypeError, match="counts must have integer dtype"):
+        J.fromcounts(np.array([1.0, 2.0]), [1, 2, 3])
+    with pytest.raises(ValueError, match="counts must be a non-negative array"):
+        J.fromcounts([1, -1], [1, 2, 3])
+    with pytest.raises(ValueError, match="offsets must be monatonically increasing"):
+        J.fromoffsets([0, 3, 2], CONTENT).sum()
+    with pytest.raises(ValueError, match=r"maximum offset 12 is beyond the length of the content \(10\)"):
+        J.fromoffsets([0, 3, 12], CONTENT).sum()
+    with pytest.raises(ValueError, match="cannot fit contents of JaggedArray into the given starts and stops arrays"):
+        a[J.fromcounts([2, 1, 2, 5], np.ones(10, dtype=bool))]
+    with pytest.raises(ValueError, match="jagged array used as index has a different shape"):
+        a[J.fromcounts([1], [0])]
+    with pytest.raises(IndexError, match="jagged array used as index contains out-of-bounds values"):
+        a[J.fromcounts([1, 0, 0, 0], [3])]
+    with pytest.raises(TypeError, match=r"jagged index must be boolean \(mask\) or integer \(fancy indexing\)"):
+        a[J.fromcounts([1, 0, 0, 0], [0.5])]
+    with pytest.raises(ValueError, match=r"cannot broadcast JaggedArray of shape \(4,\) with array of shape \(2,\)"):
+        a + np.array([1.0, 2.0])
+    with pytest.raises(NotImplementedError, match="in-place operations not supported"):
+        np.add(a, a, out=a)
+    with pytest.raises(TypeError):
+        np.add.reduce(a)
+    with pytest.raises(TypeError, match="both arrays must be JaggedArrays"):
+        a.cross(np.arange(4))
+    with pytest.raises(ValueError, match="both JaggedArrays must have the same length"):
+        a.cross(J.fromcounts([1], [1.0]))
+    with pytest.raises(ValueError, match="Choosing 0 or 1 items is trivial"):
+        a.argchoose(1)
+    with pytest.raises(NotImplementedError):
+        a.argchoose(6)
+    with pytest.raises(ValueError, match="offsets must be a non-negative array"):
+        J.fromoffsets([-1, 3], CONTENT)
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        a.argsort()
+    assert J.fromoffsets([0, 3, 2], CONTENT).valid() is False
+    ok = a[J.fromcounts([2, 0, 1, 1], [-1, 0, 1, -5])]       # negative wrap (jagged.py:552-553)
+    assert ok.tolist() == [[2.2, 0.0], [], [4.4], [5.5]]
+
+
+def test_switches(ak):
+    J = ak.JaggedArray
+
+    class Unchecked(J):
+        check_whole_valid = False
+
+    b = Unchecked.fromoffsets([0, 2, 5], np.arange(5, dtype=np.float32))
+    assert b.sum().tolist() == [1.0, 9.0]
+
+    class NoHost(J):
+        allow_tonumpy = False
+
+    c = NoHost.fromcounts([1, 1], [1.0, 2.0])
+    with pytest.raises(RuntimeError, match="allow_tonumpy is False"):
+        c.tolist()
+    assert c.sum().tolist() == [1.0, 2.0]          # flat results are plain DeviceArrays

@@ -1,0 +1,178 @@
+"""-m gpu: differential tests CUDA-vs-oracle on seeded random inputs (sizes the numpy oracle finishes in seconds)
+and size-independent properties at BASELINE.json's full sizes (100 M events)."""
+import numpy as np
+import pytest
+
+from conftest import same
+from oracle import jagged_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+@pytest.fixture(scope="module")
+def ak():
+    import awkward0_b200
+    return awkward0_b200
+
+
+def make_counts(kind, n, rng):
+    if kind == "poisson5":
+        return rng.poisson(5.0, n).astype(np.int64)
+    if kind == "poisson40":
+        return rng.poisson(40.0, n).astype(np.int64)
+    if kind == "geometric":                      # heavy tail: mostly short, a few long events
+        c = rng.geometric(0.2, n).astype(np.int64) - 1
+        c[rng.integers(0, n, 5)] = rng.integers(5000, 70000, 5)
+        return c
+    if kind == "sparse":                         # mostly empty
+        return (rng.random(n) < 0.05).astype(np.int64) * rng.integers(1, 4, n)
+    raise ValueError(kind)
+
+
+CASES = [("poisson5", 300000, np.float32), ("poisson5", 300000, np.float64), ("poisson40", 20000, np.float32),
+         ("geometric", 20000, np.float64), ("sparse", 100000, np.float32), ("poisson5", 1000, np.int32),
+         ("geometric", 3000, np.int64)]
+
+
+@pytest.mark.parametrize("kind,n,dtype", CASES)
+def test_differential(ak, kind, n, dtype):
+    rng = np.random.default_rng(hash((kind, n, np.dtype(dtype).name)) % (2**32))
+    counts = make_counts(kind, n, rng)
+    m = int(counts.sum())
+    if np.dtype(dtype).kind == "f":
+        content = rng.exponential(25.0, m).astype(dtype)
+        content[rng.random(m) < 0.01] = np.nan
+    else:
+        content = rng.integers(-1000, 1000, m).astype(dtype)
+    off = O.counts2offsets(counts)
+    a = ak.JaggedArray.fromcounts(counts, content)
+    assert same(a.offsets.get(), off)
+    assert same(a.parents.get(), O.offsets2parents(off))
+    assert same(a.localindex.content.get(), O.localindex(off)[1])
+    with np.errstate(all="ignore"):
+        for op in ("min", "max", "any", "all"):
+            assert same(getattr(a, op)().get(), O.reduce(off, content, op)), op
+        for op in ("sum", "prod"):
+            got, want = getattr(a, op)().get(), O.reduce(off, content, op)
+            assert got.dtype == want.dtype
+            if want.dtype.kind == "f":
+                if op == "sum":
+                    assert np.allclose(got, want, rtol=RTOL[want.dtype] * 4, atol=0, equal_nan=True)
+                else:
+                    fin = np.isfinite(want) & (np.abs(want) > 1e-300) & (np.abs(want) < 1e300)
+                    assert np.allclose(got[fin], want[fin], rtol=RTOL[want.dtype] * 64, atol=0)
+            else:
+                assert same(got, want), op
+        for ismin in (True, False):
+            roff, ridx = O.argminmax(off, content, ismin)
+            r = a.argmin() if ismin else a.argmax()
+            assert same(r.offsets.get(), roff) and same(r.content.get(), ridx)
+    thr = 20 if np.dtype(dtype).kind == "f" else 0
+    moff, mask = O.ufunc_broadcast(np.greater, off, content, thr)
+    gm = a > thr
+    assert same(gm.content.get(), mask)
+    soff, sel = O.mask_select(off, content, moff, mask)
+    gs = a[gm]
+    assert same(gs.offsets.get(), soff) and same(gs.content.get(), sel)
+    flat = rng.normal(size=n).astype(dtype if np.dtype(dtype).kind == "f" else np.float64)
+    with np.errstate(all="ignore"):
+        _, plus = O.ufunc_broadcast(np.add, off, content, flat)
+    assert same((a + flat).content.get(), plus)
+    assert same(a.tojagged(flat).content.get(), O.tojagged_flat(off, flat))
+    lead = a[a.argmax()]
+    roff, ridx = O.argminmax(off, content, False)
+    goff, gval = O.index_gather(off, content, roff, ridx)
+    assert same(lead.offsets.get(), goff) and same(lead.content.get(), gval)
+
+
+@pytest.mark.parametrize("mean,n", [(2.0, 200000), (5.0, 40000), (12.0, 3000)])
+def test_differential_combinatorics(ak, mean, n):
+    rng = np.random.default_rng(int(mean * 1000) + n)
+    ca, cb = rng.poisson(mean, n).astype(np.int64), rng.poisson(2.0, n).astype(np.int64)
+    xa = rng.exponential(20.0, int(ca.sum())).astype(np.float32)
+    xb = rng.integers(0, 1000, int(cb.sum())).astype(np.int64)
+    oa, ob = O.counts2offsets(ca), O.counts2offsets(cb)
+    a, b = ak.JaggedArray.fromcounts(ca, xa), ak.JaggedArray.fromcounts(cb, xb)
+    for name, fn in (("argpairs", O.argpairs), ("argdistincts", O.argdistincts)):
+        want = fn(oa)
+        got = getattr(a, name)()
+        assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+    for name, fn in (("pairs", O.pairs), ("distincts", O.distincts)):
+        want = fn(oa, xa)
+        got = getattr(a, name)()
+        assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+    for k in (2, 3):
+        want = O.argchoose(oa, k)
+        got = a.argchoose(k)
+        assert same(got.offsets.get(), want[0])
+        for c in range(k):
+            assert same(got[str(c)].content.get(), want[1 + c])
+    want = O.argcross(oa, ob)
+    got = a.argcross(b)
+    assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+    want = O.cross(oa, xa, ob, xb)
+    got = a.cross(b)
+    assert same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+
+
+def test_edge_layouts(ak):
+    J = ak.JaggedArray
+    e = J.fromcounts(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32))
+    assert len(e) == 0 and e.sum().tolist() == [] and e.argmax().tolist() == [] and e[e > 1].tolist() == []
+    assert e.pairs().tolist() == [] and e.counts.tolist() == [] and e.offsets.tolist() == [0]
+    z = J.fromcounts(np.zeros(1000, dtype=np.int64), np.zeros(0, dtype=np.float64))
+    assert z.sum().tolist() == [0.0] * 1000 and z.max().tolist() == [-np.inf] * 1000
+    assert z.argmax().counts.tolist() == [0] * 1000 and z[z > 0].offsets.tolist() == [0] * 1001
+    big = J.fromcounts([0, 1 << 24, 3], np.ones((1 << 24) + 3, dtype=np.float32))     # one huge event
+    assert big.sum().tolist() == [0.0, float(1 << 24), 3.0]
+    assert big.argmax().tolist() == [[], [0], [0]] and big.counts.tolist() == [0, 1 << 24, 3]
+    assert big[big > 0].counts.tolist() == [0, 1 << 24, 3]
+    assert int(big.parents[(1 << 24) - 1]) == 1 and int(big.parents[(1 << 24)]) == 2
+    nan = J.fromcounts([2, 1], np.array([np.nan, np.nan, 1.0], dtype=np.float32))
+    assert nan.argmax().tolist() == [[], [0]] and nan.sum().tolist() == [0.0, 1.0] and nan.max().tolist() == [-np.inf, 1.0]
+
+
+def test_properties_at_full_size(ak):
+    """BASELINE.json configs[1]/[2] size: 100 M events.  No oracle here -- only size-independent invariants."""
+    n = 100_000_000
+    rng = np.random.default_rng(12345)
+    counts = rng.poisson(5.0, n).astype(np.int64)
+    m = int(counts.sum())
+    pt = rng.standard_exponential(m, dtype=np.float32) * np.float32(25.0)
+    a = ak.JaggedArray.fromcounts(counts, pt)
+    del counts
+    off = a.offsets
+    assert int(off[0]) == 0 and int(off[-1]) == m and len(off) == n + 1
+    c = a.counts
+    assert int(c.sum()) == m and bool((c >= 0).all())
+    assert bool((ak.JaggedArray.counts2offsets(c) == off).all())                     # scan(diff(offsets)) round trip
+    s = a.sum()
+    assert np.isclose(float(s.sum()), float(a.content.sum()), rtol=1e-3)
+    assert float(a.max().max()) == float(a.content.max())
+    sel = a[a > 20.0]
+    k = len(sel.content)
+    assert k == int(sel.counts.sum()) == int(sel.offsets[-1])
+    assert float(sel.content.min()) > 20.0
+    assert np.isclose(k / m, np.exp(-0.8), atol=1e-3)
+    again = sel[sel > 20.0]                                                            # idempotence
+    assert bool((again.offsets == sel.offsets).all()) and bool((again.content == sel.content).all())
+    del again
+    lead = a[a.argmax()]
+    nonempty = a.counts > 0
+    assert bool((lead.counts == nonempty).all())
+    mx = a.max()
+    picked = a.tojagged(mx)
+    assert bool(((a == picked).sum() >= nonempty).all())        # every non-empty event holds its own maximum
+    assert int((a == picked).any().sum()) == int(nonempty.sum())
+    del picked, lead
+    par = a.parents
+    assert int(par[0]) >= 0 and int(par[-1]) <= n - 1 and len(par) == m
+    assert bool((par[1:] >= par[:-1]).all())                                           # sortedness
+    del par
+    pairs_total = int(((c * (c + 1)) // 2).sum())
+    sub = ak.JaggedArray.fromoffsets(off[:10_000_001], a.content)
+    ap = sub.argpairs()
+    assert int(ap.offsets[-1]) == int(((sub.counts * (sub.counts + 1)) // 2).sum()) <= pairs_total
+    assert bool((ap.i0.content <= ap.i1.content).all()) and int(ap.i0.content.min()) == 0
