@@ -159,7 +159,19 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
     using R = Red<OP, T, A>;
 
     EventTile tile;
-    stage_init(&s_bar, 1);
+    if (threadIdx.x == 0) {
+        // thread 0 reads the tile's two boundary offsets and starts the TMA copy of the content run straight
+        // away, so that it overlaps the cooperative load of the offsets tile below
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, blockIdx.x, ev0, nev);
+        const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
+        const int64_t nb = (b - a) * static_cast<int64_t>(sizeof(T));
+        if (nb > 0 && nb <= STAGE_BYTES)
+            stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + a), static_cast<uint32_t>(nb), &s_bar);
+    }
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t nbytes = (e1 - e0) * static_cast<int64_t>(sizeof(T));
@@ -167,8 +179,8 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
     if (nbytes <= STAGE_BYTES) {
         // ---------------- SHORT: stage the tile's content run, thread-per-event out of shared memory --------
         if (nbytes > 0) {
-            const uint32_t shift = stage_issue<sizeof(T)>(
-                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes), &s_bar);
+            const uint32_t shift = stage_edges<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes));
             stage_wait(&s_bar, 0);
             const T *sm = reinterpret_cast<const T *>(s_stage + shift);
             for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
@@ -277,7 +289,17 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
     if (threadIdx.x == 0) s_valid = 0;
 
     EventTile tile;
-    stage_init(&s_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, blockIdx.x, ev0, nev);
+        const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
+        const int64_t nb = (b - a) * static_cast<int64_t>(sizeof(T));
+        if (nb > 0 && nb <= STAGE_BYTES)
+            stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + a), static_cast<uint32_t>(nb), &s_bar);
+    }
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t nbytes = (e1 - e0) * static_cast<int64_t>(sizeof(T));
@@ -285,8 +307,8 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
     if (nbytes <= STAGE_BYTES) {
         const T *sm = nullptr;
         if (nbytes > 0) {
-            const uint32_t shift = stage_issue<sizeof(T)>(
-                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes), &s_bar);
+            const uint32_t shift = stage_edges<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes));
             stage_wait(&s_bar, 0);
             sm = reinterpret_cast<const T *>(s_stage + shift);
         }

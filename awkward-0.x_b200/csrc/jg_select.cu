@@ -67,9 +67,23 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
 
-    stage_init(s_bar, 2);
     const uint32_t tile_index = blockIdx.x;
     EventTile tile;
+    if (threadIdx.x == 0) {
+        // start both TMA copies before the cooperative offsets load (see segreduce_kernel)
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, tile_index, ev0, nev);
+        const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
+        if (b > a && b - a <= KM) {
+            stage_bulk(s_mask, mask + a + mask_shift, static_cast<uint32_t>(b - a), &s_bar[1]);
+            stage_bulk(s_content, reinterpret_cast<const unsigned char *>(content + a),
+                       static_cast<uint32_t>((b - a) * sizeof(V)), &s_bar[0]);
+        }
+    }
     tile.load(s_off, offsets, n, tile_index);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t len = e1 - e0;
@@ -83,9 +97,9 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
         const V *cv = nullptr;
         const uint8_t *mv = nullptr;
         if (L > 0) {
-            const uint32_t cs = stage_issue<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
-                                                       static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
-            const uint32_t ms = stage_issue<1>(s_mask, mask + e0 + mask_shift, static_cast<uint32_t>(L), &s_bar[1]);
+            const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
+                                                       static_cast<uint32_t>(L * sizeof(V)));
+            const uint32_t ms = stage_edges<1>(s_mask, mask + e0 + mask_shift, static_cast<uint32_t>(L));
             mbar_wait(&s_bar[1], 0);
             __syncthreads();
             cv = reinterpret_cast<const V *>(s_content + cs);

@@ -25,6 +25,12 @@ struct EventTile {
         for (int i = threadIdx.x; i <= nev; i += kTileThreads) s_off[i] = __ldg(offsets + event0 + i);
         __syncthreads();
     }
+    // the tile's event range without touching memory (for the early bulk copy)
+    __device__ static __forceinline__ void range(int64_t n, int64_t tile_index, int64_t &ev0, int &nev_) {
+        ev0 = tile_index * kTileEvents;
+        const int64_t left = n - ev0;
+        nev_ = left < kTileEvents ? static_cast<int>(left) : kTileEvents;
+    }
     __device__ __forceinline__ int64_t first_element() const { return off[0]; }
     __device__ __forceinline__ int64_t last_element() const { return off[nev]; }
     // event (local index) that contains element j, first_element() <= j < last_element()
@@ -66,30 +72,53 @@ __device__ __forceinline__ void stage_init(uint64_t *bar, int nbars) {
     __syncthreads();
 }
 
+struct StageSplit {
+    uint32_t shift;   // first requested byte within the 16-byte phase
+    uint32_t head;    // unaligned leading bytes (< 16)
+    uint32_t mid;     // 16-byte aligned body moved by the bulk copy
+};
+
+__device__ __forceinline__ StageSplit stage_split(const unsigned char *g, uint32_t nbytes) {
+    const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+    const uintptr_t mid_begin = (ga + 15) & ~static_cast<uintptr_t>(15);
+    const uintptr_t mid_end = (ga + nbytes) & ~static_cast<uintptr_t>(15);
+    StageSplit s;
+    s.shift = static_cast<uint32_t>(ga & 15);
+    s.head = static_cast<uint32_t>(mid_begin > ga + nbytes ? nbytes : mid_begin - ga);
+    s.mid = mid_end > mid_begin ? static_cast<uint32_t>(mid_end - mid_begin) : 0u;
+    return s;
+}
+
+// ONE thread: arm the mbarrier and start the bulk copy of the aligned body.  Can be called before the rest of the
+// CTA knows the run (e.g. by thread 0 straight after reading the tile's two boundary offsets), so that the copy
+// overlaps the cooperative load of the offsets tile.
+__device__ __forceinline__ void stage_bulk(unsigned char *smem, const unsigned char *g, uint32_t nbytes,
+                                           uint64_t *bar) {
+    const StageSplit s = stage_split(g, nbytes);
+    mbar_expect_tx(bar, s.mid);      // mid == 0: nothing in flight, the phase completes immediately
+    if (s.mid) bulk_g2s(smem + s.shift + s.head, g + s.head, s.mid, bar);
+}
+
+// ALL threads: copy the unaligned head and tail (< 16 bytes each) by ordinary loads; returns the shift.
+template <int ELEM>
+__device__ __forceinline__ uint32_t stage_edges(unsigned char *smem, const unsigned char *g, uint32_t nbytes) {
+    const StageSplit s = stage_split(g, nbytes);
+    for (uint32_t b = threadIdx.x * ELEM; b < s.head; b += blockDim.x * ELEM) {
+#pragma unroll
+        for (int k = 0; k < ELEM; ++k) smem[s.shift + b + k] = g[b + k];
+    }
+    for (uint32_t b = s.head + s.mid + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
+#pragma unroll
+        for (int k = 0; k < ELEM; ++k) smem[s.shift + b + k] = g[b + k];
+    }
+    return s.shift;
+}
+
 template <int ELEM>
 __device__ __forceinline__ uint32_t stage_issue(unsigned char *smem, const unsigned char *g, uint32_t nbytes,
                                                 uint64_t *bar) {
-    const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
-    const uint32_t shift = static_cast<uint32_t>(ga & 15);
-    const uintptr_t mid_begin = (ga + 15) & ~static_cast<uintptr_t>(15);
-    const uintptr_t mid_end = (ga + nbytes) & ~static_cast<uintptr_t>(15);
-    const uint32_t head = static_cast<uint32_t>(mid_begin > ga + nbytes ? nbytes : mid_begin - ga);
-    uint32_t mid = 0;
-    if (mid_end > mid_begin) mid = static_cast<uint32_t>(mid_end - mid_begin);
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, mid);    // mid == 0: nothing in flight, the phase completes immediately
-        if (mid) bulk_g2s(smem + shift + head, reinterpret_cast<const void *>(mid_begin), mid, bar);
-    }
-    // unaligned head (< 16 bytes) and tail (< 16 bytes) by ordinary loads
-    for (uint32_t b = threadIdx.x * ELEM; b < head; b += blockDim.x * ELEM) {
-#pragma unroll
-        for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
-    }
-    for (uint32_t b = head + mid + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
-#pragma unroll
-        for (int k = 0; k < ELEM; ++k) smem[shift + b + k] = g[b + k];
-    }
-    return shift;
+    if (threadIdx.x == 0) stage_bulk(smem, g, nbytes, bar);
+    return stage_edges<ELEM>(smem, g, nbytes);
 }
 
 __device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t phase) {
