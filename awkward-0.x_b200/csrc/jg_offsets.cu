@@ -136,10 +136,14 @@ __global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v) {
 // ------------------------------------------------------------------------------------------------------------
 enum { EXPAND_PARENTS = 0, EXPAND_LOCALINDEX = 1, EXPAND_BROADCAST = 2 };
 
+constexpr int kOwnPositions = 4096;      // positions of a tile the on-chip owner table covers
+
 template <int MODE, typename V>
 __global__ void __launch_bounds__(kTileThreads)
 expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out, const V *__restrict__ flat) {
     __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
+    __shared__ V s_flat[MODE == EXPAND_BROADCAST ? kTileEvents : 1];
     EventTile tile;
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t o0 = __ldg(offsets);
@@ -147,8 +151,23 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         // content below offsets[0] is unreachable: -1 (jagged.py:52-54)
         for (int64_t j = threadIdx.x; j < o0; j += kTileThreads) out[j] = static_cast<V>(-1);
     }
-    // element-parallel: every thread finds the event of its element by binary search in the tile's offsets
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    if (e1 - e0 <= kOwnPositions) {
+        // short events: scatter + max-scan owner table in shared memory, then a coalesced element-parallel sweep
+        const int L = static_cast<int>(e1 - e0);
+        if (MODE == EXPAND_BROADCAST)
+            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = flat[tile.event0 + ev];
+        build_owner_table(s_own, tile, L);
+        V *dst = (MODE == EXPAND_PARENTS) ? out + e0 : out + (e0 - o0);
+        for (int p = threadIdx.x; p < L; p += kTileThreads) {
+            const int ev = s_own[p];
+            if (MODE == EXPAND_PARENTS) __stcs(dst + p, static_cast<V>(tile.event0 + ev));
+            else if (MODE == EXPAND_LOCALINDEX) __stcs(dst + p, static_cast<V>(e0 + p - s_off[ev]));
+            else __stcs(dst + p, s_flat[ev]);
+        }
+        return;
+    }
+    // long events: every thread finds the event of its element by binary search in the tile's offsets
     for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
         const int ev = tile.find_event(j);
         if (MODE == EXPAND_PARENTS) {

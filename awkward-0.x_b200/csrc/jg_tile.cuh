@@ -127,3 +127,67 @@ __device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t phase) {
 }
 
 }  // namespace jg
+
+namespace jg {
+
+// ---------------------------------------------------------------------------------------------------------
+// Owner table: for every position p of a tile's run [0, L) the local index of the event that owns it, built in
+// shared memory by a vectorised SCATTER (each non-empty event drops its index on its first position) followed by
+// a running-MAX SCAN (rows of 128 positions per warp, 4 per lane, shuffles across lanes).  This is the on-chip
+// form of offsets2parents (jagged.py:49-54, numpy.repeat) and feeds parents / localindex / broadcast / gathers /
+// combinatorics without a per-element binary search.
+//   own : __shared__ uint16_t[KM + 128], 16-byte aligned;  requires L <= KM and nev <= 65535
+// All threads of the CTA call it; it ends with a __syncthreads().
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile &tile, int L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kTileThreads / kWarp;
+    const int padded = (L + 127) & ~127;
+    // 1. clear (128-bit stores)
+    for (int q = threadIdx.x; q < padded / 8; q += kTileThreads) reinterpret_cast<uint4 *>(own)[q] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // 2. scatter: non-empty events have distinct first positions
+    const int64_t e0 = tile.off[0];
+    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+        const int64_t a = tile.off[ev], b = tile.off[ev + 1];
+        if (b > a) own[a - e0] = static_cast<uint16_t>(ev);
+    }
+    __syncthreads();
+    // 3. running max: warp w owns a contiguous chunk of rows
+    const int rows_total = padded >> 7;
+    const int rows_per_warp = (rows_total + NW - 1) / NW;
+    const int r_begin = warp * rows_per_warp;
+    const int r_end = min(rows_total, r_begin + rows_per_warp);
+    if (r_begin < r_end) {
+        // owner of the chunk's first position (the event that started at or before it)
+        uint32_t carry = 0;
+        const int first = r_begin << 7;
+        if (first > 0 && first < L) carry = static_cast<uint32_t>(tile.find_event(e0 + first));
+        for (int r = r_begin; r < r_end; ++r) {
+            uint2 w = *reinterpret_cast<const uint2 *>(own + (r << 7) + lane * 4);
+            uint32_t v0 = w.x & 0xffffu, v1 = w.x >> 16, v2 = w.y & 0xffffu, v3 = w.y >> 16;
+            v1 = max(v1, v0);
+            v2 = max(v2, v1);
+            v3 = max(v3, v2);
+            uint32_t incl = v3;
+#pragma unroll
+            for (int d = 1; d < kWarp; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = max(incl, o);
+            }
+            uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+            before = lane == 0 ? carry : max(before, carry);
+            v0 = max(v0, before);
+            v1 = max(v1, before);
+            v2 = max(v2, before);
+            v3 = max(v3, before);
+            w.x = v0 | (v1 << 16);
+            w.y = v2 | (v3 << 16);
+            *reinterpret_cast<uint2 *>(own + (r << 7) + lane * 4) = w;
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace jg
