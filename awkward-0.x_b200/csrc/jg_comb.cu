@@ -69,6 +69,8 @@ __device__ __forceinline__ int64_t largest_binom_le(int64_t m, int k, int64_t n)
     return c;
 }
 
+constexpr int kCombPositions = 12288;    // output positions of a tile the on-chip owner table covers
+
 struct CombIndex {
     int64_t v[5];
 };
@@ -112,8 +114,11 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
     const int ncols = (KIND == JG_COMB_CHOOSE) ? k : 2;
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    const bool table = (p1 - p0) <= kCombPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
     for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
-        const int ev = pt.find_event(p);
+        const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
         const int64_t na = s_oa[ev + 1] - s_oa[ev];
         const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
         CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, k);
@@ -140,14 +145,40 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     ta.load(s_oa, offsets_a, n, blockIdx.x);
     if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
-    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
-        const int ev = pt.find_event(p);
-        const int64_t na = s_oa[ev + 1] - s_oa[ev];
-        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
-        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
-        const int64_t sb = (KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev];
-        __stcs(out_l + p, __ldg(content_a + s_oa[ev] + r.v[0]));
-        __stcs(out_r + p, __ldg(content_b + sb + r.v[1]));
+    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    const bool table = (p1 - p0) <= kCombPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+    for (int64_t pb = p0 + threadIdx.x; pb < p1; pb += 2 * kTileThreads) {
+        int64_t ia[2], ib[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = pb + u * kTileThreads;
+            if (p < p1) {
+                const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
+                const int64_t na = s_oa[ev + 1] - s_oa[ev];
+                const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+                CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
+                ia[u] = s_oa[ev] + r.v[0];
+                ib[u] = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
+            }
+        }
+        VA va[2];
+        VB vb[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (pb + u * kTileThreads < p1) {
+                va[u] = __ldg(content_a + ia[u]);
+                vb[u] = __ldg(content_b + ib[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = pb + u * kTileThreads;
+            if (p < p1) {
+                __stcs(out_l + p, va[u]);
+                __stcs(out_r + p, vb[u]);
+            }
+        }
     }
 }
 

@@ -221,16 +221,49 @@ static inline bool same_type(int dt) {
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// rhs is flat[N]; lhs/out are dense contents starting at offsets[0]
+// rhs is flat[N]; lhs/out are dense contents starting at offsets[0].  The flat values of the tile's events and the
+// owner of every position (scatter + max-scan table, jg_tile.cuh) are kept in shared memory: the broadcast of
+// jagged.py:1003-1037 is never materialised.
 template <class F, typename C>
 __global__ void __launch_bounds__(kTileThreads)
 binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__restrict__ flat, int rhs_dt, int swap,
                      typename F::Out *__restrict__ out, const int64_t *__restrict__ offsets, int64_t n) {
+    constexpr int KM = 4096;
     __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) uint16_t s_own[KM + 128];
+    __shared__ C s_flat[kTileEvents];
     EventTile tile;
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t o0 = __ldg(offsets);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    if (e1 - e0 <= KM) {
+        const int L = static_cast<int>(e1 - e0);
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = load_as<C>(flat, rhs_dt, tile.event0 + ev);
+        build_owner_table(s_own, tile, L);
+        const int64_t d0 = e0 - o0;
+        // 4 independent loads in flight per thread (the sweep is otherwise one dependent load per iteration)
+        for (int p = threadIdx.x; p < L; p += 4 * kTileThreads) {
+            C a[4];
+            int ev[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = p + u * kTileThreads;
+                if (q < L) {
+                    a[u] = load_as<C>(lhs, lhs_dt, d0 + q);
+                    ev[u] = s_own[q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = p + u * kTileThreads;
+                if (q < L) {
+                    const C b = s_flat[ev[u]];
+                    __stcs(out + d0 + q, swap ? F::apply(b, a[u]) : F::apply(a[u], b));
+                }
+            }
+        }
+        return;
+    }
     for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
         const int ev = tile.find_event(j);
         const C a = load_as<C>(lhs, lhs_dt, j - o0);

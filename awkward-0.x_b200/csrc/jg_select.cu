@@ -195,25 +195,49 @@ __global__ void __launch_bounds__(kTileThreads)
 index_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__ offsets, const I *__restrict__ index,
                     const int64_t *__restrict__ index_offsets, int64_t n, V *__restrict__ out,
                     int32_t *__restrict__ status) {
+    constexpr int KM = 4096;
     __shared__ int64_t s_ioff[kTileEvents + 1];
     __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) uint16_t s_own[KM + 128];
     EventTile itile, tile;
     itile.load(s_ioff, index_offsets, n, blockIdx.x);
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t io0 = __ldg(index_offsets);
     const int64_t k0 = itile.first_element(), k1 = itile.last_element();
     bool oob = false;
-    // element-parallel over the index run of this tile: coalesced reads of index, coalesced writes of out
-    for (int64_t k = k0 + threadIdx.x; k < k1; k += kTileThreads) {
-        const int ev = itile.find_event(k);
-        const int64_t start = s_off[ev], count = s_off[ev + 1] - start;
-        int64_t ix = static_cast<int64_t>(index[k]);
-        if (ix < 0) ix += count;                                    // jagged.py:552-553
-        if (ix < 0 || ix >= count) {                                // jagged.py:555-556
-            oob = true;
-            continue;
+    const bool table = (k1 - k0) <= KM;
+    if (table) build_owner_table(s_own, itile, static_cast<int>(k1 - k0));
+    // element-parallel over the index run of this tile: coalesced reads of index, coalesced writes of out;
+    // 4 independent (index -> content) load chains in flight per thread
+    for (int64_t kb = k0 + threadIdx.x; kb < k1; kb += 4 * kTileThreads) {
+        int64_t ix[4], src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = kb + u * kTileThreads;
+            if (k < k1) ix[u] = static_cast<int64_t>(__ldcs(index + k));
         }
-        out[k - io0] = __ldg(content + start + ix);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = kb + u * kTileThreads;
+            src[u] = -1;
+            if (k < k1) {
+                const int ev = table ? static_cast<int>(s_own[k - k0]) : itile.find_event(k);
+                const int64_t start = s_off[ev], count = s_off[ev + 1] - start;
+                int64_t i = ix[u];
+                if (i < 0) i += count;                                  // jagged.py:552-553
+                if (i < 0 || i >= count) oob = true;                    // jagged.py:555-556
+                else src[u] = start + i;
+            }
+        }
+        V val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0) val[u] = __ldg(content + src[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t k = kb + u * kTileThreads;
+            if (src[u] >= 0) __stcs(out + (k - io0), val[u]);
+        }
     }
     if (oob) atomicOr(status, JG_ST_INDEX_OOB);
 }
@@ -222,8 +246,19 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 take_kernel(const V *__restrict__ content, const int64_t *__restrict__ index, int64_t n, V *__restrict__ out) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = __ldg(content + __ldcs(index + i));
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+        int64_t ix[4];
+        V v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n) ix[u] = __ldcs(index + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n) v[u] = __ldg(content + ix[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n) __stcs(out + i + u * stride, v[u]);
+    }
 }
 
 // out_index[out_offsets[i]] = best[i] for best[i] >= 0
