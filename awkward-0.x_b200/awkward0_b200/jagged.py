@@ -939,8 +939,16 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
         call("jg_segargminmax_dense", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
-             _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
-        total, _, _ = runtime.read(scal)
+             _vp(out_offsets), _vp(out_index), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
+        total, status, _ = runtime.read(scal)
+        if status & _lib.ST_ARG_ALLNAN:
+            # a non-empty event holds only NaN: exact path (arg-reduce to best[], then scan + compaction)
+            best = empty(n, INDEXTYPE)
+            scal = runtime.scalars()
+            call("jg_segargminmax", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0, _vp(best),
+                 ctypes.c_void_p(0), runtime.stream())
+            call("jg_compact_nonneg", _vp(best), n, _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
+            total, _, _ = runtime.read(scal)
         return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
 
     # ------------------------------------------------------------------------------------------------------

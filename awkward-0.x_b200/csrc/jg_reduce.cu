@@ -377,42 +377,143 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// dense form of argmin / argmax (jagged.py:1581-1601 logical value): segarg_kernel also counts, per event tile,
-// the events that have a result; the tile totals are scanned (tiny) and compact_best_kernel turns best[] into
-// out_offsets / out_index IN PLACE (best[] lives in the out_offsets buffer), with no cross-CTA waiting.
+// OPTIMISTIC one-pass dense argmin / argmax.  For almost every input "the event has a result" == "the event is
+// not empty" (the exception: a non-empty event whose values are all NaN).  The result offsets then depend on the
+// offsets only: count_nonempty_kernel (8N bytes) + a tiny scan give every tile its base, and segarg_direct_kernel
+// writes out_offsets while its content run is still in flight and out_index straight from the arg-reduce -- no
+// best[] round trip, no compaction pass.  An all-NaN non-empty event raises JG_ST_ARG_ALLNAN and the host redoes
+// the operation with the exact three-kernel path above (jg_segargminmax + jg_compact_nonneg).
+// Traffic: 8N + vM + 8(N+1) read, 8(N+1) + 8N+ written.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads)
-compact_best_kernel(int64_t *__restrict__ best_then_offsets, int64_t n, const int64_t *__restrict__ tile_bases,
-                    int64_t *__restrict__ out_index, uint32_t ntiles) {
-    __shared__ int32_t s_scan[kTileThreads / kWarp + 1];
-    const int64_t event0 = static_cast<int64_t>(blockIdx.x) * kTileEvents;
-    const int64_t i0 = event0 + threadIdx.x * 2;       // thread t finishes events 2t and 2t+1
-    int64_t b0 = -1, b1 = -1;
-    if (i0 + 1 < n) {
-        if ((reinterpret_cast<uintptr_t>(best_then_offsets) & 15) == 0) {
-            const longlong2 v = *reinterpret_cast<const longlong2 *>(best_then_offsets + i0);
-            b0 = v.x;
-            b1 = v.y;
-        } else {
-            b0 = best_then_offsets[i0];
-            b1 = best_then_offsets[i0 + 1];
+count_nonempty_kernel(const int64_t *__restrict__ offsets, int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = static_cast<int64_t>(blockIdx.x) * (kTileThreads / kWarp) + warp;
+    if (tile >= ntiles) return;
+    const int64_t ev0 = tile * kTileEvents;
+    const int64_t ev1 = min(n, ev0 + kTileEvents);
+    int cnt = 0;
+    for (int64_t i = ev0 + lane; i < ev1; i += kWarp) cnt += (__ldg(offsets + i + 1) > __ldg(offsets + i));
+    cnt = warp_reduce_add(cnt);
+    if (lane == 0) tile_totals[tile] = cnt;
+}
+
+template <bool ISMIN, typename T, int STAGE_BYTES>
+__global__ void __launch_bounds__(kTileThreads)
+segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
+                     const int64_t *__restrict__ tile_bases, int64_t *__restrict__ out_offsets,
+                     int64_t *__restrict__ out_index, int32_t *__restrict__ status, uint32_t ntiles) {
+    constexpr int NW = kTileThreads / kWarp;
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
+    __shared__ uint64_t s_bar;
+    __shared__ ArgPartial<T> s_part[NW];
+    __shared__ int32_t s_scan[NW + 1];
+
+    EventTile tile;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, blockIdx.x, ev0, nev);
+        const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
+        const int64_t nb = (b - a) * static_cast<int64_t>(sizeof(T));
+        if (nb > 0 && nb <= STAGE_BYTES)
+            stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + a), static_cast<uint32_t>(nb), &s_bar);
+    }
+    tile.load(s_off, offsets, n, blockIdx.x);
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    const int64_t nbytes = (e1 - e0) * static_cast<int64_t>(sizeof(T));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // result offsets from the offsets alone (thread t owns events 2t, 2t+1): written while the content is in flight
+    const int ev0 = threadIdx.x * 2;
+    int64_t a[2] = {0, 0}, b[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        if (ev0 + q < tile.nev) {
+            a[q] = s_off[ev0 + q];
+            b[q] = s_off[ev0 + q + 1];
         }
-    } else if (i0 < n) {
-        b0 = best_then_offsets[i0];
-    }
-    const int has0 = b0 >= 0, has1 = b1 >= 0;
+    const int ne0 = b[0] > a[0], ne1 = b[1] > a[1];
     int32_t block_total;
-    const int32_t excl = block_excl_scan<int32_t, kTileThreads>(has0 + has1, s_scan, block_total);
+    const int32_t excl = block_excl_scan<int32_t, kTileThreads>(ne0 + ne1, s_scan, block_total);
     const int64_t base = __ldg(tile_bases + blockIdx.x) + excl;
-    if (i0 < n) {
-        best_then_offsets[i0] = base;
-        if (has0) out_index[base] = b0;
+    {
+        int64_t *dst = out_offsets + tile.event0 + ev0;
+        if (ev0 + 1 < tile.nev && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            __stcs(reinterpret_cast<longlong2 *>(dst), make_longlong2(base, base + ne0));
+        } else {
+            if (ev0 < tile.nev) dst[0] = base;
+            if (ev0 + 1 < tile.nev) dst[1] = base + ne0;
+        }
+        if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) out_offsets[n] = __ldg(tile_bases + ntiles);
     }
-    if (i0 + 1 < n) {
-        best_then_offsets[i0 + 1] = base + has0;
-        if (has1) out_index[base + has0] = b1;
+
+    int64_t idx[2] = {-1, -1};
+    if (nbytes <= STAGE_BYTES) {
+        const T *sm = nullptr;
+        if (nbytes > 0) {
+            const uint32_t shift = stage_edges<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes));
+            stage_wait(&s_bar, 0);
+            sm = reinterpret_cast<const T *>(s_stage + shift);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int ja = static_cast<int>(a[q] - e0), jb = static_cast<int>(b[q] - e0);
+            int best = -1;
+            T bv = T(0);
+#pragma unroll 1
+            for (int j = ja; j < jb; ++j) {
+                const T x = sm[j];
+                const bool take = (ISMIN ? (x < bv) : (x > bv)) || (best < 0 && !is_nan(x));
+                if (take) {
+                    bv = x;
+                    best = j - ja;
+                }
+            }
+            idx[q] = best;
+        }
+    } else {
+        __shared__ int64_t s_idx64[kTileEvents];
+        for (int ev = warp; ev < tile.nev; ev += NW) {
+            const int64_t ea = s_off[ev], eb = s_off[ev + 1];
+            if (eb - ea >= kBlockEventMin) continue;
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, ea, eb, lane, kWarp));
+            if (lane == 0) s_idx64[ev] = p.idx;
+        }
+        for (int ev = 0; ev < tile.nev; ++ev) {
+            const int64_t ea = s_off[ev], eb = s_off[ev + 1];
+            if (eb - ea < kBlockEventMin) continue;
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, ea, eb, threadIdx.x, kTileThreads));
+            __syncthreads();
+            if (lane == 0) s_part[warp] = p;
+            __syncthreads();
+            if (warp == 0) {
+                ArgPartial<T> q;
+                if (lane < NW) q = s_part[lane];
+                else { q.idx = -1; q.val = T(0); }
+                q = arg_shuffle<ISMIN, T>(q);
+                if (lane == 0) s_idx64[ev] = q.idx;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (ev0 + q < tile.nev) idx[q] = s_idx64[ev0 + q];
     }
-    if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) best_then_offsets[n] = __ldg(tile_bases + ntiles);
+    bool mismatch = false;
+    if (ne0) {
+        mismatch |= idx[0] < 0;
+        out_index[base] = idx[0];
+    }
+    if (ne1) {
+        mismatch |= idx[1] < 0;
+        out_index[base + ne0] = idx[1];
+    }
+    if (mismatch) atomicOr(status, JG_ST_ARG_ALLNAN);
 }
 
 template <typename T> struct StageBytes { static constexpr int value = sizeof(T) >= 8 ? 32768 : (sizeof(T) >= 4 ? 16384 : 8192); };
@@ -452,25 +553,33 @@ static int dispatch_arg(int is_min, const void *content, const int64_t *offsets,
 
 template <typename T>
 static int dispatch_arg_dense(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *out_offsets,
-                              int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+                              int64_t *out_index, int64_t *total, int32_t *status, void *ws, size_t ws_bytes,
+                              cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
     // workspace: [totals: nt+2][bases: nt+2][scan descriptors]
     const size_t arr = ((static_cast<size_t>(ntiles) + 2) * 8 + 255) & ~static_cast<size_t>(255);
     const size_t scan_need = sizeof(LookbackWs) + static_cast<size_t>(ceil_div(ntiles, kScanTile) + 1) * 8;
     JG_REQUIRE(ws != nullptr && ws_bytes >= 2 * arr + scan_need + 256,
                "jg_segargminmax_dense: workspace too small (%zu < %zu)", ws_bytes, 2 * arr + scan_need + 256);
+    JG_REQUIRE(status != nullptr, "jg_segargminmax_dense: status word required");
     int64_t *totals = static_cast<int64_t *>(ws);
     int64_t *bases = reinterpret_cast<int64_t *>(static_cast<char *>(ws) + arr);
     void *scan_ws = static_cast<char *>(ws) + 2 * arr;
-    if (n == 0) cudaMemsetAsync(totals, 0, 8, s);
-    int rc = n > 0 ? dispatch_arg<T>(is_min, content, offsets, n, out_offsets, nullptr, s, totals) : 0;
+    count_nonempty_kernel<<<static_cast<unsigned>(ceil_div(ntiles, kTileThreads / kWarp)), kTileThreads, 0, s>>>(
+        offsets, n, ntiles, totals);
+    int rc = check_launch("count_nonempty_kernel");
     if (rc) return rc;
-    ScanInArray<int64_t> in{totals, true};
-    rc = launch_scan(in, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
+    rc = launch_scan_array(totals, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
     if (rc) return rc;
-    compact_best_kernel<<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(out_offsets, n, bases, out_index,
-                                                                                static_cast<uint32_t>(ntiles));
-    return check_launch("compact_best_kernel");
+    if (is_min)
+        segarg_direct_kernel<true, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, status,
+            static_cast<uint32_t>(ntiles));
+    else
+        segarg_direct_kernel<false, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, status,
+            static_cast<uint32_t>(ntiles));
+    return check_launch("segarg_direct_kernel");
 }
 
 }  // namespace jg
@@ -525,17 +634,17 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
 }
 
 int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
-                          int64_t *out_offsets, int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes,
-                          void *stream) {
+                          int64_t *out_offsets, int64_t *out_index, int64_t *total, int32_t *status, void *ws,
+                          size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && out_offsets, "jg_segargminmax_dense: bad arguments");
     cudaStream_t s = as_stream(stream);
     switch (dtype) {
-        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
-        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
-        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
-        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
+        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
+        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
+        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
         case JG_U8:
-        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, total, ws, ws_bytes, s);
+        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
     }
     set_error("jg_segargminmax_dense: unsupported dtype %d", dtype);
     return -2;

@@ -111,7 +111,7 @@ def run_reference(args):
                                    "to the GPU box" % (per_worker, cores)},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -297,7 +297,7 @@ def run_gpu(args):
             "totals": {"sum": totals[0], "selected": totals[1], "leading": totals[2]},
             "roofline": roof, "cpu_baseline": cpu, "ops": ops,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -369,7 +369,7 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     aoff, aidx = empty(N + 1, np.int64), empty(N, np.int64)
     add("segargmax_dense_f32", v * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
         "jg_segargminmax_dense", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(aoff), _vp(aidx), _vp(scal),
-        ws, wsb, st()))
+        _vp(scal, 1), ws, wsb, st()))
     add("compact_nonneg", 8 * N + 8 * N + 8 * N, N, lambda: _lib.call(
         "jg_compact_nonneg", _vp(best), N, _vp(aoff), _vp(aidx), _vp(scal), ws, wsb, st()))
     mask = empty(M, np.bool_)
@@ -449,7 +449,25 @@ def cpu_baseline(args):
             "seconds": best}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; keep stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

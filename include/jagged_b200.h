@@ -47,7 +47,8 @@ enum {
     JG_ST_INDEX_OOB       = 16,  /* "jagged array used as index contains out-of-bounds"      jagged.py:555 */
     JG_ST_COUNTS_MISMATCH = 32,  /* "cannot fit contents of JaggedArray into the given ..."  jagged.py:911 */
     JG_ST_NOT_OFFSETS     = 64,  /* starts[1:] != stops[:-1]                                 jagged.py:358 */
-    JG_ST_STOPS_LT_STARTS = 128  /* "stops must be greater than or equal to starts"          jagged.py:501 */
+    JG_ST_STOPS_LT_STARTS = 128, /* "stops must be greater than or equal to starts"          jagged.py:501 */
+    JG_ST_ARG_ALLNAN      = 256  /* a non-empty event holds only NaN: redo argmin/argmax with the exact path   */
 };
 
 /* ---- reducers (base.py:193-215) -------------------------------------------------------------------------- */
@@ -129,11 +130,13 @@ int jg_segreduce(const void *content, int dtype, const int64_t *offsets, int64_t
  * or -1 for an event with none.  Optionally also writes the extreme value itself (same dtype as content).        */
 int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
                     int64_t *best, void *best_value, void *stream);
-/* the same, fused with the compaction below: one pass from content to the dense result
- * out_offsets[n+1] (scanned 0/1 counts), out_index[<= n] (allocate n), *total = number of events with a result. */
+/* the dense result in one optimistic pass: out_offsets[n+1] (scanned 0/1 counts), out_index[<= n] (allocate n),
+ * *total = number of events with a result.  Assumes every non-empty event has a result; when a non-empty event
+ * holds only NaN, JG_ST_ARG_ALLNAN is raised in *status, the outputs are not valid and the caller must use
+ * jg_segargminmax + jg_compact_nonneg instead.                                                                    */
 int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
-                          int64_t *out_offsets, int64_t *out_index, int64_t *total, void *ws, size_t ws_bytes,
-                          void *stream);
+                          int64_t *out_offsets, int64_t *out_index, int64_t *total, int32_t *status, void *ws,
+                          size_t ws_bytes, void *stream);
 /* turn best[] into the dense result: out_offsets[n+1] (0/1 counts scanned) and out_index[<=n]; *total = count.   */
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
                       void *ws, size_t ws_bytes, void *stream);
