@@ -183,18 +183,46 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
                 s_stage, reinterpret_cast<const unsigned char *>(content + e0), static_cast<uint32_t>(nbytes));
             stage_wait(&s_bar, 0);
             const T *sm = reinterpret_cast<const T *>(s_stage + shift);
-            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
-                const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
-                A acc = R::identity();
-                if (b > a) {
-                    acc = R::lift(sm[a]);
-                    // not unrolled on purpose: events are short (mean 5) and of different length per lane; an
-                    // unrolled loop with 8/4/2/1 remainder cascades makes a divergent warp execute every branch
-#pragma unroll 1
-                    for (int j = a + 1; j < b; ++j) acc = R::accumulate(acc, sm[j]);
-                }
-                out[tile.event0 + ev] = acc;
+            // Thread t reduces events t and t+256 TOGETHER, one element of each per step, predicated: the kernel is
+            // instruction-issue bound (ncu: issue-active ~80 %), and this shares the loop overhead between two
+            // events and lets a warp iterate max-over-64-events once instead of max-over-32 twice.  Each event is
+            // still reduced strictly left to right (the reference's order).  Float sum / prod run without the
+            // per-element NaN test; a NaN result (a NaN input, or inf - inf) sends that one event to the exact loop.
+            constexpr bool FAST = IsFloat<T>::value && (OP == JG_SUM || OP == JG_PROD);
+            const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
+            int aA = 0, lenA = 0, aB = 0, lenB = 0;
+            if (evA < tile.nev) {
+                aA = static_cast<int>(s_off[evA] - e0);
+                lenA = static_cast<int>(s_off[evA + 1] - e0) - aA;
             }
+            if (evB < tile.nev) {
+                aB = static_cast<int>(s_off[evB] - e0);
+                lenB = static_cast<int>(s_off[evB + 1] - e0) - aB;
+            }
+            const T *pA = sm + aA, *pB = sm + aB;
+            A accA = R::identity(), accB = R::identity();
+            if (lenA > 0) accA = FAST ? static_cast<A>(pA[0]) : R::lift(pA[0]);
+            if (lenB > 0) accB = FAST ? static_cast<A>(pB[0]) : R::lift(pB[0]);
+            const int len = max(lenA, lenB);
+#pragma unroll 1
+            for (int k = 1; k < len; k += 2) {
+                if (k < lenA) accA = FAST ? R::combine(accA, static_cast<A>(pA[k])) : R::accumulate(accA, pA[k]);
+                if (k < lenB) accB = FAST ? R::combine(accB, static_cast<A>(pB[k])) : R::accumulate(accB, pB[k]);
+                if (k + 1 < lenA) accA = FAST ? R::combine(accA, static_cast<A>(pA[k + 1])) : R::accumulate(accA, pA[k + 1]);
+                if (k + 1 < lenB) accB = FAST ? R::combine(accB, static_cast<A>(pB[k + 1])) : R::accumulate(accB, pB[k + 1]);
+            }
+            if (FAST) {
+                if (accA != accA) {
+                    accA = R::lift(pA[0]);
+                    for (int k = 1; k < lenA; ++k) accA = R::combine(accA, R::lift(pA[k]));
+                }
+                if (accB != accB) {
+                    accB = R::lift(pB[0]);
+                    for (int k = 1; k < lenB; ++k) accB = R::combine(accB, R::lift(pB[k]));
+                }
+            }
+            if (evA < tile.nev) out[tile.event0 + evA] = accA;
+            if (evB < tile.nev) out[tile.event0 + evB] = accB;
         } else {
             for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) out[tile.event0 + ev] = R::identity();
         }
@@ -460,22 +488,45 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
             stage_wait(&s_bar, 0);
             sm = reinterpret_cast<const T *>(s_stage + shift);
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int ja = static_cast<int>(a[q] - e0), jb = static_cast<int>(b[q] - e0);
-            int best = -1;
-            T bv = T(0);
+        // both events of the thread advance together, one element each per step (predicated); the running best
+        // starts at the identity, so "strictly better" needs no NaN or first-element test.  An event that ends
+        // without a result although it is not empty (only NaN, or only identity values) takes the exact loop.
+        const T *pA = sm + static_cast<int>(a[0] - e0), *pB = sm + static_cast<int>(a[1] - e0);
+        const int lenA = static_cast<int>(b[0] - a[0]), lenB = static_cast<int>(b[1] - a[1]);
+        T bvA = ISMIN ? min_identity<T>() : max_identity<T>(), bvB = bvA;
+        int iA = -1, iB = -1;
+        const int len = max(lenA, lenB);
 #pragma unroll 1
-            for (int j = ja; j < jb; ++j) {
-                const T x = sm[j];
-                const bool take = (ISMIN ? (x < bv) : (x > bv)) || (best < 0 && !is_nan(x));
-                if (take) {
-                    bv = x;
-                    best = j - ja;
+        for (int k = 0; k < len; ++k) {
+            if (k < lenA) {
+                const T x = pA[k];
+                if (ISMIN ? (x < bvA) : (x > bvA)) {
+                    bvA = x;
+                    iA = k;
                 }
             }
-            idx[q] = best;
+            if (k < lenB) {
+                const T x = pB[k];
+                if (ISMIN ? (x < bvB) : (x > bvB)) {
+                    bvB = x;
+                    iB = k;
+                }
+            }
         }
+        if (lenA > 0 && iA < 0)
+            for (int k = 0; k < lenA; ++k)
+                if (!is_nan(pA[k])) {      // every non-NaN value equals the identity: the first one wins
+                    iA = k;
+                    break;
+                }
+        if (lenB > 0 && iB < 0)
+            for (int k = 0; k < lenB; ++k)
+                if (!is_nan(pB[k])) {
+                    iB = k;
+                    break;
+                }
+        idx[0] = iA;
+        idx[1] = iB;
     } else {
         __shared__ int64_t s_idx64[kTileEvents];
         for (int ev = warp; ev < tile.nev; ev += NW) {
