@@ -62,6 +62,7 @@ class _Runtime(object):
 
     def __init__(self):
         self._ws = {}
+        self._scal = {}
 
     @staticmethod
     def device():
@@ -84,8 +85,19 @@ class _Runtime(object):
         return ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel())
 
     def scalars(self):
-        """A zeroed int64[8] on the device: [0] total, [1] status (low 32 bits), [2:6] info."""
-        return torch.zeros(8, dtype=torch.int64, device=self.device())
+        """A zeroed int64[8] on the device: [0] total, [1] status (low 32 bits), [2:6] info.
+
+        Slices of a pre-zeroed pool (one fill per 512 operations instead of one torch fill kernel per
+        operation); a slice is handed out once, so pending read-backs never alias.
+        """
+        dev = self.device()
+        pool = self._scal.get(dev.index)
+        if pool is None or pool[1] >= pool[0].numel():
+            pool = [torch.zeros(8 * 512, dtype=torch.int64, device=dev), 0]
+            self._scal[dev.index] = pool
+        out = pool[0][pool[1]:pool[1] + 8]
+        pool[1] += 8
+        return out
 
     @staticmethod
     def read(scal):

@@ -271,8 +271,15 @@ def run_gpu(args):
     if ops:
         step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "greater_f32", "mask_select_f32", "offsets2counts"]
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = float(sum(json.load(f)[dom]["kernels"].values()))
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peaks[0], "unit": "GB/s",
-                "frac": ops[dom]["gbs"] / peaks[0], "traffic": None, "peak_source": peaks[1],
+                "frac": ops[dom]["gbs"] / peaks[0], "traffic": traffic, "peak_source": peaks[1],
+                "traffic_source": "ncu --set full dram bytes of the op's kernels, profiles/r1_traffic.json",
                 "algorithmic_bytes": ops[dom]["bytes"], "ms": ops[dom]["ms"],
                 "step_share": ops[dom]["ms"] / sum(ops[k]["ms"] for k in step_ops)}
 
