@@ -102,16 +102,15 @@ __device__ __forceinline__ void stage_bulk(unsigned char *smem, const unsigned c
 // ALL threads: copy the unaligned head and tail (< 16 bytes each) by ordinary loads; returns the shift.
 template <int ELEM>
 __device__ __forceinline__ uint32_t stage_edges(unsigned char *smem, const unsigned char *g, uint32_t nbytes) {
-    const StageSplit s = stage_split(g, nbytes);
-    for (uint32_t b = threadIdx.x * ELEM; b < s.head; b += blockDim.x * ELEM) {
-#pragma unroll
-        for (int k = 0; k < ELEM; ++k) smem[s.shift + b + k] = g[b + k];
+    const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15);
+    if (threadIdx.x < 32) {      // at most 15 + 15 bytes: one warp is plenty, the others skip the address arithmetic
+        const StageSplit s = stage_split(g, nbytes);
+        const uint32_t b0 = threadIdx.x;
+        if (b0 < s.head) smem[s.shift + b0] = g[b0];
+        const uint32_t b1 = s.head + s.mid + threadIdx.x;
+        if (b1 < nbytes) smem[s.shift + b1] = g[b1];
     }
-    for (uint32_t b = s.head + s.mid + threadIdx.x * ELEM; b < nbytes; b += blockDim.x * ELEM) {
-#pragma unroll
-        for (int k = 0; k < ELEM; ++k) smem[s.shift + b + k] = g[b + k];
-    }
-    return s.shift;
+    return shift;
 }
 
 template <int ELEM>
