@@ -238,6 +238,7 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     if (e1 - e0 <= KM) {
         const int L = static_cast<int>(e1 - e0);
+#pragma unroll 1
         for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = load_as<C>(flat, rhs_dt, tile.event0 + ev);
         build_owner_table(s_own, tile, L);
         const int64_t d0 = e0 - o0;

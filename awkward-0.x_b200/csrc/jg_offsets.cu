@@ -156,9 +156,11 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         // short events: scatter + max-scan owner table in shared memory, then a coalesced element-parallel sweep
         const int L = static_cast<int>(e1 - e0);
         if (MODE == EXPAND_BROADCAST)
+#pragma unroll 1
             for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = flat[tile.event0 + ev];
         build_owner_table(s_own, tile, L);
         V *dst = (MODE == EXPAND_PARENTS) ? out + e0 : out + (e0 - o0);
+#pragma unroll 2
         for (int p = threadIdx.x; p < L; p += kTileThreads) {
             const int ev = s_own[p];
             if (MODE == EXPAND_PARENTS) __stcs(dst + p, static_cast<V>(tile.event0 + ev));

@@ -224,6 +224,7 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
             if (evA < tile.nev) out[tile.event0 + evA] = accA;
             if (evB < tile.nev) out[tile.event0 + evB] = accB;
         } else {
+#pragma unroll 1
             for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) out[tile.event0 + ev] = R::identity();
         }
         return;
@@ -341,6 +342,7 @@ segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets
             sm = reinterpret_cast<const T *>(s_stage + shift);
         }
         int nvalid = 0;
+#pragma unroll 1
         for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
             const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
             int idx = -1;

@@ -137,6 +137,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
             run += __popc(b);
         }
         __syncthreads();
+#pragma unroll 1
         for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
             new_offsets[tile.event0 + ev] = base + s_pfx[s_off[ev] - e0];
         return;

@@ -22,7 +22,15 @@ struct EventTile {
         event0 = tile_index * kTileEvents;
         const int64_t left = n - event0;
         nev = left < kTileEvents ? static_cast<int>(left) : kTileEvents;
-        for (int i = threadIdx.x; i <= nev; i += kTileThreads) s_off[i] = __ldg(offsets + event0 + i);
+        // nev + 1 <= 513 entries, 256 threads: two predicated loads per thread + one straggler (a strided loop
+        // here is unrolled by the compiler into 8/4/2/1 cascades that every warp walks through)
+        {
+            const int i0 = threadIdx.x, i1 = threadIdx.x + kTileThreads;
+            const int64_t *src = offsets + event0;
+            if (i0 <= nev) s_off[i0] = __ldg(src + i0);
+            if (i1 <= nev) s_off[i1] = __ldg(src + i1);
+            if (threadIdx.x == 0 && nev == 2 * kTileThreads) s_off[nev] = __ldg(src + nev);
+        }
         __syncthreads();
     }
     // the tile's event range without touching memory (for the early bulk copy)
@@ -147,6 +155,7 @@ __device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile
     __syncthreads();
     // 2. scatter: non-empty events have distinct first positions
     const int64_t e0 = tile.off[0];
+#pragma unroll 1
     for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
         const int64_t a = tile.off[ev], b = tile.off[ev + 1];
         if (b > a) own[a - e0] = static_cast<uint16_t>(ev);
