@@ -117,6 +117,7 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
     for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
         const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
         const int64_t na = s_oa[ev + 1] - s_oa[ev];
@@ -148,6 +149,7 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
     for (int64_t pb = p0 + threadIdx.x; pb < p1; pb += 2 * kTileThreads) {
         int64_t ia[2], ib[2];
 #pragma unroll

@@ -243,6 +243,7 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
         build_owner_table(s_own, tile, L);
         const int64_t d0 = e0 - o0;
         // 4 independent loads in flight per thread (the sweep is otherwise one dependent load per iteration)
+#pragma unroll 1
         for (int p = threadIdx.x; p < L; p += 4 * kTileThreads) {
             C a[4];
             int ev[4];

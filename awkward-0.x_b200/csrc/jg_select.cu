@@ -210,6 +210,7 @@ index_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__ o
     if (table) build_owner_table(s_own, itile, static_cast<int>(k1 - k0));
     // element-parallel over the index run of this tile: coalesced reads of index, coalesced writes of out;
     // 4 independent (index -> content) load chains in flight per thread
+#pragma unroll 1
     for (int64_t kb = k0 + threadIdx.x; kb < k1; kb += 4 * kTileThreads) {
         int64_t ix[4], src[4];
 #pragma unroll

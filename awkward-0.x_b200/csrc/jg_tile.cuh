@@ -151,6 +151,7 @@ __device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile
     constexpr int NW = kTileThreads / kWarp;
     const int padded = (L + 127) & ~127;
     // 1. clear (128-bit stores)
+#pragma unroll 1
     for (int q = threadIdx.x; q < padded / 8; q += kTileThreads) reinterpret_cast<uint4 *>(own)[q] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     // 2. scatter: non-empty events have distinct first positions
@@ -171,6 +172,7 @@ __device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile
         uint32_t carry = 0;
         const int first = r_begin << 7;
         if (first > 0 && first < L) carry = static_cast<uint32_t>(tile.find_event(e0 + first));
+#pragma unroll 1
         for (int r = r_begin; r < r_end; ++r) {
             uint2 w = *reinterpret_cast<const uint2 *>(own + (r << 7) + lane * 4);
             uint32_t v0 = w.x & 0xffffu, v1 = w.x >> 16, v2 = w.y & 0xffffu, v3 = w.y >> 16;
