@@ -16,8 +16,14 @@ namespace jg {
 
 // (i, j) of the k-th pair with i <= j in an event of n items; rows are i, row i holds n - i entries
 __device__ __forceinline__ void unrank_pairs(int64_t k, int64_t n, int64_t &i, int64_t &j) {
-    const double b = 2.0 * static_cast<double>(n) + 1.0;
-    int64_t r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    int64_t r;
+    if (n < 1024) {       // b*b - 8k < 2^23: exact in float32, the estimate is within one row and corrected below
+        const float b = 2.0f * static_cast<float>(n) + 1.0f;
+        r = static_cast<int64_t>((b - sqrtf(b * b - 8.0f * static_cast<float>(k))) * 0.5f);
+    } else {
+        const double b = 2.0 * static_cast<double>(n) + 1.0;
+        r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    }
     if (r < 0) r = 0;
     if (r > n - 1) r = n - 1;
     // L(r) = r*n - r(r-1)/2 = first index of row r
@@ -29,8 +35,14 @@ __device__ __forceinline__ void unrank_pairs(int64_t k, int64_t n, int64_t &i, i
 
 // (i, j) of the k-th pair with i < j; row i holds n - 1 - i entries
 __device__ __forceinline__ void unrank_distincts(int64_t k, int64_t n, int64_t &i, int64_t &j) {
-    const double b = 2.0 * static_cast<double>(n) - 1.0;
-    int64_t r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    int64_t r;
+    if (n < 1024) {
+        const float b = 2.0f * static_cast<float>(n) - 1.0f;
+        r = static_cast<int64_t>((b - sqrtf(b * b - 8.0f * static_cast<float>(k))) * 0.5f);
+    } else {
+        const double b = 2.0 * static_cast<double>(n) - 1.0;
+        r = static_cast<int64_t>(floor((b - sqrt(b * b - 8.0 * static_cast<double>(k))) * 0.5));
+    }
     if (r < 0) r = 0;
     if (r > n - 2) r = n - 2;
     // L(r) = r*(n-1) - r(r-1)/2
@@ -227,8 +239,14 @@ int jg_comb_offsets(int kind, int k, const int64_t *offsets_a, const int64_t *of
     JG_REQUIRE(kind >= JG_COMB_PAIRS && kind <= JG_COMB_CROSS, "jg_comb_offsets: bad kind %d", kind);
     JG_REQUIRE(kind != JG_COMB_CHOOSE || (k >= 2 && k <= 5), "jg_comb_offsets: choose needs 2 <= k <= 5");
     JG_REQUIRE(kind != JG_COMB_CROSS || offsets_b != nullptr, "jg_comb_offsets: cross needs offsets_b");
-    ScanInComb in{offsets_a, kind == JG_COMB_CROSS ? offsets_b : nullptr, kind, k};
-    return launch_scan(in, n, out_offsets, total, nullptr, ws, ws_bytes, as_stream(stream));
+    // the offsets tile(s) are parked in shared memory by TMA and the per-event count is formed on the fly
+    if (kind == JG_COMB_CROSS)
+        return launch_scan_tma<int64_t, XfComb<2>, kScanTmaItems / 2>(XfComb<2>{kind, k}, offsets_a, offsets_b, n,
+                                                                      out_offsets, total, nullptr, ws, ws_bytes,
+                                                                      as_stream(stream));
+    return launch_scan_tma<int64_t, XfComb<1>, kScanTmaItems>(XfComb<1>{kind, k}, offsets_a,
+                                                              static_cast<const int64_t *>(nullptr), n, out_offsets,
+                                                              total, nullptr, ws, ws_bytes, as_stream(stream));
 }
 
 int jg_comb_fill(int kind, int k, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,

@@ -206,16 +206,38 @@ constexpr int kScanTmaThreads = 128;
 constexpr int kScanTmaItems = 32;                                   // per thread
 constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 4096 items
 
-template <typename T, typename S>     // T = stored item type, S = in-tile accumulator (int32 fast path / int64)
-__device__ __forceinline__ void scan_tma_rows(const T *sm, int valid, int wbase, int lane, int64_t run,
-                                              int64_t *__restrict__ out, int64_t i0, int64_t n, bool out_aligned) {
-    constexpr int ROWS = kScanTmaItems / 2;
+// what a staged tile means: the items themselves, or offsets whose differences feed a combinatorial count
+struct XfIdentity {
+    static constexpr int EXTRA = 0;      // staged entries beyond the tile's items
+    static constexpr int ARRAYS = 1;
+    int kind, k;
+    template <typename T>
+    __device__ __forceinline__ int64_t item(const T *a, const T *, int p) const { return static_cast<int64_t>(a[p]); }
+};
+template <int NARR>
+struct XfComb {
+    static constexpr int EXTRA = 1;
+    static constexpr int ARRAYS = NARR;
+    int kind, k;
+    template <typename T>
+    __device__ __forceinline__ int64_t item(const T *a, const T *b, int p) const {
+        const int64_t na = static_cast<int64_t>(a[p + 1]) - static_cast<int64_t>(a[p]);
+        const int64_t nb = NARR == 2 ? static_cast<int64_t>(b[p + 1]) - static_cast<int64_t>(b[p]) : 0;
+        return comb_count(kind, k, na, nb);
+    }
+};
+
+template <typename T, typename S, class XF, int ITEMS>     // S = in-tile accumulator (int32 fast path / int64)
+__device__ __forceinline__ void scan_tma_rows(const XF &xf, const T *sa, const T *sb, int valid, int wbase, int lane,
+                                              int64_t run, int64_t *__restrict__ out, int64_t i0, int64_t n,
+                                              bool out_aligned) {
+    constexpr int ROWS = ITEMS / 2;
     S carry = 0;
 #pragma unroll 4
     for (int r = 0; r < ROWS; ++r) {
         const int p = wbase + r * 64 + lane * 2;
-        const S x = p < valid ? static_cast<S>(sm[p]) : S(0);
-        const S y = p + 1 < valid ? static_cast<S>(sm[p + 1]) : S(0);
+        const S x = p < valid ? static_cast<S>(xf.item(sa, sb, p)) : S(0);
+        const S y = p + 1 < valid ? static_cast<S>(xf.item(sa, sb, p + 1)) : S(0);
         const S s2 = x + y;
         S incl = s2;
 #pragma unroll
@@ -238,38 +260,47 @@ __device__ __forceinline__ void scan_tma_rows(const T *sm, int valid, int wbase,
     }
 }
 
-template <typename T>
+template <typename T, class XF, int ITEMS>
 __global__ void __launch_bounds__(kScanTmaThreads)
-scan_tma_kernel(const T *__restrict__ in, int64_t n, int64_t *__restrict__ out, int64_t *__restrict__ total,
-                int32_t *__restrict__ status, LookbackWs *__restrict__ ws, uint32_t ntiles, bool out_aligned) {
+scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, int64_t n, int64_t *__restrict__ out,
+                int64_t *__restrict__ total, int32_t *__restrict__ status, LookbackWs *__restrict__ ws, uint32_t ntiles,
+                bool out_aligned) {
     constexpr int NW = kScanTmaThreads / kWarp;
-    __shared__ __align__(16) unsigned char s_raw[kScanTmaTile * sizeof(T) + 32];
-    __shared__ uint64_t s_bar;
+    constexpr int TILE = kScanTmaThreads * ITEMS;
+    __shared__ __align__(16) unsigned char s_raw_a[(TILE + XF::EXTRA) * sizeof(T) + 32];
+    __shared__ __align__(16) unsigned char s_raw_b[XF::ARRAYS == 2 ? (TILE + XF::EXTRA) * sizeof(T) + 32 : 16];
+    __shared__ uint64_t s_bar[2];
     __shared__ int64_t s_warp[NW + 1];
     __shared__ int64_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    const int64_t i0 = static_cast<int64_t>(tile) * kScanTmaTile;
+    const int64_t i0 = static_cast<int64_t>(tile) * TILE;
     const int64_t left = n - i0;
-    const int valid = left < kScanTmaTile ? static_cast<int>(left < 0 ? 0 : left) : kScanTmaTile;
+    const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
 
-    stage_init(&s_bar, 1);
-    const T *sm = reinterpret_cast<const T *>(s_raw);
+    stage_init(s_bar, 2);
+    const T *sa = reinterpret_cast<const T *>(s_raw_a);
+    const T *sb = reinterpret_cast<const T *>(s_raw_b);
     if (valid > 0) {
-        const uint32_t shift = stage_issue<sizeof(T)>(s_raw, reinterpret_cast<const unsigned char *>(in + i0),
-                                                      static_cast<uint32_t>(valid * sizeof(T)), &s_bar);
-        stage_wait(&s_bar, 0);
-        sm = reinterpret_cast<const T *>(s_raw + shift);
+        const uint32_t bytes = static_cast<uint32_t>((valid + XF::EXTRA) * sizeof(T));
+        const uint32_t sha = stage_issue<sizeof(T)>(s_raw_a, reinterpret_cast<const unsigned char *>(in_a + i0), bytes, &s_bar[0]);
+        sa = reinterpret_cast<const T *>(s_raw_a + sha);
+        if (XF::ARRAYS == 2) {
+            const uint32_t shb = stage_issue<sizeof(T)>(s_raw_b, reinterpret_cast<const unsigned char *>(in_b + i0), bytes, &s_bar[1]);
+            sb = reinterpret_cast<const T *>(s_raw_b + shb);
+            mbar_wait(&s_bar[1], 0);
+        }
+        stage_wait(&s_bar[0], 0);
     }
     // phase A: warp sums + validity flags
-    const int wbase = warp * (kScanTmaItems * kWarp);
+    const int wbase = warp * (ITEMS * kWarp);
     int64_t sum = 0;
     bool neg = false, big = false;
 #pragma unroll 4
-    for (int r = 0; r < kScanTmaItems / 2; ++r) {
+    for (int r = 0; r < ITEMS / 2; ++r) {
         const int p = wbase + r * 64 + lane * 2;
-        const int64_t x = p < valid ? static_cast<int64_t>(sm[p]) : 0;
-        const int64_t y = p + 1 < valid ? static_cast<int64_t>(sm[p + 1]) : 0;
+        const int64_t x = p < valid ? xf.item(sa, sb, p) : 0;
+        const int64_t y = p + 1 < valid ? xf.item(sa, sb, p + 1) : 0;
         neg |= (x < 0) | (y < 0);
         big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
         sum += x + y;
@@ -294,14 +325,15 @@ scan_tma_kernel(const T *__restrict__ in, int64_t n, int64_t *__restrict__ out, 
     }
     __syncthreads();
     const int64_t run = s_base + s_warp[warp];
-    if (wide) scan_tma_rows<T, int64_t>(sm, valid, wbase, lane, run, out, i0, n, out_aligned);
-    else scan_tma_rows<T, int32_t>(sm, valid, wbase, lane, run, out, i0, n, out_aligned);
+    if (wide) scan_tma_rows<T, int64_t, XF, ITEMS>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+    else scan_tma_rows<T, int32_t, XF, ITEMS>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
 }
 
-template <typename T>
-int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws,
-                      size_t ws_bytes, cudaStream_t stream) {
-    const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, kScanTmaTile);
+template <typename T, class XF, int ITEMS>
+int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
+                    int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    constexpr int TILE = kScanTmaThreads * ITEMS;
+    const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
     const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;
     JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
     JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
@@ -313,13 +345,21 @@ int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int3
     }
     static bool carveout_set = false;
     if (!carveout_set) {
-        cudaFuncSetAttribute(scan_tma_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(scan_tma_kernel<T, XF, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         carveout_set = true;
     }
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    scan_tma_kernel<T><<<static_cast<unsigned>(ntiles), kScanTmaThreads, 0, stream>>>(
-        in, n, out, total, status, reinterpret_cast<LookbackWs *>(ws), static_cast<uint32_t>(ntiles), out_aligned);
+    scan_tma_kernel<T, XF, ITEMS><<<static_cast<unsigned>(ntiles), kScanTmaThreads, 0, stream>>>(
+        xf, in_a, in_b, n, out, total, status, reinterpret_cast<LookbackWs *>(ws), static_cast<uint32_t>(ntiles),
+        out_aligned);
     return check_launch("scan_tma_kernel");
+}
+
+template <typename T>
+int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws,
+                      size_t ws_bytes, cudaStream_t stream) {
+    return launch_scan_tma<T, XfIdentity, kScanTmaItems>(XfIdentity{0, 0}, in, static_cast<const T *>(nullptr), n, out,
+                                                        total, status, ws, ws_bytes, stream);
 }
 
 // Host launcher.  `out` has n+1 entries: out[i] = sum of items before i, out[n] = grand total.
