@@ -16,6 +16,18 @@ namespace jg {
 
 // (i, j) of the k-th pair with i <= j in an event of n items; rows are i, row i holds n - i entries
 __device__ __forceinline__ void unrank_pairs(int64_t k, int64_t n, int64_t &i, int64_t &j) {
+    if (n <= 48) {
+        // short events (the common case): walk the rows -- a handful of 32-bit subtractions beats the square root
+        int m = static_cast<int>(k), row = static_cast<int>(n), r32 = 0;
+        while (m >= row) {
+            m -= row;
+            --row;
+            ++r32;
+        }
+        i = r32;
+        j = r32 + m;
+        return;
+    }
     int64_t r;
     if (n < 1024) {       // b*b - 8k < 2^23: exact in float32, the estimate is within one row and corrected below
         const float b = 2.0f * static_cast<float>(n) + 1.0f;
@@ -35,6 +47,17 @@ __device__ __forceinline__ void unrank_pairs(int64_t k, int64_t n, int64_t &i, i
 
 // (i, j) of the k-th pair with i < j; row i holds n - 1 - i entries
 __device__ __forceinline__ void unrank_distincts(int64_t k, int64_t n, int64_t &i, int64_t &j) {
+    if (n <= 48) {
+        int m = static_cast<int>(k), row = static_cast<int>(n) - 1, r32 = 0;
+        while (m >= row) {
+            m -= row;
+            --row;
+            ++r32;
+        }
+        i = r32;
+        j = r32 + 1 + m;
+        return;
+    }
     int64_t r;
     if (n < 1024) {
         const float b = 2.0f * static_cast<float>(n) - 1.0f;
@@ -95,8 +118,14 @@ __device__ __forceinline__ CombIndex unrank(int64_t m, int64_t na, int64_t nb, i
     } else if constexpr (KIND == JG_COMB_DISTINCTS) {
         unrank_distincts(m, na, r.v[0], r.v[1]);
     } else if constexpr (KIND == JG_COMB_CROSS) {
-        r.v[0] = m / nb;
-        r.v[1] = m - r.v[0] * nb;
+        if ((m | nb) < (1ll << 31)) {
+            const uint32_t q = static_cast<uint32_t>(m) / static_cast<uint32_t>(nb);
+            r.v[0] = q;
+            r.v[1] = static_cast<uint32_t>(m) - q * static_cast<uint32_t>(nb);
+        } else {
+            r.v[0] = m / nb;
+            r.v[1] = m - r.v[0] * nb;
+        }
     } else {
         // columns are i1 < i2 < ... < ik; the largest index is found first
         for (int q = k; q >= 2; --q) {

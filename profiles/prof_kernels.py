@@ -47,5 +47,27 @@ for rep in range(3):
     _lib.call("jg_offsets2counts", off.data_ptr(), N, _vp(i64b), st())
     _lib.call("jg_offsets2parents", off.data_ptr(), N, _vp(par), st())
     _lib.call("jg_broadcast", _vp(f32), 4, off.data_ptr(), N, _vp(sel), st())
+# combinatorics on a dimuon-like shard (Poisson(2))
+Nc = N // 2
+mu_off = ak.JaggedArray.counts2offsets(ak.asdevice(rng.poisson(2.0, Nc).astype(np.int64)))
+Mmu = int(mu_off[-1])
+mu_pt = ak.asdevice(rng.exponential(20.0, Mmu).astype(np.float32))
+poff = empty(Nc + 1, np.int64)
+_lib.call("jg_comb_offsets", _lib.COMB_PAIRS, 2, mu_off.data_ptr(), ctypes.c_void_p(0), Nc, _vp(poff), _vp(scal), ws, wsb, st())
+P = int(scal.cpu()[0])
+c0, c1 = empty(P, np.int64), empty(P, np.int64)
+arr = (ctypes.c_void_p * 2)(c0.data_ptr(), c1.data_ptr())
+l, r = empty(P, np.float32), empty(P, np.float32)
+flat = ak.asdevice(rng.normal(size=N).astype(np.float32))
+lead = a.argmax()
+gout = empty(len(lead.content), np.float32)
+for rep in range(2):
+    _lib.call("jg_comb_offsets", _lib.COMB_PAIRS, 2, mu_off.data_ptr(), ctypes.c_void_p(0), Nc, _vp(poff), _vp(scal), ws, wsb, st())
+    _lib.call("jg_comb_fill", _lib.COMB_PAIRS, 2, mu_off.data_ptr(), ctypes.c_void_p(0), Nc, _vp(poff), arr, 0, st())
+    _lib.call("jg_comb_gather2", _lib.COMB_PAIRS, mu_off.data_ptr(), ctypes.c_void_p(0), Nc, _vp(poff), mu_pt.data_ptr(), 4, mu_pt.data_ptr(), 4, _vp(l), _vp(r), st())
+    _lib.call("jg_binary", _lib.OP["ADD"], pt_d.data_ptr(), _lib.JG_F32, flat.data_ptr(), _lib.JG_F32, _lib.RHS_PARENT,
+              ctypes.c_double(0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(sel), _lib.JG_F32, M, off.data_ptr(), N, st())
+    _lib.call("jg_index_gather", pt_d.data_ptr(), 4, off.data_ptr(), lead.content.data_ptr(), _lib.JG_I64,
+              lead._off64.data_ptr(), N, _vp(gout), _vp(scal, 1), st())
 torch.cuda.synchronize()
-print("ok", N, M)
+print("ok", N, M, P)
