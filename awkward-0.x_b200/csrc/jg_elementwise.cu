@@ -157,6 +157,13 @@ __device__ __forceinline__ void load_pack(const T *p, T (&dst)[N]) {
 
 template <typename T, int N>
 __device__ __forceinline__ void store_pack(T *p, const T (&src)[N]) {
+    if constexpr (N * sizeof(T) == 8) {          // 8 one-byte results: one 64-bit store
+        union { uint2 raw; T v[N]; } q;
+#pragma unroll
+        for (int e = 0; e < N; ++e) q.v[e] = src[e];
+        __stcs(reinterpret_cast<uint2 *>(p), q.raw);
+        return;
+    }
     constexpr int PER = 16 / sizeof(T);
 #pragma unroll
     for (int k = 0; k < N / PER; ++k) {
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(256)
 binary_vec_kernel(const C *__restrict__ lhs, const C *__restrict__ rhs, bool rhs_scalar, C scalar, int swap,
                   typename F::Out *__restrict__ out, int64_t nchunks) {
     using O = typename F::Out;
-    constexpr int EPT = 16;
+    constexpr int EPT = sizeof(C) == 8 ? 8 : 16;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
         C a[EPT], b[EPT];
@@ -194,7 +201,7 @@ template <class F, typename C>
 __global__ void __launch_bounds__(256)
 unary_vec_kernel(const C *__restrict__ in, typename F::Out *__restrict__ out, int64_t nchunks) {
     using O = typename F::Out;
-    constexpr int EPT = 16;
+    constexpr int EPT = sizeof(C) == 8 ? 8 : 16;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
         C a[EPT];
@@ -224,7 +231,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 // rhs is flat[N]; lhs/out are dense contents starting at offsets[0].  The flat values of the tile's events and the
 // owner of every position (scatter + max-scan table, jg_tile.cuh) are kept in shared memory: the broadcast of
 // jagged.py:1003-1037 is never materialised.
-template <class F, typename C>
+template <class F, typename C, bool TYPED>      // TYPED: both operands already have the compute type (no per-element dtype switch)
 __global__ void __launch_bounds__(kTileThreads)
 binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__restrict__ flat, int rhs_dt, int swap,
                      typename F::Out *__restrict__ out, const int64_t *__restrict__ offsets, int64_t n) {
@@ -239,7 +246,8 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
     if (e1 - e0 <= KM) {
         const int L = static_cast<int>(e1 - e0);
 #pragma unroll 1
-        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = load_as<C>(flat, rhs_dt, tile.event0 + ev);
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
+            s_flat[ev] = TYPED ? __ldg(static_cast<const C *>(flat) + tile.event0 + ev) : load_as<C>(flat, rhs_dt, tile.event0 + ev);
         build_owner_table(s_own, tile, L);
         const int64_t d0 = e0 - o0;
         // 4 independent loads in flight per thread (the sweep is otherwise one dependent load per iteration)
@@ -251,7 +259,7 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
             for (int u = 0; u < 4; ++u) {
                 const int q = p + u * kTileThreads;
                 if (q < L) {
-                    a[u] = load_as<C>(lhs, lhs_dt, d0 + q);
+                    a[u] = TYPED ? __ldcs(static_cast<const C *>(lhs) + d0 + q) : load_as<C>(lhs, lhs_dt, d0 + q);
                     ev[u] = s_own[q];
                 }
             }
@@ -292,8 +300,12 @@ static int launch_binary(const BinArgs &a) {
     using O = typename F::Out;
     if (a.rhs_kind == JG_RHS_PARENT) {
         if (a.n <= 0) return 0;
-        binary_parent_kernel<F, C><<<tile_grid(a.n), kTileThreads, 0, a.s>>>(a.lhs, a.lhs_dt, a.rhs, a.rhs_dt, a.swap,
-                                                                             static_cast<O *>(a.out), a.offsets, a.n);
+        if (same_type<C>(a.lhs_dt) && same_type<C>(a.rhs_dt))
+            binary_parent_kernel<F, C, true><<<tile_grid(a.n), kTileThreads, 0, a.s>>>(
+                a.lhs, a.lhs_dt, a.rhs, a.rhs_dt, a.swap, static_cast<O *>(a.out), a.offsets, a.n);
+        else
+            binary_parent_kernel<F, C, false><<<tile_grid(a.n), kTileThreads, 0, a.s>>>(
+                a.lhs, a.lhs_dt, a.rhs, a.rhs_dt, a.swap, static_cast<O *>(a.out), a.offsets, a.n);
         return check_launch("binary_parent_kernel");
     }
     if (a.len <= 0) return 0;
@@ -304,11 +316,12 @@ static int launch_binary(const BinArgs &a) {
     int64_t done = 0;
     if (same_type<C>(a.lhs_dt) && (rhs_scalar || same_type<C>(a.rhs_dt)) && aligned16(a.lhs) && aligned16(a.out) &&
         (rhs_scalar || aligned16(a.rhs)) && a.len >= 16) {
-        const int64_t nchunks = a.len / 16;
+        constexpr int EPT = sizeof(C) == 8 ? 8 : 16;
+        const int64_t nchunks = a.len / EPT;
         binary_vec_kernel<F, C><<<ew_grid(nchunks), 256, 0, a.s>>>(static_cast<const C *>(a.lhs),
                                                                   static_cast<const C *>(a.rhs), rhs_scalar, scalar,
                                                                   a.swap, static_cast<O *>(a.out), nchunks);
-        done = nchunks * 16;
+        done = nchunks * EPT;
         if (done == a.len) return check_launch("binary_vec_kernel");
     }
     // scalar tail / unaligned / mixed-dtype operands
@@ -427,9 +440,10 @@ static int launch_unary(const void *in, int in_dt, void *out, int64_t len, cudaS
     using O = typename F::Out;
     int64_t done = 0;
     if (same_type<C>(in_dt) && aligned16(in) && aligned16(out) && len >= 16) {
-        const int64_t nchunks = len / 16;
+        constexpr int EPT = sizeof(C) == 8 ? 8 : 16;
+        const int64_t nchunks = len / EPT;
         unary_vec_kernel<F, C><<<ew_grid(nchunks), 256, 0, s>>>(static_cast<const C *>(in), static_cast<O *>(out), nchunks);
-        done = nchunks * 16;
+        done = nchunks * EPT;
         if (done == len) return check_launch("unary_vec_kernel");
     }
     unary_kernel<F, C><<<ew_grid(len - done), 256, 0, s>>>(static_cast<const char *>(in) + done * dtype_size(in_dt), in_dt,

@@ -407,6 +407,24 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         ctypes.c_double(0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(bout), _lib.JG_F32, M, off.data_ptr(), N, st()))
     del bout
 
+    # float64 content (BASELINE configs[1] names float32/float64): same offsets, values cast up
+    pt64 = ak.DeviceArray(pt_dev.tensor.double())
+    out64 = empty(N, np.float64)
+    add("segreduce_sum_f64", 8 * M + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_segreduce", pt64.data_ptr(), _lib.JG_F64, off.data_ptr(), N, _lib.SUM, _vp(out64), M, st()))
+    aoff64, aidx64 = empty(N + 1, np.int64), empty(N, np.int64)
+    add("segargmax_dense_f64", 8 * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_segargminmax_dense", pt64.data_ptr(), _lib.JG_F64, off.data_ptr(), N, 0, _vp(aoff64), _vp(aidx64), _vp(scal),
+        _vp(scal, 1), ws, wsb, st()))
+    mask64 = empty(M, np.bool_)
+    add("greater_f64", 8 * M + M, M, lambda: _lib.call(
+        "jg_binary", _lib.OP["GT"], pt64.data_ptr(), _lib.JG_F64, ctypes.c_void_p(0), 0, _lib.RHS_SCALAR,
+        ctypes.c_double(THRESHOLD), ctypes.c_int64(0), 0, _lib.JG_F64, _vp(mask64), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st()))
+    sel64 = empty(M, np.float64)
+    add("mask_select_f64", 8 * M + M + 8 * N + 8 * K + 8 * N, M, lambda: _lib.call(
+        "jg_mask_select", pt64.data_ptr(), 8, _vp(mask64), 0, off.data_ptr(), N, _vp(sel64), _vp(noff), _vp(scal), ws, wsb, st()))
+    del pt64, out64, aoff64, aidx64, mask64, sel64
+
     # combinatorics on a dimuon-like shard (BASELINE configs[3]: Poisson(2) counts)
     Nc = args.comb_events
     rng = np.random.default_rng(4242)
