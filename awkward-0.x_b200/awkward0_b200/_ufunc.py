@@ -92,6 +92,27 @@ def take(content, index):
     return DeviceArray(out, content.dtype)
 
 
+def compress(columns, mask):
+    """[col[mask] for col in columns] for a flat boolean DeviceArray mask (one scan, one scatter per column)."""
+    if mask.dtype != numpy.bool_:
+        raise TypeError("boolean selection needs a bool mask")
+    n = len(mask)
+    for col in columns:
+        if len(col) != n:
+            raise IndexError("boolean index did not match indexed array along axis 0; size of axis is {0} but size of corresponding boolean axis is {1}".format(len(col), n))
+    positions = empty(n + 1, numpy.int64)
+    scal = runtime.scalars()
+    ws, wsb = runtime.workspace(n)
+    outs = []
+    for col in columns:
+        out = empty(n, col.dtype)
+        call("jg_flat_compact", col.data_ptr(), col.itemsize, mask.data_ptr(), n, ctypes.c_void_p(out.data_ptr()),
+             ctypes.c_void_p(positions.data_ptr()), ctypes.c_void_p(scal.data_ptr()), ws, wsb, runtime.stream())
+        outs.append(out)
+    total, _, _ = runtime.read(scal)
+    return [DeviceArray(o[:total], c.dtype) for o, c in zip(outs, columns)]
+
+
 def unary(ufunc, x):
     name = _UNARY.get(ufunc)
     if name is None:

@@ -230,10 +230,15 @@ class DeviceArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             if not 0 <= i < n:
                 raise IndexError("index {0} is out of bounds for axis 0 with size {1}".format(where, n))
             return self[i:i + 1].get()[0]
+        if isinstance(where, (list, numpy.ndarray)):
+            where = asdevice(numpy.asarray(where))
         if isinstance(where, DeviceArray) and where.dtype.kind in "iu":
             from . import _ufunc
             return _ufunc.take(self, where)
-        raise NotImplementedError("DeviceArray supports integer, slice and integer-array indexing only")
+        if isinstance(where, DeviceArray) and where.dtype == numpy.bool_:
+            from . import _ufunc
+            return _ufunc.compress([self], where)[0]
+        raise NotImplementedError("DeviceArray supports integer, slice, integer-array and boolean-array indexing only")
 
     def __bool__(self):
         if len(self) == 1:

@@ -263,6 +263,17 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return out
 
     @classmethod
+    def _from_general(cls, s64, e64, content):
+        """Internal constructor: a valid general (starts, stops) layout selected from a valid array."""
+        out = cls.__new__(cls)
+        out._reset()
+        out._content = content
+        out._starts, out._stops = s64, e64
+        out._general = (s64, e64)
+        out._isvalid = True
+        return out
+
+    @classmethod
     def fromiter(cls, iterable):
         """Host-side builder (generate.py is out of scope): nested python lists -> counts + content -> device."""
         rows = [list(x) for x in iterable]
@@ -711,7 +722,32 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                 return out
             return JaggedArray(self._starts[start:stop], self._stops[start:stop], self._content)
 
-        raise NotImplementedError("event-level selection with flat boolean / integer arrays is outside the round-1 GPU hot path (SURVEY.md section 8f-1); no CPU fallback")
+        # event-level selection with a flat boolean / integer array (jagged.py:599-605): new starts/stops over
+        # the SAME content; like the reference the result is not dense and is compacted on first use
+        if isinstance(where, (list, numpy.ndarray)):
+            where = asdevice(numpy.asarray(where))
+        if isinstance(where, DeviceArray):
+            if self._off64 is not None:
+                s64, e64 = self._off64[:-1], self._off64[1:]
+            else:
+                s64, e64 = self._general
+            if where.dtype == numpy.bool_:
+                if len(where) != len(self):
+                    raise IndexError("boolean index did not match indexed array along axis 0; size of axis is {0} but size of corresponding boolean axis is {1}".format(len(self), len(where)))
+                s_sel, e_sel = _ufunc.compress([s64, e64], where)
+                return self._from_general(s_sel, e_sel, self._content)
+            if where.dtype.kind in "iu":
+                n = len(self)
+                idx = where if where.dtype == numpy.int64 else where.astype(numpy.int64)
+                if len(idx) and n == 0:
+                    raise IndexError("index out of bounds for an empty JaggedArray")
+                neg = idx < 0
+                if bool(neg.any()):
+                    idx = idx + neg.astype(numpy.int64) * n
+                if len(idx) and (int(idx.min()) < 0 or int(idx.max()) >= n):
+                    raise IndexError("index is out of bounds for axis 0 with size {0}".format(n))
+                return self._from_general(_ufunc.take(s64, idx), _ufunc.take(e64, idx), self._content)
+        raise NotImplementedError("this kind of JaggedArray index is outside the GPU hot path (SURVEY.md section 8f-1); no CPU fallback")
 
     def _align(self, other):
         """_tojagged(self.starts, self.stops) of jagged.py:573/971-973: `other` must have my counts."""

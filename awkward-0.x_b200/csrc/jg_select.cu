@@ -274,6 +274,16 @@ scatter_nonneg_kernel(const int64_t *__restrict__ best, int64_t n, const int64_t
     }
 }
 
+// out[pos[i]] = content[i] for mask[i] != 0   (flat boolean selection, jagged.py:599-605 applied to starts/stops)
+template <typename V>
+__global__ void __launch_bounds__(256)
+flat_scatter_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask, const int64_t *__restrict__ pos,
+                    int64_t n, V *__restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (mask[i]) out[__ldg(pos + i)] = content[i];
+}
+
 static inline int flat_grid(int64_t work, int threads) {
     int64_t blocks = ceil_div(work, threads);
     int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -401,6 +411,25 @@ int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_i
             return -2;
     }
     return check_launch("take_kernel");
+}
+
+int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int64_t n, void *out, int64_t *positions,
+                    int64_t *total, void *ws, size_t ws_bytes, void *stream) {
+    JG_REQUIRE(n >= 0 && positions != nullptr, "jg_flat_compact: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    int rc = launch_scan_array(mask, n, positions, total, nullptr, ws, ws_bytes, s);
+    if (rc || n == 0 || content == nullptr) return rc;
+    const int g = flat_grid(n, 256);
+    switch (itemsize) {
+        case 1: flat_scatter_kernel<uint8_t><<<g, 256, 0, s>>>(static_cast<const uint8_t *>(content), mask, positions, n, static_cast<uint8_t *>(out)); break;
+        case 2: flat_scatter_kernel<uint16_t><<<g, 256, 0, s>>>(static_cast<const uint16_t *>(content), mask, positions, n, static_cast<uint16_t *>(out)); break;
+        case 4: flat_scatter_kernel<uint32_t><<<g, 256, 0, s>>>(static_cast<const uint32_t *>(content), mask, positions, n, static_cast<uint32_t *>(out)); break;
+        case 8: flat_scatter_kernel<uint64_t><<<g, 256, 0, s>>>(static_cast<const uint64_t *>(content), mask, positions, n, static_cast<uint64_t *>(out)); break;
+        default:
+            set_error("jg_flat_compact: unsupported itemsize %d", itemsize);
+            return -2;
+    }
+    return check_launch("flat_scatter_kernel");
 }
 
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,

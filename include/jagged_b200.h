@@ -157,6 +157,11 @@ int jg_check_same_counts(const int64_t *offsets_a, const int64_t *offsets_b, int
 int jg_index_gather(const void *content, int itemsize, const int64_t *offsets, const void *index,
                     int index_dtype, const int64_t *index_offsets, int64_t n, void *out, int32_t *status,
                     void *stream);
+/* flat boolean selection content[mask] (event-level selection a[flat_bool], jagged.py:599-605): positions
+ * (caller scratch, int64[n+1]) receives the exclusive scan of the mask, *total the number selected; content may
+ * be NULL to run the scan only.  out must hold n items (upper bound).                                              */
+int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int64_t n, void *out, int64_t *positions,
+                    int64_t *total, void *ws, size_t ws_bytes, void *stream);
 /* plain gather out[k] = content[index[k]] (jagged.py:1294 content[left]); no bounds check beyond content_len      */
 int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_index, void *out, void *stream);
 

@@ -151,6 +151,27 @@ def test_localindex_parents(ak):           # test_jagged.py:592-602
     assert b.tolist() == [[], [9.9]] and b.sum().tolist() == [0.0, 9.9]
 
 
+def test_event_level_selection(ak):        # test_jagged.py:592-602 and :99-149 (flat boolean / integer heads)
+    a = ak.JaggedArray.fromiter([[1.1, 2.2, 3.3, 4.4, 5.5], [], [6.6, 7.7, 8.8], [9.9]])
+    b = a[[False, True, False, True]]
+    assert b.tolist() == [[], [9.9]]
+    assert b.localindex.tolist() == [[], [0]]
+    assert b.parents.tolist() == [-1, -1, -1, -1, -1, -1, -1, -1, 1]
+    assert a[a.counts >= 2].tolist() == [[1.1, 2.2, 3.3, 4.4, 5.5], [6.6, 7.7, 8.8]]
+    assert a[a.counts >= 2].sum().tolist() == [16.5, 23.1]
+    assert a[[2, 1, 0]].tolist() == [[6.6, 7.7, 8.8], [], [1.1, 2.2, 3.3, 4.4, 5.5]]
+    assert a[np.array([-1, 0])].tolist() == [[9.9], [1.1, 2.2, 3.3, 4.4, 5.5]]
+    assert a[[0, 0, 3]].max().tolist() == [5.5, 5.5, 9.9]
+    pairs = a[a.counts >= 2].distincts()
+    assert pairs.counts.tolist() == [10, 3]
+    with pytest.raises(IndexError):
+        a[[4]]
+    with pytest.raises(IndexError):
+        a[[True, False]]
+    c = a.counts
+    assert c[c > 0].tolist() == [5, 3, 1] and c[[3, 0]].tolist() == [1, 5]
+
+
 def test_issues(ak):                       # tests/test_issues.py:16-30
     a = ak.JaggedArray.fromoffsets([2, 4, 4, 7], np.arange(10, dtype=np.float64))
     assert a[a > 3].tolist() == [[], [], [4.0, 5.0, 6.0]]
