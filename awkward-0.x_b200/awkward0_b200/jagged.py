@@ -680,8 +680,11 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                 return self
             if len(where) == 1:
                 where = where[0]
+            elif len(where) == 2:
+                node = self if (isinstance(where[0], slice) and where[0] == slice(None)) else self[where[0]]
+                return node._getitem_inner(where[1])
             else:
-                raise NotImplementedError("multi-dimensional JaggedArray slicing is outside the GPU hot path (SURVEY.md section 8f-1)")
+                raise NotImplementedError("JaggedArray slicing in more than two dimensions is outside the GPU hot path (SURVEY.md section 8f-1)")
 
         if isinstance(where, JaggedArray):
             return self._getitem_jagged(where)
@@ -748,6 +751,37 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                     raise IndexError("index is out of bounds for axis 0 with size {0}".format(n))
                 return self._from_general(_ufunc.take(s64, idx), _ufunc.take(e64, idx), self._content)
         raise NotImplementedError("this kind of JaggedArray index is outside the GPU hot path (SURVEY.md section 8f-1); no CPU fallback")
+
+    def _getitem_inner(self, head):
+        """a[:, k] and a[:, i:j] (jagged.py:615-707 for an integer or a unit-step slice), built from device ufuncs."""
+        if self._off64 is not None:
+            s64, e64 = self._off64[:-1], self._off64[1:]
+        else:
+            s64, e64 = self._general
+        counts = e64 - s64
+        if isinstance(head, (int, numpy.integer)):
+            k = int(head)
+            local = (counts + k) if k < 0 else k
+            ok = (local >= 0) & (local < counts) if k < 0 else (counts > k)
+            if len(self) and not bool(ok.all()):
+                raise IndexError("index {0} is out of bounds for jagged min size {1}".format(head, int(counts.min())))
+            return self._map_content(lambda c: _ufunc.take(c, s64 + local))
+        if isinstance(head, slice):
+            if head.step not in (None, 1):
+                raise NotImplementedError("intra-event slices with a step are outside the GPU hot path (SURVEY.md section 8f-1)")
+
+            def bound(v, default):
+                if v is None:
+                    return default
+                if v >= 0:
+                    return numpy.minimum(counts, v)
+                return numpy.maximum(numpy.minimum(counts, counts + v), 0)
+
+            lo = bound(head.start, 0)
+            hi = bound(head.stop, counts)
+            hi = numpy.maximum(lo, hi)
+            return self._from_general(s64 + lo, s64 + hi, self._content)
+        raise NotImplementedError("this kind of intra-event index is outside the GPU hot path (SURVEY.md section 8f-1)")
 
     def _align(self, other):
         """_tojagged(self.starts, self.stops) of jagged.py:573/971-973: `other` must have my counts."""
@@ -955,6 +989,41 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def max(self):
         return self._reduce(_lib.MAX)
+
+    def count(self):
+        """base.py:199-200 / jagged.py:1513-1518: number of non-NaN values per event."""
+        a = self.compact()
+        if isinstance(a._content, DeviceArray) and a._content.dtype.kind == "f":
+            return (~numpy.isnan(a)).sum()
+        return a.counts.astype(INDEXTYPE) if a.counts.dtype != INDEXTYPE else a.counts
+
+    def count_nonzero(self):
+        """base.py:202-203 / jagged.py:1520-1522."""
+        return (self != 0).sum()
+
+    def mean(self, weight=None):
+        """base.py:224-229."""
+        if weight is None:
+            return numpy.true_divide(self.sum(), self.count())
+        return numpy.true_divide((self * weight).sum(), (self * 0 + weight).sum())
+
+    def var(self, weight=None, ddof=0):
+        """base.py:231-244."""
+        if weight is None:
+            denom = self.count()
+            one = numpy.true_divide(self.sum(), denom)
+            two = numpy.true_divide((self ** 2).sum(), denom)
+        else:
+            denom = (self * 0 + weight).sum()
+            one = numpy.true_divide((self * weight).sum(), denom)
+            two = numpy.true_divide(((self * weight) ** 2).sum(), denom)
+        if ddof != 0:
+            return (two - one ** 2) * denom / (denom - ddof)
+        return two - one ** 2
+
+    def std(self, weight=None, ddof=0):
+        """base.py:246-248."""
+        return numpy.sqrt(self.var(weight=weight, ddof=ddof))
 
     def argmin(self):
         return self._argminmax(True)

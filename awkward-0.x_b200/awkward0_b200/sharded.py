@@ -75,6 +75,8 @@ def allreduce_totals(sums=(), maxima=(), minima=(), group=None):
     are reduced with max / min.  Payloads are a few bytes: the cost is launch latency, not bandwidth.
     """
     world, _ = _world(group)
+    if world == 1:
+        return tuple([v.item() if hasattr(v, "item") else v for v in vals] for vals in (sums, maxima, minima))
     device = _device_for(group)
     out = []
     for values, op in ((sums, "sum"), (maxima, "max"), (minima, "min")):

@@ -172,6 +172,28 @@ def test_event_level_selection(ak):        # test_jagged.py:592-602 and :99-149 
     assert c[c > 0].tolist() == [5, 3, 1] and c[[3, 0]].tolist() == [1, 5]
 
 
+def test_intra_event_slices_and_moments(ak):     # test_jagged.py:66-97 (a[2:, 1]), :99-149 (a[:, i:j]); base.py:199-248
+    lists = [[0.0, 1.1, 2.2], [], [3.3, 4.4], [5.5, 6.6, 7.7, 8.8, 9.9]]
+    a = std(ak)
+    assert a[2:, 1].tolist() == [4.4, 6.6] and a[2:, -2].tolist() == [3.3, 8.8]
+    with pytest.raises(IndexError):
+        a[:, 0]
+    for start in (None, 0, 1, 2, -1, -2, 7):
+        for stop in (None, 0, 1, 3, -1, 9):
+            assert a[:, start:stop].tolist() == [x[start:stop] for x in lists], (start, stop)
+    assert a[:, :2].sum().tolist() == [1.1, 0.0, 7.7, 12.1]
+    assert a[a.counts > 0][:, 0].tolist() == [0.0, 3.3, 5.5]
+    b = ak.JaggedArray.fromcounts([3, 0, 2], np.array([1.0, np.nan, 3.0, 0.0, 5.0]))
+    assert b.count().tolist() == [2, 0, 2] and b.count_nonzero().tolist() == [3, 0, 1]
+    with np.errstate(all="ignore"):
+        m = b.mean().tolist()
+    assert m[0] == 2.0 and np.isnan(m[1]) and m[2] == 2.5
+    c = ak.JaggedArray.fromcounts([2, 3], np.array([1.0, 3.0, 2.0, 4.0, 6.0]))
+    assert c.mean().tolist() == [2.0, 4.0]
+    assert np.allclose(c.var().tolist(), [1.0, np.var([2.0, 4.0, 6.0])]) and np.allclose(c.std().tolist(), [1.0, np.std([2.0, 4.0, 6.0])])
+    assert ak.JaggedArray.fromcounts([2, 1], np.array([3, 0, 5])).count().tolist() == [2, 1]
+
+
 def test_issues(ak):                       # tests/test_issues.py:16-30
     a = ak.JaggedArray.fromoffsets([2, 4, 4, 7], np.arange(10, dtype=np.float64))
     assert a[a > 3].tolist() == [[], [], [4.0, 5.0, 6.0]]
