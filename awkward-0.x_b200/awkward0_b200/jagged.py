@@ -489,6 +489,11 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             self._rebased = _ufunc.binary(numpy.subtract, self._off64, numpy.int64(self._first))
         return self._rebased
 
+    def _nested_parts(self):
+        """(compact self, rebased outer offsets, dense inner JaggedArray, number of inner events)."""
+        a, off, n, first, last = self._dense()
+        return a, a._rebased_offsets(), a._dense_content(), last - first
+
     def _dense_content(self, content=None):
         content = self._content if content is None else content
         if self._first == 0 and self._last == len(content):
@@ -522,13 +527,15 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     @property
     def columns(self):
-        return self._content.columns if isinstance(self._content, Table) else []
+        return self._content.columns if isinstance(self._content, (Table, JaggedArray)) else []
 
     def __getattr__(self, where):
         if where.startswith("_"):
             raise AttributeError(where)
         content = self.__dict__.get("_content")
         if isinstance(content, Table) and where in content:
+            return self[where]
+        if isinstance(content, JaggedArray) and where in content.columns:
             return self[where]
         raise AttributeError("no column named {0}".format(repr(where)))
 
@@ -670,7 +677,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def __getitem__(self, where):
         self._valid()
         if isinstance(where, str):
-            if not isinstance(self._content, Table):
+            if not isinstance(self._content, (Table, JaggedArray)):
                 raise ValueError("no column named {0}".format(repr(where)))
             out = self.copy()
             out._content = self._content[where]
@@ -802,8 +809,20 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return b
 
     def _getitem_jagged(self, head):
-        if isinstance(self._content, JaggedArray) and isinstance(head._content, JaggedArray):
-            return self.copy(content=self._content[head._content])
+        if isinstance(self._content, JaggedArray):
+            a, roff, inner, n_inner = self._nested_parts()
+            if len(head) != len(self):
+                raise ValueError("jagged array used as index has a different shape {0} from the jagged array it is selecting from {1}".format(head.shape, self.shape))
+            if isinstance(head._content, JaggedArray):          # jagged.py:538-539: index one level down
+                h = a._align(head)
+                return self._make(roff, inner[h._dense_content()], n_inner)
+            h = head.compact()
+            if isinstance(h._content, DeviceArray) and h._content.dtype == numpy.bool_:
+                # a mask over the INNER EVENTS: event-level selection one level down + new outer offsets
+                h = a._align(h)
+                newoffsets, total, _ = self._scan_counts(h.sum())
+                return self._make(newoffsets, inner[h._dense_content()], total)
+            raise NotImplementedError("integer jagged indexes over nested content are outside the GPU hot path")
         if not isinstance(head._content, DeviceArray):
             raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
         hdt = head._content.dtype
@@ -899,8 +918,25 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             if isinstance(x, JaggedArray):
                 lead = x
         a, off, n, first, last = lead._dense()
-        if isinstance(a._content, (Table, JaggedArray)):
-            raise NotImplementedError("ufuncs on Table / nested content are outside the GPU hot path (no CPU fallback)")
+        if isinstance(a._content, JaggedArray):
+            # jagged-of-jagged (jagged.py:1039-1051): flatten one level, let the inner arrays broadcast, re-wrap
+            inner_ops = []
+            for x in inputs:
+                if isinstance(x, JaggedArray):
+                    b = a._align(x) if x is not lead else a
+                    if not isinstance(b._content, JaggedArray):
+                        raise NotImplementedError("mixing nesting depths in one ufunc is outside the GPU hot path")
+                    inner_ops.append(b._dense_content())
+                elif _ufunc.is_scalar(x):
+                    inner_ops.append(x)
+                else:
+                    flat = asdevice(x) if not isinstance(x, DeviceArray) else x
+                    if flat.shape != (n,):
+                        raise ValueError("cannot broadcast JaggedArray of shape {0} with array of shape {1}".format((n,), flat.shape))
+                    inner_ops.append(a.tojagged(flat)._content)
+            return self._make(a._rebased_offsets(), ufunc(*inner_ops), last - first)
+        if isinstance(a._content, Table):
+            raise NotImplementedError("ufuncs on Table content are outside the GPU hot path (no CPU fallback)")
 
         operands, parent_side = [], None
         for i, x in enumerate(inputs):
@@ -957,8 +993,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def _reduce(self, op):
         a, off, n, first, last = self._dense()
-        if isinstance(a._content, JaggedArray):
-            return self.copy(content=a._content._reduce(op))
+        if isinstance(a._content, JaggedArray):      # jagged.py:1463-1464: reduce the innermost level
+            return self._make(a._rebased_offsets(), a._dense_content()._reduce(op), last - first)
         if isinstance(a._content, Table):
             out = Table.named(a._content.rowname)
             for name in a._content.columns:
@@ -1034,8 +1070,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def _argminmax(self, ismin, with_values=False):
         """jagged.py:1581-1601 -> jg_segargminmax_dense (one pass: arg-reduce, look-back scan, dense result)."""
         a, off, n, first, last = self._dense()
-        if isinstance(a._content, JaggedArray):
-            return self.copy(content=a._content._argminmax(ismin))
+        if isinstance(a._content, JaggedArray):      # jagged.py:1569-1570
+            return self._make(a._rebased_offsets(), a._dense_content()._argminmax(ismin), last - first)
         if not isinstance(a._content, DeviceArray):
             raise ValueError("cannot compute arg{0} because content is not one-dimensional".format("min" if ismin else "max"))
         col = a._content
@@ -1063,8 +1099,17 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         """jagged.py:1403-1429: dense layout -> a view of content (zero bytes moved)."""
         if not isinstance(axis, (numbers.Integral, numpy.integer)) or axis < 0:
             raise TypeError("axis must be a non-negative integer (can't count from the end)")
+        if axis == 1:
+            # jagged.py:1410-1416: merge the two innermost levels
+            if not isinstance(self._content, JaggedArray):
+                raise ValueError("cannot flatten an array containing scalar values")
+            a, roff, inner, n_inner = self._nested_parts()
+            inner = inner.compact()
+            counts = self._make(roff, inner.counts, n_inner).sum()
+            newoffsets, total, _ = self._scan_counts(counts)
+            return self._make(newoffsets, inner.flatten(), total)
         if axis != 0:
-            raise NotImplementedError("flatten(axis>0) needs jagged-of-jagged content, outside the GPU hot path")
+            raise NotImplementedError("flatten(axis>1) is outside the GPU hot path")
         if len(self) == 0:
             return self._map_content(lambda c: c[0:0])
         a, off, n, first, last = self._dense()
@@ -1142,25 +1187,39 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         table = Table.named("tuple", left, right)
         return self._make(poff, table, total)
 
+    def _nest(self, flat_result, kind, other=None):
+        """nested=True (jagged.py:1255,1275,1285,1298,1335,1356): regroup the per-event combinations by their
+        first element -- outer counts = the event's item count, inner counts from localindex / the other counts."""
+        a = self.compact()
+        if kind == _lib.COMB_CROSS:
+            outer = a.counts
+            inner = a.tojagged(other.counts)._content                  # every item meets all of other's items
+        elif kind == _lib.COMB_PAIRS:
+            outer = a.counts
+            inner = (a.tojagged(a.counts) - a.localindex)._content      # item i pairs with items i .. n-1
+        else:                                                           # distincts: item i pairs with i+1 .. n-1
+            outer = numpy.maximum(a.counts - 1, 0)
+            inner = (a.tojagged(a.counts) - a.localindex - 1)[:, :-1].flatten()
+        inner_offsets, inner_total, _ = self._scan_counts(inner)
+        outer_offsets, outer_total, _ = self._scan_counts(outer)
+        inner_array = self._make(inner_offsets, flat_result._content, inner_total)
+        return self._make(outer_offsets, inner_array, outer_total)
+
     def argpairs(self, nested=False):
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_indices(_lib.COMB_PAIRS, 2)
+        out = self._comb_indices(_lib.COMB_PAIRS, 2)
+        return self._nest(out, _lib.COMB_PAIRS) if nested else out
 
     def pairs(self, nested=False):
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_values(_lib.COMB_PAIRS)
+        out = self._comb_values(_lib.COMB_PAIRS)
+        return self._nest(out, _lib.COMB_PAIRS) if nested else out
 
     def argdistincts(self, nested=False):
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_indices(_lib.COMB_DISTINCTS, 2)
+        out = self._comb_indices(_lib.COMB_DISTINCTS, 2)
+        return self._nest(out, _lib.COMB_DISTINCTS) if nested else out
 
     def distincts(self, nested=False):
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_values(_lib.COMB_DISTINCTS)
+        out = self._comb_values(_lib.COMB_DISTINCTS)
+        return self._nest(out, _lib.COMB_DISTINCTS) if nested else out
 
     def argchoose(self, n):
         """jagged.py:1223-1230: k-combinations in colexicographic order."""
@@ -1190,16 +1249,16 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def argcross(self, other, nested=False):
         self._valid()
         self._check_cross(other)
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_indices(_lib.COMB_CROSS, 2, other=other)
+        out = self._comb_indices(_lib.COMB_CROSS, 2, other=other)
+        return self._nest(out, _lib.COMB_CROSS, other=other) if nested else out
 
     def cross(self, other, nested=False):
         self._valid()
         self._check_cross(other)
-        if nested:
-            raise NotImplementedError("nested=True combinatorics are outside the round-1 GPU hot path (SURVEY.md section 8f-2)")
-        return self._comb_values(_lib.COMB_CROSS, other=other)
+        if isinstance(self._content, JaggedArray) or isinstance(other._content, JaggedArray):
+            raise NotImplementedError("chained nested cross is outside the GPU hot path (SURVEY.md section 8f-2)")
+        out = self._comb_values(_lib.COMB_CROSS, other=other)
+        return self._nest(out, _lib.COMB_CROSS, other=other) if nested else out
 
     # ------------------------------------------------------------------------------------------------------
     # outside the hot path: fail loudly (north_star: no CPU fallback)

@@ -194,6 +194,50 @@ def test_intra_event_slices_and_moments(ak):     # test_jagged.py:66-97 (a[2:, 1
     assert ak.JaggedArray.fromcounts([2, 1], np.array([3, 0, 5])).count().tolist() == [2, 1]
 
 
+def test_nested_combinatorics(ak):         # test_jagged.py:340-382
+    J = ak.JaggedArray
+    a = J.fromiter([[1.1, 2.2, 3.3], [], [4.4, 5.5]])
+    b = J.fromiter([[100, 200], [300], [400]])
+    assert a.cross(b, nested=True).tolist() == [[[(1.1, 100), (1.1, 200)], [(2.2, 100), (2.2, 200)], [(3.3, 100), (3.3, 200)]], [], [[(4.4, 400)], [(5.5, 400)]]]
+    assert a.argcross(b, nested=True).tolist() == [[[(0, 0), (0, 1)], [(1, 0), (1, 1)], [(2, 0), (2, 1)]], [], [[(0, 0)], [(1, 0)]]]
+    assert a.pairs(nested=True).tolist() == [[[(1.1, 1.1), (1.1, 2.2), (1.1, 3.3)], [(2.2, 2.2), (2.2, 3.3)], [(3.3, 3.3)]], [], [[(4.4, 4.4), (4.4, 5.5)], [(5.5, 5.5)]]]
+    assert a.argpairs(nested=True).tolist() == [[[(0, 0), (0, 1), (0, 2)], [(1, 1), (1, 2)], [(2, 2)]], [], [[(0, 0), (0, 1)], [(1, 1)]]]
+    assert a.distincts(nested=True).tolist() == [[[(1.1, 2.2), (1.1, 3.3)], [(2.2, 3.3)]], [], [[(4.4, 5.5)]]]
+    assert a.argdistincts(nested=True).tolist() == [[[(0, 1), (0, 2)], [(1, 2)]], [], [[(0, 1)]]]
+
+
+def test_physics_idiom(ak):                # tests/test_physics.py:18-88 with delta_r written out in ufuncs
+    J = ak.JaggedArray
+
+    def particles(pt, eta, phi):
+        return J.zip(pt=J.fromiter(pt), eta=J.fromiter(eta), phi=J.fromiter(phi))
+
+    def delta_r(one, two):
+        dphi = (one.phi - two.phi + np.pi) % (2 * np.pi) - np.pi
+        return np.sqrt((one.eta - two.eta) ** 2 + dphi ** 2)
+
+    jets = particles([[10.0, 20.0, 30.0], [], [40.0, 50.0]], [[-3.0, -2.0, 2.0], [], [-1.0, 1.0]], [[-1.5, 0.0, 1.5], [], [0.78, -0.78]])
+    electrons = particles([[20.2, 50.5], [50.5], [50.5]], [[-2.2, 0.0], [0.0], [1.1]], [[0.1, 0.78], [0.78], [-0.77]])
+    combinations = jets.cross(electrons, nested=True)
+    clean = ~(delta_r(combinations.i0, combinations.i1) < 0.5).any()
+    assert clean.tolist() == [[True, False, True], [], [True, False]]
+    assert jets[clean].pt.tolist() == [[10.0, 30.0], [], [40.0]]
+
+    gen = particles([[10.0, 20.0, 30.0], [], [40.0, 50.0]], [[-3.0, -2.0, 2.0], [], [-1.0, 1.0]], [[-1.5, 0.0, 1.5], [], [0.78, -0.78]])
+    reco = particles([[20.2, 10.1, 30.3, 50.5], [50.5], [50.5]], [[-2.2, -3.3, 2.2, 0.0], [0.0], [1.1]], [[0.1, -1.4, 1.4, 0.78], [0.78], [-0.77]])
+    pairing = gen.cross(reco, nested=True)
+    metric = delta_r(pairing.i0, pairing.i1)
+    index_of_minimized = metric.argmin()
+    assert index_of_minimized.tolist() == [[[1], [0], [2]], [], [[0], [0]]]
+    passes_cut = metric[index_of_minimized] < 0.5
+    assert passes_cut.tolist() == [[[True], [True], [True]], [], [[False], [True]]]
+    best = pairing[index_of_minimized][passes_cut]
+    genrecos = best.flatten(axis=1)
+    assert genrecos.counts.tolist() == [3, 0, 1] and gen.counts.tolist() == [3, 0, 2]
+    assert genrecos.i0.pt.tolist() == [[10.0, 20.0, 30.0], [], [50.0]]
+    assert genrecos.i1.pt.tolist() == [[10.1, 20.2, 30.3], [], [50.5]]
+
+
 def test_issues(ak):                       # tests/test_issues.py:16-30
     a = ak.JaggedArray.fromoffsets([2, 4, 4, 7], np.arange(10, dtype=np.float64))
     assert a[a > 3].tolist() == [[], [], [4.0, 5.0, 6.0]]
