@@ -176,3 +176,45 @@ def test_properties_at_full_size(ak):
     ap = sub.argpairs()
     assert int(ap.offsets[-1]) == int(((sub.counts * (sub.counts + 1)) // 2).sum()) <= pairs_total
     assert bool((ap.i0.content <= ap.i1.content).all()) and int(ap.i0.content.min()) == 0
+
+
+@pytest.mark.parametrize("shift", [1, 2, 3, 5])
+def test_unaligned_views(ak, shift):
+    """Device buffers that start at odd element offsets (views): exercises the unaligned head/tail of the TMA
+    staging, the scalar fall-backs of the vector kernels and unaligned scan inputs/outputs."""
+    rng = np.random.default_rng(100 + shift)
+    n = 20011
+    counts = rng.poisson(5.0, n).astype(np.int64)
+    m = int(counts.sum())
+    for dtype in (np.float32, np.float64, np.int32):
+        vals = (rng.exponential(25.0, m) if np.dtype(dtype).kind == "f" else rng.integers(-99, 99, m)).astype(dtype)
+        big_content = ak.asdevice(np.concatenate([np.zeros(shift, dtype=dtype), vals, np.zeros(7, dtype=dtype)]))
+        big_counts = ak.asdevice(np.concatenate([np.zeros(shift, dtype=np.int64), counts]))
+        content = big_content[shift:shift + m]
+        cview = big_counts[shift:]
+        off = O.counts2offsets(counts)
+        a = ak.JaggedArray.fromcounts(cview, content)
+        assert same(a.offsets.get(), off)
+        with np.errstate(all="ignore"):
+            assert same(a.max().get(), O.reduce(off, vals, "max"))
+            want = O.reduce(off, vals, "sum")
+            got = a.sum().get()
+            assert same(got, want) if want.dtype.kind != "f" else np.allclose(got, want, rtol=1e-5)
+            roff, ridx = O.argminmax(off, vals, False)
+            r = a.argmax()
+            assert same(r.offsets.get(), roff) and same(r.content.get(), ridx)
+        thr = 20 if np.dtype(dtype).kind == "f" else 0
+        moff, mask = O.ufunc_broadcast(np.greater, off, vals, thr)
+        big_mask = ak.asdevice(np.concatenate([np.ones(shift, dtype=bool), mask]))
+        mj = ak.JaggedArray.fromoffsets(a.offsets, big_mask[shift:])
+        soff, sel = O.mask_select(off, vals, moff, mask)
+        gs = a[mj]
+        assert same(gs.offsets.get(), soff) and same(gs.content.get(), sel)
+        assert same((a > thr).content.get(), mask)
+        # an offsets view that is 8- but not 16-byte aligned
+        big_off = ak.asdevice(np.concatenate([np.zeros(1, dtype=np.int64), off]))
+        b = ak.JaggedArray.fromoffsets(big_off[1:], content)
+        assert same(b.counts.get(), counts) and same(b.parents.get(), O.offsets2parents(off))
+        with np.errstate(all="ignore"):
+            assert same(b.min().get(), O.reduce(off, vals, "min"))
+        assert same(b.argpairs().i1.content.get(), O.argpairs(off)[2])
