@@ -495,12 +495,12 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=125_000_000)
     ap.add_argument("--comb-events", type=int, default=50_000_000)
-    ap.add_argument("--cpu-events", type=int, default=4_000_000)
+    ap.add_argument("--cpu-events", type=int, default=16_000_000)
     ap.add_argument("--ref-events-per-core", type=int, default=1_000_000)
     ap.add_argument("--kernel-reps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
