@@ -1,14 +1,18 @@
-// jg_scan.cuh -- single-pass decoupled-lookback exclusive scan (int64 result) over a generated sequence.
+// jg_scan.cuh -- single-pass decoupled-lookback exclusive scans (int64 result).
 //
 // Replaces numpy.cumsum at jagged.py:46 (counts2offsets) and every later use of it (new offsets after a mask
-// :577, pair/cross counts :1075,:1095,:1164,:1311, argmax counts).  The input is a functor so the per-event
-// count can be computed on the fly (n(n+1)/2 from offsets, flags from best[] >= 0, ...) without a temporary.
+// :577, pair/cross counts :1075,:1095,:1164,:1311, argmax counts).
 //
-// Layout: CTA = 256 threads = 8 warps; a tile is 4096 items; warp w owns 512 consecutive items as 8 rows of
-// 64; lane l of row r holds items (2l, 2l+1) of that row, so loads and stores are fully coalesced 128-bit
-// accesses (LDG.128 / STG.128 for int64) with no shared-memory transpose.  The in-warp scan is done with
-// shuffles on 32-bit partials when every item of the tile is < 2^19 (the common case: counts), else 64-bit.
-// Tiles take their index from an atomic ticket so that a tile only ever waits on tiles that already started.
+// Two kernels share the look-back protocol of jg_common.cuh (one 64-bit descriptor per tile: 2-bit state +
+// 62-bit value, so flag and value travel in one atomic store):
+//   * scan_tma_kernel<T, XF, ITEMS>   -- the production path.  The tile is PARKED IN SHARED MEMORY by one TMA bulk
+//     copy and only 128 threads with ~35 registers watch over it, so 9 CTAs are resident per SM: on B200 every
+//     tile of a look-back scan waits ~6 us for the slowest of its predecessors (profiles/r1_lookback_study.md)
+//     and only parked bytes -- not registers -- can cover that wait.  XF turns the staged data into items:
+//     the items themselves (counts) or combinatorial counts formed from staged offsets (pairs / cross / choose).
+//   * scan_lookback_kernel<In>        -- functor input held in registers (validity flags, tiny tile-total scans);
+//     tiles take their index from an atomic ticket.
+// Both use 32-bit in-warp shuffle scans when every item of the tile is < 2^19 (the common case), else 64-bit.
 //
 // Algorithmic traffic: itemsize*n read + 8*(n+1) written (16n bytes for int64 counts).
 #pragma once
@@ -227,7 +231,7 @@ struct XfComb {
     }
 };
 
-template <typename T, typename S, class XF, int ITEMS>     // S = in-tile accumulator (int32 fast path / int64)
+template <typename T, typename S, class XF, int ITEMS, bool FULL>     // S = in-tile accumulator (int32 / int64); FULL: no bounds tests
 __device__ __forceinline__ void scan_tma_rows(const XF &xf, const T *sa, const T *sb, int valid, int wbase, int lane,
                                               int64_t run, int64_t *__restrict__ out, int64_t i0, int64_t n,
                                               bool out_aligned) {
@@ -236,8 +240,8 @@ __device__ __forceinline__ void scan_tma_rows(const XF &xf, const T *sa, const T
 #pragma unroll 4
     for (int r = 0; r < ROWS; ++r) {
         const int p = wbase + r * 64 + lane * 2;
-        const S x = p < valid ? static_cast<S>(xf.item(sa, sb, p)) : S(0);
-        const S y = p + 1 < valid ? static_cast<S>(xf.item(sa, sb, p + 1)) : S(0);
+        const S x = (FULL || p < valid) ? static_cast<S>(xf.item(sa, sb, p)) : S(0);
+        const S y = (FULL || p + 1 < valid) ? static_cast<S>(xf.item(sa, sb, p + 1)) : S(0);
         const S s2 = x + y;
         S incl = s2;
 #pragma unroll
@@ -247,7 +251,7 @@ __device__ __forceinline__ void scan_tma_rows(const XF &xf, const T *sa, const T
         }
         const int64_t e0 = run + static_cast<int64_t>(carry + incl - s2);
         const int64_t i = i0 + p;
-        if (i + 1 < n) {
+        if (FULL || i + 1 < n) {
             if (out_aligned) __stcs(reinterpret_cast<longlong2 *>(out + i), make_longlong2(e0, e0 + static_cast<int64_t>(x)));
             else {
                 out[i] = e0;
@@ -296,11 +300,12 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     const int wbase = warp * (ITEMS * kWarp);
     int64_t sum = 0;
     bool neg = false, big = false;
-#pragma unroll 4
+    const bool full = valid == TILE;
+#pragma unroll
     for (int r = 0; r < ITEMS / 2; ++r) {
         const int p = wbase + r * 64 + lane * 2;
-        const int64_t x = p < valid ? xf.item(sa, sb, p) : 0;
-        const int64_t y = p + 1 < valid ? xf.item(sa, sb, p + 1) : 0;
+        const int64_t x = (full || p < valid) ? xf.item(sa, sb, p) : 0;
+        const int64_t y = (full || p + 1 < valid) ? xf.item(sa, sb, p + 1) : 0;
         neg |= (x < 0) | (y < 0);
         big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
         sum += x + y;
@@ -325,8 +330,13 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     }
     __syncthreads();
     const int64_t run = s_base + s_warp[warp];
-    if (wide) scan_tma_rows<T, int64_t, XF, ITEMS>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
-    else scan_tma_rows<T, int32_t, XF, ITEMS>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+    if (valid == TILE) {
+        if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        else scan_tma_rows<T, int32_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+    } else {
+        if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        else scan_tma_rows<T, int32_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+    }
 }
 
 template <typename T, class XF, int ITEMS>
