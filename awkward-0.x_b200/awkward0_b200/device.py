@@ -64,15 +64,28 @@ class _Runtime(object):
         self._ws = {}
         self._scal = {}
 
-    @staticmethod
-    def device():
-        if not torch.cuda.is_available():
+    _has_cuda = None
+    _devices = {}
+
+    @classmethod
+    def device(cls):
+        if cls._has_cuda is None:
+            cls._has_cuda = bool(torch.cuda.is_available())     # checked once: it walks the environment
+        if not cls._has_cuda:
             raise RuntimeError("no CUDA device visible: awkward0_b200 runs on B200 only and has no CPU fallback")
-        return torch.device("cuda", torch.cuda.current_device())
+        idx = torch.cuda.current_device()
+        dev = cls._devices.get(idx)
+        if dev is None:
+            dev = cls._devices[idx] = torch.device("cuda", idx)
+        return dev
 
     @staticmethod
     def stream():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        """The current CUDA stream of the current device as a cudaStream_t (raw handle, no Stream object)."""
+        try:
+            return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+        except AttributeError:          # pragma: no cover  (older torch)
+            return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def workspace(self, n):
         """(pointer, bytes) of a scratch buffer large enough for any call on n events."""
