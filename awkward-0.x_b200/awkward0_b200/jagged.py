@@ -1067,8 +1067,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def argmax(self):
         return self._argminmax(False)
 
-    def _argminmax(self, ismin, with_values=False):
-        """jagged.py:1581-1601 -> jg_segargminmax_dense (one pass: arg-reduce, look-back scan, dense result)."""
+    def _argminmax(self, ismin):
+        """jagged.py:1581-1601 -> jg_segargminmax_dense (optimistic one pass; exact two-step path if an event is all-NaN)."""
         a, off, n, first, last = self._dense()
         if isinstance(a._content, JaggedArray):      # jagged.py:1569-1570
             return self._make(a._rebased_offsets(), a._dense_content()._argminmax(ismin), last - first)

@@ -594,7 +594,8 @@ static int dispatch_reduce(int op, const void *content, const int64_t *offsets, 
 
 template <typename T>
 static int dispatch_arg(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *best,
-                        void *best_value, cudaStream_t s, int64_t *tile_totals = nullptr) {
+                        void *best_value, cudaStream_t s) {
+    int64_t *tile_totals = nullptr;   // (per-tile counts of events with a result: kept for a future exact dense path)
     if (is_min)
         segarg_kernel<true, T, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
             static_cast<const T *>(content), offsets, n, best, static_cast<T *>(best_value), tile_totals);
