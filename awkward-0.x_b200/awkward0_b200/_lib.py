@@ -72,6 +72,8 @@ PROTOTYPES = {
     "jg_flat_reduce": (_i, [_vp, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "jg_comb_offsets": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "jg_comb_fill": (_i, [_i, _i, _vp, _vp, _i64, _vp, ctypes.POINTER(_vp), _i, _vp]),
+    "jg_comb_gather_multi": (_i, [_i, _vp, _vp, _i64, _vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i,
+                                  ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
     "jg_comb_gather2": (_i, [_i, _vp, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
 }
 

@@ -1158,6 +1158,43 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                      _vp(out_l), _vp(out_r), runtime.stream())
             return DeviceArray(out_l, col_a.dtype), DeviceArray(out_r, col_b.dtype)
 
+        def multi(leaves_l, leaves_r):
+            """Gather lists of same-itemsize leaf columns for the left / right side in one kernel (<= 4 per side)."""
+            outs_l = [empty(total, c.dtype) for c in leaves_l]
+            outs_r = [empty(total, c.dtype) for c in leaves_r]
+            if total > 0:
+                def parr(ts):
+                    return (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])
+                call("jg_comb_gather_multi", kind, off.data_ptr(),
+                     off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0), n, poff.data_ptr(),
+                     (leaves_l or leaves_r)[0].itemsize, len(leaves_l), parr([c.tensor for c in leaves_l]), parr(outs_l),
+                     len(leaves_r), parr([c.tensor for c in leaves_r]), parr(outs_r), runtime.stream())
+            return ([DeviceArray(o, c.dtype) for o, c in zip(outs_l, leaves_l)],
+                    [DeviceArray(o, c.dtype) for o, c in zip(outs_r, leaves_r)])
+
+        def records(col_a, col_b):
+            """Table content: all leaf columns of one itemsize share a sweep; returns (left tree, right tree)."""
+            la, lb = list(_leaves(col_a)), list(_leaves(col_b))
+            if any(isinstance(x, JaggedArray) for x in la + lb):
+                raise NotImplementedError("combinatorics over nested content are outside the GPU hot path")
+            res_l, res_r = [None] * len(la), [None] * len(lb)
+            for size in sorted(set(c.itemsize for c in la + lb)):
+                il = [i for i, c in enumerate(la) if c.itemsize == size]
+                ir = [i for i, c in enumerate(lb) if c.itemsize == size]
+                while il or ir:
+                    cl, cr = il[:4], ir[:4]
+                    il, ir = il[4:], ir[4:]
+                    ol, orr = multi([la[i] for i in cl], [lb[i] for i in cr])
+                    for i, o in zip(cl, ol):
+                        res_l[i] = o
+                    for i, o in zip(cr, orr):
+                        res_r[i] = o
+            return _rebuild(col_a, iter(res_l)), _rebuild(col_b, iter(res_r))
+
+        if isinstance(a._content, Table) or isinstance(b._content, Table):
+            left, right = records(a._content, b._content)
+            return self._make(poff, Table.named("tuple", left, right), total)
+
         def both(col_a, col_b):
             """(left tree, right tree) for one column (or Table of columns) of each side."""
             if isinstance(col_a, JaggedArray) or isinstance(col_b, JaggedArray):

@@ -225,6 +225,68 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     }
 }
 
+// Record form (Table content, jagged.py:1294 / 1350 with table.py:619-629 row views): every leaf column of the
+// left and of the right collection is gathered in ONE sweep, so the owner lookup and the un-ranking are paid once
+// per output pair instead of once per column.
+struct MultiCols {
+    const void *in_l[4];
+    void *out_l[4];
+    const void *in_r[4];
+    void *out_r[4];
+    int nl, nr;
+};
+
+template <int KIND, typename V>
+__global__ void __launch_bounds__(kTileThreads)
+comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                         const int64_t *__restrict__ out_offsets, MultiCols cols) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[kTileEvents + 1];
+    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    EventTile pt, ta, tb;
+    pt.load(s_po, out_offsets, n, blockIdx.x);
+    ta.load(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    const bool table = (p1 - p0) <= kCombPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
+        const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
+        const int64_t ia = s_oa[ev] + r.v[0];
+        const int64_t ib = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
+        V vl[4], vr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < cols.nl) vl[c] = __ldg(static_cast<const V *>(cols.in_l[c]) + ia);
+            if (c < cols.nr) vr[c] = __ldg(static_cast<const V *>(cols.in_r[c]) + ib);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < cols.nl) __stcs(static_cast<V *>(cols.out_l[c]) + p, vl[c]);
+            if (c < cols.nr) __stcs(static_cast<V *>(cols.out_r[c]) + p, vr[c]);
+        }
+    }
+}
+
+template <int KIND>
+static int launch_gather_multi(int itemsize, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                               const MultiCols &mc, cudaStream_t s) {
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1: comb_gather_multi_kernel<KIND, uint8_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
+        case 2: comb_gather_multi_kernel<KIND, uint16_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
+        case 4: comb_gather_multi_kernel<KIND, uint32_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
+        case 8: comb_gather_multi_kernel<KIND, uint64_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
+        default: set_error("jg_comb_gather_multi: unsupported itemsize %d", itemsize); return -2;
+    }
+    return check_launch("comb_gather_multi_kernel");
+}
+
 template <int KIND, typename VA>
 static int gather2_b(int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const void *ca,
                      const void *cb, void *l, void *r, cudaStream_t s) {
@@ -321,6 +383,34 @@ int jg_comb_gather2(int kind, const int64_t *offsets_a, const int64_t *offsets_b
             return gather2_a<JG_COMB_CROSS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
     }
     set_error("jg_comb_gather2: bad kind %d", kind);
+    return -2;
+}
+
+int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                         const int64_t *out_offsets, int itemsize, int n_left, const void *const *in_left,
+                         void *const *out_left, int n_right, const void *const *in_right, void *const *out_right,
+                         void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(n_left >= 0 && n_left <= 4 && n_right >= 0 && n_right <= 4 && n_left + n_right > 0,
+               "jg_comb_gather_multi: 0..4 columns per side");
+    MultiCols mc{};
+    mc.nl = n_left;
+    mc.nr = n_right;
+    for (int c = 0; c < n_left; ++c) {
+        mc.in_l[c] = in_left[c];
+        mc.out_l[c] = out_left[c];
+    }
+    for (int c = 0; c < n_right; ++c) {
+        mc.in_r[c] = in_right[c];
+        mc.out_r[c] = out_right[c];
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (kind) {
+        case JG_COMB_PAIRS: return launch_gather_multi<JG_COMB_PAIRS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+        case JG_COMB_DISTINCTS: return launch_gather_multi<JG_COMB_DISTINCTS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+        case JG_COMB_CROSS: return launch_gather_multi<JG_COMB_CROSS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+    }
+    set_error("jg_comb_gather_multi: bad kind %d", kind);
     return -2;
 }
 

@@ -283,6 +283,10 @@ def run_gpu(args):
                 "algorithmic_bytes": ops[dom]["bytes"], "ms": ops[dom]["ms"],
                 "step_share": ops[dom]["ms"] / sum(ops[k]["ms"] for k in step_ops)}
 
+    workflows = {}
+    if rank == 0:
+        workflows = workflow_table(ak, counts_dev, pt_dev, nev, M, args)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args)
@@ -302,7 +306,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "totals": {"sum": totals[0], "selected": totals[1], "leading": totals[2]},
-            "roofline": roof, "cpu_baseline": cpu, "ops": ops,
+            "roofline": roof, "cpu_baseline": cpu, "ops": ops, "workflows": workflows,
         }
         emit(line)
     if world > 1:
@@ -455,6 +459,70 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         del l, r
         table["arg" + name + "_fill"]["pairs"] = P
     return table
+
+
+def workflow_table(ak, counts_dev, pt_dev, N, M, args):
+    """BASELINE.json configs[1..3] through the PUBLIC API on resident data (CUDA events around the whole call
+    chain, host synchronisations for the data-dependent sizes included)."""
+    import torch
+    out = {}
+
+    def timed(name, fn, units, unit_name, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+            del r
+        ms = float(np.mean(ts))
+        out[name] = {"ms": ms, unit_name + "_per_s": units / (ms * 1e-3)}
+
+    a = ak.JaggedArray.fromcounts(counts_dev, pt_dev)
+
+    def c2(arr):
+        sel = arr[arr > THRESHOLD]
+        return sel.flatten(), sel.counts
+
+    timed("C2_mask_flatten_counts_f32", lambda: c2(a), M, "elements")
+    a64 = ak.JaggedArray.fromoffsets(a.offsets, ak.DeviceArray(pt_dev.tensor.double()))
+    timed("C2_mask_flatten_counts_f64", lambda: c2(a64), M, "elements")
+    del a64
+    timed("C3_leading_object_argmax_getitem_f32", lambda: a[a.argmax()], M, "elements")
+
+    # C4: dimuon combinatorics with the per-pair invariant mass written in ufuncs (records: pt, eta, phi)
+    Nc = args.comb_events
+    rng = np.random.default_rng(777)
+    mc = rng.poisson(2.0, Nc).astype(np.int64)
+    ec = rng.poisson(2.0, Nc).astype(np.int64)
+    Mm, Me = int(mc.sum()), int(ec.sum())
+
+    def collection(counts, m):
+        cd = ak.asdevice(counts)
+        first = ak.JaggedArray.fromcounts(cd, rng.exponential(20.0, m).astype(np.float32))
+        mk = lambda x: ak.JaggedArray.fromoffsets(first.offsets, x)
+        return ak.JaggedArray.zip(pt=first, eta=mk(rng.uniform(-2.4, 2.4, m).astype(np.float32)),
+                                  phi=mk(rng.uniform(-np.pi, np.pi, m).astype(np.float32)))
+
+    mu, el = collection(mc, Mm), collection(ec, Me)
+
+    def mass(p):
+        one, two = p.i0, p.i1
+        return np.sqrt(2 * one.pt * two.pt * (np.cosh(one.eta - two.eta) - np.cos(one.phi - two.phi)))
+
+    P = int(((mc * (mc + 1)) // 2).sum())
+    timed("C4_pairs_records", lambda: mu.pairs(), P, "pairs")
+    timed("C4_pairs_plus_invariant_mass", lambda: mass(mu.pairs()), P, "pairs")
+    timed("C4_argpairs", lambda: mu.argpairs(), P, "pairs")
+    X = int((mc * ec).sum())
+    timed("C4_cross_records", lambda: mu.cross(el), X, "pairs")
+    timed("C4_cross_plus_invariant_mass", lambda: mass(mu.cross(el)), X, "pairs")
+    out["C4_sizes"] = {"events": Nc, "muons": Mm, "electrons": Me, "pairs": P, "cross_pairs": X}
+    return out
 
 
 def cpu_baseline(args):

@@ -198,6 +198,14 @@ int jg_comb_gather2(int kind, const int64_t *offsets_a, const int64_t *offsets_b
                     const int64_t *out_offsets, const void *content_a, int itemsize_a, const void *content_b,
                     int itemsize_b, void *out_l, void *out_r, void *stream);
 
+/* record form of the above (Table content: jagged.py:1294/1350 with the row views of table.py:619-629): up to 4
+ * leaf columns per side, all of one itemsize, gathered in one sweep (host arrays of device pointers).
+ * For PAIRS / DISTINCTS pass the same input columns on both sides.                                                  */
+int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n,
+                         const int64_t *out_offsets, int itemsize, int n_left, const void *const *in_left,
+                         void *const *out_left, int n_right, const void *const *in_right, void *const *out_right,
+                         void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -296,6 +296,24 @@ def test_records_zip_pairs(ak):            # BASELINE configs[3]: dimuon records
     assert mu.sum()["pt"].tolist() == [30.0, 0.0, 120.0]
 
 
+def test_records_mixed_dtypes(ak):          # record gather groups leaf columns by itemsize (4 / 8 / 1 byte here)
+    J = ak.JaggedArray
+    counts = [2, 0, 3, 1]
+    pt = J.fromcounts(counts, np.arange(6, dtype=np.float32))
+    q = J.fromcounts(counts, np.array([1, -1, 1, 1, -1, -1], dtype=np.int64))
+    ok = J.fromcounts(counts, np.array([True, False, True, True, False, True]))
+    e = J.fromcounts(counts, np.arange(6, dtype=np.float64) * 10)
+    mu = J.zip(pt=pt, q=q, ok=ok, e=e)
+    p = mu.distincts()
+    assert p.i0.pt.tolist() == [[0.0], [], [2.0, 2.0, 3.0], []] and p.i1.pt.tolist() == [[1.0], [], [3.0, 4.0, 4.0], []]
+    assert p.i0.q.tolist() == [[1], [], [1, 1, 1], []] and p.i1.q.tolist() == [[-1], [], [1, -1, -1], []]
+    assert p.i0.ok.tolist() == [[True], [], [True, True, True], []] and p.i1.e.tolist() == [[10.0], [], [30.0, 40.0, 40.0], []]
+    x = mu.cross(J.fromcounts([1, 1, 0, 2], np.array([7, 8, 9, 10], dtype=np.int32)))
+    assert x.counts.tolist() == [2, 0, 0, 2]
+    assert x.i0.e.tolist() == [[0.0, 10.0], [], [], [50.0, 50.0]] and x.i1.tolist() == [[7, 7], [], [], [9, 10]]
+    assert (p.i0.q * p.i1.q).tolist() == [[-1], [], [1, -1, -1], []]
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
