@@ -59,7 +59,7 @@ PROTOTYPES = {
     "jg_compact_gather": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "jg_segreduce": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "jg_segargminmax": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
-    "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_check_same_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -11,7 +11,7 @@ import numpy
 
 from . import _lib
 from ._lib import OP, call
-from .device import DeviceArray, asdevice, empty, jg_code, runtime
+from .device import DeviceArray, asdevice, empty, jg_code, runtime, torch_dtype
 
 _BINARY = {
     numpy.add: "ADD", numpy.subtract: "SUB", numpy.multiply: "MUL", numpy.true_divide: "DIV",
@@ -37,6 +37,32 @@ _UNARY = {
 }
 
 _COMPUTE_OK = (_lib.JG_F32, _lib.JG_F64, _lib.JG_I32, _lib.JG_I64, _lib.JG_U8, _lib.JG_B8)
+# Narrow integer arithmetic runs in the next kernel-native wider type and is truncated back by a cast pass:
+# + - * & | ^ ~ and powers are ring homomorphisms Z/2^32 -> Z/2^16 ..., and // % comparisons of values that are
+# exactly representable give the same answers.  uint64 shares bits with int64 for the wrap-around subset.
+_WIDEN = {
+    numpy.dtype(numpy.int8): numpy.dtype(numpy.int32), numpy.dtype(numpy.int16): numpy.dtype(numpy.int32),
+    numpy.dtype(numpy.uint16): numpy.dtype(numpy.int32), numpy.dtype(numpy.uint32): numpy.dtype(numpy.int64),
+}
+_U64_BITWISE_SAFE = ("ADD", "SUB", "MUL", "AND", "OR", "XOR", "NEG", "NOT", "SQUARE", "CAST")
+
+
+def _native_compute(name, rdt, cdt):
+    """(compute dtype the kernel runs in, dtype it stores, fix-up) for numpy's (rdt, cdt)."""
+    if cdt in _WIDEN:
+        wide = _WIDEN[cdt]
+        return wide, (wide if rdt == cdt else rdt), ("cast" if rdt == cdt else None)
+    if cdt == numpy.dtype(numpy.uint64) and rdt == cdt and name in _U64_BITWISE_SAFE:
+        return numpy.dtype(numpy.int64), numpy.dtype(numpy.int64), "view"
+    return cdt, rdt, None
+
+
+def _finish(out, kdt, rdt, fix):
+    if fix == "cast":
+        return cast(DeviceArray(out, kdt), rdt)
+    if fix == "view":
+        return DeviceArray(out.view(torch_dtype(rdt)), rdt)
+    return DeviceArray(out, rdt)
 
 
 def is_scalar(x):
@@ -122,13 +148,14 @@ def unary(ufunc, x):
         x = _as_bool(x)
     if name == "NOT" and x.dtype == numpy.bool_:
         cdt = numpy.dtype(numpy.bool_)
-    ccode = jg_code(cdt)
+    kcdt, kdt, fix = _native_compute(name, rdt, cdt)
+    ccode = jg_code(kcdt)
     if ccode not in _COMPUTE_OK:
         raise NotImplementedError("{0} on dtype {1} is not implemented on the device".format(ufunc.__name__, cdt))
-    out = empty(len(x), rdt)
-    call("jg_unary", OP[name], x.data_ptr(), jg_code(x.dtype), ccode, ctypes.c_void_p(out.data_ptr()), jg_code(rdt),
+    out = empty(len(x), kdt)
+    call("jg_unary", OP[name], x.data_ptr(), jg_code(x.dtype), ccode, ctypes.c_void_p(out.data_ptr()), jg_code(kdt),
          len(x), runtime.stream())
-    return DeviceArray(out, rdt)
+    return _finish(out, kdt, rdt, fix)
 
 
 def binary(ufunc, lhs, rhs, offsets=None, nevents=0, parent_side=None):
@@ -144,7 +171,8 @@ def binary(ufunc, lhs, rhs, offsets=None, nevents=0, parent_side=None):
     if ufunc in _LOGICAL:
         lhs, rhs = _as_bool(lhs), _as_bool(rhs)
     rdt, cdt = result_dtypes(ufunc, [lhs, rhs])
-    ccode = jg_code(cdt)
+    kcdt, kdt, fix = _native_compute(name, rdt, cdt)
+    ccode = jg_code(kcdt)
     if ccode not in _COMPUTE_OK and not (name in _COMPARE and ccode == _lib.JG_U64):
         raise NotImplementedError("{0} with compute dtype {1} is not implemented on the device".format(ufunc.__name__, cdt))
 
@@ -177,12 +205,12 @@ def binary(ufunc, lhs, rhs, offsets=None, nevents=0, parent_side=None):
         if cdt.kind == "u" and si < 0:
             raise OverflowError("Python integer {0} out of bounds for {1}".format(si, cdt))
 
-    out = empty(length, rdt)
+    out = empty(length, kdt)
     call("jg_binary", OP[name], lhs.data_ptr(), jg_code(lhs.dtype),
          rhs.data_ptr() if rhs is not None else ctypes.c_void_p(0), jg_code(rhs.dtype) if rhs is not None else 0,
-         kind, ctypes.c_double(sf), ctypes.c_int64(si), swap, ccode, ctypes.c_void_p(out.data_ptr()), jg_code(rdt),
+         kind, ctypes.c_double(sf), ctypes.c_int64(si), swap, ccode, ctypes.c_void_p(out.data_ptr()), jg_code(kdt),
          length, offsets.data_ptr() if offsets is not None else ctypes.c_void_p(0), int(nevents), runtime.stream())
-    return DeviceArray(out, rdt)
+    return _finish(out, kdt, rdt, fix)
 
 
 def flat_ufunc(ufunc, inputs):

@@ -44,6 +44,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     allow_iter = True
     check_prop_valid = True
     check_whole_valid = True
+    # argmin/argmax also keep the extreme values (same pass, +v bytes per event) so that a[a.argmax()] is free
+    cache_arg_values = True
 
     DEFAULTTYPE = numpy.dtype(numpy.float64)      # base.py:42-48
     INDEXTYPE = INDEXTYPE
@@ -180,6 +182,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         self._rebased = None
         self._general = None
         self._maxcount = None
+        self._arg_source = None          # set on argmin/argmax results: (offsets, content) they were computed from
+        self._arg_values = None
 
     @classmethod
     def _tocontent(cls, content):
@@ -319,6 +323,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def copy(self, starts=None, stops=None, content=None):
         out = self.__class__.__new__(self.__class__)
         out.__dict__.update(self.__dict__)
+        if content is not None or starts is not None or stops is not None:
+            out._arg_source = out._arg_values = None
         if content is not None:
             out._content = self._tocontent(content)
             out._isvalid = False
@@ -860,6 +866,10 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if len(head) != len(self):
             raise ValueError("jagged array used as index has a different shape {0} from the jagged array it is selecting from {1}".format(head.shape, self.shape))
         a, off, n, first, last = self._dense()
+        src = head._arg_source
+        if src is not None and src[0] is a._off64 and src[1] is a._content:
+            # `head` is argmin()/argmax() of this very array: the selected values were produced by that pass
+            return self._make(head._off64, head._arg_values, head._last)
         h, hoff, _, hfirst, hlast = head._dense()
         index = h._content
         if index.dtype not in (numpy.dtype(numpy.int64), numpy.dtype(numpy.int32)):
@@ -1079,10 +1089,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out_index = empty(n, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
+        values = empty(n, col.dtype) if self.cache_arg_values else None
         call("jg_segargminmax_dense", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
-             _vp(out_offsets), _vp(out_index), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
+             _vp(out_offsets), _vp(out_index), _vp(values), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
         total, status, _ = runtime.read(scal)
         if status & _lib.ST_ARG_ALLNAN:
+            values = None
             # a non-empty event holds only NaN: exact path (arg-reduce to best[], then scan + compaction)
             best = empty(n, INDEXTYPE)
             scal = runtime.scalars()
@@ -1090,7 +1102,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                  ctypes.c_void_p(0), runtime.stream())
             call("jg_compact_nonneg", _vp(best), n, _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
             total, _, _ = runtime.read(scal)
-        return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
+        out = self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
+        if values is not None:
+            # the extreme values came out of the same pass: a[a.argmax()] on THIS array needs no gather
+            out._arg_source = (a._off64, col)
+            out._arg_values = DeviceArray(values[:total], col.dtype)
+        return out
 
     # ------------------------------------------------------------------------------------------------------
     # flatten

@@ -36,12 +36,22 @@ template <> __device__ __forceinline__ double max_identity<double>() { return -C
 template <> __device__ __forceinline__ int32_t max_identity<int32_t>() { return INT32_MIN; }
 template <> __device__ __forceinline__ int64_t max_identity<int64_t>() { return INT64_MIN; }
 template <> __device__ __forceinline__ uint8_t max_identity<uint8_t>() { return 0; }
+template <> __device__ __forceinline__ int8_t max_identity<int8_t>() { return INT8_MIN; }
+template <> __device__ __forceinline__ int16_t max_identity<int16_t>() { return INT16_MIN; }
+template <> __device__ __forceinline__ uint16_t max_identity<uint16_t>() { return 0; }
+template <> __device__ __forceinline__ uint32_t max_identity<uint32_t>() { return 0; }
+template <> __device__ __forceinline__ uint64_t max_identity<uint64_t>() { return 0; }
 template <typename A> __device__ __forceinline__ A min_identity();
 template <> __device__ __forceinline__ float min_identity<float>() { return CUDART_INF_F; }
 template <> __device__ __forceinline__ double min_identity<double>() { return CUDART_INF; }
 template <> __device__ __forceinline__ int32_t min_identity<int32_t>() { return INT32_MAX; }
 template <> __device__ __forceinline__ int64_t min_identity<int64_t>() { return INT64_MAX; }
 template <> __device__ __forceinline__ uint8_t min_identity<uint8_t>() { return 255; }
+template <> __device__ __forceinline__ int8_t min_identity<int8_t>() { return INT8_MAX; }
+template <> __device__ __forceinline__ int16_t min_identity<int16_t>() { return INT16_MAX; }
+template <> __device__ __forceinline__ uint16_t min_identity<uint16_t>() { return UINT16_MAX; }
+template <> __device__ __forceinline__ uint32_t min_identity<uint32_t>() { return UINT32_MAX; }
+template <> __device__ __forceinline__ uint64_t min_identity<uint64_t>() { return UINT64_MAX; }
 
 // Reduction functor: A = accumulator/output type, T = content type.
 template <int OP, typename T, typename A>
@@ -432,7 +442,8 @@ template <bool ISMIN, typename T, int STAGE_BYTES>
 __global__ void __launch_bounds__(kTileThreads)
 segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                      const int64_t *__restrict__ tile_bases, int64_t *__restrict__ out_offsets,
-                     int64_t *__restrict__ out_index, int32_t *__restrict__ status, uint32_t ntiles) {
+                     int64_t *__restrict__ out_index, T *__restrict__ out_value, int32_t *__restrict__ status,
+                     uint32_t ntiles) {
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
@@ -482,6 +493,7 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
     }
 
     int64_t idx[2] = {-1, -1};
+    T val[2] = {T(0), T(0)};          // the extreme value itself: the "leading object" a[a.argmax()] for free
     if (nbytes <= STAGE_BYTES) {
         const T *sm = nullptr;
         if (nbytes > 0) {
@@ -529,13 +541,19 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
                 }
         idx[0] = iA;
         idx[1] = iB;
+        val[0] = (iA >= 0) ? pA[iA] : T(0);
+        val[1] = (iB >= 0) ? pB[iB] : T(0);
     } else {
         __shared__ int64_t s_idx64[kTileEvents];
+        T *s_val = reinterpret_cast<T *>(s_stage);      // the stage is unused on this path
         for (int ev = warp; ev < tile.nev; ev += NW) {
             const int64_t ea = s_off[ev], eb = s_off[ev + 1];
             if (eb - ea >= kBlockEventMin) continue;
             ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, ea, eb, lane, kWarp));
-            if (lane == 0) s_idx64[ev] = p.idx;
+            if (lane == 0) {
+                s_idx64[ev] = p.idx;
+                s_val[ev] = p.val;
+            }
         }
         for (int ev = 0; ev < tile.nev; ++ev) {
             const int64_t ea = s_off[ev], eb = s_off[ev + 1];
@@ -549,22 +567,30 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
                 if (lane < NW) q = s_part[lane];
                 else { q.idx = -1; q.val = T(0); }
                 q = arg_shuffle<ISMIN, T>(q);
-                if (lane == 0) s_idx64[ev] = q.idx;
+                if (lane == 0) {
+                    s_idx64[ev] = q.idx;
+                    s_val[ev] = q.val;
+                }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 2; ++q)
-            if (ev0 + q < tile.nev) idx[q] = s_idx64[ev0 + q];
+            if (ev0 + q < tile.nev) {
+                idx[q] = s_idx64[ev0 + q];
+                val[q] = s_val[ev0 + q];
+            }
     }
     bool mismatch = false;
     if (ne0) {
         mismatch |= idx[0] < 0;
         out_index[base] = idx[0];
+        if (out_value) out_value[base] = val[0];
     }
     if (ne1) {
         mismatch |= idx[1] < 0;
         out_index[base + ne0] = idx[1];
+        if (out_value) out_value[base + ne0] = val[1];
     }
     if (mismatch) atomicOr(status, JG_ST_ARG_ALLNAN);
 }
@@ -607,8 +633,8 @@ static int dispatch_arg(int is_min, const void *content, const int64_t *offsets,
 
 template <typename T>
 static int dispatch_arg_dense(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *out_offsets,
-                              int64_t *out_index, int64_t *total, int32_t *status, void *ws, size_t ws_bytes,
-                              cudaStream_t s) {
+                              int64_t *out_index, void *out_value, int64_t *total, int32_t *status, void *ws,
+                              size_t ws_bytes, cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
     // workspace: [totals: nt+2][bases: nt+2][scan descriptors]
     const size_t arr = ((static_cast<size_t>(ntiles) + 2) * 8 + 255) & ~static_cast<size_t>(255);
@@ -627,12 +653,12 @@ static int dispatch_arg_dense(int is_min, const void *content, const int64_t *of
     if (rc) return rc;
     if (is_min)
         segarg_direct_kernel<true, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
-            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, status,
-            static_cast<uint32_t>(ntiles));
+            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+            status, static_cast<uint32_t>(ntiles));
     else
         segarg_direct_kernel<false, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
-            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, status,
-            static_cast<uint32_t>(ntiles));
+            static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+            status, static_cast<uint32_t>(ntiles));
     return check_launch("segarg_direct_kernel");
 }
 
@@ -654,6 +680,11 @@ int jg_segreduce(const void *content, int dtype, const int64_t *offsets, int64_t
         case JG_I32: return dispatch_reduce<int32_t, int64_t>(op, content, offsets, n, out, s);
         case JG_I64: return dispatch_reduce<int64_t, int64_t>(op, content, offsets, n, out, s);
         case JG_U8: return dispatch_reduce<uint8_t, uint64_t>(op, content, offsets, n, out, s);
+        case JG_I8: return dispatch_reduce<int8_t, int64_t>(op, content, offsets, n, out, s);
+        case JG_I16: return dispatch_reduce<int16_t, int64_t>(op, content, offsets, n, out, s);
+        case JG_U16: return dispatch_reduce<uint16_t, uint64_t>(op, content, offsets, n, out, s);
+        case JG_U32: return dispatch_reduce<uint32_t, uint64_t>(op, content, offsets, n, out, s);
+        case JG_U64: return dispatch_reduce<uint64_t, uint64_t>(op, content, offsets, n, out, s);
         case JG_B8:
             // bool: sum/prod -> int64, any/all -> bool; min/max -> float64 with +-inf identities (jagged.py:1530)
             switch (op) {
@@ -682,23 +713,33 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
         case JG_I64: return dispatch_arg<int64_t>(is_min, content, offsets, n, best, best_value, s);
         case JG_U8:
         case JG_B8: return dispatch_arg<uint8_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_I8: return dispatch_arg<int8_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_I16: return dispatch_arg<int16_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_U16: return dispatch_arg<uint16_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_U32: return dispatch_arg<uint32_t>(is_min, content, offsets, n, best, best_value, s);
+        case JG_U64: return dispatch_arg<uint64_t>(is_min, content, offsets, n, best, best_value, s);
     }
     set_error("jg_segargminmax: unsupported dtype %d", dtype);
     return -2;
 }
 
 int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
-                          int64_t *out_offsets, int64_t *out_index, int64_t *total, int32_t *status, void *ws,
-                          size_t ws_bytes, void *stream) {
+                          int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total, int32_t *status,
+                          void *ws, size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && out_offsets, "jg_segargminmax_dense: bad arguments");
     cudaStream_t s = as_stream(stream);
     switch (dtype) {
-        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
-        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
-        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
-        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
+        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
         case JG_U8:
-        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, total, status, ws, ws_bytes, s);
+        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_I8: return dispatch_arg_dense<int8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_I16: return dispatch_arg_dense<int16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_U16: return dispatch_arg_dense<uint16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_U32: return dispatch_arg_dense<uint32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_U64: return dispatch_arg_dense<uint64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
     }
     set_error("jg_segargminmax_dense: unsupported dtype %d", dtype);
     return -2;

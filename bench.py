@@ -379,7 +379,7 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         "jg_segargminmax", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(best), ctypes.c_void_p(0), st()))
     aoff, aidx = empty(N + 1, np.int64), empty(N, np.int64)
     add("segargmax_dense_f32", v * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
-        "jg_segargminmax_dense", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(aoff), _vp(aidx), _vp(scal),
+        "jg_segargminmax_dense", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(aoff), _vp(aidx), ctypes.c_void_p(0), _vp(scal),
         _vp(scal, 1), ws, wsb, st()))
     add("compact_nonneg", 8 * N + 8 * N + 8 * N, N, lambda: _lib.call(
         "jg_compact_nonneg", _vp(best), N, _vp(aoff), _vp(aidx), _vp(scal), ws, wsb, st()))
@@ -418,7 +418,7 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         "jg_segreduce", pt64.data_ptr(), _lib.JG_F64, off.data_ptr(), N, _lib.SUM, _vp(out64), M, st()))
     aoff64, aidx64 = empty(N + 1, np.int64), empty(N, np.int64)
     add("segargmax_dense_f64", 8 * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
-        "jg_segargminmax_dense", pt64.data_ptr(), _lib.JG_F64, off.data_ptr(), N, 0, _vp(aoff64), _vp(aidx64), _vp(scal),
+        "jg_segargminmax_dense", pt64.data_ptr(), _lib.JG_F64, off.data_ptr(), N, 0, _vp(aoff64), _vp(aidx64), ctypes.c_void_p(0), _vp(scal),
         _vp(scal, 1), ws, wsb, st()))
     mask64 = empty(M, np.bool_)
     add("greater_f64", 8 * M + M, M, lambda: _lib.call(

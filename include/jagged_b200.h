@@ -135,8 +135,11 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
  * holds only NaN, JG_ST_ARG_ALLNAN is raised in *status, the outputs are not valid and the caller must use
  * jg_segargminmax + jg_compact_nonneg instead.                                                                    */
 int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
-                          int64_t *out_offsets, int64_t *out_index, int64_t *total, int32_t *status, void *ws,
-                          size_t ws_bytes, void *stream);
+                          int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total, int32_t *status,
+                          void *ws, size_t ws_bytes, void *stream);
+/* out_value (optional, content dtype, n items): the extreme value of every event that has one, in the same dense
+ * order as out_index -- i.e. the "leading object" a[a.argmax()] (jagged.py:541-560 applied to the result) without
+ * the gather pass.                                                                                                 */
 /* turn best[] into the dense result: out_offsets[n+1] (0/1 counts scanned) and out_index[<=n]; *total = count.   */
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
                       void *ws, size_t ws_bytes, void *stream);

@@ -206,6 +206,15 @@ def main():
     # 10. single event / single element
     std_case("single", [1], np.array([3.25], dtype=np.float64), threshold=1.0)
 
+    # 11. narrow and unsigned integer content (result dtypes int64 / uint64, wrap-around sums and products)
+    counts = rng.poisson(5.0, 400)
+    m = int(counts.sum())
+    std_case("ints_i8", counts, rng.integers(-128, 128, m).astype(np.int8), choose_max=2, threshold=3)
+    std_case("ints_i16", counts, rng.integers(-2**15, 2**15, m).astype(np.int16), choose_max=2, threshold=100)
+    std_case("ints_u16", counts, rng.integers(0, 2**16, m).astype(np.uint16), choose_max=2, threshold=30000)
+    std_case("ints_u32", counts, rng.integers(0, 2**32, m).astype(np.uint32), choose_max=2, threshold=2**31)
+    std_case("ints_u64", counts, rng.integers(0, 2**64, m, dtype=np.uint64), choose_max=2, threshold=2**63)
+
 
 if __name__ == "__main__":
     main()

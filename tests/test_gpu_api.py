@@ -314,6 +314,49 @@ def test_records_mixed_dtypes(ak):          # record gather groups leaf columns 
     assert (p.i0.q * p.i1.q).tolist() == [[-1], [], [1, -1, -1], []]
 
 
+def test_leading_object_fused(ak):           # BASELINE configs[2]: a[a.argmax()] reuses the values of the arg pass
+    from awkward0_b200 import _lib
+    from oracle import jagged_oracle as orc
+    rng = np.random.default_rng(31)
+    for dt in (np.float32, np.float64, np.int32, np.int64, np.uint8, np.int16):
+        counts = rng.poisson(2.5, 5000)
+        counts[rng.integers(0, 5000, 5)] = rng.integers(40, 3000, 5)        # warp- and block-wide events
+        content = (rng.normal(0, 50, counts.sum())).astype(dt)
+        offsets = orc.counts2offsets(counts)
+        a = ak.JaggedArray.fromcounts(counts, content)
+        for name, ismin in (("argmax", False), ("argmin", True)):
+            arg = getattr(a, name)()
+            assert arg._arg_source is not None
+            before = _lib.LAUNCHES[0]
+            lead = a[arg]
+            assert _lib.LAUNCHES[0] == before                                 # no gather pass
+            woff, widx = orc.argminmax(offsets, content, ismin)
+            assert np.array_equal(lead.offsets.get(), woff)
+            want = content[(offsets[:-1][np.diff(woff) > 0]) + widx]
+            got = lead.content.get()
+            assert got.dtype == want.dtype and np.array_equal(got, want)
+            # the same index applied to ANOTHER array of the same shape takes the gather path and agrees
+            other = ak.JaggedArray.fromcounts(counts, content.copy())
+            before = _lib.LAUNCHES[0]
+            lead2 = other[arg]
+            assert _lib.LAUNCHES[0] > before
+            assert np.array_equal(lead2.content.get(), want) and np.array_equal(lead2.offsets.get(), woff)
+            assert lead.counts.tolist() == (counts > 0).astype(int).tolist()
+    # NaN events fall back to the exact path (no cached values) and still index correctly
+    a = ak.JaggedArray.fromiter([[1.0, np.nan, 3.0], [np.nan], [], [2.0, 5.0]])
+    arg = a.argmax()
+    assert arg.tolist() == [[2], [], [], [1]] and arg._arg_source is None
+    assert a[arg].tolist() == [[3.0], [], [], [5.0]]
+    # switch off: plain gather
+    ak.JaggedArray.cache_arg_values = False
+    try:
+        b = ak.JaggedArray.fromcounts([2, 0, 1], [1.0, 4.0, 2.0])
+        arg = b.argmax()
+        assert arg._arg_source is None and b[arg].tolist() == [[4.0], [], [2.0]]
+    finally:
+        ak.JaggedArray.cache_arg_values = True
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()

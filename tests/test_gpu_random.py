@@ -33,7 +33,9 @@ def make_counts(kind, n, rng):
 
 CASES = [("poisson5", 300000, np.float32), ("poisson5", 300000, np.float64), ("poisson40", 20000, np.float32),
          ("geometric", 20000, np.float64), ("sparse", 100000, np.float32), ("poisson5", 1000, np.int32),
-         ("geometric", 3000, np.int64)]
+         ("geometric", 3000, np.int64), ("poisson5", 20000, np.int8), ("geometric", 3000, np.int16),
+         ("poisson5", 20000, np.uint16), ("poisson40", 2000, np.uint32), ("geometric", 3000, np.uint64),
+         ("poisson5", 20000, np.uint8)]
 
 
 @pytest.mark.parametrize("kind,n,dtype", CASES)
