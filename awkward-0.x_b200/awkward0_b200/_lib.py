@@ -28,6 +28,8 @@ ST_COUNTS_MISMATCH = 32
 ST_NOT_OFFSETS = 64
 ST_STOPS_LT_STARTS = 128
 ST_ARG_ALLNAN = 256
+ST_SORT_LONG = 512
+SORT_LONG = 2048             # kSortLong in csrc/jg_sort.cu
 
 SUM, PROD, MIN, MAX, ANY, ALL, COUNT_NONZERO = range(7)
 
@@ -57,6 +59,11 @@ PROTOTYPES = {
     "jg_localindex": (_i, [_vp, _i64, _vp, _vp]),
     "jg_startsstops2parents": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "jg_compact_gather": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "jg_segment_scatter": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "jg_offsets_rebase": (_i, [_vp, _i64, _i64, _vp, _vp]),
+    "jg_argsort": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
+    "jg_argsort_long_workspace": (_i64, [_i64]),
+    "jg_argsort_long": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _sz, _vp]),
     "jg_segreduce": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "jg_segargminmax": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -36,6 +36,19 @@ def _isintegertype(dtype):
     return issubclass(numpy.dtype(dtype).type, numpy.integer)
 
 
+class _bothmethod(object):
+    """awkward0.util.bothmethod: callable on the class (arrays = all inputs) or on an instance (self comes first)."""
+
+    def __init__(self, fcn):
+        self.fcn = fcn
+
+    def __get__(self, ins, typ=None):
+        fcn = self.fcn
+        if ins is None:
+            return lambda *args, **kwargs: fcn(True, typ, *args, **kwargs)
+        return lambda *args, **kwargs: fcn(False, ins, *args, **kwargs)
+
+
 class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     """JaggedArray(starts, stops, content) on the device -- drop-in for awkward0.JaggedArray's hot path."""
 
@@ -1327,13 +1340,158 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         self._notimpl("regular")
 
     def argsort(self, ascending=False):
-        self._notimpl("argsort")
+        """jagged.py:1603-1631 -> jg_argsort (one pass; events beyond 2048 elements through jg_argsort_long)."""
+        a, off, n, first, last = self._dense()
+        if isinstance(a._content, JaggedArray):      # jagged.py:1605-1606
+            return self._make(a._rebased_offsets(), a._dense_content().argsort(ascending), last - first)
+        if not isinstance(a._content, DeviceArray):
+            raise NotImplementedError("argsort of Table content is outside the GPU hot path")
+        col = a._content
+        total = last - first
+        out = empty(total, INDEXTYPE)
+        if n > 0 and total > 0:
+            cap = total // (_lib.SORT_LONG + 1) + 1
+            scal = runtime.scalars()
+            # [0] unused, [1] status, [2] number of long events, [3:] the first few of them; a bigger list if needed
+            if cap <= 4:
+                long_list = scal[2:]
+            else:
+                long_list = torch.zeros(cap + 1, dtype=torch.int64, device=scal.device)
+            call("jg_argsort", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ascending else 0, _vp(out),
+                 _vp(scal, 1), _vp(long_list), cap, runtime.stream())
+            if total > _lib.SORT_LONG:                 # otherwise no event can be long: no read-back at all
+                _, status, _ = runtime.read(scal)
+                if status & _lib.ST_SORT_LONG:
+                    listed = long_list.cpu().numpy()
+                    events = numpy.sort(listed[1:1 + int(listed[0])])
+                    where = torch.as_tensor(numpy.concatenate([events, events + 1]), device=scal.device)
+                    bounds = off.tensor[where].cpu().numpy().reshape(2, -1)
+                    for start, stop in bounds.T:
+                        count = int(stop - start)
+                        wsb = int(_lib.lib.jg_argsort_long_workspace(count))
+                        ws = empty(wsb // 4, numpy.int32)
+                        call("jg_argsort_long", col.data_ptr(), jg_code(col.dtype), int(start), count,
+                             1 if ascending else 0, _vp(out, int(start) - first), _vp(ws), wsb, runtime.stream())
+        res = self._make(a._rebased_offsets(), DeviceArray(out, INDEXTYPE), total)
+        res._counts = a._counts
+        return res
 
     def pad(self, length, maskedwhen=True, clip=False, axis=0):
         self._notimpl("pad")
 
-    def concatenate(self, arrays, axis=0):
-        self._notimpl("concatenate")
+    # ------------------------------------------------------------------------------------------------------
+    # concatenate (base.py:567-605 -> jagged.py:1633-1733)
+    # ------------------------------------------------------------------------------------------------------
+    @_bothmethod
+    def concatenate(isclassmethod, cls_or_self, arrays, axis=0):
+        if isclassmethod:
+            cls = cls_or_self
+            arrays = tuple(arrays)
+        else:
+            cls = type(cls_or_self)
+            arrays = (cls_or_self,) + tuple(arrays)
+        if len(arrays) < 1:
+            raise ValueError("at least one array needed to concatenate")
+        if not all(isinstance(x, JaggedArray) for x in arrays):
+            raise NotImplementedError("concatenating a JaggedArray with other array types (UnionArray) is outside the GPU hot path")
+        for x in arrays:
+            x.valid(exception=True)
+        if axis == 0:
+            return cls._concatenate_axis0(arrays)
+        if axis == 1:
+            return cls._concatenate_axis1(arrays)
+        raise NotImplementedError("axis > 1")
+
+    @classmethod
+    def _concat_flat(cls, columns):
+        """numpy.concatenate of dense leaf columns: one allocation, one device copy (with cast) per input."""
+        first = columns[0]
+        if isinstance(first, Table):
+            if not all(isinstance(c, Table) and list(c.columns) == list(first.columns) for c in columns):
+                raise ValueError("cannot concatenate Tables with different fields")
+            out = Table.named(first.rowname)
+            for name in first.columns:
+                out._contents[name] = cls._concat_flat([c[name] for c in columns])
+            return out
+        if isinstance(first, JaggedArray):
+            if not all(isinstance(c, JaggedArray) for c in columns):
+                raise ValueError("cannot concatenate nested and flat content")
+            return cls._concatenate_axis0(columns)
+        if not all(isinstance(c, DeviceArray) for c in columns):
+            raise ValueError("cannot concatenate flat and structured content")
+        dtype = numpy.result_type(*[c.dtype for c in columns])
+        out = empty(sum(len(c) for c in columns), dtype)
+        at = 0
+        for c in columns:
+            if len(c):
+                c = c if c.dtype == dtype else _ufunc.cast(c, dtype)
+                out[at:at + len(c)].copy_(c.tensor)
+                at += len(c)
+        return DeviceArray(out, dtype)
+
+    @classmethod
+    def _concatenate_axis0(cls, arrays):
+        """jagged.py:1633-1649 -> jg_offsets_rebase per input + one content copy per input and leaf column."""
+        parts = [x._dense() for x in arrays]
+        nevents = sum(p[2] for p in parts)
+        out_offsets = empty(nevents + 1, INDEXTYPE)
+        at = base = 0
+        for a, off, n, first, last in parts:
+            call("jg_offsets_rebase", off.data_ptr(), n + 1, base - first, _vp(out_offsets, at), runtime.stream())
+            at += n
+            base += last - first
+        content = cls._concat_flat([p[0]._dense_content() for p in parts])
+        return cls._make(DeviceArray(out_offsets, INDEXTYPE), content, base)
+
+    @classmethod
+    def _concatenate_axis1(cls, arrays):
+        """jagged.py:1651-1733 -> counts sum, one scan, one jg_segment_scatter per input and leaf column."""
+        if any(len(a) != len(arrays[0]) for a in arrays):
+            raise ValueError("cannot concatenate JaggedArrays of different lengths with axis=1")
+        parts = [x._dense() for x in arrays]
+        n = parts[0][2]
+        counts = [p[0].counts for p in parts]
+        before = [None] * len(parts)                  # counts of the inputs in front of input k, per event
+        run = counts[0]
+        for k in range(1, len(parts)):
+            before[k] = run
+            run = _ufunc.binary(numpy.add, run, counts[k])
+        out_offsets, total, _ = cls._scan_counts(run)
+        slots = []
+        for k in range(len(parts)):
+            slots.append(out_offsets[:-1] if before[k] is None else _ufunc.binary(numpy.add, out_offsets[:-1], before[k]))
+
+        def merge(columns):
+            first = columns[0]
+            if isinstance(first, Table):
+                if not all(isinstance(c, Table) and set(c.columns) == set(first.columns) for c in columns):
+                    raise ValueError("cannot concatenate Tables with different fields")
+                out = Table.named(first.rowname)
+                for name in first.columns:
+                    out._contents[name] = merge([c[name] for c in columns])
+                return out
+            if not all(isinstance(c, DeviceArray) for c in columns):
+                raise NotImplementedError("concatenate with axis=1 is not implemented for these types")
+            nonempty = [c for c in columns if len(c)]
+            if not nonempty:
+                dtype = columns[0].dtype
+            elif all(c.dtype == numpy.bool_ for c in columns):
+                dtype = BOOLTYPE
+            else:
+                dtype = numpy.result_type(*[c.dtype for c in nonempty])
+            out = empty(total, dtype)
+            for k, c in enumerate(columns):
+                if len(c) == 0:
+                    continue
+                c = c if c.dtype == dtype else _ufunc.cast(c, dtype)
+                a, off, _, first_k, _ = parts[k]
+                # the column is dense content starting at offsets[0]: pass the un-rebased offsets with a shifted base
+                call("jg_segment_scatter", c.data_ptr(-first_k), c.itemsize, off.data_ptr(),
+                     slots[k].data_ptr(), n, _vp(out), runtime.stream())
+            return DeviceArray(out, dtype)
+
+        content = merge([p[0]._dense_content() for p in parts])
+        return cls._make(out_offsets, content, total)
 
 
 def _rebuild(template, leaves):

@@ -208,6 +208,31 @@ compact_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__
     }
 }
 
+// concatenate(axis=1): out[dst_starts[i] + k] = content[offsets[i] + k]   (jagged.py:1651-1733: the reference
+// builds a boolean mask per input array from +1/-1 marks and a cumsum, then assigns through it)
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+segment_scatter_kernel(const V *__restrict__ content, const int64_t *__restrict__ offsets,
+                       const int64_t *__restrict__ dst_starts, int64_t n, V *__restrict__ out) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ int64_t s_dst[kTileEvents];
+    EventTile tile;
+    tile.load(s_off, offsets, n, blockIdx.x);
+    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_dst[ev] = dst_starts[tile.event0 + ev];
+    __syncthreads();
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
+        const int ev = tile.find_event(j);
+        out[s_dst[ev] + (j - tile.off[ev])] = content[j];
+    }
+}
+
+// concatenate(axis=0): offsets of a later array shifted by the content that precedes it (jagged.py:1633-1649)
+__global__ void __launch_bounds__(256)
+offsets_rebase_kernel(const int64_t *__restrict__ offsets, int64_t count, int64_t delta, int64_t *__restrict__ out) {
+    for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < count; i += gridDim.x * 256LL) out[i] = offsets[i] + delta;
+}
+
 static inline int grid_for(int64_t work, int threads, int per_thread = 1) {
     int64_t blocks = ceil_div(work, static_cast<int64_t>(threads) * per_thread);
     int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -323,6 +348,43 @@ int jg_compact_gather(const void *content, int itemsize, const int64_t *starts, 
             return -2;
     }
     return check_launch("compact_gather_kernel");
+}
+
+int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets, const int64_t *dst_starts, int64_t n,
+                       void *out, void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(offsets && dst_starts && out, "jg_segment_scatter: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1:
+            segment_scatter_kernel<uint8_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), offsets,
+                                                                      dst_starts, n, static_cast<uint8_t *>(out));
+            break;
+        case 2:
+            segment_scatter_kernel<uint16_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), offsets,
+                                                                       dst_starts, n, static_cast<uint16_t *>(out));
+            break;
+        case 4:
+            segment_scatter_kernel<uint32_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), offsets,
+                                                                       dst_starts, n, static_cast<uint32_t *>(out));
+            break;
+        case 8:
+            segment_scatter_kernel<uint64_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), offsets,
+                                                                       dst_starts, n, static_cast<uint64_t *>(out));
+            break;
+        default:
+            set_error("jg_segment_scatter: unsupported itemsize %d", itemsize);
+            return -2;
+    }
+    return check_launch("segment_scatter_kernel");
+}
+
+int jg_offsets_rebase(const int64_t *offsets, int64_t count, int64_t delta, int64_t *out, void *stream) {
+    if (count <= 0) return 0;
+    JG_REQUIRE(offsets && out, "jg_offsets_rebase: bad arguments");
+    offsets_rebase_kernel<<<grid_for(count, 256, 4), 256, 0, as_stream(stream)>>>(offsets, count, delta, out);
+    return check_launch("offsets_rebase_kernel");
 }
 
 int jg_broadcast(const void *flat, int itemsize, const int64_t *offsets, int64_t n, void *out, void *stream) {

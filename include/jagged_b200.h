@@ -48,7 +48,8 @@ enum {
     JG_ST_COUNTS_MISMATCH = 32,  /* "cannot fit contents of JaggedArray into the given ..."  jagged.py:911 */
     JG_ST_NOT_OFFSETS     = 64,  /* starts[1:] != stops[:-1]                                 jagged.py:358 */
     JG_ST_STOPS_LT_STARTS = 128, /* "stops must be greater than or equal to starts"          jagged.py:501 */
-    JG_ST_ARG_ALLNAN      = 256  /* a non-empty event holds only NaN: redo argmin/argmax with the exact path   */
+    JG_ST_ARG_ALLNAN      = 256, /* a non-empty event holds only NaN: redo argmin/argmax with the exact path   */
+    JG_ST_SORT_LONG       = 512  /* jg_argsort left events to jg_argsort_long (their indices are in long_list)  */
 };
 
 /* ---- reducers (base.py:193-215) -------------------------------------------------------------------------- */
@@ -167,6 +168,28 @@ int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int6
                     int64_t *total, void *ws, size_t ws_bytes, void *stream);
 /* plain gather out[k] = content[index[k]] (jagged.py:1294 content[left]); no bounds check beyond content_len      */
 int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_index, void *out, void *stream);
+
+/* ---- per-event argsort ------------------------------------------------------------------ */
+/* jagged.py:1603-1631  out[offsets[i]-offsets[0] + r] = local index of the element of event i with rank r: stable
+ * by value (descending unless `ascending`), ties and -0.0/0.0 in position order, NaN last in both directions.
+ * Events longer than 2048 elements are not sorted here: JG_ST_SORT_LONG is raised in *status, long_list[0] counts
+ * them and long_list[1 .. long_cap] holds their event indices (long_list[0] must be zero on entry; a caller that
+ * sizes long_cap = (offsets[n]-offsets[0]) / 2049 + 1 can never overflow it); sort each with jg_argsort_long.       */
+int jg_argsort(const void *content, int dtype, const int64_t *offsets, int64_t n, int ascending, int64_t *out,
+               int32_t *status, int64_t *long_list, int64_t long_cap, void *stream);
+/* one long event: content[start .. start+count) -> out[0 .. count) (local indices); ws >= jg_argsort_long_workspace  */
+int64_t jg_argsort_long_workspace(int64_t count);
+int jg_argsort_long(const void *content, int dtype, int64_t start, int64_t count, int ascending, int64_t *out,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* ---- concatenation ---------------------------------------------------------------------- */
+/* jagged.py:1633-1649  concatenate(axis=0): out[i] = offsets[i] + delta for `count` entries (offsets of a later
+ * array shifted by the number of content items in front of it)                                                      */
+int jg_offsets_rebase(const int64_t *offsets, int64_t count, int64_t delta, int64_t *out, void *stream);
+/* jagged.py:1651-1733  concatenate(axis=1): out[dst_starts[i] + k] = content[offsets[i] + k] -- event i of a dense
+ * input lands at its slot inside the merged event                                                                    */
+int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets, const int64_t *dst_starts, int64_t n,
+                       void *out, void *stream);
 
 /* ---- broadcasting and elementwise ufuncs ------------------------------------------------------------------------ */
 /* jagged.py:866-875  tojagged(flat): out[j - offsets[0]] = flat[parent(j)]                                          */

@@ -461,6 +461,88 @@ def cross(offsets_a, content_a, offsets_b, content_b):
 # helpers for tests
 # --------------------------------------------------------------------------------------
 
+def concatenate_axis0(parts):
+    """jagged.py:1633-1649 (via base.py:567-605) -- append the events of dense arrays [(offsets, content), ...].
+
+    The reference concatenates starts / stops / content and shifts the starts and stops of every later array by
+    the length of the content in front of it; on dense inputs that is one offsets array.  Content dtypes promote
+    like numpy.concatenate.
+    """
+    offs, contents, base = [np.zeros(1, dtype=INDEX)], [], 0
+    for offsets, content in parts:
+        offsets = np.asarray(offsets, dtype=INDEX)
+        content = np.asarray(content)[offsets[0]:offsets[-1]]
+        offs.append(offsets[1:] - offsets[0] + base)
+        contents.append(content)
+        base += len(content)
+    return np.concatenate(offs), np.concatenate(contents)
+
+
+def concatenate_axis1(parts):
+    """jagged.py:1651-1733 -- event i of the result is event i of every input, one after the other.
+
+    The reference stacks the counts (vstack, transpose, flatten), scans them, and fills the content through one
+    boolean mask per input (+1 at the slot starts, -1 at the slot stops, cumsum); the slots are contiguous so
+    this is a per-event copy.  dtype: numpy promotion of the non-empty inputs, bool only if all are bool
+    (:1690-1699); all inputs empty -> dtype of the first.
+    """
+    n = len(parts[0][0]) - 1
+    if any(len(o) - 1 != n for o, _ in parts):
+        raise ValueError("cannot concatenate JaggedArrays of different lengths with axis=1")
+    dense = [(np.asarray(o, dtype=INDEX), np.asarray(c)) for o, c in parts]
+    counts = np.vstack([offsets2counts(o) for o, _ in dense])
+    slots = counts2offsets(counts.T.flatten())
+    flats = [c[o[0]:o[-1]] for o, c in dense]
+    nonempty = [f for f in flats if len(f)]
+    if not nonempty:
+        dtype = flats[0].dtype
+    elif all(f.dtype == np.dtype(bool) for f in flats):
+        dtype = np.dtype(bool)
+    else:
+        dtype = np.array([f[0] for f in nonempty]).dtype
+    content = np.zeros(slots[-1], dtype=dtype)
+    for k, (o, _) in enumerate(dense):
+        starts_k = slots[k:-1:len(dense)]
+        c = counts[k]
+        dst = np.repeat(starts_k - (o[:-1] - o[0]), c) + np.arange(len(flats[k]), dtype=INDEX)
+        content[dst] = flats[k]
+    return slots[::len(dense)].copy(), content
+
+
+def argsort(offsets, content, ascending=False):
+    """jagged.py:1603-1631 -- per-event argsort as LOCAL indices, same counts as the input.
+
+    The reference repeatedly takes ``reducer(tmp) == tmp`` (every element equal to the event's current extreme),
+    appends their local indices in position order and removes them; NaN compares unequal to everything, so NaN
+    stays until only NaN is left (:1618-1620) and is then emitted in position order.  Logically that is a stable
+    sort by value (descending unless ``ascending``) with ties -- including -0.0 == 0.0 -- in position order and
+    NaN last in both directions.
+    """
+    offsets = np.asarray(offsets, dtype=INDEX)
+    content = np.asarray(content)
+    out = np.empty(offsets[-1] - offsets[0], dtype=INDEX)
+    base = offsets[0]
+    for i in range(len(offsets) - 1):
+        x = content[offsets[i]:offsets[i + 1]]
+        if len(x) == 0:
+            continue
+        nan = np.isnan(x) if x.dtype.kind == "f" else np.zeros(len(x), dtype=bool)
+        good, bad = np.nonzero(~nan)[0], np.nonzero(nan)[0]
+        v = x[good]
+        if x.dtype.kind == "b":
+            v = v.astype(np.int8)
+        if ascending:
+            order = np.argsort(v, kind="stable")
+        elif x.dtype.kind == "u":
+            order = np.argsort(~v, kind="stable")            # descending without leaving the unsigned type
+        elif x.dtype.kind == "i":
+            order = np.argsort(-1 - v, kind="stable")         # exact for the most negative value too
+        else:
+            order = np.argsort(-v, kind="stable")
+        out[offsets[i] - base:offsets[i + 1] - base] = np.concatenate([good[order], bad])
+    return offsets - base, out
+
+
 def tolist(offsets, content):
     """base.py:159-172 -- nested python lists of a dense jagged array."""
     offsets = np.asarray(offsets)

@@ -87,6 +87,18 @@ def run_case(awkward0, name, offsets, content, flat, idx_counts, idx_content, b_
     out["out_gather_counts"] = c
     out["out_gather_flat"] = f
 
+    # argsort and concatenate
+    with np.errstate(all="ignore"):
+        for label, asc in (("desc", False), ("asc", True)):
+            c, f = logical(a.argsort(ascending=asc))
+            assert np.array_equal(c, out["out_counts"])
+            out["out_argsort_%s_flat" % label] = f.astype(np.int64)
+    b = J.fromcounts(b_counts, b_content)
+    c, f = logical(J.concatenate([a, b, a]))
+    out["out_cat0_counts"], out["out_cat0_flat"] = c, f
+    c, f = logical(a.concatenate([b, a], axis=1))
+    out["out_cat1_counts"], out["out_cat1_flat"] = c, f
+
     if not combos:
         return save(name, out)
 

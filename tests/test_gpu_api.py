@@ -357,6 +357,77 @@ def test_leading_object_fused(ak):           # BASELINE configs[2]: a[a.argmax()
         ak.JaggedArray.cache_arg_values = True
 
 
+def test_concatenate(ak):                    # test_jagged.py:451-487
+    J = ak.JaggedArray
+    lst = [[1, 2, 3], [], [4, 5], [6, 7], [8], [], [9], [10, 11], [12]]
+    a1, a2, a3 = J.fromiter(lst[:3]), J.fromiter(lst[3:6]), J.fromiter(lst[6:])
+    assert a1.concatenate([a2, a3]).tolist() == lst
+    assert J.concatenate([a1, a2, a3]).tolist() == lst
+    a1 = J([0, 0, 3, 3, 5], [0, 3, 3, 5, 10], [0.0, 1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9])
+    b1 = J([0, 0, 5, 7, 7], [0, 5, 7, 7, 10], [6.5, 7.6, 8.7, 9.8, 10.9, 4.3, 5.4, 1., 2.1, 3.2])
+    c1 = a1.concatenate([b1], axis=1)
+    assert c1.tolist() == [[], [0., 1.1, 2.2, 6.5, 7.6, 8.7, 9.8, 10.9], [4.3, 5.4], [3.3, 4.4],
+                           [5.5, 6.6, 7.7, 8.8, 9.9, 1., 2.1, 3.2]]
+    a2, b2 = J([0], [3], [False, False, False]), J([0], [3], [True, True, True])
+    assert a2.concatenate([b2], axis=1).content.dtype == np.dtype(bool)
+    a3 = a1[[True, True, True, False, True]]
+    b3 = b1[[True, True, True, True, False]]
+    assert a3.concatenate([b3], axis=1).tolist() == [[], [0., 1.1, 2.2, 6.5, 7.6, 8.7, 9.8, 10.9], [4.3, 5.4],
+                                                      [5.5, 6.6, 7.7, 8.8, 9.9]]
+    for dt in (np.int32, np.int64, np.float32, np.float64):
+        a = J([0], [1], np.ones(1, dtype=dt))
+        assert a.concatenate([a], axis=1).content.dtype == np.dtype(dt)
+    with pytest.raises(ValueError):
+        a1.concatenate([a2], axis=1)
+    with pytest.raises(ValueError):
+        J.concatenate([])
+    # records, general layouts and slices (offsets[0] != 0)
+    mu = J.zip(pt=J.fromcounts([2, 0, 1], [1.0, 2.0, 3.0]), q=J.fromcounts([2, 0, 1], [1, -1, 1]))
+    both = mu.concatenate([mu[1:]])
+    assert both.pt.tolist() == [[1.0, 2.0], [], [3.0], [], [3.0]] and both.q.tolist() == [[1, -1], [], [1], [], [1]]
+    side = mu.concatenate([mu], axis=1)
+    assert side.pt.tolist() == [[1.0, 2.0, 1.0, 2.0], [], [3.0, 3.0]]
+    assert side.q.tolist() == [[1, -1, 1, -1], [], [1, 1]]
+    x = J.fromiter(lst)
+    assert x[2:7].concatenate([x[5:]], axis=0).tolist() == lst[2:7] + lst[5:]
+    assert x[2:6].concatenate([x[5:]], axis=1).tolist() == [p + q for p, q in zip(lst[2:6], lst[5:])]
+    # mixed dtypes promote like numpy.concatenate
+    f = J.fromcounts([1, 2], np.array([0.5, 1.5, 2.5], dtype=np.float32))
+    i = J.fromcounts([2, 0], np.array([7, 8], dtype=np.int64))
+    assert J.concatenate([f, i]).content.dtype == np.dtype(np.float64)
+    assert J.concatenate([f, i]).tolist() == [[0.5], [1.5, 2.5], [7.0, 8.0], []]
+    # nested
+    nest = J.fromcounts([2, 1], J.fromcounts([1, 2, 0], [1, 2, 3]))
+    assert nest.concatenate([nest]).tolist() == [[[1], [2, 3]], [[]], [[1], [2, 3]], [[]]]
+
+
+def test_argsort(ak):                        # test_jagged.py:604-607 (masked event left out) + layouts
+    J = ak.JaggedArray
+    inf, nan = np.inf, np.nan
+    a = J.fromiter([[2., 3., 1.], [4., -inf, 5.], [inf, 4., nan, -inf], [nan]])
+    assert a.argsort().tolist() == [[1, 0, 2], [2, 0, 1], [0, 1, 3, 2], [0]]
+    assert a.argsort(True).tolist() == [[2, 0, 1], [1, 0, 2], [3, 1, 0, 2], [0]]
+    assert a[a.argsort()].tolist()[:2] == [[3., 2., 1.], [5., 4., -inf]]
+    assert a[1:3].argsort().tolist() == [[2, 0, 1], [0, 1, 3, 2]]
+    assert a[[3, 0]].argsort(True).tolist() == [[0], [2, 0, 1]]
+    assert J.fromcounts([0, 0], np.zeros(0)).argsort().tolist() == [[], []]
+    nest = J.fromcounts([2, 1], J.fromcounts([2, 3, 0], [1, 2, 5, 3, 4]))
+    assert nest.argsort().tolist() == [[[1, 0], [0, 2, 1]], [[]]]
+    # events around and beyond the shared-memory limits: 2048 / 2049 / 4096 / 4097 / 70001 elements, ties and NaN
+    from oracle import jagged_oracle as orc
+    rng = np.random.default_rng(77)
+    counts = np.array([3, 2048, 0, 2049, 5, 4096, 4097, 1, 70001, 2, 9000], dtype=np.int64)
+    for dt in (np.float32, np.float64, np.int16):
+        vals = rng.integers(-300, 300, counts.sum()).astype(dt)
+        if np.dtype(dt).kind == "f":
+            vals[rng.random(len(vals)) < 0.01] = nan
+        off = orc.counts2offsets(counts)
+        for asc in (False, True):
+            got = J.fromcounts(counts, vals).argsort(asc)
+            woff, widx = orc.argsort(off, vals, asc)
+            assert np.array_equal(got.offsets.get(), woff) and np.array_equal(got.content.get(), widx)
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
@@ -406,7 +477,7 @@ def test_exceptions(ak):
     with pytest.raises(ValueError, match="offsets must be a non-negative array"):
         J.fromoffsets([-1, 3], CONTENT)
     with pytest.raises(NotImplementedError, match="no CPU fallback"):
-        a.argsort()
+        a.pad(3)
     assert J.fromoffsets([0, 3, 2], CONTENT).valid() is False
     ok = a[J.fromcounts([2, 0, 1, 1], [-1, 0, 1, -5])]       # negative wrap (jagged.py:552-553)
     assert ok.tolist() == [[2.2, 0.0], [], [4.4], [5.5]]

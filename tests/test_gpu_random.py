@@ -71,6 +71,10 @@ def test_differential(ak, kind, n, dtype):
             roff, ridx = O.argminmax(off, content, ismin)
             r = a.argmin() if ismin else a.argmax()
             assert same(r.offsets.get(), roff) and same(r.content.get(), ridx)
+        for asc in (False, True):
+            roff, ridx = O.argsort(off, content, asc)
+            r = a.argsort(asc)
+            assert same(r.offsets.get(), roff) and same(r.content.get(), ridx), ("argsort", asc)
     thr = 20 if np.dtype(dtype).kind == "f" else 0
     moff, mask = O.ufunc_broadcast(np.greater, off, content, thr)
     gm = a > thr

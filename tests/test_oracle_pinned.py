@@ -107,6 +107,59 @@ OFF = np.array([0, 3, 3, 5, 10])
 CONTENT = np.array([0.0, 1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9])
 
 
+@pytest.mark.parametrize("ascending", [False, True])
+def test_argsort(golden, ascending):
+    g = golden
+    with np.errstate(all="ignore"):
+        roff, rflat = O.argsort(g["in_offsets"], g["in_content"], ascending)
+    assert same(O.offsets2counts(roff), g["out_counts"])
+    assert same(rflat, g["out_argsort_%s_flat" % ("asc" if ascending else "desc")])
+
+
+def test_concatenate(golden):
+    g = golden
+    a = (g["in_offsets"], g["in_content"])
+    b = (O.counts2offsets(g["in_b_counts"]), g["in_b_content"])
+    off, content = O.concatenate_axis0([a, b, a])
+    assert same(O.offsets2counts(off), g["out_cat0_counts"]) and same(content, g["out_cat0_flat"])
+    off, content = O.concatenate_axis1([a, b, a])
+    assert same(O.offsets2counts(off), g["out_cat1_counts"]) and same(content, g["out_cat1_flat"])
+
+
+def test_ref_concatenate_literals():           # tests/test_jagged.py:451-487
+    lst = [[1, 2, 3], [], [4, 5], [6, 7], [8], [], [9], [10, 11], [12]]
+
+    def build(rows):
+        counts = np.array([len(r) for r in rows], dtype=np.int64)
+        return O.counts2offsets(counts), np.array([x for r in rows for x in r], dtype=np.int64)
+    off, content = O.concatenate_axis0([build(lst[:3]), build(lst[3:6]), build(lst[6:])])
+    assert O.tolist(off, content) == lst
+    c = np.array([0.0, 1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9])
+    d = np.array([6.5, 7.6, 8.7, 9.8, 10.9, 4.3, 5.4, 1., 2.1, 3.2])
+    off, content = O.concatenate_axis1([(np.array([0, 0, 3, 3, 5, 10]), c), (np.array([0, 0, 5, 7, 7, 10]), d)])
+    assert O.tolist(off, content) == [[], [0., 1.1, 2.2, 6.5, 7.6, 8.7, 9.8, 10.9], [4.3, 5.4], [3.3, 4.4],
+                                      [5.5, 6.6, 7.7, 8.8, 9.9, 1., 2.1, 3.2]]
+    f, t = np.zeros(3, dtype=bool), np.ones(3, dtype=bool)
+    assert O.concatenate_axis1([(np.array([0, 3]), f), (np.array([0, 3]), t)])[1].dtype == np.dtype(bool)
+    for dt in (np.int32, np.int64, np.float32, np.float64):
+        one = (np.array([0, 1]), np.ones(1, dtype=dt))
+        assert O.concatenate_axis1([one, one])[1].dtype == np.dtype(dt)
+
+
+def test_ref_argsort_literals():                # tests/test_jagged.py:604-607 (without the masked event)
+    off = np.array([0, 3, 6, 10, 11])
+    c = np.array([2., 3., 1., 4., -np.inf, 5., np.inf, 4., np.nan, -np.inf, np.nan])
+    assert O.tolist(*O.argsort(off, c)) == [[1, 0, 2], [2, 0, 1], [0, 1, 3, 2], [0]]
+    assert O.tolist(*O.argsort(off, c, True)) == [[2, 0, 1], [1, 0, 2], [3, 1, 0, 2], [0]]
+    off = np.array([0, 3, 3, 5, 10])
+    c = np.array([3.3, 1.1, 2.2, 5.5, 4.4, 9.9, 6.6, 7.7, 8.8, 0.0])
+    assert O.tolist(*O.argsort(off, c)) == [[0, 2, 1], [], [0, 1], [0, 3, 2, 1, 4]]
+    assert O.tolist(*O.argsort(off, c, True)) == [[1, 2, 0], [], [1, 0], [4, 1, 2, 3, 0]]
+    c[[1, 6]] = np.nan
+    assert O.tolist(*O.argsort(off, c)) == [[0, 2, 1], [], [0, 1], [0, 3, 2, 4, 1]]
+    assert O.tolist(*O.argsort(off, c, True)) == [[2, 0, 1], [], [1, 0], [4, 2, 3, 0, 1]]
+
+
 def test_ref_sum_prod_min_max_literals():
     # tests/test_jagged.py:384-386, 398-400, 425-427, 438-440
     assert O.reduce(OFF, CONTENT, "sum").tolist() == [3.3000000000000003, 0.0, 7.7, 38.5]
