@@ -193,38 +193,80 @@ startsstops2parents_kernel(const int64_t *__restrict__ starts, const int64_t *__
     }
 }
 
-// compact(): out[dense[i] + k] = content[starts[i] + k]   (jagged.py:883-942)
-template <typename V>
+// Per-event block moves between a dense layout (offsets) and a general one (one start per event):
+//   GATHER : compact()              out[offsets[i] + k] = content[other[i] + k]   (jagged.py:883-942)
+//   SCATTER: concatenate(axis=1)    out[other[i] + k]   = content[offsets[i] + k] (jagged.py:1651-1733: the reference
+//            builds one boolean mask per input from +1/-1 marks and a cumsum, then assigns through it)
+// Element-parallel over the tile's dense run; the owner table turns a position into its event and a per-event
+// shift (other[i] - offsets[i]) turns the dense address into the general one; 4 loads in flight per thread.
+template <typename V, bool SCATTER>
 __global__ void __launch_bounds__(kTileThreads)
-compact_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__ starts,
-                      const int64_t *__restrict__ dense, int64_t n, V *__restrict__ out) {
+segment_move_kernel(const V *__restrict__ content, const int64_t *__restrict__ offsets,
+                    const int64_t *__restrict__ other, int64_t n, V *__restrict__ out) {
     __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ int64_t s_shift[kTileEvents];
+    __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
     EventTile tile;
-    tile.load(s_off, dense, n, blockIdx.x);
+    tile.load(s_off, offsets, n, blockIdx.x);
+    {
+        const int i0 = threadIdx.x, i1 = threadIdx.x + kTileThreads;
+        if (i0 < tile.nev) s_shift[i0] = __ldg(other + tile.event0 + i0) - s_off[i0];
+        if (i1 < tile.nev) s_shift[i1] = __ldg(other + tile.event0 + i1) - s_off[i1];
+    }
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
-    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
-        const int ev = tile.find_event(j);
-        out[j] = content[starts[tile.event0 + ev] + (j - tile.off[ev])];
+    const bool table = (e1 - e0) <= kOwnPositions;
+    if (table) build_owner_table(s_own, tile, static_cast<int>(e1 - e0));
+    else __syncthreads();
+#pragma unroll 1
+    for (int64_t jb = e0 + threadIdx.x; jb < e1; jb += 4 * kTileThreads) {
+        int64_t src[4], dst[4];
+        V val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t j = jb + u * kTileThreads;
+            src[u] = -1;
+            if (j < e1) {
+                const int ev = table ? static_cast<int>(s_own[j - e0]) : tile.find_event(j);
+                const int64_t g = j + s_shift[ev];
+                src[u] = SCATTER ? j : g;
+                dst[u] = SCATTER ? g : j;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0) val[u] = __ldg(content + src[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0) out[dst[u]] = val[u];
     }
 }
 
-// concatenate(axis=1): out[dst_starts[i] + k] = content[offsets[i] + k]   (jagged.py:1651-1733: the reference
-// builds a boolean mask per input array from +1/-1 marks and a cumsum, then assigns through it)
-template <typename V>
-__global__ void __launch_bounds__(kTileThreads)
-segment_scatter_kernel(const V *__restrict__ content, const int64_t *__restrict__ offsets,
-                       const int64_t *__restrict__ dst_starts, int64_t n, V *__restrict__ out) {
-    __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ int64_t s_dst[kTileEvents];
-    EventTile tile;
-    tile.load(s_off, offsets, n, blockIdx.x);
-    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_dst[ev] = dst_starts[tile.event0 + ev];
-    __syncthreads();
-    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
-    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
-        const int ev = tile.find_event(j);
-        out[s_dst[ev] + (j - tile.off[ev])] = content[j];
+template <bool SCATTER>
+static int launch_segment_move(const void *content, int itemsize, const int64_t *offsets, const int64_t *other,
+                               int64_t n, void *out, cudaStream_t s, const char *what) {
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1:
+            segment_move_kernel<uint8_t, SCATTER><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), offsets,
+                                                                            other, n, static_cast<uint8_t *>(out));
+            break;
+        case 2:
+            segment_move_kernel<uint16_t, SCATTER><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), offsets,
+                                                                             other, n, static_cast<uint16_t *>(out));
+            break;
+        case 4:
+            segment_move_kernel<uint32_t, SCATTER><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), offsets,
+                                                                             other, n, static_cast<uint32_t *>(out));
+            break;
+        case 8:
+            segment_move_kernel<uint64_t, SCATTER><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), offsets,
+                                                                             other, n, static_cast<uint64_t *>(out));
+            break;
+        default:
+            set_error("%s: unsupported itemsize %d", what, itemsize);
+            return -2;
     }
+    return check_launch(what);
 }
 
 // concatenate(axis=0): offsets of a later array shifted by the content that precedes it (jagged.py:1633-1649)
@@ -324,60 +366,17 @@ int jg_startsstops2parents(const int64_t *starts, const int64_t *stops, int64_t 
 int jg_compact_gather(const void *content, int itemsize, const int64_t *starts, const int64_t *dense_offsets,
                       int64_t n, void *out, void *stream) {
     if (n <= 0) return 0;
-    cudaStream_t s = as_stream(stream);
-    const unsigned g = tile_grid(n);
-    switch (itemsize) {
-        case 1:
-            compact_gather_kernel<uint8_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), starts,
-                                                                     dense_offsets, n, static_cast<uint8_t *>(out));
-            break;
-        case 2:
-            compact_gather_kernel<uint16_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), starts,
-                                                                      dense_offsets, n, static_cast<uint16_t *>(out));
-            break;
-        case 4:
-            compact_gather_kernel<uint32_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), starts,
-                                                                      dense_offsets, n, static_cast<uint32_t *>(out));
-            break;
-        case 8:
-            compact_gather_kernel<uint64_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), starts,
-                                                                      dense_offsets, n, static_cast<uint64_t *>(out));
-            break;
-        default:
-            set_error("jg_compact_gather: unsupported itemsize %d", itemsize);
-            return -2;
-    }
-    return check_launch("compact_gather_kernel");
+    JG_REQUIRE(starts && dense_offsets && out, "jg_compact_gather: bad arguments");
+    return launch_segment_move<false>(content, itemsize, dense_offsets, starts, n, out, as_stream(stream),
+                                      "jg_compact_gather");
 }
 
 int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets, const int64_t *dst_starts, int64_t n,
                        void *out, void *stream) {
     if (n <= 0) return 0;
     JG_REQUIRE(offsets && dst_starts && out, "jg_segment_scatter: bad arguments");
-    cudaStream_t s = as_stream(stream);
-    const unsigned g = tile_grid(n);
-    switch (itemsize) {
-        case 1:
-            segment_scatter_kernel<uint8_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), offsets,
-                                                                      dst_starts, n, static_cast<uint8_t *>(out));
-            break;
-        case 2:
-            segment_scatter_kernel<uint16_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), offsets,
-                                                                       dst_starts, n, static_cast<uint16_t *>(out));
-            break;
-        case 4:
-            segment_scatter_kernel<uint32_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), offsets,
-                                                                       dst_starts, n, static_cast<uint32_t *>(out));
-            break;
-        case 8:
-            segment_scatter_kernel<uint64_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), offsets,
-                                                                       dst_starts, n, static_cast<uint64_t *>(out));
-            break;
-        default:
-            set_error("jg_segment_scatter: unsupported itemsize %d", itemsize);
-            return -2;
-    }
-    return check_launch("segment_scatter_kernel");
+    return launch_segment_move<true>(content, itemsize, offsets, dst_starts, n, out, as_stream(stream),
+                                     "jg_segment_scatter");
 }
 
 int jg_offsets_rebase(const int64_t *offsets, int64_t count, int64_t delta, int64_t *out, void *stream) {

@@ -6,18 +6,19 @@
 // (descending unless `ascending`), -0.0 == 0.0 and other ties in position order, NaN last in both directions.
 // The comparator below is that total order on (value, position), so any sorting network gives the same answer.
 //
-//   argsort_kernel       : event tile (512 events per CTA, content run staged by TMA, owner table on chip);
-//                          ELEMENT-parallel rank sort -- each element counts the elements of its own event that
-//                          sort before it and writes its local index to that slot.  Events are a handful of
-//                          elements long, so the O(c^2) comparisons are cheaper than any network and the kernel
-//                          is one pass: v*M + 8(N+1) read, 8*M written.
+//   argsort_kernel       : event tile (512 events per CTA, content run staged by TMA and turned into
+//                          order-preserving unsigned keys in place).  Events of up to 8 elements -- nearly all
+//                          of them -- are ranked by their own thread in registers: 28 compares, fully unrolled,
+//                          no loop and no divergence; each element's local index goes to the slot of its rank.
+//                          Medium events (9 .. 2048) are listed and ranked by half a warp each.  One pass:
+//                          v*M + 8(N+1) read, 8*M written.
 //   events > kSortLong   : registered in a list and sorted one by one by a bitonic network over an index array
 //                          (shared-memory phases for strides < 4096, one launch per larger stride).
 #include "jg_tile.cuh"
 
 namespace jg {
 
-constexpr int kSortStage = 4096;     // positions of a tile that are staged on chip
+template <typename T> struct SortStage { static constexpr int value = sizeof(T) >= 8 ? 3072 : 4096; };   // positions a tile stages on chip
 constexpr int kSortLong = 2048;      // longer events go through the bitonic network
 constexpr int kBitonicChunk = 4096;  // indices per CTA in the shared-memory phases
 constexpr int kBitonicThreads = 256;
@@ -37,18 +38,70 @@ __device__ __forceinline__ bool sorts_before(T a, int64_t ia, T b, int64_t ib) {
     return ASC ? a < b : a > b;
 }
 
+// Order-preserving key: an unsigned integer of the same width whose ascending order is the output order of the
+// event (NaN -> all ones = last in both directions, -0.0 folded onto +0.0 so that it ties with it, descending =
+// bitwise complement).  With keys the comparator of the rank sort is one unsigned compare.
+template <int BYTES> struct KeyOf;
+template <> struct KeyOf<1> { using type = uint8_t; };
+template <> struct KeyOf<2> { using type = uint16_t; };
+template <> struct KeyOf<4> { using type = uint32_t; };
+template <> struct KeyOf<8> { using type = uint64_t; };
+
+template <typename T, bool ASC>
+__device__ __forceinline__ typename KeyOf<sizeof(T)>::type to_key(T x) {
+    using U = typename KeyOf<sizeof(T)>::type;
+    constexpr U kSign = static_cast<U>(U(1) << (8 * sizeof(T) - 1));
+    U u;
+    if constexpr (SortIsFloat<T>::value) {
+        if (x != x) return static_cast<U>(~U(0));
+        x += T(0);                                        // -0.0 + 0.0 = +0.0
+        if constexpr (sizeof(T) == 4) u = __float_as_uint(x);
+        else u = static_cast<U>(__double_as_longlong(x));
+        u = (u & kSign) ? static_cast<U>(~u) : static_cast<U>(u | kSign);
+    } else if constexpr (static_cast<T>(-1) < static_cast<T>(0)) {
+        u = static_cast<U>(static_cast<U>(x) ^ kSign);    // signed integers: flip the sign bit
+    } else {
+        u = static_cast<U>(x);
+    }
+    return ASC ? u : static_cast<U>(~u);
+}
+
+constexpr int kSortRegs = 8;         // events up to this length are ranked entirely in registers
+
+// Ranks of 8 keys held in registers, packed one hex digit per key.  rank_i = #(j < i: k_j <= k_i) + #(j > i:
+// k_j < k_i); with T_i = #(j > i: k_i <= k_j) the second term is (7 - i) - T_i, so ONE test per pair i < j feeds
+// both keys: digit j += 1, digit i -= 1.  The digits start at 7 - i; intermediate borrows between digits cancel
+// because the final value of every digit is a rank in [0, 7].  Two instructions per pair (compare, predicated add).
+static_assert(kSortRegs == 8, "rank_packed is written for 8 keys");
+template <typename U>
+__device__ __forceinline__ uint32_t rank_packed(const U (&k)[kSortRegs]) {
+    uint32_t ranks = 0x01234567u;
+#pragma unroll
+    for (int i = 0; i < kSortRegs; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < kSortRegs; ++j)
+            if (k[i] <= k[j]) ranks += (1u << (4 * j)) - (1u << (4 * i));
+    }
+    return ranks;
+}
+
 template <typename T, bool ASC>
 __global__ void __launch_bounds__(kTileThreads)
 argsort_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                int64_t *__restrict__ out, int32_t *__restrict__ status, int64_t *__restrict__ long_list,
                int64_t long_cap) {
+    using U = typename KeyOf<sizeof(T)>::type;
+    constexpr int kSortStage = SortStage<T>::value;
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) unsigned char s_stage[kSortStage * sizeof(T) + 32];
-    __shared__ __align__(16) uint16_t s_own[kSortStage + 128];
+    __shared__ uint16_t s_med[kTileEvents];      // medium events (9 .. kSortLong elements) of the tile
+    __shared__ uint16_t s_res[kSortStage];       // the tile's result (local indices < 2048), written out coalesced
     __shared__ uint64_t s_bar;
+    __shared__ int s_cnt;
 
     EventTile tile;
     if (threadIdx.x == 0) {
+        s_cnt = 0;
         mbar_init(&s_bar, 1);
         mbar_fence_init();
         int64_t ev0;
@@ -64,47 +117,94 @@ argsort_kernel(const T *__restrict__ content, const int64_t *__restrict__ offset
     const int64_t base0 = __ldg(offsets);
     const int64_t len = e1 - e0;
     if (len == 0) return;
+    bool has_long = false;
 
     if (len <= kSortStage) {
         const int L = static_cast<int>(len);
         const uint32_t shift = stage_edges<sizeof(T)>(s_stage, reinterpret_cast<const unsigned char *>(content + e0),
                                                       static_cast<uint32_t>(L * sizeof(T)));
-        build_owner_table(s_own, tile, L);
         stage_wait(&s_bar, 0);
-        const T *sm = reinterpret_cast<const T *>(s_stage + shift);
-        int64_t *dst = out + (e0 - base0);
+        U *sk = reinterpret_cast<U *>(s_stage + shift);
+        // values -> keys, in place
 #pragma unroll 1
-        for (int p = threadIdx.x; p < L; p += kTileThreads) {
-            const int ev = s_own[p];
-            const int a = static_cast<int>(s_off[ev] - e0), b = static_cast<int>(s_off[ev + 1] - e0);
-            if (b - a > kSortLong) continue;
-            const T key = sm[p];
-            int rank = 0;
+        for (int q = threadIdx.x; q < L; q += kTileThreads) sk[q] = to_key<T, ASC>(reinterpret_cast<const T *>(sk)[q]);
+        __syncthreads();
+        // phase 1, event-parallel: short events are ranked in registers (no loop, no divergence); the elements of
+        // medium events are put on a list
 #pragma unroll 1
-            for (int j = a; j < b; ++j) rank += sorts_before<T, ASC>(sm[j], j, key, p) ? 1 : 0;
-            dst[a + rank] = p - a;
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+            const int a = static_cast<int>(s_off[ev] - e0);
+            const int64_t c64 = s_off[ev + 1] - s_off[ev];
+            if (c64 <= kSortRegs) {
+                const int c = static_cast<int>(c64);
+                U k[kSortRegs];
+#pragma unroll
+                for (int i = 0; i < kSortRegs; ++i) k[i] = (i < c) ? sk[a + i] : static_cast<U>(~U(0));
+                const uint32_t ranks = rank_packed(k);
+#pragma unroll
+                for (int i = 0; i < kSortRegs; ++i)
+                    if (i < c) s_res[a + ((ranks >> (4 * i)) & 0xFu)] = static_cast<uint16_t>(i);
+            } else if (c64 <= kSortLong) {
+                s_med[atomicAdd(&s_cnt, 1)] = static_cast<uint16_t>(ev);
+            } else {
+                has_long = true;
+            }
         }
+        __syncthreads();
+        // phase 2, half a warp per medium event: every lane ranks one element against the whole event (the keys
+        // are broadcast reads; events of 9 .. 16 elements, the usual case, take one pass of the 16 lanes)
+        const int nmed = s_cnt;
+        constexpr int kGroup = 16;
+        const int gl = threadIdx.x & (kGroup - 1), group = threadIdx.x / kGroup;
+#pragma unroll 1
+        for (int m = group; m < nmed; m += kTileThreads / kGroup) {
+            const int ev = s_med[m];
+            const U *first = sk + (s_off[ev] - e0), *last = sk + (s_off[ev + 1] - e0);
+#pragma unroll 1
+            for (const U *mine = first + gl; mine < last; mine += kGroup) {
+                const U key = *mine;
+                int rank = 0;
+#pragma unroll 1
+                for (const U *q = first; q < last; ++q) {
+                    const U kj = *q;
+                    rank += ((kj < key) | ((kj == key) & (q < mine))) ? 1 : 0;
+                }
+                s_res[(first - sk) + rank] = static_cast<uint16_t>(mine - first);
+            }
+        }
+        __syncthreads();
+        // coalesced write-out (positions of long events hold garbage here; jg_argsort_long overwrites them)
+        int64_t *dst = out + (e0 - base0);
+#pragma unroll 2
+        for (int q = threadIdx.x; q < L; q += kTileThreads) __stcs(dst + q, static_cast<int64_t>(s_res[q]));
     } else {
-        // the tile's run does not fit on chip (long events around): same rank sort straight from L1/L2
+        // the tile's run does not fit on chip (long events around): rank sort straight from L1/L2
 #pragma unroll 1
         for (int64_t p = e0 + threadIdx.x; p < e1; p += kTileThreads) {
             const int ev = tile.find_event(p);
             const int64_t a = s_off[ev], b = s_off[ev + 1];
             if (b - a > kSortLong) continue;
-            const T key = __ldg(content + p);
+            const U key = to_key<T, ASC>(__ldg(content + p));
             int rank = 0;
 #pragma unroll 1
-            for (int64_t j = a; j < b; ++j) rank += sorts_before<T, ASC>(__ldg(content + j), j, key, p) ? 1 : 0;
+            for (int64_t j = a; j < b; ++j) {
+                const U kj = to_key<T, ASC>(__ldg(content + j));
+                rank += ((kj < key) | ((kj == key) & (j < p))) ? 1 : 0;
+            }
             out[a - base0 + rank] = p - a;
         }
+#pragma unroll 1
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) has_long |= (s_off[ev + 1] - s_off[ev] > kSortLong);
     }
     // long events are left to the bitonic path: put them on the list
+    if (has_long) {
 #pragma unroll 1
-    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
-        if (s_off[ev + 1] - s_off[ev] > kSortLong) {
-            const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long *>(long_list), 1ull);
-            if (static_cast<int64_t>(slot) < long_cap) long_list[1 + slot] = tile.event0 + ev;
-            atomicOr(status, JG_ST_SORT_LONG);
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+            if (s_off[ev + 1] - s_off[ev] > kSortLong) {
+                const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long *>(long_list), 1ull);
+                if (static_cast<int64_t>(slot) < long_cap) long_list[1 + slot] = tile.event0 + ev;
+                atomicOr(status, JG_ST_SORT_LONG);
+            }
         }
     }
 }

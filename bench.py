@@ -411,6 +411,18 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         ctypes.c_double(0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(bout), _lib.JG_F32, M, off.data_ptr(), N, st()))
     del bout
 
+    # per-event argsort (one pass: content + offsets in, one int64 local index per element out)
+    sidx = empty(M, np.int64)
+    add("argsort_f32", v * M + 8 * N + 8 * M, M, lambda: _lib.call(
+        "jg_argsort", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(sidx), _vp(scal, 1), _vp(scal, 2), 1, st()))
+    del sidx
+    # concatenate(axis=1) slot copy of one input (dense content -> its slot in the merged events)
+    cat = empty(2 * M, np.float32)
+    dst = ak.DeviceArray(off.tensor[:-1] * 2)
+    add("segment_scatter_f32", v * M + 16 * N + v * M, M, lambda: _lib.call(
+        "jg_segment_scatter", pt_dev.data_ptr(), 4, off.data_ptr(), dst.data_ptr(), N, _vp(cat), st()))
+    del cat, dst
+
     # float64 content (BASELINE configs[1] names float32/float64): same offsets, values cast up
     pt64 = ak.DeviceArray(pt_dev.tensor.double())
     out64 = empty(N, np.float64)
@@ -493,6 +505,9 @@ def workflow_table(ak, counts_dev, pt_dev, N, M, args):
     timed("C2_mask_flatten_counts_f64", lambda: c2(a64), M, "elements")
     del a64
     timed("C3_leading_object_argmax_getitem_f32", lambda: a[a.argmax()], M, "elements")
+    timed("sort_by_value_argsort_getitem_f32", lambda: a[a.argsort()], M, "elements")
+    timed("concatenate_axis0_f32", lambda: a.concatenate([a]), 2 * M, "elements", reps=2)
+    timed("concatenate_axis1_f32", lambda: a.concatenate([a], axis=1), 2 * M, "elements", reps=2)
 
     # C4: dimuon combinatorics with the per-pair invariant mass written in ufuncs (records: pt, eta, phi)
     Nc = args.comb_events
