@@ -6,9 +6,10 @@ ctypes C ABI, device-resident buffers, no CPU fallback.
     lead = a[a.argmax()]; sel = a[a > 20]; s = a.sum(); p = a.pairs()
 """
 from ._lib import LIB_PATH, JaggedLibError  # noqa: F401  (fails loudly when the .so is missing)
-from .device import DeviceArray, asdevice  # noqa: F401
+from .device import DeviceArray, DeviceMatrix, asdevice  # noqa: F401
+from .masked import MaskedArray  # noqa: F401
 from .table import Table  # noqa: F401
 from .jagged import JaggedArray  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["JaggedArray", "Table", "DeviceArray", "asdevice"]
+__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice"]

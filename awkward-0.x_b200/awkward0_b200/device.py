@@ -293,6 +293,43 @@ class DeviceArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return self._reduce(_lib.ALL)
 
 
+class DeviceMatrix(object):
+    """A rectangular (events x count) view of a DeviceArray: what JaggedArray.regular() returns (jagged.py:1053-1068
+    returns a 2-D numpy array).  Zero-copy; `.get()` / numpy.asarray() copy to the host as a 2-D array."""
+
+    __slots__ = ("_flat", "_shape")
+
+    def __init__(self, flat, shape):
+        if int(shape[0]) * int(shape[1]) != len(flat):
+            raise ValueError("cannot reshape array of size {0} into shape {1}".format(len(flat), tuple(shape)))
+        self._flat, self._shape = flat, (int(shape[0]), int(shape[1]))
+
+    shape = property(lambda self: self._shape)
+    ndim = property(lambda self: 2)
+    dtype = property(lambda self: self._flat.dtype)
+    flat = property(lambda self: self._flat)
+
+    @property
+    def tensor(self):
+        return self._flat.tensor.view(self._shape)
+
+    def __len__(self):
+        return self._shape[0]
+
+    def get(self):
+        return self._flat.get().reshape(self._shape)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.get()
+        return out if dtype is None else out.astype(dtype, copy=False)
+
+    def tolist(self):
+        return self.get().tolist()
+
+    def __repr__(self):
+        return "<DeviceMatrix {0} {1} at cuda>".format(self._shape, self.dtype)
+
+
 def asdevice(x, dtype=None):
     """Anything array-like -> DeviceArray (host data is copied host->device once)."""
     if isinstance(x, DeviceArray):

@@ -25,6 +25,8 @@ import numpy.lib.mixins
 from . import _lib, _ufunc
 from ._lib import call
 from .device import (BOOLTYPE, INDEXTYPE, DeviceArray, asdevice, empty, jg_code, runtime, torch, torch_dtype)
+from .masked import MaskedArray, fill_masked
+from .device import DeviceMatrix
 from .table import Table
 
 
@@ -200,7 +202,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     @classmethod
     def _tocontent(cls, content):
-        if isinstance(content, (DeviceArray, Table, JaggedArray)):
+        if isinstance(content, (DeviceArray, Table, JaggedArray, MaskedArray)):
             return content
         if isinstance(content, torch.Tensor):
             return asdevice(content)
@@ -428,10 +430,14 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return content.map(fcn)
         if isinstance(content, JaggedArray):
             raise NotImplementedError("jagged-of-jagged content is outside the GPU hot path (no CPU fallback)")
+        if isinstance(content, MaskedArray):
+            raise NotImplementedError("masked content (the result of pad) only supports fillna / regular / tolist on the device; call fillna() first")
         return fcn(content)
 
-    def _dense(self):
+    def _dense(self, masked_ok=False):
         """(compact array, off64, nevents, first, last): the form every kernel consumes."""
+        if not masked_ok and _has_masked(self._content):
+            raise NotImplementedError("masked content (the result of pad) only supports fillna / regular / tolist / counts on the device; call fillna() first")
         a = self.compact()
         a._valid()
         return a, a._off64, len(a._off64) - 1, a._first, a._last
@@ -1336,8 +1342,98 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def __setitem__(self, where, what):
         self._notimpl("__setitem__")
 
+    # ------------------------------------------------------------------------------------------------------
+    # pad / fillna / regular (jagged.py:1851-1900, 1053-1068)
+    # ------------------------------------------------------------------------------------------------------
+    def pad(self, length, maskedwhen=True, clip=False, axis=0):
+        """jagged.py:1851-1900 -> one jg_pad per leaf column (no parents / localindex / index temporaries)."""
+        if not isinstance(axis, (numbers.Integral, numpy.integer)) or axis < 0:
+            raise TypeError("axis must be a non-negative integer (can't count from the end)")
+        if isinstance(maskedwhen, numpy.ma.core.MaskedConstant):
+            raise NotImplementedError("numpy.ma.masked padding is outside the GPU hot path; use maskedwhen=True/False")
+        length = int(length)
+        if length < 0:
+            raise ValueError("pad length must be non-negative")
+        if axis > 0:
+            if not isinstance(self._content, JaggedArray):
+                raise NotImplementedError("pad(axis > 0) needs jagged content")
+            a, roff, inner, n_inner = self._nested_parts()
+            return self._make(roff, inner.pad(length, maskedwhen, clip, axis - 1), n_inner)
+        self._valid()
+        n = len(self)
+        counts = self.counts if self.counts.dtype == INDEXTYPE else self.counts.astype(INDEXTYPE)
+        if self._off64 is not None:
+            starts = self._off64[:-1]
+        else:
+            starts = self._general[0]
+        if clip:
+            # every event gets exactly `length` slots and keeps at most `length` items
+            arange = empty(n + 1, INDEXTYPE)
+            seed = asdevice(numpy.array([0, n + 1], dtype=INDEXTYPE))
+            call("jg_localindex", seed.data_ptr(), 1, _vp(arange), runtime.stream())
+            dst = _ufunc.binary(numpy.multiply, DeviceArray(arange, INDEXTYPE), numpy.int64(length))
+            kept = _ufunc.binary(numpy.minimum, counts, numpy.int64(length))
+            total = n * length
+        else:
+            dst, total, _ = self._scan_counts(_ufunc.binary(numpy.maximum, counts, numpy.int64(length)))
+            kept = counts
+        invalid = empty(total, BOOLTYPE)
+        first = [True]
+
+        def padded(col):
+            out = empty(total, col.dtype)
+            if n > 0 and total > 0:
+                call("jg_pad", col.data_ptr(), col.itemsize, starts.data_ptr(), kept.data_ptr(), dst.data_ptr(), n,
+                     _vp(out), _vp(invalid) if first[0] else ctypes.c_void_p(0), runtime.stream())
+                first[0] = False
+            return DeviceArray(out, col.dtype)
+
+        content = self._map_content(padded)
+        mask = DeviceArray(invalid, BOOLTYPE)
+        if not maskedwhen:
+            mask = numpy.logical_not(mask)
+
+        from_empty = len(self._content) == 0          # jagged.py:1860
+
+        def wrap(col):
+            out = MaskedArray(mask, col, maskedwhen=bool(maskedwhen))
+            out._appended = from_empty
+            return out
+
+        content = content.map(wrap) if isinstance(content, Table) else wrap(content)
+        return self._make(dst, content, total)
+
+    def fillna(self, value):
+        """jagged.py:1049-1051 (base.py:645-654): NaN and masked slots of the content become `value`."""
+        def fill(col):
+            if isinstance(col, MaskedArray):
+                return col.fillna(value)
+            if isinstance(col, Table):
+                return col.map(fill)
+            if isinstance(col, JaggedArray):
+                return col.fillna(value)
+            return fill_masked(col, None, True, value)
+
+        out = self.copy()
+        out._content = fill(self._content)
+        out._arg_source = out._arg_values = None
+        return out
+
     def regular(self):
-        self._notimpl("regular")
+        """jagged.py:1053-1068: all events must have the same count; the result is an (events x count) matrix."""
+        a, off, n, first, last = self._dense(masked_ok=True)
+        if n == 0:
+            raise NotImplementedError("regular() of an empty JaggedArray is outside the GPU hot path")
+        counts = a.counts
+        lo, hi = counts.min(), counts.max()
+        if int(lo) != int(hi):
+            raise ValueError("jagged array is not regular: different elements have different counts")
+        content = a._dense_content()
+        if isinstance(content, MaskedArray):
+            return content.get().reshape(n, int(lo))          # host masked matrix, like the reference's
+        if not isinstance(content, DeviceArray):
+            raise NotImplementedError("regular() of Table / nested content is outside the GPU hot path")
+        return DeviceMatrix(content, (n, int(lo)))
 
     def argsort(self, ascending=False):
         """jagged.py:1603-1631 -> jg_argsort (one pass; events beyond 2048 elements through jg_argsort_long)."""
@@ -1375,9 +1471,6 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         res = self._make(a._rebased_offsets(), DeviceArray(out, INDEXTYPE), total)
         res._counts = a._counts
         return res
-
-    def pad(self, length, maskedwhen=True, clip=False, axis=0):
-        self._notimpl("pad")
 
     # ------------------------------------------------------------------------------------------------------
     # concatenate (base.py:567-605 -> jagged.py:1633-1733)
@@ -1492,6 +1585,14 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
         content = merge([p[0]._dense_content() for p in parts])
         return cls._make(out_offsets, content, total)
+
+
+def _has_masked(content):
+    if isinstance(content, MaskedArray):
+        return True
+    if isinstance(content, Table):
+        return any(_has_masked(content[name]) for name in content.columns)
+    return False
 
 
 def _rebuild(template, leaves):

@@ -590,11 +590,55 @@ static int dispatch_flat_reduce(int op, const void *in, int dt, int64_t len, voi
     return -2;
 }
 
+// fillna (masked.py:401-406 via base.py:645-654): masked slots AND NaN take the fill value
+template <typename T>
+__global__ void __launch_bounds__(256)
+fill_masked_kernel(const T *__restrict__ x, const uint8_t *__restrict__ mask, int masked_when, T value,
+                   T *__restrict__ out, int64_t len) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < len; i += stride) {
+        const T v = x[i];
+        bool fill = mask != nullptr && ((mask[i] != 0) == (masked_when != 0));
+        if constexpr (sizeof(T) >= 4 && (T(0.5) != T(0))) fill |= (v != v);
+        out[i] = fill ? value : v;
+    }
+}
+
+template <typename T>
+static int launch_fill_masked(const void *x, const uint8_t *mask, int masked_when, T value, void *out, int64_t len,
+                              cudaStream_t s) {
+    fill_masked_kernel<T><<<ew_grid(len), 256, 0, s>>>(static_cast<const T *>(x), mask, masked_when, value,
+                                                       static_cast<T *>(out), len);
+    return check_launch("fill_masked_kernel");
+}
+
 }  // namespace jg
 
 using namespace jg;
 
 extern "C" {
+
+int jg_fill_masked(const void *content, int dtype, const uint8_t *mask, int masked_when, double value_f64,
+                   int64_t value_i64, void *out, int64_t len, void *stream) {
+    if (len <= 0) return 0;
+    JG_REQUIRE(content && out, "jg_fill_masked: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    switch (dtype) {
+        case JG_F32: return launch_fill_masked<float>(content, mask, masked_when, static_cast<float>(value_f64), out, len, s);
+        case JG_F64: return launch_fill_masked<double>(content, mask, masked_when, value_f64, out, len, s);
+        case JG_I32: return launch_fill_masked<int32_t>(content, mask, masked_when, static_cast<int32_t>(value_i64), out, len, s);
+        case JG_I64: return launch_fill_masked<int64_t>(content, mask, masked_when, value_i64, out, len, s);
+        case JG_U8: return launch_fill_masked<uint8_t>(content, mask, masked_when, static_cast<uint8_t>(value_i64), out, len, s);
+        case JG_B8: return launch_fill_masked<uint8_t>(content, mask, masked_when, value_i64 != 0 ? 1 : 0, out, len, s);
+        case JG_I8: return launch_fill_masked<int8_t>(content, mask, masked_when, static_cast<int8_t>(value_i64), out, len, s);
+        case JG_I16: return launch_fill_masked<int16_t>(content, mask, masked_when, static_cast<int16_t>(value_i64), out, len, s);
+        case JG_U16: return launch_fill_masked<uint16_t>(content, mask, masked_when, static_cast<uint16_t>(value_i64), out, len, s);
+        case JG_U32: return launch_fill_masked<uint32_t>(content, mask, masked_when, static_cast<uint32_t>(value_i64), out, len, s);
+        case JG_U64: return launch_fill_masked<uint64_t>(content, mask, masked_when, static_cast<uint64_t>(value_i64), out, len, s);
+    }
+    set_error("jg_fill_masked: unsupported dtype %d", dtype);
+    return -2;
+}
 
 int jg_binary(int op, const void *lhs, int lhs_dtype, const void *rhs, int rhs_dtype, int rhs_kind, double scalar_f64,
               int64_t scalar_i64, int swap, int compute_dtype, void *out, int out_dtype, int64_t len,

@@ -241,6 +241,54 @@ segment_move_kernel(const V *__restrict__ content, const int64_t *__restrict__ o
     }
 }
 
+// pad(): out[dst[i] + k] = content[starts[i] + k] for k < counts[i], else 0 with invalid[...] = 1  (jagged.py:1851-1900:
+// the reference builds an index from parents / localindex of the padded layout, gathers, and wraps the result in a
+// MaskedArray whose mask is localindex >= counts).  Element-parallel over the padded (dense) layout.
+template <typename V>
+__global__ void __launch_bounds__(kTileThreads)
+pad_kernel(const V *__restrict__ content, const int64_t *__restrict__ starts, const int64_t *__restrict__ counts,
+           const int64_t *__restrict__ dst_offsets, int64_t n, V *__restrict__ out, uint8_t *__restrict__ invalid) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ int64_t s_shift[kTileEvents];
+    __shared__ int64_t s_end[kTileEvents];       // first padded position of the event in the dense layout
+    __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
+    EventTile tile;
+    tile.load(s_off, dst_offsets, n, blockIdx.x);
+#pragma unroll 1
+    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+        s_shift[ev] = __ldg(starts + tile.event0 + ev) - s_off[ev];
+        s_end[ev] = s_off[ev] + __ldg(counts + tile.event0 + ev);
+    }
+    const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+    const bool table = (e1 - e0) <= kOwnPositions;
+    if (table) build_owner_table(s_own, tile, static_cast<int>(e1 - e0));
+    else __syncthreads();
+#pragma unroll 1
+    for (int64_t jb = e0 + threadIdx.x; jb < e1; jb += 4 * kTileThreads) {
+        int64_t src[4];
+        V val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t j = jb + u * kTileThreads;
+            src[u] = -1;
+            if (j < e1) {
+                const int ev = table ? static_cast<int>(s_own[j - e0]) : tile.find_event(j);
+                if (j < s_end[ev]) src[u] = j + s_shift[ev];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) val[u] = src[u] >= 0 ? __ldg(content + src[u]) : V(0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t j = jb + u * kTileThreads;
+            if (j < e1) {
+                out[j] = val[u];
+                if (invalid) invalid[j] = src[u] < 0;
+            }
+        }
+    }
+}
+
 template <bool SCATTER>
 static int launch_segment_move(const void *content, int itemsize, const int64_t *offsets, const int64_t *other,
                                int64_t n, void *out, cudaStream_t s, const char *what) {
@@ -377,6 +425,36 @@ int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets
     JG_REQUIRE(offsets && dst_starts && out, "jg_segment_scatter: bad arguments");
     return launch_segment_move<true>(content, itemsize, offsets, dst_starts, n, out, as_stream(stream),
                                      "jg_segment_scatter");
+}
+
+int jg_pad(const void *content, int itemsize, const int64_t *starts, const int64_t *counts, const int64_t *dst_offsets,
+           int64_t n, void *out, uint8_t *invalid, void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(starts && counts && dst_offsets && out, "jg_pad: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    const unsigned g = tile_grid(n);
+    switch (itemsize) {
+        case 1:
+            pad_kernel<uint8_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint8_t *>(content), starts, counts,
+                                                          dst_offsets, n, static_cast<uint8_t *>(out), invalid);
+            break;
+        case 2:
+            pad_kernel<uint16_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint16_t *>(content), starts, counts,
+                                                           dst_offsets, n, static_cast<uint16_t *>(out), invalid);
+            break;
+        case 4:
+            pad_kernel<uint32_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint32_t *>(content), starts, counts,
+                                                           dst_offsets, n, static_cast<uint32_t *>(out), invalid);
+            break;
+        case 8:
+            pad_kernel<uint64_t><<<g, kTileThreads, 0, s>>>(static_cast<const uint64_t *>(content), starts, counts,
+                                                           dst_offsets, n, static_cast<uint64_t *>(out), invalid);
+            break;
+        default:
+            set_error("jg_pad: unsupported itemsize %d", itemsize);
+            return -2;
+    }
+    return check_launch("pad_kernel");
 }
 
 int jg_offsets_rebase(const int64_t *offsets, int64_t count, int64_t delta, int64_t *out, void *stream) {

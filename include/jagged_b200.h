@@ -182,6 +182,17 @@ int64_t jg_argsort_long_workspace(int64_t count);
 int jg_argsort_long(const void *content, int dtype, int64_t start, int64_t count, int ascending, int64_t *out,
                     void *ws, size_t ws_bytes, void *stream);
 
+/* ---- pad / fillna ----------------------------------------------------------------------- */
+/* jagged.py:1851-1900  pad(): event i of the padded (dense) layout dst_offsets holds the first counts[i] items of
+ * content[starts[i] ...] followed by zeros; invalid[j] = 1 on the padding (optional).  The caller chooses
+ * dst_offsets: scan of max(counts, length) for clip=False, i*length with counts clipped to length for clip=True.   */
+int jg_pad(const void *content, int itemsize, const int64_t *starts, const int64_t *counts, const int64_t *dst_offsets,
+           int64_t n, void *out, uint8_t *invalid, void *stream);
+/* masked.py:401-406 + base.py:645-654  fillna(): out = value where (mask != 0) == masked_when or content is NaN,
+ * else content; mask may be NULL (NaN replacement only).  The value arrives as double and int64 like jg_binary's.  */
+int jg_fill_masked(const void *content, int dtype, const uint8_t *mask, int masked_when, double value_f64,
+                   int64_t value_i64, void *out, int64_t len, void *stream);
+
 /* ---- concatenation ---------------------------------------------------------------------- */
 /* jagged.py:1633-1649  concatenate(axis=0): out[i] = offsets[i] + delta for `count` entries (offsets of a later
  * array shifted by the number of content items in front of it)                                                      */

@@ -543,6 +543,42 @@ def argsort(offsets, content, ascending=False):
     return offsets - base, out
 
 
+def pad(starts, stops, content, length, clip=False):
+    """jagged.py:1851-1900 -- (offsets, gathered content, invalid mask) of ``a.pad(length, clip=clip)``.
+
+    The reference sizes every event to ``max(count, length)`` (or exactly ``length`` when clipping), builds
+    parents / localindex of that layout, gathers ``content[starts[parents] + localindex]`` and masks the slots
+    with ``localindex >= counts[parents]``.  What the gather reads under the mask is not part of the value; it is
+    returned as 0 here.
+    """
+    starts, stops = np.asarray(starts, dtype=INDEX), np.asarray(stops, dtype=INDEX)
+    content = np.asarray(content)
+    counts = stops - starts
+    sized = np.full(len(counts), length, dtype=INDEX) if clip else np.maximum(counts, length)
+    offsets = counts2offsets(sized)
+    parents = offsets2parents(offsets)
+    local = np.arange(len(parents), dtype=INDEX) - offsets[:-1][parents]
+    invalid = local >= counts[parents]
+    index = starts[parents] + local
+    data = np.zeros(len(parents), dtype=content.dtype)
+    data[~invalid] = content[index[~invalid]]
+    return offsets, data, invalid
+
+
+def pad_fillna(starts, stops, content, length, value, clip=False):
+    """``a.pad(length, clip=clip).fillna(value)`` (masked.py:401-406 with base.py:645-654): the padding AND any NaN
+    of the content take ``value``, cast to the content dtype."""
+    offsets, data, invalid = pad(starts, stops, content, length, clip)
+    if len(np.asarray(content)) == 0:
+        # jagged.py:1860-1864 wraps EMPTY content in an IndexedMaskedArray of -1s, whose fillna goes through
+        # numpy.append(content, value) (masked.py:910-920): the dtype is promoted with the value's
+        data = data.astype(np.result_type(data.dtype, np.asarray(value).dtype))
+    if data.dtype.kind == "f":
+        data[np.isnan(data)] = value
+    data[invalid] = value
+    return offsets, data
+
+
 def tolist(offsets, content):
     """base.py:159-172 -- nested python lists of a dense jagged array."""
     offsets = np.asarray(offsets)

@@ -99,6 +99,15 @@ def run_case(awkward0, name, offsets, content, flat, idx_counts, idx_content, b_
     c, f = logical(a.concatenate([b, a], axis=1))
     out["out_cat1_counts"], out["out_cat1_flat"] = c, f
 
+    # pad / fillna; the skewed fixture has a 9000-element event: keep it small there
+    fill = {"f": -7.5, "i": 3, "u": 3, "b": True}[content.dtype.kind]
+    out["in_fill"] = np.asarray(fill)
+    for label, clip in (("pad3", False), ("pad3clip", True)):
+        p = a.pad(3, clip=clip)
+        out["out_%s_counts" % label] = np.asarray(p.counts)
+        out["out_%s_invalid" % label] = np.asarray(p.content.boolmask(maskedwhen=True)) if len(content) else np.ones(3 * len(a), dtype=bool)
+        out["out_%s_fill" % label] = np.asarray(p.fillna(fill).flatten())
+
     if not combos:
         return save(name, out)
 

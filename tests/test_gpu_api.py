@@ -428,6 +428,43 @@ def test_argsort(ak):                        # test_jagged.py:604-607 (masked ev
             assert np.array_equal(got.offsets.get(), woff) and np.array_equal(got.content.get(), widx)
 
 
+def test_pad_fillna_regular(ak):             # test_jagged.py:189-212, 544-559
+    J = ak.JaggedArray
+    a = J.fromcounts([3, 0, 2], [1.1, 2.2, 3.3, 4.4, 5.5])
+    want = [[1.1, 2.2, 3.3, None], [None, None, None, None], [4.4, 5.5, None, None]]
+    assert a.pad(4, clip=True).tolist() == want
+    assert a.pad(4).tolist() == want
+    assert a.pad(4, clip=True).regular().tolist() == want
+    b = J.fromcounts([5, 0, 3, 1], [1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9])
+    assert b.pad(3).tolist() == [[1.1, 2.2, 3.3, 4.4, 5.5], [None, None, None], [6.6, 7.7, 8.8], [9.9, None, None]]
+    assert b.pad(3, clip=True).tolist() == [[1.1, 2.2, 3.3], [None, None, None], [6.6, 7.7, 8.8], [9.9, None, None]]
+    assert a.pad(4).fillna(999).tolist() == [[1.1, 2.2, 3.3, 999], [999, 999, 999, 999], [4.4, 5.5, 999, 999]]
+    assert a.pad(4).fillna(999).regular().tolist() == [[1.1, 2.2, 3.3, 999], [999, 999, 999, 999], [4.4, 5.5, 999, 999]]
+    assert a.pad(4, maskedwhen=False).content.maskedwhen is False
+    assert a.pad(4, maskedwhen=False).tolist() == want
+    r = J.fromcounts([3, 3, 3, 3], np.arange(12.0))
+    assert r.regular().tolist() == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0], [6.0, 7.0, 8.0], [9.0, 10.0, 11.0]]
+    assert r.regular().shape == (4, 3) and np.asarray(r.regular()).shape == (4, 3)
+    with pytest.raises(ValueError, match="jagged array is not regular"):
+        a.regular()
+    # general layouts, int content (the value is cast), NaN content (replaced too), empty content
+    g = b[[2, 0, 3]]
+    assert g.pad(4).fillna(1).tolist() == [[6.6, 7.7, 8.8, 1.0], [1.1, 2.2, 3.3, 4.4, 5.5], [9.9, 1.0, 1.0, 1.0]]
+    i = J.fromcounts([1, 2], np.array([5, 6, 7], dtype=np.int32))
+    assert i.pad(2).fillna(9.7).tolist() == [[5, 9], [6, 7]] and i.pad(2).fillna(9.7).content.dtype == np.dtype(np.int32)
+    n = J.fromcounts([2, 1], np.array([1.0, np.nan, 3.0]))
+    assert n.fillna(0).tolist() == [[1.0, 0.0], [3.0]]
+    assert n.pad(2).fillna(-1).tolist() == [[1.0, -1.0], [3.0, -1.0]]
+    e = J.fromcounts([0, 0], np.zeros(0, dtype=np.float32))
+    assert e.pad(2).tolist() == [[None, None], [None, None]] and e.pad(2).fillna(3).tolist() == [[3.0, 3.0], [3.0, 3.0]]
+    # records: every column padded with the same mask
+    mu = J.zip(pt=J.fromcounts([2, 0, 1], [1.0, 2.0, 3.0]), q=J.fromcounts([2, 0, 1], [1, -1, 1]))
+    p = mu.pad(2, clip=True).fillna(0)
+    assert p.pt.tolist() == [[1.0, 2.0], [0.0, 0.0], [3.0, 0.0]] and p.q.tolist() == [[1, -1], [0, 0], [1, 0]]
+    with pytest.raises(NotImplementedError, match="fillna"):
+        a.pad(4).sum()
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
@@ -477,7 +514,7 @@ def test_exceptions(ak):
     with pytest.raises(ValueError, match="offsets must be a non-negative array"):
         J.fromoffsets([-1, 3], CONTENT)
     with pytest.raises(NotImplementedError, match="no CPU fallback"):
-        a.pad(3)
+        a[0] = 1.0
     assert J.fromoffsets([0, 3, 2], CONTENT).valid() is False
     ok = a[J.fromcounts([2, 0, 1, 1], [-1, 0, 1, -5])]       # negative wrap (jagged.py:552-553)
     assert ok.tolist() == [[2.2, 0.0], [], [4.4], [5.5]]

@@ -126,6 +126,35 @@ def test_concatenate(golden):
     assert same(O.offsets2counts(off), g["out_cat1_counts"]) and same(content, g["out_cat1_flat"])
 
 
+@pytest.mark.parametrize("clip", [False, True])
+def test_pad_fillna(golden, clip):
+    g = golden
+    label = "pad3clip" if clip else "pad3"
+    off = g["in_offsets"]
+    fill = g["in_fill"][()]
+    poff, data, invalid = O.pad(off[:-1], off[1:], g["in_content"], 3, clip)
+    assert same(O.offsets2counts(poff), g["out_%s_counts" % label])
+    assert same(invalid, g["out_%s_invalid" % label])
+    with np.errstate(all="ignore"):
+        foff, filled = O.pad_fillna(off[:-1], off[1:], g["in_content"], 3, fill, clip)
+    assert same(filled, g["out_%s_fill" % label])
+
+
+def test_ref_pad_literals():                    # tests/test_jagged.py:544-559
+    def show(starts, stops, content, length, clip):
+        off, data, invalid = O.pad(starts, stops, content, length, clip)
+        return [[None if invalid[j] else data[j] for j in range(off[i], off[i + 1])] for i in range(len(off) - 1)]
+    c = np.array([1.1, 2.2, 3.3, 4.4, 5.5])
+    assert show([0, 3, 3], [3, 3, 5], c, 4, True) == [[1.1, 2.2, 3.3, None], [None] * 4, [4.4, 5.5, None, None]]
+    assert show([0, 3, 3], [3, 3, 5], c, 4, False) == [[1.1, 2.2, 3.3, None], [None] * 4, [4.4, 5.5, None, None]]
+    c = np.array([1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9])
+    s, e = [0, 5, 5, 8], [5, 5, 8, 9]
+    assert show(s, e, c, 3, False) == [[1.1, 2.2, 3.3, 4.4, 5.5], [None] * 3, [6.6, 7.7, 8.8], [9.9, None, None]]
+    assert show(s, e, c, 3, True) == [[1.1, 2.2, 3.3], [None] * 3, [6.6, 7.7, 8.8], [9.9, None, None]]
+    off, filled = O.pad_fillna([0, 3, 3], [3, 3, 5], np.array([1.1, 2.2, 3.3, 4.4, 5.5]), 4, 999)
+    assert O.tolist(off, filled) == [[1.1, 2.2, 3.3, 999], [999, 999, 999, 999], [4.4, 5.5, 999, 999]]
+
+
 def test_ref_concatenate_literals():           # tests/test_jagged.py:451-487
     lst = [[1, 2, 3], [], [4, 5], [6, 7], [8], [], [9], [10, 11], [12]]
 
