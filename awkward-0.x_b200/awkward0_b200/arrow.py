@@ -1,0 +1,101 @@
+"""Arrow <-> device JaggedArray (awkward0/arrow.py:231-430 fromarrow, :27-229 toarrow).
+
+Arrow delivers exactly the hot path's inputs -- a list array IS (offsets int32/int64, values) -- so ingest is one
+host->device copy per buffer and `JaggedArray.fromoffsets`; nothing is re-scanned.  Supported: list / large_list
+(nested to any depth) of numeric, boolean (bit-packed, unpacked by jg_unpack_bits) or struct-of-those values, and
+ChunkedArrays of them (chunks are appended with JaggedArray.concatenate).  Arrays with nulls map to the
+reference's BitMaskedArray, which is outside the GPU hot path: NotImplementedError, no CPU fallback.
+"""
+import ctypes
+
+import numpy
+
+from ._lib import call
+from .device import BOOLTYPE, DeviceArray, asdevice, empty, runtime
+from .jagged import JaggedArray
+from .table import Table
+
+
+def _no_nulls(array):
+    if array.null_count != 0:
+        raise NotImplementedError("Arrow arrays with nulls become BitMaskedArrays in awkward0 (arrow.py:274-276), which is outside the GPU hot path")
+
+
+def _values(array):
+    """A non-list Arrow array -> DeviceArray / Table of DeviceArrays."""
+    import pyarrow
+    _no_nulls(array)
+    tpe = array.type
+    if pyarrow.types.is_struct(tpe):
+        out = Table.named("Row")
+        for i in range(tpe.num_fields):
+            out[tpe.field(i).name] = _content(array.field(i))
+        return out
+    if pyarrow.types.is_boolean(tpe):
+        n = len(array)
+        bits = array.buffers()[1]
+        out = empty(n, BOOLTYPE)
+        if n > 0:
+            packed = asdevice(numpy.frombuffer(bits, dtype=numpy.uint8))
+            call("jg_unpack_bits", packed.data_ptr(), array.offset, n, ctypes.c_void_p(out.data_ptr()), runtime.stream())
+        return DeviceArray(out, BOOLTYPE)
+    if pyarrow.types.is_integer(tpe) or pyarrow.types.is_floating(tpe):
+        dtype = numpy.dtype(tpe.to_pandas_dtype())
+        if dtype == numpy.dtype(numpy.float16):
+            raise NotImplementedError("float16 content is not supported on the device")
+        buf = array.buffers()[1]
+        host = numpy.frombuffer(buf, dtype=dtype)[array.offset:array.offset + len(array)] if buf is not None else numpy.zeros(0, dtype)
+        return asdevice(host)
+    raise NotImplementedError("Arrow type {0} is outside the GPU hot path".format(tpe))
+
+
+def _content(array):
+    import pyarrow
+    tpe = array.type
+    if pyarrow.types.is_list(tpe) or pyarrow.types.is_large_list(tpe):
+        _no_nulls(array)
+        # .offsets honours the slice offset of the array; .values is the whole child (offsets index into it)
+        offsets = numpy.asarray(array.offsets)
+        return JaggedArray.fromoffsets(offsets, _content(array.values))
+    return _values(array)
+
+
+def fromarrow(obj):
+    """pyarrow ListArray / LargeListArray / ChunkedArray of them -> JaggedArray on the device."""
+    import pyarrow
+    if isinstance(obj, pyarrow.ChunkedArray):
+        chunks = [x for x in obj.chunks if len(x) > 0]
+        if len(chunks) == 0:
+            chunks = list(obj.chunks[:1])
+        parts = [fromarrow(x) for x in chunks]
+        return parts[0] if len(parts) == 1 else JaggedArray.concatenate(parts)
+    if isinstance(obj, pyarrow.Array):
+        out = _content(obj)
+        if not isinstance(out, JaggedArray):
+            raise NotImplementedError("fromarrow on the device expects a list-typed array (the JaggedArray hot path)")
+        return out
+    raise NotImplementedError("fromarrow of {0} is outside the GPU hot path".format(type(obj)))
+
+
+def toarrow(array):
+    """JaggedArray -> pyarrow.ListArray (int32 offsets when they fit, like arrow.py:128-136; large_list otherwise)."""
+    import pyarrow
+
+    def recurse(x):
+        if isinstance(x, JaggedArray):
+            x = x.compact()
+            offsets = x._rebased_offsets().get()
+            child = recurse(x._dense_content())
+            if len(offsets) and offsets[-1] <= numpy.iinfo(numpy.int32).max:
+                return pyarrow.ListArray.from_arrays(pyarrow.array(offsets.astype(numpy.int32)), child)
+            return pyarrow.LargeListArray.from_arrays(pyarrow.array(offsets), child)
+        if isinstance(x, Table):
+            names = list(x.columns)
+            return pyarrow.StructArray.from_arrays([recurse(x[n]) for n in names], names)
+        if isinstance(x, DeviceArray):
+            return pyarrow.array(x.get())
+        raise NotImplementedError("toarrow of {0} is outside the GPU hot path".format(type(x)))
+
+    if not isinstance(array, JaggedArray):
+        raise NotImplementedError("toarrow on the device expects a JaggedArray")
+    return recurse(array)

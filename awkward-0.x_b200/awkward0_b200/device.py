@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory (caching allocator), the current
 sharded.py -- the NCCL communicator.  All arithmetic goes through libjagged_sm100a.so (see _lib.py).
 """
 import ctypes
+import warnings
 
 import numpy
 import numpy.lib.mixins
@@ -349,8 +350,11 @@ def asdevice(x, dtype=None):
     np_dtype = arr.dtype
     tdt = torch_dtype(np_dtype)
     arr = numpy.ascontiguousarray(arr)
-    if np_dtype.kind == "u" and np_dtype.itemsize > 1:
-        host = torch.from_numpy(arr.view("i%d" % np_dtype.itemsize)).view(tdt)
-    else:
-        host = torch.from_numpy(arr)
+    with warnings.catch_warnings():
+        # read-only host buffers (Arrow, memory maps) are only ever the SOURCE of the host->device copy
+        warnings.simplefilter("ignore", UserWarning)
+        if np_dtype.kind == "u" and np_dtype.itemsize > 1:
+            host = torch.from_numpy(arr.view("i%d" % np_dtype.itemsize)).view(tdt)
+        else:
+            host = torch.from_numpy(arr)
     return DeviceArray(host.to(runtime.device()), np_dtype)

@@ -590,6 +590,24 @@ static int dispatch_flat_reduce(int op, const void *in, int dt, int64_t len, voi
     return -2;
 }
 
+// Arrow boolean buffers are bit-packed, least-significant bit first (arrow.py:380-395 unpacks them with
+// numpy.unpackbits + a byte-wise reversal): out[i] = bit (bit_offset + i) of `bits`.  8 outputs per thread.
+__global__ void __launch_bounds__(256)
+unpack_bits_kernel(const uint8_t *__restrict__ bits, int64_t bit_offset, int64_t n, uint8_t *__restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * 256 * 8;
+    for (int64_t i0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 8; i0 < n; i0 += stride) {
+        const int64_t b = bit_offset + i0;
+        // two source bytes cover 8 consecutive bits at any phase
+        const uint32_t lo = bits[b >> 3];
+        const int64_t last = min(b + 7, bit_offset + n - 1);          // last bit this thread needs
+        const uint32_t hi = ((last >> 3) != (b >> 3)) ? bits[last >> 3] : 0u;
+        const uint32_t w = (lo | (hi << 8)) >> (b & 7);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k < n) out[i0 + k] = (w >> k) & 1u;
+    }
+}
+
 // fillna (masked.py:401-406 via base.py:645-654): masked slots AND NaN take the fill value
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -617,6 +635,13 @@ static int launch_fill_masked(const void *x, const uint8_t *mask, int masked_whe
 using namespace jg;
 
 extern "C" {
+
+int jg_unpack_bits(const uint8_t *bits, int64_t bit_offset, int64_t n, uint8_t *out, void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(bits && out && bit_offset >= 0, "jg_unpack_bits: bad arguments");
+    unpack_bits_kernel<<<ew_grid((n + 7) / 8), 256, 0, as_stream(stream)>>>(bits, bit_offset, n, out);
+    return check_launch("unpack_bits_kernel");
+}
 
 int jg_fill_masked(const void *content, int dtype, const uint8_t *mask, int masked_when, double value_f64,
                    int64_t value_i64, void *out, int64_t len, void *stream) {

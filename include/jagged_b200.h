@@ -193,6 +193,12 @@ int jg_pad(const void *content, int itemsize, const int64_t *starts, const int64
 int jg_fill_masked(const void *content, int dtype, const uint8_t *mask, int masked_when, double value_f64,
                    int64_t value_i64, void *out, int64_t len, void *stream);
 
+/* ---- Arrow ingest ----------------------------------------------------------------------- */
+/* arrow.py:380-395  boolean values arrive bit-packed, LSB first: out[i] = bit (bit_offset + i) of `bits` as 0/1
+ * bytes; `bits` must hold ceil((bit_offset + n) / 8) bytes.  List offsets (int32 / int64) need no kernel of their
+ * own: JaggedArray.fromoffsets takes them as they are (jagged.py:142-153).                                          */
+int jg_unpack_bits(const uint8_t *bits, int64_t bit_offset, int64_t n, uint8_t *out, void *stream);
+
 /* ---- concatenation ---------------------------------------------------------------------- */
 /* jagged.py:1633-1649  concatenate(axis=0): out[i] = offsets[i] + delta for `count` entries (offsets of a later
  * array shifted by the number of content items in front of it)                                                      */

@@ -465,6 +465,47 @@ def test_pad_fillna_regular(ak):             # test_jagged.py:189-212, 544-559
         a.pad(4).sum()
 
 
+def test_arrow_ingest(ak):                   # arrow.py:231-430: list offsets + values straight to HBM
+    pa = pytest.importorskip("pyarrow")
+    rng = np.random.default_rng(9)
+    lists = [[1.1, 2.2], [], [3.3], [4.4, 5.5, 6.6]]
+    arr = pa.array(lists)
+    j = ak.fromarrow(arr)
+    assert j.tolist() == lists and j.offsets.dtype == np.dtype(np.int32) and j.content.dtype == np.dtype(np.float64)
+    assert (j.sum().get() == np.array([1.1 + 2.2, 0.0, 3.3, 4.4 + 5.5 + 6.6])).all()
+    assert ak.fromarrow(arr.slice(1, 3)).tolist() == lists[1:4]                       # sliced: offsets[0] != 0
+    big = pa.array([[1, 2], [3], []], type=pa.large_list(pa.int32()))
+    jb = ak.fromarrow(big)
+    assert jb.tolist() == [[1, 2], [3], []] and jb.offsets.dtype == np.dtype(np.int64) and jb.content.dtype == np.dtype(np.int32)
+    # bit-packed booleans at every bit phase
+    counts = rng.poisson(3.0, 200)
+    flags = [[bool(x) for x in rng.integers(0, 2, c)] for c in counts]
+    barr = pa.array(flags, type=pa.list_(pa.bool_()))
+    assert ak.fromarrow(barr).tolist() == flags
+    for lo in range(1, 12):
+        assert ak.fromarrow(barr.slice(lo, 50)).tolist() == flags[lo:lo + 50]
+        child = barr.values.slice(lo, 77)
+        sub = pa.ListArray.from_arrays(pa.array([0, 7, 7, 77], type=pa.int32()), child)
+        assert ak.fromarrow(sub).tolist() == sub.to_pylist()
+    # records, nested lists, chunks
+    recs = pa.array([[{"pt": 1.5, "q": 1}, {"pt": 2.5, "q": -1}], [], [{"pt": 3.5, "q": 1}]])
+    jr = ak.fromarrow(recs)
+    assert jr.pt.tolist() == [[1.5, 2.5], [], [3.5]] and jr.q.tolist() == [[1, -1], [], [1]]
+    nested = pa.array([[[1, 2], []], [], [[3]]])
+    assert ak.fromarrow(nested).tolist() == [[[1, 2], []], [], [[3]]]
+    chunked = pa.chunked_array([pa.array(lists[:2]), pa.array([], type=pa.list_(pa.float64())), pa.array(lists[2:])])
+    assert ak.fromarrow(chunked).tolist() == lists
+    with pytest.raises(NotImplementedError, match="BitMaskedArray"):
+        ak.fromarrow(pa.array([[1.0], None]))
+    with pytest.raises(NotImplementedError):
+        ak.fromarrow(pa.array([1.0, 2.0]))
+    # and back
+    back = ak.toarrow(j)
+    assert back.to_pylist() == lists and back.type == pa.list_(pa.float64())
+    assert ak.toarrow(jr).to_pylist() == recs.to_pylist()
+    assert ak.toarrow(j[j > 2]).to_pylist() == [[2.2], [], [3.3], [4.4, 5.5, 6.6]]
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
