@@ -61,6 +61,7 @@ PROTOTYPES = {
     "jg_compact_gather": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "jg_segment_scatter": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "jg_offsets_rebase": (_i, [_vp, _i64, _i64, _vp, _vp]),
+    "jg_put": (_i, [_vp, _i, _vp, _i64, _vp, ctypes.c_uint64, _i, _vp]),
     "jg_unpack_bits": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "jg_pad": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "jg_fill_masked": (_i, [_vp, _i, _vp, _i, ctypes.c_double, _i64, _vp, _i64, _vp]),

@@ -118,6 +118,38 @@ def take(content, index):
     return DeviceArray(out, content.dtype)
 
 
+def arange(n):
+    """numpy.arange(n, dtype=int64) on the device: the localindex of one event of n items."""
+    out = empty(n, numpy.int64)
+    if n > 0:
+        seed = asdevice(numpy.array([0, n], dtype=numpy.int64))
+        call("jg_localindex", seed.data_ptr(), 1, ctypes.c_void_p(out.data_ptr()), runtime.stream())
+    return DeviceArray(out, numpy.int64)
+
+
+def nonzero(mask):
+    """numpy.nonzero(mask)[0] for a flat boolean DeviceArray."""
+    return compress([arange(len(mask))], mask)[0]
+
+
+def put(target, index, values, skip_negative=False):
+    """target[index] = values (DeviceArray of the same length as index, or a scalar), in place (jg_put)."""
+    dt = target.dtype
+    if len(index) == 0:
+        return
+    if isinstance(values, DeviceArray):
+        if len(values) != len(index):
+            raise ValueError("shape mismatch: value array of shape ({0},) could not be broadcast to indexing result of shape ({1},)".format(len(values), len(index)))
+        values = values if values.dtype == dt else cast(values, dt)
+        vptr, bits = values.data_ptr(), 0
+    else:
+        vptr = ctypes.c_void_p(0)
+        bits = int(numpy.array([values]).astype(dt).view("u%d" % dt.itemsize)[0])
+    index = index if index.dtype == numpy.int64 else cast(index, numpy.int64)
+    call("jg_put", target.data_ptr(), dt.itemsize, index.data_ptr(), len(index), vptr, ctypes.c_uint64(bits),
+         1 if skip_negative else 0, runtime.stream())
+
+
 def compress(columns, mask):
     """[col[mask] for col in columns] for a flat boolean DeviceArray mask (one scan, one scatter per column)."""
     if mask.dtype != numpy.bool_:

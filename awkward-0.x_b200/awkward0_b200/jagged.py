@@ -335,6 +335,133 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out._pending_status = _lib.ST_BEYOND_CONTENT if total > len(content) else 0
         return out
 
+    # ------------------------------------------------------------------------------------------------------
+    # the other constructors (jagged.py:73-110, 168-242): compositions of compare / compaction / scatter kernels
+    # ------------------------------------------------------------------------------------------------------
+    @classmethod
+    def parents2startsstops(cls, parents, length=None):
+        """jagged.py:73-93: children contiguous, not necessarily in order or covering; negative parents are skipped."""
+        parents = cls._as_index64(asdevice(parents))
+        n = len(parents)
+        if n == 0:
+            zero = DeviceArray(empty(0, INDEXTYPE), INDEXTYPE)
+            return zero, zero
+        edge = _ufunc.binary(numpy.not_equal, parents[1:], parents[:-1])
+        inner = _ufunc.binary(numpy.add, _ufunc.nonzero(edge), numpy.int64(1))
+        changes = empty(len(inner) + 2, INDEXTYPE)
+        changes[0:1].zero_()
+        changes[1:len(inner) + 1].copy_(inner.tensor)
+        changes[len(inner) + 1:].fill_(n)
+        changes = DeviceArray(changes, INDEXTYPE)
+        nevents = int(parents.max()) + 1
+        starts = DeviceArray(empty(max(nevents, 0), INDEXTYPE).zero_(), INDEXTYPE)
+        counts = DeviceArray(empty(max(nevents, 0), INDEXTYPE).zero_(), INDEXTYPE)
+        where = _ufunc.take(parents, changes[:-1])
+        _ufunc.put(starts, where, changes[:-1], skip_negative=True)
+        _ufunc.put(counts, where, _ufunc.binary(numpy.subtract, changes[1:], changes[:-1]), skip_negative=True)
+        return starts, _ufunc.binary(numpy.add, starts, counts)
+
+    @classmethod
+    def uniques2offsetsparents(cls, uniques):
+        """jagged.py:95-110: children contiguous, in order and covering (no empty events); values only mark runs."""
+        uniques = asdevice(uniques)
+        n = len(uniques)
+        if n == 0:
+            offsets = asdevice(numpy.zeros(2, dtype=INDEXTYPE))
+            return offsets, DeviceArray(empty(0, INDEXTYPE), INDEXTYPE)
+        edge = _ufunc.binary(numpy.not_equal, uniques[1:], uniques[:-1])
+        inner = _ufunc.binary(numpy.add, _ufunc.nonzero(edge), numpy.int64(1))
+        offsets = empty(len(inner) + 2, INDEXTYPE)
+        offsets[0:1].zero_()
+        offsets[1:len(inner) + 1].copy_(inner.tensor)
+        offsets[len(inner) + 1:].fill_(n)
+        offsets = DeviceArray(offsets, INDEXTYPE)
+        return offsets, cls.offsets2parents(offsets)
+
+    @classmethod
+    def fromparents(cls, parents, content, length=None):
+        """jagged.py:168-179."""
+        parents = asdevice(parents if not isinstance(parents, (list, tuple)) else numpy.asarray(parents, dtype=INDEXTYPE))
+        if not _isintegertype(parents.dtype):
+            raise TypeError("parents must have integer dtype")
+        content = cls._tocontent(content)
+        if len(parents) != len(content):
+            raise ValueError("parents array must be one-dimensional with the same length as content")
+        starts, stops = cls.parents2startsstops(parents, length=length)
+        return cls(starts, stops, content)
+
+    @classmethod
+    def fromuniques(cls, uniques, content):
+        """jagged.py:181-192."""
+        uniques = asdevice(uniques if not isinstance(uniques, (list, tuple)) else numpy.asarray(uniques, dtype=INDEXTYPE))
+        if not _isintegertype(uniques.dtype):
+            raise TypeError("uniques must have integer dtype")
+        content = cls._tocontent(content)
+        if len(uniques) != len(content):
+            raise ValueError("uniques array must be one-dimensional with the same length as content")
+        offsets, parents = cls.uniques2offsetsparents(uniques)
+        out = cls.fromoffsets(offsets, content)
+        out._parents = parents
+        return out
+
+    @classmethod
+    def fromlocalindex(cls, index, content, validate=True):
+        """jagged.py:194-222."""
+        original_counts = None
+        if isinstance(index, JaggedArray):
+            if validate:
+                original_counts = index.counts
+            index = index.flatten()
+        index = asdevice(index if not isinstance(index, (list, tuple)) else numpy.asarray(index, dtype=INDEXTYPE))
+        if not _isintegertype(index.dtype):
+            raise TypeError("localindex must have integer dtype")
+        content = cls._tocontent(content)
+        if len(index) != len(content):
+            raise ValueError("localindex array must be one-dimensional with the same length as content")
+        if validate and len(index) > 1:
+            step_ok = _ufunc.binary(numpy.equal, _ufunc.binary(numpy.subtract, index[1:], index[:-1]), 1)
+            is_zero = _ufunc.binary(numpy.equal, index[1:], 0)
+            if not bool(_ufunc.binary(numpy.logical_or, step_ok, is_zero).all()):
+                raise ValueError("every localindex that is not zero must be one greater than the previous")
+        starts = _ufunc.nonzero(_ufunc.binary(numpy.equal, index, 0))
+        offsets = empty(len(starts) + 1, INDEXTYPE)
+        offsets[:len(starts)].copy_(starts.tensor)
+        offsets[len(starts):].fill_(len(index))
+        offsets = DeviceArray(offsets, INDEXTYPE)
+        if original_counts is not None:
+            derived = _ufunc.binary(numpy.subtract, offsets[1:], offsets[:-1])
+            same = len(derived) == len(original_counts) and bool(_ufunc.binary(numpy.equal, derived, original_counts.astype(INDEXTYPE)).all())
+            if not same:
+                raise ValueError("jagged structure of index does not match jagged structure derived from localindex")
+        return cls.fromoffsets(offsets, content)
+
+    @classmethod
+    def fromjagged(cls, jagged):
+        """jagged.py:224-226."""
+        return cls(jagged.starts, jagged.stops, jagged.content)
+
+    @classmethod
+    def fromfolding(cls, content, size):
+        """jagged.py:237-242: consecutive events of `size` items, the last one possibly shorter."""
+        content = cls._tocontent(content)
+        size = int(size)
+        quotient = -(-len(content) // size)
+        offsets = _ufunc.binary(numpy.multiply, _ufunc.arange(quotient + 1), numpy.int64(size))
+        if len(offsets) > 0:
+            offsets = _ufunc.binary(numpy.minimum, offsets, numpy.int64(len(content)))
+        return cls.fromoffsets(offsets, content)
+
+    @classmethod
+    def fromregular(cls, regular):
+        """jagged.py:228-235: a rectangular host array becomes nested events of equal length."""
+        regular = numpy.asarray(regular)
+        if regular.ndim <= 1:
+            raise ValueError("regular array must have more than one dimension")
+        out = asdevice(numpy.ascontiguousarray(regular).reshape(-1))
+        for x in regular.shape[:0:-1]:
+            out = cls.fromfolding(out, x)
+        return out
+
     def copy(self, starts=None, stops=None, content=None):
         out = self.__class__.__new__(self.__class__)
         out.__dict__.update(self.__dict__)
@@ -1340,7 +1467,36 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         raise NotImplementedError("JaggedArray.{0} is outside the GPU hot path (SURVEY.md section 8a/8f); no CPU fallback".format(name))
 
     def __setitem__(self, where, what):
-        self._notimpl("__setitem__")
+        """jagged.py:789-838: add a column (str) or assign through a jagged mask / jagged integer index, in place."""
+        if isinstance(where, str):
+            if not isinstance(self._content, Table):
+                raise ValueError("cannot assign a column to a JaggedArray whose content is not a Table")
+            self._valid()
+            if self._off64 is None or self._first != 0 or self._last != len(self._content):
+                raise NotImplementedError("column assignment needs a compact JaggedArray that covers its content (no CPU fallback)")
+            self._content[where] = self.tojagged(what)._content
+            return
+        if not isinstance(where, JaggedArray):
+            raise TypeError("invalid index for assigning to JaggedArray: {0}".format(where))
+        if not isinstance(self._content, DeviceArray):
+            raise NotImplementedError("assignment into Table / nested content is outside the GPU hot path")
+        if isinstance(what, JaggedArray):
+            what = what.flatten()
+        if len(where) != len(self):
+            raise ValueError("jagged array used as index has a different shape {0} from the jagged array it is selecting from {1}".format(where.shape, self.shape))
+        hdt = where._content.dtype if isinstance(where._content, DeviceArray) else None
+        if hdt is None or not (_isintegertype(hdt) or hdt == numpy.bool_):
+            raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
+        self._valid()
+        # absolute positions of every element in the content buffer, as a jagged array with this array's
+        # structure (jagged.py:831: localindex + starts); selecting from it with `where` reuses the checked
+        # mask / index kernels (negative wrap, bounds, shape agreement), then one scatter writes the values
+        positions = self.localindex + self.starts
+        flat = positions[where].flatten()
+        if not (isinstance(what, DeviceArray) or _ufunc.is_scalar(what)):
+            what = asdevice(numpy.asarray(what))
+        _ufunc.put(self._content, flat, what)
+        self._arg_source = self._arg_values = None
 
     # ------------------------------------------------------------------------------------------------------
     # pad / fillna / regular (jagged.py:1851-1900, 1053-1068; SURVEY.md section 8f-4)

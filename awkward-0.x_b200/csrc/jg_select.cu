@@ -3,6 +3,8 @@
 #include <stdlib.h>
 
 #include "jg_scan.cuh"
+#include <cstring>
+
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -263,6 +265,38 @@ take_kernel(const V *__restrict__ content, const int64_t *__restrict__ index, in
     }
 }
 
+// content[index[k]] = values[k] (or one scalar): the store side of __setitem__ (jagged.py:789-838) and of the
+// scatter steps of parents2startsstops (jagged.py:73-93).  Negative indexes are skipped when `skip_negative`.
+template <typename V>
+__global__ void __launch_bounds__(256)
+put_kernel(V *__restrict__ content, const int64_t *__restrict__ index, int64_t n, const V *__restrict__ values,
+           V scalar, int skip_negative) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int64_t at = __ldcs(index + k);
+        if (skip_negative && at < 0) continue;
+        content[at] = values ? __ldcs(values + k) : scalar;
+    }
+}
+
+static inline int flat_grid(int64_t work, int threads) {
+    int64_t blocks = ceil_div(work, threads);
+    int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+template <typename V>
+static int launch_put(void *content, const int64_t *index, int64_t n, const void *values, uint64_t scalar_bits,
+                      int skip_negative, cudaStream_t s) {
+    V scalar;
+    memcpy(&scalar, &scalar_bits, sizeof(V));
+    put_kernel<V><<<flat_grid(n, 256), 256, 0, s>>>(static_cast<V *>(content), index, n,
+                                                   static_cast<const V *>(values), scalar, skip_negative);
+    return check_launch("put_kernel");
+}
+
 // out_index[out_offsets[i]] = best[i] for best[i] >= 0
 __global__ void __launch_bounds__(256)
 scatter_nonneg_kernel(const int64_t *__restrict__ best, int64_t n, const int64_t *__restrict__ out_offsets,
@@ -284,13 +318,6 @@ flat_scatter_kernel(const V *__restrict__ content, const uint8_t *__restrict__ m
         if (mask[i]) out[__ldg(pos + i)] = content[i];
 }
 
-static inline int flat_grid(int64_t work, int threads) {
-    int64_t blocks = ceil_div(work, threads);
-    int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
 
 // workspace layout shared by the "tile totals -> tile bases" helpers: [totals: nt+1][bases: nt+1][scan ws]
 struct TileScanWs {
@@ -373,6 +400,21 @@ int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64
         case 8: return launch_mask_select<uint64_t, 3584>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
     }
     set_error("jg_mask_select: unsupported itemsize %d", itemsize);
+    return -2;
+}
+
+int jg_put(void *content, int itemsize, const int64_t *index, int64_t n, const void *values, uint64_t scalar_bits,
+           int skip_negative, void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(content && index, "jg_put: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    switch (itemsize) {
+        case 1: return launch_put<uint8_t>(content, index, n, values, scalar_bits, skip_negative, s);
+        case 2: return launch_put<uint16_t>(content, index, n, values, scalar_bits, skip_negative, s);
+        case 4: return launch_put<uint32_t>(content, index, n, values, scalar_bits, skip_negative, s);
+        case 8: return launch_put<uint64_t>(content, index, n, values, scalar_bits, skip_negative, s);
+    }
+    set_error("jg_put: unsupported itemsize %d", itemsize);
     return -2;
 }
 

@@ -166,6 +166,12 @@ int jg_index_gather(const void *content, int itemsize, const int64_t *offsets, c
  * be NULL to run the scan only.  out must hold n items (upper bound).                                              */
 int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int64_t n, void *out, int64_t *positions,
                     int64_t *total, void *ws, size_t ws_bytes, void *stream);
+/* scatter content[index[k]] = values[k], or the `itemsize` low bytes of scalar_bits when values is NULL: the store
+ * of __setitem__ (jagged.py:789-838: `self._content[indexes] = what`) and of parents2startsstops (jagged.py:73-93:
+ * `starts[where[real]] = ...`, for which skip_negative != 0 drops the negative parents).  No bounds check: the
+ * indexes come from jg_index_gather / jg_mask_select on absolute positions, which are checked there.              */
+int jg_put(void *content, int itemsize, const int64_t *index, int64_t n, const void *values, uint64_t scalar_bits,
+           int skip_negative, void *stream);
 /* plain gather out[k] = content[index[k]] (jagged.py:1294 content[left]); no bounds check beyond content_len      */
 int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_index, void *out, void *stream);
 

@@ -579,6 +579,81 @@ def pad_fillna(starts, stops, content, length, value, clip=False):
     return offsets, data
 
 
+def parents2startsstops(parents):
+    """jagged.py:73-93 -- children contiguous but not necessarily ordered or covering; negative parents skipped."""
+    parents = np.asarray(parents, dtype=INDEX)
+    tmp = np.nonzero(parents[1:] != parents[:-1])[0] + 1
+    changes = np.empty(len(tmp) + 2, dtype=INDEX)
+    changes[0], changes[-1], changes[1:-1] = 0, len(parents), tmp
+    length = parents.max() + 1 if len(parents) > 0 else 0
+    starts, counts = np.zeros(length, dtype=INDEX), np.zeros(length, dtype=INDEX)
+    if len(parents) == 0:
+        return starts, starts + counts
+    where = parents[changes[:-1]]
+    real = where >= 0
+    starts[where[real]] = changes[:-1][real]
+    counts[where[real]] = (changes[1:] - changes[:-1])[real]
+    return starts, starts + counts
+
+
+def uniques2offsetsparents(uniques):
+    """jagged.py:95-110 -- runs of equal values are the events (no empty events)."""
+    uniques = np.asarray(uniques)
+    changes = np.nonzero(uniques[1:] != uniques[:-1])[0] + 1
+    offsets = np.empty(len(changes) + 2, dtype=INDEX)
+    offsets[0], offsets[-1], offsets[1:-1] = 0, len(uniques), changes
+    parents = np.zeros(len(uniques), dtype=INDEX)
+    parents[changes] = 1
+    np.cumsum(parents, out=parents)
+    return offsets, parents
+
+
+def localindex2offsets(index):
+    """jagged.py:194-222 (fromlocalindex): an event starts wherever the local index is 0."""
+    index = np.asarray(index)
+    if not ((index[1:] - index[:-1])[(index != 0)[1:]] == 1).all():
+        raise ValueError("every localindex that is not zero must be one greater than the previous")
+    starts = np.nonzero(index == 0)[0]
+    offsets = np.empty(len(starts) + 1, dtype=INDEX)
+    offsets[:-1], offsets[-1] = starts, len(index)
+    return offsets
+
+
+def folding2offsets(length, size):
+    """jagged.py:237-242 (fromfolding)."""
+    quotient = -(-length // size)
+    offsets = np.arange(0, quotient * size + 1, size, dtype=INDEX)
+    if len(offsets) > 0:
+        offsets[-1] = length
+    return offsets
+
+
+def setitem(starts, stops, content, where_offsets, where, what):
+    """jagged.py:800-833 -- ``a[where] = what`` for a jagged boolean mask or jagged integer index; returns the new
+    content buffer (the reference assigns in place).  ``what`` is a scalar or one value per selected element."""
+    starts, stops = np.asarray(starts, dtype=INDEX), np.asarray(stops, dtype=INDEX)
+    content = np.array(content, copy=True)
+    where_offsets, where = np.asarray(where_offsets, dtype=INDEX), np.asarray(where)
+    counts = stops - starts
+    wcounts = where_offsets[1:] - where_offsets[:-1]
+    wparents = np.repeat(np.arange(len(wcounts), dtype=INDEX), wcounts)
+    w = where[where_offsets[0]:where_offsets[-1]]
+    if w.dtype == np.dtype(bool):
+        if not np.array_equal(wcounts, counts):
+            raise IndexError("jagged index does not fit")
+        local = np.arange(len(w), dtype=INDEX) - (where_offsets[:-1] - where_offsets[0])[wparents]
+        flat = (starts[wparents] + local)[w]
+    else:
+        idx = w.astype(INDEX)
+        c = counts[wparents]
+        idx = np.where(idx < 0, idx + c, idx)
+        if not ((0 <= idx) & (idx < c)).all():
+            raise IndexError("jagged array used as index contains out-of-bounds values")
+        flat = idx + starts[wparents]
+    content[flat] = what
+    return content
+
+
 def tolist(offsets, content):
     """base.py:159-172 -- nested python lists of a dense jagged array."""
     offsets = np.asarray(offsets)

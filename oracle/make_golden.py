@@ -108,6 +108,31 @@ def run_case(awkward0, name, offsets, content, flat, idx_counts, idx_content, b_
         out["out_%s_invalid" % label] = np.asarray(p.content.boolmask(maskedwhen=True)) if len(content) else np.ones(3 * len(a), dtype=bool)
         out["out_%s_fill" % label] = np.asarray(p.fillna(fill).flatten())
 
+    # the other constructors and jagged __setitem__ (jagged.py:73-110, 168-242, 789-838)
+    par = np.asarray(a.parents)
+    if len(par) > 0:            # the reference indexes parents[0] unconditionally (jagged.py:87): no empty case
+        rs, re = J.parents2startsstops(par)
+        out["out_p2ss_starts"], out["out_p2ss_stops"] = np.asarray(rs), np.asarray(re)
+        rs, re = J.parents2startsstops(par[::-1].copy())           # events in reverse order
+        out["out_p2ss_rev_starts"], out["out_p2ss_rev_stops"] = np.asarray(rs), np.asarray(re)
+        uo, up = J.uniques2offsetsparents(par)
+        out["out_u2op_offsets"], out["out_u2op_parents"] = np.asarray(uo), np.asarray(up)
+    dense = np.asarray(a.flatten())
+    out["out_fromlocalindex_offsets"] = np.asarray(J.fromlocalindex(np.asarray(li.flatten()), dense).offsets)
+    out["out_fromfolding7_offsets"] = np.asarray(J.fromfolding(dense, 7).offsets)
+    if content.dtype != np.bool_:
+        b2 = J.fromoffsets(offsets, content.copy())
+        b2[b2 > threshold] = fill
+        out["out_setmask_scalar"] = np.asarray(b2.content)
+        b2 = J.fromoffsets(offsets, content.copy())
+        msk = b2 > threshold
+        vals = (np.arange(int(np.asarray(msk.content).sum())) % 5).astype(content.dtype)
+        b2[msk] = vals
+        out["out_setmask_values"] = np.asarray(b2.content)
+        b2 = J.fromoffsets(offsets, content.copy())
+        b2[idx] = fill
+        out["out_setindex_scalar"] = np.asarray(b2.content)
+
     if not combos:
         return save(name, out)
 

@@ -506,6 +506,44 @@ def test_arrow_ingest(ak):                   # arrow.py:231-430: l
     assert ak.toarrow(j[j > 2]).to_pylist() == [[2.2], [], [3.3], [4.4, 5.5, 6.6]]
 
 
+def test_other_constructors_and_setitem(ak):   # test_jagged.py:33-35, 50-54, 609-657
+    J = ak.JaggedArray
+    want = [[0.0, 1.1, 2.2], [], [3.3, 4.4], [5.5, 6.6, 7.7, 8.8, 9.9]]
+    assert J.fromparents([0, 0, 0, 2, 2, 3, 3, 3, 3, 3], CONTENT).tolist() == want
+    u = J.fromuniques([9, 9, 9, 8, 8, 7, 7, 7, 7, 7], CONTENT)
+    assert u.tolist() == [[0.0, 1.1, 2.2], [3.3, 4.4], [5.5, 6.6, 7.7, 8.8, 9.9]]
+    assert u.parents.tolist() == [0, 0, 0, 1, 1, 2, 2, 2, 2, 2]
+    a = J.fromlocalindex([0, 1, 0, 0, 0, 1, 2, 0, 1, 0], CONTENT)
+    assert a.tolist() == [[0.0, 1.1], [2.2], [3.3], [4.4, 5.5, 6.6], [7.7, 8.8], [9.9]]
+    assert a.starts.tolist() == [0, 2, 3, 4, 7, 9] and a.stops.tolist() == [2, 3, 4, 7, 9, 10]
+    assert J.fromlocalindex(a.localindex, CONTENT).tolist() == a.tolist()
+    with pytest.raises(ValueError, match="one greater than the previous"):
+        J.fromlocalindex([0, 2, 0], [1.0, 2.0, 3.0])
+    with pytest.raises(ValueError, match="does not match"):
+        J.fromlocalindex(J.fromcounts([1, 2], [0, 0, 1]), [1.0, 2.0, 3.0]).tolist() and J.fromlocalindex(J.fromcounts([2, 1], [0, 0, 0]), [1.0, 2.0, 3.0])
+    assert J.fromjagged(std(ak)).tolist() == want
+    assert J.fromfolding(np.arange(7), 3).tolist() == [[0, 1, 2], [3, 4, 5], [6]]
+    assert J.fromregular(np.arange(12).reshape(4, 3)).tolist() == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11]]
+    assert J.fromregular(np.arange(12).reshape(2, 2, 3)).tolist() == [[[0, 1, 2], [3, 4, 5]], [[6, 7, 8], [9, 10, 11]]]
+    for starts, stops, content in (([0, 1, 1], [1, 1, 3], [1.1, 2.2, 3.3]), ([3, 4, 1], [4, 4, 3], [0.0, 2.2, 3.3, 1.1, 4.4])):
+        for i1, i2, i3 in (([[True], [], [True, True]], [[False], [], [True, True]], [[False], [], [True, False]]),
+                           ([[0], [], [0, 1]], [[], [], [0, 1]], [[], [], [0]])):
+            x = J(starts, stops, content)
+            x[J.fromiter(i1)] = J.fromiter([[4.4], [], [5.5, 6.6]])
+            assert x.tolist() == [[4.4], [], [5.5, 6.6]]
+            x[J.fromiter(i2) if any(len(r) for r in i2) else J.fromcounts([0, 0, 0], np.zeros(0, dtype=np.int64))] = [7.7, 8.8]
+            assert x.tolist() == [[4.4], [], [7.7, 8.8]]
+            x[J.fromiter(i3)] = 9.9
+            assert x.tolist() == [[4.4], [], [9.9, 8.8]]
+    mu = J.zip(pt=J.fromcounts([2, 0, 1], [1.0, 2.0, 3.0]), q=J.fromcounts([2, 0, 1], [1, -1, 1]))
+    mu["w"] = np.array([10.0, 20.0, 30.0])            # one value per event, broadcast (jagged.py:790-791)
+    assert mu.w.tolist() == [[10.0, 10.0], [], [30.0]]
+    mu["pt2"] = mu.pt * 2
+    assert mu.pt2.tolist() == [[2.0, 4.0], [], [6.0]]
+    with pytest.raises(IndexError):
+        x[J.fromiter([[5], [], []])] = 1.0
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
@@ -554,7 +592,7 @@ def test_exceptions(ak):
         a.argchoose(6)
     with pytest.raises(ValueError, match="offsets must be a non-negative array"):
         J.fromoffsets([-1, 3], CONTENT)
-    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+    with pytest.raises(TypeError, match="invalid index for assigning"):
         a[0] = 1.0
     assert J.fromoffsets([0, 3, 2], CONTENT).valid() is False
     ok = a[J.fromcounts([2, 0, 1, 1], [-1, 0, 1, -5])]       # negative wrap (jagged.py:552-553)

@@ -155,6 +155,61 @@ def test_ref_pad_literals():                    # tests/test_jagged.py:544-559
     assert O.tolist(off, filled) == [[1.1, 2.2, 3.3, 999], [999, 999, 999, 999], [4.4, 5.5, 999, 999]]
 
 
+def test_constructors_and_setitem(golden):
+    g = golden
+    off, content = g["in_offsets"], g["in_content"]
+    par = g["out_parents"]
+    if "out_p2ss_starts" in g:
+        s, e = O.parents2startsstops(par)
+        assert same(s, g["out_p2ss_starts"]) and same(e, g["out_p2ss_stops"])
+        s, e = O.parents2startsstops(par[::-1].copy())
+        assert same(s, g["out_p2ss_rev_starts"]) and same(e, g["out_p2ss_rev_stops"])
+        uo, up = O.uniques2offsetsparents(par)
+        assert same(uo, g["out_u2op_offsets"]) and same(up, g["out_u2op_parents"])
+    assert same(O.localindex2offsets(g["out_localindex_content"]), g["out_fromlocalindex_offsets"])
+    assert same(O.folding2offsets(int(off[-1] - off[0]), 7), g["out_fromfolding7_offsets"])
+    if "out_setmask_scalar" in g:
+        fill, thr = g["in_fill"][()], g["in_threshold"][()]
+        with np.errstate(all="ignore"):
+            moff, mask = O.ufunc_broadcast(np.greater, off, content, thr)
+        full_mask = np.zeros(len(content), dtype=bool)
+        full_mask[off[0]:off[-1]] = mask
+        assert same(O.setitem(off[:-1], off[1:], content, off, full_mask, fill), g["out_setmask_scalar"])
+        vals = (np.arange(int(mask.sum())) % 5).astype(content.dtype)
+        assert same(O.setitem(off[:-1], off[1:], content, off, full_mask, vals), g["out_setmask_values"])
+        ioff = O.counts2offsets(g["in_idx_counts"])
+        assert same(O.setitem(off[:-1], off[1:], content, ioff, g["in_idx_content"], fill), g["out_setindex_scalar"])
+
+
+def test_ref_constructor_literals():            # tests/test_jagged.py:33-35, 50-54
+    s, e = O.parents2startsstops([0, 0, 0, 2, 2, 3, 3, 3, 3, 3])
+    assert s.tolist() == [0, 0, 3, 5] and e.tolist() == [3, 0, 5, 10]
+    o, p = O.uniques2offsetsparents([9, 9, 9, 8, 8, 7, 7, 7, 7, 7])
+    assert o.tolist() == [0, 3, 5, 10] and p.tolist() == [0, 0, 0, 1, 1, 2, 2, 2, 2, 2]
+    assert O.localindex2offsets([0, 1, 0, 0, 0, 1, 2, 0, 1, 0]).tolist() == [0, 2, 3, 4, 7, 9, 10]
+    with pytest.raises(ValueError):
+        O.localindex2offsets([0, 2])
+
+
+def test_ref_setitem_literals():                # tests/test_jagged.py:609-657
+    for starts, stops, content in (([0, 1, 1], [1, 1, 3], [1.1, 2.2, 3.3]), ([3, 4, 1], [4, 4, 3], [0.0, 2.2, 3.3, 1.1, 4.4])):
+        def show(c):
+            return [c[a:b].tolist() for a, b in zip(starts, stops)]
+        woff = np.array([0, 1, 1, 3])
+        c = O.setitem(starts, stops, np.array(content), woff, np.array([True, True, True]), np.array([4.4, 5.5, 6.6]))
+        assert show(c) == [[4.4], [], [5.5, 6.6]]
+        c = O.setitem(starts, stops, c, woff, np.array([False, True, True]), np.array([7.7, 8.8]))
+        assert show(c) == [[4.4], [], [7.7, 8.8]]
+        c = O.setitem(starts, stops, c, woff, np.array([False, True, False]), 9.9)
+        assert show(c) == [[4.4], [], [9.9, 8.8]]
+        c = O.setitem(starts, stops, np.array(content), woff, np.array([0, 0, 1]), np.array([4.4, 5.5, 6.6]))
+        assert show(c) == [[4.4], [], [5.5, 6.6]]
+        c = O.setitem(starts, stops, c, np.array([0, 0, 0, 2]), np.array([0, 1]), np.array([7.7, 8.8]))
+        assert show(c) == [[4.4], [], [7.7, 8.8]]
+        c = O.setitem(starts, stops, c, np.array([0, 0, 0, 1]), np.array([0]), 9.9)
+        assert show(c) == [[4.4], [], [9.9, 8.8]]
+
+
 def test_ref_concatenate_literals():           # tests/test_jagged.py:451-487
     lst = [[1, 2, 3], [], [4, 5], [6, 7], [8], [], [9], [10, 11], [12]]
 
