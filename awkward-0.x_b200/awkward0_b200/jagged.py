@@ -912,7 +912,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         raise NotImplementedError("this kind of JaggedArray index is outside the GPU hot path (SURVEY.md section 8f-1); no CPU fallback")
 
     def _getitem_inner(self, head):
-        """a[:, k] and a[:, i:j] (jagged.py:615-707 for an integer or a unit-step slice), built from device ufuncs."""
+        """a[:, k], a[:, i:j] and a[:, i:j:step] (jagged.py:615-707), built from device ufuncs."""
         if self._off64 is not None:
             s64, e64 = self._off64[:-1], self._off64[1:]
         else:
@@ -927,7 +927,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return self._map_content(lambda c: _ufunc.take(c, s64 + local))
         if isinstance(head, slice):
             if head.step not in (None, 1):
-                raise NotImplementedError("intra-event slices with a step are outside the GPU hot path (SURVEY.md section 8f-1)")
+                return self._getitem_inner_step(s64, counts, head)
 
             def bound(v, default):
                 if v is None:
@@ -941,6 +941,52 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             hi = numpy.maximum(lo, hi)
             return self._from_general(s64 + lo, s64 + hi, self._content)
         raise NotImplementedError("this kind of intra-event index is outside the GPU hot path (SURVEY.md section 8f-1)")
+
+    def _getitem_inner_step(self, s64, counts, head):
+        """a[:, i:j:step] (jagged.py:634-707): Python slice semantics inside every event.  The reference builds an
+        (events x widest) index matrix and masks it; here the new counts come from the clamped bounds, one scan
+        gives the new offsets and the source position of output element l of event i is first_i + l * step."""
+        step = int(head.step)
+        if step == 0:
+            raise ValueError("slice step cannot be zero")
+        n = len(counts)
+        if step > 0:
+            if head.start is None:
+                lo = counts * 0
+            elif head.start >= 0:
+                lo = numpy.minimum(counts, head.start)
+            else:
+                lo = numpy.maximum(numpy.minimum(counts, counts + head.start), 0)
+            if head.stop is None:
+                hi = counts
+            elif head.stop >= 0:
+                hi = numpy.minimum(counts, head.stop)
+            else:
+                hi = numpy.maximum(numpy.minimum(counts, counts + head.stop), 0)
+            hi = numpy.maximum(lo, hi)
+            newcounts = (hi - lo + (step - 1)) // step
+        else:
+            if head.start is None:
+                lo = counts - 1
+            elif head.start >= 0:
+                lo = numpy.minimum(counts - 1, head.start)
+            else:
+                lo = numpy.maximum(numpy.minimum(counts - 1, counts + head.start), -1)
+            if head.stop is None:
+                hi = counts * 0 - 1
+            elif head.stop >= 0:
+                hi = numpy.minimum(counts - 1, head.stop)
+            else:
+                hi = numpy.maximum(numpy.minimum(counts - 1, counts + head.stop), -1)
+            hi = numpy.minimum(lo, hi)
+            newcounts = (lo - hi + (-step - 1)) // (-step)
+        newoffsets, total, _ = self._scan_counts(newcounts)
+        local = empty(total, INDEXTYPE)
+        if total > 0:
+            call("jg_localindex", newoffsets.data_ptr(), n, _vp(local), runtime.stream())
+        scaled = _ufunc.binary(numpy.multiply, DeviceArray(local, INDEXTYPE), numpy.int64(step))
+        source = _ufunc.binary(numpy.add, scaled, s64 + lo, offsets=newoffsets, nevents=n, parent_side=1) if total > 0 else scaled
+        return self._make(newoffsets, self._map_content(lambda c: _ufunc.take(c, source)), total)
 
     def _align(self, other):
         """_tojagged(self.starts, self.stops) of jagged.py:573/971-973: `other` must have my counts."""

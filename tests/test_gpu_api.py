@@ -544,6 +544,22 @@ def test_other_constructors_and_setitem(ak):   # test_jagged.py:33-35, 50-54, 60
         x[J.fromiter([[5], [], []])] = 1.0
 
 
+def test_inner_slices_with_step(ak):          # jagged.py:634-707: python slice semantics inside every event
+    rng = np.random.default_rng(5)
+    counts = rng.poisson(4.0, 300)
+    counts[:3] = [0, 1, 40]
+    rows = [list(map(float, rng.integers(0, 99, c))) for c in counts]
+    a = ak.JaggedArray.fromiter(rows)
+    for sl in (slice(None, None, 2), slice(None, None, -1), slice(1, None, 2), slice(None, -1, 3), slice(-2, None, -1),
+               slice(5, 1, -2), slice(-1, -6, -2), slice(3, None, -3), slice(None, 2, -1), slice(0, 100, 7),
+               slice(-100, 100, 2), slice(100, -100, -2), slice(2, 2, 2)):
+        assert a[:, sl].tolist() == [r[sl] for r in rows], sl
+    b = a[5:200]
+    assert b[:, ::-1].tolist() == [r[::-1] for r in rows[5:200]]
+    with pytest.raises(ValueError, match="slice step cannot be zero"):
+        a[:, ::0]
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
