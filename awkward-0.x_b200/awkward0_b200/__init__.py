@@ -11,6 +11,7 @@ from .masked import MaskedArray  # noqa: F401
 from .table import Table  # noqa: F401
 from .jagged import JaggedArray  # noqa: F401
 from .arrow import fromarrow, toarrow  # noqa: F401
+from .ingest import StreamedJaggedArray  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow"]
+__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray"]

@@ -560,6 +560,47 @@ def test_inner_slices_with_step(ak):          # jagged.py:634-707: python slice 
         a[:, ::0]
 
 
+def test_streamed_ingest(ak):                # ingest.py: host -> HBM with the copy overlapped, event-range views
+    import torch
+    from oracle import jagged_oracle as orc
+    rng = np.random.default_rng(21)
+    counts = rng.poisson(5.0, 200000).astype(np.int64)
+    counts[1000] = 30000
+    pt = rng.exponential(25.0, int(counts.sum()) + 5).astype(np.float32)       # 5 unreachable trailing items
+    cp = torch.empty(len(counts), dtype=torch.int64, pin_memory=True)
+    cp.numpy()[:] = counts
+    pp = torch.empty(len(pt), dtype=torch.float32, pin_memory=True)
+    pp.numpy()[:] = pt
+    off = orc.counts2offsets(counts)
+    want_sum = orc.reduce(off, pt, "sum")
+    want_aoff, want_aidx = orc.argminmax(off, pt, False)
+    for nchunks, piece in ((1, 1 << 20), (7, 1 << 16), (8, 64 << 20), (13, 4096)):
+        st = ak.StreamedJaggedArray(cp, pp, nchunks=nchunks, piece_bytes=piece)
+        assert len(st) == len(counts) and st.nchunks == nchunks
+        sums, idxs, sel_counts, nsel = [], [], [], 0
+        for a in st:
+            assert a.counts.dtype == np.dtype(np.int64)
+            sums.append(a.sum().get())
+            idxs.append(a.argmax().content.get())
+            sel = a[a > 20]
+            sel_counts.append(sel.counts.get())
+            nsel += len(sel.flatten())
+        assert np.allclose(np.concatenate(sums), want_sum, rtol=1e-5)
+        assert np.array_equal(np.concatenate(idxs), want_aidx)
+        moff, mask = orc.ufunc_broadcast(np.greater, off, pt, 20)
+        assert nsel == int(mask.sum())
+        assert np.array_equal(np.concatenate(sel_counts), orc.reduce_counts_of_mask(off, mask))
+        whole = st.whole()
+        assert np.array_equal(whole.offsets.get(), off) and np.allclose(whole.sum().get(), want_sum, rtol=1e-5)
+    # pageable numpy inputs work too; negative counts raise like fromcounts
+    st = ak.StreamedJaggedArray(counts[:1000], pt[:int(counts[:1000].sum())], nchunks=3)
+    assert [len(c) for c in st] == [333, 333, 334]
+    with pytest.raises(ValueError, match="non-negative"):
+        ak.StreamedJaggedArray(np.array([1, -1]), np.zeros(3))
+    with pytest.raises(ValueError, match="beyond the length of the content"):
+        ak.StreamedJaggedArray(np.array([2, 2]), np.zeros(3))
+
+
 def test_device_array_surface(ak):
     a = ak.JaggedArray.fromcounts([2, 0, 3], np.arange(5, dtype=np.float32))
     s = a.sum()
