@@ -2,9 +2,12 @@
 // cross (rectangular) index generation, jagged.py:1070-1126, 1128-1221, 1302-1325.
 //
 // Phase 1 (jg_comb_offsets): per-event output count computed on the fly inside the look-back scan -> new offsets
-// and the grand total P.  Phase 2 (jg_comb_fill / jg_comb_gather2): one CTA per event tile; the output run of the
-// tile is walked element-parallel (coalesced 8-byte stores per column), each output finds its event by binary
-// search in the tile's on-chip output offsets and inverts the triangular / rectangular / combinatorial numbering
+// and the grand total P.  Phase 2 (jg_comb_fill / jg_comb_gather2 / jg_comb_gather_multi): one CTA per event tile.
+// Usual case: the pairs of the tile are first laid out EVENT-parallel in a shared-memory pair table (each thread
+// walks its event's pairs in order with two counters), then the output run is swept element-parallel with
+// coalesced stores, reading its pair from the table.  Tiles whose output run exceeds the table, or that hold an
+// event with hundreds of pairs, take the general path: the output finds its event through the on-chip owner
+// table (binary search for very long runs) and inverts the triangular / rectangular / combinatorial numbering
 // with integer-exact arithmetic (a floating-point estimate corrected by integer comparisons; the reference's
 // float64 closed forms are exact only up to n ~ 6000 for pairs, "1000 choose 3", "100 choose 4").
 //
@@ -104,7 +107,7 @@ __device__ __forceinline__ int64_t largest_binom_le(int64_t m, int k, int64_t n)
     return c;
 }
 
-constexpr int kCombPositions = 12288;    // output positions of a tile the on-chip owner table covers
+constexpr int kCombPositions = 8192;    // output positions of a tile the on-chip owner table covers
 
 struct CombIndex {
     int64_t v[5];
@@ -138,6 +141,69 @@ __device__ __forceinline__ CombIndex unrank(int64_t m, int64_t na, int64_t nb, i
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pair table: the (left, right) item of every output position of a tile, built EVENT-parallel in shared memory --
+// a thread walks the pairs of its event in output order (two counters, no un-ranking, no owner lookup) and
+// drops them at the event's slot; the output-parallel sweep that follows reads its pair with two 16-bit loads and
+// keeps its coalesced global stores.  Used whenever the tile's output run fits the table and no single event
+// dominates it (a thread would walk that event alone); otherwise the callers fall back to owner table + un-ranking.
+//   REL = true : entries are positions relative to the first item of the tile (a0 / b0) -> value gathers
+//   REL = false: entries are the local indices i, j                                  -> arg forms
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPairTable = 4096;         // two uint16 tables of this many entries alias the owner table's storage
+constexpr int kPairEventMax = 384;       // more outputs than this in one event: un-rank instead
+static_assert(2 * kPairTable <= kCombPositions + 128, "pair tables must fit the owner table's storage");
+
+template <int KIND, bool REL>
+__device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uint16_t *__restrict__ s_r,
+                                                 const EventTile &pt, const int64_t *__restrict__ s_oa,
+                                                 const int64_t *__restrict__ s_ob) {
+    const int64_t p0 = pt.off[0], total = pt.off[pt.nev] - p0;
+    bool ok = total <= kPairTable;
+    if (REL) {
+        ok = ok && (s_oa[pt.nev] - s_oa[0]) < 65536;
+        if (KIND == JG_COMB_CROSS) ok = ok && (s_ob[pt.nev] - s_ob[0]) < 65536;
+    }
+    for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) ok = ok && (pt.off[ev + 1] - pt.off[ev]) <= kPairEventMax;
+    if (!__syncthreads_and(ok)) return false;
+#pragma unroll 1
+    for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) {
+        const int cnt = static_cast<int>(pt.off[ev + 1] - pt.off[ev]);
+        if (cnt == 0) continue;
+        uint16_t *l = s_l + (pt.off[ev] - p0), *r = s_r + (pt.off[ev] - p0);
+        const int na = static_cast<int>(s_oa[ev + 1] - s_oa[ev]);
+        const int ra = REL ? static_cast<int>(s_oa[ev] - s_oa[0]) : 0;
+        if constexpr (KIND == JG_COMB_CROSS) {
+            const int nb = static_cast<int>(s_ob[ev + 1] - s_ob[ev]);
+            const int rb = REL ? static_cast<int>(s_ob[ev] - s_ob[0]) : 0;
+            int i = 0, j = 0;
+#pragma unroll 1
+            for (int o = 0; o < cnt; ++o) {
+                l[o] = static_cast<uint16_t>(ra + i);
+                r[o] = static_cast<uint16_t>(rb + j);
+                if (++j == nb) {
+                    j = 0;
+                    ++i;
+                }
+            }
+        } else {
+            constexpr int kFirst = (KIND == JG_COMB_DISTINCTS) ? 1 : 0;      // j starts at i (pairs) or i + 1
+            int i = 0, j = kFirst;
+#pragma unroll 1
+            for (int o = 0; o < cnt; ++o) {
+                l[o] = static_cast<uint16_t>(ra + i);
+                r[o] = static_cast<uint16_t>(ra + j);
+                if (++j == na) {
+                    ++i;
+                    j = i + kFirst;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 struct ColPtrs {
     int64_t *p[5];
 };
@@ -156,6 +222,24 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     const int ncols = (KIND == JG_COMB_CHOOSE) ? k : 2;
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    if constexpr (KIND == JG_COMB_PAIRS || KIND == JG_COMB_CROSS) {      // (distincts: mostly 0-1 pairs, measured slower)
+        // relative positions when absolute indices are wanted (the tile's first item is added back), else i, j
+        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
+        const bool fast = absolute ? build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)
+                                   : build_pair_table<KIND, false>(s_l, s_r, pt, s_oa, s_ob);
+        if (fast) {
+            const int64_t add_l = absolute ? s_oa[0] : 0;
+            const int64_t add_r = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]) : 0;
+            const int total = static_cast<int>(p1 - p0);
+            int64_t *c0 = cols.p[0] + p0, *c1 = cols.p[1] + p0;
+#pragma unroll 2
+            for (int q = threadIdx.x; q < total; q += kTileThreads) {
+                __stcs(c0 + q, add_l + s_l[q]);
+                __stcs(c1 + q, add_r + s_r[q]);
+            }
+            return;
+        }
+    }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
 #pragma unroll 1
@@ -188,6 +272,39 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    {
+        // (staging the tile's content runs in shared memory by TMA was measured: slower -- the loads below hit L1)
+        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
+        if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+            const VA *ca = content_a + s_oa[0];
+            const VB *cb = content_b + ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]);
+            VA *ol = out_l + p0;
+            VB *orr = out_r + p0;
+            const int total = static_cast<int>(p1 - p0);
+#pragma unroll 1
+            for (int qb = threadIdx.x; qb < total; qb += 4 * kTileThreads) {
+                VA va[4];
+                VB vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = qb + u * kTileThreads;
+                    if (q < total) {
+                        va[u] = __ldg(ca + s_l[q]);
+                        vb[u] = __ldg(cb + s_r[q]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = qb + u * kTileThreads;
+                    if (q < total) {
+                        __stcs(ol + q, va[u]);
+                        __stcs(orr + q, vb[u]);
+                    }
+                }
+            }
+            return;
+        }
+    }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
 #pragma unroll 1
@@ -249,6 +366,29 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
     ta.load(s_oa, offsets_a, n, blockIdx.x);
     if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    {
+        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
+        if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+            const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
+            const int total = static_cast<int>(p1 - p0);
+#pragma unroll 1
+            for (int q = threadIdx.x; q < total; q += kTileThreads) {
+                const int64_t ia = a0 + s_l[q], ib = b0 + s_r[q];
+                V vl[4], vr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < cols.nl) vl[c] = __ldg(static_cast<const V *>(cols.in_l[c]) + ia);
+                    if (c < cols.nr) vr[c] = __ldg(static_cast<const V *>(cols.in_r[c]) + ib);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < cols.nl) __stcs(static_cast<V *>(cols.out_l[c]) + p0 + q, vl[c]);
+                    if (c < cols.nr) __stcs(static_cast<V *>(cols.out_r[c]) + p0 + q, vr[c]);
+                }
+            }
+            return;
+        }
+    }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
 #pragma unroll 1
