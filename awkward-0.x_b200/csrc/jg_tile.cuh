@@ -138,17 +138,39 @@ __device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t phase) {
 namespace jg {
 
 // ---------------------------------------------------------------------------------------------------------
-// Owner table: for every position p of a tile's run [0, L) the local index of the event that owns it, built in
-// shared memory by a vectorised SCATTER (each non-empty event drops its index on its first position) followed by
+// Owner table: for every position p of a tile's run [0, L) the local index of the event that owns it.  When all
+// events of the tile are short it is written event-parallel (each thread fills its own event); otherwise it is built
+// by a vectorised SCATTER (each non-empty event drops its index on its first position) followed by
 // a running-MAX SCAN (rows of 128 positions per warp, 4 per lane, shuffles across lanes).  This is the on-chip
 // form of offsets2parents (jagged.py:49-54, numpy.repeat) and feeds parents / localindex / broadcast / gathers /
 // combinatorics without a per-element binary search.
 //   own : __shared__ uint16_t[KM + 128], 16-byte aligned;  requires L <= KM and nev <= 65535
 // All threads of the CTA call it; it ends with a __syncthreads().
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kOwnerShortEvent = 24;     // events up to this long are written by their own thread
+
 __device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile &tile, int L) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kTileThreads / kWarp;
+    // 0. usual case, every event of the tile is short: each thread writes its event's index over the event's own
+    //    positions (a few 16-bit stores); no clearing, no scan, no binary search for the warp carries
+    {
+        bool small = true;
+#pragma unroll 1
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) small = small && (tile.off[ev + 1] - tile.off[ev]) <= kOwnerShortEvent;
+        if (__syncthreads_and(small)) {
+            const int64_t e0s = tile.off[0];
+#pragma unroll 1
+            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+                uint16_t *o = own + (tile.off[ev] - e0s);
+                const int c = static_cast<int>(tile.off[ev + 1] - tile.off[ev]);
+#pragma unroll 1
+                for (int k = 0; k < c; ++k) o[k] = static_cast<uint16_t>(ev);
+            }
+            __syncthreads();
+            return;
+        }
+    }
     const int padded = (L + 127) & ~127;
     // 1. clear (128-bit stores)
 #pragma unroll 1

@@ -502,7 +502,7 @@ def workflow_table(ak, counts_dev, pt_dev, N, M, args):
     import torch
     out = {}
 
-    def timed(name, fn, units, unit_name, reps=3):
+    def timed(name, fn, units, unit_name, reps=5):
         fn()
         torch.cuda.synchronize()
         ts = []
