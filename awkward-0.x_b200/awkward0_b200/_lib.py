@@ -86,6 +86,7 @@ PROTOTYPES = {
     "jg_comb_gather_multi": (_i, [_i, _vp, _vp, _i64, _vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i,
                                   ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
     "jg_comb_gather2": (_i, [_i, _vp, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "jg_comb_eval": (_i, [_i, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

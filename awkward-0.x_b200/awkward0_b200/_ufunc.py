@@ -65,6 +65,11 @@ def _finish(out, kdt, rdt, fix):
     return DeviceArray(out, rdt)
 
 
+def _lazy():
+    from . import lazy          # lazy.py imports device.py only; imported late to keep the module graph acyclic
+    return lazy
+
+
 def is_scalar(x):
     return isinstance(x, (numbers.Number, bool, numpy.bool_, numpy.number)) or (isinstance(x, numpy.ndarray) and x.ndim == 0)
 
@@ -176,6 +181,10 @@ def unary(ufunc, x):
     if name is None:
         raise NotImplementedError("ufunc {0} is not implemented on the device".format(ufunc.__name__))
     rdt, cdt = result_dtypes(ufunc, [x])
+    if isinstance(x, _lazy().LazyArray):
+        node = _lazy().try_fuse(name, [x], rdt, cdt)
+        if node is not None:
+            return node
     if ufunc is numpy.logical_not:
         x = _as_bool(x)
     if name == "NOT" and x.dtype == numpy.bool_:
@@ -203,6 +212,10 @@ def binary(ufunc, lhs, rhs, offsets=None, nevents=0, parent_side=None):
     if ufunc in _LOGICAL:
         lhs, rhs = _as_bool(lhs), _as_bool(rhs)
     rdt, cdt = result_dtypes(ufunc, [lhs, rhs])
+    if parent_side is None and (isinstance(lhs, _lazy().LazyArray) or isinstance(rhs, _lazy().LazyArray)):
+        node = _lazy().try_fuse(name, [lhs, rhs], rdt, cdt)
+        if node is not None:
+            return node
     kcdt, kdt, fix = _native_compute(name, rdt, cdt)
     ccode = jg_code(kcdt)
     if ccode not in _COMPUTE_OK and not (name in _COMPARE and ccode == _lib.JG_U64):

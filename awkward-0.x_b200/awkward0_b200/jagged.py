@@ -23,6 +23,7 @@ import numpy
 import numpy.lib.mixins
 
 from . import _lib, _ufunc
+from . import lazy as _lazy
 from ._lib import call
 from .device import (BOOLTYPE, INDEXTYPE, DeviceArray, asdevice, empty, jg_code, runtime, torch, torch_dtype)
 from .masked import MaskedArray, fill_masked
@@ -1352,86 +1353,25 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return self._make(poff, table, total)
 
     def _comb_values(self, kind, other=None):
+        """Value forms (jagged.py:1232-1367).  The columns of the result are deferred (lazy.py): a consumer that
+        needs them gets all of them from one gather sweep, a ufunc chain on them is evaluated by one fused kernel
+        straight from the two collections without the gathered temporaries ever being written."""
         a, off, n, first, last = self._dense()
         if kind == _lib.COMB_CROSS:
             b, off_b, nb, _, _ = other._dense()
         else:
             b, off_b = a, None
         poff, total = self._comb_offsets(kind, 2, off, off_b, n)
+        ctx = _lazy.CombContext(kind, off, off_b, n, poff, total)
 
-        def gather(col_a, col_b):
-            out_l, out_r = empty(total, col_a.dtype), empty(total, col_b.dtype)
-            if total > 0:
-                call("jg_comb_gather2", kind, off.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0),
-                     n, poff.data_ptr(), col_a.data_ptr(), col_a.itemsize, col_b.data_ptr(), col_b.itemsize,
-                     _vp(out_l), _vp(out_r), runtime.stream())
-            return DeviceArray(out_l, col_a.dtype), DeviceArray(out_r, col_b.dtype)
-
-        def multi(leaves_l, leaves_r):
-            """Gather lists of same-itemsize leaf columns for the left / right side in one kernel (<= 4 per side)."""
-            outs_l = [empty(total, c.dtype) for c in leaves_l]
-            outs_r = [empty(total, c.dtype) for c in leaves_r]
-            if total > 0:
-                def parr(ts):
-                    return (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])
-                call("jg_comb_gather_multi", kind, off.data_ptr(),
-                     off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0), n, poff.data_ptr(),
-                     (leaves_l or leaves_r)[0].itemsize, len(leaves_l), parr([c.tensor for c in leaves_l]), parr(outs_l),
-                     len(leaves_r), parr([c.tensor for c in leaves_r]), parr(outs_r), runtime.stream())
-            return ([DeviceArray(o, c.dtype) for o, c in zip(outs_l, leaves_l)],
-                    [DeviceArray(o, c.dtype) for o, c in zip(outs_r, leaves_r)])
-
-        def records(col_a, col_b):
-            """Table content: all leaf columns of one itemsize share a sweep; returns (left tree, right tree)."""
-            la, lb = list(_leaves(col_a)), list(_leaves(col_b))
-            if any(isinstance(x, JaggedArray) for x in la + lb):
+        def side(content, which):
+            leaves = list(_leaves(content))
+            if any(not isinstance(x, DeviceArray) for x in leaves):
                 raise NotImplementedError("combinatorics over nested content are outside the GPU hot path")
-            res_l, res_r = [None] * len(la), [None] * len(lb)
-            for size in sorted(set(c.itemsize for c in la + lb)):
-                il = [i for i, c in enumerate(la) if c.itemsize == size]
-                ir = [i for i, c in enumerate(lb) if c.itemsize == size]
-                while il or ir:
-                    cl, cr = il[:4], ir[:4]
-                    il, ir = il[4:], ir[4:]
-                    ol, orr = multi([la[i] for i in cl], [lb[i] for i in cr])
-                    for i, o in zip(cl, ol):
-                        res_l[i] = o
-                    for i, o in zip(cr, orr):
-                        res_r[i] = o
-            return _rebuild(col_a, iter(res_l)), _rebuild(col_b, iter(res_r))
+            return _rebuild(content, iter([ctx.leaf(which, c) for c in leaves]))
 
-        if isinstance(a._content, Table) or isinstance(b._content, Table):
-            left, right = records(a._content, b._content)
-            return self._make(poff, Table.named("tuple", left, right), total)
-
-        def both(col_a, col_b):
-            """(left tree, right tree) for one column (or Table of columns) of each side."""
-            if isinstance(col_a, JaggedArray) or isinstance(col_b, JaggedArray):
-                raise NotImplementedError("combinatorics over nested content are outside the GPU hot path")
-            if kind != _lib.COMB_CROSS:
-                if isinstance(col_a, Table):
-                    left, right = Table.named(col_a.rowname), Table.named(col_a.rowname)
-                    for name in col_a.columns:
-                        left._contents[name], right._contents[name] = both(col_a[name], col_a[name])
-                    return left, right
-                return gather(col_a, col_a)
-            leaves_a = list(_leaves(col_a))
-            leaves_b = list(_leaves(col_b))
-            m = max(len(leaves_a), len(leaves_b))
-            outs_a, outs_b = [], []
-            for i in range(m):
-                la = leaves_a[i] if i < len(leaves_a) else leaves_a[0]
-                lb = leaves_b[i] if i < len(leaves_b) else leaves_b[0]
-                l, r = gather(la, lb)
-                if i < len(leaves_a):
-                    outs_a.append(l)
-                if i < len(leaves_b):
-                    outs_b.append(r)
-            return _rebuild(col_a, iter(outs_a)), _rebuild(col_b, iter(outs_b))
-
-        left, right = both(a._content, b._content)
-        table = Table.named("tuple", left, right)
-        return self._make(poff, table, total)
+        left, right = side(a._content, "L"), side(b._content, "R")
+        return self._make(poff, Table.named("tuple", left, right), total)
 
     def _nest(self, flat_result, kind, other=None):
         """nested=True (jagged.py:1255,1275,1285,1298,1335,1356): regroup the per-event combinations by their

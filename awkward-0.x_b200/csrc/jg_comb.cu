@@ -12,6 +12,7 @@
 // float64 closed forms are exact only up to n ~ 6000 for pairs, "1000 choose 3", "100 choose 4").
 //
 // Algorithmic traffic: 8(N+1) [x2 for cross] read, 8(N+1) + k*8*P written.
+#include "jg_ops.cuh"
 #include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
@@ -413,6 +414,184 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused per-combination expression (SURVEY 8d "pair mass fused from index generation"): the value form of
+// pairs / distincts / cross followed by a chain of ufuncs, e.g.
+//     p = mu.pairs();  sqrt(2 * p.i0.pt * p.i1.pt * (cosh(p.i0.eta - p.i1.eta) - cos(p.i0.phi - p.i1.phi)))
+// is evaluated in ONE sweep: every output position finds its (left, right) item exactly like comb_gather2_kernel,
+// loads the columns the expression names straight from the collections and runs a small register program; the
+// 2 x columns x P gathered temporaries and the P-sized intermediate of every ufunc are never written.
+// The host (awkward0_b200/lazy.py) compiles the expression DAG into the program: one 32-bit word per step,
+//     op | dst << 8 | a << 16 | b << 24
+// with op a JG_OP_* code (the SAME functors as the eager kernels: jg_ops.cuh, so both paths round identically)
+// or one of the loads below.  The "registers" are per-thread columns of shared memory (slot-major, so the
+// accesses of a warp are consecutive words); every step is executed for U positions of the thread at once, which
+// amortises the decode over U results and keeps U independent dependency chains in flight.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int U>
+__device__ __forceinline__ void eval_program(const JgEvalProgram &pr, T *__restrict__ regs, const int64_t (&ia)[U],
+                                             const int64_t (&ib)[U], const int64_t (&ip)[U]) {
+    constexpr int S = kTileThreads;        // stride between the U copies of one slot
+#define JG_EV_BIN(OPC)                                                                        \
+    case OPC:                                                                                 \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = BinaryOp<OPC, T>::apply(ra[u * S], rb[u * S]); \
+        break;
+#define JG_EV_CMP(OPC)                                                                        \
+    case OPC:                                                                                 \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = T(CompareOp<OPC, T>::apply(ra[u * S], rb[u * S])); \
+        break;
+#define JG_EV_UN(OPC)                                                                         \
+    case OPC:                                                                                 \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = UnaryOp<OPC, T>::apply(ra[u * S]); \
+        break;
+#pragma unroll 1
+    for (int pc = 0; pc < pr.nins; ++pc) {
+        const uint32_t w = pr.ins[pc];
+        const int op = w & 255, a = (w >> 16) & 255, b = w >> 24;
+        T *rd = regs + ((w >> 8) & 255) * (U * S);
+        const T *ra = regs + a * (U * S), *rb = regs + b * (U * S);
+        switch (op) {
+            case JG_EV_LOAD_LEFT: {
+                const T *col = static_cast<const T *>(pr.left[a]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) rd[u * S] = __ldg(col + ia[u]);
+                break;
+            }
+            case JG_EV_LOAD_RIGHT: {
+                const T *col = static_cast<const T *>(pr.right[a]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) rd[u * S] = __ldg(col + ib[u]);
+                break;
+            }
+            case JG_EV_LOAD_POS: {
+                const T *col = static_cast<const T *>(pr.pos[a]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) rd[u * S] = __ldcs(col + ip[u]);
+                break;
+            }
+            case JG_EV_CONST: {
+                const T c = static_cast<T>(pr.consts[a]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) rd[u * S] = c;
+                break;
+            }
+            JG_EV_BIN(JG_OP_ADD) JG_EV_BIN(JG_OP_SUB) JG_EV_BIN(JG_OP_MUL) JG_EV_BIN(JG_OP_DIV)
+            JG_EV_BIN(JG_OP_FLOORDIV) JG_EV_BIN(JG_OP_MOD) JG_EV_BIN(JG_OP_POW) JG_EV_BIN(JG_OP_MAXIMUM)
+            JG_EV_BIN(JG_OP_MINIMUM) JG_EV_BIN(JG_OP_ARCTAN2) JG_EV_BIN(JG_OP_HYPOT)
+            JG_EV_CMP(JG_OP_GT) JG_EV_CMP(JG_OP_GE) JG_EV_CMP(JG_OP_LT) JG_EV_CMP(JG_OP_LE)
+            JG_EV_CMP(JG_OP_EQ) JG_EV_CMP(JG_OP_NE)
+            JG_EV_UN(JG_OP_NEG) JG_EV_UN(JG_OP_ABS) JG_EV_UN(JG_OP_SQRT) JG_EV_UN(JG_OP_EXP) JG_EV_UN(JG_OP_LOG)
+            JG_EV_UN(JG_OP_SIN) JG_EV_UN(JG_OP_COS) JG_EV_UN(JG_OP_TAN) JG_EV_UN(JG_OP_SINH) JG_EV_UN(JG_OP_COSH)
+            JG_EV_UN(JG_OP_TANH) JG_EV_UN(JG_OP_SQUARE) JG_EV_UN(JG_OP_CAST) JG_EV_UN(JG_OP_ARCSINH)
+            JG_EV_UN(JG_OP_FLOOR) JG_EV_UN(JG_OP_CEIL) JG_EV_UN(JG_OP_RINT) JG_EV_UN(JG_OP_SIGN)
+            JG_EV_UN(JG_OP_LOG10) JG_EV_UN(JG_OP_EXP2) JG_EV_UN(JG_OP_ARCSIN) JG_EV_UN(JG_OP_ARCCOS)
+            JG_EV_UN(JG_OP_ARCTAN) JG_EV_UN(JG_OP_LOG2) JG_EV_UN(JG_OP_LOG1P) JG_EV_UN(JG_OP_EXPM1)
+            JG_EV_UN(JG_OP_RECIPROCAL)
+            default: break;      // rejected on the host (eval_op_supported)
+        }
+    }
+#undef JG_EV_BIN
+#undef JG_EV_CMP
+#undef JG_EV_UN
+}
+
+static bool eval_op_supported(int op) {
+    if (op >= JG_EV_LOAD_LEFT && op <= JG_EV_CONST) return true;
+    if (op >= JG_OP_ADD && op <= JG_OP_HYPOT) return true;
+    if (op >= JG_OP_GT && op <= JG_OP_NE) return true;
+    switch (op) {
+        case JG_OP_NEG: case JG_OP_ABS: case JG_OP_SQRT: case JG_OP_EXP: case JG_OP_LOG: case JG_OP_SIN:
+        case JG_OP_COS: case JG_OP_TAN: case JG_OP_SINH: case JG_OP_COSH: case JG_OP_TANH: case JG_OP_SQUARE:
+        case JG_OP_CAST: case JG_OP_ARCSINH: case JG_OP_FLOOR: case JG_OP_CEIL: case JG_OP_RINT: case JG_OP_SIGN:
+        case JG_OP_LOG10: case JG_OP_EXP2: case JG_OP_ARCSIN: case JG_OP_ARCCOS: case JG_OP_ARCTAN: case JG_OP_LOG2:
+        case JG_OP_LOG1P: case JG_OP_EXPM1: case JG_OP_RECIPROCAL:
+            return true;
+    }
+    return false;
+}
+
+template <int KIND, typename T, int U>
+__global__ void __launch_bounds__(kTileThreads)
+comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                 const int64_t *__restrict__ out_offsets, const __grid_constant__ JgEvalProgram pr,
+                 void *__restrict__ out) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[kTileEvents + 1];
+    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    extern __shared__ __align__(16) unsigned char s_dyn[];        // nslots x U x 256 values of T
+    T *regs = reinterpret_cast<T *>(s_dyn) + threadIdx.x;
+    EventTile pt, ta, tb;
+    pt.load(s_po, out_offsets, n, blockIdx.x);
+    ta.load(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    const int64_t total = p1 - p0;
+    if (total <= 0) return;
+    uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
+    const bool fast = build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob);
+    bool table = false;
+    if (!fast) {
+        table = total <= kCombPositions;
+        if (table) build_owner_table(s_own, pt, static_cast<int>(total));
+    }
+    const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
+    const T *res = regs + pr.result * (U * kTileThreads);
+#pragma unroll 1
+    for (int64_t qb = threadIdx.x; qb < total; qb += U * kTileThreads) {
+        int64_t ia[U], ib[U], ip[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int64_t q = qb + u * kTileThreads;
+            if (q >= total) q = total - 1;            // the spare lanes of the last batch recompute the last position
+            ip[u] = p0 + q;
+            if (fast) {
+                ia[u] = a0 + s_l[q];
+                ib[u] = b0 + s_r[q];
+            } else {
+                const int ev = table ? static_cast<int>(s_own[q]) : pt.find_event(p0 + q);
+                const int64_t na = s_oa[ev + 1] - s_oa[ev];
+                const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+                CombIndex r = unrank<KIND>(p0 + q - s_po[ev], na, nb, 2);
+                ia[u] = s_oa[ev] + r.v[0];
+                ib[u] = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
+            }
+        }
+        eval_program<T, U>(pr, regs, ia, ib, ip);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qb + u * kTileThreads;
+            if (q < total) {
+                if (pr.out_bool) __stcs(static_cast<uint8_t *>(out) + p0 + q, static_cast<uint8_t>(res[u * kTileThreads] != T(0)));
+                else __stcs(static_cast<T *>(out) + p0 + q, res[u * kTileThreads]);
+            }
+        }
+    }
+}
+
+template <int KIND, typename T, int U>
+static int launch_comb_eval(const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const JgEvalProgram &pr,
+                            void *out, cudaStream_t s) {
+    const size_t dyn = static_cast<size_t>(pr.nslots) * U * kTileThreads * sizeof(T);
+    static bool configured = false;          // per instantiation
+    if (!configured) {
+        cudaFuncSetAttribute(comb_eval_kernel<KIND, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(JG_EVAL_MAX_SLOTS * U * kTileThreads * sizeof(T)));
+        configured = true;
+    }
+    comb_eval_kernel<KIND, T, U><<<tile_grid(n), kTileThreads, dyn, s>>>(oa, ob, n, po, pr, out);
+    return check_launch("comb_eval_kernel");
+}
+
+template <int KIND>
+static int launch_comb_eval_dtype(int dtype, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                                  const JgEvalProgram &pr, void *out, cudaStream_t s) {
+    if (dtype == JG_F32) return launch_comb_eval<KIND, float, 4>(oa, ob, n, po, pr, out, s);
+    if (dtype == JG_F64) return launch_comb_eval<KIND, double, 2>(oa, ob, n, po, pr, out, s);
+    set_error("jg_comb_eval: compute dtype must be float32 or float64 (got %d)", dtype);
+    return -2;
+}
+
 template <int KIND>
 static int launch_gather_multi(int itemsize, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
                                const MultiCols &mc, cudaStream_t s) {
@@ -551,6 +730,38 @@ int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offs
         case JG_COMB_CROSS: return launch_gather_multi<JG_COMB_CROSS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
     }
     set_error("jg_comb_gather_multi: bad kind %d", kind);
+    return -2;
+}
+
+int jg_comb_eval(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, const int64_t *out_offsets,
+                 int dtype, const JgEvalProgram *program, void *out, void *stream) {
+    if (n <= 0) return 0;
+    JG_REQUIRE(program != nullptr && out != nullptr && offsets_a != nullptr && out_offsets != nullptr,
+               "jg_comb_eval: bad arguments");
+    JG_REQUIRE(kind != JG_COMB_CROSS || offsets_b != nullptr, "jg_comb_eval: cross needs offsets_b");
+    const JgEvalProgram &pr = *program;
+    JG_REQUIRE(pr.nins > 0 && pr.nins <= JG_EVAL_MAX_INS, "jg_comb_eval: program length %d out of range", pr.nins);
+    JG_REQUIRE(pr.nslots > 0 && pr.nslots <= JG_EVAL_MAX_SLOTS, "jg_comb_eval: %d register slots out of range", pr.nslots);
+    JG_REQUIRE(pr.result >= 0 && pr.result < pr.nslots, "jg_comb_eval: bad result slot %d", pr.result);
+    for (int i = 0; i < pr.nins; ++i) {
+        const uint32_t w = pr.ins[i];
+        const int op = w & 255, d = (w >> 8) & 255, a = (w >> 16) & 255, b = w >> 24;
+        JG_REQUIRE(eval_op_supported(op), "jg_comb_eval: step %d: operator %d cannot be fused", i, op);
+        JG_REQUIRE(d < pr.nslots, "jg_comb_eval: step %d writes slot %d of %d", i, d, pr.nslots);
+        if (op == JG_EV_CONST) JG_REQUIRE(a < JG_EVAL_MAX_CONSTS, "jg_comb_eval: step %d: constant %d", i, a);
+        else if (op >= JG_EV_LOAD_LEFT && op <= JG_EV_LOAD_POS) {
+            JG_REQUIRE(a < JG_EVAL_MAX_COLS, "jg_comb_eval: step %d: column %d", i, a);
+            const void *col = op == JG_EV_LOAD_LEFT ? pr.left[a] : (op == JG_EV_LOAD_RIGHT ? pr.right[a] : pr.pos[a]);
+            JG_REQUIRE(col != nullptr, "jg_comb_eval: step %d loads a null column", i);
+        } else JG_REQUIRE(a < pr.nslots && b < pr.nslots, "jg_comb_eval: step %d reads slots %d, %d of %d", i, a, b, pr.nslots);
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (kind) {
+        case JG_COMB_PAIRS: return launch_comb_eval_dtype<JG_COMB_PAIRS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+        case JG_COMB_DISTINCTS: return launch_comb_eval_dtype<JG_COMB_DISTINCTS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+        case JG_COMB_CROSS: return launch_comb_eval_dtype<JG_COMB_CROSS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+    }
+    set_error("jg_comb_eval: bad kind %d", kind);
     return -2;
 }
 
