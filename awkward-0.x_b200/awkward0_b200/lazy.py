@@ -7,7 +7,7 @@ plus one kernel per ufunc.  Here the columns of a combination are ``LazyArray`` 
 value of column c for every combination") and ufuncs on them build an expression DAG; nothing runs until a
 consumer needs device memory (``.tensor`` / ``data_ptr()``), at which point
 
-* an expression is compiled into a small register program and evaluated by ONE kernel (``jg_comb_eval``,
+* an expression is compiled into a small accumulator program and evaluated by ONE kernel (``jg_comb_eval``,
   csrc/jg_comb.cu) that generates the combination indices, loads the columns it needs straight from the two
   collections, applies the same operator functors as the eager kernels and writes only the result;
 * a bare leaf is gathered, together with all its still-deferred siblings, by the existing one-sweep gather
@@ -26,7 +26,8 @@ from ._lib import OP, call
 from .device import DeviceArray, empty, jg_code, runtime
 
 MAX_INS, MAX_COLS, MAX_CONSTS, MAX_SLOTS = 48, 8, 8, 10      # JG_EVAL_MAX_* of include/jagged_b200.h
-EV_LOAD_LEFT, EV_LOAD_RIGHT, EV_LOAD_POS, EV_CONST = 128, 129, 130, 131
+EV_LOAD, EV_STORE = 30, 31                                      # JG_EV_* of include/jagged_b200.h
+EV_SLOT, EV_LEFT, EV_RIGHT, EV_POS, EV_CONST = 0, 1, 2, 3, 4
 
 _FUSABLE_BINARY = ("ADD", "SUB", "MUL", "DIV", "FLOORDIV", "MOD", "POW", "MAXIMUM", "MINIMUM", "ARCTAN2", "HYPOT")
 _FUSABLE_COMPARE = ("GT", "GE", "LT", "LE", "EQ", "NE")
@@ -44,8 +45,8 @@ class JgEvalProgram(ctypes.Structure):
                 ("right", ctypes.c_void_p * MAX_COLS),
                 ("pos", ctypes.c_void_p * MAX_COLS),
                 ("consts", ctypes.c_double * MAX_CONSTS),
-                ("nins", ctypes.c_int32), ("nslots", ctypes.c_int32), ("result", ctypes.c_int32),
-                ("out_bool", ctypes.c_int32)]
+                ("nins", ctypes.c_int32), ("nslots", ctypes.c_int32), ("out_bool", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 class CombContext(object):
@@ -209,10 +210,14 @@ def try_fuse(name, operands, rdt, cdt):
 
 
 def _compile(root):
-    """Expression DAG -> (JgEvalProgram, compute dtype) or None when it does not fit the evaluator's limits."""
-    # post-order over unique nodes; operands: ("node", LazyArray op) | ("L"/"R"/"P", DeviceArray) | ("K", float)
-    order, seen, keyed = [], {}, {}
+    """Expression DAG -> (JgEvalProgram, compute dtype) or None when it does not fit the evaluator's limits.
 
+    The evaluator is an accumulator machine (csrc/jg_comb.cu:eval_program): the value being built stays in a
+    register and every step combines it with ONE operand -- a column of either collection, a P-sized column, a
+    constant or a spill slot.  A chain therefore never touches a slot; a binary node whose two inputs are both
+    compound evaluates the deeper one first (Sethi-Ullman), parks it in a slot and folds it back with the
+    `reverse` bit when it was the left input; a compound node used more than once is parked after its first
+    evaluation and re-read from its slot."""
     def key_of(x):
         if isinstance(x, LazyArray) and x._mat is None:
             if x._kind == "op":
@@ -222,86 +227,148 @@ def _compile(root):
             return ("P", x.tensor.data_ptr())
         return ("K", float(x))
 
-    stack = [(root, False)]
+    # unique nodes, use counts, dtype check (iterative: no recursion limit issues while counting)
+    uses, nodes, dtypes = {}, {}, set()
+    stack = [root]
     while stack:
-        x, done = stack.pop()
+        x = stack.pop()
         k = key_of(x)
-        if done:
-            if k not in seen:
-                seen[k] = True
-                order.append(k)
-                keyed[k] = x
+        uses[k] = uses.get(k, 0) + 1
+        if k in nodes:
             continue
-        if k in seen or k in keyed:
-            continue
-        keyed[k] = x
-        stack.append((x, True))
+        nodes[k] = x
         if k[0] == "node":
-            for y in reversed(x._args[1:]):
-                stack.append((y, False))
-    if len(order) > MAX_INS:
+            stack.extend(x._args[1:])
+        elif k[0] != "K":
+            dtypes.add(x._ldtype if isinstance(x, LazyArray) else x.dtype)
+        if len(nodes) > 4 * MAX_INS:
+            return None
+    if len(dtypes) != 1:
+        return None
+    cdt = dtypes.pop()
+    if cdt not in _FLOATS:
         return None
 
-    uses = {}
-    for k in order:
-        if k[0] == "node":
-            for y in keyed[k]._args[1:]:
-                ky = key_of(y)
-                uses[ky] = uses.get(ky, 0) + 1
-    root_key = key_of(root)
-    uses[root_key] = uses.get(root_key, 0) + 1
+    need = {}
+
+    def need_of(x):                      # spill slots the evaluation of x occupies at its peak
+        k = key_of(x)
+        if k[0] != "node":
+            return 0
+        if k not in need:
+            args = x._args[1:]
+            if len(args) == 1:
+                need[k] = need_of(args[0])
+            else:
+                a, b = need_of(args[0]), need_of(args[1])
+                compound = [key_of(y)[0] == "node" for y in args]
+                need[k] = max(a, b) if not all(compound) else (max(a, b) if a != b else a + 1)
+        return need[k]
 
     prog = JgEvalProgram()
     cols = {"L": [], "R": [], "P": []}
     consts = []
     free = list(range(MAX_SLOTS - 1, -1, -1))
-    slot = {}
-    nslots = 0
-    nins = 0
-    cdt = None
-    for k in order:
-        x = keyed[k]
+    parked = {}                          # key -> slot of a shared compound node
+    remaining = dict(uses)
+    state = {"nins": 0, "nslots": 0}
+    KIND = {"L": EV_LEFT, "R": EV_RIGHT, "P": EV_POS}
+
+    class _TooBig(Exception):
+        pass
+
+    def emit(op, kind=0, index=0, reverse=False):
+        if state["nins"] == MAX_INS:
+            raise _TooBig()
+        prog.ins[state["nins"]] = op | (kind << 8) | ((1 if reverse else 0) << 12) | (index << 16)
+        state["nins"] += 1
+
+    def alloc():
+        if not free:
+            raise _TooBig()
+        s = free.pop()
+        state["nslots"] = max(state["nslots"], s + 1)
+        return s
+
+    def direct(x):
+        """(kind, index) when x can be an operand of a step as it is, else None."""
+        k = key_of(x)
         if k[0] == "node":
-            args = x._args[1:]
-            srcs = [slot[key_of(y)] for y in args]
-            for y in args:
-                ky = key_of(y)
-                uses[ky] -= 1
-            for ky in set(key_of(y) for y in args):
-                if uses[ky] == 0:
-                    free.append(slot[ky])
-            if not free:
-                return None
-            d = free.pop()
-            a = srcs[0]
-            b = srcs[1] if len(srcs) > 1 else 0
-            word = OP[x._args[0]] | (d << 8) | (a << 16) | (b << 24)
+            if k in parked:
+                return (EV_SLOT, parked[k])
+            return None
+        if k[0] == "K":
+            if k[1] not in consts:
+                if len(consts) == MAX_CONSTS:
+                    raise _TooBig()
+                consts.append(k[1])
+            return (EV_CONST, consts.index(k[1]))
+        table = cols[k[0]]
+        if k[1] not in table:
+            if len(table) == MAX_COLS:
+                raise _TooBig()
+            table.append(k[1])
+        return (KIND[k[0]], table.index(k[1]))
+
+    def used(x):
+        """One use of x has been consumed: release the slot of a parked node after its last use."""
+        k = key_of(x)
+        remaining[k] -= 1
+        if k in parked and remaining[k] == 0:
+            free.append(parked.pop(k))
+
+    def gen(x):
+        """Emit steps that leave the value of x in the accumulator."""
+        d = direct(x)
+        if d is not None:
+            emit(EV_LOAD, d[0], d[1])
+            return
+        name, args = x._args[0], x._args[1:]
+        if len(args) == 1:
+            gen(args[0])
+            used(args[0])
+            emit(OP[name])
         else:
-            if not free:
-                return None
-            d = free.pop()
-            if k[0] == "K":
-                if k[1] not in consts:
-                    if len(consts) == MAX_CONSTS:
-                        return None
-                    consts.append(k[1])
-                word = EV_CONST | (d << 8) | (consts.index(k[1]) << 16)
+            l, r = args
+            if direct(r) is not None:
+                gen(l)
+                used(l)
+                d = direct(r)              # (again: l may have been r itself and is parked now)
+                emit(OP[name], d[0], d[1])
+                used(r)
+            elif direct(l) is not None:
+                gen(r)
+                used(r)
+                d = direct(l)
+                emit(OP[name], d[0], d[1], reverse=True)
+                used(l)
             else:
-                table = cols[k[0]]
-                if len(table) == MAX_COLS:
-                    return None
-                table.append(k[1])
-                dt = x._ldtype if isinstance(x, LazyArray) else x.dtype
-                if cdt is None:
-                    cdt = dt
-                elif dt != cdt:
-                    return None
-                word = {"L": EV_LOAD_LEFT, "R": EV_LOAD_RIGHT, "P": EV_LOAD_POS}[k[0]] | (d << 8) | ((len(table) - 1) << 16)
-        slot[k] = d
-        nslots = max(nslots, d + 1)
-        prog.ins[nins] = word
-        nins += 1
-    if cdt is None or cdt not in _FLOATS:
+                first_is_left = need_of(l) >= need_of(r)
+                first, second = (l, r) if first_is_left else (r, l)
+                gen(first)
+                k1 = key_of(first)
+                if k1 in parked:           # shared: it already sits in a slot
+                    gen(second)
+                    used(second)
+                    d = direct(first)
+                    emit(OP[name], d[0], d[1], reverse=first_is_left)
+                    used(first)
+                else:
+                    s = alloc()
+                    emit(EV_STORE, EV_SLOT, s)
+                    used(first)
+                    gen(second)
+                    used(second)
+                    emit(OP[name], EV_SLOT, s, reverse=first_is_left)
+                    free.append(s)
+        k = key_of(x)
+        if uses[k] > 1 and k not in parked:
+            parked[k] = alloc()
+            emit(EV_STORE, EV_SLOT, parked[k])
+
+    try:
+        gen(root)
+    except (_TooBig, RecursionError):
         return None
     for i, p in enumerate(cols["L"]):
         prog.left[i] = p
@@ -311,6 +378,6 @@ def _compile(root):
         prog.pos[i] = p
     for i, c in enumerate(consts):
         prog.consts[i] = c
-    prog.nins, prog.nslots, prog.result = nins, nslots, slot[root_key]
+    prog.nins, prog.nslots = state["nins"], state["nslots"]
     prog.out_bool = 1 if root._ldtype == numpy.bool_ else 0
     return prog, cdt

@@ -419,67 +419,98 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
 // pairs / distincts / cross followed by a chain of ufuncs, e.g.
 //     p = mu.pairs();  sqrt(2 * p.i0.pt * p.i1.pt * (cosh(p.i0.eta - p.i1.eta) - cos(p.i0.phi - p.i1.phi)))
 // is evaluated in ONE sweep: every output position finds its (left, right) item exactly like comb_gather2_kernel,
-// loads the columns the expression names straight from the collections and runs a small register program; the
+// loads the columns the expression names straight from the collections and runs a small program; the
 // 2 x columns x P gathered temporaries and the P-sized intermediate of every ufunc are never written.
-// The host (awkward0_b200/lazy.py) compiles the expression DAG into the program: one 32-bit word per step,
-//     op | dst << 8 | a << 16 | b << 24
-// with op a JG_OP_* code (the SAME functors as the eager kernels: jg_ops.cuh, so both paths round identically)
-// or one of the loads below.  The "registers" are per-thread columns of shared memory (slot-major, so the
-// accesses of a warp are consecutive words); every step is executed for U positions of the thread at once, which
-// amortises the decode over U results and keeps U independent dependency chains in flight.
+// The host (awkward0_b200/lazy.py) compiles the expression DAG into an ACCUMULATOR program, one 32-bit word per
+// step:   op | operand kind << 8 | reverse << 12 | operand index << 16
+// A step combines the accumulator (a register) with one operand -- a column of the left / right collection, a
+// P-sized column, a constant or a spill slot -- using the SAME functors as the eager kernels (jg_ops.cuh: both
+// paths round identically); unary steps act on the accumulator alone; JG_EV_LOAD / JG_EV_STORE move between the
+// accumulator and a spill slot (a per-thread column of shared memory) when the expression is not a chain.  Every
+// step is executed for U positions of the thread at once: the decode is amortised over U results and U
+// independent dependency chains are in flight.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int U>
-__device__ __forceinline__ void eval_program(const JgEvalProgram &pr, T *__restrict__ regs, const int64_t (&ia)[U],
-                                             const int64_t (&ib)[U], const int64_t (&ip)[U]) {
+// Positions are relative to the tile (a0 / b0: first item of the tile in the left / right collection, p0: first
+// output of the tile): IX = uint32_t on the usual path (they come from the 16-bit pair table), int64_t otherwise.
+template <typename T, int U, typename IX>
+__device__ __forceinline__ void eval_program(const JgEvalProgram &pr, T *__restrict__ slots, int64_t a0, int64_t b0,
+                                             int64_t p0, const IX (&ia)[U], const IX (&ib)[U], const IX (&ip)[U],
+                                             T (&acc)[U]) {
     constexpr int S = kTileThreads;        // stride between the U copies of one slot
-#define JG_EV_BIN(OPC)                                                                        \
-    case OPC:                                                                                 \
-        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = BinaryOp<OPC, T>::apply(ra[u * S], rb[u * S]); \
+#define JG_EV_BIN(OPC)                                                                                      \
+    case OPC:                                                                                               \
+        _Pragma("unroll") for (int u = 0; u < U; ++u)                                                       \
+            acc[u] = rev ? BinaryOp<OPC, T>::apply(b[u], acc[u]) : BinaryOp<OPC, T>::apply(acc[u], b[u]);   \
         break;
-#define JG_EV_CMP(OPC)                                                                        \
-    case OPC:                                                                                 \
-        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = T(CompareOp<OPC, T>::apply(ra[u * S], rb[u * S])); \
+#define JG_EV_CMP(OPC)                                                                                      \
+    case OPC:                                                                                               \
+        _Pragma("unroll") for (int u = 0; u < U; ++u)                                                       \
+            acc[u] = T(rev ? CompareOp<OPC, T>::apply(b[u], acc[u]) : CompareOp<OPC, T>::apply(acc[u], b[u])); \
         break;
 #define JG_EV_UN(OPC)                                                                         \
     case OPC:                                                                                 \
-        _Pragma("unroll") for (int u = 0; u < U; ++u) rd[u * S] = UnaryOp<OPC, T>::apply(ra[u * S]); \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) acc[u] = UnaryOp<OPC, T>::apply(acc[u]); \
         break;
 #pragma unroll 1
     for (int pc = 0; pc < pr.nins; ++pc) {
         const uint32_t w = pr.ins[pc];
-        const int op = w & 255, a = (w >> 16) & 255, b = w >> 24;
-        T *rd = regs + ((w >> 8) & 255) * (U * S);
-        const T *ra = regs + a * (U * S), *rb = regs + b * (U * S);
-        switch (op) {
-            case JG_EV_LOAD_LEFT: {
-                const T *col = static_cast<const T *>(pr.left[a]);
+        const int op = w & 255, kind = (w >> 8) & 15, idx = w >> 16;
+        const bool rev = (w >> 12) & 1;
+        if (op == JG_EV_STORE) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) rd[u * S] = __ldg(col + ia[u]);
-                break;
-            }
-            case JG_EV_LOAD_RIGHT: {
-                const T *col = static_cast<const T *>(pr.right[a]);
+            for (int u = 0; u < U; ++u) slots[(idx * U + u) * S] = acc[u];
+            continue;
+        }
+        T b[U];
+        if (op < JG_OP_NEG) {              // binary / comparison / JG_EV_LOAD: fetch the operand
+            switch (kind) {
+                case JG_EV_LEFT: {
+                    const T *col = static_cast<const T *>(pr.left[idx]) + a0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) rd[u * S] = __ldg(col + ib[u]);
-                break;
-            }
-            case JG_EV_LOAD_POS: {
-                const T *col = static_cast<const T *>(pr.pos[a]);
+                    for (int u = 0; u < U; ++u) b[u] = __ldg(col + ia[u]);
+                    break;
+                }
+                case JG_EV_RIGHT: {
+                    const T *col = static_cast<const T *>(pr.right[idx]) + b0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) rd[u * S] = __ldcs(col + ip[u]);
-                break;
-            }
-            case JG_EV_CONST: {
-                const T c = static_cast<T>(pr.consts[a]);
+                    for (int u = 0; u < U; ++u) b[u] = __ldg(col + ib[u]);
+                    break;
+                }
+                case JG_EV_POS: {
+                    const T *col = static_cast<const T *>(pr.pos[idx]) + p0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) rd[u * S] = c;
-                break;
+                    for (int u = 0; u < U; ++u) b[u] = __ldcs(col + ip[u]);
+                    break;
+                }
+                case JG_EV_CONST: {
+                    const T c = static_cast<T>(pr.consts[idx]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) b[u] = c;
+                    break;
+                }
+                default: {                 // JG_EV_SLOT
+#pragma unroll
+                    for (int u = 0; u < U; ++u) b[u] = slots[(idx * U + u) * S];
+                    break;
+                }
             }
-            JG_EV_BIN(JG_OP_ADD) JG_EV_BIN(JG_OP_SUB) JG_EV_BIN(JG_OP_MUL) JG_EV_BIN(JG_OP_DIV)
-            JG_EV_BIN(JG_OP_FLOORDIV) JG_EV_BIN(JG_OP_MOD) JG_EV_BIN(JG_OP_POW) JG_EV_BIN(JG_OP_MAXIMUM)
-            JG_EV_BIN(JG_OP_MINIMUM) JG_EV_BIN(JG_OP_ARCTAN2) JG_EV_BIN(JG_OP_HYPOT)
-            JG_EV_CMP(JG_OP_GT) JG_EV_CMP(JG_OP_GE) JG_EV_CMP(JG_OP_LT) JG_EV_CMP(JG_OP_LE)
-            JG_EV_CMP(JG_OP_EQ) JG_EV_CMP(JG_OP_NE)
+        }
+        if (op < JG_OP_NEG) {
+            switch (op) {                  // operand steps
+                case JG_EV_LOAD:
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc[u] = b[u];
+                    break;
+                JG_EV_BIN(JG_OP_ADD) JG_EV_BIN(JG_OP_SUB) JG_EV_BIN(JG_OP_MUL) JG_EV_BIN(JG_OP_DIV)
+                JG_EV_BIN(JG_OP_FLOORDIV) JG_EV_BIN(JG_OP_MOD) JG_EV_BIN(JG_OP_POW) JG_EV_BIN(JG_OP_MAXIMUM)
+                JG_EV_BIN(JG_OP_MINIMUM) JG_EV_BIN(JG_OP_ARCTAN2) JG_EV_BIN(JG_OP_HYPOT)
+                JG_EV_CMP(JG_OP_GT) JG_EV_CMP(JG_OP_GE) JG_EV_CMP(JG_OP_LT) JG_EV_CMP(JG_OP_LE)
+                JG_EV_CMP(JG_OP_EQ) JG_EV_CMP(JG_OP_NE)
+                default: break;            // rejected on the host (eval_op_class)
+            }
+            continue;
+        }
+        switch (op) {                      // unary steps
             JG_EV_UN(JG_OP_NEG) JG_EV_UN(JG_OP_ABS) JG_EV_UN(JG_OP_SQRT) JG_EV_UN(JG_OP_EXP) JG_EV_UN(JG_OP_LOG)
             JG_EV_UN(JG_OP_SIN) JG_EV_UN(JG_OP_COS) JG_EV_UN(JG_OP_TAN) JG_EV_UN(JG_OP_SINH) JG_EV_UN(JG_OP_COSH)
             JG_EV_UN(JG_OP_TANH) JG_EV_UN(JG_OP_SQUARE) JG_EV_UN(JG_OP_CAST) JG_EV_UN(JG_OP_ARCSINH)
@@ -487,7 +518,7 @@ __device__ __forceinline__ void eval_program(const JgEvalProgram &pr, T *__restr
             JG_EV_UN(JG_OP_LOG10) JG_EV_UN(JG_OP_EXP2) JG_EV_UN(JG_OP_ARCSIN) JG_EV_UN(JG_OP_ARCCOS)
             JG_EV_UN(JG_OP_ARCTAN) JG_EV_UN(JG_OP_LOG2) JG_EV_UN(JG_OP_LOG1P) JG_EV_UN(JG_OP_EXPM1)
             JG_EV_UN(JG_OP_RECIPROCAL)
-            default: break;      // rejected on the host (eval_op_supported)
+            default: break;      // rejected on the host (eval_op_class)
         }
     }
 #undef JG_EV_BIN
@@ -495,22 +526,60 @@ __device__ __forceinline__ void eval_program(const JgEvalProgram &pr, T *__restr
 #undef JG_EV_UN
 }
 
-static bool eval_op_supported(int op) {
-    if (op >= JG_EV_LOAD_LEFT && op <= JG_EV_CONST) return true;
-    if (op >= JG_OP_ADD && op <= JG_OP_HYPOT) return true;
-    if (op >= JG_OP_GT && op <= JG_OP_NE) return true;
+// 0: not supported, 1: takes an operand (binary, comparison, load), 2: unary, 3: store
+static int eval_op_class(int op) {
+    if (op == JG_EV_LOAD) return 1;
+    if (op == JG_EV_STORE) return 3;
+    if (op >= JG_OP_ADD && op <= JG_OP_HYPOT) return 1;
+    if (op >= JG_OP_GT && op <= JG_OP_NE) return 1;
     switch (op) {
         case JG_OP_NEG: case JG_OP_ABS: case JG_OP_SQRT: case JG_OP_EXP: case JG_OP_LOG: case JG_OP_SIN:
         case JG_OP_COS: case JG_OP_TAN: case JG_OP_SINH: case JG_OP_COSH: case JG_OP_TANH: case JG_OP_SQUARE:
         case JG_OP_CAST: case JG_OP_ARCSINH: case JG_OP_FLOOR: case JG_OP_CEIL: case JG_OP_RINT: case JG_OP_SIGN:
         case JG_OP_LOG10: case JG_OP_EXP2: case JG_OP_ARCSIN: case JG_OP_ARCCOS: case JG_OP_ARCTAN: case JG_OP_LOG2:
         case JG_OP_LOG1P: case JG_OP_EXPM1: case JG_OP_RECIPROCAL:
-            return true;
+            return 2;
     }
-    return false;
+    return 0;
 }
 
-template <int KIND, typename T, int U>
+// The batches of one tile: a batch is U rows of `stride` consecutive positions and thread t owns position t of
+// every row.  Full batches use stride = 256; the last batch shrinks the rows (to a multiple of 32) so that the
+// warps that stay in it have all U positions valid and the others leave: a nearly empty tail costs what it holds,
+// not a full batch.  `resolve(q, ia, ib)` gives the tile-relative positions of the two items of output q.
+template <typename T, int U, typename IX, class Resolve>
+__device__ __forceinline__ void eval_tile(const JgEvalProgram &pr, T *__restrict__ slots, int64_t a0, int64_t b0,
+                                          int64_t p0, int64_t total, void *__restrict__ out, Resolve resolve) {
+#pragma unroll 1
+    for (int64_t base = 0; base < total; base += U * kTileThreads) {
+        const int64_t left = total - base;
+        const int stride = left >= U * kTileThreads ? kTileThreads
+                                                    : static_cast<int>(((left + U - 1) / U + 31) & ~int64_t(31));
+        if (static_cast<int>(threadIdx.x) >= stride) break;          // warp-uniform (stride is a multiple of 32)
+        IX ia[U], ib[U], ip[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int64_t q = base + u * stride + threadIdx.x;
+            if (q >= total) q = total - 1;            // spare lanes of the last row recompute the last position
+            ip[u] = static_cast<IX>(q);
+            resolve(q, ia[u], ib[u]);
+        }
+        T acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = T(0);
+        eval_program<T, U, IX>(pr, slots, a0, b0, p0, ia, ib, ip, acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = base + u * stride + threadIdx.x;
+            if (q < total) {
+                if (pr.out_bool) __stcs(static_cast<uint8_t *>(out) + p0 + q, static_cast<uint8_t>(acc[u] != T(0)));
+                else __stcs(static_cast<T *>(out) + p0 + q, acc[u]);
+            }
+        }
+    }
+}
+
+template <int KIND, typename T, int U>       // U: positions per thread and step on the pair-table path
 __global__ void __launch_bounds__(kTileThreads)
 comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
                  const int64_t *__restrict__ out_offsets, const __grid_constant__ JgEvalProgram pr,
@@ -519,8 +588,8 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     __shared__ int64_t s_oa[kTileEvents + 1];
     __shared__ int64_t s_ob[kTileEvents + 1];
     __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
-    extern __shared__ __align__(16) unsigned char s_dyn[];        // nslots x U x 256 values of T
-    T *regs = reinterpret_cast<T *>(s_dyn) + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char s_dyn[];        // spill slots: nslots x U x 256 values of T
+    T *slots = reinterpret_cast<T *>(s_dyn) + threadIdx.x;
     EventTile pt, ta, tb;
     pt.load(s_po, out_offsets, n, blockIdx.x);
     ta.load(s_oa, offsets_a, n, blockIdx.x);
@@ -528,45 +597,26 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     const int64_t total = p1 - p0;
     if (total <= 0) return;
-    uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-    const bool fast = build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob);
-    bool table = false;
-    if (!fast) {
-        table = total <= kCombPositions;
-        if (table) build_owner_table(s_own, pt, static_cast<int>(total));
-    }
     const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
-    const T *res = regs + pr.result * (U * kTileThreads);
-#pragma unroll 1
-    for (int64_t qb = threadIdx.x; qb < total; qb += U * kTileThreads) {
-        int64_t ia[U], ib[U], ip[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int64_t q = qb + u * kTileThreads;
-            if (q >= total) q = total - 1;            // the spare lanes of the last batch recompute the last position
-            ip[u] = p0 + q;
-            if (fast) {
-                ia[u] = a0 + s_l[q];
-                ib[u] = b0 + s_r[q];
-            } else {
-                const int ev = table ? static_cast<int>(s_own[q]) : pt.find_event(p0 + q);
-                const int64_t na = s_oa[ev + 1] - s_oa[ev];
-                const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
-                CombIndex r = unrank<KIND>(p0 + q - s_po[ev], na, nb, 2);
-                ia[u] = s_oa[ev] + r.v[0];
-                ib[u] = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
-            }
-        }
-        eval_program<T, U>(pr, regs, ia, ib, ip);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t q = qb + u * kTileThreads;
-            if (q < total) {
-                if (pr.out_bool) __stcs(static_cast<uint8_t *>(out) + p0 + q, static_cast<uint8_t>(res[u * kTileThreads] != T(0)));
-                else __stcs(static_cast<T *>(out) + p0 + q, res[u * kTileThreads]);
-            }
-        }
+    uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
+    if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+        eval_tile<T, U, uint32_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, uint32_t &ia, uint32_t &ib) {
+            ia = s_l[q];
+            ib = s_r[q];
+        });
+        return;
     }
+    // long events: owner table (binary search for very long runs) + un-ranking, 64-bit positions
+    const bool table = total <= kCombPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(total));
+    eval_tile<T, 2, int64_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, int64_t &ia, int64_t &ib) {
+        const int ev = table ? static_cast<int>(s_own[q]) : pt.find_event(p0 + q);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p0 + q - s_po[ev], na, nb, 2);
+        ia = s_oa[ev] - a0 + r.v[0];
+        ib = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) - b0 + r.v[1];
+    });
 }
 
 template <int KIND, typename T, int U>
@@ -576,7 +626,7 @@ static int launch_comb_eval(const int64_t *oa, const int64_t *ob, int64_t n, con
     static bool configured = false;          // per instantiation
     if (!configured) {
         cudaFuncSetAttribute(comb_eval_kernel<KIND, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(JG_EVAL_MAX_SLOTS * U * kTileThreads * sizeof(T)));
+                             static_cast<int>(JG_EVAL_MAX_SLOTS * U * kTileThreads * sizeof(T)));   // 80 KB
         configured = true;
     }
     comb_eval_kernel<KIND, T, U><<<tile_grid(n), kTileThreads, dyn, s>>>(oa, ob, n, po, pr, out);
@@ -586,8 +636,8 @@ static int launch_comb_eval(const int64_t *oa, const int64_t *ob, int64_t n, con
 template <int KIND>
 static int launch_comb_eval_dtype(int dtype, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
                                   const JgEvalProgram &pr, void *out, cudaStream_t s) {
-    if (dtype == JG_F32) return launch_comb_eval<KIND, float, 4>(oa, ob, n, po, pr, out, s);
-    if (dtype == JG_F64) return launch_comb_eval<KIND, double, 2>(oa, ob, n, po, pr, out, s);
+    if (dtype == JG_F32) return launch_comb_eval<KIND, float, 8>(oa, ob, n, po, pr, out, s);
+    if (dtype == JG_F64) return launch_comb_eval<KIND, double, 4>(oa, ob, n, po, pr, out, s);
     set_error("jg_comb_eval: compute dtype must be float32 or float64 (got %d)", dtype);
     return -2;
 }
@@ -741,20 +791,24 @@ int jg_comb_eval(int kind, const int64_t *offsets_a, const int64_t *offsets_b, i
     JG_REQUIRE(kind != JG_COMB_CROSS || offsets_b != nullptr, "jg_comb_eval: cross needs offsets_b");
     const JgEvalProgram &pr = *program;
     JG_REQUIRE(pr.nins > 0 && pr.nins <= JG_EVAL_MAX_INS, "jg_comb_eval: program length %d out of range", pr.nins);
-    JG_REQUIRE(pr.nslots > 0 && pr.nslots <= JG_EVAL_MAX_SLOTS, "jg_comb_eval: %d register slots out of range", pr.nslots);
-    JG_REQUIRE(pr.result >= 0 && pr.result < pr.nslots, "jg_comb_eval: bad result slot %d", pr.result);
+    JG_REQUIRE(pr.nslots >= 0 && pr.nslots <= JG_EVAL_MAX_SLOTS, "jg_comb_eval: %d spill slots out of range", pr.nslots);
     for (int i = 0; i < pr.nins; ++i) {
         const uint32_t w = pr.ins[i];
-        const int op = w & 255, d = (w >> 8) & 255, a = (w >> 16) & 255, b = w >> 24;
-        JG_REQUIRE(eval_op_supported(op), "jg_comb_eval: step %d: operator %d cannot be fused", i, op);
-        JG_REQUIRE(d < pr.nslots, "jg_comb_eval: step %d writes slot %d of %d", i, d, pr.nslots);
-        if (op == JG_EV_CONST) JG_REQUIRE(a < JG_EVAL_MAX_CONSTS, "jg_comb_eval: step %d: constant %d", i, a);
-        else if (op >= JG_EV_LOAD_LEFT && op <= JG_EV_LOAD_POS) {
-            JG_REQUIRE(a < JG_EVAL_MAX_COLS, "jg_comb_eval: step %d: column %d", i, a);
-            const void *col = op == JG_EV_LOAD_LEFT ? pr.left[a] : (op == JG_EV_LOAD_RIGHT ? pr.right[a] : pr.pos[a]);
-            JG_REQUIRE(col != nullptr, "jg_comb_eval: step %d loads a null column", i);
-        } else JG_REQUIRE(a < pr.nslots && b < pr.nslots, "jg_comb_eval: step %d reads slots %d, %d of %d", i, a, b, pr.nslots);
+        const int op = w & 255, kind = (w >> 8) & 15, idx = w >> 16;
+        const int cls = eval_op_class(op);
+        JG_REQUIRE(cls != 0, "jg_comb_eval: step %d: operator %d cannot be fused", i, op);
+        if (cls == 3) JG_REQUIRE(idx < pr.nslots, "jg_comb_eval: step %d stores to slot %d of %d", i, idx, pr.nslots);
+        if (cls != 1) continue;
+        switch (kind) {
+            case JG_EV_SLOT: JG_REQUIRE(idx < pr.nslots, "jg_comb_eval: step %d reads slot %d of %d", i, idx, pr.nslots); break;
+            case JG_EV_LEFT: JG_REQUIRE(idx < JG_EVAL_MAX_COLS && pr.left[idx], "jg_comb_eval: step %d: bad left column %d", i, idx); break;
+            case JG_EV_RIGHT: JG_REQUIRE(idx < JG_EVAL_MAX_COLS && pr.right[idx], "jg_comb_eval: step %d: bad right column %d", i, idx); break;
+            case JG_EV_POS: JG_REQUIRE(idx < JG_EVAL_MAX_COLS && pr.pos[idx], "jg_comb_eval: step %d: bad positional column %d", i, idx); break;
+            case JG_EV_CONST: JG_REQUIRE(idx < JG_EVAL_MAX_CONSTS, "jg_comb_eval: step %d: bad constant %d", i, idx); break;
+            default: JG_REQUIRE(false, "jg_comb_eval: step %d: bad operand kind %d", i, kind);
+        }
     }
+    JG_REQUIRE(eval_op_class(pr.ins[0] & 255) == 1 && (pr.ins[0] & 255) == JG_EV_LOAD, "jg_comb_eval: a program starts with a load");
     cudaStream_t s = as_stream(stream);
     switch (kind) {
         case JG_COMB_PAIRS: return launch_comb_eval_dtype<JG_COMB_PAIRS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);

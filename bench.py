@@ -473,6 +473,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     mu_pt = ak.asdevice(rng.exponential(20.0, Mmu).astype(np.float32))
     Mel = int(el_off[-1])
     el_pt = ak.asdevice(rng.exponential(20.0, Mel).astype(np.float32))
+    mu_eta, mu_phi = ak.asdevice(rng.uniform(-2.4, 2.4, Mmu).astype(np.float32)), ak.asdevice(rng.uniform(-np.pi, np.pi, Mmu).astype(np.float32))
+    el_eta, el_phi = ak.asdevice(rng.uniform(-2.4, 2.4, Mel).astype(np.float32)), ak.asdevice(rng.uniform(-np.pi, np.pi, Mel).astype(np.float32))
     wsc, wscb = runtime.workspace(Nc)
     for kind, name, ob in ((_lib.COMB_PAIRS, "pairs", None), (_lib.COMB_DISTINCTS, "distincts", None), (_lib.COMB_CROSS, "cross", el_off)):
         poff = empty(Nc + 1, np.int64)
@@ -493,6 +495,20 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
             _vp(l), _vp(r), st()))
         del l, r
         table["arg" + name + "_fill"]["pairs"] = P
+        # SURVEY 8d "pair mass fused from index generation": three columns per side, one result column; the program
+        # is what awkward0_b200/lazy.py compiles for sqrt(2 pt1 pt2 (cosh(eta1 - eta2) - cos(phi1 - phi2)))
+        if kind != _lib.COMB_DISTINCTS:
+            from awkward0_b200 import lazy
+            ctx = lazy.CombContext(kind, mu_off, ob, Nc, ak.DeviceArray(poff), P)
+            other = (el_pt, el_eta, el_phi) if ob is not None else (mu_pt, mu_eta, mu_phi)
+            (pt1, eta1, phi1), (pt2, eta2, phi2) = [ctx.leaf("L", c) for c in (mu_pt, mu_eta, mu_phi)], [ctx.leaf("R", c) for c in other]
+            prog, _ = lazy._compile(np.sqrt(2 * pt1 * pt2 * (np.cosh(eta1 - eta2) - np.cos(phi1 - phi2))))
+            mass_out = empty(P, np.float32)
+            add(name + "_mass_fused_f32", nin + 8 * Nc + 3 * 4 * Mmu + (3 * 4 * Mel if ob is not None else 0) + 4 * P, P,
+                lambda: _lib.call("jg_comb_eval", kind, mu_off.data_ptr(), obp, Nc, _vp(poff), _lib.JG_F32, ctypes.byref(prog),
+                                  _vp(mass_out), st()))
+            table[name + "_mass_fused_f32"]["note"] = "issue-bound (14-step program incl. cosh, cos, sqrt per pair), not HBM-bound"
+            del mass_out
     return table
 
 

@@ -258,15 +258,23 @@ int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offs
 /* Fused value form + ufunc chain ("pair mass fused from index generation"): replaces, for ONE result
  * column, the sequence  pairs()/distincts()/cross() (jagged.py:1232-1367) -> column access (table.py:587-600) ->
  * a chain of numpy ufuncs through JaggedArray.__array_ufunc__ (jagged.py:944-1051) that the reference runs as one
- * numpy pass (and one P-sized temporary) per step.  The expression is a small register program, one 32-bit word per
- * step:  op | dst << 8 | a << 16 | b << 24  where op is a JG_OP_* arithmetic / comparison / unary code (a, b: source
- * slots) or one of the JG_EV_* loads (a: column or constant index).  All columns and the result have the compute
- * dtype (JG_F32 or JG_F64); with out_bool the result slot (0 / 1 from a comparison) is stored as one byte.        */
+ * numpy pass (and one P-sized temporary) per step.  The expression is an accumulator program, one 32-bit word per
+ * step:  op | operand kind << 8 | reverse << 12 | operand index << 16
+ *   op = a binary / comparison JG_OP_* code: acc = op(acc, operand)  (reverse: op(operand, acc))
+ *      = a unary JG_OP_* code             : acc = op(acc)
+ *      = JG_EV_LOAD : acc = operand        JG_EV_STORE : slot[index] = acc
+ * All columns and the result have the compute dtype (JG_F32 or JG_F64); with out_bool the final accumulator
+ * (0 / 1 from a comparison) is stored as one byte.  The first step must be a JG_EV_LOAD.                          */
 enum {
-    JG_EV_LOAD_LEFT = 128,   /* slot <- left[a][position of the combination's first item]   */
-    JG_EV_LOAD_RIGHT = 129,  /* slot <- right[a][position of the combination's second item] */
-    JG_EV_LOAD_POS = 130,    /* slot <- pos[a][output position] (an already materialised P-sized column) */
-    JG_EV_CONST = 131        /* slot <- consts[a] */
+    JG_EV_LOAD = 30,         /* (unused JG_OP_* codes below the unary range) */
+    JG_EV_STORE = 31
+};
+enum {
+    JG_EV_SLOT = 0,          /* operand = spill slot[index]                                               */
+    JG_EV_LEFT = 1,          /* operand = left[index][position of the combination's first item]          */
+    JG_EV_RIGHT = 2,         /* operand = right[index][position of the combination's second item]        */
+    JG_EV_POS = 3,           /* operand = pos[index][output position] (an already materialised P-sized column) */
+    JG_EV_CONST = 4          /* operand = consts[index]                                                   */
 };
 #define JG_EVAL_MAX_INS 48
 #define JG_EVAL_MAX_COLS 8
@@ -278,7 +286,7 @@ typedef struct JgEvalProgram {
     const void *right[JG_EVAL_MAX_COLS];  /* ... the right collection's content (PAIRS / DISTINCTS: the same collection) */
     const void *pos[JG_EVAL_MAX_COLS];    /* device pointers, indexed by output position */
     double consts[JG_EVAL_MAX_CONSTS];
-    int32_t nins, nslots, result, out_bool;
+    int32_t nins, nslots, out_bool, reserved;
 } JgEvalProgram;
 int jg_comb_eval(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, const int64_t *out_offsets,
                  int dtype, const JgEvalProgram *program /* host */, void *out, void *stream);
