@@ -12,7 +12,8 @@ from .table import Table  # noqa: F401
 from .jagged import JaggedArray  # noqa: F401
 from .arrow import fromarrow, toarrow  # noqa: F401
 from .ingest import StreamedJaggedArray  # noqa: F401
+from .persist import load, save  # noqa: F401  (.awkd files: awkward0.save / awkward0.load)
 from . import lazy  # noqa: F401  (deferred pair columns + fused ufunc chains; lazy.ENABLED[0] = False switches fusion off)
 
 __version__ = "0.1.0"
-__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray"]
+__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray", "save", "load"]
