@@ -67,6 +67,10 @@ def _finish(out, kdt, rdt, fix):
 
 def _lazy():
     from . import lazy          # lazy.py imports device.py only; imported late to keep the module graph acyclic
+    if not lazy._UFUNC_OF:
+        for table in (_UNARY, _BINARY):
+            for uf, nm in table.items():
+                lazy._UFUNC_OF.setdefault(nm, uf)
     return lazy
 
 

@@ -37,6 +37,10 @@ _FUSABLE_UNARY = ("NEG", "ABS", "SQRT", "EXP", "LOG", "SIN", "COS", "TAN", "SINH
 _FLOATS = (numpy.dtype(numpy.float32), numpy.dtype(numpy.float64))
 
 ENABLED = [True]          # tests switch fusion off to compare the two paths
+_UNCHECKED_SIZE = 20      # expression trees up to this size are not test-compiled when they grow by one node (a
+                          # program has at most 1.5 steps per tree node; the rare misfit -- more than 8 distinct
+                          # columns of one side -- is caught when the value is needed, see LazyArray._materialise)
+_UFUNC_OF = {}            # operator name -> numpy ufunc, filled by _ufunc on import
 
 
 class JgEvalProgram(ctypes.Structure):
@@ -105,10 +109,11 @@ class LazyArray(DeviceArray):
     """A P-sized column that is computed on first use.  kind "L"/"R": args = (source column,) ; kind "op":
     args = (operator name, operand, ...) with operands LazyArray (same context) / DeviceArray (P-sized) / scalar."""
 
-    __slots__ = ("_ctx", "_kind", "_args", "_ldtype", "_mat")
+    __slots__ = ("_ctx", "_kind", "_args", "_ldtype", "_mat", "_size")
 
-    def __init__(self, ctx, kind, args, dtype):
+    def __init__(self, ctx, kind, args, dtype, size=1):
         self._ctx, self._kind, self._args, self._ldtype, self._mat = ctx, kind, args, numpy.dtype(dtype), None
+        self._size = size                 # nodes of the expression TREE below (an upper bound of the program length)
 
     # -- what DeviceArray keeps in slots is computed here
     @property
@@ -160,8 +165,23 @@ class LazyArray(DeviceArray):
             self._ctx.gather_leaves()
             return
         prog = _compile(self)
-        if prog is None:                               # cannot happen for nodes built by try_fuse; be safe
-            raise RuntimeError("deferred expression cannot be compiled")
+        if prog is None:
+            # does not fit the evaluator after all (e.g. more than 8 distinct columns of one side): evaluate the
+            # operands (each may still fuse) and run this one step as an eager kernel -- same functors, same result
+            from . import _ufunc
+            args = list(self._args[1:])
+            for x in args:
+                if isinstance(x, LazyArray):
+                    x.tensor
+            ufunc = _UFUNC_OF[self._args[0]]
+            ENABLED[0], was = False, ENABLED[0]
+            try:
+                out = _ufunc.unary(ufunc, args[0]) if len(args) == 1 else _ufunc.binary(ufunc, args[0], args[1])
+            finally:
+                ENABLED[0] = was
+            self._mat = out.tensor
+            self._args = None
+            return
         ctx = self._ctx
         out = empty(ctx.total, self._ldtype)
         if ctx.total > 0:
@@ -195,15 +215,18 @@ def try_fuse(name, operands, rdt, cdt):
         return None
     if cdt not in _FLOATS or not (rdt == cdt or (compare and rdt == numpy.bool_)):
         return None
+    size = 1
     for x in operands:
         if isinstance(x, DeviceArray) and (x.dtype != cdt or len(x) != ctx.total):
             return None
-    node = LazyArray(ctx, "op", (name,) + tuple(operands), rdt)
-    if _compile(node) is None:
+        size += x._size if isinstance(x, LazyArray) and x._mat is None else 1
+    node = LazyArray(ctx, "op", (name,) + tuple(operands), rdt, size)
+    if size > _UNCHECKED_SIZE and _compile(node) is None:
         # too long / too many columns or live values: cut here -- the deferred operands become P-sized columns
         for x in operands:
             if isinstance(x, LazyArray):
                 x._t
+        node._size = 1 + len(operands)
         if _compile(node) is None:
             return None
     return node

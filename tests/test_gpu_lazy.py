@@ -223,3 +223,22 @@ def test_fused_mass_full_size(ak):
     # the same sum two ways: fused on pairs (self pairs contribute 0) and fused on distincts
     s1, s2 = float((mm * mm).sum().sum()), float((md * md).sum().sum())
     assert abs(s1 - s2) <= 1e-4 * abs(s2)
+
+
+def test_wide_expression_falls_back_stepwise(ak):
+    """Ten distinct columns of one side: the program does not fit (8 per side); the value is still right."""
+    rng = np.random.default_rng(8)
+    counts = rng.poisson(2.0, 5000).astype(np.int64)
+    m = int(counts.sum())
+    cols = [rng.normal(size=m).astype(np.float32) for _ in range(10)]
+    first = ak.JaggedArray.fromcounts(counts, cols[0])
+    rec = ak.JaggedArray.zip(**dict(("c%d" % i, ak.JaggedArray.fromoffsets(first.offsets, c) if i else first) for i, c in enumerate(cols)))
+    p = rec.pairs()
+    e = p.i0.c0
+    for i in range(1, 10):
+        e = e + p.i0["c%d" % i]
+    poff, left, _ = O.pairs(O.counts2offsets(counts), np.arange(m))
+    want = cols[0][left]
+    for c in cols[1:]:
+        want = want + c[left]
+    assert same(e.content.get(), want)

@@ -167,3 +167,15 @@ def test_register_pressure_is_bounded():
     prog, _ = lazy._compile(bal)
     assert prog.nslots <= 3
     assert np.array_equal(emulate(prog, np.float32, cols, ia, ib), wbal)
+
+
+def test_wide_expression_is_caught_when_needed_not_when_built():
+    """More than 8 distinct columns of one side do not fit one program: building stays cheap (no test-compile for
+    small trees) and the compiler says so, which makes LazyArray._materialise evaluate the last step eagerly."""
+    ctx, ia, ib, cols, leaf = make_ctx(np.float32)
+    e = leaf("L")[0]
+    for i in range(9):
+        e = e + leaf("L")[0]
+    assert e.deferred and e._size <= lazy._UNCHECKED_SIZE
+    assert lazy._compile(e) is None                      # 10 left columns
+    assert lazy._compile(e._args[1]) is None and lazy._compile(e._args[1]._args[1]) is not None      # 9 / 8 columns
