@@ -72,7 +72,7 @@ PROTOTYPES = {
     "jg_segargminmax": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_check_same_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "jg_index_gather": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "jg_flat_compact": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),

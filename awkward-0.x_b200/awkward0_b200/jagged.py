@@ -1038,6 +1038,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         mask = head._content
         mask_shift = head._first - first
         new_offsets = empty(n + 1, INDEXTYPE)
+        new_counts = empty(n, INDEXTYPE)           # written by the same sweep: `.counts` of the result costs nothing
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
         columns = []
@@ -1045,14 +1046,17 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         def select(col):
             out = empty(last - first, col.dtype)
             call("jg_mask_select", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
-                 _vp(out), _vp(new_offsets), _vp(scal), ws, wsb, runtime.stream())
+                 _vp(out), _vp(new_offsets), _vp(new_counts) if not columns else ctypes.c_void_p(0), _vp(scal), ws, wsb,
+                 runtime.stream())
             columns.append(out)
             return out
 
         picked = a._map_content(select)
         total, _, _ = runtime.read(scal)
         content = a._map_content(lambda t: DeviceArray(t[:total], _TORCH_NP(t)), picked)
-        return self._make(DeviceArray(new_offsets, INDEXTYPE), content, total)
+        out = self._make(DeviceArray(new_offsets, INDEXTYPE), content, total)
+        out._counts = DeviceArray(new_counts, INDEXTYPE)
+        return out
 
     def _getitem_jagged_int(self, head):
         """jagged.py:541-560 -> jg_index_gather."""

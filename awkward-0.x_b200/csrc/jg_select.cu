@@ -60,7 +60,8 @@ template <typename V, int KM>     // KM = positions a tile may stage
 __global__ void __launch_bounds__(kTileThreads)
 mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask, int64_t mask_shift,
                  const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
-                 int64_t *__restrict__ new_offsets, const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
+                 int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
+                 const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
@@ -139,9 +140,14 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
             run += __popc(b);
         }
         __syncthreads();
+        // per-event new offsets -- and counts, which every later step asks for (jagged.py:383-388), for one more
+        // shared-memory read instead of a 16N-byte pass of their own
 #pragma unroll 1
-        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
-            new_offsets[tile.event0 + ev] = base + s_pfx[s_off[ev] - e0];
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+            const int first = s_pfx[s_off[ev] - e0];
+            new_offsets[tile.event0 + ev] = base + first;
+            if (new_counts) new_counts[tile.event0 + ev] = static_cast<int>(s_pfx[s_off[ev + 1] - e0]) - first;
+        }
         return;
     }
 
@@ -172,6 +178,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
         if (ev < tile.nev) {
             int64_t w = base + excl + (q ? c[0] : 0);
             new_offsets[tile.event0 + ev] = w;
+            if (new_counts) new_counts[tile.event0 + ev] = c[q];
             for (int64_t j = a[q]; j < b[q]; ++j) {
                 if (mv[j] != 0) out[w++] = cv[j];
             }
@@ -345,8 +352,8 @@ static int carve_tile_ws(void *ws, size_t ws_bytes, int64_t ntiles, TileScanWs &
 
 template <typename V, int KM>
 static int launch_mask_select(const void *content, const uint8_t *mask, int64_t mask_shift, const int64_t *offsets,
-                              int64_t n, void *out, int64_t *new_offsets, int64_t *total, void *ws, size_t ws_bytes,
-                              cudaStream_t s) {
+                              int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts, int64_t *total, void *ws,
+                              size_t ws_bytes, cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
@@ -359,8 +366,8 @@ static int launch_mask_select(const void *content, const uint8_t *mask, int64_t 
     rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
     if (rc) return rc;
     mask_fill_kernel<V, KM><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
-        static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets, t.bases,
-        static_cast<uint32_t>(ntiles));
+        static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets, new_counts,
+        t.bases, static_cast<uint32_t>(ntiles));
     return check_launch("mask_fill_kernel");
 }
 
@@ -389,15 +396,15 @@ using namespace jg;
 extern "C" {
 
 int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
-                   const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *total, void *ws,
-                   size_t ws_bytes, void *stream) {
+                   const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                   int64_t *total, void *ws, size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
     cudaStream_t s = as_stream(stream);
     switch (itemsize) {
-        case 1: return launch_mask_select<uint8_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 2: return launch_mask_select<uint16_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 4: return launch_mask_select<uint32_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
-        case 8: return launch_mask_select<uint64_t, 3584>(content, mask, mask_shift, offsets, n, out, new_offsets, total, ws, ws_bytes, s);
+        case 1: return launch_mask_select<uint8_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        case 2: return launch_mask_select<uint16_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        case 4: return launch_mask_select<uint32_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        case 8: return launch_mask_select<uint64_t, 3584>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
     }
     set_error("jg_mask_select: unsupported itemsize %d", itemsize);
     return -2;

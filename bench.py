@@ -288,7 +288,7 @@ def run_gpu(args):
     peaks = load_peaks()
     roof = None
     if ops:
-        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "greater_f32", "mask_select_f32", "offsets2counts"]
+        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "greater_f32", "mask_select_f32"]       # (the selection writes its counts itself)
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
         traffic = None
         try:
@@ -412,10 +412,11 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         ctypes.c_double(THRESHOLD), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(mask), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st()))
     sel = empty(M, np.float32)
     noff = empty(N + 1, np.int64)
-    _lib.call("jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(scal), ws, wsb, st())
+    ncnt = empty(N, np.int64)            # the result's counts, written by the same sweep
+    _lib.call("jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
     K = int(scal.cpu()[0])
-    add("mask_select_f32", v * M + M + 8 * N + v * K + 8 * N, M, lambda: _lib.call(
-        "jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(scal), ws, wsb, st()))
+    add("mask_select_f32", v * M + M + 8 * N + v * K + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st()))
     del sel, mask
     # leading-object gather a[a.argmax()]
     lead = a.argmax()
@@ -460,8 +461,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         "jg_binary", _lib.OP["GT"], pt64.data_ptr(), _lib.JG_F64, ctypes.c_void_p(0), 0, _lib.RHS_SCALAR,
         ctypes.c_double(THRESHOLD), ctypes.c_int64(0), 0, _lib.JG_F64, _vp(mask64), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st()))
     sel64 = empty(M, np.float64)
-    add("mask_select_f64", 8 * M + M + 8 * N + 8 * K + 8 * N, M, lambda: _lib.call(
-        "jg_mask_select", pt64.data_ptr(), 8, _vp(mask64), 0, off.data_ptr(), N, _vp(sel64), _vp(noff), _vp(scal), ws, wsb, st()))
+    add("mask_select_f64", 8 * M + M + 8 * N + 8 * K + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_mask_select", pt64.data_ptr(), 8, _vp(mask64), 0, off.data_ptr(), N, _vp(sel64), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st()))
     del pt64, out64, aoff64, aidx64, mask64, sel64
 
     # combinatorics on a dimuon-like shard (BASELINE configs[3]: Poisson(2) counts)

@@ -151,7 +151,8 @@ int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int6
  * mask_shift = mask_offsets[0] - offsets[0] re-bases a mask whose content starts elsewhere.
  * out must hold offsets[n]-offsets[0] items (upper bound); *total receives K.                                     */
 int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
-                   const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *total,
+                   const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                   int64_t *new_counts /* n entries, may be NULL: the result's counts for free */, int64_t *total,
                    void *ws, size_t ws_bytes, void *stream);
 /* counts of two layouts must agree (jagged.py:911-912): raises JG_ST_COUNTS_MISMATCH                               */
 int jg_check_same_counts(const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, int32_t *status,
