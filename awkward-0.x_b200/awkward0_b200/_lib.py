@@ -73,6 +73,7 @@ PROTOTYPES = {
     "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_compare_select": (_i, [_vp, _i, _vp, _i, _i, _d, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_check_same_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "jg_index_gather": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "jg_flat_compact": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -107,7 +108,7 @@ def check(rc, what):
 # kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
 LAUNCHES = [0]
 _KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
-            "jg_mask_select": 3, "jg_segargminmax_dense": 3, "jg_flat_compact": 2}
+            "jg_mask_select": 3, "jg_compare_select": 3, "jg_segargminmax_dense": 3, "jg_flat_compact": 2}
 
 
 def call(name, *args):

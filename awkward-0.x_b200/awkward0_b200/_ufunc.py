@@ -146,6 +146,7 @@ def put(target, index, values, skip_negative=False):
     dt = target.dtype
     if len(index) == 0:
         return
+    _lazy().flush_all()          # deferred values are computed from the data as it was when they were written
     if isinstance(values, DeviceArray):
         if len(values) != len(index):
             raise ValueError("shape mismatch: value array of shape ({0},) could not be broadcast to indexing result of shape ({1},)".format(len(values), len(index)))
@@ -218,6 +219,10 @@ def binary(ufunc, lhs, rhs, offsets=None, nevents=0, parent_side=None):
     rdt, cdt = result_dtypes(ufunc, [lhs, rhs])
     if parent_side is None and (isinstance(lhs, _lazy().LazyArray) or isinstance(rhs, _lazy().LazyArray)):
         node = _lazy().try_fuse(name, [lhs, rhs], rdt, cdt)
+        if node is not None:
+            return node
+    if parent_side is None and name in _COMPARE:
+        node = _lazy().try_compare(name, lhs, rhs, cdt)
         if node is not None:
             return node
     kcdt, kdt, fix = _native_compute(name, rdt, cdt)

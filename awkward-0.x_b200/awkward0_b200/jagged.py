@@ -1032,7 +1032,9 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
 
     def _getitem_jagged_bool(self, head):
-        """jagged.py:562-589 -> jg_mask_select (one pass: popcount, look-back scan, compaction)."""
+        """jagged.py:562-589 -> jg_mask_select (count per tile, scan of the tile totals, compaction; the result's
+        counts come out of the same sweep).  A mask that is a still-deferred `column > scalar` (lazy.LazyCompare)
+        over single-column content is evaluated inside those sweeps instead (jg_compare_select)."""
         a, off, n, first, last = self._dense()
         head = a._align(head)
         mask = head._content
@@ -1042,12 +1044,28 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
         columns = []
+        fused = (isinstance(mask, _lazy.LazyCompare) and mask.deferred and isinstance(a._content, DeviceArray))
+        if fused:
+            key = mask._source
+            # is the compared column the selected column itself (possibly seen through a view that starts at `first`)?
+            same = (key.dtype == a._content.dtype and
+                    key.tensor.data_ptr() + mask_shift * key.itemsize == a._content.tensor.data_ptr())
+            # two staged columns must fit a tile's shared memory without shrinking it (float64 by another float64
+            # column does not): the mask path is the better one there
+            fused = same or (a._content.itemsize in (4, 8) and key.itemsize + a._content.itemsize <= 12)
+        if fused:
+            op, scalar = _lib.OP[mask._op], mask._scalar
 
         def select(col):
             out = empty(last - first, col.dtype)
-            call("jg_mask_select", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
-                 _vp(out), _vp(new_offsets), _vp(new_counts) if not columns else ctypes.c_void_p(0), _vp(scal), ws, wsb,
-                 runtime.stream())
+            counts_ptr = _vp(new_counts) if not columns else ctypes.c_void_p(0)
+            if fused:
+                call("jg_compare_select", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
+                     jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,
+                     _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, runtime.stream())
+            else:
+                call("jg_mask_select", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
+                     _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, runtime.stream())
             columns.append(out)
             return out
 

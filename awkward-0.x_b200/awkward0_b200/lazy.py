@@ -18,6 +18,7 @@ that are too long) falls back to materialising the operands and running the eage
 on whether fusion happened: the functors are shared (csrc/jg_ops.cuh) and no step is contracted with another.
 """
 import ctypes
+import weakref
 
 import numpy
 
@@ -41,6 +42,24 @@ _UNCHECKED_SIZE = 20      # expression trees up to this size are not test-compil
                           # program has at most 1.5 steps per tree node; the rare misfit -- more than 8 distinct
                           # columns of one side -- is caught when the value is needed, see LazyArray._materialise)
 _UFUNC_OF = {}            # operator name -> numpy ufunc, filled by _ufunc on import
+
+
+_DEFERRED = {}      # id -> weak reference of every live array whose value may not have been computed yet
+
+
+def _register(x):
+    k = id(x)
+    _DEFERRED[k] = weakref.ref(x, lambda _r, k=k: _DEFERRED.pop(k, None))
+
+
+def flush_all():
+    """Compute every deferred value now.  Called before anything is written IN PLACE (jg_put, the store side of
+    __setitem__): a deferred value must not see data that changed after the expression was written."""
+    for r in list(_DEFERRED.values()):
+        x = r()
+        if x is not None and x._mat is None:
+            x.tensor
+    _DEFERRED.clear()
 
 
 class JgEvalProgram(ctypes.Structure):
@@ -109,11 +128,12 @@ class LazyArray(DeviceArray):
     """A P-sized column that is computed on first use.  kind "L"/"R": args = (source column,) ; kind "op":
     args = (operator name, operand, ...) with operands LazyArray (same context) / DeviceArray (P-sized) / scalar."""
 
-    __slots__ = ("_ctx", "_kind", "_args", "_ldtype", "_mat", "_size")
+    __slots__ = ("_ctx", "_kind", "_args", "_ldtype", "_mat", "_size", "__weakref__")
 
     def __init__(self, ctx, kind, args, dtype, size=1):
         self._ctx, self._kind, self._args, self._ldtype, self._mat = ctx, kind, args, numpy.dtype(dtype), None
         self._size = size                 # nodes of the expression TREE below (an upper bound of the program length)
+        _register(self)
 
     # -- what DeviceArray keeps in slots is computed here
     @property
@@ -404,3 +424,91 @@ def _compile(root):
     prog.nins, prog.nslots = state["nins"], state["nslots"]
     prog.out_bool = 1 if root._ldtype == numpy.bool_ else 0
     return prog, cdt
+
+
+# ---- column OP scalar, deferred so that a[a > c] never writes the mask ---------------------------------------------
+_MIRROR = {"GT": "LT", "GE": "LE", "LT": "GT", "LE": "GE"}
+
+
+class LazyCompare(DeviceArray):
+    """`column OP scalar` for an ordering comparison (> >= < <=) of a float32 / float64 column.  Used as a jagged
+    mask (jagged.py:562-589) it is evaluated inside the selection sweeps (jg_compare_select): the M-byte mask is
+    neither written nor read.  Any other use computes it with the ordinary comparison kernel first."""
+
+    __slots__ = ("_source", "_op", "_scalar", "_mat", "__weakref__")
+
+    def __init__(self, source, op, scalar):
+        self._source, self._op, self._scalar, self._mat = source, op, float(scalar), None
+        _register(self)
+
+    @property
+    def _t(self):
+        if self._mat is None:
+            from . import _ufunc
+            ENABLED[0], was = False, ENABLED[0]
+            try:
+                self._mat = _ufunc.binary(_UFUNC_OF[self._op], self._source, self._source.dtype.type(self._scalar)).tensor
+            finally:
+                ENABLED[0] = was
+            self._source = None
+        return self._mat
+
+    @property
+    def _dtype(self):
+        return numpy.dtype(numpy.bool_)
+
+    @property
+    def deferred(self):
+        return self._mat is None
+
+    def __len__(self):
+        return len(self._source) if self._mat is None else int(self._mat.shape[0])
+
+    @property
+    def shape(self):
+        return (len(self),)
+
+    @property
+    def size(self):
+        return len(self)
+
+    @property
+    def nbytes(self):
+        return len(self)
+
+    @property
+    def itemsize(self):
+        return 1
+
+    def __getitem__(self, where):
+        if self._mat is None and isinstance(where, slice):
+            start, stop, step = where.indices(len(self))
+            if step == 1:
+                if (start, stop) == (0, len(self)):
+                    return self
+                return LazyCompare(self._source[start:max(start, stop)], self._op, self._scalar)
+        return DeviceArray.__getitem__(self, where)
+
+    def __repr__(self):
+        if self._mat is None:
+            return "<LazyCompare {0} x bool, deferred {1} {2}>".format(len(self), self._op, self._scalar)
+        return DeviceArray.__repr__(self)
+
+
+def try_compare(name, lhs, rhs, cdt):
+    """An ordering comparison of a float column with a scalar -> LazyCompare, else None."""
+    if not ENABLED[0] or name not in _MIRROR:
+        return None
+    if isinstance(lhs, DeviceArray) and not isinstance(rhs, DeviceArray):
+        arr, scalar, op = lhs, rhs, name
+    elif isinstance(rhs, DeviceArray) and not isinstance(lhs, DeviceArray):
+        arr, scalar, op = rhs, lhs, _MIRROR[name]                 # c OP x  ==  x mirror(OP) c
+    else:
+        return None
+    if isinstance(arr, (LazyArray, LazyCompare)) or arr.dtype not in _FLOATS or cdt != arr.dtype or len(arr) == 0:
+        return None
+    try:
+        scalar = float(scalar)
+    except (TypeError, ValueError):
+        return None
+    return LazyCompare(arr, op, scalar)

@@ -4,6 +4,7 @@
 
 #include "jg_scan.cuh"
 #include <cstring>
+#include <type_traits>
 
 #include "jg_tile.cuh"
 
@@ -28,44 +29,90 @@ __device__ __forceinline__ int popcount_bytes16(int4 v) {
            __popc(__vcmpne4(v.z, 0) & 0x01010101u) + __popc(__vcmpne4(v.w, 0) & 0x01010101u);
 }
 
+// What decides whether a position is selected: a byte mask (a[mask]) or a comparison of a float column with a scalar
+// evaluated on the fly (a[a > c]: the mask is never written nor read).  `x OP c` is brought to one of two forms on
+// the host: flip negates both sides (x < c  ==  -x > -c, exact for every float, NaN stays unordered) and strict
+// picks > or >= (a template parameter: the test is one XOR and one compare).
+struct ByteMask {
+    using Elem = uint8_t;
+    __device__ __forceinline__ bool test(uint8_t v) const { return v != 0; }
+};
+template <typename K, bool STRICT>
+struct FloatCompare {
+    using Elem = K;
+    using Bits = typename std::conditional<sizeof(K) == 4, uint32_t, uint64_t>::type;
+    K c;             // already negated when flipping
+    Bits flip;       // sign bit when the comparison is mirrored, else 0: one XOR per item, no select
+    __device__ __forceinline__ bool test(K v) const {
+        Bits b;
+        memcpy(&b, &v, sizeof(K));
+        b ^= flip;
+        K y;
+        memcpy(&y, &b, sizeof(K));
+        return STRICT ? (y > c) : (y >= c);
+    }
+};
+
+template <class SEL>
+__device__ __forceinline__ int count16(const SEL &sel, int4 v) {
+    using E = typename SEL::Elem;
+    if constexpr (sizeof(E) == 1) {
+        return popcount_bytes16(v);
+    } else {
+        union { int4 raw; E e[16 / sizeof(E)]; } q;
+        q.raw = v;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(16 / sizeof(E)); ++k) c += sel.test(q.e[k]);
+        return c;
+    }
+}
+
 constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
 
+template <class SEL>
 __global__ void __launch_bounds__(kCountWarps * kWarp)
-mask_count_kernel(const uint8_t *__restrict__ mask, int64_t mask_shift, const int64_t *__restrict__ offsets,
-                  int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals) {
+mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
+                  const int64_t *__restrict__ offsets, int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals) {
+    using E = typename SEL::Elem;
+    constexpr int PER = 16 / sizeof(E);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = static_cast<int64_t>(blockIdx.x) * kCountWarps + warp;
     if (tile >= ntiles) return;
     const int64_t ev0 = tile * kTileEvents;
     const int64_t ev1 = min(n, ev0 + kTileEvents);
     const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
-    const uint8_t *m = mask + e0 + mask_shift;
+    const E *m = mask + e0 + mask_shift;
     const int64_t len = e1 - e0;
     int64_t cnt = 0;
-    // unaligned head, 16-byte body, tail
+    // unaligned head (< 16 bytes), 16-byte body, tail
     const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-    int64_t head = static_cast<int64_t>((16 - (addr & 15)) & 15);
+    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
     if (head > len) head = len;
-    if (lane < head) cnt += (m[lane] != 0);
-    const int64_t nvec = (len - head) >> 4;
+    if (lane < head) cnt += sel.test(m[lane]);
+    const int64_t nvec = (len - head) / PER;
     const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-    for (int64_t i = lane; i < nvec; i += kWarp) cnt += popcount_bytes16(__ldcs(mv + i));
-    const int64_t tail0 = head + (nvec << 4);
-    if (tail0 + lane < len) cnt += (m[tail0 + lane] != 0);
+#pragma unroll 2
+    for (int64_t i = lane; i < nvec; i += kWarp) cnt += count16(sel, __ldcs(mv + i));
+    const int64_t tail0 = head + nvec * PER;
+    if (tail0 + lane < len) cnt += sel.test(m[tail0 + lane]);
     cnt = warp_reduce_add(cnt);
     if (lane == 0) tile_totals[tile] = cnt;
 }
 
-template <typename V, int KM>     // KM = positions a tile may stage
+// SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both
+template <typename V, int KM, class SEL, bool SAME>     // KM = positions a tile may stage
 __global__ void __launch_bounds__(kTileThreads)
-mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask, int64_t mask_shift,
-                 const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
+mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
+                 int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
                  const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
+    using E = typename SEL::Elem;
+    static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
-    __shared__ __align__(16) unsigned char s_mask[KM + 32];
+    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
     __shared__ uint16_t s_pfx[KM + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
@@ -82,7 +129,9 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
         EventTile::range(n, tile_index, ev0, nev);
         const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
         if (b > a && b - a <= KM) {
-            stage_bulk(s_mask, mask + a + mask_shift, static_cast<uint32_t>(b - a), &s_bar[1]);
+            if (!SAME)
+                stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(mask + a + mask_shift),
+                           static_cast<uint32_t>((b - a) * sizeof(E)), &s_bar[1]);
             stage_bulk(s_content, reinterpret_cast<const unsigned char *>(content + a),
                        static_cast<uint32_t>((b - a) * sizeof(V)), &s_bar[0]);
         }
@@ -98,15 +147,21 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
         // ---------------- staged tile ----------------------------------------------------------------------
         const int L = static_cast<int>(len);
         const V *cv = nullptr;
-        const uint8_t *mv = nullptr;
+        const E *mv = nullptr;
         if (L > 0) {
             const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
                                                        static_cast<uint32_t>(L * sizeof(V)));
-            const uint32_t ms = stage_edges<1>(s_mask, mask + e0 + mask_shift, static_cast<uint32_t>(L));
-            mbar_wait(&s_bar[1], 0);
-            __syncthreads();
             cv = reinterpret_cast<const V *>(s_content + cs);
-            mv = s_mask + ms;
+            if (SAME) {
+                mbar_wait(&s_bar[0], 0);
+                mv = reinterpret_cast<const E *>(cv);
+            } else {
+                const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + e0 + mask_shift),
+                                                           static_cast<uint32_t>(L * sizeof(E)));
+                mbar_wait(&s_bar[1], 0);
+                mv = reinterpret_cast<const E *>(s_mask + ms);
+            }
+            __syncthreads();
         }
         // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
         const int rows_total = (L + 31) >> 5;
@@ -115,7 +170,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
         const int p_end = min(L, p_begin + rows_per_warp * 32);
         // pass 1: selected per warp
         int cnt = 0;
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += (mv[p] != 0);
+        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
         cnt = warp_reduce_add(cnt);
         if (lane == 0) s_scan[warp] = cnt;
         __syncthreads();
@@ -125,18 +180,18 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
             if (lane < NW) s_scan[lane] = wi - w;
             if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
         }
-        if (L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
+        if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
         __syncthreads();
         // pass 2: compaction, consecutive lanes -> consecutive output slots
         int run = s_scan[warp];
         V *dst = out + base;
         for (int p0 = p_begin; p0 < p_end; p0 += 32) {
             const int p = p0 + lane;
-            const bool sel = p < p_end && mv[p] != 0;
-            const unsigned b = __ballot_sync(0xffffffffu, sel);
+            const bool on = p < p_end && sel.test(mv[p]);
+            const unsigned b = __ballot_sync(0xffffffffu, on);
             const int slot = run + __popc(b & ((1u << lane) - 1u));
             if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-            if (sel) dst[slot] = cv[p];
+            if (on) dst[slot] = cv[p];
             run += __popc(b);
         }
         __syncthreads();
@@ -153,7 +208,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
 
     // ---------------- oversize tile (long events): straight from global memory ------------------------------
     const V *cv = content + e0;
-    const uint8_t *mv = mask + e0 + mask_shift;
+    const E *mv = mask + e0 + mask_shift;
     const int ev0 = threadIdx.x * 2;      // thread t owns events 2t and 2t+1
     int64_t a[2], b[2];
     int64_t c[2] = {0, 0};
@@ -165,7 +220,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
             a[q] = s_off[ev] - e0;
             b[q] = s_off[ev + 1] - e0;
             int64_t cnt = 0;
-            for (int64_t j = a[q]; j < b[q]; ++j) cnt += (mv[j] != 0);
+            for (int64_t j = a[q]; j < b[q]; ++j) cnt += sel.test(mv[j]);
             c[q] = cnt;
         }
     }
@@ -180,7 +235,7 @@ mask_fill_kernel(const V *__restrict__ content, const uint8_t *__restrict__ mask
             new_offsets[tile.event0 + ev] = w;
             if (new_counts) new_counts[tile.event0 + ev] = c[q];
             for (int64_t j = a[q]; j < b[q]; ++j) {
-                if (mv[j] != 0) out[w++] = cv[j];
+                if (sel.test(mv[j])) out[w++] = cv[j];
             }
         }
     }
@@ -350,25 +405,67 @@ static int carve_tile_ws(void *ws, size_t ws_bytes, int64_t ntiles, TileScanWs &
     return 0;
 }
 
-template <typename V, int KM>
-static int launch_mask_select(const void *content, const uint8_t *mask, int64_t mask_shift, const int64_t *offsets,
-                              int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts, int64_t *total, void *ws,
-                              size_t ws_bytes, cudaStream_t s) {
+template <typename V, int KM, class SEL, bool SAME>
+static int launch_mask_select(const SEL &sel, const void *content, const typename SEL::Elem *mask, int64_t mask_shift,
+                              const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                              int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
     if (rc) return rc;
-    mask_count_kernel<<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
-        mask, mask_shift, offsets, n, ntiles, t.totals);
+    mask_count_kernel<SEL><<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
+        sel, mask, mask_shift, offsets, n, ntiles, t.totals);
     rc = check_launch("mask_count_kernel");
     if (rc) return rc;
     ScanInArray<int64_t> in{t.totals, true};
     rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
     if (rc) return rc;
-    mask_fill_kernel<V, KM><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
-        static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets, new_counts,
-        t.bases, static_cast<uint32_t>(ntiles));
+    mask_fill_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+        sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+        new_counts, t.bases, static_cast<uint32_t>(ntiles));
     return check_launch("mask_fill_kernel");
+}
+
+// staged positions per tile: content + selector + 16-bit prefix must leave room for ~6 CTAs per SM
+template <class SEL, bool SAME>
+static int dispatch_mask_select(const SEL &sel, const void *content, int itemsize, const typename SEL::Elem *mask,
+                                int64_t mask_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                                int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+    constexpr int E = sizeof(typename SEL::Elem);
+    if constexpr (SAME) {
+        if constexpr (E == 4) return launch_mask_select<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        else return launch_mask_select<uint64_t, 3584, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+    } else {
+        constexpr int KM8 = E == 1 ? 3584 : (E == 4 ? 3072 : 2304);   // (f64 by another f64 column: the host keeps the mask path)
+        constexpr int KM4 = E == 8 ? 3072 : 4096;
+        if constexpr (E == 1) {          // narrow contents only through a byte mask (keeps the number of kernels down)
+            if (itemsize == 1) return launch_mask_select<uint8_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+            if (itemsize == 2) return launch_mask_select<uint16_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        }
+        switch (itemsize) {
+            case 4: return launch_mask_select<uint32_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+            case 8: return launch_mask_select<uint64_t, KM8, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        }
+        set_error("jg_mask_select: unsupported itemsize %d", itemsize);
+        return -2;
+    }
+}
+
+template <typename K, bool STRICT>
+static int compare_select(const void *content, int itemsize, const void *key, int op, double scalar, int64_t key_shift,
+                          const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                          int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+    using SEL = FloatCompare<K, STRICT>;
+    SEL sel;
+    const K c = static_cast<K>(scalar);                 // the eager comparison converts the scalar the same way
+    const bool flip = (op == JG_OP_LT || op == JG_OP_LE);
+    sel.flip = flip ? (static_cast<typename SEL::Bits>(1) << (8 * sizeof(K) - 1)) : 0;
+    sel.c = flip ? -c : c;
+    const K *k = static_cast<const K *>(key);
+    if (key == content && key_shift == 0 && itemsize == static_cast<int>(sizeof(K)))
+        return dispatch_mask_select<SEL, true>(sel, content, itemsize, k, 0, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+    JG_REQUIRE(itemsize == 4 || itemsize == 8, "jg_compare_select: a column other than the compared one must have 4- or 8-byte items");
+    return dispatch_mask_select<SEL, false>(sel, content, itemsize, k, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
 }
 
 template <typename V>
@@ -399,14 +496,23 @@ int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64
                    const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                    int64_t *total, void *ws, size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
+    return dispatch_mask_select<ByteMask, false>(ByteMask{}, content, itemsize, mask, mask_shift, offsets, n, out,
+                                                 new_offsets, new_counts, total, ws, ws_bytes, as_stream(stream));
+}
+
+int jg_compare_select(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                      int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                      int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream) {
+    JG_REQUIRE(n >= 0 && offsets && new_offsets && key, "jg_compare_select: bad arguments");
+    JG_REQUIRE(op == JG_OP_GT || op == JG_OP_GE || op == JG_OP_LT || op == JG_OP_LE,
+               "jg_compare_select: operator %d is not an ordering comparison", op);
     cudaStream_t s = as_stream(stream);
-    switch (itemsize) {
-        case 1: return launch_mask_select<uint8_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-        case 2: return launch_mask_select<uint16_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-        case 4: return launch_mask_select<uint32_t, 4096>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-        case 8: return launch_mask_select<uint64_t, 3584>(content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-    }
-    set_error("jg_mask_select: unsupported itemsize %d", itemsize);
+    const bool strict = (op == JG_OP_GT || op == JG_OP_LT);
+#define JG_CS(K, ST) compare_select<K, ST>(content, itemsize, key, op, scalar, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s)
+    if (key_dtype == JG_F32) return strict ? JG_CS(float, true) : JG_CS(float, false);
+    if (key_dtype == JG_F64) return strict ? JG_CS(double, true) : JG_CS(double, false);
+#undef JG_CS
+    set_error("jg_compare_select: key dtype %d is not float32 / float64", key_dtype);
     return -2;
 }
 

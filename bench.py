@@ -288,7 +288,7 @@ def run_gpu(args):
     peaks = load_peaks()
     roof = None
     if ops:
-        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "greater_f32", "mask_select_f32"]       # (the selection writes its counts itself)
+        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "compare_select_f32"]       # a[a > 20] is one fused op; it writes its counts itself
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
         traffic = None
         try:
@@ -417,6 +417,11 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     K = int(scal.cpu()[0])
     add("mask_select_f32", v * M + M + 8 * N + v * K + 8 * N + 8 * N, M, lambda: _lib.call(
         "jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st()))
+    # a[a > 20] as ONE op: the comparison is evaluated inside the counting and compaction sweeps (no mask).  Algorithmic
+    # bytes = what this fused op must move (content twice is NOT counted: once read, K written, offsets in and out, counts)
+    add("compare_select_f32", v * M + 8 * N + v * K + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_compare_select", pt_dev.data_ptr(), 4, pt_dev.data_ptr(), _lib.JG_F32, _lib.OP["GT"], ctypes.c_double(THRESHOLD), 0,
+        off.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st()))
     del sel, mask
     # leading-object gather a[a.argmax()]
     lead = a.argmax()

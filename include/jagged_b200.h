@@ -167,6 +167,15 @@ int jg_index_gather(const void *content, int itemsize, const int64_t *offsets, c
  * be NULL to run the scan only.  out must hold n items (upper bound).                                              */
 int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int64_t n, void *out, int64_t *positions,
                     int64_t *total, void *ws, size_t ws_bytes, void *stream);
+/* a[a OP c] in one call (jagged.py:944-1051 comparison ufunc + jagged.py:562-589 selection): the comparison of the
+ * float column `key` (JG_F32 / JG_F64, positioned like `content` shifted by key_shift items) with a scalar is
+ * evaluated inside the counting and the compaction sweeps, so the M-byte mask is neither written nor read.  op is
+ * JG_OP_GT / GE / LT / LE with the column on the left (the host mirrors `c OP a`).  When key == content the column is
+ * staged once; a content column other than the key must have 4- or 8-byte items.  The rest is jg_mask_select.     */
+int jg_compare_select(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                      int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                      int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream);
+
 /* scatter content[index[k]] = values[k], or the `itemsize` low bytes of scalar_bits when values is NULL: the store
  * of __setitem__ (jagged.py:789-838: `self._content[indexes] = what`) and of parents2startsstops (jagged.py:73-93:
  * `starts[where[real]] = ...`, for which skip_negative != 0 drops the negative parents).  No bounds check: the

@@ -242,3 +242,93 @@ def test_wide_expression_falls_back_stepwise(ak):
     for c in cols[1:]:
         want = want + c[left]
     assert same(e.content.get(), want)
+
+
+# ---- a[a > c]: the comparison is evaluated inside the selection sweeps (jg_compare_select) -------------------------
+def _counts_for(kind, n, rng):
+    if kind == "poisson5":
+        return rng.poisson(5.0, n).astype(np.int64)
+    c = rng.geometric(0.3, n).astype(np.int64) - 1                 # heavy tail: tiles that do not fit the stage
+    c[rng.integers(0, n, 4)] = rng.integers(3000, 30000, 4)
+    return c
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", ["poisson5", "heavy"])
+def test_compare_select_matches_oracle_and_mask_path(ak, shape, dtype):
+    from awkward0_b200 import lazy
+    rng = np.random.default_rng(31)
+    counts = _counts_for(shape, 60000, rng)
+    m = int(counts.sum())
+    x = rng.normal(20.0, 15.0, m).astype(dtype)
+    x[rng.integers(0, m, 200)] = np.nan
+    x[rng.integers(0, m, 50)] = np.inf
+    x[rng.integers(0, m, 50)] = -np.inf
+    x[rng.integers(0, m, 300)] = 20.0                              # ties with the threshold
+    off = O.counts2offsets(counts)
+    a = ak.JaggedArray.fromcounts(counts, x)
+    cases = [(lambda v: v > 20, np.greater), (lambda v: v >= 20, np.greater_equal), (lambda v: v < 20, np.less),
+             (lambda v: v <= 20, np.less_equal), (lambda v: 20 < v, np.greater), (lambda v: 20.0 >= v, np.less_equal),
+             (lambda v: v > -0.0, np.greater), (lambda v: v > np.inf, np.greater)]
+    for f, uf in cases:
+        mask = f(a)
+        assert isinstance(mask.content, lazy.LazyCompare) and mask.content.deferred
+        sel = a[mask]
+        assert mask.content.deferred                                # the mask was never written
+        with np.errstate(invalid="ignore"):
+            hmask = f(x)
+        soff, want = O.mask_select(off, x, off, hmask)
+        assert np.array_equal(sel.offsets.get(), soff) and same(sel.content.get(), want)
+        assert np.array_equal(sel.counts.get(), np.diff(soff))
+        assert same(mask.content.get(), hmask)                     # and it still is an ordinary mask when asked
+        lazy.ENABLED[0] = False
+        try:
+            ref = a[f(a)]
+        finally:
+            lazy.ENABLED[0] = True
+        assert np.array_equal(ref.offsets.get(), sel.offsets.get()) and same(ref.content.get(), sel.content.get())
+
+
+def test_compare_select_other_columns_views_and_writes(ak):
+    from awkward0_b200 import lazy
+    rng = np.random.default_rng(32)
+    counts = rng.poisson(4.0, 30000).astype(np.int64)
+    m = int(counts.sum())
+    off = O.counts2offsets(counts)
+    key32 = rng.normal(size=m).astype(np.float32)
+    k = ak.JaggedArray.fromcounts(counts, key32)
+    for content in (rng.normal(size=m), rng.integers(-9, 9, m).astype(np.int64), rng.integers(0, 200, m).astype(np.uint8),
+                    rng.normal(size=m).astype(np.float32), rng.integers(-9, 9, m).astype(np.int16)):
+        a = ak.JaggedArray.fromoffsets(k.offsets, content)
+        sel = a[k > 0.25]
+        soff, want = O.mask_select(off, content, off, key32 > 0.25)
+        assert np.array_equal(sel.offsets.get(), soff) and same(sel.content.get(), want)
+    key64 = rng.normal(size=m)
+    a64 = ak.JaggedArray.fromoffsets(k.offsets, rng.normal(size=m))           # float64 by another float64: mask path
+    sel = a64[ak.JaggedArray.fromoffsets(k.offsets, key64) <= 0.5]
+    soff, want = O.mask_select(off, a64.content.get(), off, key64 <= 0.5)
+    assert np.array_equal(sel.offsets.get(), soff) and same(sel.content.get(), want)
+    # a view whose content starts at offsets[0] != 0
+    v = k[1000:]
+    sel = v[v > 0.0]
+    voff = off[1000:] - off[1000]
+    vx = key32[off[1000]:]
+    soff, want = O.mask_select(voff, vx, voff, vx > 0.0)
+    assert np.array_equal(sel.offsets.get(), soff) and same(sel.content.get(), want)
+    # records: every column through the same (materialised once) mask
+    rec = ak.JaggedArray.zip(x=k, y=ak.JaggedArray.fromoffsets(k.offsets, key64))
+    r = rec[rec.x < 0.0]
+    soff, wx = O.mask_select(off, key32, off, key32 < 0.0)
+    _, wy = O.mask_select(off, key64, off, key32 < 0.0)
+    assert np.array_equal(r.offsets.get(), soff) and same(r.x.content.get(), wx) and same(r.y.content.get(), wy)
+    # a deferred comparison sees the data as it was when it was written, even if the array is assigned to later
+    b = ak.JaggedArray.fromcounts(counts, key32.copy())
+    mask = b > 0.5
+    assert mask.content.deferred
+    b[b < -0.5] = 9.0                                                           # in-place store
+    assert not mask.content.deferred
+    assert same(mask.content.get(), key32 > 0.5)
+    changed = key32.copy()
+    changed[key32 < -0.5] = 9.0
+    soff, want = O.mask_select(off, changed, off, key32 > 0.5)
+    assert same(b[mask].content.get(), want)
