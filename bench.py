@@ -283,7 +283,7 @@ def run_gpu(args):
 
     # ---- per-kernel roofline table (rank 0, device-resident, CUDA events around each C-ABI call)
     ops = {}
-    if rank == 0:
+    if rank == 0 and not args.no_tables:
         ops = kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, nev, M, args)
     peaks = load_peaks()
     roof = None
@@ -303,7 +303,7 @@ def run_gpu(args):
                 "step_share": ops[dom]["ms"] / sum(ops[k]["ms"] for k in step_ops)}
 
     workflows = {}
-    if rank == 0:
+    if rank == 0 and not args.no_tables:
         workflows = workflow_table(ak, counts_dev, pt_dev, nev, M, args)
 
     cpu = None
@@ -661,6 +661,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8,
                     help="event chunks of the streamed host->HBM ingest used by the e2e leg (0: copy everything, then compute)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tables", action="store_true",
+                    help="skip the per-kernel roofline table and the API workflow table (scaling runs: only the sweep is wanted)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
