@@ -774,15 +774,13 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def tolist(self):
         """base.py:159-172."""
         starts, stops, content = self._host()
-        istuple = isinstance(self._content, Table) and self._content.istuple
-
         def rows(cols, a, b):
             flat = OrderedDict()
             for n, c in cols.items():
                 flat[n] = rows(c, a, b) if isinstance(c, dict) else c[a:b].tolist()
             names = list(flat)
             count = b - a
-            tup = istuple
+            tup = getattr(cols, "istuple", False)          # each Table prints its own way (tuple rows / record rows)
             return [tuple(flat[n][i] for n in names) if tup else dict((n, flat[n][i]) for n in names) for i in range(count)]
 
         out = []
@@ -1393,7 +1391,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return _rebuild(content, iter([ctx.leaf(which, c) for c in leaves]))
 
         left, right = side(a._content, "L"), side(b._content, "R")
-        return self._make(poff, Table.named("tuple", left, right), total)
+        return self._make(poff, Table.named("tuple", left, right).flattentuple(), total)      # jagged.py:1271,1294,1350
 
     def _nest(self, flat_result, kind, other=None):
         """nested=True (jagged.py:1255,1275,1285,1298,1335,1356): regroup the per-event combinations by their
@@ -1446,7 +1444,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         args = self._comb_indices(_lib.COMB_CHOOSE, int(n), absolute=True)
         a = self.compact()
         cols = [a._map_content(lambda c, idx=args._content[name]: _ufunc.take(c, idx)) for name in args._content.columns]
-        return self._make(args._off64, Table.named("tuple", *cols), args._last)
+        return self._make(args._off64, Table.named("tuple", *cols).flattentuple(), args._last)      # jagged.py:1241
 
     def _check_cross(self, other):
         if not isinstance(other, JaggedArray):

@@ -10,6 +10,11 @@ from collections import OrderedDict
 from .device import DeviceArray, asdevice
 
 
+class _HostColumns(OrderedDict):
+    """Host copies of a Table's columns; remembers whether its rows print as tuples or as records."""
+    istuple = False
+
+
 class Table(object):
     def __init__(self, columns1=None, *columns2, **columns3):
         self._contents = OrderedDict()
@@ -77,18 +82,20 @@ class Table(object):
         return out
 
     def flattentuple(self):
-        """table.py:791-820 -- splice nested tuple Tables into one tuple."""
+        """table.py:791-820 -- the columns of a tuple-Table that are themselves tuple-Tables are spliced in place
+        (recursively), so that a.cross(b).cross(c) is a flat 3-tuple; record Tables stay as they are."""
+        out = Table.named(self.rowname)
+        for n, x in self._contents.items():
+            out._contents[n] = x.flattentuple() if isinstance(x, Table) else x
         if not self.istuple:
-            return self
+            return out
         flat = []
-        for x in self._contents.values():
-            if isinstance(x, Table) and x.istuple and getattr(x, "_splice", False):
-                flat.extend(x.flattentuple()._contents.values())
+        for x in out._contents.values():
+            if isinstance(x, Table) and x.istuple:
+                flat.extend(x._contents.values())
             else:
                 flat.append(x)
-        out = Table.named("tuple")
-        for i, x in enumerate(flat):
-            out._contents[str(i)] = x
+        out._contents = OrderedDict((str(i), x) for i, x in enumerate(flat))
         return out
 
     @property
@@ -121,7 +128,8 @@ class Table(object):
         return tuple(self._contents.values())
 
     def _host_columns(self):
-        out = OrderedDict()
+        out = _HostColumns()
+        out.istuple = self.istuple
         for n, x in self._contents.items():
             out[n] = x._host_columns() if isinstance(x, Table) else x.get()
         return out

@@ -672,3 +672,19 @@ def test_switches(ak):
     with pytest.raises(RuntimeError, match="allow_tonumpy is False"):
         c.tolist()
     assert c.sum().tolist() == [1.0, 2.0]          # flat results are plain DeviceArrays
+
+
+def test_chained_combinatorics_flatten_tuples(ak):      # jagged.py:1241,1271,1294,1350 + table.py:791-820
+    J = ak.JaggedArray
+    a, b, c = J.fromiter([[1, 2], [], [3]]), J.fromiter([[10], [20], [30, 40]]), J.fromiter([[100, 200], [300], [400]])
+    x = a.cross(b).cross(c)                              # literals: the reference run in the build container
+    assert x.columns == ["0", "1", "2"]
+    assert x.tolist() == [[(1, 10, 100), (1, 10, 200), (2, 10, 100), (2, 10, 200)], [], [(3, 30, 400), (3, 40, 400)]]
+    p = a.cross(b).pairs()
+    assert p.columns == ["0", "1", "2", "3"] and p.tolist()[0] == [(1, 10, 1, 10), (1, 10, 2, 10), (2, 10, 2, 10)]
+    ap = a.pairs().cross(c)
+    assert ap.tolist()[0] == [(1, 1, 100), (1, 1, 200), (1, 2, 100), (1, 2, 200), (2, 2, 100), (2, 2, 200)]
+    z = J.zip(u=a, v=a * 2)                              # record Tables are not spliced
+    zc = z.cross(b)
+    assert zc.columns == ["0", "1"] and zc.tolist()[0] == [({"u": 1, "v": 2}, 10), ({"u": 2, "v": 4}, 10)]
+    assert (x.i0 + x.i1 + x.i2).tolist() == [[111, 211, 112, 212], [], [433, 443]]
