@@ -864,7 +864,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if isinstance(where, slice):
             start, stop, step = where.indices(len(self))
             if step != 1:
-                raise NotImplementedError("event slices with a step are outside the GPU hot path (SURVEY.md section 8f-1)")
+                # events start, start + step, ...: event-level fancy indexing with the index built on the device
+                count = len(range(start, stop, step))
+                picks = _ufunc.arange(count)
+                if count:
+                    picks = picks * step + start
+                return self[picks]
             stop = max(start, stop)
             if self._off64 is not None:
                 sub = self._off64[start:stop + 1]
@@ -1123,8 +1128,11 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                               device=runtime.device())
             return self._make(a._rebased_offsets(), DeviceArray(fill, np_dtype), last - first)
         flat = asdevice(data)
-        if len(flat) != n:
-            raise ValueError("cannot broadcast AwkwardArray to match JaggedArray with a different length")
+        if len(flat) < n:
+            # jagged.py:867-869 indexes data with the parents: an array that is too short fails there
+            raise IndexError("index {0} is out of bounds for axis 0 with size {1}".format(n - 1, len(flat)))
+        if len(flat) > n:
+            flat = flat[:n]                     # ... and one that is longer is simply not read beyond len(self)
         out = empty(last - first, flat.dtype)
         if last > first:
             call("jg_broadcast", flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), runtime.stream())
@@ -1340,6 +1348,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return self._make(newoffsets, inner.flatten(), total)
         if axis != 0:
             raise NotImplementedError("flatten(axis>1) is outside the GPU hot path")
+        if isinstance(self._content, JaggedArray):
+            # jagged-of-jagged: the inner array restricted to the reachable inner events (jagged.py:1421-1423)
+            if len(self) == 0:
+                return self._content[0:0]
+            a, off, n, first, last = self._dense()
+            return a._dense_content()
         if len(self) == 0:
             return self._map_content(lambda c: c[0:0])
         a, off, n, first, last = self._dense()

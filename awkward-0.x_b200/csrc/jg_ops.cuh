@@ -105,7 +105,10 @@ template <int OP, typename C>
 struct UnaryOp {
     using Out = C;
     __device__ static __forceinline__ C apply(C x) {
-        if constexpr (OP == JG_OP_NEG) return C(0) - x;
+        if constexpr (OP == JG_OP_NEG) {
+            if constexpr (IsFp<C>::value) return -x;      // numpy.negative(0.0) is -0.0
+            else return C(0) - x;
+        }
         else if constexpr (OP == JG_OP_ABS) {
             if constexpr (IsFp<C>::value) return fabs(x);
             else return x < C(0) ? C(0) - x : x;

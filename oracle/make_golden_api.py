@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""Evaluate a battery of JaggedArray API expressions with the UNMODIFIED reference (build container only) and write
+tests/golden/api_cases.json: for every case the expression, and either the `tolist()` of its value or the name of
+the exception it raised.  tests/test_gpu_api_cases.py evaluates the same strings against awkward0_b200 on a B200.
+
+    python oracle/make_golden_api.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import _refloader  # noqa: E402
+
+# every case sees: J (the JaggedArray class), np, and the arrays built by SETUP (evaluated in order)
+SETUP = [
+    ("a", "J.fromiter([[0.0, 1.1, 2.2], [], [3.3, 4.4], [5.5, 6.6, 7.7, 8.8, 9.9]])"),
+    ("b", "J.fromiter([[10.0, 20.0, 30.0], [], [40.0, 50.0], [60.0, 70.0, 80.0, 90.0, 100.0]])"),
+    ("i", "J.fromiter([[1, -2, 3], [], [4, 4], [-5, 0, 0, 7, 2]])"),
+    ("e", "J.fromiter([[], [], []])"),
+    ("s", "J.fromiter([[3.0, 1.0, 2.0], [], [5.0, 4.0], [7.0]])"),
+    ("g", "J([4, 0, 2], [6, 2, 2], np.array([0.0, 1.1, 2.2, 3.3, 4.4, 5.5, 6.6]))"),
+    ("f32", "J.fromcounts([2, 0, 3], np.array([1.5, -2.5, 3.5, np.inf, -0.0], dtype=np.float32))"),
+    ("nan", "J.fromcounts([3, 2, 0, 1], np.array([np.nan, 1.0, -1.0, np.nan, np.nan, 2.0]))"),
+    ("x", "J.fromiter([[1, 2], [], [3]])"),
+    ("y", "J.fromiter([[10], [20], [30, 40]])"),
+    ("z", "J.fromiter([[100, 200], [300], [400]])"),
+    ("rec", "J.zip(pt=a, q=i)"),
+    ("flat", "np.array([100.0, 200.0, 300.0, 400.0])"),
+    ("deep", "J.fromcounts([2, 0, 2], J.fromcounts([2, 1, 0, 3], np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])))"),
+    ("i8", "J.fromcounts([3, 0, 2], np.array([100, 100, -7, 5, -128], dtype=np.int8))"),
+    ("u8", "J.fromcounts([3, 0, 2], np.array([200, 100, 7, 5, 255], dtype=np.uint8))"),
+    ("u32", "J.fromcounts([2, 1, 0], np.array([4000000000, 5, 7], dtype=np.uint32))"),
+    ("bl", "J.fromcounts([3, 0, 2, 1], np.array([True, False, True, False, False, True]))"),
+    ("i32", "J.fromcounts([2, 2, 0, 1], np.array([7, -7, 2147483647, 1, -3], dtype=np.int32))"),
+    ("ties", "J.fromiter([[2.0, 1.0, 2.0, 1.0], [0.0, -0.0], [np.nan, 3.0, np.nan], []])"),
+    ("o32", "J.fromoffsets(np.array([0, 2, 2, 5], dtype=np.int32), np.array([1.5, 2.5, 3.5, 4.5, 5.5]))"),
+    ("big", "J.fromcounts(np.array([40, 0, 3, 70]), np.arange(113) * 0.5 - 20)"),
+]
+
+CASES = [
+    # layout, properties
+    "a.counts", "a.offsets", "a.starts", "a.stops", "a.parents", "a.localindex", "a.content", "len(a)", "a.flatten()",
+    "g.counts", "g.parents", "g.localindex", "g.flatten()", "g.compact().offsets", "g.iscompact", "a.iscompact",
+    "e.counts", "e.sum()", "e.max()", "e.argmax()", "e.pairs().counts", "e.flatten()",
+    "J.fromoffsets([0, 2, 2, 5], [1, 2, 3, 4, 5])", "J.fromcounts([2, 0, 3], [1, 2, 3, 4, 5])",
+    "J.fromcounts([2, -1], [1, 2])", "J.fromoffsets([0, 3, 2], [1, 2, 3])", "J.fromoffsets([0, 2, 9], [1, 2, 3])",
+    "J.fromparents([0, 0, 2, 2, 2, 3], [1, 2, 3, 4, 5, 6])", "J.fromuniques([9, 9, 4, 4, 4, 7], [1, 2, 3, 4, 5, 6])",
+    "J.fromlocalindex([0, 1, 0, 0, 1, 2], [1, 2, 3, 4, 5, 6])", "J.fromfolding(np.arange(7), 3)",
+    "J.fromregular(np.arange(6).reshape(3, 2))", "J.fromjagged(g)",
+    # reducers
+    "a.sum()", "a.prod()", "a.min()", "a.max()", "a.any()", "a.all()", "a.count()", "a.count_nonzero()", "a.mean()",
+    "a.var()", "a.std()", "i.sum()", "i.prod()", "i.min()", "i.max()", "i.any()", "i.all()", "f32.sum()", "f32.min()",
+    "f32.max()", "nan.sum()", "nan.min()", "nan.max()", "nan.argmin()", "nan.argmax()", "g.sum()", "g.max()",
+    "a.argmin()", "a.argmax()", "i.argmin()", "i.argmax()", "f32.argmin()", "f32.argmax()", "a[a.argmax()]", "i[i.argmin()]",
+    "(a > 2.5).sum()", "(a > 2.5).any()", "(a > 2.5).all()", "rec.sum().pt", "rec.max().q", "deep.sum()", "deep.max()",
+    "deep.counts", "deep.flatten()", "deep.flatten(axis=1)", "deep.argmax()",
+    # selection
+    "a[a > 2.5]", "a[a <= 2.2]", "a[2.5 < a]", "a[(a > 1) & (a < 8)]", "a[~(a > 1)]", "i[i != 0]", "a[i > 0]", "rec[rec.pt > 2].q",
+    "g[g > 1]", "a[a > 2.5].counts", "a[a > 100]", "nan[nan > 0]", "nan[nan == nan]", "f32[f32 >= -0.0]",
+    "a[J.fromiter([[0, 0, -1], [], [1], [4, 0]])]", "a[J.fromiter([[3], [], [], []])]", "a[J.fromiter([[0], [0], [], []])]",
+    "a[1:]", "a[1:3]", "a[::2]", "a[-1]", "a[3]", "a[7]", "a[np.array([3, 0, 0])]", "a[np.array([True, False, True, False])]",
+    "a[[True, False, True]]", "a[:, 0]", "a[a.counts > 1][:, 0]", "a[a.counts > 1][:, -1]", "a[:, :2]", "a[:, 1:]", "a[:, ::2]",
+    "a[:, ::-1]", "a[1:, :1]", "a[np.array([3, 2])].sum()", "rec[rec.q > 0].pt", "rec[1:].q", "deep[deep > 2]", "deep[:, 0]",
+    # ufuncs and broadcasting
+    "a + b", "a * 2", "2 - a", "a / b", "b // a", "b % 7", "a ** 2", "-a", "np.abs(i)", "np.maximum(a, 3)", "np.minimum(i, 1)",
+    "np.sqrt(b)", "i + a", "i * 2.5", "i // 2", "i % 3", "i & 3", "i | 8", "~i", "a + flat", "flat - a", "a * np.array([1, 0, 1, 0])",
+    "a + a.max()", "a - a.min()", "a > a.mean()", "a + e", "a + np.array([1.0, 2.0])", "np.add(a, b)", "np.greater(a, 3.3)",
+    "a == a", "a != b", "i == 4", "np.isnan(nan)", "np.where", "rec.pt + rec.q", "deep * 2", "deep + deep", "g + 1", "a.tojagged(flat)",
+    "a.tojagged(b.flatten())", "a.tojagged(7)",
+    # combinatorics
+    "a.argpairs()", "a.pairs()", "a.argdistincts()", "a.distincts()", "a.argchoose(2)", "a.choose(3)", "a.argchoose(3)",
+    "a.choose(1)", "a.choose(6)", "x.argcross(y)", "x.cross(y)", "x.cross(y).cross(z)", "x.cross(y).pairs()", "x.pairs().cross(z)",
+    "x.cross(y).i0", "x.cross(y).i1 - x.cross(y).i0", "x.pairs(nested=True)", "x.distincts(nested=True)", "x.cross(y, nested=True)",
+    "x.argpairs(nested=True)", "x.argcross(y, nested=True)", "x.argdistincts(nested=True)", "rec.pairs().i0.pt", "rec.distincts().i1.q",
+    "rec.cross(rec).i1.pt", "x.cross(J.fromiter([[1]]))", "x.cross(np.array([1, 2, 3]))", "(a.pairs().i0 * a.pairs().i1).sum()",
+    "a.pairs().counts", "a.cross(b).counts", "g.pairs()", "g.cross(g).i1", "x.cross(y).unzip()[1]", "x.cross(y).columns",
+    # sorting, padding, concatenation
+    "s.argsort()", "s.argsort(ascending=True)", "s[s.argsort()]", "nan.argsort()", "i.argsort()", "a.pad(3)", "a.pad(2, clip=True)",
+    "a.pad(3).fillna(-1)", "a.pad(2, clip=True).fillna(0).regular()", "J.fromiter([[1, 2], [3, 4]]).regular()", "a.regular()",
+    "a.concatenate([b])", "a.concatenate([b], axis=1)", "J.concatenate([a, b, a])", "J.concatenate([x, y, z], axis=1)",
+    "a.concatenate([e], axis=1)", "rec.concatenate([rec]).pt", "a.fillna(3)", "J.zip(a, b).tolist()", "J.zip(a, b).i1", "rec.columns",
+    "rec.unzip()[0]", "J.zip(a, e)", "rec['pt']", "rec['nope']",
+    # integer / bool / unsigned contents and numpy's promotion rules
+    "i8.sum()", "i8.prod()", "i8.min()", "i8.max()", "i8.argmax()", "i8 + i8", "i8 * 2", "i8 + 1000", "i8 // 3", "i8 % 3", "-i8", "np.abs(i8)",
+    "i8 > 0", "i8 + 0.5", "u8.sum()", "u8.prod()", "u8.max()", "u8.min()", "u8 + u8", "u8 - 201", "u8 // 7", "~u8", "u8 & 15", "u8 > 100",
+    "u8.argmin()", "u32.sum()", "u32 + 1", "u32 * 2", "u32.max()", "u32 > 5", "u32.argmax()", "bl.sum()", "bl.prod()", "bl.min()", "bl.max()",
+    "bl.any()", "bl.all()", "bl.argmax()", "bl.argmin()", "~bl", "bl & bl", "bl | ~bl", "bl + bl", "bl * 3", "bl.count_nonzero()", "a[bl]",
+    "i32.sum()", "i32.prod()", "i32 + 1", "i32 * i32", "i32 // -2", "i32 % -2", "i32 ** 2", "i32 / 2", "i32.max()", "i32.argmin()", "i32 > i32.min()",
+    "np.negative(i32)", "np.sign(i32)", "np.sign(a - 3)", "np.floor(a)", "np.ceil(a)", "np.rint(a)", "np.square(i32)", "np.maximum(i32, 0)",
+    "np.minimum(a, b)", "np.hypot(a, b)", "np.arctan2(a, b)", "np.power(a, 0.5)", "np.remainder(a, 2.5)", "np.floor_divide(b, 3.0)", "np.fabs(-a)",
+    "np.logical_and(a > 1, b < 80)", "np.logical_or(i > 0, i < -1)", "np.logical_not(i)", "np.logical_xor(bl, bl)", "np.isfinite(f32)", "np.isinf(f32)",
+    "np.reciprocal(b)", "np.positive(a)", "np.bitwise_xor(i, 5)", "np.equal(i, 4)", "np.not_equal(a, a)", "np.less(a, 3)", "np.less_equal(3, a)",
+    # ties, signed zeros, NaN
+    "ties.min()", "ties.max()", "ties.argmin()", "ties.argmax()", "ties.sum()", "ties.prod()", "ties.argsort()", "ties.argsort(ascending=True)",
+    "ties[ties.argsort()]", "ties.any()", "ties.all()", "ties.count_nonzero()", "ties == ties", "ties[ties > 0]", "ties[ties >= 0]", "ties[ties < np.inf]",
+    "ties.pairs().counts", "ties.distincts().i0", "-ties", "ties * 0", "ties.mean()", "ties.count()",
+    # int32 offsets keep their dtype in the properties
+    "o32.offsets", "o32.counts", "o32.starts", "o32.sum()", "o32[o32 > 2]", "o32.parents", "o32 + 1",
+    # events longer than a warp
+    "big.sum()", "big.min()", "big.argmax()", "big.argmin()", "big[big > 0].counts", "big.pairs().counts", "big.argsort()[:, :3]", "big[:, ::7]",
+    "big.distincts().i1.sum()", "big.cross(big).counts", "big.choose(3).counts", "(big * 2 - big).sum()", "big.pad(5, clip=True).fillna(0).regular()",
+    "big.localindex[:, -1]", "big.counts", "big[big.argsort()][:, 0]", "big.cross(a.tojagged(flat)[np.array([0, 1, 2, 3])]).i1.sum()",
+]
+
+# statements: (code, expression whose value is recorded afterwards)
+STATEMENTS = [
+    ("t = J.fromiter([[1.0, 2.0, 3.0], [], [4.0, 5.0]]); t[t > 2] = 0", "t"),
+    ("t = J.fromiter([[1.0, 2.0, 3.0], [], [4.0, 5.0]]); t[J.fromiter([[0, -1], [], [1]])] = 9", "t"),
+    ("t = J.fromiter([[1.0, 2.0, 3.0], [], [4.0, 5.0]]); m = t > 2; t[t < 2] = 7; r = t[m]", "r"),
+    ("t = J.zip(u=x, v=x * 2); t['w'] = x + 1", "t.w"),
+    ("t = J.fromiter([[1, 2, 3], [], [4, 5]]); t[t % 2 == 0] = J.fromiter([[20], [], [40]])", "t"),
+    ("t = J.fromiter([[1.5, 2.5], [3.5]]); t[:, 0] = 0", "t"),
+    ("t = J.fromiter([[1, 2, 3], [], [4, 5]]); u = t + 1; t[t > 0] = 0", "u"),
+    ("p = x.pairs(); q = p.i0 * 10 + p.i1; r = q[q > 20]", "r"),
+    ("c = x.cross(y); m = (c.i0 + c.i1) > 11; r = c[m].i1", "r"),
+]
+
+
+def listify(v):
+    if isinstance(v, tuple):
+        return {"tuple": [listify(x) for x in v]}
+    if hasattr(v, "tolist"):
+        v = v.tolist()
+    if isinstance(v, (np.generic,)):
+        v = v.item()
+    return {"value": json.loads(json.dumps(v, default=_default).replace("NaN", '"nan"').replace("-Infinity", '"-inf"').replace("Infinity", '"inf"'))}
+
+
+def _default(o):
+    if isinstance(o, np.generic):
+        return o.item()
+    if hasattr(o, "tolist"):
+        return o.tolist()
+    if isinstance(o, tuple):
+        return list(o)
+    raise TypeError(type(o))
+
+
+def main():
+    ak0 = _refloader.load()
+    env = {"J": ak0.JaggedArray, "np": np}
+    for name, code in SETUP:
+        env[name] = eval(code, env)
+    out = {"setup": SETUP, "cases": [], "statements": []}
+
+    def record(expr, scope):
+        try:
+            with np.errstate(all="ignore"):
+                v = eval(expr, scope)
+            if callable(v) and not hasattr(v, "tolist"):
+                return None
+            return listify(v)
+        except Exception as err:
+            return {"raises": type(err).__name__}
+
+    for expr in CASES:
+        r = record(expr, env)
+        if r is not None:
+            out["cases"].append({"expr": expr, "expect": r})
+    for code, expr in STATEMENTS:
+        scope = dict(env)
+        try:
+            exec(code, scope)
+            out["statements"].append({"code": code, "expr": expr, "expect": record(expr, scope)})
+        except Exception as err:
+            out["statements"].append({"code": code, "expr": expr, "expect": {"raises": type(err).__name__}})
+    path = os.path.join(ROOT, "tests", "golden", "api_cases.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=0)
+    n_raise = sum(1 for c in out["cases"] if "raises" in c["expect"])
+    print(len(out["cases"]), "cases (", n_raise, "raise ),", len(out["statements"]), "statements ->", path)
+    for c in out["cases"]:
+        if "raises" in c["expect"]:
+            print("   raises", c["expect"]["raises"], ":", c["expr"])
+
+
+if __name__ == "__main__":
+    main()
