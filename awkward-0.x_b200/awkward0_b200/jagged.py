@@ -539,7 +539,13 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         counts = empty(n, INDEXTYPE)
         call("jg_startsstops2counts", s64.data_ptr(), e64.data_ptr(), n, _vp(counts), runtime.stream())
         offsets, total, _ = self._scan_counts(DeviceArray(counts, INDEXTYPE))
-        content = self._map_content(lambda c: self._compact_column(c, s64, offsets, n, total))
+        if isinstance(self._content, JaggedArray):
+            # jagged-of-jagged: the inner EVENTS are picked (the list of reachable inner event numbers is the
+            # compaction of an arange); the inner array is left in general layout and compacts itself on first use
+            picks = self._compact_column(_ufunc.arange(len(self._content)), s64, offsets, n, total)
+            content = self._content[picks]
+        else:
+            content = self._map_content(lambda c: self._compact_column(c, s64, offsets, n, total))
         out = self._make(offsets, content, total)
         out._counts = DeviceArray(counts, INDEXTYPE)
         return out
@@ -1147,7 +1153,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         lead = None
         for x in inputs:
             if isinstance(x, JaggedArray):
-                lead = x
+                if lead is None or isinstance(x._content, JaggedArray) or not isinstance(lead._content, JaggedArray):
+                    lead = x                      # the last jagged operand, a doubly jagged one if there is any
         a, off, n, first, last = lead._dense()
         if isinstance(a._content, JaggedArray):
             # jagged-of-jagged (jagged.py:1039-1051): flatten one level, let the inner arrays broadcast, re-wrap
@@ -1155,8 +1162,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             for x in inputs:
                 if isinstance(x, JaggedArray):
                     b = a._align(x) if x is not lead else a
-                    if not isinstance(b._content, JaggedArray):
-                        raise NotImplementedError("mixing nesting depths in one ufunc is outside the GPU hot path")
+                    # a singly jagged operand (e.g. deep.max()) has one value per inner event: the inner ufunc
+                    # broadcasts it as a flat array (jagged.py:1039-1051 via _tojagged)
                     inner_ops.append(b._dense_content())
                 elif _ufunc.is_scalar(x):
                     inner_ops.append(x)
@@ -1260,6 +1267,9 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def count(self):
         """base.py:199-200 / jagged.py:1513-1518: number of non-NaN values per event."""
         a = self.compact()
+        if isinstance(a._content, JaggedArray):          # jagged.py:1463-1464: the innermost level is counted
+            a, off, n, first, last = self._dense()
+            return self._make(a._rebased_offsets(), a._dense_content().count(), last - first)
         if isinstance(a._content, DeviceArray) and a._content.dtype.kind == "f":
             return (~numpy.isnan(a)).sum()
         return a.counts.astype(INDEXTYPE) if a.counts.dtype != INDEXTYPE else a.counts
@@ -1398,11 +1408,24 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         poff, total = self._comb_offsets(kind, 2, off, off_b, n)
         ctx = _lazy.CombContext(kind, off, off_b, n, poff, total)
 
+        picks = {}
+
         def side(content, which):
+            """Flat columns are deferred gathers; a jagged column (combinations of whole inner lists) is picked
+            event-wise with the absolute positions of the combination's items (jagged.py:1294 on a JaggedArray)."""
             leaves = list(_leaves(content))
-            if any(not isinstance(x, DeviceArray) for x in leaves):
-                raise NotImplementedError("combinatorics over nested content are outside the GPU hot path")
-            return _rebuild(content, iter([ctx.leaf(which, c) for c in leaves]))
+            out = []
+            for c in leaves:
+                if isinstance(c, JaggedArray):
+                    if not picks:
+                        args = self._comb_indices(kind, 2, other=other, absolute=True)
+                        picks["L"], picks["R"] = args._content["0"], args._content["1"]
+                    out.append(c[picks[which]])
+                elif isinstance(c, DeviceArray):
+                    out.append(ctx.leaf(which, c))
+                else:
+                    raise NotImplementedError("combinatorics over masked content are outside the GPU hot path; call fillna() first")
+            return _rebuild(content, iter(out))
 
         left, right = side(a._content, "L"), side(b._content, "R")
         return self._make(poff, Table.named("tuple", left, right).flattentuple(), total)      # jagged.py:1271,1294,1350

@@ -189,7 +189,9 @@ startsstops2parents_kernel(const int64_t *__restrict__ starts, const int64_t *__
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int64_t b = min(stops[i], out_len);
-        for (int64_t j = starts[i]; j < b; ++j) out[j] = i;
+        // events may overlap (a[[2, 2]]): numpy's `out[content_indexes] = parents` (jagged.py:69) leaves the LAST
+        // event's index, i.e. the largest one -- an atomic max instead of a racing plain store
+        for (int64_t j = starts[i]; j < b; ++j) atomicMax(reinterpret_cast<long long *>(out) + j, static_cast<long long>(i));
     }
 }
 

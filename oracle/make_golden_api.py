@@ -39,6 +39,12 @@ SETUP = [
     ("ties", "J.fromiter([[2.0, 1.0, 2.0, 1.0], [0.0, -0.0], [np.nan, 3.0, np.nan], []])"),
     ("o32", "J.fromoffsets(np.array([0, 2, 2, 5], dtype=np.int32), np.array([1.5, 2.5, 3.5, 4.5, 5.5]))"),
     ("big", "J.fromcounts(np.array([40, 0, 3, 70]), np.arange(113) * 0.5 - 20)"),
+    ("v", "a[1:]"),                                  # dense view, offsets[0] != 0
+    ("w", "a[np.array([3, 0, 2, 2])]"),              # general layout: reordered, repeated events
+    ("h", "J([1, 5, 5], [4, 7, 5], np.arange(10) * 1.0)"),   # general layout with unreachable content
+    ("recg", "rec[np.array([2, 0, 3])]"),
+    ("deepg", "deep[np.array([2, 0])]"),
+    ("d2", "J.fromcounts([1, 2], J.fromcounts([2, 0, 3], np.array([5.0, 1.0, 2.0, 9.0, 4.0])))"),
 ]
 
 CASES = [
@@ -104,7 +110,28 @@ CASES = [
     "big.sum()", "big.min()", "big.argmax()", "big.argmin()", "big[big > 0].counts", "big.pairs().counts", "big.argsort()[:, :3]", "big[:, ::7]",
     "big.distincts().i1.sum()", "big.cross(big).counts", "big.choose(3).counts", "(big * 2 - big).sum()", "big.pad(5, clip=True).fillna(0).regular()",
     "big.localindex[:, -1]", "big.counts", "big[big.argsort()][:, 0]", "big.cross(a.tojagged(flat)[np.array([0, 1, 2, 3])]).i1.sum()",
+    # views and general layouts go through the same operations
+    "v", "v.offsets", "v.counts", "v.parents", "v.localindex", "v.sum()", "v.argmax()", "v[v > 4]", "v[v.argmax()]", "v + 1", "v + v", "v.pairs()",
+    "v.cross(v).i1", "v.flatten()", "v.argsort()", "v.pad(2, clip=True).fillna(0)", "v.concatenate([v], axis=1)", "v[:, 0]", "v[1:]", "v.tojagged(np.array([1, 2, 3]))",
+    "v + np.array([10, 20, 30])", "v.content", "v.compact().content", "v.iscompact", "v.max()", "v[v > 100]", "v.distincts().i0", "v.mean()", "v.starts", "v.stops",
+    "w", "w.counts", "w.starts", "w.stops", "w.iscompact", "w.sum()", "w.max()", "w.argmax()", "w[w.argmax()]", "w[w > 4]", "w + 1", "w * w", "w.flatten()",
+    "w.compact().offsets", "w.parents", "w.localindex", "w.pairs().i1", "w.cross(w).counts", "w.argsort()", "w[:, :1]", "w[1:3]", "w[np.array([True, False, True, True])]",
+    "w.concatenate([w])", "w.concatenate([w], axis=1)", "w.pad(3).fillna(0)", "w + np.array([1, 2, 3, 4])", "w.tojagged(w.sum())", "w[w.counts > 2]", "w.choose(2)",
+    "w[J.fromiter([[0], [2], [1, 0], []])]", "h", "h.counts", "h.sum()", "h.parents", "h.flatten()", "h.compact().content", "h[h > 2]", "h.argmin()", "h + h", "h.pairs().i0",
+    "h.cross(h).i1", "h.localindex", "h.iscompact", "h.offsets", "h[::-1]", "h[h.argmax()]", "h.pad(2).fillna(-1)",
+    # records and nesting in general layouts
+    "recg.pt", "recg.q", "recg[recg.q > 0].pt", "recg.sum().pt", "recg.pairs().i0.q", "recg.counts", "recg.flatten().pt", "recg.argmax().q", "recg[recg.pt.argmax()].q",
+    "recg.concatenate([recg]).q", "recg.pt + recg.q", "recg.pad(2, clip=True).pt.fillna(0)", "rec.distincts().i0.pt - rec.distincts().i1.pt", "rec.cross(rec, nested=True).i0.q",
+    "rec[:, :2].pt", "rec[a > 3].q", "rec.pt.argsort()", "rec[rec.pt.argsort()].q", "J.zip(rec.pt, rec.q * 2).i1", "rec.choose(2).i1.pt",
+    "deepg", "deepg.counts", "deepg.sum()", "deepg.flatten()", "deepg.flatten(axis=1)", "deepg + 1", "deepg.max()", "deepg.argmax()", "deep[deep.argmax()]",
+    "deep.any()", "deep.count()", "deep.min()", "deep * deep", "deep - deep.max()", "deep.flatten().sum()", "deep.sum().sum()", "deep[1:]", "deep[::2].sum()", "deep.pairs().counts",
+    "d2", "d2.sum()", "d2.max().max()", "d2.flatten(axis=1).argmax()", "d2[d2 > 1.5].counts", "d2.argmin()", "d2[d2.argmin()]", "d2 + d2.flatten(axis=1).max()",
+    "x.cross(y, nested=True).i0 + x.cross(y, nested=True).i1", "(x.cross(y, nested=True).i1 > 15).any()", "x.cross(y, nested=True).i1.min()", "x.pairs(nested=True).i1.sum()",
+    "x.cross(y, nested=True).flatten(axis=1).i1", "x.cross(y, nested=True).i1.argmax()", "x.distincts(nested=True).i0.counts", "x.argcross(y, nested=True).flatten(axis=1).i0",
 ]
+
+# (not in the battery: `deepg[deepg > 2]` -- a mask over a doubly jagged array in general layout; the reference raises
+# ValueError from its shape check although the operation is well defined, the device class computes it)
 
 # statements: (code, expression whose value is recorded afterwards)
 STATEMENTS = [
@@ -159,7 +186,7 @@ def main():
 
     for expr in CASES:
         r = record(expr, env)
-        if r is not None:
+        if r is not None and r.get("raises") != "AssertionError":      # an internal assert tripping is not behaviour to pin
             out["cases"].append({"expr": expr, "expect": r})
     for code, expr in STATEMENTS:
         scope = dict(env)
