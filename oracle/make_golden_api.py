@@ -147,9 +147,30 @@ STATEMENTS = [
 ]
 
 
+def leaf_dtype(v):
+    """dtype of an array result, or of the innermost content of a (nested) JaggedArray; None for records / scalars."""
+    for _ in range(4):
+        if isinstance(v, np.ndarray):
+            return str(v.dtype)
+        if type(v).__name__ == "JaggedArray":
+            v = v.content
+        else:
+            break
+    return None
+
+
 def listify(v):
     if isinstance(v, tuple):
         return {"tuple": [listify(x) for x in v]}
+    dt = leaf_dtype(v)
+    if dt is not None:
+        out = listify_value(v)
+        out["dtype"] = dt
+        return out
+    return listify_value(v)
+
+
+def listify_value(v):
     if hasattr(v, "tolist"):
         v = v.tolist()
     if isinstance(v, (np.generic,)):

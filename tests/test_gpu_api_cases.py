@@ -29,14 +29,29 @@ def env():
     return scope
 
 
+def leaf_dtype(v):
+    """dtype of an array result, or of the innermost content of a (nested) JaggedArray; None for records / scalars."""
+    for _ in range(4):
+        name = type(v).__name__
+        if name in ("DeviceArray", "LazyArray", "LazyCompare", "DeviceMatrix", "ndarray"):
+            return str(v.dtype)
+        if name == "JaggedArray":
+            v = v.content
+        else:
+            break
+    return None
+
+
 def listify(v):
     if isinstance(v, tuple):
         return {"tuple": [listify(x) for x in v]}
+    out = {"dtype": leaf_dtype(v)}
     if hasattr(v, "tolist"):
         v = v.tolist()
     if isinstance(v, np.generic):
         v = v.item()
-    return {"value": v}
+    out["value"] = v
+    return out
 
 
 def same(got, want):
@@ -82,8 +97,12 @@ def check(expr, expect, got):
         assert "tuple" in got and len(got["tuple"]) == len(expect["tuple"]), expr
         for g, w in zip(got["tuple"], expect["tuple"]):
             assert same(g["value"], w["value"]), "{0}: {1} != {2}".format(expr, g["value"], w["value"])
+            if w.get("dtype") is not None and g.get("dtype") is not None:
+                assert g["dtype"] == w["dtype"], "{0}: dtype {1}, reference {2}".format(expr, g["dtype"], w["dtype"])
         return
     assert same(got["value"], expect["value"]), "{0}: got {1}, reference {2}".format(expr, got["value"], expect["value"])
+    if expect.get("dtype") is not None and got.get("dtype") is not None:
+        assert got["dtype"] == expect["dtype"], "{0}: dtype {1}, reference {2}".format(expr, got["dtype"], expect["dtype"])
 
 
 @pytest.mark.parametrize("case", DATA["cases"], ids=[c["expr"] for c in DATA["cases"]])
