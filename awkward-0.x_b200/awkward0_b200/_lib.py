@@ -51,6 +51,7 @@ PROTOTYPES = {
     "jg_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "jg_workspace_bytes": (_sz, [_i64]),
     "jg_counts2offsets": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_counts2offsets_tiles": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_offsets2counts": (_i, [_vp, _i64, _vp, _vp]),
     "jg_startsstops2counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "jg_validate_offsets": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
@@ -71,6 +72,7 @@ PROTOTYPES = {
     "jg_segreduce": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "jg_segargminmax": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "jg_segargminmax_dense": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_segargminmax_dense_tiles": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compare_select": (_i, [_vp, _i, _vp, _i, _i, _d, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -108,7 +110,7 @@ def check(rc, what):
 # kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
 LAUNCHES = [0]
 _KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
-            "jg_mask_select": 3, "jg_compare_select": 3, "jg_segargminmax_dense": 3, "jg_flat_compact": 2}
+            "jg_mask_select": 3, "jg_compare_select": 3, "jg_segargminmax_dense": 3, "jg_segargminmax_dense_tiles": 2, "jg_flat_compact": 2}
 
 
 def call(name, *args):

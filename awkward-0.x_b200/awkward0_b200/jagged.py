@@ -89,7 +89,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return offsets
 
     @classmethod
-    def _scan_counts(cls, counts, sync=True):
+    def _scan_counts(cls, counts, sync=True, tiles=False):
         if counts.dtype == numpy.int64 or counts.dtype == numpy.int32:
             src = counts
         elif counts.dtype == numpy.bool_ or counts.dtype == numpy.uint8:
@@ -102,11 +102,21 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         offsets = empty(n + 1, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
-        call("jg_counts2offsets", src.data_ptr(), jg_code(src.dtype), n, _vp(offsets), _vp(scal), _vp(scal, 1), ws, wsb,
-             runtime.stream())
+        if tiles and n > 0 and src.dtype.itemsize >= 4:
+            # the same pass also counts the non-empty events of every 512-event tile (what a dense argmin / argmax
+            # needs to place its results): jg_segargminmax_dense_tiles then skips its own pass over the offsets
+            tile_nonempty = empty((n + 511) // 512, INDEXTYPE)
+            call("jg_counts2offsets_tiles", src.data_ptr(), jg_code(src.dtype), n, _vp(offsets), _vp(tile_nonempty),
+                 _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
+        else:
+            tile_nonempty = None
+            call("jg_counts2offsets", src.data_ptr(), jg_code(src.dtype), n, _vp(offsets), _vp(scal), _vp(scal, 1), ws,
+                 wsb, runtime.stream())
         total, status = None, 0
         if sync:
             total, status, _ = runtime.read(scal)
+        if tiles:
+            return DeviceArray(offsets, INDEXTYPE), total, status, tile_nonempty
         return DeviceArray(offsets, INDEXTYPE), total, status
 
     @classmethod
@@ -198,6 +208,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         self._rebased = None
         self._general = None
         self._maxcount = None
+        self._tile_nonempty = None       # non-empty events per 512-event tile, a by-product of fromcounts' scan
         self._arg_source = None          # set on argmin/argmax results: (offsets, content) they were computed from
         self._arg_values = None
 
@@ -327,10 +338,11 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if counts.dtype == numpy.bool_:
             raise TypeError("counts must have integer dtype")
         content = cls._tocontent(content)
-        offsets, total, status = cls._scan_counts(counts)
+        offsets, total, status, tile_nonempty = cls._scan_counts(counts, tiles=True)
         if status & _lib.ST_NEGATIVE_COUNT:
             raise ValueError("counts must be a non-negative array")
         out = cls._make(offsets, content, total)
+        out._tile_nonempty = tile_nonempty
         out._counts = counts
         out._isvalid = False
         out._pending_status = _lib.ST_BEYOND_CONTENT if total > len(content) else 0
@@ -1321,8 +1333,9 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
         values = empty(n, col.dtype) if self.cache_arg_values else None
-        call("jg_segargminmax_dense", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
-             _vp(out_offsets), _vp(out_index), _vp(values), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
+        tiles = a._tile_nonempty               # known when the array came from fromcounts: no counting pass
+        call("jg_segargminmax_dense_tiles", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
+             _vp(tiles), _vp(out_offsets), _vp(out_index), _vp(values), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
         total, status, _ = runtime.read(scal)
         if status & _lib.ST_ARG_ALLNAN:
             values = None

@@ -55,11 +55,11 @@ def _register(x):
 def flush_all():
     """Compute every deferred value now.  Called before anything is written IN PLACE (jg_put, the store side of
     __setitem__): a deferred value must not see data that changed after the expression was written."""
-    for r in list(_DEFERRED.values()):
+    for k, r in list(_DEFERRED.items()):
         x = r()
         if x is not None and x._mat is None:
             x.tensor
-    _DEFERRED.clear()
+        _DEFERRED.pop(k, None)           # (values registered while this runs stay registered)
 
 
 class JgEvalProgram(ctypes.Structure):

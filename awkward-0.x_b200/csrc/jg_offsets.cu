@@ -358,6 +358,21 @@ int jg_counts2offsets(const void *counts, int counts_dtype, int64_t n, int64_t *
     return -2;
 }
 
+int jg_counts2offsets_tiles(const void *counts, int counts_dtype, int64_t n, int64_t *offsets, int64_t *tile_nonempty,
+                            int64_t *total, int32_t *status, void *ws, size_t ws_bytes, void *stream) {
+    JG_REQUIRE(n >= 0 && offsets != nullptr && tile_nonempty != nullptr, "jg_counts2offsets_tiles: bad arguments");
+    static_assert(kTileEvents == 512, "the scan counts non-empty events per 512-event tile");
+    cudaStream_t s = as_stream(stream);
+    switch (counts_dtype) {
+        case JG_I64:
+            return launch_scan_array(static_cast<const int64_t *>(counts), n, offsets, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_I32:
+            return launch_scan_array(static_cast<const int32_t *>(counts), n, offsets, total, status, ws, ws_bytes, s, tile_nonempty);
+    }
+    set_error("jg_counts2offsets_tiles: counts dtype %d (int32 / int64 only)", counts_dtype);
+    return -2;
+}
+
 int jg_offsets2counts(const int64_t *offsets, int64_t n, int64_t *counts, void *stream) {
     if (n <= 0) return 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(offsets) | reinterpret_cast<uintptr_t>(counts)) & 15) == 0;

@@ -634,7 +634,7 @@ static int dispatch_arg(int is_min, const void *content, const int64_t *offsets,
 template <typename T>
 static int dispatch_arg_dense(int is_min, const void *content, const int64_t *offsets, int64_t n, int64_t *out_offsets,
                               int64_t *out_index, void *out_value, int64_t *total, int32_t *status, void *ws,
-                              size_t ws_bytes, cudaStream_t s) {
+                              size_t ws_bytes, cudaStream_t s, const int64_t *tile_nonempty) {
     const int64_t ntiles = tile_grid(n);
     // workspace: [totals: nt+2][bases: nt+2][scan descriptors]
     const size_t arr = ((static_cast<size_t>(ntiles) + 2) * 8 + 255) & ~static_cast<size_t>(255);
@@ -645,11 +645,15 @@ static int dispatch_arg_dense(int is_min, const void *content, const int64_t *of
     int64_t *totals = static_cast<int64_t *>(ws);
     int64_t *bases = reinterpret_cast<int64_t *>(static_cast<char *>(ws) + arr);
     void *scan_ws = static_cast<char *>(ws) + 2 * arr;
-    count_nonempty_kernel<<<static_cast<unsigned>(ceil_div(ntiles, kTileThreads / kWarp)), kTileThreads, 0, s>>>(
-        offsets, n, ntiles, totals);
-    int rc = check_launch("count_nonempty_kernel");
-    if (rc) return rc;
-    rc = launch_scan_array(totals, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
+    int rc = 0;
+    if (tile_nonempty == nullptr) {
+        count_nonempty_kernel<<<static_cast<unsigned>(ceil_div(ntiles, kTileThreads / kWarp)), kTileThreads, 0, s>>>(
+            offsets, n, ntiles, totals);
+        rc = check_launch("count_nonempty_kernel");
+        if (rc) return rc;
+        tile_nonempty = totals;
+    }
+    rc = launch_scan_array(tile_nonempty, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
     if (rc) return rc;
     if (is_min)
         segarg_direct_kernel<true, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
@@ -723,26 +727,33 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
     return -2;
 }
 
-int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
-                          int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total, int32_t *status,
-                          void *ws, size_t ws_bytes, void *stream) {
+int jg_segargminmax_dense_tiles(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                                const int64_t *tile_nonempty, int64_t *out_offsets, int64_t *out_index, void *out_value,
+                                int64_t *total, int32_t *status, void *ws, size_t ws_bytes, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && out_offsets, "jg_segargminmax_dense: bad arguments");
     cudaStream_t s = as_stream(stream);
     switch (dtype) {
-        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_F32: return dispatch_arg_dense<float>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_F64: return dispatch_arg_dense<double>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_I32: return dispatch_arg_dense<int32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_I64: return dispatch_arg_dense<int64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
         case JG_U8:
-        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_I8: return dispatch_arg_dense<int8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_I16: return dispatch_arg_dense<int16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_U16: return dispatch_arg_dense<uint16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_U32: return dispatch_arg_dense<uint32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
-        case JG_U64: return dispatch_arg_dense<uint64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s);
+        case JG_B8: return dispatch_arg_dense<uint8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_I8: return dispatch_arg_dense<int8_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_I16: return dispatch_arg_dense<int16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_U16: return dispatch_arg_dense<uint16_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_U32: return dispatch_arg_dense<uint32_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
+        case JG_U64: return dispatch_arg_dense<uint64_t>(is_min, content, offsets, n, out_offsets, out_index, out_value, total, status, ws, ws_bytes, s, tile_nonempty);
     }
     set_error("jg_segargminmax_dense: unsupported dtype %d", dtype);
     return -2;
+}
+
+int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                          int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total, int32_t *status,
+                          void *ws, size_t ws_bytes, void *stream) {
+    return jg_segargminmax_dense_tiles(content, dtype, offsets, n, is_min, nullptr, out_offsets, out_index, out_value, total,
+                                       status, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

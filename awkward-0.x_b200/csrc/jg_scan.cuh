@@ -214,7 +214,10 @@ constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 4096 items
 struct XfIdentity {
     static constexpr int EXTRA = 0;      // staged entries beyond the tile's items
     static constexpr int ARRAYS = 1;
+    static constexpr bool NONEMPTY = true;
     int kind, k;
+    int64_t *tile_nonempty = nullptr;    // optional by-product: non-zero items per 512 consecutive items (event tile)
+    int64_t n_event_tiles = 0;
     template <typename T>
     __device__ __forceinline__ int64_t item(const T *a, const T *, int p) const { return static_cast<int64_t>(a[p]); }
 };
@@ -222,6 +225,7 @@ template <int NARR>
 struct XfComb {
     static constexpr int EXTRA = 1;
     static constexpr int ARRAYS = NARR;
+    static constexpr bool NONEMPTY = false;
     int kind, k;
     template <typename T>
     __device__ __forceinline__ int64_t item(const T *a, const T *b, int p) const {
@@ -296,11 +300,23 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         }
         stage_wait(&s_bar[0], 0);
     }
-    // phase A: warp sums + validity flags
+    // phase A: warp sums + validity flags (+ non-empty events per 512-event tile: what a dense argmin / argmax needs
+    // to place its results, jg_segargminmax_dense -- a by-product of a pass that reads every count anyway)
+    constexpr int SUBS = TILE / 512;
+    static_assert(!XF::NONEMPTY || (TILE % 512 == 0 && (ITEMS * kWarp) % 64 == 0), "event tiles must tile the scan tile");
+    __shared__ int s_ne[SUBS > 0 ? SUBS : 1];
+    bool count_ne = false;
+    if constexpr (XF::NONEMPTY) {
+        count_ne = xf.tile_nonempty != nullptr;
+        if (count_ne && tid < SUBS) s_ne[tid] = 0;
+        if (count_ne) __syncthreads();
+    }
     const int wbase = warp * (ITEMS * kWarp);
     int64_t sum = 0;
     bool neg = false, big = false;
     const bool full = valid == TILE;
+    int ne_lo = 0, ne_hi = 0;                    // a warp's 64-item rows fall into at most two event tiles
+    const int sub_lo = wbase >> 9;
 #pragma unroll
     for (int r = 0; r < ITEMS / 2; ++r) {
         const int p = wbase + r * 64 + lane * 2;
@@ -309,6 +325,23 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         neg |= (x < 0) | (y < 0);
         big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
         sum += x + y;
+        if constexpr (XF::NONEMPTY) {
+            if (count_ne) {
+                const int c = (x > 0) + (y > 0);
+                if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
+                else ne_hi += c;
+            }
+        }
+    }
+    if constexpr (XF::NONEMPTY) {
+        if (count_ne) {
+            ne_lo = warp_reduce_add(ne_lo);
+            ne_hi = warp_reduce_add(ne_hi);
+            if (lane == 0) {
+                if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
+                if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
+            }
+        }
     }
     if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
     sum = warp_reduce_add(sum);
@@ -329,6 +362,12 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         }
     }
     __syncthreads();
+    if constexpr (XF::NONEMPTY) {
+        if (count_ne && tid < SUBS) {
+            const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
+            if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
+        }
+    }
     const int64_t run = s_base + s_warp[warp];
     if (valid == TILE) {
         if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
@@ -367,9 +406,12 @@ int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
 
 template <typename T>
 int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws,
-                      size_t ws_bytes, cudaStream_t stream) {
-    return launch_scan_tma<T, XfIdentity, kScanTmaItems>(XfIdentity{0, 0}, in, static_cast<const T *>(nullptr), n, out,
-                                                        total, status, ws, ws_bytes, stream);
+                      size_t ws_bytes, cudaStream_t stream, int64_t *tile_nonempty = nullptr) {
+    XfIdentity xf{0, 0};
+    xf.tile_nonempty = tile_nonempty;
+    xf.n_event_tiles = n <= 0 ? 0 : (n + 511) / 512;
+    return launch_scan_tma<T, XfIdentity, kScanTmaItems>(xf, in, static_cast<const T *>(nullptr), n, out, total, status,
+                                                        ws, ws_bytes, stream);
 }
 
 // Host launcher.  `out` has n+1 entries: out[i] = sum of items before i, out[n] = grand total.

@@ -288,7 +288,7 @@ def run_gpu(args):
     peaks = load_peaks()
     roof = None
     if ops:
-        step_ops = ["counts2offsets", "segreduce_sum_f32", "segargmax_dense_f32", "compare_select_f32"]       # a[a > 20] is one fused op; it writes its counts itself
+        step_ops = ["counts2offsets_tiles", "segreduce_sum_f32", "segargmax_dense_tiles_f32", "compare_select_f32"]       # a[a > 20] is one fused op; it writes its counts itself
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
         traffic = None
         try:
@@ -404,6 +404,13 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     add("segargmax_dense_f32", v * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
         "jg_segargminmax_dense", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(aoff), _vp(aidx), ctypes.c_void_p(0), _vp(scal),
         _vp(scal, 1), ws, wsb, st()))
+    # what the sweep runs: the array came from fromcounts, whose scan also counted the non-empty events per tile
+    tiles = empty((N + 511) // 512, np.int64)
+    add("counts2offsets_tiles", 8 * N + 8 * (N + 1), N, lambda: _lib.call(
+        "jg_counts2offsets_tiles", counts_dev.data_ptr(), _lib.JG_I64, N, _vp(offsets_out), _vp(tiles), _vp(scal), _vp(scal, 1), ws, wsb, st()))
+    add("segargmax_dense_tiles_f32", v * M + 8 * N + 8 * N + 8 * N, M, lambda: _lib.call(
+        "jg_segargminmax_dense_tiles", pt_dev.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(tiles), _vp(aoff), _vp(aidx),
+        ctypes.c_void_p(0), _vp(scal), _vp(scal, 1), ws, wsb, st()))
     add("compact_nonneg", 8 * N + 8 * N + 8 * N, N, lambda: _lib.call(
         "jg_compact_nonneg", _vp(best), N, _vp(aoff), _vp(aidx), _vp(scal), ws, wsb, st()))
     mask = empty(M, np.bool_)

@@ -97,6 +97,13 @@ size_t      jg_workspace_bytes(int64_t n);
  * JG_ST_NEGATIVE_COUNT is raised in *status for negative counts (jagged.py:160).                              */
 int jg_counts2offsets(const void *counts, int counts_dtype, int64_t n, int64_t *offsets, int64_t *total,
                       int32_t *status, void *ws, size_t ws_bytes, void *stream);
+/* The same scan that also reports, for every tile of 512 consecutive events, how many events are non-empty
+ * (tile_nonempty: ceil(n / 512) entries; int32 / int64 counts).  jg_segargminmax_dense_tiles takes that array and
+ * skips its own 8N-byte counting pass: the reference's argmin / argmax (jagged.py:1581-1601) on an array built by
+ * fromcounts (jagged.py:155-166) then moves exactly its algorithmic bytes.                                          */
+int jg_counts2offsets_tiles(const void *counts, int counts_dtype, int64_t n, int64_t *offsets, int64_t *tile_nonempty,
+                            int64_t *total, int32_t *status, void *ws, size_t ws_bytes, void *stream);
+
 /* jagged.py:383-388  counts = stops - starts (offsets[1:] - offsets[:-1]) */
 int jg_offsets2counts(const int64_t *offsets, int64_t n, int64_t *counts, void *stream);
 /* general layout: counts[i] = stops[i] - starts[i] */
@@ -138,6 +145,11 @@ int jg_segargminmax(const void *content, int dtype, const int64_t *offsets, int6
 int jg_segargminmax_dense(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
                           int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total, int32_t *status,
                           void *ws, size_t ws_bytes, void *stream);
+int jg_segargminmax_dense_tiles(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min,
+                                const int64_t *tile_nonempty /* from jg_counts2offsets_tiles, or NULL */,
+                                int64_t *out_offsets, int64_t *out_index, void *out_value, int64_t *total,
+                                int32_t *status, void *ws, size_t ws_bytes, void *stream);
+
 /* out_value (optional, content dtype, n items): the extreme value of every event that has one, in the same dense
  * order as out_index -- i.e. the "leading object" a[a.argmax()] (jagged.py:541-560 applied to the result) without
  * the gather pass.                                                                                                 */

@@ -224,3 +224,26 @@ def test_unaligned_views(ak, shift):
         with np.errstate(all="ignore"):
             assert same(b.min().get(), O.reduce(off, vals, "min"))
         assert same(b.argpairs().i1.content.get(), O.argpairs(off)[2])
+
+
+@pytest.mark.parametrize("n", [1, 511, 512, 513, 3071, 3072, 3073, 6145, 100003])
+@pytest.mark.parametrize("cdtype", [np.int64, np.int32])
+def test_argmax_with_tile_counts_from_the_scan(ak, n, cdtype):
+    """fromcounts' scan also counts the non-empty events per 512-event tile and argmin / argmax use that instead of
+    their own pass over the offsets: same answers as the oracle and as an array built by fromoffsets (own pass)."""
+    rng = np.random.default_rng(n)
+    counts = (rng.poisson(1.2, n) * (rng.random(n) < 0.7)).astype(cdtype)          # many empty events
+    m = int(counts.sum())
+    x = rng.normal(size=m).astype(np.float32)
+    off = O.counts2offsets(counts)
+    a = ak.JaggedArray.fromcounts(counts, x)
+    assert (a._tile_nonempty is not None) == (n > 0)
+    assert np.array_equal(a._tile_nonempty.cpu().numpy(), np.add.reduceat((counts > 0).astype(np.int64), np.arange(0, n, 512)))
+    b = ak.JaggedArray.fromoffsets(off, x)
+    assert b._tile_nonempty is None
+    for ismin in (False, True):
+        woff, widx = O.argminmax(off, x, ismin)
+        for arr in (a, b):
+            r = arr.argmin() if ismin else arr.argmax()
+            assert np.array_equal(r.offsets.get(), woff) and np.array_equal(r.content.get(), widx)
+    assert same(a[a.argmax()].content.get(), x[(off[:-1][counts > 0] + O.argminmax(off, x, False)[1])])
