@@ -211,16 +211,19 @@ constexpr int kScanTmaItems = 24;                                   // per threa
 constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 4096 items
 
 // what a staged tile means: the items themselves, or offsets whose differences feed a combinatorial count
-struct XfIdentity {
+template <bool COUNT_NONEMPTY>
+struct XfItems {
     static constexpr int EXTRA = 0;      // staged entries beyond the tile's items
     static constexpr int ARRAYS = 1;
-    static constexpr bool NONEMPTY = true;
+    static constexpr bool NONEMPTY = COUNT_NONEMPTY;
     int kind, k;
-    int64_t *tile_nonempty = nullptr;    // optional by-product: non-zero items per 512 consecutive items (event tile)
+    int64_t *tile_nonempty = nullptr;    // by-product (COUNT_NONEMPTY): non-zero items per 512 consecutive items (event tile)
     int64_t n_event_tiles = 0;
     template <typename T>
     __device__ __forceinline__ int64_t item(const T *a, const T *, int p) const { return static_cast<int64_t>(a[p]); }
 };
+using XfIdentity = XfItems<false>;
+using XfIdentityTiles = XfItems<true>;
 template <int NARR>
 struct XfComb {
     static constexpr int EXTRA = 1;
@@ -286,6 +289,9 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     const int64_t left = n - i0;
     const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
 
+    constexpr int kSubs = XF::NONEMPTY ? TILE / 512 : 1;
+    __shared__ int s_ne[kSubs];
+    if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;          // (published by the barrier inside stage_init)
     stage_init(s_bar, 2);
     const T *sa = reinterpret_cast<const T *>(s_raw_a);
     const T *sb = reinterpret_cast<const T *>(s_raw_b);
@@ -304,19 +310,11 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     // to place its results, jg_segargminmax_dense -- a by-product of a pass that reads every count anyway)
     constexpr int SUBS = TILE / 512;
     static_assert(!XF::NONEMPTY || (TILE % 512 == 0 && (ITEMS * kWarp) % 64 == 0), "event tiles must tile the scan tile");
-    __shared__ int s_ne[SUBS > 0 ? SUBS : 1];
-    bool count_ne = false;
-    if constexpr (XF::NONEMPTY) {
-        count_ne = xf.tile_nonempty != nullptr;
-        if (count_ne && tid < SUBS) s_ne[tid] = 0;
-        if (count_ne) __syncthreads();
-    }
+    constexpr bool count_ne = XF::NONEMPTY;
     const int wbase = warp * (ITEMS * kWarp);
     int64_t sum = 0;
     bool neg = false, big = false;
     const bool full = valid == TILE;
-    int ne_lo = 0, ne_hi = 0;                    // a warp's 64-item rows fall into at most two event tiles
-    const int sub_lo = wbase >> 9;
 #pragma unroll
     for (int r = 0; r < ITEMS / 2; ++r) {
         const int p = wbase + r * 64 + lane * 2;
@@ -325,23 +323,6 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         neg |= (x < 0) | (y < 0);
         big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
         sum += x + y;
-        if constexpr (XF::NONEMPTY) {
-            if (count_ne) {
-                const int c = (x > 0) + (y > 0);
-                if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
-                else ne_hi += c;
-            }
-        }
-    }
-    if constexpr (XF::NONEMPTY) {
-        if (count_ne) {
-            ne_lo = warp_reduce_add(ne_lo);
-            ne_hi = warp_reduce_add(ne_hi);
-            if (lane == 0) {
-                if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
-                if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
-            }
-        }
     }
     if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
     sum = warp_reduce_add(sum);
@@ -359,6 +340,25 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
                 out[n] = tile_base + block_total;
                 if (total) *total = tile_base + block_total;
             }
+        }
+    }
+    if constexpr (XF::NONEMPTY) {
+        // OFF the critical path (the tile's aggregate is already published): warps 1.. count while warp 0 looks
+        // back, warp 0 counts afterwards.  A warp's 64-item rows fall into at most two event tiles.
+        int ne_lo = 0, ne_hi = 0;
+        const int sub_lo = wbase >> 9;
+#pragma unroll 4
+        for (int r = 0; r < ITEMS / 2; ++r) {
+            const int p = wbase + r * 64 + lane * 2;
+            const int c = ((full || p < valid) ? (xf.item(sa, sb, p) > 0) : 0) + ((full || p + 1 < valid) ? (xf.item(sa, sb, p + 1) > 0) : 0);
+            if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
+            else ne_hi += c;
+        }
+        ne_lo = warp_reduce_add(ne_lo);
+        ne_hi = warp_reduce_add(ne_hi);
+        if (lane == 0) {
+            if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
+            if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
         }
     }
     __syncthreads();
@@ -407,11 +407,14 @@ int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
 template <typename T>
 int launch_scan_array(const T *in, int64_t n, int64_t *out, int64_t *total, int32_t *status, void *ws,
                       size_t ws_bytes, cudaStream_t stream, int64_t *tile_nonempty = nullptr) {
-    XfIdentity xf{0, 0};
+    if (tile_nonempty == nullptr)
+        return launch_scan_tma<T, XfIdentity, kScanTmaItems>(XfIdentity{0, 0}, in, static_cast<const T *>(nullptr), n, out,
+                                                            total, status, ws, ws_bytes, stream);
+    XfIdentityTiles xf{0, 0};
     xf.tile_nonempty = tile_nonempty;
     xf.n_event_tiles = n <= 0 ? 0 : (n + 511) / 512;
-    return launch_scan_tma<T, XfIdentity, kScanTmaItems>(xf, in, static_cast<const T *>(nullptr), n, out, total, status,
-                                                        ws, ws_bytes, stream);
+    return launch_scan_tma<T, XfIdentityTiles, kScanTmaItems>(xf, in, static_cast<const T *>(nullptr), n, out, total,
+                                                             status, ws, ws_bytes, stream);
 }
 
 // Host launcher.  `out` has n+1 entries: out[i] = sum of items before i, out[n] = grand total.
