@@ -203,7 +203,7 @@ def main():
                 return None
             return listify(v)
         except Exception as err:
-            return {"raises": type(err).__name__}
+            return {"raises": type(err).__name__, "message": str(err)}
 
     for expr in CASES:
         r = record(expr, env)

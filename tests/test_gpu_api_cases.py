@@ -91,6 +91,8 @@ def check(expr, expect, got):
         return
     if "raises" in expect:
         assert got.get("raises") == expect["raises"], "{0}: reference raises {1}, got {2}".format(expr, expect["raises"], got)
+        if expect.get("message"):            # the wording too (an empty message, e.g. a bare NotImplementedError, is not pinned)
+            assert got["message"] == expect["message"], "{0}: message {1!r}, reference {2!r}".format(expr, got["message"], expect["message"])
         return
     assert "raises" not in got, "{0}: raised {1}: {2}".format(expr, got.get("raises"), got.get("message"))
     if "tuple" in expect:
