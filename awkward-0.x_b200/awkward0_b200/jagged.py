@@ -310,13 +310,17 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         rows = [list(x) for x in iterable]
         counts = numpy.array([len(x) for x in rows], dtype=INDEXTYPE)
         flat = [y for x in rows for y in x]
+        if any(isinstance(y, (list, tuple, numpy.ndarray)) for y in flat):
+            return cls.fromcounts(counts, cls.fromiter(flat))           # lists of lists: one more jagged level
         content = numpy.array(flat) if len(flat) else numpy.array([], dtype=cls.DEFAULTTYPE)
         return cls.fromcounts(counts, content)
 
     @classmethod
     def fromoffsets(cls, offsets, content):
         """jagged.py:142-153."""
-        offsets = asdevice(offsets if not isinstance(offsets, (list, tuple)) else numpy.asarray(offsets, dtype=INDEXTYPE))
+        if isinstance(offsets, (list, tuple)):
+            offsets = numpy.asarray(offsets) if len(offsets) else numpy.zeros(0, dtype=INDEXTYPE)
+        offsets = asdevice(offsets)
         if not _isintegertype(offsets.dtype):
             raise TypeError("offsets must have integer dtype")
         if len(offsets) == 0:
@@ -331,7 +335,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def fromcounts(cls, counts, content):
         """jagged.py:155-166 -> jg_counts2offsets; negative counts / non-integer dtype raise like the reference."""
         if isinstance(counts, (list, tuple)):
-            counts = numpy.asarray(counts, dtype=INDEXTYPE) if len(counts) else numpy.zeros(0, dtype=INDEXTYPE)
+            counts = numpy.asarray(counts) if len(counts) else numpy.zeros(0, dtype=INDEXTYPE)
         counts = asdevice(counts)
         if not _isintegertype(counts.dtype) and counts.dtype != numpy.bool_:
             raise TypeError("counts must have integer dtype")
@@ -489,6 +493,61 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             fresh = JaggedArray(s, e, out._content)
             out.__dict__.update(fresh.__dict__)
         return out
+
+    def deepcopy(self, starts=None, stops=None, content=None):
+        """jagged.py:261-269: a copy that shares no buffer with this array (same layout)."""
+        out = self.copy(starts=starts, stops=stops, content=content)
+        out._valid()
+
+        def clone(c):
+            if isinstance(c, JaggedArray):
+                return c.deepcopy()
+            if isinstance(c, Table):
+                return c.map(clone)
+            return c.copy()
+
+        if out._off64 is not None and out._general is None:
+            return self.fromoffsets(out.offsets.copy(), clone(out._content))
+        return JaggedArray(out._starts.copy(), out._stops.copy(), clone(out._content))
+
+    def _like(self, make):
+        if isinstance(self._content, JaggedArray):
+            return self.copy(content=self._content._like(make))
+        return self.copy(content=self._map_content(lambda c: DeviceArray(make(c.tensor), c.dtype)))
+
+    def zeros_like(self, **overrides):
+        """jagged.py:277-281 (a fill, not arithmetic: NaN * 0 would not do)."""
+        return self._like(torch.zeros_like)
+
+    def ones_like(self, **overrides):
+        """jagged.py:283-287."""
+        return self._like(torch.ones_like)
+
+    def empty_like(self, **overrides):
+        """jagged.py:271-275."""
+        return self._like(torch.empty_like)
+
+    def astype(self, dtype):
+        """base.py: the content converted, the structure shared."""
+        if isinstance(self._content, JaggedArray):
+            return self.copy(content=self._content.astype(dtype))
+        return self.copy(content=self._map_content(lambda c: c.astype(dtype)))
+
+    def structure1d(self, levellimit=None):
+        """jagged.py:1431-1454: starts / stops are one-dimensional here by construction."""
+        return self.copy()
+
+    def flattentuple(self):
+        """jagged.py:1400-1401."""
+        if isinstance(self._content, Table):
+            return self.copy(content=self._content.flattentuple())
+        if isinstance(self._content, JaggedArray):
+            return self.copy(content=self._content.flattentuple())
+        return self.copy()
+
+    @property
+    def size(self):
+        return len(self)
 
     # ------------------------------------------------------------------------------------------------------
     # validity

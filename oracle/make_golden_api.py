@@ -128,6 +128,17 @@ CASES = [
     "d2", "d2.sum()", "d2.max().max()", "d2.flatten(axis=1).argmax()", "d2[d2 > 1.5].counts", "d2.argmin()", "d2[d2.argmin()]", "d2 + d2.flatten(axis=1).max()",
     "x.cross(y, nested=True).i0 + x.cross(y, nested=True).i1", "(x.cross(y, nested=True).i1 > 15).any()", "x.cross(y, nested=True).i1.min()", "x.pairs(nested=True).i1.sum()",
     "x.cross(y, nested=True).flatten(axis=1).i1", "x.cross(y, nested=True).i1.argmax()", "x.distincts(nested=True).i0.counts", "x.argcross(y, nested=True).flatten(axis=1).i0",
+    # builders, copies, metadata
+    "J.fromiter([[1, 2], [3.5]])", "J.fromiter([[True, False], []])", "J.fromiter([])", "J.fromiter([[[1, 2], [3]], []])", "J.fromiter([[], []])",
+    "J.fromiter([[1, 2], [], [3]]).content", "J.fromiter([[[1.5], []], [[2.5, 3.5]]]).flatten(axis=1)", "a.ones_like()", "a.zeros_like()",
+    "i.ones_like()", "rec.zeros_like().q", "a.copy()", "a.deepcopy()", "a.copy(content=b.content)", "a.copy(starts=a.starts[:2], stops=a.stops[:2])",
+    "str(e)", "a.nbytes", "a.shape", "str(a.dtype)", "a.ndim", "str(a.type)", "a.size", "len(a.content)", "a.valid()",
+    "J.offsetsaliased(a.starts, a.stops)", "J.offsetsaliased(g.starts, g.stops)", "a.astype(np.float32)", "i.astype(np.float64)", "a.structure1d()",
+    "a.regular", "a.tolist()", "list(a)[0]", "a.counts.sum()", "a.argchoose(2).i0",
+    "J.counts2offsets(np.array([3, 0, 2]))", "J.offsets2parents(np.array([0, 3, 3, 5]))", "J.startsstops2parents(np.array([0, 3]), np.array([3, 5]))",
+    "J.parents2startsstops(np.array([0, 0, 2, 2, 2]))", "J.uniques2offsetsparents(np.array([7, 7, 8, 9, 9]))", "a.flattentuple()", "x.cross(y).flattentuple().i0",
+    "a.iscompact and a.compact() is a", "a.starts.dtype.name", "o32.starts.dtype.name", "J.fromcounts(np.array([1, 2], dtype=np.uint8), [1, 2, 3]).offsets",
+    "J.fromcounts([1.0, 2.0], [1, 2, 3])", "J.fromoffsets([0.0, 1.0], [1])", "J([[0]], [[1]], [1, 2]).tolist()", "J.fromcounts([[1, 2]], [1, 2, 3])",
 ]
 
 # (not in the battery: `deepg[deepg > 2]` -- a mask over a doubly jagged array in general layout; the reference raises

@@ -17,6 +17,8 @@ DATA = json.load(open(os.path.join(GOLDEN_DIR, "api_cases.json")))
 
 # outside the GPU hot path by design: the reference computes these, this class refuses loudly
 OUT_OF_SCOPE = set([
+    "J([[0]], [[1]], [1, 2]).tolist()",              # multi-dimensional starts / stops (jagged.py:59,163,439,1504-1506)
+    "J.fromcounts([[1, 2]], [1, 2, 3])",
 ])
 
 
