@@ -13,7 +13,19 @@ from .jagged import JaggedArray  # noqa: F401
 from .arrow import fromarrow, toarrow  # noqa: F401
 from .ingest import StreamedJaggedArray  # noqa: F401
 from .persist import load, save  # noqa: F401  (.awkd files: awkward0.save / awkward0.load)
-from . import lazy  # noqa: F401  (deferred pair columns + fused ufunc chains; lazy.ENABLED[0] = False switches fusion off)
+
+
+def concatenate(arrays, axis=0):
+    """awkward0/__init__.py:21-22."""
+    return JaggedArray.concatenate(arrays, axis=axis)
+
+
+def fromiter(iterable):
+    """awkward0/__init__.py:24 (generate.py): lists of (lists of ...) numbers; other element types are out of scope."""
+    return JaggedArray.fromiter(iterable)
+
+
+from . import lazy  # noqa: F401,E402  (deferred pair columns + fused ufunc chains; lazy.ENABLED[0] = False switches fusion off)
 
 __version__ = "0.1.0"
-__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray", "save", "load"]
+__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray", "save", "load", "concatenate", "fromiter"]

@@ -789,6 +789,53 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def i4(self):
         return self["4"]
 
+    @property
+    def i5(self):
+        return self["5"]
+
+    @property
+    def i6(self):
+        return self["6"]
+
+    @property
+    def i7(self):
+        return self["7"]
+
+    @property
+    def i8(self):
+        return self["8"]
+
+    @property
+    def i9(self):
+        return self["9"]
+
+    @property
+    def rowname(self):
+        """base.py:655-682: the row name of the records inside; TypeError when there are none."""
+        content = self._content
+        if isinstance(content, (Table, JaggedArray)):
+            return content.rowname
+        raise TypeError("not a Table, so there is no rowname")
+
+    @property
+    def istuple(self):
+        """base.py:684-687."""
+        columns = self.columns
+        return self.rowname == "tuple" and columns == [str(x) for x in range(len(columns))]
+
+    def boolmask(self, maskedwhen=True):
+        """jagged.py:1902-1906: a JaggedArray masks no event."""
+        n = len(self)
+        return asdevice(numpy.zeros(n, dtype=self.MASKTYPE) if maskedwhen else numpy.ones(n, dtype=self.MASKTYPE))
+
+    @property
+    def ismasked(self):
+        return self.boolmask(maskedwhen=True)
+
+    @property
+    def isunmasked(self):
+        return self.boolmask(maskedwhen=False)
+
     def unzip(self):
         return tuple(self[n] for n in self.columns)
 
@@ -1334,6 +1381,21 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def max(self):
         return self._reduce(_lib.MAX)
+
+    def reduce(self, ufunc, identity):
+        """base.py:190-191: the generic entry; the (ufunc, identity) pairs that have a segmented kernel."""
+        known = {numpy.add: (_lib.SUM, 0), numpy.multiply: (_lib.PROD, 1),
+                 numpy.minimum: (_lib.MIN, numpy.inf), numpy.maximum: (_lib.MAX, -numpy.inf)}
+        if ufunc in known and identity == known[ufunc][1]:
+            return self._reduce(known[ufunc][0])
+        raise NotImplementedError("JaggedArray.reduce({0}, {1}) has no segmented kernel; no CPU fallback".format(
+            getattr(ufunc, "__name__", ufunc), identity))
+
+    def moment(self, n, weight=None):
+        """base.py:217-222."""
+        if weight is None:
+            return numpy.true_divide((self ** n).sum(), self.count())
+        return numpy.true_divide(((self * weight) ** n).sum(), (self * 0 + weight).sum())
 
     def count(self):
         """base.py:199-200 / jagged.py:1513-1518: number of non-NaN values per event."""

@@ -138,6 +138,12 @@ CASES = [
     "J.counts2offsets(np.array([3, 0, 2]))", "J.offsets2parents(np.array([0, 3, 3, 5]))", "J.startsstops2parents(np.array([0, 3]), np.array([3, 5]))",
     "J.parents2startsstops(np.array([0, 0, 2, 2, 2]))", "J.uniques2offsetsparents(np.array([7, 7, 8, 9, 9]))", "a.flattentuple()", "x.cross(y).flattentuple().i0",
     "a.iscompact and a.compact() is a", "a.starts.dtype.name", "o32.starts.dtype.name", "J.fromcounts(np.array([1, 2], dtype=np.uint8), [1, 2, 3]).offsets",
+    # the rest of the public surface: generic reduce, moments, masks, row names, tuple slots, module-level functions (A = the module)
+    "a.reduce(np.add, 0)", "a.reduce(np.maximum, -np.inf)", "i.reduce(np.minimum, np.inf)", "i8.reduce(np.multiply, 1)", "nan.reduce(np.add, 0)",
+    "a.moment(1)", "a.moment(2)", "a.moment(3)", "i.moment(2)", "a.moment(2, weight=b)", "nan.moment(2)", "e.moment(2)",
+    "a.boolmask()", "a.boolmask(maskedwhen=False)", "a.ismasked", "a.isunmasked", "e.ismasked", "rec.rowname", "x.cross(y).rowname", "x.cross(y).istuple",
+    "rec.istuple", "a.rowname", "a.istuple", "deep.rowname", "J.zip(x, x, x, x, x, x, x, x, x, x).i5", "J.zip(x, x, x, x, x, x, x, x, x, x).i9 + J.zip(x, x, x, x, x, x * 3).i5",
+    "x.cross(y).i5", "A.concatenate([a, b])", "A.concatenate([x, y, z], axis=1)", "A.concatenate([])", "A.fromiter([[1, 2], [], [3]])", "A.fromiter([[1.5], [2.5, 3.5]]).sum()",
     "J.fromcounts([1.0, 2.0], [1, 2, 3])", "J.fromoffsets([0.0, 1.0], [1])", "J([[0]], [[1]], [1, 2]).tolist()", "J.fromcounts([[1, 2]], [1, 2, 3])",
 ]
 
@@ -201,7 +207,7 @@ def _default(o):
 
 def main():
     ak0 = _refloader.load()
-    env = {"J": ak0.JaggedArray, "np": np}
+    env = {"J": ak0.JaggedArray, "np": np, "A": ak0}
     for name, code in SETUP:
         env[name] = eval(code, env)
     out = {"setup": SETUP, "cases": [], "statements": []}

@@ -25,7 +25,7 @@ OUT_OF_SCOPE = set([
 @pytest.fixture(scope="module")
 def env():
     import awkward0_b200 as ak
-    scope = {"J": ak.JaggedArray, "np": np}
+    scope = {"J": ak.JaggedArray, "np": np, "A": ak}
     for name, code in DATA["setup"]:
         scope[name] = eval(code, scope)
     return scope
