@@ -61,6 +61,7 @@ PROTOTYPES = {
     "jg_startsstops2parents": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "jg_compact_gather": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "jg_segment_scatter": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "jg_segment_merge": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _vp, _i64, _vp, _vp]),
     "jg_offsets_rebase": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "jg_put": (_i, [_vp, _i, _vp, _i64, _vp, ctypes.c_uint64, _i, _vp]),
     "jg_unpack_bits": (_i, [_vp, _i64, _i64, _vp, _vp]),

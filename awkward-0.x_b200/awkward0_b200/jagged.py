@@ -1871,7 +1871,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     @classmethod
     def _concatenate_axis1(cls, arrays):
-        """jagged.py:1651-1733 -> counts sum, one scan, one jg_segment_scatter per input and leaf column."""
+        """jagged.py:1651-1733 -> counts sum, one scan, then per leaf column ONE jg_segment_merge over the output
+        layout (2..4 inputs); a single input or more than four go input by input through jg_segment_scatter."""
         if any(len(a) != len(arrays[0]) for a in arrays):
             raise ValueError("cannot concatenate JaggedArrays of different lengths with axis=1")
         parts = [x._dense() for x in arrays]
@@ -1883,8 +1884,9 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             before[k] = run
             run = _ufunc.binary(numpy.add, run, counts[k])
         out_offsets, total, _ = cls._scan_counts(run)
+        merged = 2 <= len(parts) <= 4
         slots = []
-        for k in range(len(parts)):
+        for k in range(0 if merged else len(parts)):
             slots.append(out_offsets[:-1] if before[k] is None else _ufunc.binary(numpy.add, out_offsets[:-1], before[k]))
 
         def merge(columns):
@@ -1906,8 +1908,16 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             else:
                 dtype = numpy.result_type(*[c.dtype for c in nonempty])
             out = empty(total, dtype)
+            if merged and n > 0 and total > 0:
+                cast = [c if c.dtype == dtype or len(c) == 0 else _ufunc.cast(c, dtype) for c in columns]
+                # the columns are dense contents starting at offsets[0]: un-rebased offsets with a shifted base
+                ptrs = (ctypes.c_void_p * len(parts))(*[c.data_ptr(-parts[k][3]) for k, c in enumerate(cast)])
+                offs = (ctypes.c_void_p * len(parts))(*[p[1].data_ptr() for p in parts])
+                call("jg_segment_merge", ptrs, offs, len(parts), dtype.itemsize, out_offsets.data_ptr(), n, _vp(out),
+                     runtime.stream())
+                return DeviceArray(out, dtype)
             for k, c in enumerate(columns):
-                if len(c) == 0:
+                if len(c) == 0 or merged:
                     continue
                 c = c if c.dtype == dtype else _ufunc.cast(c, dtype)
                 a, off, _, first_k, _ = parts[k]

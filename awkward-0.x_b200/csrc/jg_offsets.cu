@@ -319,6 +319,98 @@ static int launch_segment_move(const void *content, int itemsize, const int64_t 
     return check_launch(what);
 }
 
+// concatenate(axis=1) of K dense inputs in ONE sweep over the OUTPUT layout (jagged.py:1651-1733).  A tile owns 512
+// merged events; per event and input it keeps where the input's part ends in the output and the shift that turns an
+// output position into the input's content position.  The sweep is element-parallel over the tile's output run:
+// stores are fully coalesced, and so are the loads -- the parts an input contributes to consecutive events are
+// consecutive in that input's content.  (One jg_segment_scatter per input instead writes runs of a few items
+// between the gaps the other inputs fill later: partial sectors on every store.)
+constexpr int kMergeMax = 4;
+struct MergeInputs {
+    const void *content[kMergeMax];
+    const int64_t *offsets[kMergeMax];
+};
+
+template <typename V, int K>
+__global__ void __launch_bounds__(kTileThreads)
+segment_merge_kernel(const MergeInputs in, const int64_t *__restrict__ out_offsets, int64_t n, V *__restrict__ out) {
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ int64_t s_end[K - 1][kTileEvents];      // output position where the part of input q ends
+    __shared__ int64_t s_shift[K][kTileEvents];        // content position in input q = output position + shift
+    __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
+    EventTile tile;
+    tile.load(s_off, out_offsets, n, blockIdx.x);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ev = threadIdx.x + h * kTileThreads;
+        if (ev < tile.nev) {
+            int64_t pos = s_off[ev];
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                const int64_t a = __ldg(in.offsets[q] + tile.event0 + ev), b = __ldg(in.offsets[q] + tile.event0 + ev + 1);
+                s_shift[q][ev] = a - pos;
+                pos += b - a;
+                if (q < K - 1) s_end[q][ev] = pos;
+            }
+        }
+    }
+    __syncthreads();
+    // merged events are K times as long as their inputs': the tile is swept in K sub-ranges of events so that the
+    // output run of each fits the owner table as a one-input tile does
+    constexpr int kSub = (kTileEvents + K - 1) / K;
+#pragma unroll 1
+    for (int c0 = 0; c0 < tile.nev; c0 += kSub) {
+        EventTile sub;
+        sub.off = s_off + c0;
+        sub.event0 = tile.event0 + c0;
+        sub.nev = min(kSub, tile.nev - c0);
+        const int64_t e0 = sub.first_element(), e1 = sub.last_element();
+        const bool table = (e1 - e0) <= kOwnPositions;
+        if (table) build_owner_table(s_own, sub, static_cast<int>(e1 - e0));
+#pragma unroll 1
+        for (int64_t jb = e0 + threadIdx.x; jb < e1; jb += 4 * kTileThreads) {
+            const V *src[4];
+            V val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = jb + u * kTileThreads;
+                src[u] = nullptr;
+                if (j < e1) {
+                    const int ev = c0 + (table ? static_cast<int>(s_own[j - e0]) : sub.find_event(j));
+                    const V *c = static_cast<const V *>(in.content[K - 1]);
+                    int64_t shift = s_shift[K - 1][ev];
+#pragma unroll
+                    for (int q = K - 2; q >= 0; --q) {
+                        if (j < s_end[q][ev]) {
+                            c = static_cast<const V *>(in.content[q]);
+                            shift = s_shift[q][ev];
+                        }
+                    }
+                    src[u] = c + (j + shift);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (src[u]) val[u] = __ldg(src[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (src[u]) out[jb + u * kTileThreads] = val[u];
+        }
+        __syncthreads();      // the owner table is rebuilt for the next sub-range
+    }
+}
+
+template <typename V>
+static int launch_segment_merge(const MergeInputs &in, int k, const int64_t *out_offsets, int64_t n, void *out,
+                                cudaStream_t s) {
+    const unsigned g = tile_grid(n);
+    V *o = static_cast<V *>(out);
+    if (k == 2) segment_merge_kernel<V, 2><<<g, kTileThreads, 0, s>>>(in, out_offsets, n, o);
+    else if (k == 3) segment_merge_kernel<V, 3><<<g, kTileThreads, 0, s>>>(in, out_offsets, n, o);
+    else segment_merge_kernel<V, 4><<<g, kTileThreads, 0, s>>>(in, out_offsets, n, o);
+    return check_launch("jg_segment_merge");
+}
+
 // concatenate(axis=0): offsets of a later array shifted by the content that precedes it (jagged.py:1633-1649)
 __global__ void __launch_bounds__(256)
 offsets_rebase_kernel(const int64_t *__restrict__ offsets, int64_t count, int64_t delta, int64_t *__restrict__ out) {
@@ -442,6 +534,29 @@ int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets
     JG_REQUIRE(offsets && dst_starts && out, "jg_segment_scatter: bad arguments");
     return launch_segment_move<true>(content, itemsize, offsets, dst_starts, n, out, as_stream(stream),
                                      "jg_segment_scatter");
+}
+
+int jg_segment_merge(const void *const *contents, const int64_t *const *offsets, int k, int itemsize,
+                     const int64_t *out_offsets, int64_t n, void *out, void *stream) {
+    JG_REQUIRE(k >= 2 && k <= kMergeMax, "jg_segment_merge: between 2 and 4 inputs per call");
+    if (n <= 0) return 0;
+    JG_REQUIRE(contents && offsets && out_offsets && out, "jg_segment_merge: bad arguments");
+    MergeInputs in;
+    for (int q = 0; q < kMergeMax; ++q) {
+        in.content[q] = q < k ? contents[q] : nullptr;
+        in.offsets[q] = q < k ? offsets[q] : nullptr;
+        JG_REQUIRE(q >= k || in.offsets[q] != nullptr, "jg_segment_merge: missing offsets");
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (itemsize) {
+        case 1: return launch_segment_merge<uint8_t>(in, k, out_offsets, n, out, s);
+        case 2: return launch_segment_merge<uint16_t>(in, k, out_offsets, n, out, s);
+        case 4: return launch_segment_merge<uint32_t>(in, k, out_offsets, n, out, s);
+        case 8: return launch_segment_merge<uint64_t>(in, k, out_offsets, n, out, s);
+        default:
+            set_error("jg_segment_merge: unsupported itemsize %d", itemsize);
+            return -2;
+    }
 }
 
 int jg_pad(const void *content, int itemsize, const int64_t *starts, const int64_t *counts, const int64_t *dst_offsets,

@@ -457,7 +457,15 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
     dst = ak.DeviceArray(off.tensor[:-1] * 2)
     add("segment_scatter_f32", v * M + 16 * N + v * M, M, lambda: _lib.call(
         "jg_segment_scatter", pt_dev.data_ptr(), 4, off.data_ptr(), dst.data_ptr(), N, _vp(cat), st()))
-    del cat, dst
+    del dst
+    # the whole axis-1 concatenation of two inputs as ONE sweep over the output layout (coalesced loads and stores)
+    pt2, off2 = ak.DeviceArray(pt_dev.tensor.clone()), ak.DeviceArray(off.tensor.clone())
+    moff = ak.DeviceArray(off.tensor * 2)
+    mptrs = (ctypes.c_void_p * 2)(pt_dev.data_ptr(), pt2.data_ptr())
+    moffs = (ctypes.c_void_p * 2)(off.data_ptr(), off2.data_ptr())
+    add("segment_merge2_f32", 2 * v * M + 3 * 8 * N + 2 * v * M, 2 * M, lambda: _lib.call(
+        "jg_segment_merge", mptrs, moffs, 2, 4, moff.data_ptr(), N, _vp(cat), st()))
+    del cat, pt2, off2, moff
 
     # float64 content (BASELINE configs[1] names float32/float64): same offsets, values cast up
     pt64 = ak.DeviceArray(pt_dev.tensor.double())

@@ -235,6 +235,11 @@ int jg_offsets_rebase(const int64_t *offsets, int64_t count, int64_t delta, int6
  * input lands at its slot inside the merged event                                                                    */
 int jg_segment_scatter(const void *content, int itemsize, const int64_t *offsets, const int64_t *dst_starts, int64_t n,
                        void *out, void *stream);
+/* jagged.py:1651-1733  concatenate(axis=1) of k = 2..4 dense inputs in one sweep over the output layout:
+ * out[out_offsets[i] + (items of inputs < q in event i) + t] = contents[q][offsets[q][i] + t].  `contents` and `offsets`
+ * are HOST arrays of k device pointers; every content has `itemsize`; out_offsets = scan of the summed counts.           */
+int jg_segment_merge(const void *const *contents, const int64_t *const *offsets, int k, int itemsize,
+                     const int64_t *out_offsets, int64_t n, void *out, void *stream);
 
 /* ---- broadcasting and elementwise ufuncs ------------------------------------------------------------------------ */
 /* jagged.py:866-875  tojagged(flat): out[j - offsets[0]] = flat[parent(j)]                                          */

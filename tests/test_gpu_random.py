@@ -247,3 +247,27 @@ def test_argmax_with_tile_counts_from_the_scan(ak, n, cdtype):
             r = arr.argmin() if ismin else arr.argmax()
             assert np.array_equal(r.offsets.get(), woff) and np.array_equal(r.content.get(), widx)
     assert same(a[a.argmax()].content.get(), x[(off[:-1][counts > 0] + O.argminmax(off, x, False)[1])])
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+@pytest.mark.parametrize("kind,n,dtype", [("poisson5", 100003, np.float32), ("geometric", 5000, np.float64),
+                                          ("sparse", 40000, np.int16), ("poisson40", 3000, np.uint8)])
+def test_concatenate_axis1_differential(ak, k, kind, n, dtype):
+    """jagged.py:1651-1733: k inputs merged event by event (2..4: one jg_segment_merge sweep; 5: scatter per input),
+    inputs that are views (offsets[0] != 0), one of them with no content at all, against the oracle, bit for bit."""
+    rng = np.random.default_rng(4200 + 7 * k + n)
+    parts, arrays = [], []
+    for q in range(k):
+        counts = make_counts(kind, n + q, rng)
+        if q == 1:
+            counts[:] = 0                                     # an input that contributes nothing
+        off = O.counts2offsets(counts)
+        vals = (rng.normal(size=off[-1]) * 50).astype(dtype) if np.dtype(dtype).kind == "f" else rng.integers(0, 100, off[-1]).astype(dtype)
+        arr = ak.JaggedArray.fromcounts(counts, vals)[q:]     # views: the first q events dropped
+        arrays.append(arr)
+        parts.append((off[q:], vals))
+    want_off, want = O.concatenate_axis1(parts)
+    got = arrays[0].concatenate(arrays[1:], axis=1)
+    assert same(got.offsets.get(), want_off)
+    assert got.content.dtype == want.dtype
+    assert same(got.content.get(), want)
