@@ -10,7 +10,7 @@ from .device import DeviceArray, DeviceMatrix, asdevice  # noqa: F401
 from .masked import MaskedArray  # noqa: F401
 from .table import Table  # noqa: F401
 from .jagged import JaggedArray  # noqa: F401
-from .arrow import fromarrow, toarrow  # noqa: F401
+from .arrow import fromarrow, fromparquet, toarrow, toparquet  # noqa: F401
 from .ingest import StreamedJaggedArray  # noqa: F401
 from .persist import load, save  # noqa: F401  (.awkd files: awkward0.save / awkward0.load)
 
@@ -28,4 +28,4 @@ def fromiter(iterable):
 from . import lazy  # noqa: F401,E402  (deferred pair columns + fused ufunc chains; lazy.ENABLED[0] = False switches fusion off)
 
 __version__ = "0.1.0"
-__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray", "save", "load", "concatenate", "fromiter"]
+__all__ = ["JaggedArray", "Table", "DeviceArray", "DeviceMatrix", "MaskedArray", "asdevice", "fromarrow", "toarrow", "StreamedJaggedArray", "save", "load", "concatenate", "fromiter", "fromparquet", "toparquet"]

@@ -99,3 +99,66 @@ def toarrow(array):
     if not isinstance(array, JaggedArray):
         raise NotImplementedError("toarrow on the device expects a JaggedArray")
     return recurse(array)
+
+
+def toparquet(where, obj, **options):
+    """arrow.py:452-523: a JaggedArray becomes a Parquet file with ONE column named "" (the reference's layout); an
+    iterable of JaggedArrays writes one row group per item.  Host work is pyarrow's; the device side is the D2H
+    of offsets + content in `toarrow`."""
+    import pyarrow
+    import pyarrow.parquet
+
+    def convert(item, message):
+        if not isinstance(item, JaggedArray):
+            raise TypeError(message)
+        return pyarrow.Table.from_batches([pyarrow.RecordBatch.from_arrays([toarrow(item)], [""])])
+
+    if isinstance(obj, JaggedArray):
+        items = iter([obj])
+    else:
+        try:
+            items = iter(obj)
+        except TypeError:
+            raise TypeError("cannot write {0} to Parquet file".format(type(obj)))
+    try:
+        first = next(items)
+    except StopIteration:
+        raise ValueError("iterable is empty")
+    table = convert(first, "cannot write iterator of {0} to Parquet file".format(type(first)))
+    options["where"] = where
+    if "schema" not in options:
+        options["schema"] = table.schema
+    writer = pyarrow.parquet.ParquetWriter(**options)
+    try:
+        writer.write_table(table)
+        for item in items:
+            writer.write_table(convert(item, "cannot write iterator of {0} to Parquet file".format(type(item))))
+    finally:
+        writer.close()
+
+
+def fromparquet(file, columns=None):
+    """arrow.py:557-578.  The reference returns a lazy ChunkedArray of VirtualArrays, one chunk per row group
+    (outside the GPU hot path); here every row group is decoded by pyarrow on the host, its (offsets, values) buffers
+    are copied to HBM and the groups are appended with `JaggedArray.concatenate`: the result is ONE resident
+    JaggedArray for a file whose only column is "" (what `toparquet` writes), else an ordered dict column -> array."""
+    import collections
+    import pyarrow.parquet
+
+    pf = pyarrow.parquet.ParquetFile(file)
+    names = [n for n in pf.schema_arrow.names if columns is None or n in columns]
+    parts = collections.OrderedDict((n, []) for n in names)
+    for g in range(pf.num_row_groups):
+        if pf.metadata.row_group(g).num_rows == 0:
+            continue
+        table = pf.read_row_group(g, columns=names)
+        for n in names:
+            parts[n].append(fromarrow(table.column(n)))
+    out = collections.OrderedDict()
+    for n in names:
+        if not parts[n]:                               # no rows at all: an empty array of the column's type
+            parts[n].append(fromarrow(pf.schema_arrow.empty_table().column(n).combine_chunks()))
+        out[n] = parts[n][0] if len(parts[n]) == 1 else JaggedArray.concatenate(parts[n])
+    if names == [""]:
+        return out[""]
+    return out
