@@ -156,7 +156,7 @@ constexpr int kPairEventMax = 384;       // more outputs than this in one event:
 static_assert(2 * kPairTable <= kCombPositions + 128, "pair tables must fit the owner table's storage");
 
 template <int KIND, bool REL>
-__device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uint16_t *__restrict__ s_r,
+__device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uint16_t *__restrict__ /* s_l + kPairTable */,
                                                  const EventTile &pt, const int64_t *__restrict__ s_oa,
                                                  const int64_t *__restrict__ s_ob) {
     const int64_t p0 = pt.off[0], total = pt.off[pt.nev] - p0;
@@ -171,34 +171,41 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
     for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) {
         const int cnt = static_cast<int>(pt.off[ev + 1] - pt.off[ev]);
         if (cnt == 0) continue;
-        uint16_t *l = s_l + (pt.off[ev] - p0), *r = s_r + (pt.off[ev] - p0);
+        // one moving pointer: the right-hand table sits kPairTable entries behind the left-hand one (every caller
+        // carves both out of one buffer), and the counters already carry the event's relative start
+        uint16_t *l = s_l + (pt.off[ev] - p0);
+        uint16_t *const end = l + cnt;
         const int na = static_cast<int>(s_oa[ev + 1] - s_oa[ev]);
         const int ra = REL ? static_cast<int>(s_oa[ev] - s_oa[0]) : 0;
         if constexpr (KIND == JG_COMB_CROSS) {
             const int nb = static_cast<int>(s_ob[ev + 1] - s_ob[ev]);
             const int rb = REL ? static_cast<int>(s_ob[ev] - s_ob[0]) : 0;
-            int i = 0, j = 0;
+            int i = ra, j = rb;
+            const int jend = rb + nb;
 #pragma unroll 1
-            for (int o = 0; o < cnt; ++o) {
-                l[o] = static_cast<uint16_t>(ra + i);
-                r[o] = static_cast<uint16_t>(rb + j);
-                if (++j == nb) {
-                    j = 0;
+            do {
+                l[0] = static_cast<uint16_t>(i);
+                l[kPairTable] = static_cast<uint16_t>(j);
+                ++l;
+                if (++j == jend) {
+                    j = rb;
                     ++i;
                 }
-            }
+            } while (l != end);
         } else {
             constexpr int kFirst = (KIND == JG_COMB_DISTINCTS) ? 1 : 0;      // j starts at i (pairs) or i + 1
-            int i = 0, j = kFirst;
+            int i = ra, j = ra + kFirst;
+            const int jend = ra + na;
 #pragma unroll 1
-            for (int o = 0; o < cnt; ++o) {
-                l[o] = static_cast<uint16_t>(ra + i);
-                r[o] = static_cast<uint16_t>(ra + j);
-                if (++j == na) {
+            do {
+                l[0] = static_cast<uint16_t>(i);
+                l[kPairTable] = static_cast<uint16_t>(j);
+                ++l;
+                if (++j == jend) {
                     ++i;
                     j = i + kFirst;
                 }
-            }
+            } while (l != end);
         }
     }
     __syncthreads();

@@ -145,8 +145,17 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
     __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
     __shared__ V s_flat[MODE == EXPAND_BROADCAST ? kTileEvents : 1];
     EventTile tile;
-    tile.load(s_off, offsets, n, blockIdx.x);
+    // the per-event values do not depend on the offsets: their loads are in flight while the tile's offsets arrive
+    V f0 = V(), f1 = V();
+    if (MODE == EXPAND_BROADCAST) {
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, blockIdx.x, ev0, nev);
+        if (static_cast<int>(threadIdx.x) < nev) f0 = __ldg(flat + ev0 + threadIdx.x);
+        if (static_cast<int>(threadIdx.x) + kTileThreads < nev) f1 = __ldg(flat + ev0 + threadIdx.x + kTileThreads);
+    }
     const int64_t o0 = __ldg(offsets);
+    tile.load(s_off, offsets, n, blockIdx.x);
     if (MODE == EXPAND_PARENTS && blockIdx.x == 0) {
         // content below offsets[0] is unreachable: -1 (jagged.py:52-54)
         for (int64_t j = threadIdx.x; j < o0; j += kTileThreads) out[j] = static_cast<V>(-1);
@@ -155,11 +164,36 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
     if (e1 - e0 <= kOwnPositions) {
         // short events: scatter + max-scan owner table in shared memory, then a coalesced element-parallel sweep
         const int L = static_cast<int>(e1 - e0);
-        if (MODE == EXPAND_BROADCAST)
-#pragma unroll 1
-            for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) s_flat[ev] = flat[tile.event0 + ev];
+        if (MODE == EXPAND_BROADCAST) {
+            if (static_cast<int>(threadIdx.x) < tile.nev) s_flat[threadIdx.x] = f0;
+            if (static_cast<int>(threadIdx.x) + kTileThreads < tile.nev) s_flat[threadIdx.x + kTileThreads] = f1;
+        }
         build_owner_table(s_own, tile, L);
         V *dst = (MODE == EXPAND_PARENTS) ? out + e0 : out + (e0 - o0);
+        if constexpr (MODE == EXPAND_BROADCAST) {
+            // 16 bytes per thread and store: the sweep is issue-bound, not DRAM-bound, when every 1..4-byte item
+            // costs its own store and loop step (tojagged(float32): 61 % of peak).  Head and tail of the run, up to
+            // the first / from the last 16-byte boundary of the OUTPUT, go item by item.
+            constexpr int VEC = 16 / static_cast<int>(sizeof(V));
+            const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(dst) / sizeof(V)) & (VEC - 1));
+            const int head = min(L, (VEC - mis) & (VEC - 1));
+            const int ngroups = (L - head) / VEC;
+            const int tail0 = head + ngroups * VEC;
+            if (static_cast<int>(threadIdx.x) < head) dst[threadIdx.x] = s_flat[s_own[threadIdx.x]];
+            if (tail0 + static_cast<int>(threadIdx.x) < L) dst[tail0 + threadIdx.x] = s_flat[s_own[tail0 + threadIdx.x]];
+#pragma unroll 1
+            for (int g = threadIdx.x; g < ngroups; g += kTileThreads) {
+                const int p = head + g * VEC;
+                union {
+                    uint4 q;
+                    V e[VEC];
+                } w;
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) w.e[u] = s_flat[s_own[p + u]];
+                __stcs(reinterpret_cast<uint4 *>(dst + p), w.q);
+            }
+            return;
+        }
 #pragma unroll 2
         for (int p = threadIdx.x; p < L; p += kTileThreads) {
             const int ev = s_own[p];
@@ -339,6 +373,25 @@ segment_merge_kernel(const MergeInputs in, const int64_t *__restrict__ out_offse
     __shared__ int64_t s_shift[K][kTileEvents];        // content position in input q = output position + shift
     __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
     EventTile tile;
+    // the inputs' offsets of this thread's two events are requested before the tile's output offsets are waited for
+    int64_t ia[2][K], ib[2][K];
+    {
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, blockIdx.x, ev0, nev);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ev = threadIdx.x + h * kTileThreads;
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                ia[h][q] = ib[h][q] = 0;
+                if (ev < nev) {
+                    ia[h][q] = __ldg(in.offsets[q] + ev0 + ev);
+                    ib[h][q] = __ldg(in.offsets[q] + ev0 + ev + 1);
+                }
+            }
+        }
+    }
     tile.load(s_off, out_offsets, n, blockIdx.x);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -347,9 +400,8 @@ segment_merge_kernel(const MergeInputs in, const int64_t *__restrict__ out_offse
             int64_t pos = s_off[ev];
 #pragma unroll
             for (int q = 0; q < K; ++q) {
-                const int64_t a = __ldg(in.offsets[q] + tile.event0 + ev), b = __ldg(in.offsets[q] + tile.event0 + ev + 1);
-                s_shift[q][ev] = a - pos;
-                pos += b - a;
+                s_shift[q][ev] = ia[h][q] - pos;
+                pos += ib[h][q] - ia[h][q];
                 if (q < K - 1) s_end[q][ev] = pos;
             }
         }

@@ -43,7 +43,7 @@ for rep in range(3):
     _lib.call("jg_segargminmax_dense", pt_d.data_ptr(), _lib.JG_F32, off.data_ptr(), N, 0, _vp(i64a), _vp(i64b), ctypes.c_void_p(0), _vp(scal), _vp(scal, 1), ws, wsb, st())
     _lib.call("jg_binary", _lib.OP["GT"], pt_d.data_ptr(), _lib.JG_F32, ctypes.c_void_p(0), 0, _lib.RHS_SCALAR,
               ctypes.c_double(20.0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(mask), _lib.JG_B8, M, ctypes.c_void_p(0), 0, st())
-    _lib.call("jg_mask_select", pt_d.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(i64a), _vp(scal), ws, wsb, st())
+    _lib.call("jg_mask_select", pt_d.data_ptr(), 4, _vp(mask), 0, off.data_ptr(), N, _vp(sel), _vp(i64a), ctypes.c_void_p(0), _vp(scal), ws, wsb, st())
     _lib.call("jg_offsets2counts", off.data_ptr(), N, _vp(i64b), st())
     _lib.call("jg_offsets2parents", off.data_ptr(), N, _vp(par), st())
     _lib.call("jg_broadcast", _vp(f32), 4, off.data_ptr(), N, _vp(sel), st())
