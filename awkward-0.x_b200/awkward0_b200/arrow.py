@@ -3,8 +3,9 @@
 Arrow delivers exactly the hot path's inputs -- a list array IS (offsets int32/int64, values) -- so ingest is one
 host->device copy per buffer and `JaggedArray.fromoffsets`; nothing is re-scanned.  Supported: list / large_list
 (nested to any depth) of numeric, boolean (bit-packed, unpacked by jg_unpack_bits) or struct-of-those values, and
-ChunkedArrays of them (chunks are appended with JaggedArray.concatenate).  Arrays with nulls map to the
-reference's BitMaskedArray, which is outside the GPU hot path: NotImplementedError, no CPU fallback.
+ChunkedArrays of them (chunks are appended with JaggedArray.concatenate).  Null VALUES become a MaskedArray content
+(the reference: BitMaskedArray; `fillna` / `tolist` / `counts` work, everything else asks for fillna first); null
+LISTS or structs (a BitMaskedArray around the JaggedArray itself) are outside the GPU hot path: NotImplementedError.
 """
 import ctypes
 
@@ -13,6 +14,7 @@ import numpy
 from ._lib import call
 from .device import BOOLTYPE, DeviceArray, asdevice, empty, runtime
 from .jagged import JaggedArray
+from .masked import MaskedArray
 from .table import Table
 
 
@@ -21,24 +23,38 @@ def _no_nulls(array):
         raise NotImplementedError("Arrow arrays with nulls become BitMaskedArrays in awkward0 (arrow.py:274-276), which is outside the GPU hot path")
 
 
+def _unpack(bits, offset, n):
+    out = empty(n, BOOLTYPE)
+    if n > 0:
+        packed = asdevice(numpy.frombuffer(bits, dtype=numpy.uint8))
+        call("jg_unpack_bits", packed.data_ptr(), offset, n, ctypes.c_void_p(out.data_ptr()), runtime.stream())
+    return DeviceArray(out, BOOLTYPE)
+
+
 def _values(array):
-    """A non-list Arrow array -> DeviceArray / Table of DeviceArrays."""
+    """A non-list Arrow array -> DeviceArray / Table of DeviceArrays; numeric or boolean values with nulls ->
+    MaskedArray (the reference wraps them in a BitMaskedArray over Arrow's validity bits, arrow.py:262-266; here the
+    bits are unpacked to a byte mask by jg_unpack_bits, valid = unmasked)."""
     import pyarrow
-    _no_nulls(array)
+    tpe = array.type
+    if array.null_count != 0 and not pyarrow.types.is_struct(tpe) and array.buffers()[0] is not None:
+        valid = _unpack(array.buffers()[0], array.offset, len(array))
+        plain = _values_plain(array)
+        return MaskedArray(valid, plain, maskedwhen=False)
+    return _values_plain(array)
+
+
+def _values_plain(array):
+    import pyarrow
     tpe = array.type
     if pyarrow.types.is_struct(tpe):
+        _no_nulls(array)
         out = Table.named("Row")
         for i in range(tpe.num_fields):
             out[tpe.field(i).name] = _content(array.field(i))
         return out
     if pyarrow.types.is_boolean(tpe):
-        n = len(array)
-        bits = array.buffers()[1]
-        out = empty(n, BOOLTYPE)
-        if n > 0:
-            packed = asdevice(numpy.frombuffer(bits, dtype=numpy.uint8))
-            call("jg_unpack_bits", packed.data_ptr(), array.offset, n, ctypes.c_void_p(out.data_ptr()), runtime.stream())
-        return DeviceArray(out, BOOLTYPE)
+        return _unpack(array.buffers()[1], array.offset, len(array))
     if pyarrow.types.is_integer(tpe) or pyarrow.types.is_floating(tpe):
         dtype = numpy.dtype(tpe.to_pandas_dtype())
         if dtype == numpy.dtype(numpy.float16):

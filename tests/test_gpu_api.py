@@ -499,6 +499,21 @@ def test_arrow_ingest(ak):                   # arrow.py:231-430: l
         ak.fromarrow(pa.array([[1.0], None]))
     with pytest.raises(NotImplementedError):
         ak.fromarrow(pa.array([1.0, 2.0]))
+    # null VALUES: masked content (the reference: BitMaskedArray, arrow.py:262-266); same tolist / fillna as the
+    # reference gives for these arrays (checked in the build container)
+    for arr, filled in ((pa.array([[1.0, None, 2.0], [], [None]]), [[1.0, 0.0, 2.0], [], [0.0]]),
+                        (pa.array([[1, 2, None], [None], [3]], type=pa.list_(pa.int32())), [[1, 2, 0], [0], [3]]),
+                        (pa.array([[True, None], [False]]), [[True, False], [False]])):
+        jn = ak.fromarrow(arr)
+        assert isinstance(jn.content, ak.MaskedArray)
+        assert jn.tolist() == arr.to_pylist()
+        assert jn.fillna(0).tolist() == filled
+        assert jn.counts.tolist() == [len(x) for x in arr.to_pylist()]
+        with pytest.raises(NotImplementedError, match="fillna"):
+            jn.sum()
+    sliced = pa.array([[1.5, None, 2.5], [], [None, 4.5], [6.5]]).slice(1, 3)
+    assert ak.fromarrow(sliced).tolist() == [[], [None, 4.5], [6.5]]
+    assert ak.fromarrow(sliced).fillna(-1).sum().tolist() == [0.0, 3.5, 6.5]
     # and back
     back = ak.toarrow(j)
     assert back.to_pylist() == lists and back.type == pa.list_(pa.float64())
