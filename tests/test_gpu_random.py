@@ -271,3 +271,89 @@ def test_concatenate_axis1_differential(ak, k, kind, n, dtype):
     assert same(got.offsets.get(), want_off)
     assert got.content.dtype == want.dtype
     assert same(got.content.get(), want)
+
+
+def test_more_than_2_to_31_elements(ak):
+    """Maximum sizes: 220 M events, 2.2e9 float32 elements (positions beyond int32, byte offsets beyond uint32).
+    Inputs are drawn on the device (no 10 GB host copy).  Every operation is run on the WHOLE array and checked
+    through size-independent properties, and bit for bit against the oracle on the last events, whose positions
+    lie above 2^31 -- once as the tail of the whole-array result, once computed on a view that starts there."""
+    import torch
+    n, t = 220_000_000, 60_000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2031)
+    counts_t = torch.randint(0, 21, (n,), generator=gen, device="cuda", dtype=torch.int64)
+    m = int(counts_t.sum())
+    assert m > 2 ** 31 + 10_000_000
+    content_t = torch.empty(m, dtype=torch.float32, device="cuda")
+    content_t.exponential_(1.0 / 25.0, generator=gen)
+    a = ak.JaggedArray.fromcounts(counts_t, content_t)
+    off = a.offsets
+    assert int(off[-1]) == m and len(off) == n + 1
+    off_tail = off.tensor[n - t:].cpu().numpy()                      # absolute offsets of the last t events
+    base = int(off_tail[0])
+    assert base > 2 ** 31
+    host_tail = content_t[base:].cpu().numpy()
+    rel = off_tail - base
+    tail = a[n - t:]                                                  # a view whose offsets[0] is above 2^31
+
+    s = a.sum()
+    assert np.isclose(float(s.tensor.double().sum()), float(content_t.double().sum()), rtol=1e-9)
+    want = O.reduce(rel, host_tail, "sum")
+    assert np.allclose(s.tensor[n - t:].cpu().numpy(), want, rtol=1e-5, atol=0)
+    assert np.allclose(tail.sum().get(), want, rtol=1e-5, atol=0)
+    want = O.reduce(rel, host_tail, "max")
+    assert same(a.max().tensor[n - t:].cpu().numpy(), want) and same(tail.max().get(), want)
+    del s
+
+    roff, ridx = O.argminmax(rel, host_tail, False)
+    am = a.argmax()
+    nonempty = int((counts_t > 0).sum())
+    assert int(am.offsets[-1]) == nonempty == len(am.content)
+    assert same(am.content.tensor[nonempty - len(ridx):].cpu().numpy(), ridx)
+    ta = tail.argmax()
+    assert same(ta.offsets.get(), roff) and same(ta.content.get(), ridx)
+    lead = a[am]
+    goff, gval = O.index_gather(rel, host_tail, roff, ridx)
+    assert same(lead.content.tensor[nonempty - len(gval):].cpu().numpy(), gval)
+    assert same(tail[ta].content.get(), gval)
+    del am, lead
+
+    sel = a[a > 20.0]
+    k = int((content_t > 20.0).sum())
+    assert len(sel.content) == k == int(sel.offsets[-1]) and k > 2 ** 29
+    moff, mask = O.ufunc_broadcast(np.greater, rel, host_tail, 20.0)
+    soff, want = O.mask_select(rel, host_tail, moff, mask)
+    assert same(sel.content.tensor[k - len(want):].cpu().numpy(), want)
+    assert same(sel.counts.tensor[n - t:].cpu().numpy(), O.offsets2counts(soff))
+    ts = tail[tail > 20.0]
+    assert same(ts.offsets.get(), soff) and same(ts.content.get(), want)
+    bm = ak.JaggedArray.fromoffsets(off, ak.asdevice(content_t > 20.0))       # the mask as an array of its own (M bytes)
+    assert same(a[bm].content.tensor[k - len(want):].cpu().numpy(), want)
+    del sel, bm
+
+    par = a.parents
+    assert len(par) == m and same(par.tensor[base:].cpu().numpy(), O.offsets2parents(rel) + (n - t))
+    assert bool((par.tensor[1:] >= par.tensor[:-1]).all())
+    del par
+    li = a.localindex
+    assert same(li.content.tensor[base:].cpu().numpy(), O.localindex(rel)[1])
+    del li
+    flat_t = ak.asdevice(torch.arange(n, dtype=torch.int64, device="cuda").float())
+    flat_tail = np.arange(n - t, n, dtype=np.int64).astype(np.float32)
+    tj = a.tojagged(flat_t)
+    assert same(tj.content.tensor[base:].cpu().numpy(), O.tojagged_flat(rel, flat_tail))
+    plus = a + flat_t
+    with np.errstate(all="ignore"):
+        _, want = O.ufunc_broadcast(np.add, rel, host_tail, flat_tail)
+    assert same(plus.content.tensor[base:].cpu().numpy(), want)
+    del tj, plus, flat_t
+
+    poff, pi, pj = O.argpairs(rel)
+    tp = tail.argpairs()
+    assert same(tp.offsets.get(), poff) and same(tp.i0.content.get(), pi) and same(tp.i1.content.get(), pj)
+    _, left, right = O.pairs(rel, host_tail)
+    tv = tail.pairs()
+    assert same(tv.i0.content.get(), left) and same(tv.i1.content.get(), right)
+    srt = tail.argsort()
+    assert same(srt.content.get(), O.argsort(rel, host_tail)[1])
