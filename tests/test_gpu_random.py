@@ -357,3 +357,31 @@ def test_more_than_2_to_31_elements(ak):
     assert same(tv.i0.content.get(), left) and same(tv.i1.content.get(), right)
     srt = tail.argsort()
     assert same(srt.content.get(), O.argsort(rel, host_tail)[1])
+
+
+def test_one_event_longer_than_2_to_31(ak):
+    """A single event of 2^31 + 1000 elements between two empty ones (block-per-event paths with 64-bit positions)."""
+    import torch
+    m = 2 ** 31 + 1000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(31)
+    content_t = torch.empty(m, dtype=torch.float32, device="cuda")
+    content_t.exponential_(1.0 / 25.0, generator=gen)
+    content_t[m - 7] = 1.0e6                                   # the maximum sits above position 2^31
+    content_t[5] = -3.0                                        # the minimum at the front
+    a = ak.JaggedArray.fromcounts(np.array([0, m, 0], dtype=np.int64), content_t)
+    assert a.max().tolist() == [-np.inf, 1.0e6, -np.inf] and a.min().tolist() == [np.inf, -3.0, np.inf]
+    assert a.argmax().tolist() == [[], [m - 7], []] and a.argmin().tolist() == [[], [5], []]
+    assert a[a.argmax()].tolist() == [[], [1.0e6], []]
+    s = a.sum().get()
+    assert s[0] == 0 and s[2] == 0 and np.isclose(s[1], float(content_t.double().sum()), rtol=1e-4)
+    # (no selection here: in a tile whose run does not fit the stage, mask_select walks every event with ONE thread --
+    # fine for many long events, minutes for a single one of 2^31 elements; DESIGN.md section 9)
+    par = a.parents
+    assert int(par.tensor.min()) == 1 and int(par.tensor.max()) == 1
+    del par
+    li = a.localindex.content.tensor
+    assert int(li[0]) == 0 and int(li[-1]) == m - 1 and bool((li[1:] - li[:-1] == 1).all())
+    del li
+    tj = a.tojagged(np.array([1.5, 2.5, 3.5], dtype=np.float32))
+    assert float(tj.content.tensor.min()) == 2.5 == float(tj.content.tensor.max())
