@@ -206,37 +206,68 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         return;
     }
 
-    // ---------------- oversize tile (long events): straight from global memory ------------------------------
+    // ---------------- oversize tile (long events): chunks of KM positions straight from global memory --------
+    // The whole CTA compacts the run chunk by chunk exactly like a staged tile (coalesced reads, ballot / popc
+    // slots, consecutive stores) with a running base; an event takes its new offset from the chunk that holds its
+    // first position.  (One thread per event, as before, walked an event of a million elements alone.)
     const V *cv = content + e0;
     const E *mv = mask + e0 + mask_shift;
-    const int ev0 = threadIdx.x * 2;      // thread t owns events 2t and 2t+1
-    int64_t a[2], b[2];
-    int64_t c[2] = {0, 0};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int ev = ev0 + q;
-        a[q] = b[q] = 0;
-        if (ev < tile.nev) {
-            a[q] = s_off[ev] - e0;
-            b[q] = s_off[ev + 1] - e0;
-            int64_t cnt = 0;
-            for (int64_t j = a[q]; j < b[q]; ++j) cnt += sel.test(mv[j]);
-            c[q] = cnt;
+    int64_t *s_new = reinterpret_cast<int64_t *>(s_content);      // the stage is idle here: new offsets within the tile
+    static_assert(KM * sizeof(V) + 32 >= (kTileEvents + 1) * sizeof(int64_t), "stage too small for the offsets");
+    const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
+    const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
+    const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
+    int64_t run = 0;
+#pragma unroll 1
+    for (int64_t cs = 0; cs < len; cs += KM) {
+        const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
+        const E *m = mv + cs;
+        const V *c = cv + cs;
+        const int rows_total = (L + 31) >> 5;
+        const int rows_per_warp = (rows_total + NW - 1) / NW;
+        const int p_begin = min(L, warp * rows_per_warp * 32);
+        const int p_end = min(L, p_begin + rows_per_warp * 32);
+        int cnt = 0;
+#pragma unroll 1
+        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0) s_scan[warp] = cnt;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < NW ? s_scan[lane] : 0;
+            int wi = warp_incl_scan_add(w, lane);
+            if (lane < NW) s_scan[lane] = wi - w;
+            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
         }
+        __syncthreads();
+        int wrun = s_scan[warp];
+        V *dst = out + base + run;
+#pragma unroll 1
+        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+            const int p = p0 + lane;
+            const bool on = p < p_end && sel.test(m[p]);
+            const unsigned b = __ballot_sync(0xffffffffu, on);
+            const int slot = wrun + __popc(b & ((1u << lane) - 1u));
+            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+            if (on) dst[slot] = c[p];
+            wrun += __popc(b);
+        }
+        __syncthreads();
+        if (stA >= cs && stA < cs + L) s_new[evA] = run + s_pfx[stA - cs];
+        if (stB >= cs && stB < cs + L) s_new[evB] = run + s_pfx[stB - cs];
+        run += s_pfx[L];
+        __syncthreads();      // s_pfx and s_scan are rewritten by the next chunk
     }
-    __shared__ int64_t s_scan64[NW + 1];
-    int64_t block_total;
-    const int64_t excl = block_excl_scan<int64_t, kTileThreads>(c[0] + c[1], s_scan64, block_total);
+    if (stA >= len) s_new[evA] = run;       // empty events at the end of the tile
+    if (stB >= len) s_new[evB] = run;
+    if (threadIdx.x == 0) s_new[tile.nev] = run;
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int ev = ev0 + q;
+    for (int h = 0; h < 2; ++h) {
+        const int ev = threadIdx.x + h * kTileThreads;
         if (ev < tile.nev) {
-            int64_t w = base + excl + (q ? c[0] : 0);
-            new_offsets[tile.event0 + ev] = w;
-            if (new_counts) new_counts[tile.event0 + ev] = c[q];
-            for (int64_t j = a[q]; j < b[q]; ++j) {
-                if (sel.test(mv[j])) out[w++] = cv[j];
-            }
+            new_offsets[tile.event0 + ev] = base + s_new[ev];
+            if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
         }
     }
 }

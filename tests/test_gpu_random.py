@@ -375,8 +375,11 @@ def test_one_event_longer_than_2_to_31(ak):
     assert a[a.argmax()].tolist() == [[], [1.0e6], []]
     s = a.sum().get()
     assert s[0] == 0 and s[2] == 0 and np.isclose(s[1], float(content_t.double().sum()), rtol=1e-4)
-    # (no selection here: in a tile whose run does not fit the stage, mask_select walks every event with ONE thread --
-    # fine for many long events, minutes for a single one of 2^31 elements)
+    k = int((content_t > 20.0).sum())
+    sel = a[a > 20.0]                      # an oversize tile: the CTA compacts the run chunk by chunk
+    assert sel.counts.tolist() == [0, k, 0] and len(sel.content) == k
+    assert bool((sel.content.tensor == content_t[content_t > 20.0]).all())
+    del sel
     par = a.parents
     assert int(par.tensor.min()) == 1 and int(par.tensor.max()) == 1
     del par
