@@ -102,7 +102,7 @@ mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, in
 
 // SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both
 template <typename V, int KM, class SEL, bool SAME>     // KM = positions a tile may stage
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : (SAME ? 7 : 6))
 mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                  int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
