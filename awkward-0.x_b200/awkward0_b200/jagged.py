@@ -1810,14 +1810,14 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     # ------------------------------------------------------------------------------------------------------
     @_bothmethod
     def concatenate(isclassmethod, cls_or_self, arrays, axis=0):
+        arrays = tuple(arrays)
+        if len(arrays) < 1:              # base.py:569-570: checked before `self` is put in front (a.concatenate([]) raises)
+            raise ValueError("at least one array needed to concatenate")
         if isclassmethod:
             cls = cls_or_self
-            arrays = tuple(arrays)
         else:
             cls = type(cls_or_self)
-            arrays = (cls_or_self,) + tuple(arrays)
-        if len(arrays) < 1:
-            raise ValueError("at least one array needed to concatenate")
+            arrays = (cls_or_self,) + arrays
         if not all(isinstance(x, JaggedArray) for x in arrays):
             raise NotImplementedError("concatenating a JaggedArray with other array types (UnionArray) is outside the GPU hot path")
         for x in arrays:

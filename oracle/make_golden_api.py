@@ -143,7 +143,7 @@ CASES = [
     "a.moment(1)", "a.moment(2)", "a.moment(3)", "i.moment(2)", "a.moment(2, weight=b)", "nan.moment(2)", "e.moment(2)",
     "a.boolmask()", "a.boolmask(maskedwhen=False)", "a.ismasked", "a.isunmasked", "e.ismasked", "rec.rowname", "x.cross(y).rowname", "x.cross(y).istuple",
     "rec.istuple", "a.rowname", "a.istuple", "deep.rowname", "J.zip(x, x, x, x, x, x, x, x, x, x).i5", "J.zip(x, x, x, x, x, x, x, x, x, x).i9 + J.zip(x, x, x, x, x, x * 3).i5",
-    "x.cross(y).i5", "A.concatenate([a, b])", "A.concatenate([x, y, z], axis=1)", "A.concatenate([])", "A.fromiter([[1, 2], [], [3]])", "A.fromiter([[1.5], [2.5, 3.5]]).sum()",
+    "x.cross(y).i5", "A.concatenate([a, b])", "A.concatenate([x, y, z], axis=1)", "A.concatenate([])", "a.concatenate([])", "a.concatenate([], axis=1)", "J.concatenate([a])", "J.concatenate([a], axis=1)", "A.fromiter([[1, 2], [], [3]])", "A.fromiter([[1.5], [2.5, 3.5]]).sum()",
     "J.fromcounts([1.0, 2.0], [1, 2, 3])", "J.fromoffsets([0.0, 1.0], [1])", "J([[0]], [[1]], [1, 2]).tolist()", "J.fromcounts([[1, 2]], [1, 2, 3])",
 ]
 
