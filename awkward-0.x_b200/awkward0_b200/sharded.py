@@ -6,7 +6,8 @@ chunk by chunk; tests/test_crosscut.py:86-89) and why counts are position indepe
 (docs/classes.adoc:33-36).  Rank r owns a contiguous range of events with LOCAL offsets that start at 0; all
 kernels run locally with no data-path collective.  NCCL is used only for
   * whole-array totals (sum of sums, global max/min, number selected, number of pairs): all_reduce of a few bytes;
-  * replicated per-event results on request: all_gather (sizes first when shards are unequal).
+  * replicated per-event results on request: all_gather (sizes first when shards are unequal); variable-size
+    jagged results the same way, counts and content separately (`gather_jagged`).
 
 Everything here works on whatever backend the process group uses: "nccl" with CUDA tensors in production,
 "gloo" with CPU tensors in the world_size-2 CPU tests (tests/test_sharded_gloo.py), where the local compute
@@ -121,6 +122,14 @@ def gather_per_event(local, group=None):
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
 
 
+def gather_jagged(counts, content, group=None):
+    """Replicate a VARIABLE-size jagged result (a selection, pairs, argmax ...) on every rank: the per-event counts and
+    the dense content of every shard, each in global event order -- (counts, content) as torch tensors on the group's
+    device; `fromcounts(counts, content)` is the whole-array result.  Two size exchanges + two padded all_gathers
+    ("gather = allgather(sizes) + grouped send/recv"); results normally STAY sharded, this is on request."""
+    return gather_per_event(counts, group=group), gather_per_event(content, group=group)
+
+
 def global_offsets_base(local_total, group=None):
     """Exclusive prefix over ranks of the local element totals: what to add to local offsets to get global ones."""
     world, rank = _world(group)
@@ -175,3 +184,9 @@ class ShardedJaggedArray(object):
 
     def gather(self, per_event):
         return gather_per_event(per_event, group=self.group)
+
+    def gather_jagged(self, result):
+        """A jagged per-shard result (`s.local[s.local > 20]`, `s.local.argmax()` ...) replicated whole on every rank,
+        built with the result's own class (`fromcounts`)."""
+        counts, content = gather_jagged(result.counts, result.flatten(), group=self.group)
+        return type(result).fromcounts(counts, content)

@@ -48,6 +48,7 @@ def _worker(rank, world, port, nevents, result_dir):
         (gsum, gk), (gmax,), _ = sharded.allreduce_totals(
             sums=[float(lsum.sum(dtype=np.float64)), int(len(sel))], maxima=[float(lmax.max())])
         every_sum = sharded.gather_per_event(lsum).numpy()
+        sel_counts, sel_content = sharded.gather_jagged(O.offsets2counts(soff), sel)      # variable-size result
         base = sharded.global_offsets_base(len(lpt))
         assert base == goff[lo]
 
@@ -66,8 +67,22 @@ def _worker(rank, world, port, nevents, result_dir):
             def min(self):
                 return O.reduce(loff, lpt, "min")
 
+        class Result(object):           # a jagged result with the surface gather_jagged uses
+            def __init__(self, counts, content):
+                self.counts, self.content = counts, content
+
+            def flatten(self):
+                return self.content
+
+            @classmethod
+            def fromcounts(cls, counts, content):
+                return cls(counts, content)
+
         s = sharded.ShardedJaggedArray(Local())
+        whole = s.gather_jagged(Result(O.offsets2counts(soff), sel))
+        assert np.array_equal(whole.counts.numpy(), sel_counts.numpy()) and np.array_equal(whole.content.numpy(), sel_content.numpy())
         np.savez(os.path.join(result_dir, "rank%d.npz" % rank), gsum=gsum, gk=gk, gmax=gmax, every_sum=every_sum,
+                 sel_counts=sel_counts.numpy(), sel_content=sel_content.numpy(),
                  n=len(s), tsum=s.total_sum(), tmax=s.total_max(), tmin=s.total_min(), tcontent=s.total_content())
     finally:
         dist.destroy_process_group()
@@ -82,13 +97,14 @@ def test_two_rank_gloo_matches_single_process(tmp_path, nevents):
     off = O.counts2offsets(counts)
     want_sum = O.reduce(off, pt, "sum")
     moff, mask = O.ufunc_broadcast(np.greater, off, pt, np.float32(20))
-    _, sel = O.mask_select(off, pt, moff, mask)
+    soff, sel = O.mask_select(off, pt, moff, mask)
     for rank in range(world):
         r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
         assert np.isclose(float(r["gsum"]), float(want_sum.sum(dtype=np.float64)), rtol=1e-6)
         assert int(r["gk"]) == len(sel)
         assert float(r["gmax"]) == float(O.reduce(off, pt, "max").max())
         assert np.array_equal(r["every_sum"], want_sum)              # per-event sums: bit-exact, in global event order
+        assert np.array_equal(r["sel_counts"], O.offsets2counts(soff)) and np.array_equal(r["sel_content"], sel)
         assert int(r["n"]) == nevents and int(r["tcontent"]) == len(pt)
         assert np.isclose(float(r["tsum"]), float(want_sum.sum(dtype=np.float64)), rtol=1e-6)
         assert float(r["tmax"]) == float(pt.max()) and float(r["tmin"]) == float(pt.min())
