@@ -126,3 +126,58 @@ def test_concatenate(J, k):
     off0, cat0 = O.concatenate_axis0(parts)
     ref0 = arrays[0].concatenate(arrays[1:])
     assert same(O.offsets2counts(off0), ref0.counts) and same(cat0, ref0.flatten())
+
+
+@pytest.mark.parametrize("seed", [41, 42, 43])
+def test_constructors_general_layouts_and_setitem(J, seed):
+    rng = np.random.default_rng(seed)
+    counts, off, content = make(rng, 200, 3.0, np.float64)
+    a = J.fromcounts(counts, content)
+    # general layout: reordered, repeated and dropped events over the same content (jagged.py:599-605)
+    pick = rng.integers(0, len(counts), 150)
+    g = a[pick]
+    goff, gcontent = O.compact(off[:-1][pick], off[1:][pick], content)
+    assert same(O.offsets2counts(goff), g.counts) and same(gcontent, g.flatten())
+    assert same(O.reduce(goff, gcontent, "sum"), g.sum())
+    assert O.is_offsets_compatible(off[:-1], off[1:]) and a.iscompact
+    # fromparents / fromuniques / fromlocalindex / fromfolding (jagged.py:73-110, 168-242)
+    parents = np.sort(rng.integers(-1, 40, 300)).astype(np.int64)
+    starts, stops = O.parents2startsstops(parents)
+    ref = J.fromparents(parents, np.arange(300))
+    assert same(starts, ref.starts) and same(stops, ref.stops)
+    uniques = np.sort(rng.integers(0, 30, 200))
+    uoff, upar = O.uniques2offsetsparents(uniques)
+    rstarts_stops = J.fromuniques(uniques, np.arange(200))
+    assert same(uoff[:-1], rstarts_stops.starts) and same(uoff[1:], rstarts_stops.stops) and same(upar, rstarts_stops.parents)
+    li = a.localindex.flatten()
+    nonempty = counts[counts > 0]
+    assert same(O.offsets2counts(O.localindex2offsets(li)), J.fromlocalindex(li, content).counts)
+    assert same(O.offsets2counts(O.localindex2offsets(li)), nonempty)
+    for length, size in ((17, 5), (20, 5), (3, 7)):
+        assert same(O.offsets2counts(O.folding2offsets(length, size)), J.fromfolding(np.arange(length), size).counts)
+    # __setitem__ through a jagged mask and through a jagged index (jagged.py:789-838)
+    t = J.fromcounts(counts, content.copy())
+    m = t > 0
+    t[m] = -1.0
+    moff, mask = O.ufunc_broadcast(np.greater, off, content, 0)
+    assert same(O.setitem(off[:-1], off[1:], content, moff, mask, -1.0), t.content)
+    t = J.fromcounts(counts, content.copy())
+    idx = J.fromcounts((counts > 0).astype(np.int64), -np.ones(int((counts > 0).sum()), dtype=np.int64))     # last item of every event
+    t[idx] = 99.0
+    ioff = O.counts2offsets((counts > 0).astype(np.int64))
+    assert same(O.setitem(off[:-1], off[1:], content, ioff, idx.content, 99.0), t.content)
+
+
+@pytest.mark.parametrize("seed,n,mean", [(51, 300, 2.5), (52, 60, 7.0)])
+def test_value_combinatorics_and_distincts(J, seed, n, mean):
+    rng = np.random.default_rng(seed)
+    counts, off, content = make(rng, n, mean, np.float32)
+    a = J.fromcounts(counts, content)
+    _, left, right = O.distincts(off, content)
+    assert same(left, a.distincts().i0.flatten()) and same(right, a.distincts().i1.flatten())
+    for k in (2, 3):
+        out = O.choose(off, content, k)
+        ref = a.choose(k)
+        assert same(O.offsets2counts(out[0]), ref.counts)
+        for c in range(k):
+            assert same(out[1 + c], ref[str(c)].flatten()), (k, c)
