@@ -54,3 +54,24 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert not pattern.search(open(os.path.join(base, f)).read()), (base, f)
+
+
+def declared_arities():
+    """name -> number of parameters of every function the header declares."""
+    text = open(os.path.join(ROOT, "include", "jagged_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    for name, params in re.findall(r"\b(jg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else len(params.split(","))
+    return out
+
+
+def test_ctypes_prototypes_have_the_header_arity():
+    """A ctypes argtypes list that is one argument short of the C declaration does not fail: it corrupts the call."""
+    from awkward0_b200 import _lib
+    arities = declared_arities()
+    assert sorted(arities) == declared_symbols()
+    wrong = {n: (len(args), arities[n]) for n, (_, args) in _lib.PROTOTYPES.items() if len(args) != arities[n]}
+    assert not wrong, wrong
