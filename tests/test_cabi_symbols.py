@@ -75,3 +75,38 @@ def test_ctypes_prototypes_have_the_header_arity():
     assert sorted(arities) == declared_symbols()
     wrong = {n: (len(args), arities[n]) for n, (_, args) in _lib.PROTOTYPES.items() if len(args) != arities[n]}
     assert not wrong, wrong
+
+
+def test_ctypes_prototypes_have_the_header_types():
+    """Pointer / int / int64_t / size_t / double / uint64_t of every parameter, header against the ctypes table."""
+    from awkward0_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "jagged_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+
+    def kind_c(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return "ptr"
+        for c, k in (("int64_t", "i64"), ("uint64_t", "u64"), ("size_t", "size"), ("double", "f64"), ("int32_t", "i32"),
+                     ("int", "i32")):
+            if re.search(r"\b%s\b" % c, param):
+                return k
+        raise AssertionError("unknown C parameter type: " + param)
+
+    def kind_py(t):
+        if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents") or getattr(t, "_type_", None) not in ("i", "l", "q", "L", "Q", "d", "I"):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_int64: "i64", ctypes.c_uint64: "u64", ctypes.c_size_t: "size",
+                ctypes.c_double: "f64"}[t]
+
+    same_width = ({"size", "u64"},)                      # ctypes aliases c_size_t to c_ulong == c_uint64 on LP64
+    bad = []
+    for name, params in re.findall(r"\b(jg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        cs = [] if params in ("", "void") else [kind_c(p) for p in params.split(",")]
+        ps = [kind_py(t) for t in _lib.PROTOTYPES[name][1]]
+        for i, (c, p) in enumerate(zip(cs, ps)):
+            if c != p and not any({c, p} <= s for s in same_width):
+                bad.append((name, i, c, p))
+    assert not bad, bad
