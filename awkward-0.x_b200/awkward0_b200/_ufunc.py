@@ -141,11 +141,18 @@ def nonzero(mask):
     return compress([arange(len(mask))], mask)[0]
 
 
+# Incremented by every in-place store.  Values cached from a buffer (the extreme values an argmin / argmax pass wrote
+# beside its indexes) remember the epoch they were computed in and are dropped once ANY store has happened since:
+# views share storage, so tracking the written object alone would miss a store through another view.
+WRITE_EPOCH = [0]
+
+
 def put(target, index, values, skip_negative=False):
     """target[index] = values (DeviceArray of the same length as index, or a scalar), in place (jg_put)."""
     dt = target.dtype
     if len(index) == 0:
         return
+    WRITE_EPOCH[0] += 1
     _lazy().flush_all()          # deferred values are computed from the data as it was when they were written
     if isinstance(values, DeviceArray):
         if len(values) != len(index):

@@ -59,7 +59,7 @@ def torch_dtype(dtype):
 
 # ---- runtime ----------------------------------------------------------------------------------------------------
 class _Runtime(object):
-    """Per-device scratch: the look-back workspace and the small status/total words kernels write."""
+    """Per-(device, stream) scratch: the scan workspace and the small status/total words kernels write."""
 
     def __init__(self):
         self._ws = {}
@@ -88,14 +88,20 @@ class _Runtime(object):
         except AttributeError:          # pragma: no cover  (older torch)
             return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def _key(self, dev):
+        """Scratch is per (device, stream): kernels of two streams may run concurrently, and the descriptors of a scan
+        or the zero fill of a fresh scalars pool are only ordered on the stream that issued them."""
+        return (dev.index, self.stream().value or 0)
+
     def workspace(self, n):
         """(pointer, bytes) of a scratch buffer large enough for any call on n events."""
         dev = self.device()
         need = int(lib.jg_workspace_bytes(int(n)))
-        buf = self._ws.get(dev.index)
+        key = self._key(dev)
+        buf = self._ws.get(key)
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
-            self._ws[dev.index] = buf
+            self._ws[key] = buf
         return ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel())
 
     def scalars(self):
@@ -105,10 +111,11 @@ class _Runtime(object):
         operation); a slice is handed out once, so pending read-backs never alias.
         """
         dev = self.device()
-        pool = self._scal.get(dev.index)
+        key = self._key(dev)
+        pool = self._scal.get(key)
         if pool is None or pool[1] >= pool[0].numel():
             pool = [torch.zeros(8 * 512, dtype=torch.int64, device=dev), 0]
-            self._scal[dev.index] = pool
+            self._scal[key] = pool
         out = pool[0][pool[1]:pool[1] + 8]
         pool[1] += 8
         return out

@@ -1209,7 +1209,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             raise ValueError("jagged array used as index has a different shape {0} from the jagged array it is selecting from {1}".format(head.shape, self.shape))
         a, off, n, first, last = self._dense()
         src = head._arg_source
-        if src is not None and src[0] is a._off64 and src[1] is a._content:
+        if src is not None and src[0] is a._off64 and src[1] is a._content and src[2] == _ufunc.WRITE_EPOCH[0]:
             # `head` is argmin()/argmax() of this very array: the selected values were produced by that pass
             return self._make(head._off64, head._arg_values, head._last)
         h, hoff, _, hfirst, hlast = head._dense()
@@ -1470,7 +1470,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out = self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
         if values is not None:
             # the extreme values came out of the same pass: a[a.argmax()] on THIS array needs no gather
-            out._arg_source = (a._off64, col)
+            out._arg_source = (a._off64, col, _ufunc.WRITE_EPOCH[0])
             out._arg_values = DeviceArray(values[:total], col.dtype)
         return out
 
@@ -1672,8 +1672,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         flat = positions[where].flatten()
         if not (isinstance(what, DeviceArray) or _ufunc.is_scalar(what)):
             what = asdevice(numpy.asarray(what))
-        _ufunc.put(self._content, flat, what)
-        self._arg_source = self._arg_values = None
+        _ufunc.put(self._content, flat, what)       # bumps _ufunc.WRITE_EPOCH: cached argmin / argmax values are dropped
 
     # ------------------------------------------------------------------------------------------------------
     # pad / fillna / regular (jagged.py:1851-1900, 1053-1068)

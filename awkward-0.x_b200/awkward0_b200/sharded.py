@@ -94,11 +94,14 @@ def allreduce_totals(sums=(), maxima=(), minima=(), group=None):
     return tuple(out)
 
 
-def gather_per_event(local, group=None):
+def gather_per_event(local, group=None, sizes=None):
     """Replicate a per-event result (one value per local event) on every rank, in global event order.
 
-    Equal shards use one all_gather; unequal shards exchange the sizes first and pad.  `local` is a
-    DeviceArray / torch tensor / numpy array; the result is a torch tensor on the group's device.
+    ONE `all_gather_into_tensor` into a (world, biggest) buffer -- NCCL writes every rank's part straight into its
+    row, no list of per-rank tensors and no staging copy when the shards are equal (the usual case: the row view IS
+    the result).  Unequal shards are padded to the biggest and the rows trimmed afterwards.  `sizes` (events per
+    rank) saves the 8-byte size exchange when the caller knows them (`event_range`).  `local` is a DeviceArray /
+    torch tensor / numpy array; the result is a torch tensor on the group's device.
     """
     world, rank = _world(group)
     device = _device_for(group)
@@ -110,16 +113,91 @@ def gather_per_event(local, group=None):
         t = torch.as_tensor(numpy.asarray(local), device=device).reshape(-1)
     if world == 1:
         return t
-    size = torch.tensor([t.numel()], dtype=torch.int64, device=device)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(sizes, size, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        mine = torch.tensor([t.numel()], dtype=torch.int64, device=device)
+        every = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        sizes = [int(x) for x in every.cpu().tolist()]
+    else:
+        sizes = [int(x) for x in sizes]
+        if len(sizes) != world or sizes[rank] != t.numel():
+            raise ValueError("sizes must list the events of every rank")
     biggest = max(sizes)
-    padded = torch.zeros(biggest, dtype=t.dtype, device=device)
-    padded[:t.numel()] = t
-    parts = [torch.empty(biggest, dtype=t.dtype, device=device) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+    flat = torch.empty(world * biggest, dtype=t.dtype, device=device)      # (gloo insists on a flat output)
+    out = flat.view(world, biggest)
+    if t.numel() == biggest:
+        src = t.contiguous()
+    else:
+        src = torch.zeros(biggest, dtype=t.dtype, device=device)
+        src[:t.numel()] = t
+    dist.all_gather_into_tensor(flat, src, group=group)
+    if min(sizes) == biggest:
+        return flat
+    return torch.cat([out[r, :n] for r, n in enumerate(sizes)])
+
+
+class DeviceTotals(object):
+    """Whole-array totals that never leave the device until the end of the step.
+
+    Each partial (the sum of per-event sums, the number of selected elements, the number of leading objects ...) is
+    already in HBM where a kernel epilogue wrote it -- a 1-element result of `jg_flat_reduce`, the `total` word of a
+    selection / arg-reduction (`JaggedArray._total_dev`).  `add_*` copies its 8 bytes device-to-device into one slot of
+    a small buffer; `finish()` exchanges the buffer with ONE collective (`all_gather_into_tensor`: mixed integer / float
+    slots and sum / max / min reductions ride in the same message as raw 64-bit words) and reads it back with ONE
+    device-to-host copy.  Replaces one D2H per partial plus an H2D, an all_reduce and a D2H per reduction kind
+    (chunked.py:596-597 sums per-chunk results on the host the same way).
+    """
+
+    def __init__(self, group=None, capacity=16):
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.device = _device_for(group)
+        self.buf = torch.zeros(capacity, dtype=torch.int64, device=self.device)
+        self.slots = []                          # (kind, numpy dtype)
+
+    def _add(self, value, kind):
+        i = len(self.slots)
+        if i >= self.buf.numel():
+            raise ValueError("DeviceTotals is full")
+        if hasattr(value, "tensor"):
+            value = value.tensor
+        if torch.is_tensor(value):
+            t = value.reshape(-1)[:1]
+            if t.dtype.is_floating_point:
+                t, dt = t.to(torch.float64), numpy.dtype(numpy.float64)
+            else:
+                t, dt = t.to(torch.int64), numpy.dtype(numpy.int64)
+            self.buf[i:i + 1].copy_(t.to(self.device).view(torch.int64), non_blocking=True)
+        else:                                    # a host number (sizes the host already had to know)
+            dt = numpy.dtype(numpy.int64 if isinstance(value, (int, numpy.integer)) else numpy.float64)
+            self.buf[i:i + 1].copy_(torch.from_numpy(numpy.array([value], dtype=dt).view(numpy.int64)), non_blocking=True)
+        self.slots.append((kind, dt))
+        return i
+
+    def add_sum(self, value):
+        return self._add(value, "sum")
+
+    def add_max(self, value):
+        return self._add(value, "max")
+
+    def add_min(self, value):
+        return self._add(value, "min")
+
+    def finish(self):
+        """-> list of python numbers, one per slot, reduced over all ranks."""
+        k = len(self.slots)
+        if self.world > 1:
+            flat = torch.empty(self.world * k, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(flat, self.buf[:k].contiguous(), group=self.group)
+            every = flat.view(self.world, k)
+        else:
+            every = self.buf[:k].view(1, k)
+        host = every.cpu().numpy()                       # the step's ONE device-to-host copy
+        out = []
+        for j, (kind, dt) in enumerate(self.slots):
+            col = numpy.ascontiguousarray(host[:, j]).view(dt)
+            out.append({"sum": col.sum, "max": col.max, "min": col.min}[kind]().item())
+        return out
 
 
 def gather_jagged(counts, content, group=None):
@@ -169,12 +247,25 @@ class ShardedJaggedArray(object):
         (tot,), _, _ = allreduce_totals(sums=[float(self._scalar(self.local.sum().sum()))], group=self.group)
         return tot
 
+    def _extreme(self, ismin):
+        """This shard's extreme as a python int / float; an EMPTY shard contributes the identity instead of raising, so
+        that every rank always enters the collective (a rank that raised would leave the others waiting in NCCL)."""
+        per_event = self.local.min() if ismin else self.local.max()       # identities for empty events
+        if len(per_event) == 0:
+            dt = numpy.dtype(getattr(per_event, "dtype", numpy.float64))
+            if dt.kind in "iu":
+                info = numpy.iinfo(dt)
+                return int(info.max if ismin else info.min)
+            return float("inf") if ismin else float("-inf")
+        x = self._scalar(per_event.min() if ismin else per_event.max())
+        return int(x) if isinstance(x, (int, numpy.integer)) else float(x)   # ints stay exact above 2^53
+
     def total_max(self):
-        _, (m,), _ = allreduce_totals(maxima=[float(self._scalar(self.local.max().max()))], group=self.group)
+        _, (m,), _ = allreduce_totals(maxima=[self._extreme(False)], group=self.group)
         return m
 
     def total_min(self):
-        _, _, (m,) = allreduce_totals(minima=[float(self._scalar(self.local.min().min()))], group=self.group)
+        _, _, (m,) = allreduce_totals(minima=[self._extreme(True)], group=self.group)
         return m
 
     def total_content(self):

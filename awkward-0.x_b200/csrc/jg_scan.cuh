@@ -17,7 +17,10 @@
 // Algorithmic traffic: itemsize*n read + 8*(n+1) written (16n bytes for int64 counts).
 #pragma once
 
+#include <stdlib.h>
+
 #include "jg_common.cuh"
+#include "jg_lag.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -378,9 +381,208 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent form of scan_tma_kernel on the lagged prefixes of jg_lag.cuh: phase A sums the tile a CTA will own LAG
+// iterations later straight from global memory (coalesced 8/4/1-byte loads, which leave the tile in L2) and
+// publishes the aggregate; phase B stages the current tile with one TMA bulk copy (an L2 hit), takes its base from
+// the published aggregates -- one L2 round trip, overlapped with the copy -- and writes the offsets.  No tile waits
+// on another unless a predecessor is a whole iteration late.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, class XF, int ITEMS, int LAG>
+__global__ void __launch_bounds__(kScanTmaThreads)
+scan_lag_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, int64_t n, int64_t *__restrict__ out,
+                int64_t *__restrict__ total, int32_t *__restrict__ status, LagDesc lag, uint32_t ntiles,
+                bool out_aligned) {
+    constexpr int NW = kScanTmaThreads / kWarp;
+    constexpr int TILE = kScanTmaThreads * ITEMS;
+    __shared__ __align__(16) unsigned char s_raw_a[(TILE + XF::EXTRA) * sizeof(T) + 32];
+    __shared__ __align__(16) unsigned char s_raw_b[XF::ARRAYS == 2 ? (TILE + XF::EXTRA) * sizeof(T) + 32 : 16];
+    __shared__ uint64_t s_bar[2];
+    __shared__ int64_t s_warp[NW + 1];
+    __shared__ int64_t s_agg[NW];
+    __shared__ int64_t s_base;
+    constexpr int kSubs = XF::NONEMPTY ? TILE / 512 : 1;
+    __shared__ int s_ne[kSubs];
+    constexpr int SUBS = TILE / 512;
+    static_assert(!XF::NONEMPTY || (TILE % 512 == 0 && (ITEMS * kWarp) % 64 == 0), "event tiles must tile the scan tile");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = gridDim.x;
+    stage_init(s_bar, 2);
+
+    // phase A: aggregate of one tile from global memory; thread 0 publishes
+    auto phase_a = [&](uint32_t ta) {
+        const int64_t a0 = static_cast<int64_t>(ta) * TILE;
+        const int64_t left = n - a0;
+        const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
+        const T *ga = in_a + a0;
+        const T *gb = XF::ARRAYS == 2 ? in_b + a0 : nullptr;
+        int64_t sum = 0;
+        if (valid == TILE) {
+#pragma unroll 8
+            for (int j = 0; j < ITEMS; ++j) sum += xf.item(ga, gb, j * kScanTmaThreads + tid);
+        } else {
+#pragma unroll 1
+            for (int p = tid; p < valid; p += kScanTmaThreads) sum += xf.item(ga, gb, p);
+        }
+        sum = warp_reduce_add(sum);
+        if (lane == 0) s_agg[warp] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            int64_t t = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += s_agg[w];
+            lag_publish(lag, ta, t);
+        }
+    };
+
+#pragma unroll 1
+    for (int j = 0; j < LAG; ++j) {
+        const uint64_t ta = static_cast<uint64_t>(blockIdx.x) + static_cast<uint64_t>(j) * G;
+        if (ta < ntiles) phase_a(static_cast<uint32_t>(ta));
+        __syncthreads();
+    }
+
+    uint32_t it = 0;
+#pragma unroll 1
+    for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G, ++it) {
+        const uint32_t tile = static_cast<uint32_t>(tile64);
+        const uint32_t parity = it & 1u;
+        const int64_t i0 = static_cast<int64_t>(tile) * TILE;
+        const int64_t left = n - i0;
+        const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
+        if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
+        const T *sa = reinterpret_cast<const T *>(s_raw_a);
+        const T *sb = reinterpret_cast<const T *>(s_raw_b);
+        if (valid > 0) {
+            if (tid == 0) fence_proxy_async_smem();
+            const uint32_t bytes = static_cast<uint32_t>((valid + XF::EXTRA) * sizeof(T));
+            const uint32_t sha = stage_issue<sizeof(T)>(s_raw_a, reinterpret_cast<const unsigned char *>(in_a + i0), bytes, &s_bar[0]);
+            sa = reinterpret_cast<const T *>(s_raw_a + sha);
+            if (XF::ARRAYS == 2) {
+                const uint32_t shb = stage_issue<sizeof(T)>(s_raw_b, reinterpret_cast<const unsigned char *>(in_b + i0), bytes, &s_bar[1]);
+                sb = reinterpret_cast<const T *>(s_raw_b + shb);
+            }
+        }
+        // phase A of the tile this CTA owns LAG iterations from now (its loads overlap the bulk copy above)
+        {
+            const uint64_t ta = tile64 + static_cast<uint64_t>(LAG) * G;
+            if (ta < ntiles) phase_a(static_cast<uint32_t>(ta));
+        }
+        // phase B: the tile's base comes from aggregates published an iteration ago (one L2 round trip, taken by
+        // warp 0 while the bulk copy lands)
+        if (warp == 0) {
+            const int64_t tile_base = lag_prefix(lag, tile);
+            if (lane == 0) s_base = tile_base;
+        }
+        if (valid > 0) {
+            if (XF::ARRAYS == 2) mbar_wait(&s_bar[1], parity);
+            stage_wait(&s_bar[0], parity);
+        } else {
+            __syncthreads();
+        }
+        const int wbase = warp * (ITEMS * kWarp);
+        const bool full = valid == TILE;
+        int64_t sum = 0;
+        bool neg = false, big = false;
+#pragma unroll
+        for (int r = 0; r < ITEMS / 2; ++r) {
+            const int p = wbase + r * 64 + lane * 2;
+            const int64_t x = (full || p < valid) ? xf.item(sa, sb, p) : 0;
+            const int64_t y = (full || p + 1 < valid) ? xf.item(sa, sb, p + 1) : 0;
+            neg |= (x < 0) | (y < 0);
+            big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
+            sum += x + y;
+        }
+        if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
+        sum = warp_reduce_add(sum);
+        if (lane == 0) s_warp[warp] = sum;
+        if constexpr (XF::NONEMPTY) {
+            int ne_lo = 0, ne_hi = 0;
+            const int sub_lo = wbase >> 9;
+#pragma unroll 4
+            for (int r = 0; r < ITEMS / 2; ++r) {
+                const int p = wbase + r * 64 + lane * 2;
+                const int c = ((full || p < valid) ? (xf.item(sa, sb, p) > 0) : 0) + ((full || p + 1 < valid) ? (xf.item(sa, sb, p + 1) > 0) : 0);
+                if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
+                else ne_hi += c;
+            }
+            ne_lo = warp_reduce_add(ne_lo);
+            ne_hi = warp_reduce_add(ne_hi);
+            if (lane == 0) {
+                if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
+                if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
+            }
+        }
+        const bool wide = __syncthreads_or(big);
+        if constexpr (XF::NONEMPTY) {
+            if (tid < SUBS) {
+                const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
+                if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
+            }
+        }
+        int64_t run = s_base, tile_sum = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int64_t part = s_warp[w];
+            if (w < warp) run += part;
+            tile_sum += part;
+        }
+        if (tile == ntiles - 1 && tid == 0) {
+            out[n] = s_base + tile_sum;
+            if (total) *total = s_base + tile_sum;
+        }
+        if (full) {
+            if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+            else scan_tma_rows<T, int32_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        } else {
+            if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+            else scan_tma_rows<T, int32_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        }
+        __syncthreads();      // the stage, s_warp, s_base and s_ne are rewritten by the next iteration
+    }
+}
+
+inline int scan_mode() {      // experiment switch (JG_SCAN_MODE): 0 = look-back (round 1), 1 = lagged LAG 1, 2 = lagged LAG 2
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("JG_SCAN_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+template <typename T, class XF, int ITEMS, int LAG>
+int launch_scan_lag(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
+                    int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    constexpr int TILE = kScanTmaThreads * ITEMS;
+    const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
+    const size_t need = lag_ws_bytes(ntiles);
+    JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
+    JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
+    JG_REQUIRE(ntiles < (1ll << 31), "scan: too many tiles");
+    cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
+    if (e != cudaSuccess) {
+        set_error("scan: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    static unsigned resident = 0;
+    if (resident == 0) {
+        cudaFuncSetAttribute(scan_lag_kernel<T, XF, ITEMS, LAG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        resident = persistent_grid(scan_lag_kernel<T, XF, ITEMS, LAG>, kScanTmaThreads, 1ll << 40);
+        if (const char *c = getenv("JG_SCAN_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
+    }
+    const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    scan_lag_kernel<T, XF, ITEMS, LAG><<<grid, kScanTmaThreads, 0, stream>>>(
+        xf, in_a, in_b, n, out, total, status, lag_carve(ws, ntiles), static_cast<uint32_t>(ntiles), out_aligned);
+    return check_launch("scan_lag_kernel");
+}
+
 template <typename T, class XF, int ITEMS>
 int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    if (scan_mode() == 1) return launch_scan_lag<T, XF, ITEMS, 1>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
+    if (scan_mode() == 2) return launch_scan_lag<T, XF, ITEMS, 2>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
     constexpr int TILE = kScanTmaThreads * ITEMS;
     const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
     const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;

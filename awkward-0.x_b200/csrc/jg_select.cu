@@ -272,6 +272,292 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same selection as ONE persistent launch on the lagged prefixes of jg_lag.cuh.  In every iteration a CTA
+//   A. counts the selected positions of the tile it will own LAG iterations later (the whole CTA, 16-byte loads that
+//      leave the run in L2; the tile's offsets are prefetched into L2 on the way) and publishes the count;
+//   B. compacts its current tile exactly like mask_fill_kernel -- the staged run is now an L2 hit and the tile's base
+//      is the sum of aggregates published an iteration ago (lag_prefix: one L2 round trip, no waiting).
+// DRAM traffic is the algorithmic one: the column is read from HBM once (a[a > c] moved 9.1 GB for 6.6 GB before).
+// ------------------------------------------------------------------------------------------------------------
+template <class SEL>
+__device__ __forceinline__ int64_t cta_count_selected(const SEL &sel, const typename SEL::Elem *m, int64_t len) {
+    using E = typename SEL::Elem;
+    constexpr int PER = 16 / sizeof(E);
+    const int tid = threadIdx.x;
+    int64_t cnt = 0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
+    if (head > len) head = len;
+    if (tid < head) cnt += sel.test(m[tid]);
+    const int64_t nvec = (len - head) / PER;
+    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
+#pragma unroll 2
+    for (int64_t i = tid; i < nvec; i += kTileThreads) cnt += count16(sel, __ldg(mv + i));
+    const int64_t tail0 = head + nvec * PER;
+    if (tail0 + tid < len) cnt += sel.test(m[tail0 + tid]);
+    return cnt;
+}
+
+template <typename V, int KM, class SEL, bool SAME, int LAG>
+__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : 6)
+mask_select_lag_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
+                       int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
+                       int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
+                       int64_t *__restrict__ total, LagDesc lag, uint32_t ntiles) {
+    using E = typename SEL::Elem;
+    static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
+    constexpr int NW = kTileThreads / kWarp;
+    constexpr int R = LAG + 2;                  // ring of tile boundaries: current .. LAG ahead, plus the one in flight
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
+    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
+    __shared__ uint16_t s_pfx[KM + 2];
+    __shared__ uint64_t s_bar[2];
+    __shared__ int32_t s_scan[NW + 1];
+    __shared__ int64_t s_bnd[R][2];
+    __shared__ unsigned long long s_acc;
+    __shared__ int64_t s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t G = gridDim.x;
+    auto boundary = [&](uint64_t t, int which) -> int64_t {      // first / one-past-last event of tile t
+        const int64_t ev = static_cast<int64_t>(t) * kTileEvents + (which ? kTileEvents : 0);
+        return __ldg(offsets + (ev < n ? ev : n));
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        s_acc = 0ull;
+    }
+    if (tid < 2 * (LAG + 1)) {
+        const uint64_t t = blockIdx.x + static_cast<uint64_t>(tid >> 1) * G;
+        s_bnd[tid >> 1][tid & 1] = t < ntiles ? boundary(t, tid & 1) : 0;
+    }
+    __syncthreads();
+
+    // phase A of tile ta (its boundaries are in ring slot `slot`): every thread adds its share to s_acc
+    auto phase_a = [&](uint64_t ta, int slot) {
+        const int64_t a = s_bnd[slot][0], b = s_bnd[slot][1];
+        int64_t cnt = cta_count_selected(sel, mask + a + mask_shift, b - a);
+        if (tid <= (kTileEvents * 8) / 128) {                // the tile's offsets: 4 KB, fetched again by phase B
+            const int64_t ev = static_cast<int64_t>(ta) * kTileEvents + tid * 16;
+            if (ev <= n) prefetch_l2(offsets + ev);
+        }
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0 && cnt) atomicAdd(&s_acc, static_cast<unsigned long long>(cnt));
+    };
+    auto publish_a = [&](uint64_t ta) {                       // thread 0, after a barrier
+        lag_publish(lag, static_cast<uint32_t>(ta), static_cast<int64_t>(s_acc));
+        s_acc = 0ull;
+    };
+#pragma unroll 1
+    for (int j = 0; j < LAG; ++j) {
+        const uint64_t ta = blockIdx.x + static_cast<uint64_t>(j) * G;
+        if (ta < ntiles) phase_a(ta, j);
+        __syncthreads();
+        if (tid == 0 && ta < ntiles) publish_a(ta);
+        __syncthreads();
+    }
+
+    uint32_t it = 0;
+#pragma unroll 1
+    for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G, ++it) {
+        const uint32_t tile_index = static_cast<uint32_t>(tile64);
+        const uint32_t parity = it & 1u;
+        const int slot_b = it % R, slot_a = (it + LAG) % R, slot_n = (it + LAG + 1) % R;
+        // boundaries of the tile LAG + 1 iterations ahead (consumed by the next iteration's phase A)
+        int64_t next_bnd = 0;
+        {
+            const uint64_t tn = tile64 + static_cast<uint64_t>(LAG + 1) * G;
+            if (tid < 2 && tn < ntiles) next_bnd = boundary(tn, tid);
+        }
+        EventTile tile;
+        int64_t ev0;
+        int nev;
+        EventTile::range(n, tile_index, ev0, nev);
+        if (tid == 0) {
+            const int64_t a = s_bnd[slot_b][0], b = s_bnd[slot_b][1];
+            if (b > a && b - a <= KM) {
+                fence_proxy_async_smem();
+                if (!SAME)
+                    stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(mask + a + mask_shift),
+                               static_cast<uint32_t>((b - a) * sizeof(E)), &s_bar[1]);
+                stage_bulk(s_content, reinterpret_cast<const unsigned char *>(content + a),
+                           static_cast<uint32_t>((b - a) * sizeof(V)), &s_bar[0]);
+            }
+        }
+        // the tile's offsets (in flight during phase A)
+        int64_t o0 = 0, o1 = 0, o2 = 0;
+        {
+            const int64_t *src = offsets + ev0;
+            if (tid <= nev) o0 = __ldg(src + tid);
+            if (tid + kTileThreads <= nev) o1 = __ldg(src + tid + kTileThreads);
+            if (tid == 0 && nev == 2 * kTileThreads) o2 = __ldg(src + nev);
+        }
+        const uint64_t ta = tile64 + static_cast<uint64_t>(LAG) * G;
+        if (ta < ntiles) phase_a(ta, slot_a);
+        if (tid <= nev) s_off[tid] = o0;
+        if (tid + kTileThreads <= nev) s_off[tid + kTileThreads] = o1;
+        if (tid == 0 && nev == 2 * kTileThreads) s_off[nev] = o2;
+        if (tid < 2) s_bnd[slot_n][tid] = next_bnd;
+        __syncthreads();
+        if (tid == 0 && ta < ntiles) publish_a(ta);
+        tile.off = s_off;
+        tile.event0 = ev0;
+        tile.nev = nev;
+        if (warp == NW - 1) {                                     // the last warp has the least to do in pass 1
+            const int64_t b = lag_prefix(lag, tile_index);
+            if (lane == 0) s_base = b;
+        }
+        const int64_t e0 = tile.first_element(), e1 = tile.last_element();
+        const int64_t len = e1 - e0;
+
+        if (len <= KM) {
+            // ---------------- staged tile ------------------------------------------------------------------
+            const int L = static_cast<int>(len);
+            const V *cv = nullptr;
+            const E *mv = nullptr;
+            if (L > 0) {
+                const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
+                                                           static_cast<uint32_t>(L * sizeof(V)));
+                cv = reinterpret_cast<const V *>(s_content + cs);
+                if (SAME) {
+                    mbar_wait(&s_bar[0], parity);
+                    mv = reinterpret_cast<const E *>(cv);
+                } else {
+                    const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + e0 + mask_shift),
+                                                               static_cast<uint32_t>(L * sizeof(E)));
+                    mbar_wait(&s_bar[1], parity);
+                    mv = reinterpret_cast<const E *>(s_mask + ms);
+                }
+                __syncthreads();
+            }
+            const int rows_total = (L + 31) >> 5;
+            const int rows_per_warp = (rows_total + NW - 1) / NW;
+            const int p_begin = min(L, warp * rows_per_warp * 32);
+            const int p_end = min(L, p_begin + rows_per_warp * 32);
+            int cnt = 0;
+            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
+            cnt = warp_reduce_add(cnt);
+            if (lane == 0) s_scan[warp] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                int w = lane < NW ? s_scan[lane] : 0;
+                int wi = warp_incl_scan_add(w, lane);
+                if (lane < NW) s_scan[lane] = wi - w;
+                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+            }
+            if (!SAME && L > 0) mbar_wait(&s_bar[0], parity);
+            __syncthreads();
+            const int64_t base = s_base;
+            int run = s_scan[warp];
+            V *dst = out + base;
+            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+                const int p = p0 + lane;
+                const bool on = p < p_end && sel.test(mv[p]);
+                const unsigned b = __ballot_sync(0xffffffffu, on);
+                const int slot = run + __popc(b & ((1u << lane) - 1u));
+                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+                if (on) dst[slot] = cv[p];
+                run += __popc(b);
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int ev = tid; ev < tile.nev; ev += kTileThreads) {
+                const int first = s_pfx[s_off[ev] - e0];
+                new_offsets[tile.event0 + ev] = base + first;
+                if (new_counts) new_counts[tile.event0 + ev] = static_cast<int>(s_pfx[s_off[ev + 1] - e0]) - first;
+            }
+            if (tile_index == ntiles - 1 && tid == 0) {
+                new_offsets[n] = base + s_pfx[L];
+                if (total) *total = base + s_pfx[L];
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---------------- oversize tile (long events): chunks of KM positions straight from global memory ----
+        const V *cv = content + e0;
+        const E *mv = mask + e0 + mask_shift;
+        int64_t *s_new = reinterpret_cast<int64_t *>(s_content);
+        static_assert(KM * sizeof(V) + 32 >= (kTileEvents + 1) * sizeof(int64_t), "stage too small for the offsets");
+        const int evA = tid, evB = tid + kTileThreads;
+        const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
+        const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
+        __syncthreads();                                           // s_base
+        const int64_t base = s_base;
+        int64_t run = 0;
+#pragma unroll 1
+        for (int64_t cs = 0; cs < len; cs += KM) {
+            const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
+            const E *m = mv + cs;
+            const V *c = cv + cs;
+            const int rows_total = (L + 31) >> 5;
+            const int rows_per_warp = (rows_total + NW - 1) / NW;
+            const int p_begin = min(L, warp * rows_per_warp * 32);
+            const int p_end = min(L, p_begin + rows_per_warp * 32);
+            int cnt = 0;
+#pragma unroll 1
+            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);
+            cnt = warp_reduce_add(cnt);
+            if (lane == 0) s_scan[warp] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                int w = lane < NW ? s_scan[lane] : 0;
+                int wi = warp_incl_scan_add(w, lane);
+                if (lane < NW) s_scan[lane] = wi - w;
+                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+            }
+            __syncthreads();
+            int wrun = s_scan[warp];
+            V *dst = out + base + run;
+#pragma unroll 1
+            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+                const int p = p0 + lane;
+                const bool on = p < p_end && sel.test(m[p]);
+                const unsigned b = __ballot_sync(0xffffffffu, on);
+                const int slot = wrun + __popc(b & ((1u << lane) - 1u));
+                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+                if (on) dst[slot] = c[p];
+                wrun += __popc(b);
+            }
+            __syncthreads();
+            if (stA >= cs && stA < cs + L) s_new[evA] = run + s_pfx[stA - cs];
+            if (stB >= cs && stB < cs + L) s_new[evB] = run + s_pfx[stB - cs];
+            run += s_pfx[L];
+            __syncthreads();
+        }
+        if (stA >= len) s_new[evA] = run;
+        if (stB >= len) s_new[evB] = run;
+        if (tid == 0) s_new[tile.nev] = run;
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ev = tid + h * kTileThreads;
+            if (ev < tile.nev) {
+                new_offsets[tile.event0 + ev] = base + s_new[ev];
+                if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
+            }
+        }
+        if (tile_index == ntiles - 1 && tid == 0) {
+            new_offsets[n] = base + run;
+            if (total) *total = base + run;
+        }
+        __syncthreads();
+    }
+}
+
+inline int select_mode() {    // experiment switch (JG_SELECT_MODE): 0 = count / scan / fill (round 1), 1 / 2 = lagged, LAG 1 / 2
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("JG_SELECT_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
 // counts of two layouts must agree (jagged.py:911-912)
 __global__ void __launch_bounds__(256)
 same_counts_kernel(const int64_t *__restrict__ oa, const int64_t *__restrict__ ob, int64_t n,
@@ -441,6 +727,37 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
                               const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                               int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
+    if (select_mode() != 0) {
+        const size_t need = lag_ws_bytes(ntiles);
+        JG_REQUIRE(ws != nullptr && ws_bytes >= need, "jg_mask_select: workspace too small (%zu < %zu)", ws_bytes, need);
+        JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "jg_mask_select: workspace must be 16-byte aligned");
+        cudaError_t e = cudaMemsetAsync(ws, 0, need, s);
+        if (e != cudaSuccess) {
+            set_error("jg_mask_select: cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        const LagDesc lag = lag_carve(ws, ntiles);
+        if (select_mode() == 2) {
+            static unsigned resident = 0;
+            if (resident == 0) {
+                resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 2>, kTileThreads, 1ll << 40);
+                if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
+            }
+            mask_select_lag_kernel<V, KM, SEL, SAME, 2><<<static_cast<unsigned>(ntiles < resident ? ntiles : resident), kTileThreads, 0, s>>>(
+                sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+                new_counts, total, lag, static_cast<uint32_t>(ntiles));
+        } else {
+            static unsigned resident = 0;
+            if (resident == 0) {
+                resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 1>, kTileThreads, 1ll << 40);
+                if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
+            }
+            mask_select_lag_kernel<V, KM, SEL, SAME, 1><<<static_cast<unsigned>(ntiles < resident ? ntiles : resident), kTileThreads, 0, s>>>(
+                sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+                new_counts, total, lag, static_cast<uint32_t>(ntiles));
+        }
+        return check_launch("mask_select_lag_kernel");
+    }
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
     if (rc) return rc;

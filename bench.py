@@ -3,7 +3,7 @@
 for sum/argmax/mask/pairs at 1/2/4/8 GPUs").
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port), host cores
+    python bench.py --impl reference --gpus N --steps K ...   # the reference itself (awkward0, oracle/_ref), host cores
 
 Workload (config.workload): BASELINE.json configs[4] shard -- per GPU 125 M events (1 B events at 8 GPUs),
 Poisson(5) counts, float32 content Exp(25); one STEP = counts2offsets scan + segmented sum + argmax +
@@ -13,8 +13,9 @@ scaling: every rank owns the same number of events, no data-path collective.
 value  = content elements swept per second with inputs resident in HBM (CUDA events, max over ranks)
 e2e    = the same sweep through the public API from pinned HOST buffers (H2D inside the timed region, totals read back)
 roofline = dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
-cpu_baseline = the numpy oracle (a port of the reference's algorithm, oracle/jagged_oracle.py) on one host core,
-               bounded sample; `--impl reference` runs it on all host cores (one process per core, equal shards)
+cpu_baseline = the UNMODIFIED reference (oracle/_ref, see oracle/fetch_ref.py; the numpy oracle port only if that copy
+               is absent) on one host core, bounded sample; `--impl reference` runs it on all host cores (one process
+               per core, equal shards); every API workflow also carries the reference's time on a stated sample
 """
 import argparse
 import json
@@ -60,8 +61,34 @@ def _worker_init(nevents, seed_base):
     _W["data"] = make_shard(nevents, seed)
 
 
+def reference_module():
+    """The UNMODIFIED reference (awkward0): /root/reference in the build container, else the byte-identical copy
+    oracle/_ref that oracle/fetch_ref.py made and the gpurun snapshot carried (None when neither exists)."""
+    if "mod" not in _REF:
+        from oracle import _refloader
+        _REF["mod"] = _refloader.load() if _refloader.available() else None
+    return _REF["mod"]
+
+
+_REF = {}
+
+
+def cpu_kind():
+    return "reference" if reference_module() is not None else "port"
+
+
 def cpu_sweep(counts, pt):
-    """The same sweep with the reference's algorithm (numpy): returns (elements, checksum tuple)."""
+    """The same sweep on the CPU: through the reference's own API when the reference is here, else with the numpy
+    oracle port of its algorithm.  Returns (elements, checksum tuple)."""
+    ref = reference_module()
+    if ref is not None:
+        a = ref.JaggedArray.fromcounts(counts, pt)
+        s = a.sum()
+        lead = a.argmax()
+        sel = a[a > THRESHOLD]
+        flat = sel.flatten()
+        c = sel.counts
+        return len(pt), (float(s.sum(dtype=np.float64)), int(len(flat)), int(lead.counts.sum()), int(c.sum()))
     from oracle import jagged_oracle as O
     off = O.counts2offsets(counts)
     s = O.reduce(off, pt, "sum")
@@ -105,15 +132,20 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "events_per_step": per_worker * cores, "threshold": THRESHOLD},
-        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port",
-                         "sample": "%d events per core x %d cores per step (Poisson(5), f32), numpy oracle port of "
-                                   "awkward0/array/jagged.py; the reference itself is pure Python and cannot travel "
-                                   "to the GPU box" % (per_worker, cores)},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": cpu_kind(),
+                         "sample": "%d events per core x %d cores per step (Poisson(5), f32), one process per core on equal "
+                                   "event shards (the reference's ChunkedArray decomposition); %s"
+                                   % (per_worker, cores, CPU_KIND_NOTE[cpu_kind()])},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
     return 0
 
+
+CPU_KIND_NOTE = {
+    "reference": "the UNMODIFIED reference awkward0 (oracle/_ref, copied by oracle/fetch_ref.py) through its own API",
+    "port": "numpy oracle port of awkward0/array/jagged.py (oracle/_ref is absent on this box)",
+}
 
 WORKLOAD_NAME = ("C5 sweep shard: 125M events/GPU (1B events at 8 GPUs), Poisson(5) counts, float32 Exp(25) content; "
                  "step = counts2offsets + sum + argmax + (pt>20) mask-select + flatten/counts + global totals")
@@ -309,6 +341,14 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args)
+        if workflows:
+            # the reference's time for the same API chains (per-unit rates are comparable: the CPU sample is smaller)
+            for name, row in cpu_workflows(args).items():
+                if name in workflows:
+                    workflows[name].update(row)
+                    unit = [k for k in row if k.endswith("_per_s")][0][4:]
+                    if unit in workflows[name]:
+                        workflows[name]["speedup_vs_cpu_1core"] = workflows[name][unit] / row["cpu_" + unit]
 
     if rank == 0:
         line = {
@@ -560,6 +600,8 @@ def workflow_table(ak, counts_dev, pt_dev, N, M, args):
         sel = arr[arr > THRESHOLD]
         return sel.flatten(), sel.counts
 
+    timed("C1_sum_f32", lambda: a.sum(), M, "elements")
+    timed("C1_max_f32", lambda: a.max(), M, "elements")
     timed("C2_mask_flatten_counts_f32", lambda: c2(a), M, "elements")
     a64 = ak.JaggedArray.fromoffsets(a.offsets, ak.DeviceArray(pt_dev.tensor.double()))
     timed("C2_mask_flatten_counts_f64", lambda: c2(a64), M, "elements")
@@ -618,6 +660,93 @@ def workflow_table(ak, counts_dev, pt_dev, N, M, args):
     return out
 
 
+def cpu_workflows(args):
+    """BASELINE configs[0..3] on the host CPU (one core: numpy's cumsum / repeat / reduceat / take are single
+    threaded), the same API chains as workflow_table on a stated sample of the same synthetic data.  With the
+    reference present (oracle/_ref) this is the reference itself; otherwise the oracle port covers what it restates."""
+    ref = reference_module()
+    out = {}
+
+    def best_of(fn, reps=1):
+        fn()                      # warm-up (page faults of the temporaries)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    def put(name, seconds, units, unit_name, sample):
+        out[name] = {"cpu_ms": 1e3 * seconds, "cpu_" + unit_name + "_per_s": units / seconds, "cpu_sample": sample,
+                     "cpu_kind": cpu_kind(), "cpu_cores": 1}
+
+    n = args.cpu_workflow_events
+    counts, pt = make_shard(n, 12345)
+    M = len(pt)
+    sample = "%d events, %d elements (Poisson(5), Exp(25))" % (n, M)
+    if ref is not None:
+        JA = ref.JaggedArray
+        a = JA.fromcounts(counts, pt)
+        put("C1_sum_f32", best_of(lambda: a.sum()), M, "elements", sample)
+        put("C1_max_f32", best_of(lambda: a.max()), M, "elements", sample)
+
+        def c2(arr):
+            sel = arr[arr > THRESHOLD]
+            return sel.flatten(), sel.counts
+        put("C2_mask_flatten_counts_f32", best_of(lambda: c2(a)), M, "elements", sample)
+        a64 = JA.fromoffsets(a.offsets, pt.astype(np.float64))
+        put("C2_mask_flatten_counts_f64", best_of(lambda: c2(a64)), M, "elements", sample)
+        del a64
+        put("C3_leading_object_argmax_getitem_f32", best_of(lambda: a[a.argmax()]), M, "elements", sample)
+        nc = args.cpu_comb_events
+        rng = np.random.default_rng(777)
+        mc, ec = rng.poisson(2.0, nc).astype(np.int64), rng.poisson(2.0, nc).astype(np.int64)
+        Mm, Me = int(mc.sum()), int(ec.sum())
+
+        def collection(c, m):
+            first = JA.fromcounts(c, rng.exponential(20.0, m).astype(np.float32))
+            mk = lambda x: JA.fromoffsets(first.offsets, x)
+            return JA.zip(pt=first, eta=mk(rng.uniform(-2.4, 2.4, m).astype(np.float32)),
+                          phi=mk(rng.uniform(-np.pi, np.pi, m).astype(np.float32)))
+
+        mu, el = collection(mc, Mm), collection(ec, Me)
+
+        def mass(p):
+            one, two = p.i0, p.i1
+            return np.sqrt(2 * one.pt * two.pt * (np.cosh(one.eta - two.eta) - np.cos(one.phi - two.phi)))
+
+        csample = "%d events, %d muons, %d electrons (Poisson(2))" % (nc, Mm, Me)
+        P, X, D = int(((mc * (mc + 1)) // 2).sum()), int((mc * ec).sum()), int(((mc * (mc - 1)) // 2).sum())
+        put("C4_argpairs", best_of(lambda: mu.argpairs(), 1), P, "pairs", csample)
+        put("C4_pairs_plus_invariant_mass", best_of(lambda: mass(mu.pairs()), 1), P, "pairs", csample)
+        put("C4_cross_plus_invariant_mass", best_of(lambda: mass(mu.cross(el)), 1), X, "pairs", csample)
+        put("C4_distincts_plus_invariant_mass", best_of(lambda: mass(mu.distincts()), 1), D, "pairs", csample)
+    else:
+        from oracle import jagged_oracle as O
+        off = O.counts2offsets(counts)
+        put("C1_sum_f32", best_of(lambda: O.reduce(off, pt, "sum")), M, "elements", sample)
+        put("C1_max_f32", best_of(lambda: O.reduce(off, pt, "max")), M, "elements", sample)
+
+        def c2(content):
+            moff, mask = O.ufunc_broadcast(np.greater, off, content, content.dtype.type(THRESHOLD))
+            soff, sel = O.mask_select(off, content, moff, mask)
+            return O.flatten(soff, sel), O.offsets2counts(soff)
+        put("C2_mask_flatten_counts_f32", best_of(lambda: c2(pt)), M, "elements", sample)
+        pt64 = pt.astype(np.float64)
+        put("C2_mask_flatten_counts_f64", best_of(lambda: c2(pt64)), M, "elements", sample)
+
+        def c3():
+            aoff, aidx = O.argminmax(off, pt, False)
+            return O.index_gather(off, pt, aoff, aidx)
+        put("C3_leading_object_argmax_getitem_f32", best_of(c3), M, "elements", sample)
+        nc = args.cpu_comb_events
+        mc = np.random.default_rng(777).poisson(2.0, nc).astype(np.int64)
+        moff = O.counts2offsets(mc)
+        put("C4_argpairs", best_of(lambda: O.argpairs(moff), 1), int(((mc * (mc + 1)) // 2).sum()), "pairs",
+            "%d events (Poisson(2))" % nc)
+    return out
+
+
 def _leaf_columns(content):
     if hasattr(content, "columns") and not hasattr(content, "tensor"):
         for name in content.columns:
@@ -638,9 +767,9 @@ def cpu_baseline(args):
         elements, _ = cpu_sweep(counts, pt)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": elements / best, "unit": "elements/s", "cores": 1, "kind": "port",
-            "sample": "%d events (%d elements) of the same sweep, numpy oracle port of awkward0/array/jagged.py, "
-                      "best of 2; host has %d cores" % (n, elements, os.cpu_count() or 0),
+    return {"value": elements / best, "unit": "elements/s", "cores": 1, "kind": cpu_kind(),
+            "sample": "%d events (%d elements) of the same sweep, %s, best of 2; host has %d cores"
+                      % (n, elements, CPU_KIND_NOTE[cpu_kind()], os.cpu_count() or 0),
             "seconds": best}
 
 
@@ -670,8 +799,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=125_000_000)
     ap.add_argument("--comb-events", type=int, default=50_000_000)
-    ap.add_argument("--cpu-events", type=int, default=16_000_000)
+    ap.add_argument("--cpu-events", type=int, default=4_000_000)
     ap.add_argument("--ref-events-per-core", type=int, default=1_000_000)
+    ap.add_argument("--cpu-workflow-events", type=int, default=10_000_000,
+                    help="events of the CPU sample behind every workflow's cpu_ms (C1 runs at its full size)")
+    ap.add_argument("--cpu-comb-events", type=int, default=1_000_000)
     ap.add_argument("--kernel-reps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=8,
                     help="event chunks of the streamed host->HBM ingest used by the e2e leg (0: copy everything, then compute)")

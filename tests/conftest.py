@@ -44,3 +44,36 @@ def same(a, b):
         return bool(np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb]) and
                     np.array_equal(np.signbit(a[~na]), np.signbit(b[~nb])))
     return bool(np.array_equal(a, b))
+
+
+def reduce_close(op, got, want, offsets, content, rtol):
+    """north_star's tolerance for float `sum` / `prod` (the reduction order differs from the reference's sequential
+    reduceat): |got - want| <= rtol * |want|, rtol = 1e-5 (float32) / 1e-12 (float64).  Events that fail it must be
+    explained by the conditioning of the event itself, the same bound the golden test uses:
+      sum : |got - want| <= rtol * sum(|x|)        (cancellation between terms of mixed sign)
+      prod: relative error <= 2 * n * eps           (n roundings in another order; only beyond n ~ 80 (f32))
+    Returns a boolean array (one per event)."""
+    got = np.asarray(got)
+    want = np.asarray(want)
+    with np.errstate(all="ignore"):
+        ok = np.isclose(got, want, rtol=rtol, atol=0, equal_nan=True)
+        if ok.all() or len(content) == 0:
+            return ok
+        off = np.asarray(offsets)
+        x = np.nan_to_num(np.asarray(content).astype(np.float64), nan=0.0 if op == "sum" else 1.0, posinf=0.0, neginf=0.0)
+        starts = np.minimum(off[:-1], len(x) - 1)
+        nonempty = off[1:] > off[:-1]
+        if op == "sum":
+            absum = np.where(nonempty, np.add.reduceat(np.abs(x), starts), 0.0)
+            ok |= np.abs(got.astype(np.float64) - want.astype(np.float64)) <= rtol * absum
+        else:
+            n = (off[1:] - off[:-1]).astype(np.float64)
+            bound = np.maximum(rtol, 2.0 * n * np.finfo(want.dtype).eps)
+            finite = np.isfinite(want) & np.isfinite(got) & (np.abs(want) > np.finfo(want.dtype).tiny)
+            ok |= finite & (np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound * np.abs(want.astype(np.float64)))
+            # a product that over- or underflows does so in both orders only up to the last factor: accept inf / 0 /
+            # subnormal results when the exact (float64, log-domain) magnitude is outside the normal range
+            logmag = np.where(nonempty, np.add.reduceat(np.log2(np.maximum(np.abs(x), 1e-300)), starts), 0.0)
+            info = np.finfo(want.dtype)
+            ok |= (logmag > info.maxexp - 2) | (logmag < info.minexp + 2)
+    return ok

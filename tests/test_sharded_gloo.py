@@ -45,8 +45,19 @@ def _worker(rank, world, port, nevents, result_dir):
         lmax = O.reduce(loff, lpt, "max")
         moff, mask = O.ufunc_broadcast(np.greater, loff, lpt, np.float32(20))
         soff, sel = O.mask_select(loff, lpt, moff, mask)
+        local_max = float(lmax.max()) if len(lmax) else float("-inf")     # an empty shard contributes the identity
         (gsum, gk), (gmax,), _ = sharded.allreduce_totals(
-            sums=[float(lsum.sum(dtype=np.float64)), int(len(sel))], maxima=[float(lmax.max())])
+            sums=[float(lsum.sum(dtype=np.float64)), int(len(sel))], maxima=[local_max])
+        # the same totals through the one-collective / one-read-back buffer (device tensors and host numbers mixed)
+        acc = sharded.DeviceTotals()
+        acc.add_sum(torch.tensor([float(lsum.sum(dtype=np.float64))], dtype=torch.float64))
+        acc.add_sum(int(len(sel)))
+        acc.add_max(torch.tensor([local_max], dtype=torch.float32))
+        acc.add_min(torch.tensor([2 ** 60 + 7 + rank], dtype=torch.int64))       # integers stay exact above 2^53
+        dsum, dk, dmax, dmin = acc.finish()
+        assert dsum == gsum and dk == gk and dmax == gmax and dmin == 2 ** 60 + 7 and isinstance(dk, int)
+        lo_sizes = [b - a for a, b in (sharded.event_range(nevents, r, world) for r in range(world))]
+        assert np.array_equal(sharded.gather_per_event(lsum, sizes=lo_sizes).numpy(), sharded.gather_per_event(lsum).numpy())
         every_sum = sharded.gather_per_event(lsum).numpy()
         sel_counts, sel_content = sharded.gather_jagged(O.offsets2counts(soff), sel)      # variable-size result
         base = sharded.global_offsets_base(len(lpt))
@@ -88,7 +99,7 @@ def _worker(rank, world, port, nevents, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nevents", [10001, 4])
+@pytest.mark.parametrize("nevents", [10001, 10000, 4, 1])      # unequal / equal shards, tiny, and an EMPTY shard on rank 1
 def test_two_rank_gloo_matches_single_process(tmp_path, nevents):
     from oracle import jagged_oracle as O
     world = 2
