@@ -91,6 +91,12 @@ PROTOTYPES = {
                                   ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
     "jg_comb_gather2": (_i, [_i, _vp, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "jg_comb_eval": (_i, [_i, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
+    "jg_elem_workspace_bytes": (_sz, [_i64, _i]),
+    "jg_segreduce_elem": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _sz, _vp]),
+    "jg_segargminmax_elem": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "jg_mask_select_elem": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "jg_compare_select_elem": (_i, [_vp, _i, _vp, _i, _i, _d, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "jg_expand_elem": (_i, [_i, _vp, _i, _vp, _i64, _vp, _i64, _vp, _sz, _vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():
@@ -111,7 +117,8 @@ def check(rc, what):
 # kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
 LAUNCHES = [0]
 _KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
-            "jg_mask_select": 3, "jg_compare_select": 3, "jg_segargminmax_dense": 3, "jg_segargminmax_dense_tiles": 2, "jg_flat_compact": 2}
+            "jg_mask_select": 1, "jg_compare_select": 1, "jg_segreduce_elem": 3, "jg_segargminmax_elem": 3,
+            "jg_mask_select_elem": 3, "jg_compare_select_elem": 3, "jg_expand_elem": 2, "jg_segargminmax_dense": 3, "jg_segargminmax_dense_tiles": 2, "jg_flat_compact": 2}
 
 
 def call(name, *args):

@@ -104,6 +104,17 @@ class _Runtime(object):
             self._ws[key] = buf
         return ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel())
 
+    def elem_workspace(self, content_len, itemsize):
+        """(pointer, bytes) of scratch for the element-tiled calls (sized by content elements, not by events)."""
+        dev = self.device()
+        need = int(lib.jg_elem_workspace_bytes(int(content_len), int(itemsize)))
+        key = self._key(dev) + ("elem",)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+            self._ws[key] = buf
+        return ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel())
+
     def scalars(self):
         """A zeroed int64[8] on the device: [0] total, [1] status (low 32 bits), [2:6] info.
 
@@ -270,7 +281,7 @@ class DeviceArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         from . import _ufunc
         for x in inputs:
-            if type(x).__name__ == "JaggedArray":       # let the jagged operand drive the broadcast
+            if type(x).__name__ in ("JaggedArray", "Table"):     # the jagged operand drives the broadcast, a Table its columns
                 return NotImplemented
         if "out" in kwargs:
             raise NotImplementedError("in-place operations not supported")
@@ -284,6 +295,20 @@ class DeviceArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     def sum(self):
         return self._reduce(_lib.SUM)
+
+    def device_sum(self):
+        """sum() left in HBM as a 1-element DeviceArray (no device-to-host copy, no synchronisation): what a step
+        hands to sharded.DeviceTotals so that all its whole-array totals travel in one collective and one read-back."""
+        from . import _ufunc
+        return _ufunc.flat_reduce_device(self, _lib.SUM)
+
+    def device_max(self):
+        from . import _ufunc
+        return _ufunc.flat_reduce_device(self, _lib.MAX)
+
+    def device_min(self):
+        from . import _ufunc
+        return _ufunc.flat_reduce_device(self, _lib.MIN)
 
     def prod(self):
         return self._reduce(_lib.PROD)

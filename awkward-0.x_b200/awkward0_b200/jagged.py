@@ -30,6 +30,8 @@ from .masked import MaskedArray, fill_masked
 from .device import DeviceMatrix
 from .table import Table
 
+_ELEM_DTYPES = (numpy.dtype(numpy.float32), numpy.dtype(numpy.float64), numpy.dtype(numpy.int32), numpy.dtype(numpy.int64))
+
 
 def _vp(t, offset_items=0):
     return ctypes.c_void_p(t.data_ptr() + offset_items * t.element_size()) if t is not None else ctypes.c_void_p(0)
@@ -126,14 +128,28 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         n = len(offsets) - 1
         if n < 0:
             raise ValueError("offsets must be a non-empty array")
-        last = int(offsets[-1]) if n >= 0 else 0
-        return cls._parents_from(offsets, n, last)
+        first, last = (int(x) for x in offsets.tensor[[0, -1]].cpu().tolist())
+        return cls._parents_from(offsets, n, last, first)
+
+    # Count distribution -> kernel variant (north_star: "variants chosen by count distribution").  The event tile (512
+    # events, 16 KB of staged content) fits mean counts up to ~7; beyond that -- Poisson(40), a few huge events -- the
+    # element-tiled kernels of csrc/jg_elem.cu split the work by CONTENT instead.  Both give the same results.
+    LONG_EVENTS_MEAN = 7
 
     @classmethod
-    def _parents_from(cls, off64, n, last):
+    def _long_events(cls, n, content_len):
+        return n > 0 and content_len > cls.LONG_EVENTS_MEAN * n and content_len >= (1 << 14)
+
+    @classmethod
+    def _parents_from(cls, off64, n, last, first=None):
         out = empty(last, INDEXTYPE)
         if last > 0:
-            call("jg_offsets2parents", off64.data_ptr(), n, _vp(out), runtime.stream())
+            if first is not None and cls._long_events(n, last - first):
+                ws, wsb = runtime.elem_workspace(last - first, 4)
+                call("jg_expand_elem", 0, ctypes.c_void_p(0), 8, off64.data_ptr(), n, _vp(out), last - first, ws, wsb,
+                     runtime.stream())
+            else:
+                call("jg_offsets2parents", off64.data_ptr(), n, _vp(out), runtime.stream())
         return DeviceArray(out, INDEXTYPE)
 
     @classmethod
@@ -209,8 +225,9 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         self._general = None
         self._maxcount = None
         self._tile_nonempty = None       # non-empty events per 512-event tile, a by-product of fromcounts' scan
-        self._arg_source = None          # set on argmin/argmax results: (offsets, content) they were computed from
+        self._arg_source = None          # set on argmin/argmax results: (offsets, content, write epoch) they were computed from
         self._arg_values = None
+        self._nestedcross = None         # set on cross(nested=True) results: the flat form (jagged.py:1357)
 
     @classmethod
     def _tocontent(cls, content):
@@ -696,7 +713,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if self._parents is None:
             self._valid()
             if self._off64 is not None:
-                self._parents = self._parents_from(self._off64, len(self._off64) - 1, self._last)
+                self._parents = self._parents_from(self._off64, len(self._off64) - 1, self._last, self._first)
             else:
                 self._parents = self.startsstops2parents(*self._general)
         return self._parents
@@ -707,7 +724,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         a, off, n, first, last = self._dense()
         out = empty(last - first, INDEXTYPE)
         if last > first:
-            call("jg_localindex", off.data_ptr(), n, _vp(out), runtime.stream())
+            if self._long_events(n, last - first):
+                ws, wsb = runtime.elem_workspace(last - first, 4)
+                call("jg_expand_elem", 1, ctypes.c_void_p(0), 8, off.data_ptr(), n, _vp(out), last - first, ws, wsb,
+                     runtime.stream())
+            else:
+                call("jg_localindex", off.data_ptr(), n, _vp(out), runtime.stream())
         return self._make(a._rebased_offsets(), DeviceArray(out, INDEXTYPE), last - first)
 
     def _rebased_offsets(self):
@@ -1148,7 +1170,14 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                 h = a._align(h)
                 newoffsets, total, _ = self._scan_counts(h.sum())
                 return self._make(newoffsets, inner[h._dense_content()], total)
-            raise NotImplementedError("integer jagged indexes over nested content are outside the GPU hot path")
+            if isinstance(h._content, DeviceArray) and _isintegertype(h._content.dtype):
+                # jagged.py:541-560 one level down: local indexes pick whole INNER EVENTS.  The checked gather kernel
+                # (negative wrap, bounds) runs on the positions 0 .. n_inner-1 laid out like the outer level; the
+                # absolute positions it returns select the inner events (event-level selection, general layout).
+                positions = self._make(roff, DeviceArray(torch.arange(n_inner, dtype=torch.int64, device=runtime.device())), n_inner)
+                picked = positions._getitem_jagged_int(h)
+                return self._make(picked._off64, inner[picked._dense_content()], picked._last, picked._first)
+            raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
         if not isinstance(head._content, DeviceArray):
             raise TypeError("jagged index must be boolean (mask) or integer (fancy indexing)")
         hdt = head._content.dtype
@@ -1183,10 +1212,23 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if fused:
             op, scalar = _lib.OP[mask._op], mask._scalar
 
+        long_events = self._long_events(n, last - first)
+        if long_events:
+            ews, ewsb = runtime.elem_workspace(last - first, 4)
+
         def select(col):
             out = empty(last - first, col.dtype)
             counts_ptr = _vp(new_counts) if not columns else ctypes.c_void_p(0)
-            if fused:
+            if long_events and col.itemsize in (4, 8) and (not fused or same or key.itemsize == col.itemsize):
+                # long events: flat compaction of 16 KB content tiles (one persistent launch) + rank at event boundaries
+                if fused:
+                    call("jg_compare_select_elem", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
+                         jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,
+                         _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), last - first, ews, ewsb, runtime.stream())
+                else:
+                    call("jg_mask_select_elem", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
+                         _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), last - first, ews, ewsb, runtime.stream())
+            elif fused:
                 call("jg_compare_select", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
                      jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,
                      _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, runtime.stream())
@@ -1259,7 +1301,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             flat = flat[:n]                     # ... and one that is longer is simply not read beyond len(self)
         out = empty(last - first, flat.dtype)
         if last > first:
-            call("jg_broadcast", flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), runtime.stream())
+            if self._long_events(n, last - first):
+                ws, wsb = runtime.elem_workspace(last - first, 4)
+                call("jg_expand_elem", 2, flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), last - first, ws,
+                     wsb, runtime.stream())
+            else:
+                call("jg_broadcast", flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), runtime.stream())
         return self._make(a._rebased_offsets(), DeviceArray(out, flat.dtype), last - first)
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
@@ -1291,8 +1338,24 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                         raise ValueError("cannot broadcast JaggedArray of shape {0} with array of shape {1}".format((n,), flat.shape))
                     inner_ops.append(a.tojagged(flat)._content)
             return self._make(a._rebased_offsets(), ufunc(*inner_ops), last - first)
-        if isinstance(a._content, Table):
-            raise NotImplementedError("ufuncs on Table content are outside the GPU hot path (no CPU fallback)")
+        if isinstance(a._content, Table) or any(isinstance(x, JaggedArray) and isinstance(x._content, Table) for x in inputs):
+            # records (table.py:668-738 under jagged.py:1039-1051): flatten, let the Table apply the ufunc column by
+            # column (flat operands are broadcast to the content's length first), re-wrap on the shared offsets
+            flat_ops = []
+            for x in inputs:
+                if isinstance(x, JaggedArray):
+                    b = a._align(x) if x is not lead else a
+                    flat_ops.append(b._dense_content())
+                elif _ufunc.is_scalar(x):
+                    flat_ops.append(x)
+                else:
+                    flat = asdevice(x) if not isinstance(x, DeviceArray) else x
+                    if flat.shape != (n,):
+                        raise ValueError("cannot broadcast JaggedArray of shape {0} with array of shape {1}".format((n,), flat.shape))
+                    flat_ops.append(a.tojagged(flat)._content)
+            out = self._make(a._rebased_offsets(), ufunc(*flat_ops), last - first)
+            out._counts = a._counts
+            return out
 
         operands, parent_side = [], None
         for i, x in enumerate(inputs):
@@ -1360,8 +1423,13 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         odt = self._reduce_out_dtype(op, col.dtype)
         out = empty(n, odt)
         if n > 0:
-            call("jg_segreduce", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out), len(col),
-                 runtime.stream())
+            if self._long_events(n, last - first) and col.dtype in _ELEM_DTYPES:
+                ws, wsb = runtime.elem_workspace(last - first, col.itemsize)
+                call("jg_segreduce_elem", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out),
+                     last - first, ws, wsb, runtime.stream())
+            else:
+                call("jg_segreduce", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out), len(col),
+                     runtime.stream())
         return DeviceArray(out, odt)
 
     def any(self):
@@ -1453,6 +1521,16 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out_index = empty(n, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
+        if self._long_events(n, last - first) and col.dtype in _ELEM_DTYPES:
+            # long events: element-tiled arg-reduce to best[] (a partial per tile, merged in tile order), then the scan +
+            # compaction of jg_compact_nonneg -- N-sized passes, small next to the content when events are long
+            best, best_value = empty(n, INDEXTYPE), empty(n, col.dtype)
+            ews, ewsb = runtime.elem_workspace(last - first, col.itemsize)
+            call("jg_segargminmax_elem", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0, _vp(best),
+                 _vp(best_value), last - first, ews, ewsb, runtime.stream())
+            call("jg_compact_nonneg", _vp(best), n, _vp(out_offsets), _vp(out_index), _vp(scal), ws, wsb, runtime.stream())
+            total, _, _ = runtime.read(scal)
+            return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
         values = empty(n, col.dtype) if self.cache_arg_values else None
         tiles = a._tile_nonempty               # known when the array came from fromcounts: no counting pass
         call("jg_segargminmax_dense_tiles", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
@@ -1630,12 +1708,30 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return self._nest(out, _lib.COMB_CROSS, other=other) if nested else out
 
     def cross(self, other, nested=False):
+        """jagged.py:1339-1367.  A `nested=True` result remembers its flat form (`_nestedcross`); crossing it again
+        crosses that flat form with `other` and regroups the combinations under the first array's items, so that
+        a.cross(b, nested=True).cross(c, nested=True) is [event][a][b][c] (jagged.py:1342-1365)."""
         self._valid()
         self._check_cross(other)
-        if isinstance(self._content, JaggedArray) or isinstance(other._content, JaggedArray):
-            raise NotImplementedError("chained nested cross is outside the GPU hot path (SURVEY.md section 8f-2)")
-        out = self._comb_values(_lib.COMB_CROSS, other=other)
-        return self._nest(out, _lib.COMB_CROSS, other=other) if nested else out
+        thyself = self._nestedcross if self._nestedcross is not None else self
+        if isinstance(thyself._content, JaggedArray) or isinstance(other._content, JaggedArray):
+            raise NotImplementedError("cross over jagged-of-jagged content is outside the GPU hot path (SURVEY.md section 8f-2)")
+        out = thyself._comb_values(_lib.COMB_CROSS, other=other)
+        if nested:
+            old = out
+            out = thyself._nest(out, _lib.COMB_CROSS, other=other)
+            out._nestedcross = old
+        if thyself is not self:
+            # jagged.py:1359-1365: the outer level of `out` counts combinations per event of `thyself`; split it by the
+            # first array's items (counts // self.counts wherever self.counts != 0; both are 0 elsewhere)
+            mine = self.counts
+            per_item = out.counts // numpy.maximum(mine, 1)
+            inner_offsets, inner_total, _ = self._scan_counts(self.tojagged(per_item).flatten())
+            outer_offsets, outer_total, _ = self._scan_counts(mine)
+            old = out
+            out = self._make(outer_offsets, self._make(inner_offsets, out._content, inner_total), outer_total)
+            out._nestedcross = old
+        return out
 
     # ------------------------------------------------------------------------------------------------------
     # outside the hot path: fail loudly (north_star: no CPU fallback)

@@ -7,6 +7,9 @@ Row objects, views and recarray I/O are host-side conveniences of the reference 
 """
 from collections import OrderedDict
 
+import numpy
+import numpy.lib.mixins
+
 from .device import DeviceArray, asdevice
 
 
@@ -15,7 +18,43 @@ class _HostColumns(OrderedDict):
     istuple = False
 
 
-class Table(object):
+_COMPARISONS = (numpy.less, numpy.less_equal, numpy.equal, numpy.not_equal, numpy.greater, numpy.greater_equal)
+
+
+class Table(numpy.lib.mixins.NDArrayOperatorsMixin):
+    __array_priority__ = 60          # above DeviceArray: `column (op) table` is the table's business
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """table.py:668-738: a ufunc on records is the ufunc on every column (one launch per column; operands that
+        are not Tables meet every column); a comparison is the AND of the per-column comparisons (one bool array)."""
+        if "out" in kwargs:
+            raise NotImplementedError("in-place operations not supported")
+        if method != "__call__":
+            return NotImplemented
+        table = None
+        for x in inputs:
+            if isinstance(x, Table):
+                if table is None:
+                    table = x
+                elif set(table._contents) != set(x._contents):
+                    raise ValueError("Tables have different sets of columns")
+        newcolumns = OrderedDict()
+        for n in table._contents:
+            newcolumns[n] = ufunc(*[x._contents[n] if isinstance(x, Table) else x for x in inputs])
+        if len(newcolumns) == 0:
+            raise AssertionError("ufunc on a Table without columns")
+        if any(ufunc is c for c in _COMPARISONS):
+            out = None
+            for x in newcolumns.values():
+                out = x if out is None else numpy.bitwise_and(out, x)
+            return out
+        if isinstance(next(iter(newcolumns.values())), tuple):
+            raise NotImplementedError("ufuncs with several results on Table content are outside the GPU hot path")
+        out = Table.named(table.rowname)
+        for n, x in newcolumns.items():
+            out._contents[n] = x
+        return out
+
     def __init__(self, columns1=None, *columns2, **columns3):
         self._contents = OrderedDict()
         self.rowname = "Row"

@@ -120,4 +120,18 @@ static inline unsigned persistent_grid(Kernel kernel, int threads, int64_t ntile
     return static_cast<unsigned>(g);
 }
 
+// Launch a persistent kernel whose CTAs wait on each other.  A cooperative launch makes the runtime guarantee what
+// the protocol needs -- every CTA of the grid resident at the same time -- and fail with an error (instead of
+// dead-locking) if the grid does not fit, e.g. when another kernel holds part of the device.
+template <class... Params, class... Args>
+static inline cudaError_t launch_resident(void (*kernel)(Params...), unsigned grid, unsigned threads, cudaStream_t stream,
+                                          Args... args) {
+    static_assert(sizeof...(Params) == sizeof...(Args), "argument count");
+    auto pack = [&](Params... p) {
+        void *ptrs[] = {static_cast<void *>(&p)...};
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3(grid), dim3(threads), ptrs, 0, stream);
+    };
+    return pack(args...);
+}
+
 }  // namespace jg

@@ -573,8 +573,12 @@ int launch_scan_lag(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
     }
     const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    scan_lag_kernel<T, XF, ITEMS, LAG><<<grid, kScanTmaThreads, 0, stream>>>(
-        xf, in_a, in_b, n, out, total, status, lag_carve(ws, ntiles), static_cast<uint32_t>(ntiles), out_aligned);
+    e = launch_resident(scan_lag_kernel<T, XF, ITEMS, LAG>, grid, kScanTmaThreads, stream, xf, in_a, in_b, n, out, total,
+                        status, lag_carve(ws, ntiles), static_cast<uint32_t>(ntiles), out_aligned);
+    if (e != cudaSuccess) {
+        set_error("scan_lag_kernel: %s", cudaGetErrorString(e));
+        return -1;
+    }
     return check_launch("scan_lag_kernel");
 }
 

@@ -362,10 +362,10 @@ mask_select_lag_kernel(const SEL sel, const V *__restrict__ content, const typen
     }
 
     uint32_t it = 0;
+    uint32_t parity = 0;          // of the mbarriers' current phase: flips only in iterations that arm them (a staged tile)
 #pragma unroll 1
     for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G, ++it) {
         const uint32_t tile_index = static_cast<uint32_t>(tile64);
-        const uint32_t parity = it & 1u;
         const int slot_b = it % R, slot_a = (it + LAG) % R, slot_n = (it + LAG + 1) % R;
         // boundaries of the tile LAG + 1 iterations ahead (consumed by the next iteration's phase A)
         int64_t next_bnd = 0;
@@ -474,6 +474,7 @@ mask_select_lag_kernel(const SEL sel, const V *__restrict__ content, const typen
                 new_offsets[n] = base + s_pfx[L];
                 if (total) *total = base + s_pfx[L];
             }
+            if (L > 0) parity ^= 1u;
             __syncthreads();
             continue;
         }
@@ -743,18 +744,22 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
                 resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 2>, kTileThreads, 1ll << 40);
                 if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
             }
-            mask_select_lag_kernel<V, KM, SEL, SAME, 2><<<static_cast<unsigned>(ntiles < resident ? ntiles : resident), kTileThreads, 0, s>>>(
-                sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
-                new_counts, total, lag, static_cast<uint32_t>(ntiles));
+            e = launch_resident(mask_select_lag_kernel<V, KM, SEL, SAME, 2>, static_cast<unsigned>(ntiles < resident ? ntiles : resident),
+                                kTileThreads, s, sel, static_cast<const V *>(content), mask, mask_shift, offsets, n,
+                                static_cast<V *>(out), new_offsets, new_counts, total, lag, static_cast<uint32_t>(ntiles));
         } else {
             static unsigned resident = 0;
             if (resident == 0) {
                 resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 1>, kTileThreads, 1ll << 40);
                 if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
             }
-            mask_select_lag_kernel<V, KM, SEL, SAME, 1><<<static_cast<unsigned>(ntiles < resident ? ntiles : resident), kTileThreads, 0, s>>>(
-                sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
-                new_counts, total, lag, static_cast<uint32_t>(ntiles));
+            e = launch_resident(mask_select_lag_kernel<V, KM, SEL, SAME, 1>, static_cast<unsigned>(ntiles < resident ? ntiles : resident),
+                                kTileThreads, s, sel, static_cast<const V *>(content), mask, mask_shift, offsets, n,
+                                static_cast<V *>(out), new_offsets, new_counts, total, lag, static_cast<uint32_t>(ntiles));
+        }
+        if (e != cudaSuccess) {
+            set_error("mask_select_lag_kernel: %s", cudaGetErrorString(e));
+            return -1;
         }
         return check_launch("mask_select_lag_kernel");
     }

@@ -223,49 +223,73 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    nev = args.events_per_gpu
-    counts_np, pt_np = make_shard(nev, 12345 + rank)
-    M = len(pt_np)
-    # pinned host staging (the e2e leg copies from here every step)
-    counts_pin = torch.empty(nev, dtype=torch.int64, pin_memory=True)
-    counts_pin.numpy()[:] = counts_np
-    pt_pin = torch.empty(M, dtype=torch.float32, pin_memory=True)
-    pt_pin.numpy()[:] = pt_np
-    del counts_np, pt_np
-
-    counts_dev = ak.asdevice(counts_pin)
-    pt_dev = ak.asdevice(pt_pin)
+    binding = bind_host_to_gpu(local_rank)           # before any pinned allocation: first touch on the GPU's NUMA node
+    strong = args.total_events > 0
+    if strong:
+        lo, hi = sharded.event_range(args.total_events, rank, world)     # BASELINE configs[4]: 1 B events over 1/2/4/8 GPUs
+        nev = hi - lo
+    else:
+        nev = args.events_per_gpu
+    device_rng = strong or args.device_rng
+    if device_rng:
+        # drawn in HBM (a 1 B-event shard would be a 28 GB host draw): same distributions, torch's generators
+        g = torch.Generator(device=dev)
+        g.manual_seed(12345 + rank)
+        counts_t = torch.poisson(torch.full((nev,), 5.0, device=dev), generator=g).to(torch.int64)
+        M = int(counts_t.sum())
+        pt_t = torch.empty(M, device=dev, dtype=torch.float32).exponential_(1.0 / 25.0, generator=g)
+        counts_dev, pt_dev = ak.DeviceArray(counts_t), ak.DeviceArray(pt_t)
+        counts_pin = pt_pin = None
+        del counts_t, pt_t
+    else:
+        counts_np, pt_np = make_shard(nev, 12345 + rank)
+        M = len(pt_np)
+        # pinned host staging (the e2e leg copies from here every step)
+        counts_pin = torch.empty(nev, dtype=torch.int64, pin_memory=True)
+        counts_pin.numpy()[:] = counts_np
+        pt_pin = torch.empty(M, dtype=torch.float32, pin_memory=True)
+        pt_pin.numpy()[:] = pt_np
+        del counts_np, pt_np
+        counts_dev = ak.asdevice(counts_pin)
+        pt_dev = ak.asdevice(pt_pin)
     torch.cuda.synchronize()
 
     def sweep(counts, content):
-        """One step through the public API.  Returns the whole-array totals (python numbers)."""
+        """One step through the public API.  Returns the whole-array totals (python numbers).  The partial totals stay in
+        HBM where the kernels wrote them (the sum of sums from jg_flat_reduce, K and the number of leading objects as
+        the last entry of the results' offsets): ONE collective and ONE device-to-host copy per step."""
         a = ak.JaggedArray.fromcounts(counts, content)          # scan (+ total/negative-count read-back)
         s = a.sum()
         lead = a.argmax()
         sel = a[a > THRESHOLD]
         flat = sel.flatten()
         c = sel.counts
-        local_sum = float(s.sum())                               # device reduction, one 8-byte read
-        (gsum, gk, glead), _, _ = sharded.allreduce_totals(sums=[local_sum, float(len(flat)), float(len(lead.content))])
+        acc = sharded.DeviceTotals()
+        acc.add_sum(s.device_sum())
+        acc.add_sum(sel.offsets[-1:])
+        acc.add_sum(lead.offsets[-1:])
+        gsum, gk, glead = acc.finish()
+        assert len(flat) <= gk and len(c) == len(a)
         return gsum, gk, glead, len(c)
 
     def sweep_streamed(counts_host, content_host):
         """The same step from HOST buffers: the copy is queued once on a side stream and the sweep runs event chunk
         by event chunk on views of the resident array while later pieces are still on the bus (ingest.py)."""
         stream = ak.StreamedJaggedArray(counts_host, content_host, nchunks=args.e2e_chunks)   # H2D + scan
-        local_sum, selected, leading, nev = 0.0, 0, 0, 0
+        acc = sharded.DeviceTotals(capacity=3 * max(args.e2e_chunks, 1))
+        nev = 0
         for a in stream:
             s = a.sum()
             lead = a.argmax()
             sel = a[a > THRESHOLD]
             flat = sel.flatten()
             c = sel.counts
-            local_sum += float(s.sum())
-            selected += len(flat)
-            leading += len(lead.content)
+            acc.add_sum(s.device_sum())
+            acc.add_sum(sel.offsets[-1:])
+            acc.add_sum(lead.offsets[-1:])
             nev += len(c)
-        (gsum, gk, glead), _, _ = sharded.allreduce_totals(sums=[local_sum, float(selected), float(leading)])
-        return gsum, gk, glead, nev
+        parts = acc.finish()
+        return sum(parts[0::3]), sum(parts[1::3]), sum(parts[2::3]), nev
 
     def barrier():
         if world > 1:
@@ -289,6 +313,22 @@ def run_gpu(args):
         barrier()
         return ms, out
 
+    # ---- parity of the very step that is timed, at every N: every rank sweeps the same fixed 1 M-event shard through
+    # the same code path (collective included) and the totals must equal the CPU arm's (reference / oracle) x world
+    check_counts, check_pt = make_shard(1_000_000, 4242)
+    _, (want_sum, want_k, want_lead, _) = cpu_sweep(check_counts, check_pt)
+    got_sum, got_k, got_lead, got_n = sweep(ak.asdevice(check_counts), ak.asdevice(check_pt))
+    totals_ok = (abs(got_sum - world * want_sum) <= 1e-5 * world * abs(want_sum) and got_k == world * want_k
+                 and got_lead == world * want_lead and got_n == len(check_counts))
+    if world > 1:
+        flag = torch.tensor([1 if totals_ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        totals_ok = bool(flag.item())
+    if not totals_ok:
+        raise SystemExit("totals_check FAILED on rank %d: got %r, want %r x %d" % (
+            rank, (got_sum, got_k, got_lead), (want_sum, want_k, want_lead), world))
+    del check_counts, check_pt
+
     # ---- warm-up, then the device-resident timed region
     for _ in range(max(args.warmup, 3)):
         totals = sweep(counts_dev, pt_dev)
@@ -300,18 +340,58 @@ def run_gpu(args):
     launches = _lib.LAUNCHES[0]
 
     # ---- e2e: pinned host -> device inside the timed region, totals read back
-    e2e_step = (lambda: sweep_streamed(counts_pin, pt_pin)) if args.e2e_chunks > 0 else (lambda: sweep(counts_pin, pt_pin))
-    for _ in range(1):
-        e2e_step()
-    ms_e2e, totals_e2e = timed(e2e_step, args.steps)
+    ms_e2e, h2d = None, None
+    if counts_pin is not None:
+        e2e_step = (lambda: sweep_streamed(counts_pin, pt_pin)) if args.e2e_chunks > 0 else (lambda: sweep(counts_pin, pt_pin))
+        for _ in range(1):
+            e2e_step()
+        ms_e2e, totals_e2e = timed(e2e_step, args.steps)
+        assert totals_e2e[1] == totals[1] and totals_e2e[2] == totals[2], (totals_e2e, totals)
+        # the ceiling of that leg: the same bytes copied from the same pinned buffers with NO compute, all ranks at once
+        stage_c, stage_p = torch.empty_like(counts_dev.tensor), torch.empty_like(pt_dev.tensor)
+
+        def copy_only():
+            stage_c.copy_(counts_pin, non_blocking=True)
+            stage_p.copy_(pt_pin, non_blocking=True)
+        copy_only()
+        ms_copy, _ = timed(copy_only, max(2, args.steps // 4))
+        ms_copy /= max(2, args.steps // 4)
+        mine = torch.tensor([(nev * 8 + M * 4) / (ms_copy * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        every = torch.empty(world, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(every, mine)
+        else:
+            every = mine
+        h2d = {"copy_only_ms": ms_copy, "gbs_per_rank": [round(float(x), 2) for x in every.cpu().tolist()]}
+        del stage_c, stage_p
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- result gather over NVLink: the per-event sums of every shard replicated on every rank
+    gather_row = None
+    if world > 1:
+        a_full = ak.JaggedArray.fromcounts(counts_dev, pt_dev)
+        per_event = a_full.sum()
+        sizes = [sharded.event_range(args.total_events, r, world)[1] - sharded.event_range(args.total_events, r, world)[0]
+                 for r in range(world)] if strong else [nev] * world
+        sharded.gather_per_event(per_event, sizes=sizes)
+        ms_g, gathered = timed(lambda: sharded.gather_per_event(per_event, sizes=sizes), 5)
+        ms_g /= 5
+        recv = (sum(sizes) - nev) * 4
+        gather_row = {"ms": ms_g, "bytes_received_per_rank": recv, "gbs_per_rank": recv / (ms_g * 1e-3) / 1e9,
+                      "elements": sum(sizes), "collective": "ncclAllGather (all_gather_into_tensor, one call, no staging copy)"}
+        assert gathered.numel() == sum(sizes)
+        del a_full, per_event, gathered
 
     Mt = torch.tensor([M], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(Mt)
     M_all = float(Mt.item())
     value = M_all * args.steps / (ms_dev * 1e-3)
-    e2e_value = M_all * args.steps / (ms_e2e * 1e-3)
+    e2e_value = M_all * args.steps / (ms_e2e * 1e-3) if ms_e2e else None
+    Nt = torch.tensor([nev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(Nt)
+    N_all = int(Nt.item())
 
     # ---- per-kernel roofline table (rank 0, device-resident, CUDA events around each C-ABI call)
     ops = {}
@@ -337,6 +417,7 @@ def run_gpu(args):
     workflows = {}
     if rank == 0 and not args.no_tables:
         workflows = workflow_table(ak, counts_dev, pt_dev, nev, M, args)
+        ops.update(distribution_table(ak, args))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -354,27 +435,66 @@ def run_gpu(args):
         line = {
             "metric": "jagged elements/sec (offsets scan + sum + argmax + mask sweep)", "value": value,
             "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "events_per_gpu": nev, "content_elements_per_gpu": M,
-                       "threshold": THRESHOLD, "l2": "inputs (3.5 GB/GPU) are larger than L2; no flush needed",
-                       "parallelism": "event-range shards, %d rank(s)" % world},
-            "e2e": {"value": e2e_value, "unit": "elements/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(nev * 8 + M * 4), # 64-byte status/total words: scan + per chunk (argmax, mask select, sum of sums); + the chunk boundaries
-                    "d2h_bytes_per_step": (64 + max(args.e2e_chunks, 1) * 3 * 64 + (max(args.e2e_chunks, 1) + 1) * 8) if args.e2e_chunks > 0 else 5 * 64,
-                    "note": ("public API from pinned host buffers (StreamedJaggedArray: ONE copy of counts + content per step on a side stream, "
-                             "the sweep runs on %d event-range views while later pieces are still on the bus); results stay in HBM, "
-                             "totals are read back" % args.e2e_chunks) if args.e2e_chunks > 0 else
-                            "public API from pinned host buffers (copy, then compute); results stay in HBM, totals are read back"},
+                       "total_events": N_all, "total_content_elements": int(M_all),
+                       "threshold": THRESHOLD, "l2": "inputs (%.1f GB/GPU) are larger than L2; no flush needed" % ((nev * 8 + M * 4) / 1e9),
+                       "rng": "torch generators on the device" if device_rng else "numpy default_rng(12345 + rank) on the host (SURVEY 8d)",
+                       "parallelism": "event-range shards, %d rank(s)" % world, "host_binding": binding},
+            "e2e": ({"value": e2e_value, "unit": "elements/s", "ms_per_step": ms_e2e / args.steps,
+                     "h2d_bytes_per_step": int(nev * 8 + M * 4),
+                     # the scan's 64-byte status / total word, per chunk those of argmax and the selection, the chunk
+                     # boundaries, and ONE buffer with every partial total (3 x 8 bytes per chunk)
+                     "d2h_bytes_per_step": (64 + max(args.e2e_chunks, 1) * (2 * 64 + 24) + (max(args.e2e_chunks, 1) + 1) * 8) if args.e2e_chunks > 0 else 3 * 64 + 24,
+                     "h2d": h2d,
+                     "note": ("public API from pinned host buffers (StreamedJaggedArray: ONE copy of counts + content per step on a side stream, "
+                              "the sweep runs on %d event-range views while later pieces are still on the bus); per-event results stay in "
+                              "HBM (none returns to the host inside the timed region), only the whole-array totals are read back; "
+                              "h2d.copy_only_ms is the same copy with no compute, all ranks at once: the ceiling of this leg"
+                              % args.e2e_chunks) if args.e2e_chunks > 0 else
+                             "public API from pinned host buffers (copy, then compute); results stay in HBM, totals are read back"}
+                    if ms_e2e else
+                    {"value": None, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                     "note": "not measured in this mode: the shard is drawn in HBM (no host copy of it exists)"}),
             "gpu_launches": launches,
             "clocks": clocks,
             "totals": {"sum": totals[0], "selected": totals[1], "leading": totals[2]},
+            "totals_check": totals_ok,
+            "nccl_gather_per_event_f32": gather_row,
             "roofline": roof, "cpu_baseline": cpu, "ops": ops, "workflows": workflows,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bind_host_to_gpu(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host memory is allocated, so
+    that the staging buffers are first touched on the GPU's NUMA node (at 8 ranks the host-to-device copies of ranks
+    whose buffers sit on the far socket fall to a fraction of PCIe line rate).  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        numa = None
+        try:
+            numa = int(open("/sys/bus/pci/devices/%s/numa_node" % pynvml.nvmlDeviceGetPciInfo(h).busId.decode().lower()[4:]).read())
+        except Exception:
+            pass
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return {"bound": True, "cpus": len(cpus), "of": len(allowed), "numa_node": numa}
+        return {"bound": False, "cpus": len(allowed), "numa_node": numa,
+                "why": "NVML reports every allowed CPU as local to the GPU (no NUMA topology visible in this VM)"}
+    except Exception as err:                                   # pragma: no cover
+        return {"bound": False, "why": "%s: %s" % (type(err).__name__, err)}
 
 
 def load_peaks():
@@ -549,6 +669,21 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
         add("arg" + name + "_fill", nin + 8 * Nc + 16 * P, P, lambda: _lib.call(
             "jg_comb_fill", kind, 2, mu_off.data_ptr(), obp, Nc, _vp(poff), arr, 0, st()))
         del c0, c1
+        if kind == _lib.COMB_PAIRS:
+            # argchoose(k), k = 2..5 (jagged.py:1128-1221): colexicographic k-combinations, k index columns.  Counted on
+            # a Poisson(5) shard: Poisson(2) events hold almost no 4- or 5-combinations
+            Nk = min(N, 20_000_000)
+            for kk in (2, 3, 4, 5):
+                koff = empty(Nk + 1, np.int64)
+                add("comb_offsets_choose_k%d" % kk, 16 * Nk, Nk, lambda: _lib.call(
+                    "jg_comb_offsets", _lib.COMB_CHOOSE, kk, off.data_ptr(), ctypes.c_void_p(0), Nk, _vp(koff), _vp(scal), wsc, wscb, st()))
+                Pk = int(scal.cpu()[0])
+                kcols = [empty(Pk, np.int64) for _ in range(kk)]
+                karr = (ctypes.c_void_p * kk)(*[c.data_ptr() for c in kcols])
+                add("argchoose_k%d_fill" % kk, 16 * Nk + 8 * kk * Pk, Pk, lambda: _lib.call(
+                    "jg_comb_fill", _lib.COMB_CHOOSE, kk, off.data_ptr(), ctypes.c_void_p(0), Nk, _vp(koff), karr, 0, st()))
+                table["argchoose_k%d_fill" % kk]["combinations"] = Pk
+                del kcols, koff
         l, r = empty(P, np.float32), empty(P, np.float32)
         cb = el_pt if ob is not None else mu_pt
         add(name + "_values_f32", nin + 8 * Nc + 4 * Mmu + (4 * Mel if ob is not None else 0) + 8 * P, P, lambda: _lib.call(
@@ -571,6 +706,64 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
             table[name + "_mass_fused_f32"]["note"] = "issue-bound (14-step program incl. cosh, cos, sqrt per pair), not HBM-bound"
             del mass_out
     return table
+
+
+def distribution_table(ak, args):
+    """north_star: "variants chosen by count distribution".  The same four hot-path operations -- sum, argmax, a[a > 20],
+    parents -- through the public API on count distributions other than the Poisson(5) the sweep is quoted on: long
+    events (Poisson(40)), a heavy tail (geometric, mean 4, plus events of 5 k - 70 k elements) and a few huge events
+    (1000 events x 1 M elements).  CUDA events around the call, host synchronisations included; algorithmic bytes as
+    in SURVEY 8d."""
+    import torch
+    peak = load_peaks()[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    out = {}
+
+    def shapes():
+        n = args.dist_elements // 40
+        yield "poisson40", torch.poisson(torch.full((n,), 40.0, device=dev), generator=g).to(torch.int64)
+        n = args.dist_elements // 4
+        c = torch.empty(n, device=dev, dtype=torch.float32).geometric_(0.2, generator=g).to(torch.int64) - 1
+        where = torch.randint(0, n, (1000,), device=dev, generator=g)
+        c[where] = torch.randint(5000, 70000, (1000,), device=dev, generator=g)
+        yield "geometric_tail", c
+        yield "huge_1k_x_1M", torch.full((1000,), max(1, args.dist_elements // 1000), device=dev, dtype=torch.int64)
+
+    for name, counts_t in shapes():
+        N = int(counts_t.numel())
+        M = int(counts_t.sum())
+        pt_t = torch.empty(M, device=dev, dtype=torch.float32).exponential_(1.0 / 25.0, generator=g)
+        a = ak.JaggedArray.fromcounts(ak.DeviceArray(counts_t), ak.DeviceArray(pt_t))
+        off = a.offsets
+        K = len(a[a > THRESHOLD].content)
+        npos = int((counts_t > 0).sum())
+        rows = (("segreduce_sum_f32", 4 * M + 8 * N + 4 * N, lambda: a.sum()),
+                ("segargmax_dense_f32", 4 * M + 8 * N + 8 * N + 8 * npos, lambda: a.argmax()),
+                ("compare_select_f32", 4 * M + 8 * N + 4 * K + 16 * N, lambda: a[a > THRESHOLD]),
+                ("offsets2parents", 8 * N + 8 * M, lambda: ak.JaggedArray.offsets2parents(off)))
+        for op, nbytes, fn in rows:
+            r = fn()
+            del r
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.kernel_reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+                del r
+            ms = float(np.mean(ts))
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out["%s_%s" % (name, op)] = {"ms": ms, "best_ms": float(min(ts)), "bytes": int(nbytes), "gbs": gbs, "frac": gbs / peak,
+                                         "elements_per_s": M / (ms * 1e-3), "events": N, "elements": M,
+                                         "max_count": int(counts_t.max())}
+        del a, off, pt_t, counts_t
+        torch.cuda.empty_cache()
+    return out
 
 
 def workflow_table(ak, counts_dev, pt_dev, N, M, args):
@@ -798,6 +991,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--total-events", type=float, default=0,
+                    help="STRONG scaling: this many events in total, split over the ranks (BASELINE configs[4]: 1e9); the "
+                         "shards are drawn on the device and the e2e leg is skipped")
+    ap.add_argument("--device-rng", action="store_true", help="draw the weak-scaling shard on the device as well")
     ap.add_argument("--comb-events", type=int, default=50_000_000)
     ap.add_argument("--cpu-events", type=int, default=4_000_000)
     ap.add_argument("--ref-events-per-core", type=int, default=1_000_000)
@@ -805,12 +1002,15 @@ def main():
                     help="events of the CPU sample behind every workflow's cpu_ms (C1 runs at its full size)")
     ap.add_argument("--cpu-comb-events", type=int, default=1_000_000)
     ap.add_argument("--kernel-reps", type=int, default=5)
+    ap.add_argument("--dist-elements", type=int, default=600_000_000,
+                    help="content elements of each shard of the count-distribution table (Poisson(40), heavy tail, huge events)")
     ap.add_argument("--e2e-chunks", type=int, default=8,
                     help="event chunks of the streamed host->HBM ingest used by the e2e leg (0: copy everything, then compute)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tables", action="store_true",
                     help="skip the per-kernel roofline table and the API workflow table (scaling runs: only the sweep is wanted)")
     args = ap.parse_args()
+    args.total_events = int(args.total_events)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -197,6 +197,34 @@ int jg_put(void *content, int itemsize, const int64_t *index, int64_t n, const v
 /* plain gather out[k] = content[index[k]] (jagged.py:1294 content[left]); no bounds check beyond content_len      */
 int jg_take(const void *content, int itemsize, const int64_t *index, int64_t n_index, void *out, void *stream);
 
+/* ---- element-tiled variants for long events ------------------------------------------------------------------------
+ * jagged.py:1552-1563 (the per-event reduceat loop) and its siblings when the COUNT DISTRIBUTION has long events:
+ * the host calls these instead of the event-tiled entry points above when content_len > 7 * n (north_star: "variants
+ * chosen by count distribution").  Work is split into tiles of 16 KB of content instead of 512 events, so Poisson(40)
+ * counts, heavy tails and a single event of 2^31 elements all keep every SM busy; an event that spans several tiles
+ * is merged by a second, tiny launch.  Results are identical to the event-tiled calls (float sum / prod within the
+ * reduction-order tolerance).  `content_len` = offsets[n] - offsets[0]; `ws` holds jg_elem_workspace_bytes bytes.     */
+size_t jg_elem_workspace_bytes(int64_t content_len, int itemsize);
+/* jagged.py:1459-1565: as jg_segreduce; dtype in {JG_F32, JG_F64, JG_I32, JG_I64}                                      */
+int jg_segreduce_elem(const void *content, int dtype, const int64_t *offsets, int64_t n, int op, void *out,
+                      int64_t content_len, void *ws, size_t ws_bytes, void *stream);
+/* jagged.py:1567-1601: as jg_segargminmax (best[] and best_value[] both required); jg_compact_nonneg makes it dense  */
+int jg_segargminmax_elem(const void *content, int dtype, const int64_t *offsets, int64_t n, int is_min, int64_t *best,
+                         void *best_value, int64_t content_len, void *ws, size_t ws_bytes, void *stream);
+/* jagged.py:562-589: as jg_mask_select / jg_compare_select for 4- and 8-byte items: ONE persistent launch (flat stream
+ * compaction on lagged tile prefixes; an event reads its new offset from the on-chip prefix of the tile it starts in) */
+int jg_mask_select_elem(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift, const int64_t *offsets,
+                        int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts, int64_t *total,
+                        int64_t content_len, void *ws, size_t ws_bytes, void *stream);
+int jg_compare_select_elem(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                           int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                           int64_t *new_counts, int64_t *total, int64_t content_len, void *ws, size_t ws_bytes,
+                           void *stream);
+/* jagged.py:49-54, 430-443, 840-881: mode 0 = offsets2parents (int64 out, absolute positions, -1 below offsets[0]),
+ * 1 = localindex (int64 out), 2 = broadcast of flat[n] (`itemsize` bytes per item) onto the content positions         */
+int jg_expand_elem(int mode, const void *flat, int itemsize, const int64_t *offsets, int64_t n, void *out,
+                   int64_t content_len, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- per-event argsort ------------------------------------------------------------------ */
 /* jagged.py:1603-1631  out[offsets[i]-offsets[0] + r] = local index of the element of event i with rank r: stable
  * by value (descending unless `ascending`), ties and -0.0/0.0 in position order, NaN last in both directions.

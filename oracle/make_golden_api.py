@@ -145,6 +145,18 @@ CASES = [
     "rec.istuple", "a.rowname", "a.istuple", "deep.rowname", "J.zip(x, x, x, x, x, x, x, x, x, x).i5", "J.zip(x, x, x, x, x, x, x, x, x, x).i9 + J.zip(x, x, x, x, x, x * 3).i5",
     "x.cross(y).i5", "A.concatenate([a, b])", "A.concatenate([x, y, z], axis=1)", "A.concatenate([])", "a.concatenate([])", "a.concatenate([], axis=1)", "J.concatenate([a])", "J.concatenate([a], axis=1)", "A.fromiter([[1, 2], [], [3]])", "A.fromiter([[1.5], [2.5, 3.5]]).sum()",
     "J.fromcounts([1.0, 2.0], [1, 2, 3])", "J.fromoffsets([0.0, 1.0], [1])", "J([[0]], [[1]], [1, 2]).tolist()", "J.fromcounts([[1, 2]], [1, 2, 3])",
+    # round 2 (SURVEY 8f-2 finished): ufuncs on records column by column (table.py:668-738), chained nested cross
+    # (jagged.py:1342-1365), integer jagged indexes that pick whole inner events (jagged.py:541-560 one level down)
+    "rec + 1", "rec * 2.5", "rec + rec", "rec > 2", "rec == rec", "rec + flat", "np.sqrt(rec).pt", "-rec", "np.abs(rec).q", "rec + a", "a + rec",
+    "rec < a", "(rec + 1).q", "(rec + 1).rowname", "(x.cross(y) * 2).i1", "x.cross(y) + 1", "rec + J.zip(pt=a, z=i)", "np.add(rec, 1, out=rec)",
+    "recg * 2", "(rec[rec.pt > 2] + 1).q", "rec[rec > 2].pt", "(rec - rec.max()).pt", "np.maximum(rec, 2).q", "(rec.pairs().i0 + rec.pairs().i1).pt",
+    "x.cross(y, nested=True).cross(z, nested=True)", "x.cross(y, nested=True).cross(z)", "x.cross(y, nested=True).cross(z, nested=True).i2",
+    "x.cross(y, nested=True).cross(z).i0", "x.cross(y, nested=True).cross(z, nested=True).counts", "x.cross(y, nested=True).cross(z, nested=True).i0.sum()",
+    "rec.cross(rec, nested=True).cross(rec, nested=True).i2.q", "x.cross(y, nested=True).cross(z, nested=True).flatten(axis=1).counts",
+    "x.cross(y).cross(z, nested=True)", "x.cross(y, nested=True).cross(z).i2.max()",
+    "deep[J.fromiter([[0, 1], [], [0]])]", "deep[J.fromiter([[-1], [], [1, 1, 0]])]", "deep[J.fromiter([[2], [], []])]", "deep[J.fromiter([[0], [0], []])]",
+    "d2[J.fromiter([[0], [1, 0]])]", "deepg[J.fromiter([[1], [0, 0]])]", "deep[J.fromiter([[0, 1], [], [0]])].sum()", "deep[J.fromiter([[1.5], [], []])]",
+    "deep[J.fromiter([[0, 1], []])]",
 ]
 
 # (not in the battery: `deepg[deepg > 2]` -- a mask over a doubly jagged array in general layout; the reference raises

@@ -461,3 +461,79 @@ def test_c4_slice_against_the_oracle(ak):
         floor = np.sqrt(2 * l64["pt"] * r64["pt"] * 8 * eps * np.cosh(2 * 2.4))
         assert got.dtype == np.float32 and got.shape == ref.shape
         assert np.all(np.abs(got.astype(np.float64) - ref) <= 1e-5 * np.abs(ref) + floor), kind
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# count distributions with LONG events: the element-tiled variants (csrc/jg_elem.cu) against the oracle
+# ----------------------------------------------------------------------------------------------------------------
+def long_counts(kind, rng):
+    if kind == "poisson40":
+        return rng.poisson(40.0, 30000).astype(np.int64)
+    if kind == "uniform3000":                     # events of 0 .. 3000 elements: thread, warp and CTA segments mixed
+        return rng.integers(0, 3000, 700).astype(np.int64)
+    if kind == "huge":                            # a few events of 1e5 .. 3e5 elements between empty ones: many tiles per event
+        c = np.zeros(40, dtype=np.int64)
+        c[rng.choice(40, 7, replace=False)] = rng.integers(100000, 300000, 7)
+        return c
+    if kind == "tile_edges":                      # events that end exactly on 4096- / 2048-element tile boundaries, empties there
+        return np.array([4096, 0, 0, 2048, 2048, 0, 8192, 1, 4095, 0, 4096 * 3, 0, 0], dtype=np.int64)
+    if kind == "one_event":
+        return np.array([1 << 20], dtype=np.int64)
+    if kind == "sparse_long":                     # 99 % empty events and a few long ones: tiles that own thousands of events
+        c = np.zeros(200000, dtype=np.int64)
+        c[rng.choice(200000, 2000, replace=False)] = rng.integers(500, 3000, 2000)
+        return c
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("kind", ["poisson40", "uniform3000", "huge", "tile_edges", "one_event", "sparse_long"])
+def test_long_event_variants(ak, kind, dtype):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32((kind + np.dtype(dtype).name).encode()))
+    counts = long_counts(kind, rng)
+    m = int(counts.sum())
+    assert m > 7 * len(counts)                    # the host picks the element-tiled kernels
+    if np.dtype(dtype).kind == "f":
+        content = rng.exponential(25.0, m).astype(dtype)
+        content[rng.random(m) < 0.001] = np.nan
+        content[rng.random(m) < 0.001] = -0.0
+    else:
+        content = rng.integers(-1000, 1000, m).astype(dtype)
+    off = O.counts2offsets(counts)
+    for shift in (0, 3):                          # a dense array, and a view that starts at event 3 (offsets[0] != 0)
+        if shift >= len(counts):
+            continue
+        a = ak.JaggedArray.fromcounts(counts, content)
+        o = off
+        if shift:
+            a, o = a[shift:], off[shift:]
+        assert same(a.parents.get(), O.offsets2parents(o))
+        assert same(a.localindex.content.get(), O.localindex(o)[1])
+        with np.errstate(all="ignore"):
+            for op in ("min", "max", "any", "all"):
+                assert same(getattr(a, op)().get(), O.reduce(o, content, op)), (kind, op)
+            for op in ("sum", "prod"):
+                got, want = getattr(a, op)().get(), O.reduce(o, content, op)
+                assert got.dtype == want.dtype
+                if want.dtype.kind == "f":
+                    ok = reduce_close(op, got, want, o, content, RTOL[want.dtype])
+                    assert ok.all(), (kind, op, got[~ok][:5], want[~ok][:5])
+                else:
+                    assert same(got, want), (kind, op)
+            for ismin in (True, False):
+                roff, ridx = O.argminmax(o, content, ismin)
+                r = a.argmin() if ismin else a.argmax()
+                assert same(r.offsets.get(), roff) and same(r.content.get(), ridx), (kind, ismin)
+        thr = 20 if np.dtype(dtype).kind == "f" else 0
+        moff, mask = O.ufunc_broadcast(np.greater, o, content, thr)
+        soff, sel = O.mask_select(o, content, moff, mask)
+        for gs in (a[a > thr], a[ak.JaggedArray.fromoffsets(o - o[0], mask)]):       # fused comparison (floats) and byte mask
+            assert same(gs.offsets.get(), soff) and same(gs.content.get(), sel), kind
+            assert same(gs.counts.get(), O.offsets2counts(soff)), kind
+        flat = rng.normal(size=len(o) - 1).astype(dtype if np.dtype(dtype).kind == "f" else np.float64)
+        assert same(a.tojagged(flat).content.get(), O.tojagged_flat(o, flat))
+        lead = a[a.argmax()]
+        roff, ridx = O.argminmax(o, content, False)
+        goff, gval = O.index_gather(o, content, roff, ridx)
+        assert same(lead.offsets.get(), goff) and same(lead.content.get(), gval)
