@@ -1213,13 +1213,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             op, scalar = _lib.OP[mask._op], mask._scalar
 
         long_events = self._long_events(n, last - first)
-        if long_events:
-            ews, ewsb = runtime.elem_workspace(last - first, 4)
 
         def select(col):
             out = empty(last - first, col.dtype)
             counts_ptr = _vp(new_counts) if not columns else ctypes.c_void_p(0)
             if long_events and col.itemsize in (4, 8) and (not fused or same or key.itemsize == col.itemsize):
+                ews, ewsb = runtime.elem_workspace(last - first, col.itemsize)
                 # long events: flat compaction of 16 KB content tiles (one persistent launch) + rank at event boundaries
                 if fused:
                     call("jg_compare_select_elem", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
@@ -1348,6 +1347,10 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                     flat_ops.append(b._dense_content())
                 elif _ufunc.is_scalar(x):
                     flat_ops.append(x)
+                elif isinstance(x, Table):                 # one record per event (rec.max(), ...): broadcast column by column
+                    if len(x) != n:
+                        raise ValueError("cannot broadcast JaggedArray of shape {0} with array of shape {1}".format((n,), (len(x),)))
+                    flat_ops.append(x.map(lambda c: a.tojagged(c)._content))
                 else:
                     flat = asdevice(x) if not isinstance(x, DeviceArray) else x
                     if flat.shape != (n,):

@@ -31,6 +31,8 @@ class Table(numpy.lib.mixins.NDArrayOperatorsMixin):
             raise NotImplementedError("in-place operations not supported")
         if method != "__call__":
             return NotImplemented
+        if any(type(x).__name__ == "JaggedArray" for x in inputs):
+            return NotImplemented                 # the jagged operand flattens first (jagged.py:1039-1051), then comes here
         table = None
         for x in inputs:
             if isinstance(x, Table):

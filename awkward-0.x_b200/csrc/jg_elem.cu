@@ -28,6 +28,7 @@
 
 #include <type_traits>
 
+#include "jg_compact.cuh"
 #include "jg_lag.cuh"
 #include "jg_reduce.cuh"
 #include "jg_tile.cuh"
@@ -525,153 +526,123 @@ __device__ __forceinline__ int elem_count16(const SEL &sel, int4 v) {
     }
 }
 
-template <typename V, class SEL, bool SAME, int LAG>
+constexpr int kElemSelectWindow = 2048;      // tiles per window: ~32 MB between a tile's two reads
+
+template <typename V, class SEL, bool SAME>
 __global__ void __launch_bounds__(kElemThreads, 5)
 select_elem_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                    int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n,
                    const int64_t *__restrict__ first_event, V *__restrict__ out, int64_t *__restrict__ new_offsets,
-                   int64_t *__restrict__ new_counts, int64_t *__restrict__ total, LagDesc lag, uint32_t ntiles) {
+                   int64_t *__restrict__ new_counts, int64_t *__restrict__ total, LagDesc lag, const LagSchedule sched) {
     using E = typename SEL::Elem;
     constexpr int ET = ElemTile<V>::ET;
     constexpr int PERV = 16 / static_cast<int>(sizeof(E));
-    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32];
+    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32 + 512];      // (+ one row of slack)
     __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : ET * sizeof(E) + 32];
-    __shared__ uint16_t s_pfx[ET + 2];
+    __shared__ __align__(16) uint16_t s_pfx_raw[ET + 8 + 128];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[kElemWarps + 1];
-    __shared__ unsigned long long s_acc;
     __shared__ int64_t s_base;
+    __shared__ uint32_t s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t G = gridDim.x;
+    const uint32_t ntiles = sched.ntiles;
+    uint32_t tile, tile_end;
+    const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile, tile_end);
+    if (role < 0) return;
     const int64_t o0 = __ldg(offsets), end = __ldg(offsets + n);
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        s_acc = 0ull;
-    }
-    __syncthreads();
 
-    auto tile_range = [&](uint64_t t, int64_t &lo, int &len) {
-        lo = o0 + static_cast<int64_t>(t) * ET;
+    if (role == 0) {
+        // ---------------- count: one warp per tile (16-byte loads; the run stays in L2) ---------------------------
+        const uint32_t t = tile + warp;
+        if (t >= tile_end) return;
+        const int64_t lo = o0 + static_cast<int64_t>(t) * ET;
         const int64_t hi = lo + ET < end ? lo + ET : end;
-        len = hi > lo ? static_cast<int>(hi - lo) : 0;
-    };
-    // phase A: selected positions of tile ta (16-byte loads; the run stays in L2 for phase B)
-    auto phase_a = [&](uint64_t ta) {
-        int64_t lo;
-        int len;
-        tile_range(ta, lo, len);
+        const int L = hi > lo ? static_cast<int>(hi - lo) : 0;
         const E *m = mask + lo + mask_shift;
         int cnt = 0;
         const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
         int head = static_cast<int>(((16 - (addr & 15)) & 15) / sizeof(E));
-        if (head > len) head = len;
-        if (tid < head) cnt += sel.test(m[tid]);
-        const int nvec = (len - head) / PERV;
+        if (head > L) head = L;
+        if (lane < head) cnt += sel.test(m[lane]);
+        const int nvec = (L - head) / PERV;
         const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-#pragma unroll 2
-        for (int i = tid; i < nvec; i += kElemThreads) cnt += elem_count16(sel, __ldg(mv + i));
+#pragma unroll 4
+        for (int i = lane; i < nvec; i += kWarp) cnt += elem_count16(sel, __ldg(mv + i));
         const int tail0 = head + nvec * PERV;
-        if (tail0 + tid < len) cnt += sel.test(m[tail0 + tid]);
+        if (tail0 + lane < L) cnt += sel.test(m[tail0 + lane]);
         cnt = warp_reduce_add(cnt);
-        if (lane == 0 && cnt) atomicAdd(&s_acc, static_cast<unsigned long long>(cnt));
-    };
-#pragma unroll 1
-    for (int j = 0; j < LAG; ++j) {
-        const uint64_t ta = blockIdx.x + static_cast<uint64_t>(j) * G;
-        if (ta < ntiles) phase_a(ta);
-        __syncthreads();
-        if (tid == 0 && ta < ntiles) {
-            lag_publish(lag, static_cast<uint32_t>(ta), static_cast<int64_t>(s_acc));
-            s_acc = 0ull;
-        }
-        __syncthreads();
+        if (lane == 0) lag_publish(lag, t, cnt);
+        return;
     }
+    const int64_t lo = o0 + static_cast<int64_t>(tile) * ET;
+    const int64_t hi = lo + ET < end ? lo + ET : end;
+    const int L = hi > lo ? static_cast<int>(hi - lo) : 0;
 
-    uint32_t parity = 0;
-#pragma unroll 1
-    for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G) {
-        const uint32_t tile = static_cast<uint32_t>(tile64);
-        int64_t lo;
-        int L;
-        tile_range(tile64, lo, L);
-        if (tid == 0 && L > 0) {
-            fence_proxy_async_smem();
+    // ---------------- fill ----------------------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        if (L > 0) {
             if (!SAME) stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(mask + lo + mask_shift), static_cast<uint32_t>(L * sizeof(E)), &s_bar[1]);
             stage_bulk(s_content, reinterpret_cast<const unsigned char *>(content + lo), static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
         }
-        const int64_t ev_lo = __ldg(first_event + tile), ev_hi = __ldg(first_event + tile + 1);
-        const uint64_t ta = tile64 + static_cast<uint64_t>(LAG) * G;
-        if (ta < ntiles) phase_a(ta);
-        __syncthreads();
-        if (tid == 0 && ta < ntiles) {
-            lag_publish(lag, static_cast<uint32_t>(ta), static_cast<int64_t>(s_acc));
-            s_acc = 0ull;
+    }
+    const int64_t ev_lo = __ldg(first_event + tile), ev_hi = __ldg(first_event + tile + 1);
+    if (warp == kElemWarps - 1) {
+        const int64_t b = lag_prefix(lag, tile);
+        if (lane == 0) s_base = b;
+    }
+    __syncthreads();
+    const V *cv = nullptr;
+    const E *mv = nullptr;
+    if (L > 0) {
+        const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + lo), static_cast<uint32_t>(L * sizeof(V)));
+        cv = reinterpret_cast<const V *>(s_content + cs);
+        if (SAME) {
+            mbar_wait(&s_bar[0], 0);
+            mv = reinterpret_cast<const E *>(cv);
+        } else {
+            const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + lo + mask_shift), static_cast<uint32_t>(L * sizeof(E)));
+            mbar_wait(&s_bar[1], 0);
+            mv = reinterpret_cast<const E *>(s_mask + ms);
         }
-        if (warp == kElemWarps - 1) {
-            const int64_t b = lag_prefix(lag, tile);
-            if (lane == 0) s_base = b;
-        }
-        const V *cv = nullptr;
-        const E *mv = nullptr;
-        if (L > 0) {
-            const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + lo), static_cast<uint32_t>(L * sizeof(V)));
-            cv = reinterpret_cast<const V *>(s_content + cs);
-            if (SAME) {
-                mbar_wait(&s_bar[0], parity);
-                mv = reinterpret_cast<const E *>(cv);
-            } else {
-                const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + lo + mask_shift), static_cast<uint32_t>(L * sizeof(E)));
-                mbar_wait(&s_bar[1], parity);
-                mv = reinterpret_cast<const E *>(s_mask + ms);
-            }
-        }
-        __syncthreads();
-        const int rows_total = (L + 31) >> 5;
-        const int rows_per_warp = (rows_total + kElemWarps - 1) / kElemWarps;
-        const int p_begin = min(L, warp * rows_per_warp * 32);
-        const int p_end = min(L, p_begin + rows_per_warp * 32);
-        int cnt = 0;
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-        cnt = warp_reduce_add(cnt);
-        if (lane == 0) s_scan[warp] = cnt;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < kElemWarps ? s_scan[lane] : 0;
-            int wi = warp_incl_scan_add(w, lane);
-            if (lane < kElemWarps) s_scan[lane] = wi - w;
-            if (lane == kElemWarps - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-        }
-        if (!SAME && L > 0) mbar_wait(&s_bar[0], parity);
-        __syncthreads();
-        const int64_t base = s_base;
-        int run = s_scan[warp];
-        V *dst = out + base;
-        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-            const int p = p0 + lane;
-            const bool on = p < p_end && sel.test(mv[p]);
-            const unsigned bal = __ballot_sync(0xffffffffu, on);
-            const int slot = run + __popc(bal & ((1u << lane) - 1u));
-            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-            if (on) dst[slot] = cv[p];
-            run += __popc(bal);
-        }
-        __syncthreads();
-        // owned events read their new offset from the per-position prefix; an event that ends inside the tile its count too
+    }
+    __syncthreads();
+    // 16-byte rows (jg_compact.cuh): positions are counted from the 16-byte boundary below the first element
+    constexpr int ROW = RowCompact<V>::ROW;
+    const int lead = L > 0 ? static_cast<int>((reinterpret_cast<uintptr_t>(cv) & 15) / sizeof(V)) : 0;
+    const V *cvb = cv - lead;
+    const int rows_total = L > 0 ? (lead + L + ROW - 1) / ROW : 0;
+    const int rows_per_warp = (rows_total + kElemWarps - 1) / kElemWarps;
+    const int row_begin = min(rows_total, warp * rows_per_warp);
+    const int row_end = min(rows_total, row_begin + rows_per_warp);
+    const int cnt = rows_count<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end);
+    if (lane == 0) s_scan[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kElemWarps ? s_scan[lane] : 0;
+        int wi = warp_incl_scan_add(w, lane);
+        if (lane < kElemWarps) s_scan[lane] = wi - w;
+        if (lane == kElemWarps - 1) s_pfx_raw[lead + L] = static_cast<uint16_t>(wi);
+    }
+    if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);
+    __syncthreads();
+    const int64_t base = s_base;
+    rows_compact<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end, s_scan[warp], out + base, s_pfx_raw);
+    __syncthreads();
+    const uint16_t *s_pfx = s_pfx_raw + lead;
+    // owned events read their new offset from the per-position prefix; an event that ends inside the tile its count too
 #pragma unroll 1
-        for (int64_t e = ev_lo + tid; e < ev_hi; e += kElemThreads) {
-            const int64_t a = __ldg(offsets + e) - lo, b = __ldg(offsets + e + 1) - lo;
-            const int first = s_pfx[a];
-            new_offsets[e] = base + first;
-            if (new_counts && b <= L) new_counts[e] = static_cast<int>(s_pfx[b]) - first;
-        }
-        if (tile == ntiles - 1 && tid == 0) {
-            new_offsets[n] = base + s_pfx[L];
-            if (total) *total = base + s_pfx[L];
-        }
-        if (L > 0) parity ^= 1u;
-        __syncthreads();
+    for (int64_t e = ev_lo + tid; e < ev_hi; e += kElemThreads) {
+        const int64_t a = __ldg(offsets + e) - lo, b = __ldg(offsets + e + 1) - lo;
+        const int first = s_pfx[a];
+        new_offsets[e] = base + first;
+        if (new_counts && b <= L) new_counts[e] = static_cast<int>(s_pfx[b]) - first;
+    }
+    if (tile == ntiles - 1 && tid == 0) {
+        new_offsets[n] = base + s_pfx[L];
+        if (total) *total = base + s_pfx[L];
     }
 }
 
@@ -770,24 +741,18 @@ template <typename V, class SEL, bool SAME>
 static int launch_select_elem(const SEL &sel, const void *content, const typename SEL::Elem *mask, int64_t mask_shift,
                               const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                               int64_t *total, const ElemPlan &p, cudaStream_t s) {
-    constexpr int LAG = 2;
     const size_t need = lag_ws_bytes(p.ntiles);
     JG_REQUIRE(p.rest_bytes >= need, "jg_select_elem: workspace too small (%zu < %zu)", p.rest_bytes, need);
-    JG_REQUIRE(p.ntiles < (1ll << 31), "jg_select_elem: too many tiles");
+    JG_REQUIRE(p.ntiles < (1ll << 30), "jg_select_elem: too many tiles");
     cudaError_t e = cudaMemsetAsync(p.rest, 0, need, s);
     if (e != cudaSuccess) {
         set_error("jg_select_elem: cudaMemsetAsync: %s", cudaGetErrorString(e));
         return -1;
     }
-    static unsigned resident = 0;
-    if (resident == 0) resident = persistent_grid(select_elem_kernel<V, SEL, SAME, LAG>, kElemThreads, 1ll << 40);
-    e = launch_resident(select_elem_kernel<V, SEL, SAME, LAG>, static_cast<unsigned>(p.ntiles < resident ? p.ntiles : resident),
-                        kElemThreads, s, sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, p.first_event,
-                        static_cast<V *>(out), new_offsets, new_counts, total, lag_carve(p.rest, p.ntiles), static_cast<uint32_t>(p.ntiles));
-    if (e != cudaSuccess) {
-        set_error("select_elem_kernel: %s", cudaGetErrorString(e));
-        return -1;
-    }
+    const LagSchedule sched = lag_schedule(p.ntiles, kElemSelectWindow, kElemWarps);
+    select_elem_kernel<V, SEL, SAME><<<static_cast<unsigned>(lag_grid(sched)), kElemThreads, 0, s>>>(
+        sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, p.first_event, static_cast<V *>(out), new_offsets,
+        new_counts, total, lag_carve(p.rest, p.ntiles), sched);
     int rc = check_launch("select_elem_kernel");
     if (rc || new_counts == nullptr) return rc;
     select_elem_fix_kernel<<<static_cast<unsigned>(ceil_div(p.ntiles, 256)), 256, 0, s>>>(offsets, p.first_event, p.ntiles, p.et,

@@ -227,6 +227,15 @@ struct XfItems {
 };
 using XfIdentity = XfItems<false>;
 using XfIdentityTiles = XfItems<true>;
+// item = (best[i] >= 0): the 0 / 1 counts of a dense argmin / argmax result (jg_compact_nonneg)
+struct XfNonNeg {
+    static constexpr int EXTRA = 0;
+    static constexpr int ARRAYS = 1;
+    static constexpr bool NONEMPTY = false;
+    int kind, k;
+    template <typename T>
+    __device__ __forceinline__ int64_t item(const T *a, const T *, int p) const { return a[p] >= 0 ? 1 : 0; }
+};
 template <int NARR>
 struct XfComb {
     static constexpr int EXTRA = 1;
@@ -382,16 +391,17 @@ scan_tma_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Persistent form of scan_tma_kernel on the lagged prefixes of jg_lag.cuh: phase A sums the tile a CTA will own LAG
-// iterations later straight from global memory (coalesced 8/4/1-byte loads, which leave the tile in L2) and
-// publishes the aggregate; phase B stages the current tile with one TMA bulk copy (an L2 hit), takes its base from
-// the published aggregates -- one L2 round trip, overlapped with the copy -- and writes the offsets.  No tile waits
-// on another unless a predecessor is a whole iteration late.
+// scan_tma_kernel without the look-back wait, on the windowed count / fill schedule of jg_lag.cuh.  A COUNT CTA sums
+// one tile straight from global memory (coalesced loads that leave the tile in L2) and publishes the aggregate; a
+// FILL CTA, a window of tickets later, stages the same tile with one TMA bulk copy (an L2 hit), takes its base from
+// the published aggregates -- one L2 round trip, overlapped with the copy -- and writes the offsets.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, class XF, int ITEMS, int LAG>
+constexpr int kScanWindow = 512;         // tiles per window: 12 MB of int64 counts between a tile's two reads
+
+template <typename T, class XF, int ITEMS>
 __global__ void __launch_bounds__(kScanTmaThreads)
-scan_lag_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, int64_t n, int64_t *__restrict__ out,
-                int64_t *__restrict__ total, int32_t *__restrict__ status, LagDesc lag, uint32_t ntiles,
+scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, int64_t n, int64_t *__restrict__ out,
+                int64_t *__restrict__ total, int32_t *__restrict__ status, LagDesc lag, const LagSchedule sched,
                 bool out_aligned) {
     constexpr int NW = kScanTmaThreads / kWarp;
     constexpr int TILE = kScanTmaThreads * ITEMS;
@@ -399,19 +409,23 @@ scan_lag_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     __shared__ __align__(16) unsigned char s_raw_b[XF::ARRAYS == 2 ? (TILE + XF::EXTRA) * sizeof(T) + 32 : 16];
     __shared__ uint64_t s_bar[2];
     __shared__ int64_t s_warp[NW + 1];
-    __shared__ int64_t s_agg[NW];
     __shared__ int64_t s_base;
+    __shared__ uint32_t s_ticket;
     constexpr int kSubs = XF::NONEMPTY ? TILE / 512 : 1;
     __shared__ int s_ne[kSubs];
     constexpr int SUBS = TILE / 512;
     static_assert(!XF::NONEMPTY || (TILE % 512 == 0 && (ITEMS * kWarp) % 64 == 0), "event tiles must tile the scan tile");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t G = gridDim.x;
-    stage_init(s_bar, 2);
+    const uint32_t ntiles = sched.ntiles;
+    uint32_t tile, tile_end;
+    const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile, tile_end);
+    if (role < 0) return;
 
-    // phase A: aggregate of one tile from global memory; thread 0 publishes
-    auto phase_a = [&](uint32_t ta) {
-        const int64_t a0 = static_cast<int64_t>(ta) * TILE;
+    if (role == 0) {
+        // ---------------- count: one warp per tile, the tile's aggregate straight from global memory ------------
+        const uint32_t t = tile + warp;
+        if (t >= tile_end) return;
+        const int64_t a0 = static_cast<int64_t>(t) * TILE;
         const int64_t left = n - a0;
         const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
         const T *ga = in_a + a0;
@@ -419,130 +433,104 @@ scan_lag_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         int64_t sum = 0;
         if (valid == TILE) {
 #pragma unroll 8
-            for (int j = 0; j < ITEMS; ++j) sum += xf.item(ga, gb, j * kScanTmaThreads + tid);
+            for (int j = 0; j < TILE / kWarp; ++j) sum += xf.item(ga, gb, j * kWarp + lane);
         } else {
 #pragma unroll 1
-            for (int p = tid; p < valid; p += kScanTmaThreads) sum += xf.item(ga, gb, p);
+            for (int p = lane; p < valid; p += kWarp) sum += xf.item(ga, gb, p);
         }
         sum = warp_reduce_add(sum);
-        if (lane == 0) s_agg[warp] = sum;
-        __syncthreads();
-        if (tid == 0) {
-            int64_t t = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += s_agg[w];
-            lag_publish(lag, ta, t);
-        }
-    };
+        if (lane == 0) lag_publish(lag, t, sum);
+        return;
+    }
+    const int64_t i0 = static_cast<int64_t>(tile) * TILE;
+    const int64_t left = n - i0;
+    const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
 
-#pragma unroll 1
-    for (int j = 0; j < LAG; ++j) {
-        const uint64_t ta = static_cast<uint64_t>(blockIdx.x) + static_cast<uint64_t>(j) * G;
-        if (ta < ntiles) phase_a(static_cast<uint32_t>(ta));
+    // ---------------- fill ------------------------------------------------------------------------------------
+    if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
+    stage_init(s_bar, 2);
+    const T *sa = reinterpret_cast<const T *>(s_raw_a);
+    const T *sb = reinterpret_cast<const T *>(s_raw_b);
+    if (valid > 0) {
+        const uint32_t bytes = static_cast<uint32_t>((valid + XF::EXTRA) * sizeof(T));
+        const uint32_t sha = stage_issue<sizeof(T)>(s_raw_a, reinterpret_cast<const unsigned char *>(in_a + i0), bytes, &s_bar[0]);
+        sa = reinterpret_cast<const T *>(s_raw_a + sha);
+        if (XF::ARRAYS == 2) {
+            const uint32_t shb = stage_issue<sizeof(T)>(s_raw_b, reinterpret_cast<const unsigned char *>(in_b + i0), bytes, &s_bar[1]);
+            sb = reinterpret_cast<const T *>(s_raw_b + shb);
+        }
+    }
+    if (warp == 0) {          // the base: aggregates published a window ago (one L2 round trip while the copy lands)
+        const int64_t tile_base = lag_prefix(lag, tile);
+        if (lane == 0) s_base = tile_base;
+    }
+    if (valid > 0) {
+        if (XF::ARRAYS == 2) mbar_wait(&s_bar[1], 0);
+        stage_wait(&s_bar[0], 0);
+    } else {
         __syncthreads();
     }
-
-    uint32_t it = 0;
-#pragma unroll 1
-    for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G, ++it) {
-        const uint32_t tile = static_cast<uint32_t>(tile64);
-        const uint32_t parity = it & 1u;
-        const int64_t i0 = static_cast<int64_t>(tile) * TILE;
-        const int64_t left = n - i0;
-        const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
-        if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
-        const T *sa = reinterpret_cast<const T *>(s_raw_a);
-        const T *sb = reinterpret_cast<const T *>(s_raw_b);
-        if (valid > 0) {
-            if (tid == 0) fence_proxy_async_smem();
-            const uint32_t bytes = static_cast<uint32_t>((valid + XF::EXTRA) * sizeof(T));
-            const uint32_t sha = stage_issue<sizeof(T)>(s_raw_a, reinterpret_cast<const unsigned char *>(in_a + i0), bytes, &s_bar[0]);
-            sa = reinterpret_cast<const T *>(s_raw_a + sha);
-            if (XF::ARRAYS == 2) {
-                const uint32_t shb = stage_issue<sizeof(T)>(s_raw_b, reinterpret_cast<const unsigned char *>(in_b + i0), bytes, &s_bar[1]);
-                sb = reinterpret_cast<const T *>(s_raw_b + shb);
-            }
-        }
-        // phase A of the tile this CTA owns LAG iterations from now (its loads overlap the bulk copy above)
-        {
-            const uint64_t ta = tile64 + static_cast<uint64_t>(LAG) * G;
-            if (ta < ntiles) phase_a(static_cast<uint32_t>(ta));
-        }
-        // phase B: the tile's base comes from aggregates published an iteration ago (one L2 round trip, taken by
-        // warp 0 while the bulk copy lands)
-        if (warp == 0) {
-            const int64_t tile_base = lag_prefix(lag, tile);
-            if (lane == 0) s_base = tile_base;
-        }
-        if (valid > 0) {
-            if (XF::ARRAYS == 2) mbar_wait(&s_bar[1], parity);
-            stage_wait(&s_bar[0], parity);
-        } else {
-            __syncthreads();
-        }
-        const int wbase = warp * (ITEMS * kWarp);
-        const bool full = valid == TILE;
-        int64_t sum = 0;
-        bool neg = false, big = false;
+    const int wbase = warp * (ITEMS * kWarp);
+    const bool full = valid == TILE;
+    int64_t sum = 0;
+    bool neg = false, big = false;
 #pragma unroll
+    for (int r = 0; r < ITEMS / 2; ++r) {
+        const int p = wbase + r * 64 + lane * 2;
+        const int64_t x = (full || p < valid) ? xf.item(sa, sb, p) : 0;
+        const int64_t y = (full || p + 1 < valid) ? xf.item(sa, sb, p + 1) : 0;
+        neg |= (x < 0) | (y < 0);
+        big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
+        sum += x + y;
+    }
+    if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
+    sum = warp_reduce_add(sum);
+    if (lane == 0) s_warp[warp] = sum;
+    if constexpr (XF::NONEMPTY) {
+        int ne_lo = 0, ne_hi = 0;
+        const int sub_lo = wbase >> 9;
+#pragma unroll 4
         for (int r = 0; r < ITEMS / 2; ++r) {
             const int p = wbase + r * 64 + lane * 2;
-            const int64_t x = (full || p < valid) ? xf.item(sa, sb, p) : 0;
-            const int64_t y = (full || p + 1 < valid) ? xf.item(sa, sb, p + 1) : 0;
-            neg |= (x < 0) | (y < 0);
-            big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
-            sum += x + y;
+            const int c = ((full || p < valid) ? (xf.item(sa, sb, p) > 0) : 0) + ((full || p + 1 < valid) ? (xf.item(sa, sb, p + 1) > 0) : 0);
+            if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
+            else ne_hi += c;
         }
-        if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
-        sum = warp_reduce_add(sum);
-        if (lane == 0) s_warp[warp] = sum;
-        if constexpr (XF::NONEMPTY) {
-            int ne_lo = 0, ne_hi = 0;
-            const int sub_lo = wbase >> 9;
-#pragma unroll 4
-            for (int r = 0; r < ITEMS / 2; ++r) {
-                const int p = wbase + r * 64 + lane * 2;
-                const int c = ((full || p < valid) ? (xf.item(sa, sb, p) > 0) : 0) + ((full || p + 1 < valid) ? (xf.item(sa, sb, p + 1) > 0) : 0);
-                if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
-                else ne_hi += c;
-            }
-            ne_lo = warp_reduce_add(ne_lo);
-            ne_hi = warp_reduce_add(ne_hi);
-            if (lane == 0) {
-                if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
-                if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
-            }
+        ne_lo = warp_reduce_add(ne_lo);
+        ne_hi = warp_reduce_add(ne_hi);
+        if (lane == 0) {
+            if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
+            if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
         }
-        const bool wide = __syncthreads_or(big);
-        if constexpr (XF::NONEMPTY) {
-            if (tid < SUBS) {
-                const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
-                if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
-            }
+    }
+    const bool wide = __syncthreads_or(big);
+    if constexpr (XF::NONEMPTY) {
+        if (tid < SUBS) {
+            const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
+            if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
         }
-        int64_t run = s_base, tile_sum = 0;
+    }
+    int64_t run = s_base, tile_sum = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const int64_t part = s_warp[w];
-            if (w < warp) run += part;
-            tile_sum += part;
-        }
-        if (tile == ntiles - 1 && tid == 0) {
-            out[n] = s_base + tile_sum;
-            if (total) *total = s_base + tile_sum;
-        }
-        if (full) {
-            if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
-            else scan_tma_rows<T, int32_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
-        } else {
-            if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
-            else scan_tma_rows<T, int32_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
-        }
-        __syncthreads();      // the stage, s_warp, s_base and s_ne are rewritten by the next iteration
+    for (int w = 0; w < NW; ++w) {
+        const int64_t part = s_warp[w];
+        if (w < warp) run += part;
+        tile_sum += part;
+    }
+    if (tile == ntiles - 1 && tid == 0) {
+        out[n] = s_base + tile_sum;
+        if (total) *total = s_base + tile_sum;
+    }
+    if (full) {
+        if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        else scan_tma_rows<T, int32_t, XF, ITEMS, true>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+    } else {
+        if (wide) scan_tma_rows<T, int64_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
+        else scan_tma_rows<T, int32_t, XF, ITEMS, false>(xf, sa, sb, valid, wbase, lane, run, out, i0, n, out_aligned);
     }
 }
 
-inline int scan_mode() {      // experiment switch (JG_SCAN_MODE): 0 = look-back (round 1), 1 = lagged LAG 1, 2 = lagged LAG 2
+inline int scan_mode() {      // experiment switch (JG_SCAN_MODE): 0 = look-back (round 1), 1 = windowed count / fill
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("JG_SCAN_MODE");
@@ -551,42 +539,44 @@ inline int scan_mode() {      // experiment switch (JG_SCAN_MODE): 0 = look-back
     return mode;
 }
 
-template <typename T, class XF, int ITEMS, int LAG>
-int launch_scan_lag(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
+template <typename T, class XF, int ITEMS>
+int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
     constexpr int TILE = kScanTmaThreads * ITEMS;
     const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
     const size_t need = lag_ws_bytes(ntiles);
     JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
     JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
-    JG_REQUIRE(ntiles < (1ll << 31), "scan: too many tiles");
+    JG_REQUIRE(ntiles < (1ll << 30), "scan: too many tiles");
     cudaError_t e = cudaMemsetAsync(ws, 0, need, stream);
     if (e != cudaSuccess) {
         set_error("scan: cudaMemsetAsync: %s", cudaGetErrorString(e));
         return -1;
     }
-    static unsigned resident = 0;
-    if (resident == 0) {
-        cudaFuncSetAttribute(scan_lag_kernel<T, XF, ITEMS, LAG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        resident = persistent_grid(scan_lag_kernel<T, XF, ITEMS, LAG>, kScanTmaThreads, 1ll << 40);
-        if (const char *c = getenv("JG_SCAN_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(scan_win_kernel<T, XF, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
     }
-    const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
+    static int win_env = -1;
+    if (win_env < 0) {
+        const char *c = getenv("JG_SCAN_WINDOW");
+        win_env = c ? atoi(c) : 0;
+    }
+    const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kScanWindow, kScanTmaThreads / kWarp);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    e = launch_resident(scan_lag_kernel<T, XF, ITEMS, LAG>, grid, kScanTmaThreads, stream, xf, in_a, in_b, n, out, total,
-                        status, lag_carve(ws, ntiles), static_cast<uint32_t>(ntiles), out_aligned);
-    if (e != cudaSuccess) {
-        set_error("scan_lag_kernel: %s", cudaGetErrorString(e));
-        return -1;
-    }
-    return check_launch("scan_lag_kernel");
+    scan_win_kernel<T, XF, ITEMS><<<static_cast<unsigned>(lag_grid(sched)), kScanTmaThreads, 0, stream>>>(
+        xf, in_a, in_b, n, out, total, status, lag_carve(ws, ntiles), sched, out_aligned);
+    return check_launch("scan_win_kernel");
 }
 
 template <typename T, class XF, int ITEMS>
 int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
-    if (scan_mode() == 1) return launch_scan_lag<T, XF, ITEMS, 1>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
-    if (scan_mode() == 2) return launch_scan_lag<T, XF, ITEMS, 2>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
+    // plain scans: the windowed count / fill kernel; combinatorial counts (two offsets per item, a division-free but
+    // longer transform) keep the look-back -- their count CTAs cost more than the wait they avoid (measured)
+    if (XF::EXTRA == 0 && scan_mode() == 1)
+        return launch_scan_win<T, XF, ITEMS>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
     constexpr int TILE = kScanTmaThreads * ITEMS;
     const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
     const size_t need = sizeof(LookbackWs) + static_cast<size_t>(ntiles) * 8;

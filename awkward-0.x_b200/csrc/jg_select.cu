@@ -6,6 +6,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "jg_compact.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -70,6 +71,26 @@ __device__ __forceinline__ int count16(const SEL &sel, int4 v) {
 
 constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
 
+// ONE WARP: number of selected positions of a run (16-byte loads; unaligned head and tail item by item)
+template <class SEL>
+__device__ __forceinline__ int64_t warp_count_selected(const SEL &sel, const typename SEL::Elem *m, int64_t len) {
+    using E = typename SEL::Elem;
+    constexpr int PER = 16 / sizeof(E);
+    const int lane = threadIdx.x & 31;
+    int64_t cnt = 0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
+    if (head > len) head = len;
+    if (lane < head) cnt += sel.test(m[lane]);
+    const int64_t nvec = (len - head) / PER;
+    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
+#pragma unroll 2
+    for (int64_t i = lane; i < nvec; i += kWarp) cnt += count16(sel, __ldg(mv + i));
+    const int64_t tail0 = head + nvec * PER;
+    if (tail0 + lane < len) cnt += sel.test(m[tail0 + lane]);
+    return warp_reduce_add(cnt);
+}
+
 template <class SEL>
 __global__ void __launch_bounds__(kCountWarps * kWarp)
 mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
@@ -100,24 +121,52 @@ mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, in
     if (lane == 0) tile_totals[tile] = cnt;
 }
 
-// SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both
-template <typename V, int KM, class SEL, bool SAME>     // KM = positions a tile may stage
-__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : (SAME ? 7 : 6))
+constexpr int kSelectWindow = 2048;      // tiles per window of the one-launch form: ~28 MB between a tile's two reads
+
+// SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both.
+// WIN: the ONE-LAUNCH form on the windowed count / fill schedule of jg_lag.cuh -- a count CTA popcounts a tile's
+// selector run (16-byte loads that leave the run in L2, the tile's offsets are prefetched on the way) and publishes
+// the total; a fill CTA, a window of tickets later, compacts the tile exactly as below with the staged run now an L2
+// hit and its base the sum of the published totals (one L2 round trip).  The column comes from HBM once.
+template <typename V, int KM, class SEL, bool SAME, bool WIN>     // KM = positions a tile may stage
+__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : ((SAME && !WIN) ? 7 : 6))
 mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                  int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
-                 const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
+                 const int64_t *__restrict__ tile_bases, uint32_t ntiles, int64_t *__restrict__ total, LagDesc lag,
+                 const LagSchedule sched) {
     using E = typename SEL::Elem;
     static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32 + (sizeof(V) >= 4 ? 512 : 0)];     // (+ one row of slack)
     __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
-    __shared__ uint16_t s_pfx[KM + 2];
+    __shared__ __align__(16) uint16_t s_pfx[KM + 8 + (sizeof(V) >= 4 ? 128 : 0)];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
+    __shared__ uint32_t s_ticket;
+    __shared__ int64_t s_base;
 
-    const uint32_t tile_index = blockIdx.x;
+    uint32_t tile_index = blockIdx.x;
+    if constexpr (WIN) {
+        uint32_t tile_end;
+        const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile_index, tile_end);
+        if (role < 0) return;
+        if (role == 0) {          // count: one warp per tile
+            const uint32_t t = tile_index + (threadIdx.x >> 5);
+            if (t >= tile_end) return;
+            int64_t ev0;
+            int nev;
+            EventTile::range(n, t, ev0, nev);
+            const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
+            const int64_t ev = ev0 + (threadIdx.x & 31) * 16;          // the tile's offsets: 4 KB the fill CTA reads
+            if (ev <= ev0 + nev) prefetch_l2(offsets + ev);
+            if ((threadIdx.x & 31) == 0) prefetch_l2(offsets + ev0 + nev);
+            const int64_t cnt = warp_count_selected(sel, mask + a + mask_shift, b - a);
+            if ((threadIdx.x & 31) == 0) lag_publish(lag, t, cnt);
+            return;
+        }
+    }
     EventTile tile;
     if (threadIdx.x == 0) {
         // start both TMA copies before the cooperative offsets load (see segreduce_kernel)
@@ -140,8 +189,16 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t len = e1 - e0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = __ldg(tile_bases + tile_index);
-    if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
+    int64_t base = 0;
+    if constexpr (WIN) {
+        if (warp == NW - 1) {                 // (the last warp has the least to do in the passes below)
+            const int64_t b = lag_prefix(lag, tile_index);
+            if (lane == 0) s_base = b;
+        }
+    } else {
+        base = __ldg(tile_bases + tile_index);
+        if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
+    }
 
     if (len <= KM) {
         // ---------------- staged tile ----------------------------------------------------------------------
@@ -163,45 +220,101 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             }
             __syncthreads();
         }
-        // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
-        const int rows_total = (L + 31) >> 5;
-        const int rows_per_warp = (rows_total + NW - 1) / NW;
-        const int p_begin = min(L, warp * rows_per_warp * 32);
-        const int p_end = min(L, p_begin + rows_per_warp * 32);
-        // pass 1: selected per warp
-        int cnt = 0;
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-        cnt = warp_reduce_add(cnt);
-        if (lane == 0) s_scan[warp] = cnt;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < NW ? s_scan[lane] : 0;
-            int wi = warp_incl_scan_add(w, lane);
-            if (lane < NW) s_scan[lane] = wi - w;
-            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-        }
-        if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
-        __syncthreads();
-        // pass 2: compaction, consecutive lanes -> consecutive output slots
-        int run = s_scan[warp];
-        V *dst = out + base;
-        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-            const int p = p0 + lane;
-            const bool on = p < p_end && sel.test(mv[p]);
-            const unsigned b = __ballot_sync(0xffffffffu, on);
-            const int slot = run + __popc(b & ((1u << lane) - 1u));
-            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-            if (on) dst[slot] = cv[p];
-            run += __popc(b);
+        constexpr bool ROWS = sizeof(V) >= 4;       // 16-byte rows (jg_compact.cuh); 1- and 2-byte items keep 32 positions per step
+        int lead = 0;
+        if constexpr (ROWS) {
+            if (L > 0) lead = static_cast<int>((reinterpret_cast<uintptr_t>(cv) & 15) / sizeof(V));
+            constexpr int ROW = RowCompact<V>::ROW;
+            const V *cvb = cv - lead;
+            const int rows_total = L > 0 ? (lead + L + ROW - 1) / ROW : 0;
+            const int rows_per_warp = (rows_total + NW - 1) / NW;
+            const int row_begin = min(rows_total, warp * rows_per_warp);
+            const int row_end = min(rows_total, row_begin + rows_per_warp);
+            // pass 1: selected per warp
+            const int cnt = rows_count<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end);
+            if (lane == 0) s_scan[warp] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                int w = lane < NW ? s_scan[lane] : 0;
+                int wi = warp_incl_scan_add(w, lane);
+                if (lane < NW) s_scan[lane] = wi - w;
+                if (lane == NW - 1) s_pfx[lead + L] = static_cast<uint16_t>(wi);
+            }
+            if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
+            __syncthreads();
+            if constexpr (WIN) base = s_base;
+            // pass 2: compaction, a lane's selected values go to consecutive slots
+            rows_compact<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end, s_scan[warp], out + base, s_pfx);
+        } else {
+            // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
+            const int rows_total = (L + 31) >> 5;
+            const int rows_per_warp = (rows_total + NW - 1) / NW;
+            const int p_begin = min(L, warp * rows_per_warp * 32);
+            const int p_end = min(L, p_begin + rows_per_warp * 32);
+            int cnt = 0;
+            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
+            cnt = warp_reduce_add(cnt);
+            if (lane == 0) s_scan[warp] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                int w = lane < NW ? s_scan[lane] : 0;
+                int wi = warp_incl_scan_add(w, lane);
+                if (lane < NW) s_scan[lane] = wi - w;
+                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+            }
+            if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);
+            __syncthreads();
+            if constexpr (WIN) base = s_base;
+            int run = s_scan[warp];
+            V *dst = out + base;
+            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+                const int p = p0 + lane;
+                const bool on = p < p_end && sel.test(mv[p]);
+                const unsigned b = __ballot_sync(0xffffffffu, on);
+                const int slot = run + __popc(b & ((1u << lane) - 1u));
+                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+                if (on) dst[slot] = cv[p];
+                run += __popc(b);
+            }
         }
         __syncthreads();
         // per-event new offsets -- and counts, which every later step asks for (jagged.py:383-388), for one more
-        // shared-memory read instead of a 16N-byte pass of their own
-#pragma unroll 1
-        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
-            const int first = s_pfx[s_off[ev] - e0];
-            new_offsets[tile.event0 + ev] = base + first;
-            if (new_counts) new_counts[tile.event0 + ev] = static_cast<int>(s_pfx[s_off[ev + 1] - e0]) - first;
+        // shared-memory read instead of a 16N-byte pass of their own.  Thread t owns the events 2t and 2t + 1: their
+        // offsets and counts leave as one 16-byte store each, positions are 32-bit and relative to the tile.
+        const uint16_t *pfx = s_pfx + lead;
+        {
+            const int ev = threadIdx.x * 2;
+            if (ev < tile.nev) {
+                const int r0 = static_cast<int>(s_off[ev] - e0);
+                const int r1 = static_cast<int>(s_off[ev + 1] - e0);
+                const int f0 = pfx[r0], f1 = pfx[r1];
+                int64_t *po = new_offsets + tile.event0 + ev;
+                int64_t *pc = new_counts ? new_counts + tile.event0 + ev : nullptr;
+                if (ev + 1 < tile.nev) {
+                    const int f2 = pfx[static_cast<int>(s_off[ev + 2] - e0)];
+                    if ((reinterpret_cast<uintptr_t>(po) & 15) == 0) __stcs(reinterpret_cast<longlong2 *>(po), make_longlong2(base + f0, base + f1));
+                    else {
+                        po[0] = base + f0;
+                        po[1] = base + f1;
+                    }
+                    if (pc) {
+                        if ((reinterpret_cast<uintptr_t>(pc) & 15) == 0) __stcs(reinterpret_cast<longlong2 *>(pc), make_longlong2(f1 - f0, f2 - f1));
+                        else {
+                            pc[0] = f1 - f0;
+                            pc[1] = f2 - f1;
+                        }
+                    }
+                } else {
+                    po[0] = base + f0;
+                    if (pc) pc[0] = f1 - f0;
+                }
+            }
+        }
+        if constexpr (WIN) {
+            if (tile_index == ntiles - 1 && threadIdx.x == 0) {
+                new_offsets[n] = base + pfx[L];
+                if (total) *total = base + pfx[L];
+            }
         }
         return;
     }
@@ -217,6 +330,10 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
     const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
     const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
+    if constexpr (WIN) {
+        __syncthreads();
+        base = s_base;
+    }
     int64_t run = 0;
 #pragma unroll 1
     for (int64_t cs = 0; cs < len; cs += KM) {
@@ -270,287 +387,15 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// The same selection as ONE persistent launch on the lagged prefixes of jg_lag.cuh.  In every iteration a CTA
-//   A. counts the selected positions of the tile it will own LAG iterations later (the whole CTA, 16-byte loads that
-//      leave the run in L2; the tile's offsets are prefetched into L2 on the way) and publishes the count;
-//   B. compacts its current tile exactly like mask_fill_kernel -- the staged run is now an L2 hit and the tile's base
-//      is the sum of aggregates published an iteration ago (lag_prefix: one L2 round trip, no waiting).
-// DRAM traffic is the algorithmic one: the column is read from HBM once (a[a > c] moved 9.1 GB for 6.6 GB before).
-// ------------------------------------------------------------------------------------------------------------
-template <class SEL>
-__device__ __forceinline__ int64_t cta_count_selected(const SEL &sel, const typename SEL::Elem *m, int64_t len) {
-    using E = typename SEL::Elem;
-    constexpr int PER = 16 / sizeof(E);
-    const int tid = threadIdx.x;
-    int64_t cnt = 0;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
-    if (head > len) head = len;
-    if (tid < head) cnt += sel.test(m[tid]);
-    const int64_t nvec = (len - head) / PER;
-    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-#pragma unroll 2
-    for (int64_t i = tid; i < nvec; i += kTileThreads) cnt += count16(sel, __ldg(mv + i));
-    const int64_t tail0 = head + nvec * PER;
-    if (tail0 + tid < len) cnt += sel.test(m[tail0 + tid]);
-    return cnt;
-}
-
-template <typename V, int KM, class SEL, bool SAME, int LAG>
-__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : 6)
-mask_select_lag_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
-                       int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
-                       int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
-                       int64_t *__restrict__ total, LagDesc lag, uint32_t ntiles) {
-    using E = typename SEL::Elem;
-    static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
-    constexpr int NW = kTileThreads / kWarp;
-    constexpr int R = LAG + 2;                  // ring of tile boundaries: current .. LAG ahead, plus the one in flight
-    __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
-    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
-    __shared__ uint16_t s_pfx[KM + 2];
-    __shared__ uint64_t s_bar[2];
-    __shared__ int32_t s_scan[NW + 1];
-    __shared__ int64_t s_bnd[R][2];
-    __shared__ unsigned long long s_acc;
-    __shared__ int64_t s_base;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t G = gridDim.x;
-    auto boundary = [&](uint64_t t, int which) -> int64_t {      // first / one-past-last event of tile t
-        const int64_t ev = static_cast<int64_t>(t) * kTileEvents + (which ? kTileEvents : 0);
-        return __ldg(offsets + (ev < n ? ev : n));
-    };
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        s_acc = 0ull;
-    }
-    if (tid < 2 * (LAG + 1)) {
-        const uint64_t t = blockIdx.x + static_cast<uint64_t>(tid >> 1) * G;
-        s_bnd[tid >> 1][tid & 1] = t < ntiles ? boundary(t, tid & 1) : 0;
-    }
-    __syncthreads();
-
-    // phase A of tile ta (its boundaries are in ring slot `slot`): every thread adds its share to s_acc
-    auto phase_a = [&](uint64_t ta, int slot) {
-        const int64_t a = s_bnd[slot][0], b = s_bnd[slot][1];
-        int64_t cnt = cta_count_selected(sel, mask + a + mask_shift, b - a);
-        if (tid <= (kTileEvents * 8) / 128) {                // the tile's offsets: 4 KB, fetched again by phase B
-            const int64_t ev = static_cast<int64_t>(ta) * kTileEvents + tid * 16;
-            if (ev <= n) prefetch_l2(offsets + ev);
-        }
-        cnt = warp_reduce_add(cnt);
-        if (lane == 0 && cnt) atomicAdd(&s_acc, static_cast<unsigned long long>(cnt));
-    };
-    auto publish_a = [&](uint64_t ta) {                       // thread 0, after a barrier
-        lag_publish(lag, static_cast<uint32_t>(ta), static_cast<int64_t>(s_acc));
-        s_acc = 0ull;
-    };
-#pragma unroll 1
-    for (int j = 0; j < LAG; ++j) {
-        const uint64_t ta = blockIdx.x + static_cast<uint64_t>(j) * G;
-        if (ta < ntiles) phase_a(ta, j);
-        __syncthreads();
-        if (tid == 0 && ta < ntiles) publish_a(ta);
-        __syncthreads();
-    }
-
-    uint32_t it = 0;
-    uint32_t parity = 0;          // of the mbarriers' current phase: flips only in iterations that arm them (a staged tile)
-#pragma unroll 1
-    for (uint64_t tile64 = blockIdx.x; tile64 < ntiles; tile64 += G, ++it) {
-        const uint32_t tile_index = static_cast<uint32_t>(tile64);
-        const int slot_b = it % R, slot_a = (it + LAG) % R, slot_n = (it + LAG + 1) % R;
-        // boundaries of the tile LAG + 1 iterations ahead (consumed by the next iteration's phase A)
-        int64_t next_bnd = 0;
-        {
-            const uint64_t tn = tile64 + static_cast<uint64_t>(LAG + 1) * G;
-            if (tid < 2 && tn < ntiles) next_bnd = boundary(tn, tid);
-        }
-        EventTile tile;
-        int64_t ev0;
-        int nev;
-        EventTile::range(n, tile_index, ev0, nev);
-        if (tid == 0) {
-            const int64_t a = s_bnd[slot_b][0], b = s_bnd[slot_b][1];
-            if (b > a && b - a <= KM) {
-                fence_proxy_async_smem();
-                if (!SAME)
-                    stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(mask + a + mask_shift),
-                               static_cast<uint32_t>((b - a) * sizeof(E)), &s_bar[1]);
-                stage_bulk(s_content, reinterpret_cast<const unsigned char *>(content + a),
-                           static_cast<uint32_t>((b - a) * sizeof(V)), &s_bar[0]);
-            }
-        }
-        // the tile's offsets (in flight during phase A)
-        int64_t o0 = 0, o1 = 0, o2 = 0;
-        {
-            const int64_t *src = offsets + ev0;
-            if (tid <= nev) o0 = __ldg(src + tid);
-            if (tid + kTileThreads <= nev) o1 = __ldg(src + tid + kTileThreads);
-            if (tid == 0 && nev == 2 * kTileThreads) o2 = __ldg(src + nev);
-        }
-        const uint64_t ta = tile64 + static_cast<uint64_t>(LAG) * G;
-        if (ta < ntiles) phase_a(ta, slot_a);
-        if (tid <= nev) s_off[tid] = o0;
-        if (tid + kTileThreads <= nev) s_off[tid + kTileThreads] = o1;
-        if (tid == 0 && nev == 2 * kTileThreads) s_off[nev] = o2;
-        if (tid < 2) s_bnd[slot_n][tid] = next_bnd;
-        __syncthreads();
-        if (tid == 0 && ta < ntiles) publish_a(ta);
-        tile.off = s_off;
-        tile.event0 = ev0;
-        tile.nev = nev;
-        if (warp == NW - 1) {                                     // the last warp has the least to do in pass 1
-            const int64_t b = lag_prefix(lag, tile_index);
-            if (lane == 0) s_base = b;
-        }
-        const int64_t e0 = tile.first_element(), e1 = tile.last_element();
-        const int64_t len = e1 - e0;
-
-        if (len <= KM) {
-            // ---------------- staged tile ------------------------------------------------------------------
-            const int L = static_cast<int>(len);
-            const V *cv = nullptr;
-            const E *mv = nullptr;
-            if (L > 0) {
-                const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
-                                                           static_cast<uint32_t>(L * sizeof(V)));
-                cv = reinterpret_cast<const V *>(s_content + cs);
-                if (SAME) {
-                    mbar_wait(&s_bar[0], parity);
-                    mv = reinterpret_cast<const E *>(cv);
-                } else {
-                    const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + e0 + mask_shift),
-                                                               static_cast<uint32_t>(L * sizeof(E)));
-                    mbar_wait(&s_bar[1], parity);
-                    mv = reinterpret_cast<const E *>(s_mask + ms);
-                }
-                __syncthreads();
-            }
-            const int rows_total = (L + 31) >> 5;
-            const int rows_per_warp = (rows_total + NW - 1) / NW;
-            const int p_begin = min(L, warp * rows_per_warp * 32);
-            const int p_end = min(L, p_begin + rows_per_warp * 32);
-            int cnt = 0;
-            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-            cnt = warp_reduce_add(cnt);
-            if (lane == 0) s_scan[warp] = cnt;
-            __syncthreads();
-            if (warp == 0) {
-                int w = lane < NW ? s_scan[lane] : 0;
-                int wi = warp_incl_scan_add(w, lane);
-                if (lane < NW) s_scan[lane] = wi - w;
-                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-            }
-            if (!SAME && L > 0) mbar_wait(&s_bar[0], parity);
-            __syncthreads();
-            const int64_t base = s_base;
-            int run = s_scan[warp];
-            V *dst = out + base;
-            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-                const int p = p0 + lane;
-                const bool on = p < p_end && sel.test(mv[p]);
-                const unsigned b = __ballot_sync(0xffffffffu, on);
-                const int slot = run + __popc(b & ((1u << lane) - 1u));
-                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-                if (on) dst[slot] = cv[p];
-                run += __popc(b);
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int ev = tid; ev < tile.nev; ev += kTileThreads) {
-                const int first = s_pfx[s_off[ev] - e0];
-                new_offsets[tile.event0 + ev] = base + first;
-                if (new_counts) new_counts[tile.event0 + ev] = static_cast<int>(s_pfx[s_off[ev + 1] - e0]) - first;
-            }
-            if (tile_index == ntiles - 1 && tid == 0) {
-                new_offsets[n] = base + s_pfx[L];
-                if (total) *total = base + s_pfx[L];
-            }
-            if (L > 0) parity ^= 1u;
-            __syncthreads();
-            continue;
-        }
-
-        // ---------------- oversize tile (long events): chunks of KM positions straight from global memory ----
-        const V *cv = content + e0;
-        const E *mv = mask + e0 + mask_shift;
-        int64_t *s_new = reinterpret_cast<int64_t *>(s_content);
-        static_assert(KM * sizeof(V) + 32 >= (kTileEvents + 1) * sizeof(int64_t), "stage too small for the offsets");
-        const int evA = tid, evB = tid + kTileThreads;
-        const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
-        const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
-        __syncthreads();                                           // s_base
-        const int64_t base = s_base;
-        int64_t run = 0;
-#pragma unroll 1
-        for (int64_t cs = 0; cs < len; cs += KM) {
-            const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
-            const E *m = mv + cs;
-            const V *c = cv + cs;
-            const int rows_total = (L + 31) >> 5;
-            const int rows_per_warp = (rows_total + NW - 1) / NW;
-            const int p_begin = min(L, warp * rows_per_warp * 32);
-            const int p_end = min(L, p_begin + rows_per_warp * 32);
-            int cnt = 0;
-#pragma unroll 1
-            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);
-            cnt = warp_reduce_add(cnt);
-            if (lane == 0) s_scan[warp] = cnt;
-            __syncthreads();
-            if (warp == 0) {
-                int w = lane < NW ? s_scan[lane] : 0;
-                int wi = warp_incl_scan_add(w, lane);
-                if (lane < NW) s_scan[lane] = wi - w;
-                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-            }
-            __syncthreads();
-            int wrun = s_scan[warp];
-            V *dst = out + base + run;
-#pragma unroll 1
-            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-                const int p = p0 + lane;
-                const bool on = p < p_end && sel.test(m[p]);
-                const unsigned b = __ballot_sync(0xffffffffu, on);
-                const int slot = wrun + __popc(b & ((1u << lane) - 1u));
-                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-                if (on) dst[slot] = c[p];
-                wrun += __popc(b);
-            }
-            __syncthreads();
-            if (stA >= cs && stA < cs + L) s_new[evA] = run + s_pfx[stA - cs];
-            if (stB >= cs && stB < cs + L) s_new[evB] = run + s_pfx[stB - cs];
-            run += s_pfx[L];
-            __syncthreads();
-        }
-        if (stA >= len) s_new[evA] = run;
-        if (stB >= len) s_new[evB] = run;
-        if (tid == 0) s_new[tile.nev] = run;
-        __syncthreads();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ev = tid + h * kTileThreads;
-            if (ev < tile.nev) {
-                new_offsets[tile.event0 + ev] = base + s_new[ev];
-                if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
-            }
-        }
-        if (tile_index == ntiles - 1 && tid == 0) {
+    if constexpr (WIN) {
+        if (tile_index == ntiles - 1 && threadIdx.x == 0) {
             new_offsets[n] = base + run;
             if (total) *total = base + run;
         }
-        __syncthreads();
     }
 }
 
-inline int select_mode() {    // experiment switch (JG_SELECT_MODE): 0 = count / scan / fill (round 1), 1 / 2 = lagged, LAG 1 / 2
+inline int select_mode() {    // experiment switch (JG_SELECT_MODE): 0 = count / scan / fill (round 1), 1 = one launch, windowed
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("JG_SELECT_MODE");
@@ -732,36 +577,22 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
         const size_t need = lag_ws_bytes(ntiles);
         JG_REQUIRE(ws != nullptr && ws_bytes >= need, "jg_mask_select: workspace too small (%zu < %zu)", ws_bytes, need);
         JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "jg_mask_select: workspace must be 16-byte aligned");
+        JG_REQUIRE(ntiles < (1ll << 30), "jg_mask_select: too many tiles");
         cudaError_t e = cudaMemsetAsync(ws, 0, need, s);
         if (e != cudaSuccess) {
             set_error("jg_mask_select: cudaMemsetAsync: %s", cudaGetErrorString(e));
             return -1;
         }
-        const LagDesc lag = lag_carve(ws, ntiles);
-        if (select_mode() == 2) {
-            static unsigned resident = 0;
-            if (resident == 0) {
-                resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 2>, kTileThreads, 1ll << 40);
-                if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
-            }
-            e = launch_resident(mask_select_lag_kernel<V, KM, SEL, SAME, 2>, static_cast<unsigned>(ntiles < resident ? ntiles : resident),
-                                kTileThreads, s, sel, static_cast<const V *>(content), mask, mask_shift, offsets, n,
-                                static_cast<V *>(out), new_offsets, new_counts, total, lag, static_cast<uint32_t>(ntiles));
-        } else {
-            static unsigned resident = 0;
-            if (resident == 0) {
-                resident = persistent_grid(mask_select_lag_kernel<V, KM, SEL, SAME, 1>, kTileThreads, 1ll << 40);
-                if (const char *c = getenv("JG_SELECT_CTAS")) resident = static_cast<unsigned>(atoi(c)) * sm_count();
-            }
-            e = launch_resident(mask_select_lag_kernel<V, KM, SEL, SAME, 1>, static_cast<unsigned>(ntiles < resident ? ntiles : resident),
-                                kTileThreads, s, sel, static_cast<const V *>(content), mask, mask_shift, offsets, n,
-                                static_cast<V *>(out), new_offsets, new_counts, total, lag, static_cast<uint32_t>(ntiles));
+        static int win_env = -1;
+        if (win_env < 0) {
+            const char *c = getenv("JG_SELECT_WINDOW");
+            win_env = c ? atoi(c) : 0;
         }
-        if (e != cudaSuccess) {
-            set_error("mask_select_lag_kernel: %s", cudaGetErrorString(e));
-            return -1;
-        }
-        return check_launch("mask_select_lag_kernel");
+        const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kSelectWindow, kTileThreads / kWarp);
+        mask_fill_kernel<V, KM, SEL, SAME, true><<<static_cast<unsigned>(lag_grid(sched)), kTileThreads, 0, s>>>(
+            sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+            new_counts, nullptr, static_cast<uint32_t>(ntiles), total, lag_carve(ws, ntiles), sched);
+        return check_launch("mask_fill_kernel<one launch>");
     }
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
@@ -773,9 +604,9 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
     ScanInArray<int64_t> in{t.totals, true};
     rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
     if (rc) return rc;
-    mask_fill_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+    mask_fill_kernel<V, KM, SEL, SAME, false><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
         sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
-        new_counts, t.bases, static_cast<uint32_t>(ntiles));
+        new_counts, t.bases, static_cast<uint32_t>(ntiles), nullptr, LagDesc{}, LagSchedule{});
     return check_launch("mask_fill_kernel");
 }
 
@@ -943,8 +774,8 @@ int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int6
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
                       void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t s = as_stream(stream);
-    ScanInNonNeg in{best};
-    int rc = launch_scan(in, n, out_offsets, total, nullptr, ws, ws_bytes, s);
+    int rc = launch_scan_tma<int64_t, XfNonNeg, kScanTmaItems>(XfNonNeg{0, 0}, best, static_cast<const int64_t *>(nullptr), n,
+                                                               out_offsets, total, nullptr, ws, ws_bytes, s);
     if (rc) return rc;
     if (n > 0) {
         scatter_nonneg_kernel<<<flat_grid(n, 256), 256, 0, s>>>(best, n, out_offsets, out_index);

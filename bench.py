@@ -725,7 +725,7 @@ def distribution_table(ak, args):
         n = args.dist_elements // 40
         yield "poisson40", torch.poisson(torch.full((n,), 40.0, device=dev), generator=g).to(torch.int64)
         n = args.dist_elements // 4
-        c = torch.empty(n, device=dev, dtype=torch.float32).geometric_(0.2, generator=g).to(torch.int64) - 1
+        c = (torch.empty(n, device=dev, dtype=torch.float32).geometric_(0.2, generator=g).to(torch.int64) - 1).clamp_(min=0)
         where = torch.randint(0, n, (1000,), device=dev, generator=g)
         c[where] = torch.randint(5000, 70000, (1000,), device=dev, generator=g)
         yield "geometric_tail", c

@@ -173,6 +173,10 @@ STATEMENTS = [
     ("t = J.fromiter([[1, 2, 3], [], [4, 5]]); u = t + 1; t[t > 0] = 0", "u"),
     ("p = x.pairs(); q = p.i0 * 10 + p.i1; r = q[q > 20]", "r"),
     ("c = x.cross(y); m = (c.i0 + c.i1) > 11; r = c[m].i1", "r"),
+    # an in-place store between argmax() and the gather: the gather reads the CURRENT content (jagged.py:541-560)
+    ("t = J.fromiter([[1.0, 9.0, 3.0], [], [4.0, 5.0]]); k = t.argmax(); t[t > 4] = 0; r = t[k]", "r"),
+    ("t = J.fromiter([[1.0, 9.0, 3.0], [], [4.0, 5.0]]); k = t.argmin(); u = J(t.starts, t.stops, t.content); u[u < 2] = 7; r = t[k]", "r"),
+    ("t = J.fromiter([[1.0, 9.0, 3.0], [], [4.0, 5.0]]); k = t.argmax(); r = t[k]", "r"),
 ]
 
 

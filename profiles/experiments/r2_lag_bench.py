@@ -67,7 +67,7 @@ call = lambda: _lib.call("jg_counts2offsets", counts_dev.data_ptr(), _lib.JG_I64
 call()
 ref_off = torch.zeros(N + 1, dtype=torch.int64, device=dev)
 torch.cumsum(counts_t, 0, out=ref_off[1:])
-ok = bool(torch.equal(off.tensor, ref_off)) and int(scal.cpu()[0]) == M
+ok = bool(torch.equal(off, ref_off)) and int(scal.cpu()[0]) == M
 report("counts2offsets", 16 * N, call, ok)
 
 tiles = empty((N + 511) // 512, np.int64)
@@ -77,7 +77,7 @@ call()
 ne = (counts_t > 0).to(torch.int64)
 pad = (-N) % 512
 ne_tiles = torch.cat([ne, torch.zeros(pad, dtype=torch.int64, device=dev)]).view(-1, 512).sum(1)
-ok = bool(torch.equal(off2.tensor, ref_off)) and bool(torch.equal(tiles.tensor, ne_tiles))
+ok = bool(torch.equal(off2, ref_off)) and bool(torch.equal(tiles, ne_tiles))
 report("counts2offsets_tiles", 16 * N, call, ok)
 del off2, ne, ne_tiles
 
@@ -85,7 +85,7 @@ c32 = ak.DeviceArray(counts_t.to(torch.int32))
 off3 = empty(N + 1, np.int64)
 call = lambda: _lib.call("jg_counts2offsets", c32.data_ptr(), _lib.JG_I32, N, _vp(off3), _vp(scal), _vp(scal, 1), ws, wsb, st())
 call()
-report("counts2offsets_i32", 12 * N, call, bool(torch.equal(off3.tensor, ref_off)))
+report("counts2offsets_i32", 12 * N, call, bool(torch.equal(off3, ref_off)))
 del c32, off3
 
 # ---- comb offsets -----------------------------------------------------------------------------------------------
@@ -106,7 +106,7 @@ for kind, name, second in ((_lib.COMB_PAIRS, "pairs", None), (_lib.COMB_CROSS, "
     per = ca * (ca + 1) // 2 if second is None else ca * cb
     ref = torch.zeros(Nc + 1, dtype=torch.int64, device=dev)
     torch.cumsum(per, 0, out=ref[1:])
-    report("comb_offsets_" + name, (16 if second is None else 24) * Nc, call, bool(torch.equal(poff.tensor, ref)))
+    report("comb_offsets_" + name, (16 if second is None else 24) * Nc, call, bool(torch.equal(poff, ref)))
     del poff, ref, per
 del ca, cb, oa, ob, oa_d, ob_d
 
@@ -128,14 +128,14 @@ ncnt = empty(N, np.int64)
 
 
 def check_sel():
-    return (int(scal.cpu()[0]) == K and bool(torch.equal(sel.tensor[:K], ref_sel)) and bool(torch.equal(noff.tensor, ref_noff))
-            and bool(torch.equal(ncnt.tensor, newc)))
+    return (int(scal.cpu()[0]) == K and bool(torch.equal(sel[:K], ref_sel)) and bool(torch.equal(noff, ref_noff))
+            and bool(torch.equal(ncnt, newc)))
 
 
-call = lambda: _lib.call("jg_mask_select", pt_dev.data_ptr(), 4, _vp(mask), 0, offd.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
+call = lambda: _lib.call("jg_mask_select", pt_dev.data_ptr(), 4, mask.data_ptr(), 0, offd.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
 call()
 report("mask_select_f32", 4 * M + M + 8 * N + 4 * K + 16 * N, call, check_sel())
-sel.tensor.zero_(); noff.tensor.zero_(); ncnt.tensor.zero_()
+sel.zero_(); noff.zero_(); ncnt.zero_()
 call = lambda: _lib.call("jg_compare_select", pt_dev.data_ptr(), 4, pt_dev.data_ptr(), _lib.JG_F32, _lib.OP["GT"], ctypes.c_double(20.0), 0,
                          offd.data_ptr(), N, _vp(sel), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
 call()
@@ -146,9 +146,9 @@ sel64 = empty(M, np.float64)
 call = lambda: _lib.call("jg_compare_select", pt64.data_ptr(), 8, pt64.data_ptr(), _lib.JG_F64, _lib.OP["GT"], ctypes.c_double(20.0), 0,
                          offd.data_ptr(), N, _vp(sel64), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
 call()
-ok = int(scal.cpu()[0]) == K and bool(torch.equal(sel64.tensor[:K], pt64.tensor[mask_t])) and bool(torch.equal(noff.tensor, ref_noff))
+ok = int(scal.cpu()[0]) == K and bool(torch.equal(sel64[:K], pt64.tensor[mask_t])) and bool(torch.equal(noff, ref_noff))
 report("compare_select_f64", 8 * M + 8 * N + 8 * K + 16 * N, call, ok)
-call = lambda: _lib.call("jg_mask_select", pt64.data_ptr(), 8, _vp(mask), 0, offd.data_ptr(), N, _vp(sel64), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
+call = lambda: _lib.call("jg_mask_select", pt64.data_ptr(), 8, mask.data_ptr(), 0, offd.data_ptr(), N, _vp(sel64), _vp(noff), _vp(ncnt), _vp(scal), ws, wsb, st())
 call()
-ok = int(scal.cpu()[0]) == K and bool(torch.equal(sel64.tensor[:K], pt64.tensor[mask_t])) and bool(torch.equal(noff.tensor, ref_noff))
+ok = int(scal.cpu()[0]) == K and bool(torch.equal(sel64[:K], pt64.tensor[mask_t])) and bool(torch.equal(noff, ref_noff))
 report("mask_select_f64", 8 * M + M + 8 * N + 8 * K + 16 * N, call, ok)

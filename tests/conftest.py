@@ -71,9 +71,13 @@ def reduce_close(op, got, want, offsets, content, rtol):
             bound = np.maximum(rtol, 2.0 * n * np.finfo(want.dtype).eps)
             finite = np.isfinite(want) & np.isfinite(got) & (np.abs(want) > np.finfo(want.dtype).tiny)
             ok |= finite & (np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound * np.abs(want.astype(np.float64)))
-            # a product that over- or underflows does so in both orders only up to the last factor: accept inf / 0 /
-            # subnormal results when the exact (float64, log-domain) magnitude is outside the normal range
-            logmag = np.where(nonempty, np.add.reduceat(np.log2(np.maximum(np.abs(x), 1e-300)), starts), 0.0)
+            # a product whose magnitude leaves the normal range depends on the order legitimately: it overflows to inf
+            # (and inf * 0 = NaN if a zero follows) in one order and not in another, or underflows at a different
+            # factor.  Judge that on the exact log-domain magnitude of the NON-ZERO factors; an event that holds a zero
+            # and cannot overflow is +-0 in every order and must simply match.
+            nz = np.abs(x) > 0
+            logmag = np.where(nonempty, np.add.reduceat(np.where(nz, np.log2(np.where(nz, np.abs(x), 1.0)), 0.0), starts), 0.0)
+            haszero = np.where(nonempty, np.add.reduceat((~nz).astype(np.int64), starts), 0) > 0
             info = np.finfo(want.dtype)
-            ok |= (logmag > info.maxexp - 2) | (logmag < info.minexp + 2)
+            ok |= (logmag > info.maxexp - 2) | (~haszero & (logmag < info.minexp + 2))
     return ok

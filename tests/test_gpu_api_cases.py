@@ -84,7 +84,7 @@ def same(got, want):
 # the evaluation order or on the libm in use (north_star: "float sums and products within rtol"): re-associated
 # reductions and transcendental functions.  Everything else on this path is data movement or correctly rounded IEEE.
 EXACT = [True]
-ORDER_OR_LIBM = re.compile(r"sum|prod|mean|var|std|sqrt|exp|log|sin|cos|tan|power|\*\*|hypot|arctan|arcsin|arccos|cbrt")
+ORDER_OR_LIBM = re.compile(r"sum|prod|mean|var|std|moment|sqrt|exp|log|sin|cos|tan|power|\*\*|hypot|arctan|arcsin|arccos|cbrt")
 
 
 def evaluate(expr, scope, code=None):
