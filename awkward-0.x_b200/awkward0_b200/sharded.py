@@ -140,39 +140,32 @@ class DeviceTotals(object):
     """Whole-array totals that never leave the device until the end of the step.
 
     Each partial (the sum of per-event sums, the number of selected elements, the number of leading objects ...) is
-    already in HBM where a kernel epilogue wrote it -- a 1-element result of `jg_flat_reduce`, the `total` word of a
-    selection / arg-reduction (`JaggedArray._total_dev`).  `add_*` copies its 8 bytes device-to-device into one slot of
-    a small buffer; `finish()` exchanges the buffer with ONE collective (`all_gather_into_tensor`: mixed integer / float
-    slots and sum / max / min reductions ride in the same message as raw 64-bit words) and reads it back with ONE
+    already in HBM where a kernel epilogue wrote it -- a 1-element result of `jg_flat_reduce`, the last entry of a
+    result's offsets (the number of selected elements, of leading objects ...).  `add_*` only remembers the device
+    scalar; `finish()` packs them, exchanges the pack with ONE collective (`all_gather_into_tensor`: mixed integer /
+    float slots and sum / max / min reductions ride in the same message as raw bytes) and reads it back with ONE
     device-to-host copy.  Replaces one D2H per partial plus an H2D, an all_reduce and a D2H per reduction kind
     (chunked.py:596-597 sums per-chunk results on the host the same way).
     """
 
-    def __init__(self, group=None, capacity=16):
+    def __init__(self, group=None, capacity=None):
         self.group = group
         self.world, self.rank = _world(group)
         self.device = _device_for(group)
-        self.buf = torch.zeros(capacity, dtype=torch.int64, device=self.device)
-        self.slots = []                          # (kind, numpy dtype)
+        self.parts = []                          # (tensor on the device, kind, numpy dtype), in slot order
 
     def _add(self, value, kind):
-        i = len(self.slots)
-        if i >= self.buf.numel():
-            raise ValueError("DeviceTotals is full")
         if hasattr(value, "tensor"):
             value = value.tensor
         if torch.is_tensor(value):
-            t = value.reshape(-1)[:1]
-            if t.dtype.is_floating_point:
-                t, dt = t.to(torch.float64), numpy.dtype(numpy.float64)
-            else:
-                t, dt = t.to(torch.int64), numpy.dtype(numpy.int64)
-            self.buf[i:i + 1].copy_(t.to(self.device).view(torch.int64), non_blocking=True)
+            t = value.reshape(-1)[:1].to(self.device)
+            if t.dtype == torch.bool:
+                t = t.to(torch.int64)
         else:                                    # a host number (sizes the host already had to know)
-            dt = numpy.dtype(numpy.int64 if isinstance(value, (int, numpy.integer)) else numpy.float64)
-            self.buf[i:i + 1].copy_(torch.from_numpy(numpy.array([value], dtype=dt).view(numpy.int64)), non_blocking=True)
-        self.slots.append((kind, dt))
-        return i
+            dt = torch.int64 if isinstance(value, (int, numpy.integer)) else torch.float64
+            t = torch.tensor([value], dtype=dt).to(self.device, non_blocking=True)
+        self.parts.append((t, kind, numpy.dtype(str(t.dtype).replace("torch.", ""))))
+        return len(self.parts) - 1
 
     def add_sum(self, value):
         return self._add(value, "sum")
@@ -184,19 +177,38 @@ class DeviceTotals(object):
         return self._add(value, "min")
 
     def finish(self):
-        """-> list of python numbers, one per slot, reduced over all ranks."""
-        k = len(self.slots)
+        """-> list of python numbers, one per slot, reduced over all ranks.  The partials are concatenated dtype by dtype
+        (one tiny launch per dtype, no conversion: integers stay exact, a float32 sum stays the float32 the kernel wrote),
+        packed as bytes, exchanged with one all_gather and read back with one copy."""
+        if not self.parts:
+            return []
+        by_dtype = {}
+        for j, (_, _, dt) in enumerate(self.parts):
+            by_dtype.setdefault(str(dt), []).append(j)
+        groups, layout, at = [], {}, 0
+        for name in sorted(by_dtype):
+            slots = by_dtype[name]
+            dt = self.parts[slots[0]][2]
+            groups.append(torch.cat([self.parts[j][0] for j in slots]).view(torch.uint8))
+            for k, j in enumerate(slots):
+                layout[j] = (at + k * dt.itemsize, dt)
+            at += len(slots) * dt.itemsize
+        mine = groups[0] if len(groups) == 1 else torch.cat(groups)
+        nbytes = int(mine.numel())
         if self.world > 1:
-            flat = torch.empty(self.world * k, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(flat, self.buf[:k].contiguous(), group=self.group)
-            every = flat.view(self.world, k)
+            flat = torch.empty(self.world * nbytes, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(flat, mine.contiguous(), group=self.group)
         else:
-            every = self.buf[:k].view(1, k)
-        host = every.cpu().numpy()                       # the step's ONE device-to-host copy
+            flat = mine
+        host = flat.cpu().numpy().reshape(self.world, nbytes)          # the step's ONE device-to-host copy
         out = []
-        for j, (kind, dt) in enumerate(self.slots):
-            col = numpy.ascontiguousarray(host[:, j]).view(dt)
-            out.append({"sum": col.sum, "max": col.max, "min": col.min}[kind]().item())
+        for j, (_, kind, _) in enumerate(self.parts):
+            off, dt = layout[j]
+            col = numpy.ascontiguousarray(host[:, off:off + dt.itemsize]).view(dt).reshape(-1)
+            if kind == "sum":
+                out.append(col.sum(dtype=numpy.float64 if dt.kind == "f" else numpy.int64).item())
+            else:
+                out.append((col.max() if kind == "max" else col.min()).item())
         return out
 
 

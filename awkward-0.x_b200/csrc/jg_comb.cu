@@ -108,6 +108,20 @@ __device__ __forceinline__ int64_t largest_binom_le(int64_t m, int k, int64_t n)
     return c;
 }
 
+// C(c, q) for c <= 64 in 32-bit arithmetic (C(64, 5) = 7 624 512; the falling factorial 64*63*62*61*60 < 2^32).
+// c < q gives 0: one of the factors is zero.
+__device__ __forceinline__ uint32_t binom32(uint32_t c, int q) {
+    switch (q) {
+        case 1: return c;
+        case 2: return c * (c - 1) / 2;
+        case 3: return c * (c - 1) * (c - 2) / 6;
+        case 4: return c * (c - 1) * (c - 2) * (c - 3) / 24;
+        default: return c * (c - 1) * (c - 2) * (c - 3) * (c - 4) / 120;
+    }
+}
+
+constexpr int kChooseSmall = 64;        // events up to this long un-rank k-combinations by a short downward walk
+
 constexpr int kCombPositions = 8192;    // output positions of a tile the on-chip owner table covers
 
 struct CombIndex {
@@ -132,6 +146,24 @@ __device__ __forceinline__ CombIndex unrank(int64_t m, int64_t na, int64_t nb, i
         }
     } else {
         // columns are i1 < i2 < ... < ik; the largest index is found first
+        if (na <= kChooseSmall) {
+            // short events (every collider event): walk c down from the previous column's index -- at most n + k steps of
+            // 32-bit integer arithmetic in total, where the closed-form estimates below cost a double-precision
+            // sqrt / cbrt / pow per column (jagged.py:1131-1144 `root2/3/4`)
+            uint32_t m32 = static_cast<uint32_t>(m), c = static_cast<uint32_t>(na);
+            for (int q = k; q >= 2; --q) {
+                --c;
+                uint32_t bq = binom32(c, q);
+                while (bq > m32) {
+                    --c;
+                    bq = binom32(c, q);
+                }
+                r.v[q - 1] = c;
+                m32 -= bq;
+            }
+            r.v[0] = m32;
+            return r;
+        }
         for (int q = k; q >= 2; --q) {
             const int64_t c = largest_binom_le(m, q, na);
             r.v[q - 1] = c;

@@ -20,17 +20,16 @@
 //     tile order (one warp per spanning event, lanes stride the tiles), so a single event of 2^31 elements is spread
 //     over half a million CTAs instead of one.
 //
-// Selection (a[mask], a[a > c]) is a flat stream compaction plus "rank at the event boundaries": the persistent
-// lagged kernel of jg_lag.cuh over element tiles; an owned event reads its new offset from the tile's on-chip
-// per-position prefix.  parents / localindex / broadcast build the owner table of a tile from the events that start
+// Selection (a[mask], a[a > c]) is a flat stream compaction plus "rank at the event boundaries": tile totals, their
+// scan, then the compaction of every staged tile, in which an owned event reads its new offset from the tile's on-chip
+// per-position prefix (three launches that never wait on another CTA, as in jg_select.cu).  parents / localindex / broadcast build the owner table of a tile from the events that start
 // in it (scatter + running maximum over 32-bit relative event numbers).
 #include <stdlib.h>
 
 #include <type_traits>
 
-#include "jg_compact.cuh"
-#include "jg_lag.cuh"
 #include "jg_reduce.cuh"
+#include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -40,6 +39,10 @@ constexpr int kElemStageBytes = 16384;
 constexpr int kElemWarpSeg = 64;        // segments at least this long: one warp
 constexpr int kElemCtaSeg = 1024;       // segments at least this long: the whole CTA
 constexpr int kElemWarps = kElemThreads / kWarp;
+// the reductions run 128-thread CTAs: a tile's lifetime is dominated by the latency of its one bulk copy, so what counts
+// is how many 16 KB tiles an SM has in flight (13 CTAs of 128 threads fit the shared memory, 8 CTAs of 256 the threads)
+constexpr int kElemRedThreads = 128;
+constexpr int kElemRedWarps = kElemRedThreads / kWarp;
 
 template <typename T>
 struct ElemTile {
@@ -126,7 +129,7 @@ __device__ __forceinline__ Partial<A> smem_strided_partial(const T *__restrict__
 }
 
 template <int OP, typename T, typename A>
-__global__ void __launch_bounds__(kElemThreads)
+__global__ void __launch_bounds__(kElemRedThreads)
 segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                       const int64_t *__restrict__ first_event, A *__restrict__ out, A *__restrict__ carry) {
     constexpr int ET = ElemTile<T>::ET;
@@ -135,7 +138,7 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
     __shared__ uint64_t s_bar;
     __shared__ int64_t s_list[ET / kElemWarpSeg + 2];       // event numbers of the long segments (-1: the entering one)
     __shared__ int s_nlist;
-    __shared__ Partial<A> s_part[kElemWarps];
+    __shared__ Partial<A> s_part[kElemRedWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ElemRange r = elem_range(offsets, n, first_event, blockIdx.x, ET);
     const int L = static_cast<int>(r.hi - r.lo);
@@ -167,7 +170,7 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
     }
     // owned events: short ones by their own thread, sequentially (the reference's order)
 #pragma unroll 1
-    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemThreads) {
+    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemRedThreads) {
         const int64_t a64 = __ldg(offsets + e), b64 = __ldg(offsets + e + 1);
         const int a = static_cast<int>(a64 - r.lo);
         const int b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
@@ -199,13 +202,13 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
             b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
         }
         if (b - a >= kElemCtaSeg) {
-            Partial<A> p = shuffle_merge<OP, T, A>(smem_strided_partial<OP, T, A>(sm, a, b, tid, kElemThreads, r.lo));
+            Partial<A> p = shuffle_merge<OP, T, A>(smem_strided_partial<OP, T, A>(sm, a, b, tid, kElemRedThreads, r.lo));
             __syncthreads();
             if (lane == 0) s_part[warp] = p;
             __syncthreads();
             if (warp == 0) {
                 Partial<A> w;
-                if (lane < kElemWarps) w = s_part[lane];
+                if (lane < kElemRedWarps) w = s_part[lane];
                 else { w.has = false; w.val = R::identity(); w.pos = -1; }
                 w = shuffle_merge<OP, T, A>(w);
                 if (lane == 0) {
@@ -214,7 +217,7 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
                     else out[e] = v;
                 }
             }
-        } else if ((q & (kElemWarps - 1)) == warp) {
+        } else if ((q & (kElemRedWarps - 1)) == warp) {
             Partial<A> p = shuffle_merge<OP, T, A>(smem_strided_partial<OP, T, A>(sm, a, b, lane, kWarp, r.lo));
             if (lane == 0) {
                 const A v = p.has ? p.val : R::identity();
@@ -271,23 +274,35 @@ segreduce_elem_fix_kernel(const int64_t *__restrict__ offsets, int64_t n, const 
 template <bool ISMIN, typename T>
 __device__ __forceinline__ ArgPartial<T> smem_arg_strided(const T *__restrict__ sm, int a, int b, int first, int step,
                                                           int64_t pos0) {
-    ArgPartial<T> p;
-    p.idx = -1;
-    p.val = T(0);
-#pragma unroll 1
+    // (32-bit tile-relative index in the loop; the running best starts at the identity so that "strictly better" needs no
+    // first-element test; a segment whose non-NaN values all equal the identity takes the exact loop)
+    T best = ISMIN ? min_identity<T>() : max_identity<T>();
+    int jbest = -1;
+#pragma unroll 2
     for (int j = a + first; j < b; j += step) {
         const T x = sm[j];
-        if (is_nan(x)) continue;
-        if (p.idx < 0 || (ISMIN ? (x < p.val) : (x > p.val))) {
-            p.val = x;
-            p.idx = pos0 + j;               // absolute content position
+        if (ISMIN ? (x < best) : (x > best)) {
+            best = x;
+            jbest = j;
         }
     }
+    if (jbest < 0) {
+#pragma unroll 1
+        for (int j = a + first; j < b; j += step)
+            if (!is_nan(sm[j])) {
+                jbest = j;
+                best = sm[j];
+                break;
+            }
+    }
+    ArgPartial<T> p;
+    p.val = jbest < 0 ? T(0) : best;
+    p.idx = jbest < 0 ? -1 : pos0 + jbest;          // absolute content position
     return p;
 }
 
 template <bool ISMIN, typename T>
-__global__ void __launch_bounds__(kElemThreads)
+__global__ void __launch_bounds__(kElemRedThreads)
 segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                    const int64_t *__restrict__ first_event, int64_t *__restrict__ best, T *__restrict__ best_value,
                    int64_t *__restrict__ carry_idx, T *__restrict__ carry_val) {
@@ -296,7 +311,7 @@ segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ of
     __shared__ uint64_t s_bar;
     __shared__ int64_t s_list[ET / kElemWarpSeg + 2];
     __shared__ int s_nlist;
-    __shared__ ArgPartial<T> s_part[kElemWarps];
+    __shared__ ArgPartial<T> s_part[kElemRedWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ElemRange r = elem_range(offsets, n, first_event, blockIdx.x, ET);
     const int L = static_cast<int>(r.hi - r.lo);
@@ -331,7 +346,7 @@ segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ of
         emit(-1, smem_arg_strided<ISMIN, T>(sm, 0, in_len, 0, 1, r.lo));
     }
 #pragma unroll 1
-    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemThreads) {
+    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemRedThreads) {
         const int64_t a64 = __ldg(offsets + e), b64 = __ldg(offsets + e + 1);
         const int a = static_cast<int>(a64 - r.lo);
         const int b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
@@ -356,18 +371,18 @@ segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ of
             b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
         }
         if (b - a >= kElemCtaSeg) {
-            ArgPartial<T> p = arg_shuffle<ISMIN, T>(smem_arg_strided<ISMIN, T>(sm, a, b, tid, kElemThreads, r.lo));
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(smem_arg_strided<ISMIN, T>(sm, a, b, tid, kElemRedThreads, r.lo));
             __syncthreads();
             if (lane == 0) s_part[warp] = p;
             __syncthreads();
             if (warp == 0) {
                 ArgPartial<T> w;
-                if (lane < kElemWarps) w = s_part[lane];
+                if (lane < kElemRedWarps) w = s_part[lane];
                 else { w.idx = -1; w.val = T(0); }
                 w = arg_shuffle<ISMIN, T>(w);
                 if (lane == 0) emit(e, w);
             }
-        } else if ((q & (kElemWarps - 1)) == warp) {
+        } else if ((q & (kElemRedWarps - 1)) == warp) {
             ArgPartial<T> p = arg_shuffle<ISMIN, T>(smem_arg_strided<ISMIN, T>(sm, a, b, lane, kWarp, r.lo));
             if (lane == 0) emit(e, p);
         }
@@ -526,59 +541,58 @@ __device__ __forceinline__ int elem_count16(const SEL &sel, int4 v) {
     }
 }
 
-constexpr int kElemSelectWindow = 2048;      // tiles per window: ~32 MB between a tile's two reads
+// count: one warp per tile (16-byte loads, unaligned head and tail item by item) -> tile_totals
+template <class SEL>
+__global__ void __launch_bounds__(kElemThreads)
+select_elem_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
+                         const int64_t *__restrict__ offsets, int64_t n, int64_t et, int64_t ntiles,
+                         int64_t *__restrict__ tile_totals) {
+    using E = typename SEL::Elem;
+    constexpr int PERV = 16 / static_cast<int>(sizeof(E));
+    const int lane = threadIdx.x & 31;
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * kElemWarps + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int64_t o0 = __ldg(offsets), end = __ldg(offsets + n);
+    const int64_t lo = o0 + t * et;
+    const int64_t hi = lo + et < end ? lo + et : end;
+    const int L = hi > lo ? static_cast<int>(hi - lo) : 0;
+    const E *m = mask + lo + mask_shift;
+    int cnt = 0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    int head = static_cast<int>(((16 - (addr & 15)) & 15) / sizeof(E));
+    if (head > L) head = L;
+    if (lane < head) cnt += sel.test(m[lane]);
+    const int nvec = (L - head) / PERV;
+    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
+#pragma unroll 4
+    for (int i = lane; i < nvec; i += kWarp) cnt += elem_count16(sel, __ldcs(mv + i));
+    const int tail0 = head + nvec * PERV;
+    if (tail0 + lane < L) cnt += sel.test(m[tail0 + lane]);
+    cnt = warp_reduce_add(cnt);
+    if (lane == 0) tile_totals[t] = cnt;
+}
 
+// fill: the tile's run staged by TMA, element-parallel ballot / popc compaction (a warp's stores are consecutive), then
+// every owned event reads its new offset (and, when it ends inside the tile, its count) from the per-position prefix
 template <typename V, class SEL, bool SAME>
-__global__ void __launch_bounds__(kElemThreads, 5)
-select_elem_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
-                   int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n,
-                   const int64_t *__restrict__ first_event, V *__restrict__ out, int64_t *__restrict__ new_offsets,
-                   int64_t *__restrict__ new_counts, int64_t *__restrict__ total, LagDesc lag, const LagSchedule sched) {
+__global__ void __launch_bounds__(kElemThreads, 6)
+select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
+                        int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n,
+                        const int64_t *__restrict__ first_event, V *__restrict__ out, int64_t *__restrict__ new_offsets,
+                        int64_t *__restrict__ new_counts, const int64_t *__restrict__ tile_bases, int64_t ntiles) {
     using E = typename SEL::Elem;
     constexpr int ET = ElemTile<V>::ET;
-    constexpr int PERV = 16 / static_cast<int>(sizeof(E));
-    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32 + 512];      // (+ one row of slack)
+    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32];
     __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : ET * sizeof(E) + 32];
-    __shared__ __align__(16) uint16_t s_pfx_raw[ET + 8 + 128];
+    __shared__ uint16_t s_pfx[ET + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[kElemWarps + 1];
-    __shared__ int64_t s_base;
-    __shared__ uint32_t s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ntiles = sched.ntiles;
-    uint32_t tile, tile_end;
-    const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile, tile_end);
-    if (role < 0) return;
+    const int64_t tile = blockIdx.x;
     const int64_t o0 = __ldg(offsets), end = __ldg(offsets + n);
-
-    if (role == 0) {
-        // ---------------- count: one warp per tile (16-byte loads; the run stays in L2) ---------------------------
-        const uint32_t t = tile + warp;
-        if (t >= tile_end) return;
-        const int64_t lo = o0 + static_cast<int64_t>(t) * ET;
-        const int64_t hi = lo + ET < end ? lo + ET : end;
-        const int L = hi > lo ? static_cast<int>(hi - lo) : 0;
-        const E *m = mask + lo + mask_shift;
-        int cnt = 0;
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-        int head = static_cast<int>(((16 - (addr & 15)) & 15) / sizeof(E));
-        if (head > L) head = L;
-        if (lane < head) cnt += sel.test(m[lane]);
-        const int nvec = (L - head) / PERV;
-        const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-#pragma unroll 4
-        for (int i = lane; i < nvec; i += kWarp) cnt += elem_count16(sel, __ldg(mv + i));
-        const int tail0 = head + nvec * PERV;
-        if (tail0 + lane < L) cnt += sel.test(m[tail0 + lane]);
-        cnt = warp_reduce_add(cnt);
-        if (lane == 0) lag_publish(lag, t, cnt);
-        return;
-    }
-    const int64_t lo = o0 + static_cast<int64_t>(tile) * ET;
+    const int64_t lo = o0 + tile * ET;
     const int64_t hi = lo + ET < end ? lo + ET : end;
     const int L = hi > lo ? static_cast<int>(hi - lo) : 0;
-
-    // ---------------- fill ----------------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -589,10 +603,8 @@ select_elem_kernel(const SEL sel, const V *__restrict__ content, const typename 
         }
     }
     const int64_t ev_lo = __ldg(first_event + tile), ev_hi = __ldg(first_event + tile + 1);
-    if (warp == kElemWarps - 1) {
-        const int64_t b = lag_prefix(lag, tile);
-        if (lane == 0) s_base = b;
-    }
+    const int64_t base = __ldg(tile_bases + tile);
+    if (tile == ntiles - 1 && tid == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
     __syncthreads();
     const V *cv = nullptr;
     const E *mv = nullptr;
@@ -609,40 +621,41 @@ select_elem_kernel(const SEL sel, const V *__restrict__ content, const typename 
         }
     }
     __syncthreads();
-    // 16-byte rows (jg_compact.cuh): positions are counted from the 16-byte boundary below the first element
-    constexpr int ROW = RowCompact<V>::ROW;
-    const int lead = L > 0 ? static_cast<int>((reinterpret_cast<uintptr_t>(cv) & 15) / sizeof(V)) : 0;
-    const V *cvb = cv - lead;
-    const int rows_total = L > 0 ? (lead + L + ROW - 1) / ROW : 0;
+    const int rows_total = (L + 31) >> 5;
     const int rows_per_warp = (rows_total + kElemWarps - 1) / kElemWarps;
-    const int row_begin = min(rows_total, warp * rows_per_warp);
-    const int row_end = min(rows_total, row_begin + rows_per_warp);
-    const int cnt = rows_count<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end);
+    const int p_begin = min(L, warp * rows_per_warp * 32);
+    const int p_end = min(L, p_begin + rows_per_warp * 32);
+    int cnt = 0;
+    for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
+    cnt = warp_reduce_add(cnt);
     if (lane == 0) s_scan[warp] = cnt;
     __syncthreads();
     if (warp == 0) {
         int w = lane < kElemWarps ? s_scan[lane] : 0;
         int wi = warp_incl_scan_add(w, lane);
         if (lane < kElemWarps) s_scan[lane] = wi - w;
-        if (lane == kElemWarps - 1) s_pfx_raw[lead + L] = static_cast<uint16_t>(wi);
+        if (lane == kElemWarps - 1) s_pfx[L] = static_cast<uint16_t>(wi);
     }
     if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);
     __syncthreads();
-    const int64_t base = s_base;
-    rows_compact<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end, s_scan[warp], out + base, s_pfx_raw);
+    int run = s_scan[warp];
+    V *dst = out + base;
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+        const int p = p0 + lane;
+        const bool on = p < p_end && sel.test(mv[p]);
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        const int slot = run + __popc(bal & ((1u << lane) - 1u));
+        if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+        if (on) dst[slot] = cv[p];
+        run += __popc(bal);
+    }
     __syncthreads();
-    const uint16_t *s_pfx = s_pfx_raw + lead;
-    // owned events read their new offset from the per-position prefix; an event that ends inside the tile its count too
 #pragma unroll 1
     for (int64_t e = ev_lo + tid; e < ev_hi; e += kElemThreads) {
         const int64_t a = __ldg(offsets + e) - lo, b = __ldg(offsets + e + 1) - lo;
         const int first = s_pfx[a];
         new_offsets[e] = base + first;
         if (new_counts && b <= L) new_counts[e] = static_cast<int>(s_pfx[b]) - first;
-    }
-    if (tile == ntiles - 1 && tid == 0) {
-        new_offsets[n] = base + s_pfx[L];
-        if (total) *total = base + s_pfx[L];
     }
 }
 
@@ -692,7 +705,7 @@ static int launch_reduce_elem(const void *content, const int64_t *offsets, int64
     const size_t need = static_cast<size_t>(p.ntiles) * sizeof(A);
     JG_REQUIRE(p.rest_bytes >= need, "jg_segreduce_elem: workspace too small");
     A *carry = reinterpret_cast<A *>(p.rest);
-    segreduce_elem_kernel<OP, T, A><<<static_cast<unsigned>(p.ntiles), kElemThreads, 0, s>>>(
+    segreduce_elem_kernel<OP, T, A><<<static_cast<unsigned>(p.ntiles), kElemRedThreads, 0, s>>>(
         static_cast<const T *>(content), offsets, n, p.first_event, static_cast<A *>(out), carry);
     int rc = check_launch("segreduce_elem_kernel");
     if (rc) return rc;
@@ -724,12 +737,12 @@ static int dispatch_arg_elem(int is_min, const void *content, const int64_t *off
     T *carry_val = reinterpret_cast<T *>(p.rest + idx_bytes);
     const unsigned g = static_cast<unsigned>(p.ntiles), gf = static_cast<unsigned>(ceil_div(p.ntiles, kElemWarps));
     if (is_min) {
-        segarg_elem_kernel<true, T><<<g, kElemThreads, 0, s>>>(static_cast<const T *>(content), offsets, n, p.first_event, best,
+        segarg_elem_kernel<true, T><<<g, kElemRedThreads, 0, s>>>(static_cast<const T *>(content), offsets, n, p.first_event, best,
                                                               static_cast<T *>(best_value), carry_idx, carry_val);
         segarg_elem_fix_kernel<true, T><<<gf, kElemThreads, 0, s>>>(offsets, n, p.first_event, p.ntiles, best,
                                                                    static_cast<T *>(best_value), carry_idx, carry_val);
     } else {
-        segarg_elem_kernel<false, T><<<g, kElemThreads, 0, s>>>(static_cast<const T *>(content), offsets, n, p.first_event, best,
+        segarg_elem_kernel<false, T><<<g, kElemRedThreads, 0, s>>>(static_cast<const T *>(content), offsets, n, p.first_event, best,
                                                                static_cast<T *>(best_value), carry_idx, carry_val);
         segarg_elem_fix_kernel<false, T><<<gf, kElemThreads, 0, s>>>(offsets, n, p.first_event, p.ntiles, best,
                                                                     static_cast<T *>(best_value), carry_idx, carry_val);
@@ -741,19 +754,24 @@ template <typename V, class SEL, bool SAME>
 static int launch_select_elem(const SEL &sel, const void *content, const typename SEL::Elem *mask, int64_t mask_shift,
                               const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                               int64_t *total, const ElemPlan &p, cudaStream_t s) {
-    const size_t need = lag_ws_bytes(p.ntiles);
-    JG_REQUIRE(p.rest_bytes >= need, "jg_select_elem: workspace too small (%zu < %zu)", p.rest_bytes, need);
-    JG_REQUIRE(p.ntiles < (1ll << 30), "jg_select_elem: too many tiles");
-    cudaError_t e = cudaMemsetAsync(p.rest, 0, need, s);
-    if (e != cudaSuccess) {
-        set_error("jg_select_elem: cudaMemsetAsync: %s", cudaGetErrorString(e));
-        return -1;
-    }
-    const LagSchedule sched = lag_schedule(p.ntiles, kElemSelectWindow, kElemWarps);
-    select_elem_kernel<V, SEL, SAME><<<static_cast<unsigned>(lag_grid(sched)), kElemThreads, 0, s>>>(
+    // three launches, none of which waits on another CTA (see jg_select.cu): tile totals, their scan, the compaction
+    const size_t arr = align256(static_cast<size_t>(p.ntiles + 2) * 8);
+    const size_t scan_need = lag_ws_bytes(ceil_div(p.ntiles, kScanTmaThreads * kScanTmaItems) + 1) + sizeof(LookbackWs) +
+                             static_cast<size_t>(ceil_div(p.ntiles, kScanTmaThreads * kScanTmaItems) + 1) * 8;
+    JG_REQUIRE(p.rest_bytes >= 2 * arr + scan_need + 256, "jg_select_elem: workspace too small (%zu < %zu)", p.rest_bytes,
+               2 * arr + scan_need + 256);
+    int64_t *totals = reinterpret_cast<int64_t *>(p.rest);
+    int64_t *bases = reinterpret_cast<int64_t *>(p.rest + arr);
+    select_elem_count_kernel<SEL><<<static_cast<unsigned>(ceil_div(p.ntiles, kElemWarps)), kElemThreads, 0, s>>>(
+        sel, mask, mask_shift, offsets, n, p.et, p.ntiles, totals);
+    int rc = check_launch("select_elem_count_kernel");
+    if (rc) return rc;
+    rc = launch_scan_array(totals, p.ntiles, bases, total, nullptr, p.rest + 2 * arr, p.rest_bytes - 2 * arr, s);
+    if (rc) return rc;
+    select_elem_fill_kernel<V, SEL, SAME><<<static_cast<unsigned>(p.ntiles), kElemThreads, 0, s>>>(
         sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, p.first_event, static_cast<V *>(out), new_offsets,
-        new_counts, total, lag_carve(p.rest, p.ntiles), sched);
-    int rc = check_launch("select_elem_kernel");
+        new_counts, bases, p.ntiles);
+    rc = check_launch("select_elem_fill_kernel");
     if (rc || new_counts == nullptr) return rc;
     select_elem_fix_kernel<<<static_cast<unsigned>(ceil_div(p.ntiles, 256)), 256, 0, s>>>(offsets, p.first_event, p.ntiles, p.et,
                                                                                         new_offsets, new_counts);
@@ -789,8 +807,8 @@ size_t jg_elem_workspace_bytes(int64_t content_len, int itemsize) {
     if (content_len < 0) content_len = 0;
     if (itemsize < 1) itemsize = 1;
     const size_t tiles = static_cast<size_t>(content_len / elem_tile_items(itemsize < 4 ? 4 : itemsize) + 2);
-    // first_event + (carry index + carry value | lagged descriptors)
-    return align256((tiles + 1) * 8) + 2 * align256(tiles * 8) + lag_ws_bytes(static_cast<int64_t>(tiles)) + 4096;
+    // first_event + (carry index + carry value | tile totals + tile bases + the scratch of their scan)
+    return align256((tiles + 1) * 8) + 2 * align256((tiles + 2) * 8) + lag_ws_bytes(static_cast<int64_t>(tiles)) + 4096;
 }
 
 int jg_segreduce_elem(const void *content, int dtype, const int64_t *offsets, int64_t n, int op, void *out,

@@ -110,6 +110,7 @@ __device__ __forceinline__ int lag_role(uint32_t ticket, const LagSchedule &s, u
 
 // all threads: this CTA's ticket (one atomic by thread 0, broadcast through shared memory)
 __device__ __forceinline__ uint32_t lag_take_ticket(const LagDesc &d, uint32_t *s_ticket) {
+    if (d.ticket == nullptr) return blockIdx.x;          // in-order dispatch of a 1-D grid (see launch_scan_win)
     if (threadIdx.x == 0) *s_ticket = atomicAdd(d.ticket, 1u);
     __syncthreads();
     return *s_ticket;

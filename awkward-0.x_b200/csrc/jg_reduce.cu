@@ -19,8 +19,10 @@
 
 namespace jg {
 
+// (launch bounds = the residency shared memory allows: the long-event paths below must not cost the staged path a CTA
+// through register allocation, profiles/r1_owner_table_and_launch_bounds.md)
 template <int OP, typename T, typename A, int STAGE_BYTES>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, STAGE_BYTES > 16384 ? 6 : 8)
 segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                  A *__restrict__ out) {
     __shared__ int64_t s_off[kTileEvents + 1];
@@ -149,7 +151,7 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
 // argmin / argmax: best[i] = local index of the FIRST extreme non-NaN element, -1 if the event has none.
 // ------------------------------------------------------------------------------------------------------------
 template <bool ISMIN, typename T, int STAGE_BYTES>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, STAGE_BYTES > 16384 ? 6 : 8)
 segarg_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
               int64_t *__restrict__ best, T *__restrict__ best_value, int64_t *__restrict__ tile_totals) {
     __shared__ int64_t s_off[kTileEvents + 1];
@@ -271,7 +273,7 @@ count_nonempty_kernel(const int64_t *__restrict__ offsets, int64_t n, int64_t nt
 }
 
 template <bool ISMIN, typename T, int STAGE_BYTES>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, STAGE_BYTES > 16384 ? 5 : 8)
 segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                      const int64_t *__restrict__ tile_bases, int64_t *__restrict__ out_offsets,
                      int64_t *__restrict__ out_index, T *__restrict__ out_value, int32_t *__restrict__ status,
@@ -381,7 +383,7 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
         for (int ev = warp; ev < tile.nev; ev += NW) {
             const int64_t ea = s_off[ev], eb = s_off[ev + 1];
             if (eb - ea >= kBlockEventMin) continue;
-            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, ea, eb, lane, kWarp));
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T, 2>(content, ea, eb, lane, kWarp));
             if (lane == 0) {
                 s_idx64[ev] = p.idx;
                 s_val[ev] = p.val;
@@ -390,7 +392,7 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
         for (int ev = 0; ev < tile.nev; ++ev) {
             const int64_t ea = s_off[ev], eb = s_off[ev + 1];
             if (eb - ea < kBlockEventMin) continue;
-            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T>(content, ea, eb, threadIdx.x, kTileThreads));
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T, 2>(content, ea, eb, threadIdx.x, kTileThreads));
             __syncthreads();
             if (lane == 0) s_part[warp] = p;
             __syncthreads();

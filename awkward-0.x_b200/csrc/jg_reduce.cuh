@@ -78,7 +78,7 @@ struct Red {
     }
 };
 
-constexpr int kBlockEventMin = 1 << 15;   // events at least this long are reduced by the whole CTA
+constexpr int kBlockEventMin = 1 << 11;   // events at least this long are reduced by the whole CTA (a warp alone keeps too few loads in flight)
 
 // partial result of a lane/warp over a strided subset; `pos` = position of the element that produced a
 // min/max value (needed only to reproduce "later wins on ties" exactly for +-0.0)
@@ -124,24 +124,39 @@ __device__ __forceinline__ Partial<A> shuffle_merge(Partial<A> p) {
 template <int OP, typename T, typename A>
 __device__ __forceinline__ Partial<A> strided_partial(const T *__restrict__ content, int64_t a, int64_t b, int first,
                                                       int step) {
+    // four independent loads in flight per thread: a long event is read by few threads, and one load per iteration
+    // makes every iteration a full memory round trip (a 37 k-element event took a warp 0.8 ms that way)
+    constexpr int U = 4;
     Partial<A> p;
     p.has = false;
     p.val = Red<OP, T, A>::identity();
     p.pos = -1;
-    for (int64_t j = a + first; j < b; j += step) {
-        const A x = Red<OP, T, A>::lift(__ldcs(content + j));
-        if (!p.has) {
-            p.val = x;
-            p.pos = j;
-            p.has = true;
-        } else if constexpr (OP == JG_MIN || OP == JG_MAX) {
-            const bool keep = (OP == JG_MIN) ? (p.val < x) : (p.val > x);
-            if (!keep) {
+#pragma unroll 1
+    for (int64_t j0 = a + first; j0 < b; j0 += static_cast<int64_t>(U) * step) {
+        T raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + static_cast<int64_t>(u) * step;
+            if (j < b) raw[u] = __ldcs(content + j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + static_cast<int64_t>(u) * step;
+            if (j >= b) break;
+            const A x = Red<OP, T, A>::lift(raw[u]);
+            if (!p.has) {
                 p.val = x;
                 p.pos = j;
+                p.has = true;
+            } else if constexpr (OP == JG_MIN || OP == JG_MAX) {
+                const bool keep = (OP == JG_MIN) ? (p.val < x) : (p.val > x);
+                if (!keep) {
+                    p.val = x;
+                    p.pos = j;
+                }
+            } else {
+                p.val = Red<OP, T, A>::combine(p.val, x);
             }
-        } else {
-            p.val = Red<OP, T, A>::combine(p.val, x);
         }
     }
     return p;
@@ -176,18 +191,30 @@ __device__ __forceinline__ ArgPartial<T> arg_shuffle(ArgPartial<T> p) {
     return p;
 }
 
-template <bool ISMIN, typename T>
+template <bool ISMIN, typename T, int U = 4>      // U independent loads in flight per thread (see strided_partial)
 __device__ __forceinline__ ArgPartial<T> arg_strided(const T *__restrict__ content, int64_t a, int64_t b, int first,
                                                      int step) {
     ArgPartial<T> p;
     p.idx = -1;
     p.val = T(0);
-    for (int64_t j = a + first; j < b; j += step) {
-        const T x = __ldcs(content + j);
-        if (is_nan(x)) continue;
-        if (p.idx < 0 || (ISMIN ? (x < p.val) : (x > p.val))) {
-            p.val = x;
-            p.idx = j - a;
+#pragma unroll 1
+    for (int64_t j0 = a + first; j0 < b; j0 += static_cast<int64_t>(U) * step) {
+        T raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + static_cast<int64_t>(u) * step;
+            if (j < b) raw[u] = __ldcs(content + j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t j = j0 + static_cast<int64_t>(u) * step;
+            if (j >= b) break;
+            const T x = raw[u];
+            if (is_nan(x)) continue;
+            if (p.idx < 0 || (ISMIN ? (x < p.val) : (x > p.val))) {
+                p.val = x;
+                p.idx = j - a;
+            }
         }
     }
     return p;

@@ -421,30 +421,33 @@ scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile, tile_end);
     if (role < 0) return;
 
-    if (role == 0) {
-        // ---------------- count: one warp per tile, the tile's aggregate straight from global memory ------------
-        const uint32_t t = tile + warp;
-        if (t >= tile_end) return;
-        const int64_t a0 = static_cast<int64_t>(t) * TILE;
-        const int64_t left = n - a0;
-        const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
-        const T *ga = in_a + a0;
-        const T *gb = XF::ARRAYS == 2 ? in_b + a0 : nullptr;
-        int64_t sum = 0;
-        if (valid == TILE) {
-#pragma unroll 8
-            for (int j = 0; j < TILE / kWarp; ++j) sum += xf.item(ga, gb, j * kWarp + lane);
-        } else {
-#pragma unroll 1
-            for (int p = lane; p < valid; p += kWarp) sum += xf.item(ga, gb, p);
-        }
-        sum = warp_reduce_add(sum);
-        if (lane == 0) lag_publish(lag, t, sum);
-        return;
-    }
     const int64_t i0 = static_cast<int64_t>(tile) * TILE;
     const int64_t left = n - i0;
     const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
+    if (role == 0) {
+        // ---------------- count: the tile's aggregate straight from global memory (the whole CTA: a lone warp has
+        // too few loads in flight for 24 KB, measured) ----------------------------------------------------------
+        const T *ga = in_a + i0;
+        const T *gb = XF::ARRAYS == 2 ? in_b + i0 : nullptr;
+        int64_t sum = 0;
+        if (valid == TILE) {
+#pragma unroll 8
+            for (int j = 0; j < ITEMS; ++j) sum += xf.item(ga, gb, j * kScanTmaThreads + tid);
+        } else {
+#pragma unroll 1
+            for (int p = tid; p < valid; p += kScanTmaThreads) sum += xf.item(ga, gb, p);
+        }
+        sum = warp_reduce_add(sum);
+        if (lane == 0) s_warp[warp] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            int64_t t = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += s_warp[w];
+            lag_publish(lag, tile, t);
+        }
+        return;
+    }
 
     // ---------------- fill ------------------------------------------------------------------------------------
     if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
@@ -563,10 +566,21 @@ int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
         const char *c = getenv("JG_SCAN_WINDOW");
         win_env = c ? atoi(c) : 0;
     }
-    const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kScanWindow, kScanTmaThreads / kWarp);
+    const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kScanWindow, 1);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    LagDesc lag = lag_carve(ws, ntiles);
+    // CTA order: blockIdx.x by default -- a fill CTA then only waits for count CTAs with smaller block indices, which a
+    // 1-D grid dispatches first (the same assumption CUB-style single-pass scans made before tickets, and round 1's
+    // scan_tma_kernel).  JG_TICKET=1 deals the tiles by an execution-order atomic instead: no assumption at all, for
+    // +0.7 us (one atomic round trip) at the head of every CTA, 0.427 -> 0.446 ms on 125 M counts.
+    static int ticket_env = -1;
+    if (ticket_env < 0) {
+        const char *c = getenv("JG_TICKET");
+        ticket_env = c ? atoi(c) : 0;
+    }
+    if (ticket_env == 0) lag.ticket = nullptr;
     scan_win_kernel<T, XF, ITEMS><<<static_cast<unsigned>(lag_grid(sched)), kScanTmaThreads, 0, stream>>>(
-        xf, in_a, in_b, n, out, total, status, lag_carve(ws, ntiles), sched, out_aligned);
+        xf, in_a, in_b, n, out, total, status, lag, sched, out_aligned);
     return check_launch("scan_win_kernel");
 }
 

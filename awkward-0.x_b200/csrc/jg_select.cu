@@ -6,7 +6,6 @@
 #include <cstring>
 #include <type_traits>
 
-#include "jg_compact.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -14,8 +13,12 @@ namespace jg {
 // ------------------------------------------------------------------------------------------------------------
 // a[jagged_bool]   (jagged.py:562-589)
 //
-// Three launches, none of which waits on another CTA (a single-pass decoupled look-back was measured first:
-// every tile ends up waiting ~6 us for the slowest of its predecessors, profiles/r1_lookback_study.md):
+// Three launches, none of which waits on another CTA.  Single-pass forms were measured in both rounds and lost: the
+// decoupled look-back (every tile waits ~6 us for the slowest of its predecessors, profiles/r1_lookback_study.md), a
+// persistent kernel that counts LAG tiles ahead and fills from L2, and a one-launch "count CTAs a window ahead of fill
+// CTAs" schedule (profiles/r2_lag_study.md: 2.0 - 2.7 ms against 1.62 ms, and a straggling count stalls a whole
+// window).  The column is therefore read twice (the second read is what keeps a[a > c] at 62 % of its ALGORITHMIC
+// bytes while the two kernels run at 86 % of the HBM peak on the bytes they actually move):
 //   1. mask_count_kernel : one WARP per event tile popcounts the tile's mask run (M bytes read) -> tile totals
 //   2. the look-back scan of jg_scan.cuh over the N/512 tile totals -> tile bases + grand total K (tiny)
 //   3. mask_fill_kernel  : the tile's content run and mask run are staged with TMA bulk copies (UBLKCP); the
@@ -71,26 +74,6 @@ __device__ __forceinline__ int count16(const SEL &sel, int4 v) {
 
 constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
 
-// ONE WARP: number of selected positions of a run (16-byte loads; unaligned head and tail item by item)
-template <class SEL>
-__device__ __forceinline__ int64_t warp_count_selected(const SEL &sel, const typename SEL::Elem *m, int64_t len) {
-    using E = typename SEL::Elem;
-    constexpr int PER = 16 / sizeof(E);
-    const int lane = threadIdx.x & 31;
-    int64_t cnt = 0;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
-    if (head > len) head = len;
-    if (lane < head) cnt += sel.test(m[lane]);
-    const int64_t nvec = (len - head) / PER;
-    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-#pragma unroll 2
-    for (int64_t i = lane; i < nvec; i += kWarp) cnt += count16(sel, __ldg(mv + i));
-    const int64_t tail0 = head + nvec * PER;
-    if (tail0 + lane < len) cnt += sel.test(m[tail0 + lane]);
-    return warp_reduce_add(cnt);
-}
-
 template <class SEL>
 __global__ void __launch_bounds__(kCountWarps * kWarp)
 mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
@@ -121,52 +104,24 @@ mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, in
     if (lane == 0) tile_totals[tile] = cnt;
 }
 
-constexpr int kSelectWindow = 2048;      // tiles per window of the one-launch form: ~28 MB between a tile's two reads
-
-// SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both.
-// WIN: the ONE-LAUNCH form on the windowed count / fill schedule of jg_lag.cuh -- a count CTA popcounts a tile's
-// selector run (16-byte loads that leave the run in L2, the tile's offsets are prefetched on the way) and publishes
-// the total; a fill CTA, a window of tickets later, compacts the tile exactly as below with the staged run now an L2
-// hit and its base the sum of the published totals (one L2 round trip).  The column comes from HBM once.
-template <typename V, int KM, class SEL, bool SAME, bool WIN>     // KM = positions a tile may stage
-__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : ((SAME && !WIN) ? 7 : 6))
+// SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both
+template <typename V, int KM, class SEL, bool SAME>     // KM = positions a tile may stage
+__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : (SAME ? 7 : 6))
 mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                  int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
-                 const int64_t *__restrict__ tile_bases, uint32_t ntiles, int64_t *__restrict__ total, LagDesc lag,
-                 const LagSchedule sched) {
+                 const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
     using E = typename SEL::Elem;
     static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32 + (sizeof(V) >= 4 ? 512 : 0)];     // (+ one row of slack)
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
     __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
-    __shared__ __align__(16) uint16_t s_pfx[KM + 8 + (sizeof(V) >= 4 ? 128 : 0)];
+    __shared__ uint16_t s_pfx[KM + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
-    __shared__ uint32_t s_ticket;
-    __shared__ int64_t s_base;
 
-    uint32_t tile_index = blockIdx.x;
-    if constexpr (WIN) {
-        uint32_t tile_end;
-        const int role = lag_role(lag_take_ticket(lag, &s_ticket), sched, tile_index, tile_end);
-        if (role < 0) return;
-        if (role == 0) {          // count: one warp per tile
-            const uint32_t t = tile_index + (threadIdx.x >> 5);
-            if (t >= tile_end) return;
-            int64_t ev0;
-            int nev;
-            EventTile::range(n, t, ev0, nev);
-            const int64_t a = __ldg(offsets + ev0), b = __ldg(offsets + ev0 + nev);
-            const int64_t ev = ev0 + (threadIdx.x & 31) * 16;          // the tile's offsets: 4 KB the fill CTA reads
-            if (ev <= ev0 + nev) prefetch_l2(offsets + ev);
-            if ((threadIdx.x & 31) == 0) prefetch_l2(offsets + ev0 + nev);
-            const int64_t cnt = warp_count_selected(sel, mask + a + mask_shift, b - a);
-            if ((threadIdx.x & 31) == 0) lag_publish(lag, t, cnt);
-            return;
-        }
-    }
+    const uint32_t tile_index = blockIdx.x;
     EventTile tile;
     if (threadIdx.x == 0) {
         // start both TMA copies before the cooperative offsets load (see segreduce_kernel)
@@ -189,16 +144,8 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t len = e1 - e0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t base = 0;
-    if constexpr (WIN) {
-        if (warp == NW - 1) {                 // (the last warp has the least to do in the passes below)
-            const int64_t b = lag_prefix(lag, tile_index);
-            if (lane == 0) s_base = b;
-        }
-    } else {
-        base = __ldg(tile_bases + tile_index);
-        if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
-    }
+    const int64_t base = __ldg(tile_bases + tile_index);
+    if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
 
     if (len <= KM) {
         // ---------------- staged tile ----------------------------------------------------------------------
@@ -220,101 +167,45 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             }
             __syncthreads();
         }
-        constexpr bool ROWS = sizeof(V) >= 4;       // 16-byte rows (jg_compact.cuh); 1- and 2-byte items keep 32 positions per step
-        int lead = 0;
-        if constexpr (ROWS) {
-            if (L > 0) lead = static_cast<int>((reinterpret_cast<uintptr_t>(cv) & 15) / sizeof(V));
-            constexpr int ROW = RowCompact<V>::ROW;
-            const V *cvb = cv - lead;
-            const int rows_total = L > 0 ? (lead + L + ROW - 1) / ROW : 0;
-            const int rows_per_warp = (rows_total + NW - 1) / NW;
-            const int row_begin = min(rows_total, warp * rows_per_warp);
-            const int row_end = min(rows_total, row_begin + rows_per_warp);
-            // pass 1: selected per warp
-            const int cnt = rows_count<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end);
-            if (lane == 0) s_scan[warp] = cnt;
-            __syncthreads();
-            if (warp == 0) {
-                int w = lane < NW ? s_scan[lane] : 0;
-                int wi = warp_incl_scan_add(w, lane);
-                if (lane < NW) s_scan[lane] = wi - w;
-                if (lane == NW - 1) s_pfx[lead + L] = static_cast<uint16_t>(wi);
-            }
-            if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
-            __syncthreads();
-            if constexpr (WIN) base = s_base;
-            // pass 2: compaction, a lane's selected values go to consecutive slots
-            rows_compact<V, SEL, SAME>(sel, cvb, mv, lead, L, row_begin, row_end, s_scan[warp], out + base, s_pfx);
-        } else {
-            // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
-            const int rows_total = (L + 31) >> 5;
-            const int rows_per_warp = (rows_total + NW - 1) / NW;
-            const int p_begin = min(L, warp * rows_per_warp * 32);
-            const int p_end = min(L, p_begin + rows_per_warp * 32);
-            int cnt = 0;
-            for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-            cnt = warp_reduce_add(cnt);
-            if (lane == 0) s_scan[warp] = cnt;
-            __syncthreads();
-            if (warp == 0) {
-                int w = lane < NW ? s_scan[lane] : 0;
-                int wi = warp_incl_scan_add(w, lane);
-                if (lane < NW) s_scan[lane] = wi - w;
-                if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-            }
-            if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);
-            __syncthreads();
-            if constexpr (WIN) base = s_base;
-            int run = s_scan[warp];
-            V *dst = out + base;
-            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-                const int p = p0 + lane;
-                const bool on = p < p_end && sel.test(mv[p]);
-                const unsigned b = __ballot_sync(0xffffffffu, on);
-                const int slot = run + __popc(b & ((1u << lane) - 1u));
-                if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-                if (on) dst[slot] = cv[p];
-                run += __popc(b);
-            }
+        // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
+        const int rows_total = (L + 31) >> 5;
+        const int rows_per_warp = (rows_total + NW - 1) / NW;
+        const int p_begin = min(L, warp * rows_per_warp * 32);
+        const int p_end = min(L, p_begin + rows_per_warp * 32);
+        // pass 1: selected per warp
+        int cnt = 0;
+        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0) s_scan[warp] = cnt;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < NW ? s_scan[lane] : 0;
+            int wi = warp_incl_scan_add(w, lane);
+            if (lane < NW) s_scan[lane] = wi - w;
+            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+        }
+        if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
+        __syncthreads();
+        // pass 2: compaction, consecutive lanes -> consecutive output slots
+        int run = s_scan[warp];
+        V *dst = out + base;
+        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+            const int p = p0 + lane;
+            const bool on = p < p_end && sel.test(mv[p]);
+            const unsigned b = __ballot_sync(0xffffffffu, on);
+            const int slot = run + __popc(b & ((1u << lane) - 1u));
+            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
+            if (on) dst[slot] = cv[p];
+            run += __popc(b);
         }
         __syncthreads();
         // per-event new offsets -- and counts, which every later step asks for (jagged.py:383-388), for one more
-        // shared-memory read instead of a 16N-byte pass of their own.  Thread t owns the events 2t and 2t + 1: their
-        // offsets and counts leave as one 16-byte store each, positions are 32-bit and relative to the tile.
-        const uint16_t *pfx = s_pfx + lead;
-        {
-            const int ev = threadIdx.x * 2;
-            if (ev < tile.nev) {
-                const int r0 = static_cast<int>(s_off[ev] - e0);
-                const int r1 = static_cast<int>(s_off[ev + 1] - e0);
-                const int f0 = pfx[r0], f1 = pfx[r1];
-                int64_t *po = new_offsets + tile.event0 + ev;
-                int64_t *pc = new_counts ? new_counts + tile.event0 + ev : nullptr;
-                if (ev + 1 < tile.nev) {
-                    const int f2 = pfx[static_cast<int>(s_off[ev + 2] - e0)];
-                    if ((reinterpret_cast<uintptr_t>(po) & 15) == 0) __stcs(reinterpret_cast<longlong2 *>(po), make_longlong2(base + f0, base + f1));
-                    else {
-                        po[0] = base + f0;
-                        po[1] = base + f1;
-                    }
-                    if (pc) {
-                        if ((reinterpret_cast<uintptr_t>(pc) & 15) == 0) __stcs(reinterpret_cast<longlong2 *>(pc), make_longlong2(f1 - f0, f2 - f1));
-                        else {
-                            pc[0] = f1 - f0;
-                            pc[1] = f2 - f1;
-                        }
-                    }
-                } else {
-                    po[0] = base + f0;
-                    if (pc) pc[0] = f1 - f0;
-                }
-            }
-        }
-        if constexpr (WIN) {
-            if (tile_index == ntiles - 1 && threadIdx.x == 0) {
-                new_offsets[n] = base + pfx[L];
-                if (total) *total = base + pfx[L];
-            }
+        // shared-memory read instead of a 16N-byte pass of their own
+#pragma unroll 1
+        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+            const int first = s_pfx[s_off[ev] - e0];
+            new_offsets[tile.event0 + ev] = base + first;
+            if (new_counts) new_counts[tile.event0 + ev] = static_cast<int>(s_pfx[s_off[ev + 1] - e0]) - first;
         }
         return;
     }
@@ -330,10 +221,6 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
     const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
     const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
-    if constexpr (WIN) {
-        __syncthreads();
-        base = s_base;
-    }
     int64_t run = 0;
 #pragma unroll 1
     for (int64_t cs = 0; cs < len; cs += KM) {
@@ -345,8 +232,8 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         const int p_begin = min(L, warp * rows_per_warp * 32);
         const int p_end = min(L, p_begin + rows_per_warp * 32);
         int cnt = 0;
-#pragma unroll 1
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);
+#pragma unroll 8
+        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);       // (unrolled: loads in flight)
         cnt = warp_reduce_add(cnt);
         if (lane == 0) s_scan[warp] = cnt;
         __syncthreads();
@@ -359,7 +246,7 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         __syncthreads();
         int wrun = s_scan[warp];
         V *dst = out + base + run;
-#pragma unroll 1
+#pragma unroll 4
         for (int p0 = p_begin; p0 < p_end; p0 += 32) {
             const int p = p0 + lane;
             const bool on = p < p_end && sel.test(m[p]);
@@ -387,21 +274,6 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
         }
     }
-    if constexpr (WIN) {
-        if (tile_index == ntiles - 1 && threadIdx.x == 0) {
-            new_offsets[n] = base + run;
-            if (total) *total = base + run;
-        }
-    }
-}
-
-inline int select_mode() {    // experiment switch (JG_SELECT_MODE): 0 = count / scan / fill (round 1), 1 = one launch, windowed
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("JG_SELECT_MODE");
-        mode = e ? atoi(e) : 1;
-    }
-    return mode;
 }
 
 // counts of two layouts must agree (jagged.py:911-912)
@@ -573,27 +445,6 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
                               const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                               int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
     const int64_t ntiles = tile_grid(n);
-    if (select_mode() != 0) {
-        const size_t need = lag_ws_bytes(ntiles);
-        JG_REQUIRE(ws != nullptr && ws_bytes >= need, "jg_mask_select: workspace too small (%zu < %zu)", ws_bytes, need);
-        JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "jg_mask_select: workspace must be 16-byte aligned");
-        JG_REQUIRE(ntiles < (1ll << 30), "jg_mask_select: too many tiles");
-        cudaError_t e = cudaMemsetAsync(ws, 0, need, s);
-        if (e != cudaSuccess) {
-            set_error("jg_mask_select: cudaMemsetAsync: %s", cudaGetErrorString(e));
-            return -1;
-        }
-        static int win_env = -1;
-        if (win_env < 0) {
-            const char *c = getenv("JG_SELECT_WINDOW");
-            win_env = c ? atoi(c) : 0;
-        }
-        const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kSelectWindow, kTileThreads / kWarp);
-        mask_fill_kernel<V, KM, SEL, SAME, true><<<static_cast<unsigned>(lag_grid(sched)), kTileThreads, 0, s>>>(
-            sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
-            new_counts, nullptr, static_cast<uint32_t>(ntiles), total, lag_carve(ws, ntiles), sched);
-        return check_launch("mask_fill_kernel<one launch>");
-    }
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
     if (rc) return rc;
@@ -604,9 +455,9 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
     ScanInArray<int64_t> in{t.totals, true};
     rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
     if (rc) return rc;
-    mask_fill_kernel<V, KM, SEL, SAME, false><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+    mask_fill_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
         sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
-        new_counts, t.bases, static_cast<uint32_t>(ntiles), nullptr, LagDesc{}, LagSchedule{});
+        new_counts, t.bases, static_cast<uint32_t>(ntiles));
     return check_launch("mask_fill_kernel");
 }
 

@@ -260,12 +260,12 @@ def run_gpu(args):
         the last entry of the results' offsets): ONE collective and ONE device-to-host copy per step."""
         a = ak.JaggedArray.fromcounts(counts, content)          # scan (+ total/negative-count read-back)
         s = a.sum()
+        acc = sharded.DeviceTotals()
+        acc.add_sum(s.device_sum())                              # queued behind the reduction: no host round trip
         lead = a.argmax()
         sel = a[a > THRESHOLD]
         flat = sel.flatten()
         c = sel.counts
-        acc = sharded.DeviceTotals()
-        acc.add_sum(s.device_sum())
         acc.add_sum(sel.offsets[-1:])
         acc.add_sum(lead.offsets[-1:])
         gsum, gk, glead = acc.finish()
@@ -327,6 +327,14 @@ def run_gpu(args):
     if not totals_ok:
         raise SystemExit("totals_check FAILED on rank %d: got %r, want %r x %d" % (
             rank, (got_sum, got_k, got_lead), (want_sum, want_k, want_lead), world))
+    if world > 1:
+        # a variable-size result replicated whole over NCCL (counts and content gathered separately, sizes first)
+        chk = ak.JaggedArray.fromcounts(ak.asdevice(check_counts), ak.asdevice(check_pt))
+        picked = chk[chk > THRESHOLD]
+        gc, gt = sharded.gather_jagged(picked.counts, picked.flatten())
+        assert gc.numel() == world * len(check_counts) and gt.numel() == world * want_k, (gc.numel(), gt.numel())
+        assert int(gc.sum().item()) == world * want_k
+        del chk, picked, gc, gt
     del check_counts, check_pt
 
     # ---- warm-up, then the device-resident timed region
