@@ -177,23 +177,15 @@ class DeviceTotals(object):
         return self._add(value, "min")
 
     def finish(self):
-        """-> list of python numbers, one per slot, reduced over all ranks.  The partials are concatenated dtype by dtype
-        (one tiny launch per dtype, no conversion: integers stay exact, a float32 sum stays the float32 the kernel wrote),
-        packed as bytes, exchanged with one all_gather and read back with one copy."""
+        """-> list of python numbers, one per slot, reduced over all ranks: one packing launch, one all_gather, one copy."""
         if not self.parts:
             return []
-        by_dtype = {}
-        for j, (_, _, dt) in enumerate(self.parts):
-            by_dtype.setdefault(str(dt), []).append(j)
-        groups, layout, at = [], {}, 0
-        for name in sorted(by_dtype):
-            slots = by_dtype[name]
-            dt = self.parts[slots[0]][2]
-            groups.append(torch.cat([self.parts[j][0] for j in slots]).view(torch.uint8))
-            for k, j in enumerate(slots):
-                layout[j] = (at + k * dt.itemsize, dt)
-            at += len(slots) * dt.itemsize
-        mine = groups[0] if len(groups) == 1 else torch.cat(groups)
+        layout, at = [], 0
+        for _, _, dt in self.parts:
+            layout.append((at, dt))
+            at += dt.itemsize
+        # ONE launch packs every partial as raw bytes (no conversion: integers stay exact, a float32 stays float32)
+        mine = torch.cat([t.view(torch.uint8) for t, _, _ in self.parts])
         nbytes = int(mine.numel())
         if self.world > 1:
             flat = torch.empty(self.world * nbytes, dtype=torch.uint8, device=self.device)

@@ -69,5 +69,17 @@ for rep in range(2):
               ctypes.c_double(0), ctypes.c_int64(0), 0, _lib.JG_F32, _vp(sel), _lib.JG_F32, M, off.data_ptr(), N, st())
     _lib.call("jg_index_gather", pt_d.data_ptr(), 4, off.data_ptr(), lead.content.data_ptr(), _lib.JG_I64,
               lead._off64.data_ptr(), N, _vp(gout), _vp(scal, 1), st())
+    # the fused comparison + selection of the sweep (a[a > 20] as one op)
+    _lib.call("jg_compare_select", pt_d.data_ptr(), 4, pt_d.data_ptr(), _lib.JG_F32, _lib.OP["GT"], ctypes.c_double(20.0), 0,
+              off.data_ptr(), N, _vp(sel), _vp(i64a), _vp(i64b), _vp(scal), ws, wsb, st())
+    _lib.call("jg_validate_offsets", off.data_ptr(), N, M, _vp(scal, 2), _vp(scal, 1), st())
+# count distributions with long events: the element-tiled variants (round 2), through the public API
+gen = torch.Generator(device="cuda")
+gen.manual_seed(5)
+c40 = torch.poisson(torch.full((N // 8,), 40.0, device="cuda"), generator=gen).to(torch.int64)
+x40 = torch.empty(int(c40.sum()), device="cuda", dtype=torch.float32).exponential_(1.0 / 25.0, generator=gen)
+b = ak.JaggedArray.fromcounts(ak.DeviceArray(c40), ak.DeviceArray(x40))
+for rep in range(2):
+    b.sum(); b.argmax(); b[b > 20.0]; ak.JaggedArray.offsets2parents(b.offsets)
 torch.cuda.synchronize()
 print("ok", N, M, P)
