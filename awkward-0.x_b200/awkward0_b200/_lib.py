@@ -116,9 +116,10 @@ def check(rc, what):
 
 # kernels launched per entry point (everything else launches one); bench.py reports the count as gpu_launches
 LAUNCHES = [0]
-_KERNELS = {"jg_compact_nonneg": 2, "jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
-            "jg_mask_select": 1, "jg_compare_select": 1, "jg_segreduce_elem": 3, "jg_segargminmax_elem": 3,
-            "jg_mask_select_elem": 3, "jg_compare_select_elem": 3, "jg_expand_elem": 2, "jg_segargminmax_dense": 3, "jg_segargminmax_dense_tiles": 2, "jg_flat_compact": 2}
+_KERNELS = {"jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_startsstops": 2,
+            "jg_mask_select": 3, "jg_compare_select": 3, "jg_segargminmax_dense": 3, "jg_segargminmax_dense_tiles": 2,
+            "jg_flat_compact": 2, "jg_segreduce_elem": 3, "jg_segargminmax_elem": 3, "jg_mask_select_elem": 5,
+            "jg_compare_select_elem": 5, "jg_expand_elem": 2}
 
 
 def call(name, *args):

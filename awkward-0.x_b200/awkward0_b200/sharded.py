@@ -158,12 +158,16 @@ class DeviceTotals(object):
         if hasattr(value, "tensor"):
             value = value.tensor
         if torch.is_tensor(value):
-            t = value.reshape(-1)[:1].to(self.device)
+            t = value.reshape(-1)[:1]
+            if self.world > 1 and t.device != self.device:
+                t = t.to(self.device)
             if t.dtype == torch.bool:
                 t = t.to(torch.int64)
         else:                                    # a host number (sizes the host already had to know)
             dt = torch.int64 if isinstance(value, (int, numpy.integer)) else torch.float64
-            t = torch.tensor([value], dtype=dt).to(self.device, non_blocking=True)
+            t = torch.tensor([value], dtype=dt)
+            if self.device.type != "cpu":
+                t = t.to(self.device, non_blocking=True)
         self.parts.append((t, kind, numpy.dtype(str(t.dtype).replace("torch.", ""))))
         return len(self.parts) - 1
 
@@ -185,7 +189,10 @@ class DeviceTotals(object):
             layout.append((at, dt))
             at += dt.itemsize
         # ONE launch packs every partial as raw bytes (no conversion: integers stay exact, a float32 stays float32)
-        mine = torch.cat([t.view(torch.uint8) for t, _, _ in self.parts])
+        where = self.device
+        if self.world == 1:                      # a single process packs where the partials already are (no copy)
+            where = next((t.device for t, _, _ in self.parts if t.is_cuda), self.device)
+        mine = torch.cat([t.to(where, non_blocking=True).view(torch.uint8) for t, _, _ in self.parts])
         nbytes = int(mine.numel())
         if self.world > 1:
             flat = torch.empty(self.world * nbytes, dtype=torch.uint8, device=self.device)

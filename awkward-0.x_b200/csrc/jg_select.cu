@@ -394,17 +394,6 @@ static int launch_put(void *content, const int64_t *index, int64_t n, const void
     return check_launch("put_kernel");
 }
 
-// out_index[out_offsets[i]] = best[i] for best[i] >= 0
-__global__ void __launch_bounds__(256)
-scatter_nonneg_kernel(const int64_t *__restrict__ best, int64_t n, const int64_t *__restrict__ out_offsets,
-                      int64_t *__restrict__ out_index) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t b = best[i];
-        if (b >= 0) out_index[out_offsets[i]] = b;
-    }
-}
-
 // out[pos[i]] = content[i] for mask[i] != 0   (flat boolean selection, jagged.py:599-605 applied to starts/stops)
 template <typename V>
 __global__ void __launch_bounds__(256)
@@ -625,14 +614,9 @@ int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int6
 int jg_compact_nonneg(const int64_t *best, int64_t n, int64_t *out_offsets, int64_t *out_index, int64_t *total,
                       void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t s = as_stream(stream);
-    int rc = launch_scan_tma<int64_t, XfNonNeg, kScanTmaItems>(XfNonNeg{0, 0}, best, static_cast<const int64_t *>(nullptr), n,
-                                                               out_offsets, total, nullptr, ws, ws_bytes, s);
-    if (rc) return rc;
-    if (n > 0) {
-        scatter_nonneg_kernel<<<flat_grid(n, 256), 256, 0, s>>>(best, n, out_offsets, out_index);
-        return check_launch("scatter_nonneg_kernel");
-    }
-    return 0;
+    XfNonNeg xf{0, 0, out_index};
+    return launch_scan_tma<int64_t, XfNonNeg, kScanTmaItems>(xf, best, static_cast<const int64_t *>(nullptr), n, out_offsets, total,
+                                                            nullptr, ws, ws_bytes, s);
 }
 
 }  // extern "C"

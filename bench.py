@@ -412,13 +412,13 @@ def run_gpu(args):
         dom = max(step_ops, key=lambda k: ops[k]["ms"])
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 traffic = float(sum(json.load(f)[dom]["kernels"].values()))
         except Exception:
             traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ops[dom]["gbs"], "peak": peaks[0], "unit": "GB/s",
                 "frac": ops[dom]["gbs"] / peaks[0], "traffic": traffic, "peak_source": peaks[1],
-                "traffic_source": "ncu --set full dram bytes of the op's kernels, profiles/r1_traffic.json",
+                "traffic_source": "ncu --set full dram bytes of the op's kernels at 125 M events, profiles/r2_traffic.json",
                 "algorithmic_bytes": ops[dom]["bytes"], "ms": ops[dom]["ms"],
                 "step_share": ops[dom]["ms"] / sum(ops[k]["ms"] for k in step_ops)}
 

@@ -44,7 +44,10 @@ def launches(path, command):
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):          # `ncu -i X.ncu-rep --page raw --csv` exported on the GPU box (the report itself can exceed what travels back)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     head, units, rows = rows[0], rows[1], rows[2:]
     cols = [head.index("Kernel Name")] + [head.index(m) for m in METRICS]
