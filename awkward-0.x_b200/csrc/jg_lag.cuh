@@ -26,14 +26,7 @@
 
 namespace jg {
 
-// per-tile words a count CTA leaves for the fill CTA of the SAME tile (scan_win_kernel): bit 63 = published, bit 62 =
-// "an item of the tile needs 64-bit arithmetic" (first word only), low 61 bits = the sum of one warp chunk
-constexpr uint64_t kMetaValid = 1ull << 63;
-constexpr uint64_t kMetaWide = 1ull << 62;
-constexpr uint64_t kMetaValue = (1ull << 61) - 1;
-
 struct LagDesc {
-    uint64_t *wmeta;   // optional: words per tile for the tile's own fill CTA (see above)
     uint32_t *ticket;  // execution-order counter of the launch's CTAs
     uint64_t *l0;      // per tile:              bit 63 = published, low 63 bits = aggregate
     uint64_t *l1;      // per 32 tiles:          low 16 bits = members added, high 48 bits = their sum
@@ -52,7 +45,6 @@ static inline size_t lag_ws_bytes(int64_t ntiles) {
 static inline LagDesc lag_carve(void *ws, int64_t ntiles) {
     const size_t t = static_cast<size_t>(ntiles < 1 ? 1 : ntiles);
     LagDesc d;
-    d.wmeta = nullptr;
     d.ticket = static_cast<uint32_t *>(ws);
     d.l0 = static_cast<uint64_t *>(ws) + 2;
     d.l1 = d.l0 + t;

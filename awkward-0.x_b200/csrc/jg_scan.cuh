@@ -436,75 +436,33 @@ scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     const int64_t i0 = static_cast<int64_t>(tile) * TILE;
     const int64_t left = n - i0;
     const int valid = left < TILE ? static_cast<int>(left < 0 ? 0 : left) : TILE;
-    constexpr int JPW = ITEMS / NW;                       // the fill CTA's warp w owns the items j * 128 + tid with j / JPW == w
-    static_assert(ITEMS % NW == 0, "items per thread must split evenly over the fill warps");
-    uint64_t *wmeta = lag.wmeta + static_cast<size_t>(tile) * NW;
-    const bool full = valid == TILE;
     if (role == 0) {
-        // ---------------- count: everything the fill CTA needs besides the items themselves -----------------------
-        // the whole CTA reads the tile straight from global memory (coalesced; the tile stays in L2): the sums of the
-        // fill CTA's four warp chunks, the validity flags and (NONEMPTY) the non-empty events per 512-event tile.  The
-        // fill CTA then goes straight to its one pass over the staged tile.  (A lone warp per tile was measured: too
-        // few loads in flight for 24 KB.)
+        // ---------------- count: the tile's aggregate straight from global memory (the whole CTA: a lone warp has
+        // too few loads in flight for 24 KB, measured) ----------------------------------------------------------
         const T *ga = in_a + i0;
         const T *gb = XF::ARRAYS == 2 ? in_b + i0 : nullptr;
-        int64_t wsum[NW];
-        int ne[kSubs];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) wsum[w] = 0;
-#pragma unroll
-        for (int q = 0; q < kSubs; ++q) ne[q] = 0;
-        bool neg = false, big = false;
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const int p = j * kScanTmaThreads + tid;
-            if (full || p < valid) {
-                const int64_t x = xf.item(ga, gb, p);
-                wsum[j / JPW] += x;
-                neg |= x < 0;
-                big |= static_cast<uint64_t>(x) >= (1ull << 19);
-                if constexpr (XF::NONEMPTY) ne[(j * kScanTmaThreads) >> 9] += (x > 0);
-            }
+        int64_t sum = 0;
+        if (valid == TILE) {
+#pragma unroll 8
+            for (int j = 0; j < ITEMS; ++j) sum += xf.item(ga, gb, j * kScanTmaThreads + tid);
+        } else {
+#pragma unroll 1
+            for (int p = tid; p < valid; p += kScanTmaThreads) sum += xf.item(ga, gb, p);
         }
-        if (tid < NW) s_warp[tid] = 0;
-        if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
+        sum = warp_reduce_add(sum);
+        if (lane == 0) s_warp[warp] = sum;
         __syncthreads();
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const int64_t v = warp_reduce_add(wsum[w]);
-            if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(&s_warp[w]), static_cast<unsigned long long>(v));
-        }
-        if constexpr (XF::NONEMPTY) {
-#pragma unroll
-            for (int q = 0; q < kSubs; ++q) {
-                const int v = warp_reduce_add(ne[q]);
-                if (lane == 0 && v) atomicAdd(&s_ne[q], v);
-            }
-        }
-        const bool any_neg = __syncthreads_or(neg);
-        const bool any_big = __syncthreads_or(big);
-        if constexpr (XF::NONEMPTY) {
-            if (tid < SUBS) {
-                const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
-                if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
-            }
-        }
         if (tid == 0) {
-            if (any_neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
             int64_t t = 0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const uint64_t part = static_cast<uint64_t>(s_warp[w]) & kMetaValue;
-                t += s_warp[w];
-                st_relaxed_u64(wmeta + w, kMetaValid | (w == 0 && any_big ? kMetaWide : 0ull) | part);
-            }
+            for (int w = 0; w < NW; ++w) t += s_warp[w];
             lag_publish(lag, tile, t);
         }
         return;
     }
 
-    // ---------------- fill: one pass over the staged tile ------------------------------------------------------------
-    __shared__ int s_wide;
+    // ---------------- fill ------------------------------------------------------------------------------------
+    if (XF::NONEMPTY && tid < kSubs) s_ne[tid] = 0;
     stage_init(s_bar, 2);
     const T *sa = reinterpret_cast<const T *>(s_raw_a);
     const T *sb = reinterpret_cast<const T *>(s_raw_b);
@@ -520,13 +478,6 @@ scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     if (warp == 0) {          // the base: aggregates published a window ago (one L2 round trip while the copy lands)
         const int64_t tile_base = lag_prefix(lag, tile);
         if (lane == 0) s_base = tile_base;
-    } else if (warp == 1) {   // this tile's own warp sums and flags, published by its count CTA
-        uint64_t w = kMetaValid;
-        do {
-            if (lane < NW) w = ld_relaxed_u64(wmeta + lane);
-        } while (!__all_sync(0xffffffffu, (w >> 63) != 0));
-        if (lane < NW) s_warp[lane] = static_cast<int64_t>(w & kMetaValue);
-        if (lane == 0) s_wide = (w & kMetaWide) != 0;
     }
     if (valid > 0) {
         if (XF::ARRAYS == 2) mbar_wait(&s_bar[1], 0);
@@ -535,7 +486,45 @@ scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
         __syncthreads();
     }
     const int wbase = warp * (ITEMS * kWarp);
-    const bool wide = s_wide != 0;
+    const bool full = valid == TILE;
+    int64_t sum = 0;
+    bool neg = false, big = false;
+#pragma unroll
+    for (int r = 0; r < ITEMS / 2; ++r) {
+        const int p = wbase + r * 64 + lane * 2;
+        const int64_t x = (full || p < valid) ? xf.item(sa, sb, p) : 0;
+        const int64_t y = (full || p + 1 < valid) ? xf.item(sa, sb, p + 1) : 0;
+        neg |= (x < 0) | (y < 0);
+        big |= (static_cast<uint64_t>(x) >= (1ull << 19)) | (static_cast<uint64_t>(y) >= (1ull << 19));
+        sum += x + y;
+    }
+    if (neg && status) atomicOr(status, JG_ST_NEGATIVE_COUNT);
+    sum = warp_reduce_add(sum);
+    if (lane == 0) s_warp[warp] = sum;
+    if constexpr (XF::NONEMPTY) {
+        int ne_lo = 0, ne_hi = 0;
+        const int sub_lo = wbase >> 9;
+#pragma unroll 4
+        for (int r = 0; r < ITEMS / 2; ++r) {
+            const int p = wbase + r * 64 + lane * 2;
+            const int c = ((full || p < valid) ? (xf.item(sa, sb, p) > 0) : 0) + ((full || p + 1 < valid) ? (xf.item(sa, sb, p + 1) > 0) : 0);
+            if (((wbase + r * 64) >> 9) == sub_lo) ne_lo += c;
+            else ne_hi += c;
+        }
+        ne_lo = warp_reduce_add(ne_lo);
+        ne_hi = warp_reduce_add(ne_hi);
+        if (lane == 0) {
+            if (ne_lo) atomicAdd(&s_ne[sub_lo], ne_lo);
+            if (ne_hi) atomicAdd(&s_ne[sub_lo + 1], ne_hi);
+        }
+    }
+    const bool wide = __syncthreads_or(big);
+    if constexpr (XF::NONEMPTY) {
+        if (tid < SUBS) {
+            const int64_t et = static_cast<int64_t>(tile) * SUBS + tid;
+            if (et < xf.n_event_tiles) xf.tile_nonempty[et] = s_ne[tid];
+        }
+    }
     int64_t run = s_base, tile_sum = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
@@ -570,8 +559,7 @@ int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
     constexpr int TILE = kScanTmaThreads * ITEMS;
     const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
-    const size_t lag_bytes = (lag_ws_bytes(ntiles) + 15) & ~static_cast<size_t>(15);
-    const size_t need = lag_bytes + static_cast<size_t>(ntiles) * (kScanTmaThreads / kWarp) * 8;      // + the per-tile warp sums
+    const size_t need = lag_ws_bytes(ntiles);
     JG_REQUIRE(ws != nullptr && ws_bytes >= need, "scan: workspace too small (%zu < %zu)", ws_bytes, need);
     JG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "scan: workspace must be 16-byte aligned");
     JG_REQUIRE(ntiles < (1ll << 30), "scan: too many tiles");
@@ -593,7 +581,6 @@ int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
     const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kScanWindow, 1);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     LagDesc lag = lag_carve(ws, ntiles);
-    lag.wmeta = reinterpret_cast<uint64_t *>(static_cast<char *>(ws) + lag_bytes);
     // CTA order: blockIdx.x by default -- a fill CTA then only waits for count CTAs with smaller block indices, which a
     // 1-D grid dispatches first (the same assumption CUB-style single-pass scans made before tickets, and round 1's
     // scan_tma_kernel).  JG_TICKET=1 deals the tiles by an execution-order atomic instead: no assumption at all, for
