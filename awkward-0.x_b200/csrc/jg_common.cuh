@@ -162,7 +162,9 @@ constexpr uint64_t kStatePrefix = 2ull;
 constexpr uint64_t kValueMask = (1ull << 62) - 1;
 
 struct LookbackWs {
-    uint32_t ticket;      // dynamic tile counter (tiles are ordered by arrival => forward progress)
+    uint32_t ticket;      // dynamic tile counter of scan_lookback_kernel (tiles ordered by arrival => forward progress with
+                          // any dispatch order); scan_tma_kernel takes blockIdx.x instead and relies on the in-order
+                          // dispatch of a 1-D grid -- stated where it is launched (launch_scan_tma)
     uint32_t pad[3];
     uint64_t desc[1];     // ntiles entries follow
 };
@@ -221,7 +223,10 @@ __device__ __forceinline__ int64_t lookback_exclusive_warp(uint64_t *desc, uint3
             const unsigned prefix = __ballot_sync(0xffffffffu, st == kStatePrefix);
             const int first_prefix = prefix ? (__ffs(prefix) - 1) : 32;
             const unsigned need = first_prefix >= 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);
-            if (invalid & need) break;                  // a needed predecessor has not published: re-poll from here
+            if (invalid & need) {                       // a needed predecessor has not published: re-poll from here
+                __nanosleep(32);                        // (back off: the predecessor's CTA shares the memory system)
+                break;
+            }
             const uint64_t contrib = (lane <= first_prefix) ? (w[g] & kValueMask) : 0ull;
             excl += warp_reduce_add(contrib);
             base -= 32;

@@ -5,11 +5,13 @@
 //
 // Two kernels share the look-back protocol of jg_common.cuh (one 64-bit descriptor per tile: 2-bit state +
 // 62-bit value, so flag and value travel in one atomic store):
-//   * scan_tma_kernel<T, XF, ITEMS>   -- the production path.  The tile is PARKED IN SHARED MEMORY by one TMA bulk
-//     copy and only 128 threads with ~35 registers watch over it, so 9 CTAs are resident per SM: on B200 every
-//     tile of a look-back scan waits ~6 us for the slowest of its predecessors (profiles/r1_lookback_study.md)
-//     and only parked bytes -- not registers -- can cover that wait.  XF turns the staged data into items:
-//     the items themselves (counts) or combinatorial counts formed from staged offsets (pairs / cross / choose).
+//   * scan_win_kernel<T, XF, ITEMS>   -- round 2, every plain scan: windowed count / fill CTAs on published aggregates
+//     (jg_lag.cuh), no tile waits.
+//   * scan_tma_kernel<T, XF, ITEMS>   -- round 1's look-back, kept for the combinatorial counts.  The tile (128 threads
+//     x 24 items = 3072 items, 24.6 KB of int64) is PARKED IN SHARED MEMORY by one TMA bulk copy, 9 CTAs resident per
+//     SM: on B200 every tile of a look-back scan waits ~6 us for the slowest of its predecessors
+//     (profiles/r1_lookback_study.md) and only parked bytes -- not registers -- can cover that wait.  XF turns the
+//     staged data into items: the items themselves (counts) or combinatorial counts formed from staged offsets.
 //   * scan_lookback_kernel<In>        -- functor input held in registers (validity flags, tiny tile-total scans);
 //     tiles take their index from an atomic ticket.
 // Both use 32-bit in-warp shuffle scans when every item of the tile is < 2^19 (the common case), else 64-bit.
@@ -58,15 +60,6 @@ struct ScanInArray {
         } else if (i < n) {
             a = static_cast<int64_t>(p[i]);
         }
-    }
-};
-
-// counts of non-negative flags: item = (best[i] >= 0)
-struct ScanInNonNeg {
-    const int64_t *p;
-    __device__ __forceinline__ void load2(int64_t i, int64_t n, int64_t &a, int64_t &b) const {
-        a = (i < n) ? (p[i] >= 0) : 0;
-        b = (i + 1 < n) ? (p[i + 1] >= 0) : 0;
     }
 };
 
@@ -203,15 +196,16 @@ scan_lookback_kernel(In in, int64_t n, int64_t *__restrict__ out, int64_t *__res
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Array-input variant with the tile PARKED IN SHARED MEMORY: the tile (4096 items) is fetched with one TMA bulk
-// copy (UBLKCP), the 128 threads keep only a handful of registers, so 6-7 CTAs are resident per SM.  That
+// Array-input variant with the tile PARKED IN SHARED MEMORY: the tile (128 x 24 = 3072 items) is fetched with one TMA
+// bulk copy (UBLKCP), the 128 threads keep only a handful of registers, so 9 CTAs are resident per SM.  That
 // residency is what a look-back scan needs on B200: every tile waits ~6 us for the slowest of its predecessors
 // (profiles/r1_lookback_study.md), and only parked tiles -- not registers -- can cover that wait.
-// Measured 4.4 TB/s (vs 2.9 TB/s for the register-resident kernel above at 3 CTAs/SM).
+// Measured 4.0 TB/s (vs 2.9 TB/s for the register-resident kernel above at 3 CTAs/SM).  The tile index is
+// blockIdx.x: a tile only waits for tiles with smaller block indices, which a 1-D grid dispatches first.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kScanTmaThreads = 128;
 constexpr int kScanTmaItems = 24;                                   // per thread (24.6 KB tile -> 9 CTAs/SM)
-constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 4096 items
+constexpr int kScanTmaTile = kScanTmaThreads * kScanTmaItems;      // 3072 items
 
 // what a staged tile means: the items themselves, or offsets whose differences feed a combinatorial count
 template <bool COUNT_NONEMPTY>
@@ -545,15 +539,6 @@ scan_win_kernel(XF xf, const T *__restrict__ in_a, const T *__restrict__ in_b, i
     }
 }
 
-inline int scan_mode() {      // experiment switch (JG_SCAN_MODE): 0 = look-back (round 1), 1 = windowed count / fill
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("JG_SCAN_MODE");
-        mode = e ? atoi(e) : 1;
-    }
-    return mode;
-}
-
 template <typename T, class XF, int ITEMS>
 int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64_t *out, int64_t *total,
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
@@ -573,12 +558,7 @@ int launch_scan_win(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
         cudaFuncSetAttribute(scan_win_kernel<T, XF, ITEMS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         carveout_set = true;
     }
-    static int win_env = -1;
-    if (win_env < 0) {
-        const char *c = getenv("JG_SCAN_WINDOW");
-        win_env = c ? atoi(c) : 0;
-    }
-    const LagSchedule sched = lag_schedule(ntiles, win_env > 0 ? win_env : kScanWindow, 1);
+    const LagSchedule sched = lag_schedule(ntiles, kScanWindow, 1);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     LagDesc lag = lag_carve(ws, ntiles);
     // CTA order: blockIdx.x by default -- a fill CTA then only waits for count CTAs with smaller block indices, which a
@@ -601,7 +581,7 @@ int launch_scan_tma(const XF &xf, const T *in_a, const T *in_b, int64_t n, int64
                     int32_t *status, void *ws, size_t ws_bytes, cudaStream_t stream) {
     // plain scans: the windowed count / fill kernel; combinatorial counts (two offsets per item, a division-free but
     // longer transform) keep the look-back -- their count CTAs cost more than the wait they avoid (measured)
-    if (XF::EXTRA == 0 && scan_mode() == 1)
+    if (XF::EXTRA == 0)
         return launch_scan_win<T, XF, ITEMS>(xf, in_a, in_b, n, out, total, status, ws, ws_bytes, stream);
     constexpr int TILE = kScanTmaThreads * ITEMS;
     const int64_t ntiles = n <= 0 ? 1 : ceil_div(n, TILE);
