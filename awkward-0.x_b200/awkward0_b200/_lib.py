@@ -77,6 +77,8 @@ PROTOTYPES = {
     "jg_compact_nonneg": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_mask_select": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "jg_compare_select": (_i, [_vp, _i, _vp, _i, _i, _d, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "jg_mask_select_phase": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "jg_compare_select_phase": (_i, [_vp, _i, _vp, _i, _i, _d, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "jg_check_same_counts": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "jg_index_gather": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "jg_flat_compact": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -122,7 +124,13 @@ _KERNELS = {"jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_start
             "jg_compare_select_elem": 5, "jg_expand_elem": 2}
 
 
+_PHASED = {"jg_mask_select_phase": (3, 2, 1), "jg_compare_select_phase": (3, 2, 1)}      # launches of phase 0 / 1 / 2
+
+
 def call(name, *args):
     """Call a C entry point that returns an int status and raise on failure."""
-    LAUNCHES[0] += _KERNELS.get(name, 1)
+    if name in _PHASED:
+        LAUNCHES[0] += _PHASED[name][args[-2]]
+    else:
+        LAUNCHES[0] += _KERNELS.get(name, 1)
     check(getattr(lib, name)(*args), name)

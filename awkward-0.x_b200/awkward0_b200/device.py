@@ -64,6 +64,7 @@ class _Runtime(object):
     def __init__(self):
         self._ws = {}
         self._scal = {}
+        self._side = {}         # per device: (side stream, pinned int64[8]) of read_early
 
     _has_cuda = None
     _devices = {}
@@ -130,6 +131,31 @@ class _Runtime(object):
         out = pool[0][pool[1]:pool[1] + 8]
         pool[1] += 8
         return out
+
+    def read_early(self, scal):
+        """Start reading `scal` back NOW, on a side stream that waits only for what has been queued so far: returns a
+        function that gives (total, status, info) like read() but waits for that copy alone -- kernels queued on the
+        compute stream in the meantime keep running while the host goes on (the selection reads K this way after its
+        counting pass and queues the compaction before asking for it)."""
+        dev = self.device()
+        key = dev.index
+        side = self._side.get(key)
+        if side is None:
+            side = self._side[key] = (torch.cuda.Stream(device=dev), torch.empty(8, dtype=torch.int64).pin_memory())
+        stream, host = side
+        ready = torch.cuda.Event()
+        ready.record()                                   # the compute stream, after everything queued so far
+        stream.wait_event(ready)
+        with torch.cuda.stream(stream):
+            host.copy_(scal, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+
+        def result():
+            done.synchronize()
+            h = host.numpy()
+            return int(h[0]), int(h[1]) & 0xffffffff, h[2:6].copy()
+        return result
 
     @staticmethod
     def read(scal):

@@ -1227,18 +1227,25 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
                 else:
                     call("jg_mask_select_elem", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
                          _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), last - first, ews, ewsb, runtime.stream())
-            elif fused:
-                call("jg_compare_select", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
-                     jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,
-                     _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, runtime.stream())
             else:
-                call("jg_mask_select", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
-                     _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, runtime.stream())
+                # the first column in two phases: count + scan, start reading K back, queue the compaction; the host
+                # then waits for K alone and the next operation is queued while the compaction is still running
+                for phase in ((1, 2) if not columns else (0,)):
+                    if fused:
+                        call("jg_compare_select_phase", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
+                             jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,
+                             _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, phase, runtime.stream())
+                    else:
+                        call("jg_mask_select_phase", col.data_ptr(), col.itemsize, mask.data_ptr(), mask_shift, off.data_ptr(), n,
+                             _vp(out), _vp(new_offsets), counts_ptr, _vp(scal), ws, wsb, phase, runtime.stream())
+                    if phase == 1:
+                        early.append(runtime.read_early(scal))
             columns.append(out)
             return out
 
+        early = []
         picked = a._map_content(select)
-        total, _, _ = runtime.read(scal)
+        total, _, _ = early[0]() if early else runtime.read(scal)
         content = a._map_content(lambda t: DeviceArray(t[:total], _TORCH_NP(t)), picked)
         out = self._make(DeviceArray(new_offsets, INDEXTYPE), content, total)
         out._counts = DeviceArray(new_counts, INDEXTYPE)

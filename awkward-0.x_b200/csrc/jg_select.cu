@@ -429,21 +429,27 @@ static int carve_tile_ws(void *ws, size_t ws_bytes, int64_t ntiles, TileScanWs &
     return 0;
 }
 
+// phase 0: the whole selection; 1: count + scan only (the total K is then in *total, one read-back away, while the
+// compaction has not been queued yet); 2: the compaction only (after a phase-1 call with the same arguments and
+// workspace).  Splitting lets the host read K while the compaction runs: the next operation is queued behind it
+// without the device ever going idle.
 template <typename V, int KM, class SEL, bool SAME>
 static int launch_mask_select(const SEL &sel, const void *content, const typename SEL::Elem *mask, int64_t mask_shift,
                               const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
-                              int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+                              int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s, int phase) {
     const int64_t ntiles = tile_grid(n);
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
     if (rc) return rc;
-    mask_count_kernel<SEL><<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
-        sel, mask, mask_shift, offsets, n, ntiles, t.totals);
-    rc = check_launch("mask_count_kernel");
-    if (rc) return rc;
-    ScanInArray<int64_t> in{t.totals, true};
-    rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
-    if (rc) return rc;
+    if (phase != 2) {
+        mask_count_kernel<SEL><<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
+            sel, mask, mask_shift, offsets, n, ntiles, t.totals);
+        rc = check_launch("mask_count_kernel");
+        if (rc) return rc;
+        ScanInArray<int64_t> in{t.totals, true};
+        rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
+        if (rc || phase == 1) return rc;
+    }
     mask_fill_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
         sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
         new_counts, t.bases, static_cast<uint32_t>(ntiles));
@@ -454,21 +460,21 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
 template <class SEL, bool SAME>
 static int dispatch_mask_select(const SEL &sel, const void *content, int itemsize, const typename SEL::Elem *mask,
                                 int64_t mask_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
-                                int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+                                int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s, int phase) {
     constexpr int E = sizeof(typename SEL::Elem);
     if constexpr (SAME) {
-        if constexpr (E == 4) return launch_mask_select<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-        else return launch_mask_select<uint64_t, 3584, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        if constexpr (E == 4) return launch_mask_select<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
+        else return launch_mask_select<uint64_t, 3584, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
     } else {
         constexpr int KM8 = E == 1 ? 3584 : (E == 4 ? 3072 : 2304);   // (f64 by another f64 column: the host keeps the mask path)
         constexpr int KM4 = E == 8 ? 3072 : 4096;
         if constexpr (E == 1) {          // narrow contents only through a byte mask (keeps the number of kernels down)
-            if (itemsize == 1) return launch_mask_select<uint8_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-            if (itemsize == 2) return launch_mask_select<uint16_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+            if (itemsize == 1) return launch_mask_select<uint8_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
+            if (itemsize == 2) return launch_mask_select<uint16_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
         }
         switch (itemsize) {
-            case 4: return launch_mask_select<uint32_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
-            case 8: return launch_mask_select<uint64_t, KM8, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+            case 4: return launch_mask_select<uint32_t, KM4, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
+            case 8: return launch_mask_select<uint64_t, KM8, SEL, false>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
         }
         set_error("jg_mask_select: unsupported itemsize %d", itemsize);
         return -2;
@@ -478,7 +484,7 @@ static int dispatch_mask_select(const SEL &sel, const void *content, int itemsiz
 template <typename K, bool STRICT>
 static int compare_select(const void *content, int itemsize, const void *key, int op, double scalar, int64_t key_shift,
                           const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
-                          int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+                          int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s, int phase) {
     using SEL = FloatCompare<K, STRICT>;
     SEL sel;
     const K c = static_cast<K>(scalar);                 // the eager comparison converts the scalar the same way
@@ -487,9 +493,9 @@ static int compare_select(const void *content, int itemsize, const void *key, in
     sel.c = flip ? -c : c;
     const K *k = static_cast<const K *>(key);
     if (key == content && key_shift == 0 && itemsize == static_cast<int>(sizeof(K)))
-        return dispatch_mask_select<SEL, true>(sel, content, itemsize, k, 0, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+        return dispatch_mask_select<SEL, true>(sel, content, itemsize, k, 0, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
     JG_REQUIRE(itemsize == 4 || itemsize == 8, "jg_compare_select: a column other than the compared one must have 4- or 8-byte items");
-    return dispatch_mask_select<SEL, false>(sel, content, itemsize, k, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+    return dispatch_mask_select<SEL, false>(sel, content, itemsize, k, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
 }
 
 template <typename V>
@@ -516,28 +522,44 @@ using namespace jg;
 
 extern "C" {
 
+int jg_mask_select_phase(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
+                         const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                         int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream) {
+    JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
+    JG_REQUIRE(phase >= 0 && phase <= 2, "jg_mask_select: phase must be 0, 1 or 2");
+    return dispatch_mask_select<ByteMask, false>(ByteMask{}, content, itemsize, mask, mask_shift, offsets, n, out,
+                                                 new_offsets, new_counts, total, ws, ws_bytes, as_stream(stream), phase);
+}
+
 int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
                    const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                    int64_t *total, void *ws, size_t ws_bytes, void *stream) {
-    JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
-    return dispatch_mask_select<ByteMask, false>(ByteMask{}, content, itemsize, mask, mask_shift, offsets, n, out,
-                                                 new_offsets, new_counts, total, ws, ws_bytes, as_stream(stream));
+    return jg_mask_select_phase(content, itemsize, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws,
+                                ws_bytes, 0, stream);
 }
 
-int jg_compare_select(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
-                      int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
-                      int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream) {
+int jg_compare_select_phase(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                            int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                            int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && new_offsets && key, "jg_compare_select: bad arguments");
     JG_REQUIRE(op == JG_OP_GT || op == JG_OP_GE || op == JG_OP_LT || op == JG_OP_LE,
                "jg_compare_select: operator %d is not an ordering comparison", op);
+    JG_REQUIRE(phase >= 0 && phase <= 2, "jg_compare_select: phase must be 0, 1 or 2");
     cudaStream_t s = as_stream(stream);
     const bool strict = (op == JG_OP_GT || op == JG_OP_LT);
-#define JG_CS(K, ST) compare_select<K, ST>(content, itemsize, key, op, scalar, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s)
+#define JG_CS(K, ST) compare_select<K, ST>(content, itemsize, key, op, scalar, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase)
     if (key_dtype == JG_F32) return strict ? JG_CS(float, true) : JG_CS(float, false);
     if (key_dtype == JG_F64) return strict ? JG_CS(double, true) : JG_CS(double, false);
 #undef JG_CS
     set_error("jg_compare_select: key dtype %d is not float32 / float64", key_dtype);
     return -2;
+}
+
+int jg_compare_select(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                      int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                      int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream) {
+    return jg_compare_select_phase(content, itemsize, key, key_dtype, op, scalar, key_shift, offsets, n, out, new_offsets,
+                                   new_counts, total, ws, ws_bytes, 0, stream);
 }
 
 int jg_put(void *content, int itemsize, const int64_t *index, int64_t n, const void *values, uint64_t scalar_bits,

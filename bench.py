@@ -262,8 +262,10 @@ def run_gpu(args):
         s = a.sum()
         acc = sharded.DeviceTotals()
         acc.add_sum(s.device_sum())                              # queued behind the reduction: no host round trip
-        lead = a.argmax()
+        # the selection hands K back as soon as its counting pass has run (the compaction is still in flight), so the
+        # arg-reduction is queued behind it without the device going idle; the arg-reduction needs the whole pass
         sel = a[a > THRESHOLD]
+        lead = a.argmax()
         flat = sel.flatten()
         c = sel.counts
         acc.add_sum(sel.offsets[-1:])
@@ -280,11 +282,11 @@ def run_gpu(args):
         nev = 0
         for a in stream:
             s = a.sum()
-            lead = a.argmax()
+            acc.add_sum(s.device_sum())
             sel = a[a > THRESHOLD]
+            lead = a.argmax()
             flat = sel.flatten()
             c = sel.counts
-            acc.add_sum(s.device_sum())
             acc.add_sum(sel.offsets[-1:])
             acc.add_sum(lead.offsets[-1:])
             nev += len(c)

@@ -166,6 +166,14 @@ int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64
                    const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
                    int64_t *new_counts /* n entries, may be NULL: the result's counts for free */, int64_t *total,
                    void *ws, size_t ws_bytes, void *stream);
+/* The same selection in two calls: phase 1 queues the counting pass and the scan of the tile totals (after it *total
+ * holds K), phase 2 the compaction (same arguments and workspace); phase 0 is jg_mask_select.  The host reads K on a
+ * side stream as soon as phase 1 has run and allocates / returns the result while the compaction is still running, so
+ * the operation that follows is queued behind it without the device going idle (jagged.py:562-589 returns only after
+ * numpy has finished; on a device the data-dependent size is the only thing the host ever waits for).              */
+int jg_mask_select_phase(const void *content, int itemsize, const uint8_t *mask, int64_t mask_shift,
+                         const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                         int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream);
 /* counts of two layouts must agree (jagged.py:911-912): raises JG_ST_COUNTS_MISMATCH                               */
 int jg_check_same_counts(const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, int32_t *status,
                          void *stream);
@@ -187,6 +195,11 @@ int jg_flat_compact(const void *content, int itemsize, const uint8_t *mask, int6
 int jg_compare_select(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
                       int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
                       int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream);
+
+/* jg_compare_select in two calls (see jg_mask_select_phase)                                                           */
+int jg_compare_select_phase(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
+                            int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
+                            int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream);
 
 /* scatter content[index[k]] = values[k], or the `itemsize` low bytes of scalar_bits when values is NULL: the store
  * of __setitem__ (jagged.py:789-838: `self._content[indexes] = what`) and of parents2startsstops (jagged.py:73-93:

@@ -19,8 +19,8 @@ def sweep(c, p):
     s = a.sum()
     acc = sharded.DeviceTotals()
     acc.add_sum(s.device_sum())
-    lead = a.argmax()
     sel = a[a > 20.0]
+    lead = a.argmax()
     flat = sel.flatten(); cc = sel.counts
     acc.add_sum(sel.offsets[-1:]); acc.add_sum(lead.offsets[-1:])
     return acc.finish()
