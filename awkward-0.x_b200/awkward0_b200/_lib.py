@@ -42,6 +42,14 @@ OP = dict(
 
 RHS_ARRAY, RHS_SCALAR, RHS_PARENT = 0, 1, 2
 COMB_PAIRS, COMB_DISTINCTS, COMB_CHOOSE, COMB_CROSS = 0, 1, 2, 3
+COMB_LONG = 0x100                # hint OR-ed into `kind`: events hold more than a handful of combinations each
+COMB_LONG_MEAN = 8               # ... from this many combinations per event on (512 events then overflow a 4096-entry pair table)
+
+
+def comb_kind(kind, total, nevents):
+    """`kind` with the long-events hint when the mean number of combinations per event says so (same result either way;
+    the kernels chosen differ: include/jagged_b200.h JG_COMB_LONG)."""
+    return kind | COMB_LONG if total > COMB_LONG_MEAN * max(nevents, 1) else kind
 
 # every symbol include/jagged_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them all)
 _vp, _i, _i64, _sz, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_double

@@ -1613,7 +1613,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         cols = [empty(total, INDEXTYPE) for _ in range(ncols)]
         if total > 0:
             arr = (ctypes.c_void_p * ncols)(*[c.data_ptr() for c in cols])
-            call("jg_comb_fill", kind, k, off.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0), n,
+            call("jg_comb_fill", _lib.comb_kind(kind, total, n), k, off.data_ptr(), off_b.data_ptr() if off_b is not None else ctypes.c_void_p(0), n,
                  poff.data_ptr(), arr, 1 if absolute else 0, runtime.stream())
         table = Table.named("tuple", *[DeviceArray(c, INDEXTYPE) for c in cols])
         return self._make(poff, table, total)

@@ -103,7 +103,7 @@ class CombContext(object):
             right = [x for x in todo if x._kind == "R"]
             if len(left) == 1 and len(right) == 1:
                 l, r = left[0], right[0]
-                call("jg_comb_gather2", self.kind, self.off_a.data_ptr(), self._ob(), self.n, self.poff.data_ptr(),
+                call("jg_comb_gather2", _lib.comb_kind(self.kind, self.total, self.n), self.off_a.data_ptr(), self._ob(), self.n, self.poff.data_ptr(),
                      l._args[0].data_ptr(), l._args[0].itemsize, r._args[0].data_ptr(), r._args[0].itemsize,
                      ctypes.c_void_p(l._mat.data_ptr()), ctypes.c_void_p(r._mat.data_ptr()), runtime.stream())
             else:
@@ -115,7 +115,7 @@ class CombContext(object):
 
                         def parr(ptrs):
                             return (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
-                        call("jg_comb_gather_multi", self.kind, self.off_a.data_ptr(), self._ob(), self.n,
+                        call("jg_comb_gather_multi", _lib.comb_kind(self.kind, self.total, self.n), self.off_a.data_ptr(), self._ob(), self.n,
                              self.poff.data_ptr(), size,
                              len(cl), parr([x._args[0].tensor.data_ptr() for x in cl]), parr([x._mat.data_ptr() for x in cl]),
                              len(cr), parr([x._args[0].tensor.data_ptr() for x in cr]), parr([x._mat.data_ptr() for x in cr]),
@@ -206,7 +206,7 @@ class LazyArray(DeviceArray):
         out = empty(ctx.total, self._ldtype)
         if ctx.total > 0:
             _lib.LAUNCHES[0] += 1
-            _lib.check(_lib.lib.jg_comb_eval(ctx.kind, ctx.off_a.data_ptr(), ctx._ob(), ctx.n, ctx.poff.data_ptr(),
+            _lib.check(_lib.lib.jg_comb_eval(_lib.comb_kind(ctx.kind, ctx.total, ctx.n), ctx.off_a.data_ptr(), ctx._ob(), ctx.n, ctx.poff.data_ptr(),
                                              jg_code(prog[1]), ctypes.byref(prog[0]), ctypes.c_void_p(out.data_ptr()),
                                              runtime.stream()), "jg_comb_eval")
         self._mat = out

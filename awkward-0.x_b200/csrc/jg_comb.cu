@@ -16,6 +16,10 @@
 #include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
+#include <cstddef>
+#include <mutex>
+#include <type_traits>
+
 namespace jg {
 
 // (i, j) of the k-th pair with i <= j in an event of n items; rows are i, row i holds n - i entries
@@ -122,7 +126,9 @@ __device__ __forceinline__ uint32_t binom32(uint32_t c, int q) {
 
 constexpr int kChooseSmall = 64;        // events up to this long un-rank k-combinations by a short downward walk
 
-constexpr int kCombPositions = 8192;    // output positions of a tile the on-chip owner table covers
+constexpr int kCombPositions = 4096;    // output positions one owner table of the direct path covers (longer runs: chunk by chunk)
+constexpr int kOwnerPositions = 8192;   // ... and of the short-event kernels (two pair tables of 4096 entries alias its storage)
+static_assert(2 * kCombPositions <= kOwnerPositions + 128, "pair tables must fit the owner table's storage");
 
 struct CombIndex {
     int64_t v[5];
@@ -175,20 +181,240 @@ __device__ __forceinline__ CombIndex unrank(int64_t m, int64_t na, int64_t nb, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pair table: the (left, right) item of every output position of a tile, built EVENT-parallel in shared memory --
-// a thread walks the pairs of its event in output order (two counters, no un-ranking, no owner lookup) and
-// drops them at the event's slot; the output-parallel sweep that follows reads its pair with two 16-bit loads and
-// keeps its coalesced global stores.  Used whenever the tile's output run fits the table and no single event
-// dominates it (a thread would walk that event alone); otherwise the callers fall back to owner table + un-ranking.
+// Direct tables: every OUTPUT position of a tile finds its combination with a handful of instructions and no
+// divergence -- the usual path of all four kernels below.
+//   * owner table (jg_tile.cuh): output position -> event, built by scatter + running maximum over chunks of
+//     kCombPositions positions (a tile of "choose 4" holds more outputs than one table: it is swept chunk by chunk);
+//   * event info (16 bytes per event, built event-parallel): where the event's outputs and items start, relative to
+//     the tile, and how to turn the rank r of an output inside its event into item indices:
+//       pairs / distincts / choose(k): a look-up table indexed by (combinations of all shorter events) + r holds the
+//         k indices in 6-bit fields -- events up to comb_lut_max_n items; the table is filled once per device by
+//         running the exact un-ranking above on every (n, r), so both paths agree by construction.  Its head (events
+//         up to comb_lut_stage_n items: every collider event) is copied to shared memory by each CTA while the
+//         offsets tiles are in flight; the rest is read from global memory (with ~35 KB of shared memory per CTA the
+//         L1 is too small to keep it: reading everything from there made the pair kernels 10 - 80 % slower);
+//       cross: i = r / nb by one multiply-high with a per-event reciprocal, j = r - i * nb;
+//   * longer events un-rank arithmetically (rare lanes); tiles whose runs do not fit the packed fields (2^20 outputs,
+//     cross with 4096 or more right-hand items in one event) take the general path of each kernel.
+// Round 2 (profiles/r2_comb_direct.md): the event-parallel pair table this replaces cost 2.9 warp instructions per
+// pair at 18 of 32 lanes active (a warp walked the longest of its 32 events).
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kNoLut = 0xffffffffu;
+constexpr int kCombLutShared = 1536;          // entries of the table a CTA keeps on chip
+constexpr int kCombDirectMax = 1 << 20;      // outputs of a tile the packed event info can address
+constexpr int kCrossMaxRight = 1 << 12;
+
+__host__ __device__ constexpr int comb_lut_slot(int kind, int k) { return kind == JG_COMB_PAIRS ? 0 : (kind == JG_COMB_DISTINCTS ? 1 : k); }
+__host__ __device__ constexpr int comb_lut_max_n(int kind, int k) {
+    return kind != JG_COMB_CHOOSE ? 24 : (k == 2 ? 24 : (k == 3 ? 20 : (k == 4 ? 16 : 14)));
+}
+// events up to this long are un-ranked from the on-chip head of the table
+__host__ __device__ constexpr int comb_lut_stage_n(int kind, int k) { return (kind == JG_COMB_CHOOSE && k == 5) ? 10 : 12; }
+// number of combinations of all events shorter than n: the first table entry of the n-item events
+__host__ __device__ inline uint32_t comb_lut_base(int kind, int k, uint32_t n) {
+    if (kind == JG_COMB_PAIRS) return n == 0 ? 0u : (n - 1) * n * (n + 1) / 6;                 // sum m(m+1)/2
+    if (kind == JG_COMB_DISTINCTS) return n < 3 ? 0u : n * (n - 1) * (n - 2) / 6;              // sum m(m-1)/2 = C(n, 3)
+    // sum over m < n of C(m, k) = C(n, k + 1)
+    if (n < static_cast<uint32_t>(k + 1)) return 0u;
+    uint32_t c = 1;
+    for (int q = 1; q <= k + 1; ++q) c = c * (n - (k + 1) + q) / q;      // exact at every step, < 2^32 for n <= 25
+    return c;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+comb_lut_kernel(uint32_t *__restrict__ lut, int k) {
+    const uint32_t n = blockIdx.x;
+    const uint32_t base = comb_lut_base(KIND, k, n), cnt = comb_lut_base(KIND, k, n + 1) - base;
+    const int ncols = KIND == JG_COMB_CHOOSE ? k : 2;
+    for (uint32_t m = threadIdx.x; m < cnt; m += blockDim.x) {
+        const CombIndex r = unrank<KIND>(m, n, 0, k);
+        uint32_t code = 0;
+        for (int c = 0; c < ncols; ++c) code |= static_cast<uint32_t>(r.v[c]) << (6 * c);
+        lut[base + m] = code;
+    }
+}
+
+// the table of (kind, k) on the current device, filled on first use
+static const uint32_t *comb_lut(int kind, int k, cudaStream_t s) {
+    if (kind == JG_COMB_CROSS) return nullptr;
+    constexpr int kMaxDev = 64;
+    static std::mutex mu;
+    static uint32_t *tab[kMaxDev][6] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    const int slot = comb_lut_slot(kind, k);
+    std::lock_guard<std::mutex> lock(mu);
+    if (tab[dev][slot]) return tab[dev][slot];
+    const int maxn = comb_lut_max_n(kind, k);
+    const uint32_t entries = comb_lut_base(kind, k, static_cast<uint32_t>(maxn) + 1);
+    uint32_t *t = nullptr;
+    if (cudaMalloc(&t, static_cast<size_t>(entries) * 4) != cudaSuccess) return nullptr;
+    switch (kind) {
+        case JG_COMB_PAIRS: comb_lut_kernel<JG_COMB_PAIRS><<<maxn + 1, 256, 0, s>>>(t, k); break;
+        case JG_COMB_DISTINCTS: comb_lut_kernel<JG_COMB_DISTINCTS><<<maxn + 1, 256, 0, s>>>(t, k); break;
+        default: comb_lut_kernel<JG_COMB_CHOOSE><<<maxn + 1, 256, 0, s>>>(t, k); break;
+    }
+    // once per device and table: later calls may come on other streams
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaFree(t);
+        return nullptr;
+    }
+    tab[dev][slot] = t;
+    return t;
+}
+
+template <int KIND>
+__device__ __noinline__ CombIndex unrank_call(uint32_t m, uint32_t na, int k) {
+    return unrank<KIND>(m, na, 0, k);
+}
+
+struct CombLut {
+    const uint32_t *table;     // device memory
+    uint32_t staged;           // leading entries every CTA copies to shared memory
+};
+
+static CombLut comb_lut_for(int kind, int k, cudaStream_t s) {
+    CombLut l{comb_lut(kind, k, s), 0};
+    if (l.table) l.staged = comb_lut_base(kind, k, static_cast<uint32_t>(comb_lut_stage_n(kind, k)) + 1);
+    return l;
+}
+
+// all threads, before the offsets tiles are loaded: the copy's latency hides behind theirs (made visible by the
+// barrier that follows those loads)
+__device__ __forceinline__ void comb_stage_lut(uint32_t *__restrict__ s_lut, const CombLut &lut) {
+    for (uint32_t i = threadIdx.x; i < lut.staged; i += kTileThreads) s_lut[i] = __ldg(lut.table + i);
+}
+
+// Shared memory of the direct path (one per kernel, next to the offsets tiles)
+template <int KIND, bool VALUES = false>
+struct CombShared {
+    uint4 info[kTileEvents];                                    // one entry per event of the tile
+    uint16_t own[kCombPositions + 128];                         // owner of every output position of the current chunk
+    uint16_t right[VALUES ? kCombPositions : 1];                // value forms: own / right double as the pair table
+    uint32_t lut[KIND == JG_COMB_CROSS ? 1 : kCombLutShared];   // head of the table
+    uint16_t carry[kTileThreads / kWarp];                       // owner of the first position of each warp's part
+    int flags;                                                  // 1: general path, 2: some event is not in the on-chip head
+};
+
+template <int KIND, bool VALUES = false>
+struct CombDirect {
+    CombShared<KIND, VALUES> &sh;
+    CombLut lut;
+    int k;
+
+    // all threads, first thing in the kernel (nothing here depends on the offsets: it overlaps their load; the
+    // barrier after that load covers it)
+    __device__ __forceinline__ void prologue() const {
+        if (threadIdx.x == 0) sh.flags = 0;
+        owner_clear(sh.own, kCombPositions);
+        if constexpr (KIND != JG_COMB_CROSS) {
+            for (uint32_t i = threadIdx.x; i < lut.staged; i += kTileThreads) sh.lut[i] = __ldg(lut.table + i);
+        }
+    }
+
+    // all threads, after the offsets tiles are on chip: ONE walk over the events builds their info, drops them on the
+    // first chunk's owner table and registers the warp carries; then the running maximum.  Returns the flags
+    // (bit 0: take the general path) after two barriers.
+    __device__ __forceinline__ int setup(const EventTile &pt, const int64_t *__restrict__ s_oa,
+                                         const int64_t *__restrict__ s_ob, int64_t total) const {
+        int bad = (total < kCombDirectMax && (s_oa[pt.nev] - s_oa[0]) < (1ll << 32)) ? 0 : 1;
+        if (KIND == JG_COMB_CROSS) bad |= (s_ob[pt.nev] - s_ob[0]) < (1ll << 32) ? 0 : 1;
+        else bad |= lut.table != nullptr ? 0 : 1;               // (the table could not be allocated: un-rank everything)
+        const int64_t p0 = pt.off[0], a0 = s_oa[0];
+        const int stage_n = comb_lut_stage_n(KIND, k), maxn = comb_lut_max_n(KIND, k);
+        const int L = static_cast<int>(min(total, static_cast<int64_t>(kCombPositions)));
+        const int lg = owner_chunk_lg(L);
+#pragma unroll 1
+        for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) {
+            uint4 w;
+            const int64_t pa = pt.off[ev] - p0, pb = pt.off[ev + 1] - p0;
+            w.x = static_cast<uint32_t>(pa);
+            w.z = static_cast<uint32_t>(s_oa[ev] - a0);
+            const int64_t na = s_oa[ev + 1] - s_oa[ev];
+            if constexpr (KIND == JG_COMB_CROSS) {
+                const int64_t nb = s_ob[ev + 1] - s_ob[ev];
+                if (nb >= kCrossMaxRight) bad |= 1;
+                const uint32_t nb32 = static_cast<uint32_t>(nb);
+                w.x |= nb32 << 20;
+                w.y = nb32 > 1 ? 0xffffffffu / nb32 + 1u : 0u;      // floor(2^32 / nb) + 1 (2^32 / nb for powers of two)
+                w.w = static_cast<uint32_t>(s_ob[ev] - s_ob[0]);
+            } else {
+                w.y = na <= maxn ? comb_lut_base(KIND, k, static_cast<uint32_t>(na)) : kNoLut;
+                w.w = static_cast<uint32_t>(na);
+                if (na > stage_n && pb > pa) bad |= 2;
+            }
+            sh.info[ev] = w;
+            owner_scatter_event(sh.own, sh.carry, ev, pa, pb, L, lg);
+        }
+        if (bad) atomicOr(&sh.flags, bad);
+        __syncthreads();
+        const int flags = sh.flags;
+        if (flags & 1) return flags;
+        owner_scan(sh.own, sh.carry, L, lg);
+        __syncthreads();
+        return flags;
+    }
+
+    // all threads: the owner table of the chunk that starts at output `cb` of the tile (cb > 0; the first chunk's
+    // table comes out of setup)
+    __device__ __forceinline__ void next_chunk(const EventTile &pt, int64_t cb, int L) const {
+        __syncthreads();                                        // the previous chunk's table is still being read
+        owner_clear(sh.own, L);
+        __syncthreads();
+        const int lg = owner_chunk_lg(L);
+        const int64_t e0 = pt.off[0] + cb;
+#pragma unroll 1
+        for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads)
+            owner_scatter_event(sh.own, sh.carry, ev, pt.off[ev] - e0, pt.off[ev + 1] - e0, L, lg);
+        __syncthreads();
+        owner_scan(sh.own, sh.carry, L, lg);
+        __syncthreads();
+    }
+
+    // local item indices of the output at tile-relative position qt, q-th of the current chunk (the info of its event
+    // is returned in w).  SIMPLE: every event of the tile is in the on-chip head of the table -- no branch at all.
+    template <bool SIMPLE, int NC>
+    __device__ __forceinline__ void resolve(uint32_t qt, int q, uint32_t (&idx)[NC], uint4 &w) const {
+        w = sh.info[sh.own[q]];
+        if constexpr (KIND == JG_COMB_CROSS) {
+            const uint32_t nb = w.x >> 20, r = qt - (w.x & 0xfffffu);
+            const uint32_t i = nb == 1 ? r : __umulhi(r, w.y);        // r * nb < 2^32: the reciprocal is exact
+            idx[0] = i;
+            idx[1] = r - i * nb;
+        } else {
+            const uint32_t r = qt - w.x;
+            if (SIMPLE || w.y != kNoLut) {
+                const uint32_t at = w.y + r;
+                const uint32_t code = (SIMPLE || at < lut.staged) ? sh.lut[at] : __ldg(lut.table + at);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) idx[c] = c == NC - 1 ? code >> (6 * c) : (code >> (6 * c)) & 63u;
+            } else {
+                const CombIndex ci = unrank_call<KIND>(r, w.w, k);      // a call: the usual path stays lean
+#pragma unroll
+                for (int c = 0; c < NC; ++c) idx[c] = static_cast<uint32_t>(ci.v[c]);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Pair table of the VALUE forms: the (left, right) item of every output position, as 16-bit positions relative to the
+// tile's first item; the output-parallel sweep reads its pair with two 16-bit loads and keeps its coalesced stores.
+// Tiles of short events (dimuon-like: a few pairs per event) build it EVENT-parallel -- a thread walks the pairs of
+// its event in output order with two counters: 2.2 warp instructions per pair, still fewer than the direct tables need
+// when an event's info serves only 2 - 4 outputs (measured, profiles/r2_comb_direct.md).  Longer runs or events are
+// resolved through the direct tables chunk by chunk INTO the same pair table (comb_value_tables), so each value
+// kernel has one sweep.
 //   REL = true : entries are positions relative to the first item of the tile (a0 / b0) -> value gathers
 //   REL = false: entries are the local indices i, j                                  -> arg forms
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kPairTable = 4096;         // two uint16 tables of this many entries alias the owner table's storage
-constexpr int kPairEventMax = 384;       // more outputs than this in one event: un-rank instead
-static_assert(2 * kPairTable <= kCombPositions + 128, "pair tables must fit the owner table's storage");
+constexpr int kPairTable = kCombPositions;   // entries of the left and of the right table
+constexpr int kPairEventMax = 384;           // more outputs than this in one event: the direct tables instead
+constexpr int kPairStride = kCombPositions + 128;    // the right-hand table follows the left-hand one (CombShared)
 
-template <int KIND, bool REL>
-__device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uint16_t *__restrict__ /* s_l + kPairTable */,
+template <int KIND, bool REL, int STRIDE>
+__device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uint16_t *__restrict__ /* s_l + STRIDE */,
                                                  const EventTile &pt, const int64_t *__restrict__ s_oa,
                                                  const int64_t *__restrict__ s_ob) {
     const int64_t p0 = pt.off[0], total = pt.off[pt.nev] - p0;
@@ -203,10 +429,10 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
     for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) {
         const int cnt = static_cast<int>(pt.off[ev + 1] - pt.off[ev]);
         if (cnt == 0) continue;
-        // one moving pointer: the right-hand table sits kPairTable entries behind the left-hand one (every caller
-        // carves both out of one buffer), and the counters already carry the event's relative start
+        // one moving pointer (the right-hand entry at a fixed distance), the counters carry the event's relative start
         uint16_t *l = s_l + (pt.off[ev] - p0);
         uint16_t *const end = l + cnt;
+        constexpr int rd = STRIDE;
         const int na = static_cast<int>(s_oa[ev + 1] - s_oa[ev]);
         const int ra = REL ? static_cast<int>(s_oa[ev] - s_oa[0]) : 0;
         if constexpr (KIND == JG_COMB_CROSS) {
@@ -217,7 +443,7 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
 #pragma unroll 1
             do {
                 l[0] = static_cast<uint16_t>(i);
-                l[kPairTable] = static_cast<uint16_t>(j);
+                l[rd] = static_cast<uint16_t>(j);
                 ++l;
                 if (++j == jend) {
                     j = rb;
@@ -231,7 +457,7 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
 #pragma unroll 1
             do {
                 l[0] = static_cast<uint16_t>(i);
-                l[kPairTable] = static_cast<uint16_t>(j);
+                l[rd] = static_cast<uint16_t>(j);
                 ++l;
                 if (++j == jend) {
                     ++i;
@@ -241,6 +467,49 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
         }
     }
     __syncthreads();
+    return true;
+}
+
+// The pair table(s) of a tile for the value kernels: `sweep(cb, L)` is called once per chunk of the tile's output run
+// with sh.own[q] / sh.right[q] = the tile-relative left / right item of output cb + q.  false: nothing was done, the
+// tile takes the caller's general path.  All threads.
+template <int KIND, class Sweep>
+__device__ __forceinline__ bool comb_value_tables(CombShared<KIND, true> &sh, const CombLut &lut, const EventTile &pt,
+                                                  const int64_t *__restrict__ s_oa, const int64_t *__restrict__ s_ob,
+                                                  Sweep sweep) {
+    using Shared = CombShared<KIND, true>;
+    static_assert(offsetof(Shared, right) - offsetof(Shared, own) == 2 * kPairStride, "the right-hand table must follow the left-hand one");
+    const int64_t total = pt.off[pt.nev] - pt.off[0];
+    if (build_pair_table<KIND, true, kPairStride>(sh.own, sh.right, pt, s_oa, s_ob)) {
+        sweep(int64_t(0), static_cast<int>(total));
+        return true;
+    }
+    // (16-bit item positions: a tile whose items do not fit takes the general path)
+    const bool narrow = (s_oa[pt.nev] - s_oa[0]) < 65536 && (KIND != JG_COMB_CROSS || (s_ob[pt.nev] - s_ob[0]) < 65536);
+    const CombDirect<KIND, true> direct{sh, lut, 2};
+    const int flags = direct.setup(pt, s_oa, s_ob, narrow ? total : int64_t(kCombDirectMax));
+    if (flags & 1) return false;
+#pragma unroll 1
+    for (int64_t cb = 0; cb < total; cb += kCombPositions) {
+        const int L = static_cast<int>(min(static_cast<int64_t>(kCombPositions), total - cb));
+        if (cb) direct.next_chunk(pt, cb, L);
+        const uint32_t q0 = static_cast<uint32_t>(cb);
+        // every look-up of the chunk is resolved ONCE, the left item over the owner entry it came from
+        auto lookup = [&](auto simple) {
+#pragma unroll 2
+            for (int q = threadIdx.x; q < L; q += kTileThreads) {
+                uint32_t idx[2];
+                uint4 w;
+                direct.template resolve<decltype(simple)::value>(q0 + q, q, idx, w);
+                sh.own[q] = static_cast<uint16_t>(w.z + idx[0]);
+                sh.right[q] = static_cast<uint16_t>(((KIND == JG_COMB_CROSS) ? w.w : w.z) + idx[1]);
+            }
+        };
+        if (flags & 2) lookup(std::false_type{});
+        else lookup(std::true_type{});
+        __syncthreads();
+        sweep(cb, L);
+    }
     return true;
 }
 
@@ -256,17 +525,19 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     __shared__ int64_t s_oa[kTileEvents + 1];
     __shared__ int64_t s_ob[kTileEvents + 1];
     EventTile pt, ta, tb;
-    pt.load(s_po, out_offsets, n, blockIdx.x);
-    ta.load(s_oa, offsets_a, n, blockIdx.x);
-    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    // the two or three offsets tiles in ONE memory round trip
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
     const int ncols = (KIND == JG_COMB_CHOOSE) ? k : 2;
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
-    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     if constexpr (KIND == JG_COMB_PAIRS || KIND == JG_COMB_CROSS) {      // (distincts: mostly 0-1 pairs, measured slower)
         // relative positions when absolute indices are wanted (the tile's first item is added back), else i, j
         uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        const bool fast = absolute ? build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)
-                                   : build_pair_table<KIND, false>(s_l, s_r, pt, s_oa, s_ob);
+        const bool fast = absolute ? build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)
+                                   : build_pair_table<KIND, false, kPairTable>(s_l, s_r, pt, s_oa, s_ob);
         if (fast) {
             const int64_t add_l = absolute ? s_oa[0] : 0;
             const int64_t add_r = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]) : 0;
@@ -279,6 +550,74 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
             }
             return;
         }
+    }
+    const bool table = (p1 - p0) <= kOwnerPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
+        const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, k);
+        const int64_t base_a = absolute ? s_oa[ev] : 0;
+        const int64_t base_b = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) : 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            if (c < ncols) __stcs(cols.p[c] + p, r.v[c] + ((c == 1 && KIND == JG_COMB_CROSS) ? base_b : base_a));
+        }
+    }
+}
+
+// the same on the direct tables (choose, cross, and pairs / distincts of long events)
+template <int KIND>
+__global__ void __launch_bounds__(kTileThreads)
+comb_fill_direct_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                 const int64_t *__restrict__ out_offsets, ColPtrs cols, int k, int absolute, const CombLut lut) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[KIND == JG_COMB_CROSS ? kTileEvents + 1 : 1];
+    __shared__ __align__(16) CombShared<KIND> sh;
+    uint16_t *const s_own = sh.own;
+    const CombDirect<KIND> direct{sh, lut, k};
+    direct.prologue();
+    EventTile pt, ta, tb;
+    // the two or three offsets tiles in ONE memory round trip
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
+    const int ncols = (KIND == JG_COMB_CHOOSE) ? k : 2;
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    const int flags = direct.setup(pt, s_oa, s_ob, p1 - p0);
+    if (!(flags & 1)) {
+        const int64_t a0 = absolute ? s_oa[0] : 0, b0 = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]) : 0;
+        const uint32_t rel = absolute ? 0xffffffffu : 0u;        // local indices: the event's start is not added
+#pragma unroll 1
+        for (int64_t cb = 0; cb < p1 - p0; cb += kCombPositions) {
+            const int L = static_cast<int>(min(static_cast<int64_t>(kCombPositions), p1 - p0 - cb));
+            if (cb) direct.next_chunk(pt, cb, L);
+            const uint32_t q0 = static_cast<uint32_t>(cb);
+            int64_t *const c0 = cols.p[0] + p0 + cb, *const c1 = cols.p[1] + p0 + cb;
+            auto sweep = [&](auto simple) {
+#pragma unroll 2
+                for (int q = threadIdx.x; q < L; q += kTileThreads) {
+                    uint32_t idx[KIND == JG_COMB_CHOOSE ? 5 : 2];
+                    uint4 w;
+                    direct.template resolve<decltype(simple)::value>(q0 + q, q, idx, w);
+                    const int64_t sa = a0 + (w.z & rel);
+                    __stcs(c0 + q, sa + idx[0]);
+                    __stcs(c1 + q, ((KIND == JG_COMB_CROSS) ? b0 + (w.w & rel) : sa) + idx[1]);
+                    if constexpr (KIND == JG_COMB_CHOOSE) {
+#pragma unroll
+                        for (int c = 2; c < 5; ++c)
+                            if (c < ncols) __stcs(cols.p[c] + p0 + cb + q, sa + idx[c]);
+                    }
+                }
+            };
+            if (flags & 2) sweep(std::false_type{});
+            else sweep(std::true_type{});
+        }
+        return;
     }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
@@ -307,15 +646,17 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     __shared__ int64_t s_oa[kTileEvents + 1];
     __shared__ int64_t s_ob[kTileEvents + 1];
     EventTile pt, ta, tb;
-    pt.load(s_po, out_offsets, n, blockIdx.x);
-    ta.load(s_oa, offsets_a, n, blockIdx.x);
-    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    // the two or three offsets tiles in ONE memory round trip
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
-    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     {
         // (staging the tile's content runs in shared memory by TMA was measured: slower -- the loads below hit L1)
         uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+        if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
             const VA *ca = content_a + s_oa[0];
             const VB *cb = content_b + ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]);
             VA *ol = out_l + p0;
@@ -344,6 +685,94 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
             }
             return;
         }
+    }
+    const bool table = (p1 - p0) <= kOwnerPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
+    for (int64_t pb = p0 + threadIdx.x; pb < p1; pb += 2 * kTileThreads) {
+        int64_t ia[2], ib[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = pb + u * kTileThreads;
+            if (p < p1) {
+                const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
+                const int64_t na = s_oa[ev + 1] - s_oa[ev];
+                const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+                CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
+                ia[u] = s_oa[ev] + r.v[0];
+                ib[u] = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
+            }
+        }
+        VA va[2];
+        VB vb[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (pb + u * kTileThreads < p1) {
+                va[u] = __ldg(content_a + ia[u]);
+                vb[u] = __ldg(content_b + ib[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = pb + u * kTileThreads;
+            if (p < p1) {
+                __stcs(out_l + p, va[u]);
+                __stcs(out_r + p, vb[u]);
+            }
+        }
+    }
+}
+
+// the same for long events: pair tables chunk by chunk out of the direct tables
+template <int KIND, typename VA, typename VB>
+__global__ void __launch_bounds__(kTileThreads, 5)
+comb_gather2_direct_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                    const int64_t *__restrict__ out_offsets, const VA *__restrict__ content_a,
+                    const VB *__restrict__ content_b, VA *__restrict__ out_l, VB *__restrict__ out_r,
+                    const CombLut lut) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[KIND == JG_COMB_CROSS ? kTileEvents + 1 : 1];
+    __shared__ __align__(16) CombShared<KIND, true> sh;
+    uint16_t *const s_own = sh.own;
+    CombDirect<KIND, true>{sh, lut, 2}.prologue();
+    EventTile pt, ta, tb;
+    // the two or three offsets tiles in ONE memory round trip, and the items the pairs will gather already on their way
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync<sizeof(VA)>(s_oa, offsets_a, n, blockIdx.x, content_a);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync<sizeof(VB)>(s_ob, offsets_b, n, blockIdx.x, content_b);
+    __syncthreads();
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    {
+        // (staging the tile's content runs in shared memory by TMA was measured: slower -- the loads below hit L1)
+        const VA *ca = content_a + s_oa[0];
+        const VB *cb_ = content_b + ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]);
+        if (comb_value_tables<KIND>(sh, lut, pt, s_oa, s_ob, [&](int64_t cb, int L) {
+                VA *ol = out_l + p0 + cb;
+                VB *orr = out_r + p0 + cb;
+#pragma unroll 1
+                for (int qb = threadIdx.x; qb < L; qb += 4 * kTileThreads) {
+                    VA va[4];
+                    VB vb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = qb + u * kTileThreads;
+                        if (q < L) {
+                            va[u] = __ldg(ca + sh.own[q]);
+                            vb[u] = __ldg(cb_ + sh.right[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = qb + u * kTileThreads;
+                        if (q < L) {
+                            __stcs(ol + q, va[u]);
+                            __stcs(orr + q, vb[u]);
+                        }
+                    }
+                }
+            }))
+            return;
     }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
@@ -400,15 +829,17 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
     __shared__ int64_t s_po[kTileEvents + 1];
     __shared__ int64_t s_oa[kTileEvents + 1];
     __shared__ int64_t s_ob[kTileEvents + 1];
-    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     EventTile pt, ta, tb;
-    pt.load(s_po, out_offsets, n, blockIdx.x);
-    ta.load(s_oa, offsets_a, n, blockIdx.x);
-    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    // the two or three offsets tiles in ONE memory round trip
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     {
         uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+        if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
             const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
             const int total = static_cast<int>(p1 - p0);
 #pragma unroll 1
@@ -428,6 +859,67 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
             }
             return;
         }
+    }
+    const bool table = (p1 - p0) <= kOwnerPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
+#pragma unroll 1
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kTileThreads) {
+        const int ev = table ? static_cast<int>(s_own[p - p0]) : pt.find_event(p);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p - s_po[ev], na, nb, 2);
+        const int64_t ia = s_oa[ev] + r.v[0];
+        const int64_t ib = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) + r.v[1];
+        V vl[4], vr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < cols.nl) vl[c] = __ldg(static_cast<const V *>(cols.in_l[c]) + ia);
+            if (c < cols.nr) vr[c] = __ldg(static_cast<const V *>(cols.in_r[c]) + ib);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < cols.nl) __stcs(static_cast<V *>(cols.out_l[c]) + p, vl[c]);
+            if (c < cols.nr) __stcs(static_cast<V *>(cols.out_r[c]) + p, vr[c]);
+        }
+    }
+}
+
+template <int KIND, typename V>
+__global__ void __launch_bounds__(kTileThreads, 5)
+comb_gather_multi_direct_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                         const int64_t *__restrict__ out_offsets, MultiCols cols, const CombLut lut) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[KIND == JG_COMB_CROSS ? kTileEvents + 1 : 1];
+    __shared__ __align__(16) CombShared<KIND, true> sh;
+    uint16_t *const s_own = sh.own;
+    CombDirect<KIND, true>{sh, lut, 2}.prologue();
+    EventTile pt, ta, tb;
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync<sizeof(V)>(s_oa, offsets_a, n, blockIdx.x, cols.nl > 0 ? cols.in_l[0] : cols.in_r[0]);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync<sizeof(V)>(s_ob, offsets_b, n, blockIdx.x, cols.nr > 0 ? cols.in_r[0] : cols.in_l[0]);
+    __syncthreads();
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    {
+        const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
+        if (comb_value_tables<KIND>(sh, lut, pt, s_oa, s_ob, [&](int64_t cb, int L) {
+#pragma unroll 1
+                for (int q = threadIdx.x; q < L; q += kTileThreads) {
+                    const int64_t ia = a0 + sh.own[q], ib = b0 + sh.right[q];
+                    V vl[4], vr[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < cols.nl) vl[c] = __ldg(static_cast<const V *>(cols.in_l[c]) + ia);
+                        if (c < cols.nr) vr[c] = __ldg(static_cast<const V *>(cols.in_r[c]) + ib);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < cols.nl) __stcs(static_cast<V *>(cols.out_l[c]) + p0 + cb + q, vl[c]);
+                        if (c < cols.nr) __stcs(static_cast<V *>(cols.out_r[c]) + p0 + cb + q, vr[c]);
+                    }
+                }
+            }))
+            return;
     }
     const bool table = (p1 - p0) <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(p1 - p0));
@@ -626,19 +1118,21 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     __shared__ int64_t s_po[kTileEvents + 1];
     __shared__ int64_t s_oa[kTileEvents + 1];
     __shared__ int64_t s_ob[kTileEvents + 1];
-    __shared__ __align__(16) uint16_t s_own[kCombPositions + 128];
+    __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     extern __shared__ __align__(16) unsigned char s_dyn[];        // spill slots: nslots x U x 256 values of T
     T *slots = reinterpret_cast<T *>(s_dyn) + threadIdx.x;
     EventTile pt, ta, tb;
-    pt.load(s_po, out_offsets, n, blockIdx.x);
-    ta.load(s_oa, offsets_a, n, blockIdx.x);
-    if (KIND == JG_COMB_CROSS) tb.load(s_ob, offsets_b, n, blockIdx.x);
+    // the two or three offsets tiles in ONE memory round trip
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     const int64_t total = p1 - p0;
     if (total <= 0) return;
     const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
     uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-    if (build_pair_table<KIND, true>(s_l, s_r, pt, s_oa, s_ob)) {
+    if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
         eval_tile<T, U, uint32_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, uint32_t &ia, uint32_t &ib) {
             ia = s_l[q];
             ib = s_r[q];
@@ -646,6 +1140,50 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
         return;
     }
     // long events: owner table (binary search for very long runs) + un-ranking, 64-bit positions
+    const bool table = total <= kOwnerPositions;
+    if (table) build_owner_table(s_own, pt, static_cast<int>(total));
+    eval_tile<T, 2, int64_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, int64_t &ia, int64_t &ib) {
+        const int ev = table ? static_cast<int>(s_own[q]) : pt.find_event(p0 + q);
+        const int64_t na = s_oa[ev + 1] - s_oa[ev];
+        const int64_t nb = (KIND == JG_COMB_CROSS) ? (s_ob[ev + 1] - s_ob[ev]) : 0;
+        CombIndex r = unrank<KIND>(p0 + q - s_po[ev], na, nb, 2);
+        ia = s_oa[ev] - a0 + r.v[0];
+        ib = ((KIND == JG_COMB_CROSS) ? s_ob[ev] : s_oa[ev]) - b0 + r.v[1];
+    });
+}
+
+template <int KIND, typename T, int U>       // U: positions per thread and step on the pair-table path
+__global__ void __launch_bounds__(kTileThreads, 4)        // (64 registers)
+comb_eval_direct_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restrict__ offsets_b, int64_t n,
+                 const int64_t *__restrict__ out_offsets, const __grid_constant__ JgEvalProgram pr,
+                 void *__restrict__ out, const CombLut lut) {
+    __shared__ int64_t s_po[kTileEvents + 1];
+    __shared__ int64_t s_oa[kTileEvents + 1];
+    __shared__ int64_t s_ob[KIND == JG_COMB_CROSS ? kTileEvents + 1 : 1];
+    __shared__ __align__(16) CombShared<KIND, true> sh;
+    uint16_t *const s_own = sh.own;
+    extern __shared__ __align__(16) unsigned char s_dyn[];        // spill slots: nslots x U x 256 values of T
+    T *slots = reinterpret_cast<T *>(s_dyn) + threadIdx.x;
+    CombDirect<KIND, true>{sh, lut, 2}.prologue();
+    EventTile pt, ta, tb;
+    pt.load_nosync(s_po, out_offsets, n, blockIdx.x);
+    ta.load_nosync(s_oa, offsets_a, n, blockIdx.x);
+    if (KIND == JG_COMB_CROSS) tb.load_nosync(s_ob, offsets_b, n, blockIdx.x);
+    __syncthreads();
+    const int64_t p0 = pt.first_element(), p1 = pt.last_element();
+    const int64_t total = p1 - p0;
+    if (total <= 0) return;
+    const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
+    // the U positions a thread evaluates together cost two 16-bit loads each: resolving the direct tables inside the
+    // interpreter's loop took 122 registers (or spills at 64)
+    if (comb_value_tables<KIND>(sh, lut, pt, s_oa, s_ob, [&](int64_t cb, int L) {
+            eval_tile<T, U, uint32_t>(pr, slots, a0, b0, p0 + cb, L, out, [&](int64_t q, uint32_t &ia, uint32_t &ib) {
+                ia = sh.own[q];
+                ib = sh.right[q];
+            });
+        }))
+        return;
+    // runs that do not fit the packed event info: owner table (binary search for very long runs) + un-ranking, 64-bit positions
     const bool table = total <= kCombPositions;
     if (table) build_owner_table(s_own, pt, static_cast<int>(total));
     eval_tile<T, 2, int64_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, int64_t &ia, int64_t &ib) {
@@ -659,50 +1197,65 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
 }
 
 template <int KIND, typename T, int U>
-static int launch_comb_eval(const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const JgEvalProgram &pr,
-                            void *out, cudaStream_t s) {
+static int launch_comb_eval(bool direct, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                            const JgEvalProgram &pr, void *out, cudaStream_t s) {
     const size_t dyn = static_cast<size_t>(pr.nslots) * U * kTileThreads * sizeof(T);
     static bool configured = false;          // per instantiation
     if (!configured) {
-        cudaFuncSetAttribute(comb_eval_kernel<KIND, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(JG_EVAL_MAX_SLOTS * U * kTileThreads * sizeof(T)));   // 80 KB
+        const int most = static_cast<int>(JG_EVAL_MAX_SLOTS * U * kTileThreads * sizeof(T));   // 80 KB
+        cudaFuncSetAttribute(comb_eval_kernel<KIND, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        cudaFuncSetAttribute(comb_eval_direct_kernel<KIND, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         configured = true;
     }
-    comb_eval_kernel<KIND, T, U><<<tile_grid(n), kTileThreads, dyn, s>>>(oa, ob, n, po, pr, out);
+    if (direct) comb_eval_direct_kernel<KIND, T, U><<<tile_grid(n), kTileThreads, dyn, s>>>(oa, ob, n, po, pr, out, comb_lut_for(KIND, 2, s));
+    else comb_eval_kernel<KIND, T, U><<<tile_grid(n), kTileThreads, dyn, s>>>(oa, ob, n, po, pr, out);
     return check_launch("comb_eval_kernel");
 }
 
 template <int KIND>
-static int launch_comb_eval_dtype(int dtype, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+static int launch_comb_eval_dtype(bool direct, int dtype, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
                                   const JgEvalProgram &pr, void *out, cudaStream_t s) {
-    if (dtype == JG_F32) return launch_comb_eval<KIND, float, 8>(oa, ob, n, po, pr, out, s);
-    if (dtype == JG_F64) return launch_comb_eval<KIND, double, 4>(oa, ob, n, po, pr, out, s);
+    if (dtype == JG_F32) return launch_comb_eval<KIND, float, 8>(direct, oa, ob, n, po, pr, out, s);
+    if (dtype == JG_F64) return launch_comb_eval<KIND, double, 4>(direct, oa, ob, n, po, pr, out, s);
     set_error("jg_comb_eval: compute dtype must be float32 or float64 (got %d)", dtype);
     return -2;
 }
 
-template <int KIND>
-static int launch_gather_multi(int itemsize, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
-                               const MultiCols &mc, cudaStream_t s) {
+template <int KIND, typename V>
+static void launch_gather_multi_v(bool direct, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                                  const MultiCols &mc, cudaStream_t s) {
     const unsigned g = tile_grid(n);
+    if (direct) comb_gather_multi_direct_kernel<KIND, V><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc, comb_lut_for(KIND, 2, s));
+    else comb_gather_multi_kernel<KIND, V><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc);
+}
+
+template <int KIND>
+static int launch_gather_multi(bool direct, int itemsize, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                               const MultiCols &mc, cudaStream_t s) {
     switch (itemsize) {
-        case 1: comb_gather_multi_kernel<KIND, uint8_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
-        case 2: comb_gather_multi_kernel<KIND, uint16_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
-        case 4: comb_gather_multi_kernel<KIND, uint32_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
-        case 8: comb_gather_multi_kernel<KIND, uint64_t><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, mc); break;
+        case 1: launch_gather_multi_v<KIND, uint8_t>(direct, oa, ob, n, po, mc, s); break;
+        case 2: launch_gather_multi_v<KIND, uint16_t>(direct, oa, ob, n, po, mc, s); break;
+        case 4: launch_gather_multi_v<KIND, uint32_t>(direct, oa, ob, n, po, mc, s); break;
+        case 8: launch_gather_multi_v<KIND, uint64_t>(direct, oa, ob, n, po, mc, s); break;
         default: set_error("jg_comb_gather_multi: unsupported itemsize %d", itemsize); return -2;
     }
     return check_launch("comb_gather_multi_kernel");
 }
 
 template <int KIND, typename VA>
-static int gather2_b(int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const void *ca,
-                     const void *cb, void *l, void *r, cudaStream_t s) {
+static int gather2_b(bool direct, int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
+                     const void *ca, const void *cb, void *l, void *r, cudaStream_t s) {
     const unsigned g = tile_grid(n);
-#define JG_G2(VB)                                                                                                   \
-    comb_gather2_kernel<KIND, VA, VB><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, static_cast<const VA *>(ca),         \
-                                                                 static_cast<const VB *>(cb), static_cast<VA *>(l),  \
-                                                                 static_cast<VB *>(r))
+    const CombLut lut = direct ? comb_lut_for(KIND, 2, s) : CombLut{nullptr, 0};
+#define JG_G2(VB)                                                                                                     \
+    if (direct)                                                                                                       \
+        comb_gather2_direct_kernel<KIND, VA, VB><<<g, kTileThreads, 0, s>>>(                                          \
+            oa, ob, n, po, static_cast<const VA *>(ca), static_cast<const VB *>(cb), static_cast<VA *>(l),            \
+            static_cast<VB *>(r), lut);                                                                               \
+    else                                                                                                              \
+        comb_gather2_kernel<KIND, VA, VB><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, static_cast<const VA *>(ca),       \
+                                                                     static_cast<const VB *>(cb), static_cast<VA *>(l), \
+                                                                     static_cast<VB *>(r))
     switch (itemsize_b) {
         case 1: JG_G2(uint8_t); break;
         case 2: JG_G2(uint16_t); break;
@@ -715,16 +1268,24 @@ static int gather2_b(int itemsize_b, const int64_t *oa, const int64_t *ob, int64
 }
 
 template <int KIND>
-static int gather2_a(int itemsize_a, int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po,
-                     const void *ca, const void *cb, void *l, void *r, cudaStream_t s) {
+static int gather2_a(bool direct, int itemsize_a, int itemsize_b, const int64_t *oa, const int64_t *ob, int64_t n,
+                     const int64_t *po, const void *ca, const void *cb, void *l, void *r, cudaStream_t s) {
     switch (itemsize_a) {
-        case 1: return gather2_b<KIND, uint8_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
-        case 2: return gather2_b<KIND, uint16_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
-        case 4: return gather2_b<KIND, uint32_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
-        case 8: return gather2_b<KIND, uint64_t>(itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 1: return gather2_b<KIND, uint8_t>(direct, itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 2: return gather2_b<KIND, uint16_t>(direct, itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 4: return gather2_b<KIND, uint32_t>(direct, itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
+        case 8: return gather2_b<KIND, uint64_t>(direct, itemsize_b, oa, ob, n, po, ca, cb, l, r, s);
     }
     set_error("jg_comb_gather2: unsupported itemsize %d", itemsize_a);
     return -2;
+}
+
+template <int KIND>
+static void launch_comb_fill(bool direct, const int64_t *oa, const int64_t *ob, int64_t n, const int64_t *po, const ColPtrs &cp,
+                             int k, int absolute, cudaStream_t s) {
+    const unsigned g = tile_grid(n);
+    if (direct) comb_fill_direct_kernel<KIND><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, cp, k, absolute, comb_lut_for(KIND, k, s));
+    else comb_fill_kernel<KIND><<<g, kTileThreads, 0, s>>>(oa, ob, n, po, cp, k, absolute);
 }
 
 }  // namespace jg
@@ -752,24 +1313,19 @@ int jg_comb_fill(int kind, int k, const int64_t *offsets_a, const int64_t *offse
                  const int64_t *out_offsets, int64_t *const *cols, int absolute, void *stream) {
     if (n <= 0) return 0;
     cudaStream_t s = as_stream(stream);
+    const bool long_events = (kind & JG_COMB_LONG) != 0;
+    kind &= ~JG_COMB_LONG;
     const int ncols = kind == JG_COMB_CHOOSE ? k : 2;
     JG_REQUIRE(ncols >= 2 && ncols <= 5, "jg_comb_fill: bad column count %d", ncols);
     ColPtrs cp{};
     for (int c = 0; c < ncols; ++c) cp.p[c] = cols[c];
-    const unsigned g = tile_grid(n);
+    // choose and cross always run on the direct tables (measured faster on short and on long events alike); pairs and
+    // distincts of dimuon-like events keep the event-parallel pair table / owner table + walk
     switch (kind) {
-        case JG_COMB_PAIRS:
-            comb_fill_kernel<JG_COMB_PAIRS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
-            break;
-        case JG_COMB_DISTINCTS:
-            comb_fill_kernel<JG_COMB_DISTINCTS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
-            break;
-        case JG_COMB_CHOOSE:
-            comb_fill_kernel<JG_COMB_CHOOSE><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
-            break;
-        case JG_COMB_CROSS:
-            comb_fill_kernel<JG_COMB_CROSS><<<g, kTileThreads, 0, s>>>(offsets_a, offsets_b, n, out_offsets, cp, k, absolute);
-            break;
+        case JG_COMB_PAIRS: launch_comb_fill<JG_COMB_PAIRS>(long_events, offsets_a, offsets_b, n, out_offsets, cp, k, absolute, s); break;
+        case JG_COMB_DISTINCTS: launch_comb_fill<JG_COMB_DISTINCTS>(long_events, offsets_a, offsets_b, n, out_offsets, cp, k, absolute, s); break;
+        case JG_COMB_CHOOSE: launch_comb_fill<JG_COMB_CHOOSE>(true, offsets_a, offsets_b, n, out_offsets, cp, k, absolute, s); break;
+        case JG_COMB_CROSS: launch_comb_fill<JG_COMB_CROSS>(true, offsets_a, offsets_b, n, out_offsets, cp, k, absolute, s); break;
         default:
             set_error("jg_comb_fill: bad kind %d", kind);
             return -2;
@@ -782,13 +1338,15 @@ int jg_comb_gather2(int kind, const int64_t *offsets_a, const int64_t *offsets_b
                     void *out_r, void *stream) {
     if (n <= 0) return 0;
     cudaStream_t s = as_stream(stream);
+    const bool direct = (kind & JG_COMB_LONG) != 0;
+    kind &= ~JG_COMB_LONG;
     switch (kind) {
         case JG_COMB_PAIRS:
-            return gather2_a<JG_COMB_PAIRS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+            return gather2_a<JG_COMB_PAIRS>(direct, itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
         case JG_COMB_DISTINCTS:
-            return gather2_a<JG_COMB_DISTINCTS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+            return gather2_a<JG_COMB_DISTINCTS>(direct, itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
         case JG_COMB_CROSS:
-            return gather2_a<JG_COMB_CROSS>(itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
+            return gather2_a<JG_COMB_CROSS>(direct, itemsize_a, itemsize_b, offsets_a, offsets_b, n, out_offsets, content_a, content_b, out_l, out_r, s);
     }
     set_error("jg_comb_gather2: bad kind %d", kind);
     return -2;
@@ -813,10 +1371,12 @@ int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offs
         mc.out_r[c] = out_right[c];
     }
     cudaStream_t s = as_stream(stream);
+    const bool direct = (kind & JG_COMB_LONG) != 0;
+    kind &= ~JG_COMB_LONG;
     switch (kind) {
-        case JG_COMB_PAIRS: return launch_gather_multi<JG_COMB_PAIRS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
-        case JG_COMB_DISTINCTS: return launch_gather_multi<JG_COMB_DISTINCTS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
-        case JG_COMB_CROSS: return launch_gather_multi<JG_COMB_CROSS>(itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+        case JG_COMB_PAIRS: return launch_gather_multi<JG_COMB_PAIRS>(direct, itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+        case JG_COMB_DISTINCTS: return launch_gather_multi<JG_COMB_DISTINCTS>(direct, itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
+        case JG_COMB_CROSS: return launch_gather_multi<JG_COMB_CROSS>(direct, itemsize, offsets_a, offsets_b, n, out_offsets, mc, s);
     }
     set_error("jg_comb_gather_multi: bad kind %d", kind);
     return -2;
@@ -825,6 +1385,8 @@ int jg_comb_gather_multi(int kind, const int64_t *offsets_a, const int64_t *offs
 int jg_comb_eval(int kind, const int64_t *offsets_a, const int64_t *offsets_b, int64_t n, const int64_t *out_offsets,
                  int dtype, const JgEvalProgram *program, void *out, void *stream) {
     if (n <= 0) return 0;
+    const bool direct = (kind & JG_COMB_LONG) != 0;
+    kind &= ~JG_COMB_LONG;
     JG_REQUIRE(program != nullptr && out != nullptr && offsets_a != nullptr && out_offsets != nullptr,
                "jg_comb_eval: bad arguments");
     JG_REQUIRE(kind != JG_COMB_CROSS || offsets_b != nullptr, "jg_comb_eval: cross needs offsets_b");
@@ -850,9 +1412,9 @@ int jg_comb_eval(int kind, const int64_t *offsets_a, const int64_t *offsets_b, i
     JG_REQUIRE(eval_op_class(pr.ins[0] & 255) == 1 && (pr.ins[0] & 255) == JG_EV_LOAD, "jg_comb_eval: a program starts with a load");
     cudaStream_t s = as_stream(stream);
     switch (kind) {
-        case JG_COMB_PAIRS: return launch_comb_eval_dtype<JG_COMB_PAIRS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
-        case JG_COMB_DISTINCTS: return launch_comb_eval_dtype<JG_COMB_DISTINCTS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
-        case JG_COMB_CROSS: return launch_comb_eval_dtype<JG_COMB_CROSS>(dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+        case JG_COMB_PAIRS: return launch_comb_eval_dtype<JG_COMB_PAIRS>(direct, dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+        case JG_COMB_DISTINCTS: return launch_comb_eval_dtype<JG_COMB_DISTINCTS>(direct, dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
+        case JG_COMB_CROSS: return launch_comb_eval_dtype<JG_COMB_CROSS>(direct, dtype, offsets_a, offsets_b, n, out_offsets, pr, out, s);
     }
     set_error("jg_comb_eval: bad kind %d", kind);
     return -2;

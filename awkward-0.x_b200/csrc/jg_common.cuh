@@ -72,6 +72,11 @@ __device__ __forceinline__ void st_stream(T *p, T v) {
     __stcs(p, v);
 }
 
+// a hint, no register result and nothing to wait for: start moving the line that holds *p towards L2
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -167,11 +167,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// L2 prefetch of a byte range (any alignment; one instruction per 128-byte line and caller thread)
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 #endif  // __CUDACC__
 
 }  // namespace jg

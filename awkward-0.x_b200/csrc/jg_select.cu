@@ -300,8 +300,11 @@ index_gather_kernel(const V *__restrict__ content, const int64_t *__restrict__ o
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) uint16_t s_own[KM + 128];
     EventTile itile, tile;
-    itile.load(s_ioff, index_offsets, n, blockIdx.x);
-    tile.load(s_off, offsets, n, blockIdx.x);
+    // both offsets tiles in ONE memory round trip; the index run and the start of every event's content are asked
+    // for at the same time, so the two dependent loads below (index, then content[start + index]) find them in L2
+    itile.load_nosync<sizeof(I)>(s_ioff, index_offsets, n, blockIdx.x, index);
+    tile.load_nosync<sizeof(V)>(s_off, offsets, n, blockIdx.x, content);
+    __syncthreads();
     const int64_t io0 = __ldg(index_offsets);
     const int64_t k0 = itile.first_element(), k1 = itile.last_element();
     bool oob = false;

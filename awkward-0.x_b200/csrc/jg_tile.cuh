@@ -18,20 +18,42 @@ struct EventTile {
     // all threads of the CTA call this; `s_off` is a __shared__ int64_t[kTileEvents + 1]
     __device__ __forceinline__ void load(int64_t *s_off, const int64_t *__restrict__ offsets, int64_t n,
                                          int64_t tile_index) {
+        load_nosync(s_off, offsets, n, tile_index);
+        __syncthreads();
+    }
+    // The same without the barrier: a kernel that needs several offsets tiles (combinatorics: output, left, right;
+    // a[jagged_int]: index and content layouts) issues all their loads back to back and synchronises ONCE -- the
+    // tiles arrive in one memory round trip instead of one per tile (a CTA of these kernels lives a few
+    // microseconds, most of it waiting for dependent loads).
+    //   PF != 0: every thread also asks L2 for the line at `pf_base + offset * PF` of each offset it loaded (the
+    //   start of each event's run in a PF-byte-item array): by the time the tile is on chip the run that the next,
+    //   dependent stage reads is on its way -- the second round trip overlaps the first.
+    template <int PF = 0>
+    __device__ __forceinline__ void load_nosync(int64_t *s_off, const int64_t *__restrict__ offsets, int64_t n,
+                                                int64_t tile_index, const void *pf_base = nullptr) {
         off = s_off;
         event0 = tile_index * kTileEvents;
         const int64_t left = n - event0;
         nev = left < kTileEvents ? static_cast<int>(left) : kTileEvents;
         // nev + 1 <= 513 entries, 256 threads: two predicated loads per thread + one straggler (a strided loop
         // here is unrolled by the compiler into 8/4/2/1 cascades that every warp walks through)
-        {
-            const int i0 = threadIdx.x, i1 = threadIdx.x + kTileThreads;
-            const int64_t *src = offsets + event0;
-            if (i0 <= nev) s_off[i0] = __ldg(src + i0);
-            if (i1 <= nev) s_off[i1] = __ldg(src + i1);
-            if (threadIdx.x == 0 && nev == 2 * kTileThreads) s_off[nev] = __ldg(src + nev);
+        const int i0 = threadIdx.x, i1 = threadIdx.x + kTileThreads;
+        const int64_t *src = offsets + event0;
+        int64_t v0 = 0, v1 = 0;
+        if (i0 <= nev) v0 = __ldg(src + i0);
+        if (i1 <= nev) v1 = __ldg(src + i1);
+        if (i0 <= nev) s_off[i0] = v0;
+        if (i1 <= nev) s_off[i1] = v1;
+        if (threadIdx.x == 0 && nev == 2 * kTileThreads) s_off[nev] = __ldg(src + nev);
+        if constexpr (PF != 0) {
+            // only where an event is known to hold an item (its start is then a valid address): a lane sees its
+            // neighbour's offset by shuffle, the last lane of a warp leaves its event to the neighbouring lines
+            const char *b = static_cast<const char *>(pf_base);
+            const int64_t n0 = __shfl_down_sync(0xffffffffu, v0, 1), n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+            const bool inner = (threadIdx.x & 31) != 31;
+            if (inner && i0 < nev && n0 > v0) prefetch_l2(b + v0 * PF);
+            if (inner && i1 < nev && n1 > v1) prefetch_l2(b + v1 * PF);
         }
-        __syncthreads();
     }
     // the tile's event range without touching memory (for the early bulk copy)
     __device__ static __forceinline__ void range(int64_t n, int64_t tile_index, int64_t &ev0, int &nev_) {
@@ -149,9 +171,121 @@ namespace jg {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kOwnerShortEvent = 24;     // events up to this long are written by their own thread
 
-__device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile &tile, int L) {
+// positions [base, base + L) of the tile's run (relative to its first position): scatter + running maximum, free of
+// divergence whatever the counts are.  A run longer than the table is swept in chunks of KM positions, one table each.
+__device__ __forceinline__ void build_owner_range(uint16_t *own, const EventTile &tile, int64_t base, int L) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kTileThreads / kWarp;
+    const int padded = (L + 127) & ~127;
+    // 1. clear (128-bit stores)
+#pragma unroll 1
+    for (int q = threadIdx.x; q < padded / 8; q += kTileThreads) reinterpret_cast<uint4 *>(own)[q] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // 2. scatter: non-empty events have distinct first positions
+    const int64_t e0 = tile.off[0] + base;
+#pragma unroll 1
+    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
+        const int64_t a = tile.off[ev] - e0, b = tile.off[ev + 1] - e0;
+        if (b > a && a >= 0 && a < L) own[a] = static_cast<uint16_t>(ev);
+    }
+    __syncthreads();
+    // 3. running max: warp w owns a contiguous chunk of rows
+    const int rows_total = padded >> 7;
+    const int rows_per_warp = (rows_total + NW - 1) / NW;
+    const int r_begin = warp * rows_per_warp;
+    const int r_end = min(rows_total, r_begin + rows_per_warp);
+    if (r_begin < r_end) {
+        // owner of the chunk's first position (the event that started at or before it)
+        uint32_t carry = 0;
+        const int first = r_begin << 7;
+        if ((first > 0 || base > 0) && first < L) carry = static_cast<uint32_t>(tile.find_event(e0 + first));
+#pragma unroll 1
+        for (int r = r_begin; r < r_end; ++r) {
+            uint2 w = *reinterpret_cast<const uint2 *>(own + (r << 7) + lane * 4);
+            uint32_t v0 = w.x & 0xffffu, v1 = w.x >> 16, v2 = w.y & 0xffffu, v3 = w.y >> 16;
+            v1 = max(v1, v0);
+            v2 = max(v2, v1);
+            v3 = max(v3, v2);
+            uint32_t incl = v3;
+#pragma unroll
+            for (int d = 1; d < kWarp; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = max(incl, o);
+            }
+            uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+            before = lane == 0 ? carry : max(before, carry);
+            v0 = max(v0, before);
+            v1 = max(v1, before);
+            v2 = max(v2, before);
+            v3 = max(v3, before);
+            w.x = v0 | (v1 << 16);
+            w.y = v2 | (v3 << 16);
+            *reinterpret_cast<uint2 *>(own + (r << 7) + lane * 4) = w;
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+        }
+    }
+    __syncthreads();
+}
+
+// The same table in three separable steps, for kernels that already walk the tile's events once (they scatter in that
+// walk) and clear the table while their offsets tiles are still in flight -- and with NO binary search: the event that
+// owns the first position of each warp's chunk registers itself in `carry` during the scatter.
+//   lg: log2 of the positions one warp scans (a power of two >= 128, 8 << lg >= L: owner_chunk_lg)
+__device__ __forceinline__ int owner_chunk_lg(int L) {
+    int lg = 7;
+    while ((kTileThreads / kWarp) << lg < L) ++lg;
+    return lg;
+}
+__device__ __forceinline__ void owner_clear(uint16_t *own, int L) {
+    const int padded = (L + 127) & ~127;
+#pragma unroll 1
+    for (int q = threadIdx.x; q < padded / 8; q += kTileThreads) reinterpret_cast<uint4 *>(own)[q] = make_uint4(0, 0, 0, 0);
+}
+// one event whose positions are [a, b) relative to the first position of the table (any thread; a barrier after the
+// clear and before this, another one before owner_scan)
+__device__ __forceinline__ void owner_scatter_event(uint16_t *own, uint16_t *carry, int ev, int64_t a, int64_t b, int L, int lg) {
+    if (b > a && b > 0 && a < L) {
+        if (a >= 0) own[a] = static_cast<uint16_t>(ev);
+        const int lo = a <= 0 ? 0 : static_cast<int>((a + (int64_t(1) << lg) - 1) >> lg);
+        const int hi = static_cast<int>((b < L ? b - 1 : int64_t(L) - 1) >> lg);
+        for (int w = lo; w <= hi; ++w) carry[w] = static_cast<uint16_t>(ev);
+    }
+}
+__device__ __forceinline__ void owner_scan(uint16_t *own, const uint16_t *carry_in, int L, int lg) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_total = (L + 127) >> 7;
+    const int r_begin = warp << (lg - 7);
+    const int r_end = min(rows_total, (warp + 1) << (lg - 7));
+    if (r_begin < r_end) {
+        uint32_t carry = carry_in[warp];
+#pragma unroll 1
+        for (int r = r_begin; r < r_end; ++r) {
+            uint2 w = *reinterpret_cast<const uint2 *>(own + (r << 7) + lane * 4);
+            uint32_t v0 = w.x & 0xffffu, v1 = w.x >> 16, v2 = w.y & 0xffffu, v3 = w.y >> 16;
+            v1 = max(v1, v0);
+            v2 = max(v2, v1);
+            v3 = max(v3, v2);
+            uint32_t incl = v3;
+#pragma unroll
+            for (int d = 1; d < kWarp; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = max(incl, o);
+            }
+            uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+            before = lane == 0 ? carry : max(before, carry);
+            v0 = max(v0, before);
+            v1 = max(v1, before);
+            v2 = max(v2, before);
+            v3 = max(v3, before);
+            w.x = v0 | (v1 << 16);
+            w.y = v2 | (v3 << 16);
+            *reinterpret_cast<uint2 *>(own + (r << 7) + lane * 4) = w;
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+        }
+    }
+}
+
+__device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile &tile, int L) {
     // 0. usual case, every event of the tile is short: each thread writes its event's index over the event's own
     //    positions (a few 16-bit stores); no clearing, no scan, no binary search for the warp carries
     {
@@ -179,55 +313,7 @@ __device__ __forceinline__ void build_owner_table(uint16_t *own, const EventTile
             return;
         }
     }
-    const int padded = (L + 127) & ~127;
-    // 1. clear (128-bit stores)
-#pragma unroll 1
-    for (int q = threadIdx.x; q < padded / 8; q += kTileThreads) reinterpret_cast<uint4 *>(own)[q] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    // 2. scatter: non-empty events have distinct first positions
-    const int64_t e0 = tile.off[0];
-#pragma unroll 1
-    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads) {
-        const int64_t a = tile.off[ev], b = tile.off[ev + 1];
-        if (b > a) own[a - e0] = static_cast<uint16_t>(ev);
-    }
-    __syncthreads();
-    // 3. running max: warp w owns a contiguous chunk of rows
-    const int rows_total = padded >> 7;
-    const int rows_per_warp = (rows_total + NW - 1) / NW;
-    const int r_begin = warp * rows_per_warp;
-    const int r_end = min(rows_total, r_begin + rows_per_warp);
-    if (r_begin < r_end) {
-        // owner of the chunk's first position (the event that started at or before it)
-        uint32_t carry = 0;
-        const int first = r_begin << 7;
-        if (first > 0 && first < L) carry = static_cast<uint32_t>(tile.find_event(e0 + first));
-#pragma unroll 1
-        for (int r = r_begin; r < r_end; ++r) {
-            uint2 w = *reinterpret_cast<const uint2 *>(own + (r << 7) + lane * 4);
-            uint32_t v0 = w.x & 0xffffu, v1 = w.x >> 16, v2 = w.y & 0xffffu, v3 = w.y >> 16;
-            v1 = max(v1, v0);
-            v2 = max(v2, v1);
-            v3 = max(v3, v2);
-            uint32_t incl = v3;
-#pragma unroll
-            for (int d = 1; d < kWarp; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl = max(incl, o);
-            }
-            uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
-            before = lane == 0 ? carry : max(before, carry);
-            v0 = max(v0, before);
-            v1 = max(v1, before);
-            v2 = max(v2, before);
-            v3 = max(v3, before);
-            w.x = v0 | (v1 << 16);
-            w.y = v2 | (v3 << 16);
-            *reinterpret_cast<uint2 *>(own + (r << 7) + lane * 4) = w;
-            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
-        }
-    }
-    __syncthreads();
+    build_owner_range(own, tile, 0, L);
 }
 
 }  // namespace jg

@@ -18,6 +18,7 @@ cpu_baseline = the UNMODIFIED reference (oracle/_ref, see oracle/fetch_ref.py; t
                per core, equal shards); every API workflow also carries the reference's time on a stated sample
 """
 import argparse
+import re
 import json
 import os
 import subprocess
@@ -538,7 +539,12 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
             best.append(e0.elapsed_time(e1))
         return float(np.mean(best)), float(min(best))
 
+    only = getattr(args, "only", None)
+
     def add(name, nbytes, elements, fn):
+        if only and not re.search(only, name):
+            fn()                          # (later rows use what this call leaves behind)
+            return
         ms, best = time_call(fn)
         gbs = nbytes / (ms * 1e-3) / 1e9
         table[name] = {"ms": ms, "best_ms": best, "bytes": int(nbytes), "gbs": gbs, "frac": gbs / peak,
@@ -692,7 +698,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
                 karr = (ctypes.c_void_p * kk)(*[c.data_ptr() for c in kcols])
                 add("argchoose_k%d_fill" % kk, 16 * Nk + 8 * kk * Pk, Pk, lambda: _lib.call(
                     "jg_comb_fill", _lib.COMB_CHOOSE, kk, off.data_ptr(), ctypes.c_void_p(0), Nk, _vp(koff), karr, 0, st()))
-                table["argchoose_k%d_fill" % kk]["combinations"] = Pk
+                if "argchoose_k%d_fill" % kk in table:
+                    table["argchoose_k%d_fill" % kk]["combinations"] = Pk
                 del kcols, koff
         l, r = empty(P, np.float32), empty(P, np.float32)
         cb = el_pt if ob is not None else mu_pt
@@ -700,7 +707,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
             "jg_comb_gather2", kind, mu_off.data_ptr(), obp, Nc, _vp(poff), mu_pt.data_ptr(), 4, cb.data_ptr(), 4,
             _vp(l), _vp(r), st()))
         del l, r
-        table["arg" + name + "_fill"]["pairs"] = P
+        if "arg" + name + "_fill" in table:
+            table["arg" + name + "_fill"]["pairs"] = P
         # SURVEY 8d "pair mass fused from index generation": three columns per side, one result column; the program
         # is what awkward0_b200/lazy.py compiles for sqrt(2 pt1 pt2 (cosh(eta1 - eta2) - cos(phi1 - phi2)))
         if kind != _lib.COMB_DISTINCTS:
@@ -713,7 +721,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
             add(name + "_mass_fused_f32", nin + 8 * Nc + 3 * 4 * Mmu + (3 * 4 * Mel if ob is not None else 0) + 4 * P, P,
                 lambda: _lib.call("jg_comb_eval", kind, mu_off.data_ptr(), obp, Nc, _vp(poff), _lib.JG_F32, ctypes.byref(prog),
                                   _vp(mass_out), st()))
-            table[name + "_mass_fused_f32"]["note"] = "issue-bound (14-step program incl. cosh, cos, sqrt per pair), not HBM-bound"
+            if name + "_mass_fused_f32" in table:
+                table[name + "_mass_fused_f32"]["note"] = "issue-bound (14-step program incl. cosh, cos, sqrt per pair), not HBM-bound"
             del mass_out
     return table
 

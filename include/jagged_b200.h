@@ -83,6 +83,11 @@ enum {
     JG_COMB_CHOOSE = 2,     /* k = 2..5, colexicographic         jagged.py:1128-1221 */
     JG_COMB_CROSS = 3       /* rectangular, left index slow      jagged.py:1302-1325 */
 };
+/* OR-ed into `kind` of jg_comb_fill / jg_comb_gather2 / jg_comb_gather_multi / jg_comb_eval: a HINT that events hold
+ * more than a handful of combinations each (the caller knows the total and the number of events).  The result is the
+ * same either way; with the hint the kernels built for long events run (direct tables: owner table over output
+ * chunks + per-event info + combination look-up table) instead of those tuned for dimuon-like events.              */
+#define JG_COMB_LONG 0x100
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int         jg_version(void);

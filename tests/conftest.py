@@ -71,13 +71,18 @@ def reduce_close(op, got, want, offsets, content, rtol):
             bound = np.maximum(rtol, 2.0 * n * np.finfo(want.dtype).eps)
             finite = np.isfinite(want) & np.isfinite(got) & (np.abs(want) > np.finfo(want.dtype).tiny)
             ok |= finite & (np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound * np.abs(want.astype(np.float64)))
-            # a product whose magnitude leaves the normal range depends on the order legitimately: it overflows to inf
-            # (and inf * 0 = NaN if a zero follows) in one order and not in another, or underflows at a different
-            # factor.  Judge that on the exact log-domain magnitude of the NON-ZERO factors; an event that holds a zero
-            # and cannot overflow is +-0 in every order and must simply match.
+            # a product whose magnitude CAN leave the normal range on the way depends on the order legitimately: it
+            # overflows to inf (and inf * 0 = NaN if a zero follows) in one order and not in another, or underflows at a
+            # different factor -- also when the final value is representable (factors above 1 first, below 1 later: the
+            # reference's sequential order overflows where a tree order does not).  No order's partial product exceeds the
+            # product of all factors above 1 (or falls below that of all factors below 1): judge that, in the log
+            # domain, on the NON-ZERO factors; an event that holds a zero and cannot overflow is +-0 in every order and
+            # must simply match.
             nz = np.abs(x) > 0
-            logmag = np.where(nonempty, np.add.reduceat(np.where(nz, np.log2(np.where(nz, np.abs(x), 1.0)), 0.0), starts), 0.0)
+            logs = np.where(nz, np.log2(np.where(nz, np.abs(x), 1.0)), 0.0)
+            up = np.where(nonempty, np.add.reduceat(np.maximum(logs, 0.0), starts), 0.0)
+            down = np.where(nonempty, np.add.reduceat(np.minimum(logs, 0.0), starts), 0.0)
             haszero = np.where(nonempty, np.add.reduceat((~nz).astype(np.int64), starts), 0) > 0
             info = np.finfo(want.dtype)
-            ok |= (logmag > info.maxexp - 2) | (~haszero & (logmag < info.minexp + 2))
+            ok |= (up > info.maxexp - 2) | (~haszero & (down < info.minexp + 2))
     return ok

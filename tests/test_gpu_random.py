@@ -1,5 +1,7 @@
 """-m gpu: differential tests CUDA-vs-oracle on seeded random inputs (sizes the numpy oracle finishes in seconds)
 and size-independent properties at BASELINE.json's full sizes (100 M events)."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -40,7 +42,7 @@ CASES = [("poisson5", 300000, np.float32), ("poisson5", 300000, np.float64), ("p
 
 @pytest.mark.parametrize("kind,n,dtype", CASES)
 def test_differential(ak, kind, n, dtype):
-    rng = np.random.default_rng(hash((kind, n, np.dtype(dtype).name)) % (2**32))
+    rng = np.random.default_rng(zlib.crc32(repr((kind, n, np.dtype(dtype).name)).encode()))      # (hash() of a str changes per process)
     counts = make_counts(kind, n, rng)
     m = int(counts.sum())
     if np.dtype(dtype).kind == "f":
@@ -537,3 +539,73 @@ def test_long_event_variants(ak, kind, dtype):
         roff, ridx = O.argminmax(o, content, False)
         goff, gval = O.index_gather(o, content, roff, ridx)
         assert same(lead.offsets.get(), goff) and same(lead.content.get(), gval)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# combinatorics: the dimuon-like kernels (pair table / owner table + walk) and the long-event kernels (direct tables,
+# include/jagged_b200.h JG_COMB_LONG) must both give the oracle's result on EVERY distribution -- the hint only
+# chooses the kernel
+# ----------------------------------------------------------------------------------------------------------------
+def comb_counts(kind, rng):
+    if kind == "poisson2":
+        return rng.poisson(2.0, 60000).astype(np.int64)
+    if kind == "poisson6":                        # tiles of "choose 4" hold several owner-table chunks
+        return rng.poisson(6.0, 6000).astype(np.int64)
+    if kind == "around_the_table":                # events at and beyond the look-up table's limits (10 / 12 on chip, 14 - 24 in memory)
+        return rng.integers(8, 30, 300).astype(np.int64)
+    if kind == "mixed_long":                      # short events with events of 40 - 400 items among them, empties, a tail of empties
+        c = rng.poisson(3.0, 5000).astype(np.int64)
+        c[rng.choice(5000, 40, replace=False)] = rng.integers(40, 400, 40)
+        c[rng.choice(5000, 500, replace=False)] = 0
+        c[-700:] = 0
+        return c
+    if kind == "one_big":                         # one event whose pairs exceed 2^20 among ordinary ones
+        c = rng.poisson(2.0, 1500).astype(np.int64)
+        c[700] = 1500
+        return c
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("variant", ["short", "long"])
+@pytest.mark.parametrize("kind", ["poisson2", "poisson6", "around_the_table", "mixed_long", "one_big"])
+def test_combinatorics_kernel_variants(ak, kind, variant, monkeypatch):
+    from awkward0_b200 import _lib
+    monkeypatch.setattr(_lib, "COMB_LONG_MEAN", -1 if variant == "long" else 1 << 60)
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))
+    ca = comb_counts(kind, rng)
+    cb = rng.poisson(2.0, len(ca)).astype(np.int64)
+    if kind == "mixed_long":
+        cb[rng.choice(len(cb), 5, replace=False)] = rng.integers(4000, 5000, 5)      # right-hand events of 4096 and more items
+    xa = rng.exponential(20.0, int(ca.sum())).astype(np.float32)
+    xb = rng.integers(0, 1000, int(cb.sum())).astype(np.int64)
+    oa, ob = O.counts2offsets(ca), O.counts2offsets(cb)
+    a, b = ak.JaggedArray.fromcounts(ca, xa), ak.JaggedArray.fromcounts(cb, xb)
+    for name, fn in (("argpairs", O.argpairs), ("argdistincts", O.argdistincts)):
+        want = fn(oa)
+        got = getattr(a, name)()
+        assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2]), name
+    for name, fn in (("pairs", O.pairs), ("distincts", O.distincts)):
+        want = fn(oa, xa)
+        got = getattr(a, name)()
+        assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2]), name
+        # the fused expression on the same combinations, bit for bit what the gathered columns give
+        fused = (got.i0 * 2 - got.i1).content.get()
+        assert same(fused, want[1] * np.float32(2) - want[2]), name
+    small = kind not in ("mixed_long", "one_big")       # (k-combinations of a 400-item event do not fit any memory)
+    for k in ((2, 3, 4, 5) if small else (2,)):
+        want = O.argchoose(oa, k)
+        got = a.argchoose(k)
+        assert same(got.offsets.get(), want[0]), k
+        for c in range(k):
+            assert same(got[str(c)].content.get(), want[1 + c]), (k, c)
+    want = O.argcross(oa, ob)
+    got = a.argcross(b)
+    assert same(got.offsets.get(), want[0]) and same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+    want = O.cross(oa, xa, ob, xb)
+    got = a.cross(b)
+    assert same(got.i0.content.get(), want[1]) and same(got.i1.content.get(), want[2])
+    # records: every leaf column in one sweep (jg_comb_gather_multi)
+    rec = ak.JaggedArray.zip(x=a, y=ak.JaggedArray.fromoffsets(a.offsets, (xa * 3).astype(np.float32)))
+    want = O.pairs(oa, xa)
+    got = rec.pairs()
+    assert same(got.i0.x.content.get(), want[1]) and same(got.i1.y.content.get(), (want[2] * np.float32(3)).astype(np.float32))
