@@ -470,6 +470,71 @@ __device__ __forceinline__ bool build_pair_table(uint16_t *__restrict__ s_l, uin
     return true;
 }
 
+// The same table with both items in ONE 32-bit entry (left | right << 16), `shift` entries into `tab`: the short-event
+// kernels read it with one load per output -- or one 64-bit load per TWO outputs, entry u = q + shift having the
+// parity of its global position so that the two results go out in one vector store.  The walk keeps the entry
+// itself as its counter: j + 1 is += 0x10000 and "row finished" one comparison with jend << 16.
+template <int KIND, bool REL>
+__device__ __forceinline__ bool build_pair_table_packed(uint32_t *__restrict__ tab, int shift, const EventTile &pt,
+                                                        const int64_t *__restrict__ s_oa, const int64_t *__restrict__ s_ob) {
+    const int64_t p0 = pt.off[0], total = pt.off[pt.nev] - p0;
+    bool ok = total <= kPairTable;
+    // (the arg forms hold local indices: an event of 65536 items has more than kPairEventMax pairs anyway)
+    if (REL) {
+        ok = ok && (s_oa[pt.nev] - s_oa[0]) < 65536;
+        if (KIND == JG_COMB_CROSS) ok = ok && (s_ob[pt.nev] - s_ob[0]) < 65536;
+    }
+    for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) ok = ok && (pt.off[ev + 1] - pt.off[ev]) <= kPairEventMax;
+    if (!__syncthreads_and(ok)) return false;
+#pragma unroll 1
+    for (int ev = threadIdx.x; ev < pt.nev; ev += kTileThreads) {
+        const int cnt = static_cast<int>(pt.off[ev + 1] - pt.off[ev]);
+        if (cnt == 0) continue;
+        uint32_t *t = tab + shift + (pt.off[ev] - p0);
+        uint32_t *const end = t + cnt;
+        const uint32_t na = static_cast<uint32_t>(s_oa[ev + 1] - s_oa[ev]);
+        const uint32_t ra = REL ? static_cast<uint32_t>(s_oa[ev] - s_oa[0]) : 0u;
+        if constexpr (KIND == JG_COMB_CROSS) {
+            const uint32_t nb = static_cast<uint32_t>(s_ob[ev + 1] - s_ob[ev]);
+            const uint32_t rb = REL ? static_cast<uint32_t>(s_ob[ev] - s_ob[0]) : 0u;
+            uint32_t e = ra | (rb << 16);
+            const uint32_t lim = (rb + nb) << 16, back = (nb << 16) - 1u;      // next row: j back to rb, i + 1
+#pragma unroll 1
+            do {
+                *t++ = e;
+                e += 0x10000u;
+                if (e >= lim) e -= back;
+            } while (t != end);
+        } else {
+            constexpr uint32_t kFirst = (KIND == JG_COMB_DISTINCTS) ? 1u : 0u;      // j starts at i (pairs) or i + 1
+            uint32_t i = ra, e = ra | ((ra + kFirst) << 16);
+            const uint32_t lim = (ra + na) << 16;
+#pragma unroll 1
+            do {
+                *t++ = e;
+                e += 0x10000u;
+                if (e >= lim) {
+                    ++i;
+                    e = i * 0x10001u + (kFirst << 16);
+                }
+            } while (t != end);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// two adjacent results in one streaming store
+template <typename V>
+__device__ __forceinline__ void st2_cs(V *p, V x, V y) {
+    if constexpr (sizeof(V) == 1) __stcs(reinterpret_cast<uchar2 *>(p), make_uchar2(x, y));
+    else if constexpr (sizeof(V) == 2) __stcs(reinterpret_cast<ushort2 *>(p), make_ushort2(x, y));
+    else if constexpr (sizeof(V) == 4) __stcs(reinterpret_cast<uint2 *>(p), make_uint2(x, y));
+    else __stcs(reinterpret_cast<ulonglong2 *>(p), make_ulonglong2(x, y));
+}
+template <typename V>
+__device__ __forceinline__ bool aligned2(const V *p) { return (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(V) - 1)) == 0; }
+
 // The pair table(s) of a tile for the value kernels: `sweep(cb, L)` is called once per chunk of the tile's output run
 // with sh.own[q] / sh.right[q] = the tile-relative left / right item of output cb + q.  false: nothing was done, the
 // tile takes the caller's general path.  All threads.
@@ -535,18 +600,37 @@ comb_fill_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     if constexpr (KIND == JG_COMB_PAIRS || KIND == JG_COMB_CROSS) {      // (distincts: mostly 0-1 pairs, measured slower)
         // relative positions when absolute indices are wanted (the tile's first item is added back), else i, j
-        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        const bool fast = absolute ? build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)
-                                   : build_pair_table<KIND, false, kPairTable>(s_l, s_r, pt, s_oa, s_ob);
+        uint32_t *tab = reinterpret_cast<uint32_t *>(s_own);
+        const int shift = static_cast<int>(p0 & 1);
+        const bool fast = absolute ? build_pair_table_packed<KIND, true>(tab, shift, pt, s_oa, s_ob)
+                                   : build_pair_table_packed<KIND, false>(tab, shift, pt, s_oa, s_ob);
         if (fast) {
-            const int64_t add_l = absolute ? s_oa[0] : 0;
-            const int64_t add_r = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]) : 0;
-            const int total = static_cast<int>(p1 - p0);
-            int64_t *c0 = cols.p[0] + p0, *c1 = cols.p[1] + p0;
+            const uint64_t add_l = absolute ? s_oa[0] : 0;
+            const uint64_t add_r = absolute ? ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]) : 0;
+            const int last = static_cast<int>(p1 - p0) + shift;          // entries [shift, last)
+            // two outputs per thread: one 64-bit table load, one 16-byte store per column
+            unsigned long long *c0 = reinterpret_cast<unsigned long long *>(cols.p[0]) + (p0 - shift);
+            unsigned long long *c1 = reinterpret_cast<unsigned long long *>(cols.p[1]) + (p0 - shift);
+            const bool vec = aligned2(c0) && aligned2(c1);
 #pragma unroll 2
-            for (int q = threadIdx.x; q < total; q += kTileThreads) {
-                __stcs(c0 + q, add_l + s_l[q]);
-                __stcs(c1 + q, add_r + s_r[q]);
+            for (int u = 2 * threadIdx.x; u < last; u += 2 * kTileThreads) {
+                const uint2 e = *reinterpret_cast<const uint2 *>(tab + u);
+                const bool v0 = u >= shift, v1 = u + 1 < last;
+                const unsigned long long l0 = add_l + (e.x & 0xffffu), r0 = add_r + (e.x >> 16);
+                const unsigned long long l1 = add_l + (e.y & 0xffffu), r1 = add_r + (e.y >> 16);
+                if (v0 && v1 && vec) {
+                    st2_cs(c0 + u, l0, l1);
+                    st2_cs(c1 + u, r0, r1);
+                } else {
+                    if (v0) {
+                        __stcs(c0 + u, l0);
+                        __stcs(c1 + u, r0);
+                    }
+                    if (v1) {
+                        __stcs(c0 + u + 1, l1);
+                        __stcs(c1 + u + 1, r1);
+                    }
+                }
             }
             return;
         }
@@ -655,31 +739,53 @@ comb_gather2_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__rest
     __shared__ __align__(16) uint16_t s_own[kOwnerPositions + 128];
     {
         // (staging the tile's content runs in shared memory by TMA was measured: slower -- the loads below hit L1)
-        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
+        uint32_t *tab = reinterpret_cast<uint32_t *>(s_own);
+        const int shift = static_cast<int>(p0 & 1);
+        if (build_pair_table_packed<KIND, true>(tab, shift, pt, s_oa, s_ob)) {
             const VA *ca = content_a + s_oa[0];
             const VB *cb = content_b + ((KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0]);
-            VA *ol = out_l + p0;
-            VB *orr = out_r + p0;
-            const int total = static_cast<int>(p1 - p0);
+            // two outputs per thread and step (one 64-bit table load, one vector store per column), two steps in flight
+            VA *ol = out_l + (p0 - shift);
+            VB *orr = out_r + (p0 - shift);
+            const bool vec = aligned2(ol) && aligned2(orr);
+            const int last = static_cast<int>(p1 - p0) + shift;          // entries [shift, last)
 #pragma unroll 1
-            for (int qb = threadIdx.x; qb < total; qb += 4 * kTileThreads) {
-                VA va[4];
-                VB vb[4];
+            for (int ub = 2 * threadIdx.x; ub < last; ub += 4 * kTileThreads) {
+                VA va[2][2];
+                VB vb[2][2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = qb + u * kTileThreads;
-                    if (q < total) {
-                        va[u] = __ldg(ca + s_l[q]);
-                        vb[u] = __ldg(cb + s_r[q]);
+                for (int h = 0; h < 2; ++h) {
+                    const int u = ub + h * 2 * kTileThreads;
+                    if (u < last) {
+                        const uint2 e = *reinterpret_cast<const uint2 *>(tab + u);
+                        if (u >= shift) {
+                            va[h][0] = __ldg(ca + (e.x & 0xffffu));
+                            vb[h][0] = __ldg(cb + (e.x >> 16));
+                        }
+                        if (u + 1 < last) {
+                            va[h][1] = __ldg(ca + (e.y & 0xffffu));
+                            vb[h][1] = __ldg(cb + (e.y >> 16));
+                        }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = qb + u * kTileThreads;
-                    if (q < total) {
-                        __stcs(ol + q, va[u]);
-                        __stcs(orr + q, vb[u]);
+                for (int h = 0; h < 2; ++h) {
+                    const int u = ub + h * 2 * kTileThreads;
+                    if (u < last) {
+                        const bool v0 = u >= shift, v1 = u + 1 < last;
+                        if (v0 && v1 && vec) {
+                            st2_cs(ol + u, va[h][0], va[h][1]);
+                            st2_cs(orr + u, vb[h][0], vb[h][1]);
+                        } else {
+                            if (v0) {
+                                __stcs(ol + u, va[h][0]);
+                                __stcs(orr + u, vb[h][0]);
+                            }
+                            if (v1) {
+                                __stcs(ol + u + 1, va[h][1]);
+                                __stcs(orr + u + 1, vb[h][1]);
+                            }
+                        }
                     }
                 }
             }
@@ -838,13 +944,14 @@ comb_gather_multi_kernel(const int64_t *__restrict__ offsets_a, const int64_t *_
     __syncthreads();
     const int64_t p0 = pt.first_element(), p1 = pt.last_element();
     {
-        uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-        if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
+        uint32_t *tab = reinterpret_cast<uint32_t *>(s_own);
+        if (build_pair_table_packed<KIND, true>(tab, 0, pt, s_oa, s_ob)) {
             const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
             const int total = static_cast<int>(p1 - p0);
 #pragma unroll 1
             for (int q = threadIdx.x; q < total; q += kTileThreads) {
-                const int64_t ia = a0 + s_l[q], ib = b0 + s_r[q];
+                const uint32_t e = tab[q];
+                const int64_t ia = a0 + (e & 0xffffu), ib = b0 + (e >> 16);
                 V vl[4], vr[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -1131,11 +1238,12 @@ comb_eval_kernel(const int64_t *__restrict__ offsets_a, const int64_t *__restric
     const int64_t total = p1 - p0;
     if (total <= 0) return;
     const int64_t a0 = s_oa[0], b0 = (KIND == JG_COMB_CROSS) ? s_ob[0] : s_oa[0];
-    uint16_t *s_l = s_own, *s_r = s_own + kPairTable;
-    if (build_pair_table<KIND, true, kPairTable>(s_l, s_r, pt, s_oa, s_ob)) {
+    uint32_t *tab = reinterpret_cast<uint32_t *>(s_own);
+    if (build_pair_table_packed<KIND, true>(tab, 0, pt, s_oa, s_ob)) {
         eval_tile<T, U, uint32_t>(pr, slots, a0, b0, p0, total, out, [&](int64_t q, uint32_t &ia, uint32_t &ib) {
-            ia = s_l[q];
-            ib = s_r[q];
+            const uint32_t e = tab[q];
+            ia = e & 0xffffu;
+            ib = e >> 16;
         });
         return;
     }
