@@ -16,6 +16,7 @@ Design differences from the reference that do not change results:
     logical value (tolist(), counts, flatten()) is identical.
 """
 import ctypes
+import os
 import numbers
 from collections import OrderedDict
 
@@ -52,6 +53,11 @@ class _bothmethod(object):
         if ins is None:
             return lambda *args, **kwargs: fcn(True, typ, *args, **kwargs)
         return lambda *args, **kwargs: fcn(False, ins, *args, **kwargs)
+
+
+# Selection schedule of the event-tiled path: False = counting pass, scan of the tile totals, compaction (K is read back
+# while the compaction runs); True = ONE pass on published tile aggregates (include/jagged_b200.h, phase 3).
+SELECT_SINGLE_PASS = [os.environ.get("JG_SELECT_SINGLE", "0") == "1"]
 
 
 class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
@@ -1230,7 +1236,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             else:
                 # the first column in two phases: count + scan, start reading K back, queue the compaction; the host
                 # then waits for K alone and the next operation is queued while the compaction is still running
-                for phase in ((1, 2) if not columns else (0,)):
+                for phase in ((3,) if SELECT_SINGLE_PASS[0] else ((1, 2) if not columns else (0,))):
                     if fused:
                         call("jg_compare_select_phase", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
                              jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,

@@ -74,10 +74,13 @@ __device__ __forceinline__ int count16(const SEL &sel, int4 v) {
 
 constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
 
-template <class SEL>
+// OVERSIZE: only the tiles whose run exceeds `km` positions are counted (the single-pass selection counts every other
+// tile out of its own staged copy) and the totals are PUBLISHED (jg_lag.cuh) instead of stored.
+template <class SEL, bool OVERSIZE = false>
 __global__ void __launch_bounds__(kCountWarps * kWarp)
 mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
-                  const int64_t *__restrict__ offsets, int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals) {
+                  const int64_t *__restrict__ offsets, int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals,
+                  const LagDesc lag = LagDesc{}, int64_t km = 0) {
     using E = typename SEL::Elem;
     constexpr int PER = 16 / sizeof(E);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,6 +91,7 @@ mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, in
     const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
     const E *m = mask + e0 + mask_shift;
     const int64_t len = e1 - e0;
+    if (OVERSIZE && len <= km) return;
     int64_t cnt = 0;
     // unaligned head (< 16 bytes), 16-byte body, tail
     const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
@@ -101,16 +105,26 @@ mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, in
     const int64_t tail0 = head + nvec * PER;
     if (tail0 + lane < len) cnt += sel.test(m[tail0 + lane]);
     cnt = warp_reduce_add(cnt);
-    if (lane == 0) tile_totals[tile] = cnt;
+    if (lane == 0) {
+        if (OVERSIZE) lag_publish(lag, static_cast<uint32_t>(tile), cnt);
+        else tile_totals[tile] = cnt;
+    }
 }
 
 // SAME: the selector looks at the content column itself (a[a > c]): one staged copy serves both
-template <typename V, int KM, class SEL, bool SAME>     // KM = positions a tile may stage
+// SINGLE: ONE pass over the data -- the tile's total comes out of the counting pass over its own staged copy, is
+// published (jg_lag.cuh: hierarchical aggregates, no chain of prefixes) and the tile's base is the sum of what its
+// predecessors published; a tile waits only until the tiles before it (dispatched earlier, so resident or done) have
+// counted theirs.  `tile_bases` is not read; the grand total goes to *total_out.  (Tiles too long to stage were
+// counted and published by mask_count_kernel<OVERSIZE> before the launch: a CTA reading a long run alone would hold
+// up every tile behind it.)
+template <typename V, int KM, class SEL, bool SAME, bool SINGLE = false>     // KM = positions a tile may stage
 __global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : (SAME ? 7 : 6))
 mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                  int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts,
-                 const int64_t *__restrict__ tile_bases, uint32_t ntiles) {
+                 const int64_t *__restrict__ tile_bases, uint32_t ntiles, const LagDesc lag = LagDesc{},
+                 int64_t *__restrict__ total_out = nullptr) {
     using E = typename SEL::Elem;
     static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
     constexpr int NW = kTileThreads / kWarp;
@@ -120,6 +134,7 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     __shared__ uint16_t s_pfx[KM + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
+    __shared__ int64_t s_base;
 
     const uint32_t tile_index = blockIdx.x;
     EventTile tile;
@@ -144,8 +159,11 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
     const int64_t len = e1 - e0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = __ldg(tile_bases + tile_index);
-    if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
+    int64_t base = 0;
+    if constexpr (!SINGLE) {
+        base = __ldg(tile_bases + tile_index);
+        if (tile_index == ntiles - 1 && threadIdx.x == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
+    }
 
     if (len <= KM) {
         // ---------------- staged tile ----------------------------------------------------------------------
@@ -183,9 +201,22 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             int wi = warp_incl_scan_add(w, lane);
             if (lane < NW) s_scan[lane] = wi - w;
             if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
+            if constexpr (SINGLE) {
+                const int64_t tile_total = __shfl_sync(0xffffffffu, wi, NW - 1);
+                if (lane == 0) lag_publish(lag, tile_index, tile_total);
+                const int64_t b = lag_prefix(lag, tile_index);
+                if (lane == 0) {
+                    s_base = b;
+                    if (tile_index == ntiles - 1) {
+                        new_offsets[n] = b + tile_total;
+                        *total_out = b + tile_total;
+                    }
+                }
+            }
         }
         if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
         __syncthreads();
+        if constexpr (SINGLE) base = s_base;
         // pass 2: compaction, consecutive lanes -> consecutive output slots
         int run = s_scan[warp];
         V *dst = out + base;
@@ -214,6 +245,14 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     // The whole CTA compacts the run chunk by chunk exactly like a staged tile (coalesced reads, ballot / popc
     // slots, consecutive stores) with a running base; an event takes its new offset from the chunk that holds its
     // first position.  (One thread per event, as before, walked an event of a million elements alone.)
+    if constexpr (SINGLE) {       // (counted and published before the launch)
+        if (warp == 0) {
+            const int64_t b = lag_prefix(lag, tile_index);
+            if (lane == 0) s_base = b;
+        }
+        __syncthreads();
+        base = s_base;
+    }
     const V *cv = content + e0;
     const E *mv = mask + e0 + mask_shift;
     int64_t *s_new = reinterpret_cast<int64_t *>(s_content);      // the stage is idle here: new offsets within the tile
@@ -264,7 +303,13 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     }
     if (stA >= len) s_new[evA] = run;       // empty events at the end of the tile
     if (stB >= len) s_new[evB] = run;
-    if (threadIdx.x == 0) s_new[tile.nev] = run;
+    if (threadIdx.x == 0) {
+        s_new[tile.nev] = run;
+        if (SINGLE && tile_index == ntiles - 1) {
+            new_offsets[n] = base + run;
+            *total_out = base + run;
+        }
+    }
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -444,7 +489,7 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
     TileScanWs t;
     int rc = carve_tile_ws(ws, ws_bytes, ntiles, t, "jg_mask_select");
     if (rc) return rc;
-    if (phase != 2) {
+    if (phase != 2 && phase != 3) {
         mask_count_kernel<SEL><<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
             sel, mask, mask_shift, offsets, n, ntiles, t.totals);
         rc = check_launch("mask_count_kernel");
@@ -452,6 +497,27 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
         ScanInArray<int64_t> in{t.totals, true};
         rc = launch_scan(in, ntiles, t.bases, total, nullptr, t.scan_ws, t.scan_ws_bytes, s);
         if (rc || phase == 1) return rc;
+    }
+    if (phase == 3) {
+        // single pass: descriptors zeroed, the (usually absent) oversize tiles counted and published, then ONE sweep
+        const size_t need = lag_ws_bytes(ntiles);
+        if (need > 2 * ((static_cast<size_t>(ntiles) + 2) * 8 + 255)) {      // (never: 8.3 bytes per tile against 16)
+            set_error("jg_mask_select: workspace too small for the single-pass descriptors");
+            return -2;
+        }
+        if (cudaMemsetAsync(t.totals, 0, need, s) != cudaSuccess) {
+            set_error("jg_mask_select: cudaMemsetAsync failed");
+            return -3;
+        }
+        const LagDesc lag = lag_carve(t.totals, ntiles);
+        mask_count_kernel<SEL, true><<<static_cast<unsigned>(ceil_div(ntiles, kCountWarps)), kCountWarps * kWarp, 0, s>>>(
+            sel, mask, mask_shift, offsets, n, ntiles, nullptr, lag, KM);
+        rc = check_launch("mask_count_kernel<oversize>");
+        if (rc) return rc;
+        mask_fill_kernel<V, KM, SEL, SAME, true><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+            sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+            new_counts, nullptr, static_cast<uint32_t>(ntiles), lag, total);
+        return check_launch("mask_fill_kernel<single>");
     }
     mask_fill_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
         sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
@@ -529,7 +595,7 @@ int jg_mask_select_phase(const void *content, int itemsize, const uint8_t *mask,
                          const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
                          int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream) {
     JG_REQUIRE(n >= 0 && offsets && new_offsets, "jg_mask_select: bad arguments");
-    JG_REQUIRE(phase >= 0 && phase <= 2, "jg_mask_select: phase must be 0, 1 or 2");
+    JG_REQUIRE(phase >= 0 && phase <= 3, "jg_mask_select: phase must be 0 .. 3");
     return dispatch_mask_select<ByteMask, false>(ByteMask{}, content, itemsize, mask, mask_shift, offsets, n, out,
                                                  new_offsets, new_counts, total, ws, ws_bytes, as_stream(stream), phase);
 }
@@ -547,7 +613,7 @@ int jg_compare_select_phase(const void *content, int itemsize, const void *key, 
     JG_REQUIRE(n >= 0 && offsets && new_offsets && key, "jg_compare_select: bad arguments");
     JG_REQUIRE(op == JG_OP_GT || op == JG_OP_GE || op == JG_OP_LT || op == JG_OP_LE,
                "jg_compare_select: operator %d is not an ordering comparison", op);
-    JG_REQUIRE(phase >= 0 && phase <= 2, "jg_compare_select: phase must be 0, 1 or 2");
+    JG_REQUIRE(phase >= 0 && phase <= 3, "jg_compare_select: phase must be 0 .. 3");
     cudaStream_t s = as_stream(stream);
     const bool strict = (op == JG_OP_GT || op == JG_OP_LT);
 #define JG_CS(K, ST) compare_select<K, ST>(content, itemsize, key, op, scalar, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase)
