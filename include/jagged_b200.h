@@ -172,7 +172,9 @@ int jg_mask_select(const void *content, int itemsize, const uint8_t *mask, int64
                    int64_t *new_counts /* n entries, may be NULL: the result's counts for free */, int64_t *total,
                    void *ws, size_t ws_bytes, void *stream);
 /* The same selection in two calls: phase 1 queues the counting pass and the scan of the tile totals (after it *total
- * holds K), phase 2 the compaction (same arguments and workspace); phase 0 is jg_mask_select.  The host reads K on a
+ * holds K), phase 2 the compaction (same arguments and workspace); phase 0 is jg_mask_select.  (phase 3: the whole
+ * selection as ONE pass over the data on published tile aggregates -- same result, measured slower on B200, kept as
+ * the documented alternative: profiles/r2_lag_study.md section 9.)  The host reads K on a
  * side stream as soon as phase 1 has run and allocates / returns the result while the compaction is still running, so
  * the operation that follows is queued behind it without the device going idle (jagged.py:562-589 returns only after
  * numpy has finished; on a device the data-dependent size is the only thing the host ever waits for).              */
