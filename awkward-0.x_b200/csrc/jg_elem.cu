@@ -29,6 +29,7 @@
 #include <type_traits>
 
 #include "jg_reduce.cuh"
+#include "jg_compact.cuh"
 #include "jg_scan.cuh"
 #include "jg_tile.cuh"
 
@@ -505,25 +506,10 @@ expand_elem_kernel(const int64_t *__restrict__ offsets, int64_t n, const int64_t
 // ------------------------------------------------------------------------------------------------------------
 // selection: flat compaction of element tiles on the lagged prefixes + rank at the event boundaries
 // ------------------------------------------------------------------------------------------------------------
-struct ElemByteMask {
-    using Elem = uint8_t;
-    __device__ __forceinline__ bool test(uint8_t v) const { return v != 0; }
-};
+// (the selectors and the two passes over a staged run are shared with the event-tiled kernels: jg_compact.cuh)
+using ElemByteMask = ByteMask;
 template <typename K, bool STRICT>
-struct ElemCompare {
-    using Elem = K;
-    using Bits = typename std::conditional<sizeof(K) == 4, uint32_t, uint64_t>::type;
-    K c;
-    Bits flip;
-    __device__ __forceinline__ bool test(K v) const {
-        Bits b;
-        memcpy(&b, &v, sizeof(K));
-        b ^= flip;
-        K y;
-        memcpy(&y, &b, sizeof(K));
-        return STRICT ? (y > c) : (y >= c);
-    }
-};
+using ElemCompare = FloatCompare<K, STRICT>;
 
 template <class SEL>
 __device__ __forceinline__ int elem_count16(const SEL &sel, int4 v) {
@@ -582,8 +568,9 @@ select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const type
                         int64_t *__restrict__ new_counts, const int64_t *__restrict__ tile_bases, int64_t ntiles) {
     using E = typename SEL::Elem;
     constexpr int ET = ElemTile<V>::ET;
-    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32];
-    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : ET * sizeof(E) + 32];
+    // (+ one row of padding behind the selector's run: the rows of the compaction are whole)
+    __shared__ __align__(16) unsigned char s_content[ET * sizeof(V) + 32 + (SAME ? 32 * sizeof(V) : 0)];
+    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : ET * sizeof(E) + 32 + 32 * sizeof(E)];
     __shared__ uint16_t s_pfx[ET + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[kElemWarps + 1];
@@ -611,44 +598,30 @@ select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const type
     if (L > 0) {
         const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + lo), static_cast<uint32_t>(L * sizeof(V)));
         cv = reinterpret_cast<const V *>(s_content + cs);
+        E *pad;
         if (SAME) {
-            mbar_wait(&s_bar[0], 0);
-            mv = reinterpret_cast<const E *>(cv);
+            pad = reinterpret_cast<E *>(s_content + cs);
         } else {
             const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + lo + mask_shift), static_cast<uint32_t>(L * sizeof(E)));
-            mbar_wait(&s_bar[1], 0);
-            mv = reinterpret_cast<const E *>(s_mask + ms);
+            pad = reinterpret_cast<E *>(s_mask + ms);
         }
+        mv = pad;
+        if (warp == 1) rows_pad<SEL>(pad, L, lane);
+        mbar_wait(&s_bar[SAME ? 0 : 1], 0);
     }
     __syncthreads();
+    // rows of 32 positions (jg_compact.cuh): warp w owns rows [w * rows_per_warp, (w + 1) * rows_per_warp)
     const int rows_total = (L + 31) >> 5;
     const int rows_per_warp = (rows_total + kElemWarps - 1) / kElemWarps;
-    const int p_begin = min(L, warp * rows_per_warp * 32);
-    const int p_end = min(L, p_begin + rows_per_warp * 32);
-    int cnt = 0;
-    for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-    cnt = warp_reduce_add(cnt);
+    const int r_begin = min(rows_total, warp * rows_per_warp);
+    const int r_end = min(rows_total, r_begin + rows_per_warp);
+    const int cnt = rows_count(sel, mv, r_begin, r_end, lane);
     if (lane == 0) s_scan[warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < kElemWarps ? s_scan[lane] : 0;
-        int wi = warp_incl_scan_add(w, lane);
-        if (lane < kElemWarps) s_scan[lane] = wi - w;
-        if (lane == kElemWarps - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-    }
     if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);
     __syncthreads();
-    int run = s_scan[warp];
-    V *dst = out + base;
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-        const int p = p0 + lane;
-        const bool on = p < p_end && sel.test(mv[p]);
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        const int slot = run + __popc(bal & ((1u << lane) - 1u));
-        if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-        if (on) dst[slot] = cv[p];
-        run += __popc(bal);
-    }
+    uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? s_scan[lane] : 0);
+    run = rows_compact<V, SEL, SAME>(sel, mv, cv, s_pfx, r_begin, r_end, lane, run, out + base);
+    if (warp == kElemWarps - 1 && lane == 0) s_pfx[rows_total << 5] = static_cast<uint16_t>(run);
     __syncthreads();
 #pragma unroll 1
     for (int64_t e = ev_lo + tid; e < ev_hi; e += kElemThreads) {

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "jg_compact.cuh"
 #include "jg_tile.cuh"
 
 namespace jg {
@@ -32,30 +33,6 @@ __device__ __forceinline__ int popcount_bytes16(int4 v) {
     return __popc(__vcmpne4(v.x, 0) & 0x01010101u) + __popc(__vcmpne4(v.y, 0) & 0x01010101u) +
            __popc(__vcmpne4(v.z, 0) & 0x01010101u) + __popc(__vcmpne4(v.w, 0) & 0x01010101u);
 }
-
-// What decides whether a position is selected: a byte mask (a[mask]) or a comparison of a float column with a scalar
-// evaluated on the fly (a[a > c]: the mask is never written nor read).  `x OP c` is brought to one of two forms on
-// the host: flip negates both sides (x < c  ==  -x > -c, exact for every float, NaN stays unordered) and strict
-// picks > or >= (a template parameter: the test is one XOR and one compare).
-struct ByteMask {
-    using Elem = uint8_t;
-    __device__ __forceinline__ bool test(uint8_t v) const { return v != 0; }
-};
-template <typename K, bool STRICT>
-struct FloatCompare {
-    using Elem = K;
-    using Bits = typename std::conditional<sizeof(K) == 4, uint32_t, uint64_t>::type;
-    K c;             // already negated when flipping
-    Bits flip;       // sign bit when the comparison is mirrored, else 0: one XOR per item, no select
-    __device__ __forceinline__ bool test(K v) const {
-        Bits b;
-        memcpy(&b, &v, sizeof(K));
-        b ^= flip;
-        K y;
-        memcpy(&y, &b, sizeof(K));
-        return STRICT ? (y > c) : (y >= c);
-    }
-};
 
 template <class SEL>
 __device__ __forceinline__ int count16(const SEL &sel, int4 v) {
@@ -129,8 +106,9 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32];
-    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32];
+    // (+ one row of padding behind the selector's run: the rows of the compaction are whole)
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32 + (SAME ? 32 * sizeof(V) : 0)];
+    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32 + 32 * sizeof(E)];
     __shared__ uint16_t s_pfx[KM + 2];
     __shared__ uint64_t s_bar[2];
     __shared__ int32_t s_scan[NW + 1];
@@ -166,43 +144,40 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
     }
 
     if (len <= KM) {
-        // ---------------- staged tile ----------------------------------------------------------------------
+        // ---------------- staged tile (rows of 32 positions, jg_compact.cuh) ------------------------------------
         const int L = static_cast<int>(len);
+        const int rows_total = (L + 31) >> 5;
         const V *cv = nullptr;
         const E *mv = nullptr;
         if (L > 0) {
             const uint32_t cs = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(content + e0),
                                                        static_cast<uint32_t>(L * sizeof(V)));
             cv = reinterpret_cast<const V *>(s_content + cs);
+            E *pad;
             if (SAME) {
-                mbar_wait(&s_bar[0], 0);
-                mv = reinterpret_cast<const E *>(cv);
+                pad = reinterpret_cast<E *>(s_content + cs);
             } else {
                 const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(mask + e0 + mask_shift),
                                                            static_cast<uint32_t>(L * sizeof(E)));
-                mbar_wait(&s_bar[1], 0);
-                mv = reinterpret_cast<const E *>(s_mask + ms);
+                pad = reinterpret_cast<E *>(s_mask + ms);
             }
+            mv = pad;
+            if (warp == 1) rows_pad<SEL>(pad, L, lane);
+            mbar_wait(&s_bar[SAME ? 0 : 1], 0);
             __syncthreads();
         }
-        // warp w owns positions [w*chunk, (w+1)*chunk), chunk a multiple of 32
-        const int rows_total = (L + 31) >> 5;
+        // warp w owns rows [w * rows_per_warp, (w + 1) * rows_per_warp)
         const int rows_per_warp = (rows_total + NW - 1) / NW;
-        const int p_begin = min(L, warp * rows_per_warp * 32);
-        const int p_end = min(L, p_begin + rows_per_warp * 32);
-        // pass 1: selected per warp
-        int cnt = 0;
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(mv[p]);
-        cnt = warp_reduce_add(cnt);
+        const int r_begin = min(rows_total, warp * rows_per_warp);
+        const int r_end = min(rows_total, r_begin + rows_per_warp);
+        const int cnt = rows_count(sel, mv, r_begin, r_end, lane);
         if (lane == 0) s_scan[warp] = cnt;
         __syncthreads();
-        if (warp == 0) {
-            int w = lane < NW ? s_scan[lane] : 0;
-            int wi = warp_incl_scan_add(w, lane);
-            if (lane < NW) s_scan[lane] = wi - w;
-            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-            if constexpr (SINGLE) {
-                const int64_t tile_total = __shfl_sync(0xffffffffu, wi, NW - 1);
+        // every warp adds up the warps before it itself (one REDUX): no scan by warp 0, no second barrier
+        uint32_t run = __reduce_add_sync(0xffffffffu, lane < warp ? s_scan[lane] : 0);
+        if constexpr (SINGLE) {
+            if (warp == 0) {
+                const int64_t tile_total = __reduce_add_sync(0xffffffffu, lane < NW ? s_scan[lane] : 0);
                 if (lane == 0) lag_publish(lag, tile_index, tile_total);
                 const int64_t b = lag_prefix(lag, tile_index);
                 if (lane == 0) {
@@ -213,22 +188,14 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
                     }
                 }
             }
+            __syncthreads();
+            base = s_base;
         }
         if (!SAME && L > 0) mbar_wait(&s_bar[0], 0);      // content has landed (waited late: it is only needed now)
-        __syncthreads();
-        if constexpr (SINGLE) base = s_base;
-        // pass 2: compaction, consecutive lanes -> consecutive output slots
-        int run = s_scan[warp];
-        V *dst = out + base;
-        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-            const int p = p0 + lane;
-            const bool on = p < p_end && sel.test(mv[p]);
-            const unsigned b = __ballot_sync(0xffffffffu, on);
-            const int slot = run + __popc(b & ((1u << lane) - 1u));
-            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-            if (on) dst[slot] = cv[p];
-            run += __popc(b);
-        }
+        run = rows_compact<V, SEL, SAME>(sel, mv, cv, s_pfx, r_begin, r_end, lane, run, out + base);
+        // the rank one past the last row (the end of the last event when L is a multiple of 32; the last warp's chunk
+        // always ends the tile, also when it is empty)
+        if (warp == NW - 1 && lane == 0) s_pfx[rows_total << 5] = static_cast<uint16_t>(run);
         __syncthreads();
         // per-event new offsets -- and counts, which every later step asks for (jagged.py:383-388), for one more
         // shared-memory read instead of a 16N-byte pass of their own

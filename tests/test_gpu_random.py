@@ -609,3 +609,50 @@ def test_combinatorics_kernel_variants(ak, kind, variant, monkeypatch):
     want = O.pairs(oa, xa)
     got = rec.pairs()
     assert same(got.i0.x.content.get(), want[1]) and same(got.i1.y.content.get(), (want[2] * np.float32(3)).astype(np.float32))
+
+
+@pytest.mark.parametrize("shift", [0, 1, 3])
+@pytest.mark.parametrize("L", [0, 1, 31, 32, 33, 64, 2048, 4064, 4095, 4096, 4097, 8192])
+def test_selection_row_edges(ak, L, shift):
+    """The compaction walks a staged run in rows of 32 positions padded with a never-selected item
+    (csrc/jg_compact.cuh): runs that end on / one short of / one past a row or the stage, in every 16-byte phase,
+    for the event-tiled kernels (512 events share the run, a second tile follows so that the base is not zero) and
+    the element-tiled ones (three long events); strict, non-strict and mirrored comparisons, byte masks, everything /
+    nothing / a random half selected."""
+    rng = np.random.default_rng(7000 + 13 * L + shift)
+    layouts = []
+    c = np.full(512, L // 512, dtype=np.int64)
+    c[:L % 512] += 1
+    layouts.append(np.concatenate([rng.permutation(c), rng.poisson(5.0, 700).astype(np.int64)]))
+    if L >= 24:
+        cuts = np.sort(rng.integers(0, L + 1, 2))
+        layouts.append(np.array([cuts[0], cuts[1] - cuts[0], L - cuts[1]], dtype=np.int64))
+    for counts in layouts:
+        m = int(counts.sum())
+        off = O.counts2offsets(counts)
+        for dtype in (np.float32, np.float64, np.int32, np.int16):
+            isf = np.dtype(dtype).kind == "f"
+            vals = (rng.normal(20.0, 10.0, m) if isf else rng.integers(-99, 99, m)).astype(dtype)
+            if isf and m:
+                vals[rng.random(m) < 0.02] = np.nan
+                vals[rng.random(m) < 0.02] = 20.0
+            big = ak.asdevice(np.concatenate([np.zeros(shift, dtype=dtype), vals, np.zeros(5, dtype=dtype)]))
+            a = ak.JaggedArray.fromcounts(counts, big[shift:shift + m])
+            checks = []
+            if isf:
+                with np.errstate(invalid="ignore"):
+                    checks += [(a > 20, vals > 20), (a >= 20, vals >= 20), (a < 20, vals < 20), (a <= 20, vals <= 20),
+                               (a > -1e30, vals > -1e30), (a > 1e30, vals > 1e30)]
+                    got = [a[a > 20], a[a >= 20], a[a < 20], a[a <= 20], a[a > -1e30], a[a > 1e30]]
+            else:
+                got = []
+            for mask in (rng.random(m) < 0.5, np.ones(m, dtype=bool), np.zeros(m, dtype=bool)):
+                bigm = ak.asdevice(np.concatenate([np.ones(shift + 1, dtype=bool), mask]))
+                mj = ak.JaggedArray.fromoffsets(a.offsets, bigm[shift + 1:])
+                checks.append((mj, mask))
+                got.append(a[mj])
+            for (_, mask), g in zip(checks, got):
+                soff, sel = O.mask_select(off, vals, off, mask)
+                assert same(g.offsets.get(), soff), (L, shift, dtype)
+                assert same(g.content.get(), sel), (L, shift, dtype)
+                assert same(g.counts.get(), O.offsets2counts(soff)), (L, shift, dtype)
