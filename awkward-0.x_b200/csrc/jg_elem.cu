@@ -151,6 +151,15 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
     }
     __syncthreads();
     const T *sm = reinterpret_cast<const T *>(s_stage);
+    // the offsets of the thread's first owned event are asked for BEFORE the wait for the tile, those of its next event
+    // while the current one is reduced: a tile's life is one bulk copy (~1.5 us), and a dependent round trip to the
+    // offsets behind it (one more per 128 owned events) was a third of it at mean counts of 10 - 40
+    int64_t e = r.ev_lo + tid;
+    int64_t a64 = 0, b64 = 0;
+    if (e < r.ev_hi) {
+        a64 = __ldg(offsets + e);
+        b64 = __ldg(offsets + e + 1);
+    }
     if (L > 0) {
         const uint32_t shift = stage_edges<sizeof(T)>(s_stage, reinterpret_cast<const unsigned char *>(content + r.lo),
                                                       static_cast<uint32_t>(L * sizeof(T)));
@@ -171,21 +180,29 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
     }
     // owned events: short ones by their own thread, sequentially (the reference's order)
 #pragma unroll 1
-    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemRedThreads) {
-        const int64_t a64 = __ldg(offsets + e), b64 = __ldg(offsets + e + 1);
+    while (e < r.ev_hi) {
+        const int64_t en = e + kElemRedThreads;
+        int64_t na = 0, nb = 0;
+        if (en < r.ev_hi) {
+            na = __ldg(offsets + en);
+            nb = __ldg(offsets + en + 1);
+        }
         const int a = static_cast<int>(a64 - r.lo);
         const int b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
         if (b - a >= kElemWarpSeg) {
             s_list[atomicAdd(&s_nlist, 1)] = e;
-            continue;
-        }
-        A acc = R::identity();
-        if (b > a) {
-            acc = R::lift(sm[a]);
+        } else {
+            A acc = R::identity();
+            if (b > a) {
+                acc = R::lift(sm[a]);
 #pragma unroll 1
-            for (int k = a + 1; k < b; ++k) acc = R::accumulate(acc, sm[k]);
+                for (int k = a + 1; k < b; ++k) acc = R::accumulate(acc, sm[k]);
+            }
+            out[e] = acc;
         }
-        out[e] = acc;
+        e = en;
+        a64 = na;
+        b64 = nb;
     }
     __syncthreads();
     // long segments: one warp each, or the whole CTA
@@ -324,22 +341,31 @@ segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ of
     }
     __syncthreads();
     const T *sm = reinterpret_cast<const T *>(s_stage);
+    // (offsets of the thread's first owned event before the wait for the tile, of its next one while the current one is
+    // reduced: see segreduce_elem_kernel)
+    int64_t e = r.ev_lo + tid;
+    int64_t a64 = 0, b64 = 0;
+    if (e < r.ev_hi) {
+        a64 = __ldg(offsets + e);
+        b64 = __ldg(offsets + e + 1);
+    }
     if (L > 0) {
         const uint32_t shift = stage_edges<sizeof(T)>(s_stage, reinterpret_cast<const unsigned char *>(content + r.lo),
                                                       static_cast<uint32_t>(L * sizeof(T)));
         sm = reinterpret_cast<const T *>(s_stage + shift);
         stage_wait(&s_bar, 0);
     }
-    // a result is (absolute position, value); `start` turns it into the local index of an owned event
-    auto emit = [&](int64_t e, ArgPartial<T> p) {
-        if (e < 0) {
+    // a result is (absolute position, value); the event's start turns it into a local index
+    auto emit_at = [&](int64_t ev, int64_t start, ArgPartial<T> p) {
+        if (ev < 0) {
             carry_idx[blockIdx.x] = p.idx;
             carry_val[blockIdx.x] = p.val;
         } else {
-            best[e] = p.idx < 0 ? -1 : p.idx - __ldg(offsets + e);
-            best_value[e] = p.val;
+            best[ev] = p.idx < 0 ? -1 : p.idx - start;
+            best_value[ev] = p.val;
         }
     };
+    auto emit = [&](int64_t ev, ArgPartial<T> p) { emit_at(ev, ev < 0 ? 0 : __ldg(offsets + ev), p); };
     const int in_len = static_cast<int>(r.in_end - r.lo);
     if (in_len >= kElemWarpSeg) {
         if (tid == 0) s_list[atomicAdd(&s_nlist, 1)] = -1;
@@ -347,15 +373,20 @@ segarg_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__ of
         emit(-1, smem_arg_strided<ISMIN, T>(sm, 0, in_len, 0, 1, r.lo));
     }
 #pragma unroll 1
-    for (int64_t e = r.ev_lo + tid; e < r.ev_hi; e += kElemRedThreads) {
-        const int64_t a64 = __ldg(offsets + e), b64 = __ldg(offsets + e + 1);
+    while (e < r.ev_hi) {
+        const int64_t en = e + kElemRedThreads;
+        int64_t na = 0, nb = 0;
+        if (en < r.ev_hi) {
+            na = __ldg(offsets + en);
+            nb = __ldg(offsets + en + 1);
+        }
         const int a = static_cast<int>(a64 - r.lo);
         const int b = static_cast<int>((b64 < r.hi ? b64 : r.hi) - r.lo);
-        if (b - a >= kElemWarpSeg) {
-            s_list[atomicAdd(&s_nlist, 1)] = e;
-            continue;
-        }
-        emit(e, smem_arg_strided<ISMIN, T>(sm, a, b, 0, 1, r.lo));
+        if (b - a >= kElemWarpSeg) s_list[atomicAdd(&s_nlist, 1)] = e;
+        else emit_at(e, a64, smem_arg_strided<ISMIN, T>(sm, a, b, 0, 1, r.lo));
+        e = en;
+        a64 = na;
+        b64 = nb;
     }
     __syncthreads();
     const int nlist = s_nlist;
