@@ -206,16 +206,27 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         }
         return;
     }
-    // long events: every thread finds the event of its element by binary search in the tile's offsets
-    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
-        const int ev = tile.find_event(j);
-        if (MODE == EXPAND_PARENTS) {
-            out[j] = static_cast<V>(tile.event0 + ev);
-        } else if (MODE == EXPAND_LOCALINDEX) {
-            out[j - o0] = static_cast<V>(j - tile.off[ev]);
-        } else {
-            out[j - o0] = flat[tile.event0 + ev];
+    // long events: the run in chunks of kOwnPositions positions, one owner table each (scatter + running maximum, the
+    // owner of a chunk's first position by one binary search per warp).  A binary search per ELEMENT, as in round 1,
+    // is ~60 instructions per element: 1000 tiles with an event of 5 k - 70 k elements among 150 M short events made
+    // up 40 % of the kernel's instructions (parents: 1.35 against 1.15 ms without them, profiles/r2_exp32.log).
+    if (MODE == EXPAND_BROADCAST) {
+        if (static_cast<int>(threadIdx.x) < tile.nev) s_flat[threadIdx.x] = f0;
+        if (static_cast<int>(threadIdx.x) + kTileThreads < tile.nev) s_flat[threadIdx.x + kTileThreads] = f1;
+    }
+#pragma unroll 1
+    for (int64_t cs = 0; cs < e1 - e0; cs += kOwnPositions) {
+        const int L = static_cast<int>(min(static_cast<int64_t>(kOwnPositions), e1 - e0 - cs));
+        build_owner_range(s_own, tile, cs, L);          // (ends with a barrier; s_flat is published by its first one)
+        V *dst = (MODE == EXPAND_PARENTS) ? out + e0 + cs : out + (e0 + cs - o0);
+#pragma unroll 2
+        for (int p = threadIdx.x; p < L; p += kTileThreads) {
+            const int ev = s_own[p];
+            if (MODE == EXPAND_PARENTS) __stcs(dst + p, static_cast<V>(tile.event0 + ev));
+            else if (MODE == EXPAND_LOCALINDEX) __stcs(dst + p, static_cast<V>(e0 + cs + p - s_off[ev]));
+            else __stcs(dst + p, s_flat[ev]);
         }
+        __syncthreads();                                 // the table is rewritten by the next chunk
     }
 }
 

@@ -103,47 +103,85 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
         return;
     }
 
-    // ---------------- LONG: warp-per-event (block-per-event for very long events) ---------------------------
+    // ---------------- LONG: the tile's run does not fit the stage ----------------------------------------------
+    // The events are taken in GROUPS of consecutive events whose run does fit (the largest such group, by a binary
+    // search over the offsets tile): each group is staged with one bulk copy and reduced exactly like a short tile;
+    // an event that exceeds the stage on its own is reduced by the whole CTA from global memory (16-byte loads, four in
+    // flight per thread).  A tile of 511 short events and one of 70 000 elements is two staged groups and one long
+    // event, ~25 us; round 1 reduced all 512 events one warp at a time from global memory (64 dependent round trips
+    // per warp, ~250 us), and a kernel ends when its slowest CTA does: 1000 such tiles among 150 M events cost the
+    // sum 0.22 ms of 1.12 (profiles/r2_exp32.log).
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int ev = warp; ev < tile.nev; ev += kTileThreads / kWarp) {
-        const int64_t a = s_off[ev], b = s_off[ev + 1];
-        if (b - a >= kBlockEventMin) continue;     // handled below by the whole CTA
-        Partial<A> p = strided_partial<OP, T, A>(content, a, b, lane, kWarp);
-        p = shuffle_merge<OP, T, A>(p);
-        if (lane == 0) out[tile.event0 + ev] = p.has ? p.val : R::identity();
-    }
-    for (int ev = 0; ev < tile.nev; ++ev) {
-        const int64_t a = s_off[ev], b = s_off[ev + 1];
-        if (b - a < kBlockEventMin) continue;
-        // in chunks of 1024 elements per thread: a thread's running float32 sum over millions of elements would
-        // drop the low bits of everything it adds (0.8 % on a 2^31-element event); chunk totals merged pairwise
-        // keep the order-of-summation error at the 1e-6 level for any length
-        Partial<A> p;
-        if constexpr (IsFloat<T>::value && (OP == JG_SUM || OP == JG_PROD)) {
-            // float sums in chunks of 1024 elements per thread: a thread's running float32 sum over millions of
-            // elements drops the low bits of everything it adds (0.8 % on a 2^31-element event); chunk totals keep
-            // the order-of-summation error at the 1e-6 level for any length.  (Only where rounding exists: the
-            // chunk loop costs the min / max instantiations 8 registers and a resident CTA.)
-            p.has = false;
-            p.val = R::identity();
-            p.pos = -1;
-            constexpr int64_t kChunk = static_cast<int64_t>(kTileThreads) * 1024;
-            for (int64_t c = a; c < b; c += kChunk)
-                p = merge<OP, T, A>(p, strided_partial<OP, T, A>(content, c, min(b, c + kChunk), threadIdx.x, kTileThreads));
-        } else {
-            p = strided_partial<OP, T, A>(content, a, b, threadIdx.x, kTileThreads);
+    constexpr int64_t kCap = STAGE_BYTES / static_cast<int64_t>(sizeof(T));
+    uint32_t phase = 0;
+    int g0 = 0;
+#pragma unroll 1
+    while (g0 < tile.nev) {
+        const int64_t start = s_off[g0];
+        int lo = g0, hi = tile.nev;                      // largest g1 with off[g1] - off[g0] <= kCap
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] - start <= kCap) lo = mid;
+            else hi = mid - 1;
         }
-        p = shuffle_merge<OP, T, A>(p);
-        __syncthreads();
-        if (lane == 0) s_part[warp] = p;
-        __syncthreads();
-        if (warp == 0) {
-            Partial<A> q;
-            if (lane < kTileThreads / kWarp) q = s_part[lane];
-            else { q.has = false; q.val = R::identity(); q.pos = -1; }
-            q = shuffle_merge<OP, T, A>(q);
-            if (lane == 0) out[tile.event0 + ev] = q.has ? q.val : R::identity();
+        if (lo == g0) {
+            // ---- one event longer than the stage: the whole CTA
+            const int64_t a = start, b = s_off[g0 + 1];
+            Partial<A> p;
+            if constexpr (IsFloat<T>::value && (OP == JG_SUM || OP == JG_PROD)) {
+                // float sums in chunks of 1024 elements per thread: a thread's running float32 sum over millions of
+                // elements drops the low bits of everything it adds (0.8 % on a 2^31-element event); chunk totals keep
+                // the order-of-summation error at the 1e-6 level for any length.  (Only where rounding exists: the
+                // chunk loop costs the min / max instantiations 8 registers and a resident CTA.)
+                p.has = false;
+                p.val = R::identity();
+                p.pos = -1;
+                constexpr int64_t kChunk = static_cast<int64_t>(kTileThreads) * 1024;
+                for (int64_t c = a; c < b; c += kChunk)
+                    p = merge<OP, T, A>(p, strided_partial<OP, T, A>(content, c, min(b, c + kChunk), threadIdx.x, kTileThreads));
+            } else {
+                p = strided_partial<OP, T, A>(content, a, b, threadIdx.x, kTileThreads);
+            }
+            p = shuffle_merge<OP, T, A>(p);
+            __syncthreads();
+            if (lane == 0) s_part[warp] = p;
+            __syncthreads();
+            if (warp == 0) {
+                Partial<A> q;
+                if (lane < kTileThreads / kWarp) q = s_part[lane];
+                else { q.has = false; q.val = R::identity(); q.pos = -1; }
+                q = shuffle_merge<OP, T, A>(q);
+                if (lane == 0) out[tile.event0 + g0] = q.has ? q.val : R::identity();
+            }
+            ++g0;
+            continue;
         }
+        // ---- events [g0, g1): staged, thread-per-event (two events per thread as in the short path)
+        const int g1 = lo;
+        const int64_t nb = (s_off[g1] - start) * static_cast<int64_t>(sizeof(T));
+        __syncthreads();                                 // the stage is free (the previous group has been read)
+        const T *sm = reinterpret_cast<const T *>(s_stage);
+        if (nb > 0) {
+            if (threadIdx.x == 0)
+                stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb), &s_bar);
+            const uint32_t shift = stage_edges<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb));
+            stage_wait(&s_bar, phase);
+            phase ^= 1u;
+            sm = reinterpret_cast<const T *>(s_stage + shift);
+        }
+#pragma unroll 1
+        for (int ev = g0 + threadIdx.x; ev < g1; ev += kTileThreads) {
+            const int a = static_cast<int>(s_off[ev] - start), len = static_cast<int>(s_off[ev + 1] - start) - a;
+            A acc = R::identity();
+            if (len > 0) {
+                acc = R::lift(sm[a]);
+#pragma unroll 1
+                for (int k = 1; k < len; ++k) acc = R::accumulate(acc, sm[a + k]);
+            }
+            out[tile.event0 + ev] = acc;
+        }
+        g0 = g1;
     }
 }
 
@@ -272,6 +310,76 @@ count_nonempty_kernel(const int64_t *__restrict__ offsets, int64_t n, int64_t nt
     if (lane == 0) tile_totals[tile] = cnt;
 }
 
+// A tile whose run does not fit the stage: groups of consecutive events that do are staged and arg-reduced by one thread
+// per event, an event longer than the stage by the whole CTA from global memory (see the long path of segreduce_kernel).
+// s_idx64[ev] = local index of the event's first extreme non-NaN item or -1; ends with a barrier.
+template <bool ISMIN, typename T, int STAGE_BYTES>
+__device__ __noinline__ void segarg_long_tile(const T *__restrict__ content, const int64_t *s_off, int nev,
+                                              unsigned char *s_stage, uint64_t *s_bar, ArgPartial<T> *s_part,
+                                              int64_t *s_idx64) {
+    constexpr int NW = kTileThreads / kWarp;
+    constexpr int64_t kCap = STAGE_BYTES / static_cast<int64_t>(sizeof(T));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t phase = 0;
+    int g0 = 0;
+#pragma unroll 1
+    while (g0 < nev) {
+        const int64_t start = s_off[g0];
+        int lo = g0, hi = nev;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] - start <= kCap) lo = mid;
+            else hi = mid - 1;
+        }
+        if (lo == g0) {
+            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T, 2>(content, start, s_off[g0 + 1], threadIdx.x, kTileThreads));
+            __syncthreads();
+            if (lane == 0) s_part[warp] = p;
+            __syncthreads();
+            if (warp == 0) {
+                ArgPartial<T> q;
+                if (lane < NW) q = s_part[lane];
+                else { q.idx = -1; q.val = T(0); }
+                q = arg_shuffle<ISMIN, T>(q);
+                if (lane == 0) s_idx64[g0] = q.idx;
+            }
+            ++g0;
+            continue;
+        }
+        const int g1 = lo;
+        const int64_t nb = (s_off[g1] - start) * static_cast<int64_t>(sizeof(T));
+        __syncthreads();                             // the stage is free (the previous group has been read)
+        const T *sm = reinterpret_cast<const T *>(s_stage);
+        if (nb > 0) {
+            if (threadIdx.x == 0)
+                stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb), s_bar);
+            const uint32_t shift = stage_edges<sizeof(T)>(
+                s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb));
+            stage_wait(s_bar, phase);
+            phase ^= 1u;
+            sm = reinterpret_cast<const T *>(s_stage + shift);
+        }
+#pragma unroll 1
+        for (int ev = g0 + threadIdx.x; ev < g1; ev += kTileThreads) {
+            const T *pe = sm + static_cast<int>(s_off[ev] - start);
+            const int len = static_cast<int>(s_off[ev + 1] - s_off[ev]);
+            int ibest = -1;
+            T vbest = T(0);
+#pragma unroll 1
+            for (int k = 0; k < len; ++k) {
+                const T x = pe[k];
+                if (!is_nan(x) && (ibest < 0 || (ISMIN ? (x < vbest) : (x > vbest)))) {
+                    vbest = x;
+                    ibest = k;
+                }
+            }
+            s_idx64[ev] = ibest;
+        }
+        g0 = g1;
+    }
+    __syncthreads();
+}
+
 template <bool ISMIN, typename T, int STAGE_BYTES>
 __global__ void __launch_bounds__(kTileThreads, STAGE_BYTES > 16384 ? 5 : 8)
 segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
@@ -386,42 +494,26 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
         val[0] = (iA >= 0) ? pA[iA] : T(0);
         val[1] = (iB >= 0) ? pB[iB] : T(0);
     } else {
+        // the tile's run does not fit the stage (a separate function: inlined, its live ranges cost the staged path a
+        // spilled register and 7 % of its speed)
         __shared__ int64_t s_idx64[kTileEvents];
-        T *s_val = reinterpret_cast<T *>(s_stage);      // the stage is unused on this path
-        for (int ev = warp; ev < tile.nev; ev += NW) {
-            const int64_t ea = s_off[ev], eb = s_off[ev + 1];
-            if (eb - ea >= kBlockEventMin) continue;
-            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T, 2>(content, ea, eb, lane, kWarp));
-            if (lane == 0) {
-                s_idx64[ev] = p.idx;
-                s_val[ev] = p.val;
-            }
+        segarg_long_tile<ISMIN, T, STAGE_BYTES>(content, s_off, tile.nev, s_stage, &s_bar, s_part, s_idx64);
+        // (results written here: joining the staged path's idx / val below costs that path a spilled register)
+        bool missing = false;
+        if (ne0) {
+            const int64_t i = s_idx64[ev0];
+            missing |= i < 0;
+            out_index[base] = i;
+            if (out_value) out_value[base] = i >= 0 ? __ldg(content + s_off[ev0] + i) : T(0);
         }
-        for (int ev = 0; ev < tile.nev; ++ev) {
-            const int64_t ea = s_off[ev], eb = s_off[ev + 1];
-            if (eb - ea < kBlockEventMin) continue;
-            ArgPartial<T> p = arg_shuffle<ISMIN, T>(arg_strided<ISMIN, T, 2>(content, ea, eb, threadIdx.x, kTileThreads));
-            __syncthreads();
-            if (lane == 0) s_part[warp] = p;
-            __syncthreads();
-            if (warp == 0) {
-                ArgPartial<T> q;
-                if (lane < NW) q = s_part[lane];
-                else { q.idx = -1; q.val = T(0); }
-                q = arg_shuffle<ISMIN, T>(q);
-                if (lane == 0) {
-                    s_idx64[ev] = q.idx;
-                    s_val[ev] = q.val;
-                }
-            }
+        if (ne1) {
+            const int64_t i = s_idx64[ev0 + 1];
+            missing |= i < 0;
+            out_index[base + ne0] = i;
+            if (out_value) out_value[base + ne0] = i >= 0 ? __ldg(content + s_off[ev0 + 1] + i) : T(0);
         }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-            if (ev0 + q < tile.nev) {
-                idx[q] = s_idx64[ev0 + q];
-                val[q] = s_val[ev0 + q];
-            }
+        if (missing) atomicOr(status, JG_ST_ARG_ALLNAN);
+        return;
     }
     bool mismatch = false;
     if (ne0) {

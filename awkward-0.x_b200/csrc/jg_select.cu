@@ -51,40 +51,84 @@ __device__ __forceinline__ int count16(const SEL &sel, int4 v) {
 
 constexpr int kCountWarps = 8;     // event tiles per CTA of the counting kernel
 
+constexpr int64_t kCountLongRun = 1 << 14;      // a run at least this long is counted by the whole CTA
+
+// selected items of m[0, len) seen by threads first, first + step, ...: unaligned head (< 16 bytes), 16-byte body (U
+// loads in flight per thread), tail
+template <class SEL, int U>
+__device__ __forceinline__ int64_t count_run(const SEL &sel, const typename SEL::Elem *m, int64_t len, int first, int step) {
+    using E = typename SEL::Elem;
+    constexpr int PER = 16 / sizeof(E);
+    int64_t cnt = 0;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
+    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
+    if (head > len) head = len;
+    if (first < head) cnt += sel.test(m[first]);
+    const int64_t nvec = (len - head) / PER;
+    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
+#pragma unroll U
+    for (int64_t i = first; i < nvec; i += step) cnt += count16(sel, __ldcs(mv + i));
+    const int64_t tail0 = head + nvec * PER;
+    if (tail0 + first < len) cnt += sel.test(m[tail0 + first]);
+    return cnt;
+}
+
 // OVERSIZE: only the tiles whose run exceeds `km` positions are counted (the single-pass selection counts every other
 // tile out of its own staged copy) and the totals are PUBLISHED (jg_lag.cuh) instead of stored.
+// One warp per event tile; a tile with a LONG run (an event of tens of thousands of items among short ones) is left to
+// the whole CTA afterwards: one warp keeps 1 KB in flight, and a kernel ends when its slowest warp does (70 000
+// float32 items: ~280 us for a warp, ~20 us for the CTA).
 template <class SEL, bool OVERSIZE = false>
-__global__ void __launch_bounds__(kCountWarps * kWarp)
+__global__ void __launch_bounds__(kCountWarps * kWarp, 8)
 mask_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ mask, int64_t mask_shift,
                   const int64_t *__restrict__ offsets, int64_t n, int64_t ntiles, int64_t *__restrict__ tile_totals,
                   const LagDesc lag = LagDesc{}, int64_t km = 0) {
     using E = typename SEL::Elem;
-    constexpr int PER = 16 / sizeof(E);
+    __shared__ int s_nlong;
+    __shared__ int s_long[kCountWarps];
+    __shared__ int64_t s_part[kCountWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_nlong = 0;
+    __syncthreads();
     const int64_t tile = static_cast<int64_t>(blockIdx.x) * kCountWarps + warp;
-    if (tile >= ntiles) return;
-    const int64_t ev0 = tile * kTileEvents;
-    const int64_t ev1 = min(n, ev0 + kTileEvents);
-    const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
-    const E *m = mask + e0 + mask_shift;
-    const int64_t len = e1 - e0;
-    if (OVERSIZE && len <= km) return;
-    int64_t cnt = 0;
-    // unaligned head (< 16 bytes), 16-byte body, tail
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(m);
-    int64_t head = static_cast<int64_t>(((16 - (addr & 15)) & 15) / sizeof(E));
-    if (head > len) head = len;
-    if (lane < head) cnt += sel.test(m[lane]);
-    const int64_t nvec = (len - head) / PER;
-    const int4 *mv = reinterpret_cast<const int4 *>(m + head);
-#pragma unroll 2
-    for (int64_t i = lane; i < nvec; i += kWarp) cnt += count16(sel, __ldcs(mv + i));
-    const int64_t tail0 = head + nvec * PER;
-    if (tail0 + lane < len) cnt += sel.test(m[tail0 + lane]);
-    cnt = warp_reduce_add(cnt);
-    if (lane == 0) {
-        if (OVERSIZE) lag_publish(lag, static_cast<uint32_t>(tile), cnt);
-        else tile_totals[tile] = cnt;
+    if (tile < ntiles) {
+        const int64_t ev0 = tile * kTileEvents;
+        const int64_t ev1 = min(n, ev0 + kTileEvents);
+        const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
+        const int64_t len = e1 - e0;
+        if (!(OVERSIZE && len <= km)) {
+            if (len >= kCountLongRun) {
+                if (lane == 0) s_long[atomicAdd(&s_nlong, 1)] = warp;
+            } else {
+                int64_t cnt = count_run<SEL, 2>(sel, mask + e0 + mask_shift, len, lane, kWarp);
+                cnt = warp_reduce_add(cnt);
+                if (lane == 0) {
+                    if (OVERSIZE) lag_publish(lag, static_cast<uint32_t>(tile), cnt);
+                    else tile_totals[tile] = cnt;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nlong = s_nlong;
+#pragma unroll 1
+    for (int q = 0; q < nlong; ++q) {
+        const int64_t t = static_cast<int64_t>(blockIdx.x) * kCountWarps + s_long[q];
+        const int64_t ev0 = t * kTileEvents;
+        const int64_t ev1 = min(n, ev0 + kTileEvents);
+        const int64_t e0 = __ldg(offsets + ev0), e1 = __ldg(offsets + ev1);
+        int64_t cnt = count_run<SEL, 4>(sel, mask + e0 + mask_shift, e1 - e0, threadIdx.x, kCountWarps * kWarp);
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0) s_part[warp] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kCountWarps; ++w) total += s_part[w];
+            if (OVERSIZE) lag_publish(lag, static_cast<uint32_t>(t), total);
+            else tile_totals[t] = total;
+        }
+        __syncthreads();
     }
 }
 
@@ -208,10 +252,12 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         return;
     }
 
-    // ---------------- oversize tile (long events): chunks of KM positions straight from global memory --------
-    // The whole CTA compacts the run chunk by chunk exactly like a staged tile (coalesced reads, ballot / popc
-    // slots, consecutive stores) with a running base; an event takes its new offset from the chunk that holds its
-    // first position.  (One thread per event, as before, walked an event of a million elements alone.)
+    // ---------------- oversize tile (long events): the run in chunks of KM positions ---------------------------
+    // Every chunk is staged and compacted exactly like a staged tile (one bulk copy, the same two passes over whole
+    // rows) with a running base; an event takes its new offset from the chunk that holds its first position.  (Round 1
+    // read every chunk twice from global memory between four barriers; a kernel ends when its slowest CTA does, and
+    // 1000 tiles with an event of 5 k - 70 k elements among 150 M short events cost a[a > 20] 0.35 ms of 2.05,
+    // profiles/r2_exp32.log.)
     if constexpr (SINGLE) {       // (counted and published before the launch)
         if (warp == 0) {
             const int64_t b = lag_prefix(lag, tile_index);
@@ -220,53 +266,52 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         __syncthreads();
         base = s_base;
     }
-    const V *cv = content + e0;
-    const E *mv = mask + e0 + mask_shift;
-    int64_t *s_new = reinterpret_cast<int64_t *>(s_content);      // the stage is idle here: new offsets within the tile
-    static_assert(KM * sizeof(V) + 32 >= (kTileEvents + 1) * sizeof(int64_t), "stage too small for the offsets");
     const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
     const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
     const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
+    __syncthreads();              // every start is in its thread's registers: the offsets tile becomes the NEW offsets
+    int64_t *s_new = s_off;
     int64_t run = 0;
+    uint32_t phase = 0;           // (neither barrier has been used: thread 0 only starts a copy for a run that fits)
 #pragma unroll 1
     for (int64_t cs = 0; cs < len; cs += KM) {
         const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
-        const E *m = mv + cs;
-        const V *c = cv + cs;
+        const V *gc = content + e0 + cs;
+        const E *gm = mask + e0 + mask_shift + cs;
+        if (threadIdx.x == 0) {
+            if (!SAME) stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(gm), static_cast<uint32_t>(L * sizeof(E)), &s_bar[1]);
+            stage_bulk(s_content, reinterpret_cast<const unsigned char *>(gc), static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
+        }
+        const uint32_t cshift = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(gc), static_cast<uint32_t>(L * sizeof(V)));
+        const V *cv = reinterpret_cast<const V *>(s_content + cshift);
+        E *pad;
+        if (SAME) {
+            pad = reinterpret_cast<E *>(s_content + cshift);
+        } else {
+            const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(gm), static_cast<uint32_t>(L * sizeof(E)));
+            pad = reinterpret_cast<E *>(s_mask + ms);
+        }
+        const E *mv = pad;
+        if (warp == 1) rows_pad<SEL>(pad, L, lane);
+        mbar_wait(&s_bar[0], phase);
+        if (!SAME) mbar_wait(&s_bar[1], phase);
+        phase ^= 1u;
+        __syncthreads();
         const int rows_total = (L + 31) >> 5;
         const int rows_per_warp = (rows_total + NW - 1) / NW;
-        const int p_begin = min(L, warp * rows_per_warp * 32);
-        const int p_end = min(L, p_begin + rows_per_warp * 32);
-        int cnt = 0;
-#pragma unroll 8
-        for (int p = p_begin + lane; p < p_end; p += 32) cnt += sel.test(m[p]);       // (unrolled: loads in flight)
-        cnt = warp_reduce_add(cnt);
+        const int r_begin = min(rows_total, warp * rows_per_warp);
+        const int r_end = min(rows_total, r_begin + rows_per_warp);
+        const int cnt = rows_count(sel, mv, r_begin, r_end, lane);
         if (lane == 0) s_scan[warp] = cnt;
         __syncthreads();
-        if (warp == 0) {
-            int w = lane < NW ? s_scan[lane] : 0;
-            int wi = warp_incl_scan_add(w, lane);
-            if (lane < NW) s_scan[lane] = wi - w;
-            if (lane == NW - 1) s_pfx[L] = static_cast<uint16_t>(wi);
-        }
-        __syncthreads();
-        int wrun = s_scan[warp];
-        V *dst = out + base + run;
-#pragma unroll 4
-        for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-            const int p = p0 + lane;
-            const bool on = p < p_end && sel.test(m[p]);
-            const unsigned b = __ballot_sync(0xffffffffu, on);
-            const int slot = wrun + __popc(b & ((1u << lane) - 1u));
-            if (p < p_end) s_pfx[p] = static_cast<uint16_t>(slot);
-            if (on) dst[slot] = c[p];
-            wrun += __popc(b);
-        }
+        uint32_t wrun = __reduce_add_sync(0xffffffffu, lane < warp ? s_scan[lane] : 0);
+        wrun = rows_compact<V, SEL, SAME>(sel, mv, cv, s_pfx, r_begin, r_end, lane, wrun, out + base + run);
+        if (warp == NW - 1 && lane == 0) s_pfx[rows_total << 5] = static_cast<uint16_t>(wrun);
         __syncthreads();
         if (stA >= cs && stA < cs + L) s_new[evA] = run + s_pfx[stA - cs];
         if (stB >= cs && stB < cs + L) s_new[evB] = run + s_pfx[stB - cs];
         run += s_pfx[L];
-        __syncthreads();      // s_pfx and s_scan are rewritten by the next chunk
+        __syncthreads();      // the stage, s_pfx and s_scan are rewritten by the next chunk
     }
     if (stA >= len) s_new[evA] = run;       // empty events at the end of the tile
     if (stB >= len) s_new[evB] = run;
