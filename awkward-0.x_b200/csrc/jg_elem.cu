@@ -592,7 +592,7 @@ select_elem_count_kernel(const SEL sel, const typename SEL::Elem *__restrict__ m
 // fill: the tile's run staged by TMA, element-parallel ballot / popc compaction (a warp's stores are consecutive), then
 // every owned event reads its new offset (and, when it ends inside the tile, its count) from the per-position prefix
 template <typename V, class SEL, bool SAME>
-__global__ void __launch_bounds__(kElemThreads, 6)
+__global__ void __launch_bounds__(kElemThreads, sizeof(V) == 8 ? 6 : 8)
 select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
                         int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n,
                         const int64_t *__restrict__ first_event, V *__restrict__ out, int64_t *__restrict__ new_offsets,
@@ -623,6 +623,13 @@ select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const type
     const int64_t ev_lo = __ldg(first_event + tile), ev_hi = __ldg(first_event + tile + 1);
     const int64_t base = __ldg(tile_bases + tile);
     if (tile == ntiles - 1 && tid == 0) new_offsets[n] = __ldg(tile_bases + ntiles);
+    // the offsets of the thread's first owned event are asked for now, while the tile is on its way (they are needed
+    // after the compaction: a dependent round trip at the end of the CTA's life otherwise, holding its shared memory)
+    int64_t ea = 0, eb = 0;
+    if (ev_lo + tid < ev_hi) {
+        ea = __ldg(offsets + ev_lo + tid);
+        eb = __ldg(offsets + ev_lo + tid + 1);
+    }
     __syncthreads();
     const V *cv = nullptr;
     const E *mv = nullptr;
@@ -656,10 +663,18 @@ select_elem_fill_kernel(const SEL sel, const V *__restrict__ content, const type
     __syncthreads();
 #pragma unroll 1
     for (int64_t e = ev_lo + tid; e < ev_hi; e += kElemThreads) {
-        const int64_t a = __ldg(offsets + e) - lo, b = __ldg(offsets + e + 1) - lo;
+        const int64_t en = e + kElemThreads;
+        int64_t na = 0, nb = 0;
+        if (en < ev_hi) {
+            na = __ldg(offsets + en);
+            nb = __ldg(offsets + en + 1);
+        }
+        const int64_t a = ea - lo, b = eb - lo;
         const int first = s_pfx[a];
         new_offsets[e] = base + first;
         if (new_counts && b <= L) new_counts[e] = static_cast<int>(s_pfx[b]) - first;
+        ea = na;
+        eb = nb;
     }
 }
 
