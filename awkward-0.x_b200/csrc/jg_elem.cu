@@ -247,7 +247,12 @@ segreduce_elem_kernel(const T *__restrict__ content, const int64_t *__restrict__
 }
 
 // events that span several tiles: out[e] holds the part inside the tile where e starts, carry[t] the parts inside the
-// following tiles.  One warp per tile whose last owned event leaves it; lanes stride the tiles, merged in tile order.
+// following tiles, merged in tile order.  One THREAD per tile whose last owned event leaves it (the usual case at mean
+// counts of 10 - 100: the event ends in the next tile or the one after: a warp per tile ran four dependent loads for
+// one useful lane, 52 us of a 0.67 ms argmax on Poisson(40)); a span of more than kFixSerial tiles is handed to the
+// whole warp (lanes stride the tiles, shuffle merge).
+constexpr int kFixSerial = 8;
+
 template <int OP, typename T, typename A>
 __global__ void __launch_bounds__(kElemThreads)
 segreduce_elem_fix_kernel(const int64_t *__restrict__ offsets, int64_t n, const int64_t *__restrict__ first_event,
@@ -255,34 +260,59 @@ segreduce_elem_fix_kernel(const int64_t *__restrict__ offsets, int64_t n, const 
     constexpr int ET = ElemTile<T>::ET;
     using R = Red<OP, T, A>;
     const int lane = threadIdx.x & 31;
-    const int64_t c = static_cast<int64_t>(blockIdx.x) * kElemWarps + (threadIdx.x >> 5);
-    if (c >= ntiles) return;
-    const int64_t ev_lo = __ldg(first_event + c), ev_hi = __ldg(first_event + c + 1);
-    if (ev_hi <= ev_lo) return;
-    const int64_t e = ev_hi - 1;
-    const int64_t base = __ldg(offsets);
-    const int64_t hi = base + (c + 1) * ET;
-    const int64_t stop = __ldg(offsets + e + 1);
-    if (stop <= hi) return;                                   // the event ends inside its own tile
-    const int64_t t_end = (stop - 1 - base) / ET;
-    Partial<A> p;
-    p.has = false;
-    p.val = R::identity();
-    p.pos = -1;
-    for (int64_t t = c + 1 + lane; t <= t_end; t += kWarp) {
-        Partial<A> q;
-        q.has = true;
-        q.val = carry[t];
-        q.pos = t;
-        p = merge<OP, T, A>(p, q);
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * kElemThreads + threadIdx.x;
+    int64_t e = -1, t_end = -1;
+    if (c < ntiles) {
+        const int64_t ev_lo = __ldg(first_event + c), ev_hi = __ldg(first_event + c + 1);
+        if (ev_hi > ev_lo) {
+            const int64_t base = __ldg(offsets);
+            const int64_t stop = __ldg(offsets + ev_hi);
+            if (stop > base + (c + 1) * ET) {             // the last owned event leaves its tile
+                e = ev_hi - 1;
+                t_end = (stop - 1 - base) / ET;
+            }
+        }
     }
-    p = shuffle_merge<OP, T, A>(p);
-    if (lane == 0) {
-        Partial<A> first;
-        first.has = true;
-        first.val = out[e];
-        first.pos = c;
-        out[e] = merge<OP, T, A>(first, p).val;
+    const bool spans = e >= 0;
+    if (spans && t_end - c <= kFixSerial) {
+        Partial<A> p;
+        p.has = true;
+        p.val = out[e];
+        p.pos = c;
+        for (int64_t t = c + 1; t <= t_end; ++t) {
+            Partial<A> q;
+            q.has = true;
+            q.val = carry[t];
+            q.pos = t;
+            p = merge<OP, T, A>(p, q);
+        }
+        out[e] = p.val;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, spans && t_end - c > kFixSerial);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t wc = __shfl_sync(0xffffffffu, c, src), we = __shfl_sync(0xffffffffu, e, src);
+        const int64_t wt = __shfl_sync(0xffffffffu, t_end, src);
+        Partial<A> p;
+        p.has = false;
+        p.val = R::identity();
+        p.pos = -1;
+        for (int64_t t = wc + 1 + lane; t <= wt; t += kWarp) {
+            Partial<A> q;
+            q.has = true;
+            q.val = carry[t];
+            q.pos = t;
+            p = merge<OP, T, A>(p, q);
+        }
+        p = shuffle_merge<OP, T, A>(p);
+        if (lane == 0) {
+            Partial<A> first;
+            first.has = true;
+            first.val = out[we];
+            first.pos = wc;
+            out[we] = merge<OP, T, A>(first, p).val;
+        }
     }
 }
 
@@ -426,36 +456,63 @@ __global__ void __launch_bounds__(kElemThreads)
 segarg_elem_fix_kernel(const int64_t *__restrict__ offsets, int64_t n, const int64_t *__restrict__ first_event,
                        int64_t ntiles, int64_t *__restrict__ best, T *__restrict__ best_value,
                        const int64_t *__restrict__ carry_idx, const T *__restrict__ carry_val) {
+    // (one thread per tile, long spans by the whole warp: see segreduce_elem_fix_kernel)
     constexpr int ET = ElemTile<T>::ET;
     const int lane = threadIdx.x & 31;
-    const int64_t c = static_cast<int64_t>(blockIdx.x) * kElemWarps + (threadIdx.x >> 5);
-    if (c >= ntiles) return;
-    const int64_t ev_lo = __ldg(first_event + c), ev_hi = __ldg(first_event + c + 1);
-    if (ev_hi <= ev_lo) return;
-    const int64_t e = ev_hi - 1;
-    const int64_t base = __ldg(offsets);
-    const int64_t hi = base + (c + 1) * ET;
-    const int64_t start = __ldg(offsets + e), stop = __ldg(offsets + e + 1);
-    if (stop <= hi) return;
-    const int64_t t_end = (stop - 1 - base) / ET;
-    ArgPartial<T> p;
-    p.idx = -1;
-    p.val = T(0);
-    for (int64_t t = c + 1 + lane; t <= t_end; t += kWarp) {
-        ArgPartial<T> q;
-        q.idx = carry_idx[t];
-        q.val = carry_val[t];
-        p = arg_merge<ISMIN, T>(p, q);
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * kElemThreads + threadIdx.x;
+    int64_t e = -1, t_end = -1, start = 0;
+    if (c < ntiles) {
+        const int64_t ev_lo = __ldg(first_event + c), ev_hi = __ldg(first_event + c + 1);
+        if (ev_hi > ev_lo) {
+            const int64_t base = __ldg(offsets);
+            const int64_t stop = __ldg(offsets + ev_hi);
+            if (stop > base + (c + 1) * ET) {
+                e = ev_hi - 1;
+                start = __ldg(offsets + e);
+                t_end = (stop - 1 - base) / ET;
+            }
+        }
     }
-    p = arg_shuffle<ISMIN, T>(p);
-    if (lane == 0) {
-        ArgPartial<T> first;
+    const bool spans = e >= 0;
+    if (spans && t_end - c <= kFixSerial) {
+        ArgPartial<T> p;
         const int64_t local = best[e];
-        first.idx = local < 0 ? -1 : local + start;
-        first.val = best_value[e];
-        const ArgPartial<T> w = arg_merge<ISMIN, T>(first, p);
-        best[e] = w.idx < 0 ? -1 : w.idx - start;
-        best_value[e] = w.val;
+        p.idx = local < 0 ? -1 : local + start;
+        p.val = best_value[e];
+        for (int64_t t = c + 1; t <= t_end; ++t) {
+            ArgPartial<T> q;
+            q.idx = carry_idx[t];
+            q.val = carry_val[t];
+            p = arg_merge<ISMIN, T>(p, q);
+        }
+        best[e] = p.idx < 0 ? -1 : p.idx - start;
+        best_value[e] = p.val;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, spans && t_end - c > kFixSerial);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t wc = __shfl_sync(0xffffffffu, c, src), we = __shfl_sync(0xffffffffu, e, src);
+        const int64_t wt = __shfl_sync(0xffffffffu, t_end, src), ws = __shfl_sync(0xffffffffu, start, src);
+        ArgPartial<T> p;
+        p.idx = -1;
+        p.val = T(0);
+        for (int64_t t = wc + 1 + lane; t <= wt; t += kWarp) {
+            ArgPartial<T> q;
+            q.idx = carry_idx[t];
+            q.val = carry_val[t];
+            p = arg_merge<ISMIN, T>(p, q);
+        }
+        p = arg_shuffle<ISMIN, T>(p);
+        if (lane == 0) {
+            ArgPartial<T> first;
+            const int64_t local = best[we];
+            first.idx = local < 0 ? -1 : local + ws;
+            first.val = best_value[we];
+            const ArgPartial<T> w = arg_merge<ISMIN, T>(first, p);
+            best[we] = w.idx < 0 ? -1 : w.idx - ws;
+            best_value[we] = w.val;
+        }
     }
 }
 
@@ -728,7 +785,7 @@ static int launch_reduce_elem(const void *content, const int64_t *offsets, int64
         static_cast<const T *>(content), offsets, n, p.first_event, static_cast<A *>(out), carry);
     int rc = check_launch("segreduce_elem_kernel");
     if (rc) return rc;
-    segreduce_elem_fix_kernel<OP, T, A><<<static_cast<unsigned>(ceil_div(p.ntiles, kElemWarps)), kElemThreads, 0, s>>>(
+    segreduce_elem_fix_kernel<OP, T, A><<<static_cast<unsigned>(ceil_div(p.ntiles, kElemThreads)), kElemThreads, 0, s>>>(
         offsets, n, p.first_event, p.ntiles, static_cast<A *>(out), carry);
     return check_launch("segreduce_elem_fix_kernel");
 }
@@ -754,7 +811,7 @@ static int dispatch_arg_elem(int is_min, const void *content, const int64_t *off
     JG_REQUIRE(p.rest_bytes >= idx_bytes + static_cast<size_t>(p.ntiles) * sizeof(T), "jg_segargminmax_elem: workspace too small");
     int64_t *carry_idx = reinterpret_cast<int64_t *>(p.rest);
     T *carry_val = reinterpret_cast<T *>(p.rest + idx_bytes);
-    const unsigned g = static_cast<unsigned>(p.ntiles), gf = static_cast<unsigned>(ceil_div(p.ntiles, kElemWarps));
+    const unsigned g = static_cast<unsigned>(p.ntiles), gf = static_cast<unsigned>(ceil_div(p.ntiles, kElemThreads));
     if (is_min) {
         segarg_elem_kernel<true, T><<<g, kElemRedThreads, 0, s>>>(static_cast<const T *>(content), offsets, n, p.first_event, best,
                                                               static_cast<T *>(best_value), carry_idx, carry_val);
