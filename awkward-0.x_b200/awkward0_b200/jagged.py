@@ -143,8 +143,19 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     LONG_EVENTS_MEAN = 7
 
     @classmethod
-    def _long_events(cls, n, content_len):
-        return n > 0 and content_len > cls.LONG_EVENTS_MEAN * n and content_len >= (1 << 14)
+    def _long_events(cls, n, content_len, wide=1):
+        return n > 0 and content_len > cls.LONG_EVENTS_MEAN * wide * n and content_len >= (1 << 14)
+
+    @classmethod
+    def _stage_hint(cls, n, content_len, dtype):
+        """(element tiles?, hint for the event-tiled call): the reductions keep 4-byte contents with mean counts of
+        7 - 14 on the event-tiled kernels by staging 32 KB per tile (JG_WIDE_STAGE); beyond that -- and from 7 on for
+        8-byte items, whose stage is 32 KB already -- the element-tiled kernels take over."""
+        dtype = numpy.dtype(dtype)
+        wide = 2 if dtype.itemsize == 4 else 1
+        if dtype in _ELEM_DTYPES and cls._long_events(n, content_len, wide):
+            return True, 0
+        return False, (_lib.WIDE_STAGE if wide == 2 and cls._long_events(n, content_len) else 0)
 
     @classmethod
     def _parents_from(cls, off64, n, last, first=None):
@@ -1439,12 +1450,13 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         odt = self._reduce_out_dtype(op, col.dtype)
         out = empty(n, odt)
         if n > 0:
-            if self._long_events(n, last - first) and col.dtype in _ELEM_DTYPES:
+            elem, hint = self._stage_hint(n, last - first, col.dtype)
+            if elem:
                 ws, wsb = runtime.elem_workspace(last - first, col.itemsize)
                 call("jg_segreduce_elem", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out),
                      last - first, ws, wsb, runtime.stream())
             else:
-                call("jg_segreduce", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op, _vp(out), len(col),
+                call("jg_segreduce", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, op | hint, _vp(out), len(col),
                      runtime.stream())
         return DeviceArray(out, odt)
 
@@ -1537,7 +1549,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out_index = empty(n, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
-        if self._long_events(n, last - first) and col.dtype in _ELEM_DTYPES:
+        elem, hint = self._stage_hint(n, last - first, col.dtype)
+        if elem:
             # long events: element-tiled arg-reduce to best[] (a partial per tile, merged in tile order), then the scan +
             # compaction of jg_compact_nonneg -- N-sized passes, small next to the content when events are long
             best, best_value = empty(n, INDEXTYPE), empty(n, col.dtype)
@@ -1549,7 +1562,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             return self._make(DeviceArray(out_offsets, INDEXTYPE), DeviceArray(out_index[:total], INDEXTYPE), total)
         values = empty(n, col.dtype) if self.cache_arg_values else None
         tiles = a._tile_nonempty               # known when the array came from fromcounts: no counting pass
-        call("jg_segargminmax_dense_tiles", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, 1 if ismin else 0,
+        call("jg_segargminmax_dense_tiles", col.data_ptr(), jg_code(col.dtype), off.data_ptr(), n, (1 if ismin else 0) | hint,
              _vp(tiles), _vp(out_offsets), _vp(out_index), _vp(values), _vp(scal), _vp(scal, 1), ws, wsb, runtime.stream())
         total, status, _ = runtime.read(scal)
         if status & _lib.ST_ARG_ALLNAN:

@@ -531,8 +531,20 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
 
 template <typename T> struct StageBytes { static constexpr int value = sizeof(T) >= 8 ? 32768 : (sizeof(T) >= 4 ? 16384 : 8192); };
 
+// JG_WIDE_STAGE (a hint OR-ed into the operation by a caller who knows the mean count is 7 - 14): 4-byte contents are
+// staged 32 KB per tile instead of 16 KB, so that the 512 events of a tile still fit and such arrays stay on the
+// thread-per-event kernels (5 - 6 resident CTAs per SM instead of 8, twice the bytes each).  Same results either way.
+template <typename T> struct WideStage { static constexpr bool value = sizeof(T) == 4; };
+
 template <int OP, typename T, typename A>
-static int launch_reduce(const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s) {
+static int launch_reduce(const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s, bool wide = false) {
+    if constexpr (WideStage<T>::value) {
+        if (wide) {
+            segreduce_kernel<OP, T, A, 32768><<<tile_grid(n), kTileThreads, 0, s>>>(
+                static_cast<const T *>(content), offsets, n, static_cast<A *>(out));
+            return check_launch("segreduce_kernel<wide>");
+        }
+    }
     segreduce_kernel<OP, T, A, StageBytes<T>::value><<<tile_grid(n), kTileThreads, 0, s>>>(
         static_cast<const T *>(content), offsets, n, static_cast<A *>(out));
     return check_launch("segreduce_kernel");
@@ -540,13 +552,14 @@ static int launch_reduce(const void *content, const int64_t *offsets, int64_t n,
 
 template <typename T, typename ASUM>
 static int dispatch_reduce(int op, const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s) {
-    switch (op) {
-        case JG_SUM: return launch_reduce<JG_SUM, T, ASUM>(content, offsets, n, out, s);
-        case JG_PROD: return launch_reduce<JG_PROD, T, ASUM>(content, offsets, n, out, s);
-        case JG_MIN: return launch_reduce<JG_MIN, T, T>(content, offsets, n, out, s);
-        case JG_MAX: return launch_reduce<JG_MAX, T, T>(content, offsets, n, out, s);
-        case JG_ANY: return launch_reduce<JG_ANY, T, uint8_t>(content, offsets, n, out, s);
-        case JG_ALL: return launch_reduce<JG_ALL, T, uint8_t>(content, offsets, n, out, s);
+    const bool wide = (op & JG_WIDE_STAGE) != 0;
+    switch (op & ~JG_WIDE_STAGE) {
+        case JG_SUM: return launch_reduce<JG_SUM, T, ASUM>(content, offsets, n, out, s, wide);
+        case JG_PROD: return launch_reduce<JG_PROD, T, ASUM>(content, offsets, n, out, s, wide);
+        case JG_MIN: return launch_reduce<JG_MIN, T, T>(content, offsets, n, out, s, wide);
+        case JG_MAX: return launch_reduce<JG_MAX, T, T>(content, offsets, n, out, s, wide);
+        case JG_ANY: return launch_reduce<JG_ANY, T, uint8_t>(content, offsets, n, out, s, wide);
+        case JG_ALL: return launch_reduce<JG_ALL, T, uint8_t>(content, offsets, n, out, s, wide);
     }
     set_error("jg_segreduce: unsupported op %d", op);
     return -2;
@@ -589,6 +602,21 @@ static int dispatch_arg_dense(int is_min, const void *content, const int64_t *of
     }
     rc = launch_scan_array(tile_nonempty, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
     if (rc) return rc;
+    const bool wide = (is_min & JG_WIDE_STAGE) != 0;
+    is_min &= ~JG_WIDE_STAGE;
+    if constexpr (WideStage<T>::value) {
+        if (wide) {
+            if (is_min)
+                segarg_direct_kernel<true, T, 32768><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+                    static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+                    status, static_cast<uint32_t>(ntiles));
+            else
+                segarg_direct_kernel<false, T, 32768><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
+                    static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+                    status, static_cast<uint32_t>(ntiles));
+            return check_launch("segarg_direct_kernel<wide>");
+        }
+    }
     if (is_min)
         segarg_direct_kernel<true, T, StageBytes<T>::value><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(
             static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),

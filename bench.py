@@ -729,8 +729,8 @@ def kernel_table(ak, _lib, DeviceArray, empty, runtime, counts_dev, pt_dev, N, M
 
 def distribution_table(ak, args):
     """north_star: "variants chosen by count distribution".  The same four hot-path operations -- sum, argmax, a[a > 20],
-    parents -- through the public API on count distributions other than the Poisson(5) the sweep is quoted on: long
-    events (Poisson(40)), a heavy tail (geometric, mean 4, plus events of 5 k - 70 k elements) and a few huge events
+    parents -- through the public API on count distributions other than the Poisson(5) the sweep is quoted on: mean
+    counts of 10 (the event tile staged 32 KB at a time for the reductions), long events (Poisson(40)), a heavy tail (geometric, mean 4, plus events of 5 k - 70 k elements) and a few huge events
     (1000 events x 1 M elements).  CUDA events around the call, host synchronisations included; algorithmic bytes as
     in SURVEY 8d."""
     import torch
@@ -741,6 +741,8 @@ def distribution_table(ak, args):
     out = {}
 
     def shapes():
+        n = args.dist_elements // 10
+        yield "poisson10", torch.poisson(torch.full((n,), 10.0, device=dev), generator=g).to(torch.int64)
         n = args.dist_elements // 40
         yield "poisson40", torch.poisson(torch.full((n,), 40.0, device=dev), generator=g).to(torch.int64)
         n = args.dist_elements // 4

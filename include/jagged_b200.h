@@ -88,6 +88,11 @@ enum {
  * same either way; with the hint the kernels built for long events run (direct tables: owner table over output
  * chunks + per-event info + combination look-up table) instead of those tuned for dimuon-like events.              */
 #define JG_COMB_LONG 0x100
+/* OR-ed into `op` of jg_segreduce and into `is_min` of jg_segargminmax_dense / _dense_tiles: a HINT that the mean event
+ * holds 7 - 14 items (the caller knows content length and number of events).  The result is the same either way; with
+ * the hint 4-byte contents are staged 32 KB per 512-event tile instead of 16 KB, so such arrays stay on the
+ * thread-per-event kernels instead of taking the long-tile path (ignored for other item sizes).                     */
+#define JG_WIDE_STAGE 0x100
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int         jg_version(void);

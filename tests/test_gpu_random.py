@@ -656,3 +656,78 @@ def test_selection_row_edges(ak, L, shift):
                 assert same(g.offsets.get(), soff), (L, shift, dtype)
                 assert same(g.content.get(), sel), (L, shift, dtype)
                 assert same(g.counts.get(), O.offsets2counts(soff)), (L, shift, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int8])
+@pytest.mark.parametrize("layout", ["first", "last", "adjacent", "exact", "one_over", "only_long", "between_empties"])
+def test_tiles_that_do_not_fit_the_stage(ak, layout, dtype):
+    """Event tiles (512 events) whose run exceeds the 16 KB stage because of a few long events among short ones (mean
+    count below 7, so the event-tiled kernels run): the reductions take such a tile in staged GROUPS of consecutive events
+    and reduce an event longer than the stage with the whole CTA, the selection stages its chunks, parents / localindex /
+    broadcast build one owner table per chunk.  Long events at the start / end of a tile, next to each other, of exactly
+    the stage's capacity and one more, alone among empty events."""
+    rng = np.random.default_rng(zlib.crc32(repr((layout, np.dtype(dtype).name)).encode()))
+    stage = 16384 // np.dtype(dtype).itemsize if np.dtype(dtype).itemsize >= 4 else 8192
+    n = 512 * 200
+    counts = rng.poisson(3.0, n).astype(np.int64)
+    tiles = rng.choice(200, 8, replace=False) * 512
+    for j, t in enumerate(tiles):
+        big = int(rng.integers(stage + 1, 3 * stage)) if j % 2 else int(rng.integers(stage // 2, stage))
+        if layout == "first":
+            counts[t] = big
+        elif layout == "last":
+            counts[t + 511] = big
+        elif layout == "adjacent":
+            counts[t + 200] = big
+            counts[t + 201] = int(rng.integers(stage + 1, 2 * stage))
+            counts[t + 202] = stage // 3
+        elif layout == "exact":
+            counts[t + 100] = stage
+            counts[t + 300] = stage
+        elif layout == "one_over":
+            counts[t + 100] = stage + 1
+            counts[t + 101] = stage - 1
+        elif layout == "only_long":
+            counts[t:t + 512] = 0
+            counts[t + 17] = big
+            counts[t + 400] = stage + 5
+        elif layout == "between_empties":
+            counts[t + 250:t + 262] = 0
+            counts[t + 256] = big
+    assert counts.sum() <= 7 * n
+    m = int(counts.sum())
+    if np.dtype(dtype).kind == "f":
+        content = rng.normal(0.0, 30.0, m).astype(dtype)
+        content[rng.random(m) < 0.01] = np.nan
+    else:
+        content = rng.integers(-100, 100, m).astype(dtype)
+    off = O.counts2offsets(counts)
+    a = ak.JaggedArray.fromcounts(counts, content)
+    with np.errstate(all="ignore"):
+        for op in ("min", "max", "any", "all"):
+            assert same(getattr(a, op)().get(), O.reduce(off, content, op)), op
+        want = O.reduce(off, content, "sum")
+        got = a.sum().get()
+        if want.dtype.kind == "f":
+            assert reduce_close("sum", got, want, off, content, RTOL[np.dtype(dtype)]).all()
+        else:
+            assert same(got, want)
+        for ismin in (False, True):
+            roff, ridx = O.argminmax(off, content, ismin)
+            r = a.argmin() if ismin else a.argmax()
+            assert same(r.offsets.get(), roff) and same(r.content.get(), ridx)
+        lead = a[a.argmax()]
+        loff, lval = O.index_gather(off, content, *O.argminmax(off, content, False))
+        assert same(lead.offsets.get(), loff) and same(lead.content.get(), lval)
+    thr = 10 if np.dtype(dtype).kind == "f" else 0
+    with np.errstate(invalid="ignore"):
+        mask = content > thr
+    soff, sel = O.mask_select(off, content, off, mask)
+    for g in (a[a > thr], a[ak.JaggedArray.fromoffsets(a.offsets, ak.asdevice(mask))]):
+        assert same(g.offsets.get(), soff) and same(g.content.get(), sel) and same(g.counts.get(), O.offsets2counts(soff))
+    assert same(a.parents.get(), O.offsets2parents(off))
+    assert same(a.localindex.content.get(), O.localindex(off)[1])
+    flat = rng.integers(-5, 5, n).astype(dtype)
+    boff, bval = O.ufunc_broadcast(np.add, off, content, flat)
+    b = a + flat
+    assert same(b.offsets.get(), boff) and same(b.content.get(), bval)
