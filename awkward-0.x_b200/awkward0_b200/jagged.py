@@ -161,7 +161,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
     def _parents_from(cls, off64, n, last, first=None):
         out = empty(last, INDEXTYPE)
         if last > 0:
-            if first is not None and cls._long_events(n, last - first):
+            if first is not None and cls._long_events(n, last - first, 2):      # (the event-tiled table covers means up to 14)
                 ws, wsb = runtime.elem_workspace(last - first, 4)
                 call("jg_expand_elem", 0, ctypes.c_void_p(0), 8, off64.data_ptr(), n, _vp(out), last - first, ws, wsb,
                      runtime.stream())
@@ -741,7 +741,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         a, off, n, first, last = self._dense()
         out = empty(last - first, INDEXTYPE)
         if last > first:
-            if self._long_events(n, last - first):
+            if self._long_events(n, last - first, 2):
                 ws, wsb = runtime.elem_workspace(last - first, 4)
                 call("jg_expand_elem", 1, ctypes.c_void_p(0), 8, off.data_ptr(), n, _vp(out), last - first, ws, wsb,
                      runtime.stream())
@@ -1229,11 +1229,12 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         if fused:
             op, scalar = _lib.OP[mask._op], mask._scalar
 
-        long_events = self._long_events(n, last - first)
-
         def select(col):
             out = empty(last - first, col.dtype)
             counts_ptr = _vp(new_counts) if not columns else ctypes.c_void_p(0)
+            # (element tiles from a mean count of 7 on: a 7168-position event tile -- 4 CTAs per SM -- was measured on
+            # Poisson(8 / 10 / 13): 54 - 55 % against 57 % for the element tiles, profiles/r2_exp42.log)
+            long_events = self._long_events(n, last - first)
             if long_events and col.itemsize in (4, 8) and (not fused or same or key.itemsize == col.itemsize):
                 ews, ewsb = runtime.elem_workspace(last - first, col.itemsize)
                 # long events: flat compaction of 16 KB content tiles (one persistent launch) + rank at event boundaries
@@ -1324,7 +1325,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             flat = flat[:n]                     # ... and one that is longer is simply not read beyond len(self)
         out = empty(last - first, flat.dtype)
         if last > first:
-            if self._long_events(n, last - first):
+            if self._long_events(n, last - first, 2):
                 ws, wsb = runtime.elem_workspace(last - first, 4)
                 call("jg_expand_elem", 2, flat.data_ptr(), flat.itemsize, off.data_ptr(), n, _vp(out), last - first, ws,
                      wsb, runtime.stream())

@@ -141,11 +141,15 @@ enum { EXPAND_PARENTS = 0, EXPAND_LOCALINDEX = 1, EXPAND_BROADCAST = 2 };
 
 constexpr int kOwnPositions = 4096;      // positions of a tile the on-chip owner table covers
 
+// (the expansions afford a table of 8192 positions -- 16 KB, still 8 CTAs per SM: tiles of mean counts up to ~14 fit it,
+// so the host keeps such arrays on this kernel instead of the element-tiled one: parents on Poisson(10) 79 -> 9x %)
+constexpr int kExpandPositions = 8192;
+
 template <int MODE, typename V>
 __global__ void __launch_bounds__(kTileThreads)
 expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out, const V *__restrict__ flat) {
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) uint16_t s_own[kOwnPositions + 128];
+    __shared__ __align__(16) uint16_t s_own[kExpandPositions + 128];
     __shared__ V s_flat[MODE == EXPAND_BROADCAST ? kTileEvents : 1];
     EventTile tile;
     // the per-event values do not depend on the offsets: their loads are in flight while the tile's offsets arrive
@@ -164,7 +168,7 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         for (int64_t j = threadIdx.x; j < o0; j += kTileThreads) out[j] = static_cast<V>(-1);
     }
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
-    if (e1 - e0 <= kOwnPositions) {
+    if (e1 - e0 <= kExpandPositions) {
         // short events: scatter + max-scan owner table in shared memory, then a coalesced element-parallel sweep
         const int L = static_cast<int>(e1 - e0);
         if (MODE == EXPAND_BROADCAST) {
@@ -206,7 +210,7 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         }
         return;
     }
-    // long events: the run in chunks of kOwnPositions positions, one owner table each (scatter + running maximum, the
+    // long events: the run in chunks of kExpandPositions positions, one owner table each (scatter + running maximum, the
     // owner of a chunk's first position by one binary search per warp).  A binary search per ELEMENT, as in round 1,
     // is ~60 instructions per element: 1000 tiles with an event of 5 k - 70 k elements among 150 M short events made
     // up 40 % of the kernel's instructions (parents: 1.35 against 1.15 ms without them, profiles/r2_exp32.log).
@@ -215,8 +219,8 @@ expand_kernel(const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ ou
         if (static_cast<int>(threadIdx.x) + kTileThreads < tile.nev) s_flat[threadIdx.x + kTileThreads] = f1;
     }
 #pragma unroll 1
-    for (int64_t cs = 0; cs < e1 - e0; cs += kOwnPositions) {
-        const int L = static_cast<int>(min(static_cast<int64_t>(kOwnPositions), e1 - e0 - cs));
+    for (int64_t cs = 0; cs < e1 - e0; cs += kExpandPositions) {
+        const int L = static_cast<int>(min(static_cast<int64_t>(kExpandPositions), e1 - e0 - cs));
         build_owner_range(s_own, tile, cs, L);          // (ends with a barrier; s_flat is published by its first one)
         V *dst = (MODE == EXPAND_PARENTS) ? out + e0 + cs : out + (e0 + cs - o0);
 #pragma unroll 2

@@ -22,6 +22,8 @@ def ak():
 def make_counts(kind, n, rng):
     if kind == "poisson5":
         return rng.poisson(5.0, n).astype(np.int64)
+    if kind == "poisson10":                      # mean counts of 7 - 14: the event tile staged 32 KB at a time (JG_WIDE_STAGE)
+        return rng.poisson(10.0, n).astype(np.int64)
     if kind == "poisson40":
         return rng.poisson(40.0, n).astype(np.int64)
     if kind == "geometric":                      # heavy tail: mostly short, a few long events
@@ -37,7 +39,8 @@ CASES = [("poisson5", 300000, np.float32), ("poisson5", 300000, np.float64), ("p
          ("geometric", 20000, np.float64), ("sparse", 100000, np.float32), ("poisson5", 1000, np.int32),
          ("geometric", 3000, np.int64), ("poisson5", 20000, np.int8), ("geometric", 3000, np.int16),
          ("poisson5", 20000, np.uint16), ("poisson40", 2000, np.uint32), ("geometric", 3000, np.uint64),
-         ("poisson5", 20000, np.uint8)]
+         ("poisson5", 20000, np.uint8), ("poisson10", 60000, np.float32), ("poisson10", 30000, np.float64),
+         ("poisson10", 30000, np.int32), ("poisson10", 20000, np.uint32), ("poisson10", 20000, np.int16)]
 
 
 @pytest.mark.parametrize("kind,n,dtype", CASES)
@@ -612,7 +615,7 @@ def test_combinatorics_kernel_variants(ak, kind, variant, monkeypatch):
 
 
 @pytest.mark.parametrize("shift", [0, 1, 3])
-@pytest.mark.parametrize("L", [0, 1, 31, 32, 33, 64, 2048, 4064, 4095, 4096, 4097, 8192])
+@pytest.mark.parametrize("L", [0, 1, 31, 32, 33, 64, 2048, 4064, 4095, 4096, 4097, 7167, 7168, 7169, 8192])
 def test_selection_row_edges(ak, L, shift):
     """The compaction walks a staged run in rows of 32 positions padded with a never-selected item
     (csrc/jg_compact.cuh): runs that end on / one short of / one past a row or the stage, in every 16-byte phase,
