@@ -43,6 +43,7 @@ OP = dict(
 RHS_ARRAY, RHS_SCALAR, RHS_PARENT = 0, 1, 2
 COMB_PAIRS, COMB_DISTINCTS, COMB_CHOOSE, COMB_CROSS = 0, 1, 2, 3
 WIDE_STAGE = 0x100               # hint OR-ed into `op` / `is_min` of the event-tiled reductions: mean count 7 - 14 (JG_WIDE_STAGE)
+WIDER_STAGE = 0x200              # ... 14 - 28 (JG_WIDER_STAGE)
 COMB_LONG = 0x100                # hint OR-ed into `kind`: events hold more than a handful of combinations each
 COMB_LONG_MEAN = 8               # ... from this many combinations per event on (512 events then overflow a 4096-entry pair table)
 

@@ -147,15 +147,25 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         return n > 0 and content_len > cls.LONG_EVENTS_MEAN * wide * n and content_len >= (1 << 14)
 
     @classmethod
-    def _stage_hint(cls, n, content_len, dtype):
-        """(element tiles?, hint for the event-tiled call): the reductions keep 4-byte contents with mean counts of
-        7 - 14 on the event-tiled kernels by staging 32 KB per tile (JG_WIDE_STAGE); beyond that -- and from 7 on for
-        8-byte items, whose stage is 32 KB already -- the element-tiled kernels take over."""
+    def _stage_hint(cls, n, content_len, dtype, arg=False):
+        """(element tiles?, hint for the event-tiled call).  The reductions keep 4-byte contents with mean counts of
+        7 - 14 on the event-tiled kernels by staging 32 KB per tile (JG_WIDE_STAGE) and, where the tiles are full enough
+        to pay for 3 CTAs per SM, 64 KB (JG_WIDER_STAGE: means of 14 - 28 for the arg-reductions, 20 - 28 for the others;
+        measured on Poisson(15 / 20 / 26), profiles/r2_exp43.log); elsewhere -- and from 7 on for 8-byte items, whose
+        stage is 32 KB already -- the element-tiled kernels."""
         dtype = numpy.dtype(dtype)
-        wide = 2 if dtype.itemsize == 4 else 1
-        if dtype in _ELEM_DTYPES and cls._long_events(n, content_len, wide):
-            return True, 0
-        return False, (_lib.WIDE_STAGE if wide == 2 and cls._long_events(n, content_len) else 0)
+        can_elem = dtype in _ELEM_DTYPES
+        if dtype.itemsize != 4:
+            return (can_elem and cls._long_events(n, content_len)), 0
+        if not cls._long_events(n, content_len):                    # mean <= 7
+            return False, 0
+        if not cls._long_events(n, content_len, 2):                 # 7 < mean <= 14
+            return False, _lib.WIDE_STAGE
+        if cls._long_events(n, content_len, 4):                     # mean > 28
+            return can_elem, (0 if can_elem else _lib.WIDER_STAGE)
+        if arg or not can_elem or cls._long_events(n, content_len, 20.0 / 7.0):
+            return False, _lib.WIDER_STAGE
+        return True, 0
 
     @classmethod
     def _parents_from(cls, off64, n, last, first=None):
@@ -1550,7 +1560,7 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
         out_index = empty(n, INDEXTYPE)
         scal = runtime.scalars()
         ws, wsb = runtime.workspace(n)
-        elem, hint = self._stage_hint(n, last - first, col.dtype)
+        elem, hint = self._stage_hint(n, last - first, col.dtype, arg=True)
         if elem:
             # long events: element-tiled arg-reduce to best[] (a partial per tile, merged in tile order), then the scan +
             # compaction of jg_compact_nonneg -- N-sized passes, small next to the content when events are long

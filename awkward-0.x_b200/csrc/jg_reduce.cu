@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(kTileThreads, STAGE_BYTES > 16384 ? 6 : 8)
 segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offsets, int64_t n,
                  A *__restrict__ out) {
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
+    // (a stage of more than 32 KB is dynamic shared memory: the static limit is 48 KB per CTA)
+    __shared__ __align__(16) unsigned char s_stage_static[STAGE_BYTES > 32768 ? 16 : STAGE_BYTES + 32];
+    extern __shared__ __align__(16) unsigned char s_stage_dynamic[];
+    unsigned char *const s_stage = STAGE_BYTES > 32768 ? s_stage_dynamic : s_stage_static;
     __shared__ uint64_t s_bar;
     __shared__ Partial<A> s_part[kTileThreads / kWarp];
     using R = Red<OP, T, A>;
@@ -388,7 +391,10 @@ segarg_direct_kernel(const T *__restrict__ content, const int64_t *__restrict__ 
                      uint32_t ntiles) {
     constexpr int NW = kTileThreads / kWarp;
     __shared__ int64_t s_off[kTileEvents + 1];
-    __shared__ __align__(16) unsigned char s_stage[STAGE_BYTES + 32];
+    // (a stage of more than 32 KB is dynamic shared memory: the static limit is 48 KB per CTA)
+    __shared__ __align__(16) unsigned char s_stage_static[STAGE_BYTES > 32768 ? 16 : STAGE_BYTES + 32];
+    extern __shared__ __align__(16) unsigned char s_stage_dynamic[];
+    unsigned char *const s_stage = STAGE_BYTES > 32768 ? s_stage_dynamic : s_stage_static;
     __shared__ uint64_t s_bar;
     __shared__ ArgPartial<T> s_part[NW];
     __shared__ int32_t s_scan[NW + 1];
@@ -535,10 +541,26 @@ template <typename T> struct StageBytes { static constexpr int value = sizeof(T)
 // staged 32 KB per tile instead of 16 KB, so that the 512 events of a tile still fit and such arrays stay on the
 // thread-per-event kernels (5 - 6 resident CTAs per SM instead of 8, twice the bytes each).  Same results either way.
 template <typename T> struct WideStage { static constexpr bool value = sizeof(T) == 4; };
+// JG_WIDER_STAGE (mean 14 - 28): 64 KB per tile, dynamic shared memory, 3 resident CTAs per SM with the same bytes in flight
+constexpr int kWiderStage = 65536;
+template <class K>
+static void allow_wider_stage(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWiderStage + 32);
+}
 
 template <int OP, typename T, typename A>
-static int launch_reduce(const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s, bool wide = false) {
+static int launch_reduce(const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s, int wide = 0) {
     if constexpr (WideStage<T>::value) {
+        if (wide == 2) {
+            static bool allowed = false;
+            if (!allowed) {
+                allow_wider_stage(segreduce_kernel<OP, T, A, kWiderStage>);
+                allowed = true;
+            }
+            segreduce_kernel<OP, T, A, kWiderStage><<<tile_grid(n), kTileThreads, kWiderStage + 32, s>>>(
+                static_cast<const T *>(content), offsets, n, static_cast<A *>(out));
+            return check_launch("segreduce_kernel<wider>");
+        }
         if (wide) {
             segreduce_kernel<OP, T, A, 32768><<<tile_grid(n), kTileThreads, 0, s>>>(
                 static_cast<const T *>(content), offsets, n, static_cast<A *>(out));
@@ -552,8 +574,8 @@ static int launch_reduce(const void *content, const int64_t *offsets, int64_t n,
 
 template <typename T, typename ASUM>
 static int dispatch_reduce(int op, const void *content, const int64_t *offsets, int64_t n, void *out, cudaStream_t s) {
-    const bool wide = (op & JG_WIDE_STAGE) != 0;
-    switch (op & ~JG_WIDE_STAGE) {
+    const int wide = (op & JG_WIDER_STAGE) ? 2 : ((op & JG_WIDE_STAGE) ? 1 : 0);
+    switch (op & ~(JG_WIDE_STAGE | JG_WIDER_STAGE)) {
         case JG_SUM: return launch_reduce<JG_SUM, T, ASUM>(content, offsets, n, out, s, wide);
         case JG_PROD: return launch_reduce<JG_PROD, T, ASUM>(content, offsets, n, out, s, wide);
         case JG_MIN: return launch_reduce<JG_MIN, T, T>(content, offsets, n, out, s, wide);
@@ -602,9 +624,26 @@ static int dispatch_arg_dense(int is_min, const void *content, const int64_t *of
     }
     rc = launch_scan_array(tile_nonempty, ntiles, bases, total, nullptr, scan_ws, ws_bytes - 2 * arr, s);
     if (rc) return rc;
-    const bool wide = (is_min & JG_WIDE_STAGE) != 0;
-    is_min &= ~JG_WIDE_STAGE;
+    const int wide = (is_min & JG_WIDER_STAGE) ? 2 : ((is_min & JG_WIDE_STAGE) ? 1 : 0);
+    is_min &= ~(JG_WIDE_STAGE | JG_WIDER_STAGE);
     if constexpr (WideStage<T>::value) {
+        if (wide == 2) {
+            static bool allowed = false;
+            if (!allowed) {
+                allow_wider_stage(segarg_direct_kernel<true, T, kWiderStage>);
+                allow_wider_stage(segarg_direct_kernel<false, T, kWiderStage>);
+                allowed = true;
+            }
+            if (is_min)
+                segarg_direct_kernel<true, T, kWiderStage><<<static_cast<unsigned>(ntiles), kTileThreads, kWiderStage + 32, s>>>(
+                    static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+                    status, static_cast<uint32_t>(ntiles));
+            else
+                segarg_direct_kernel<false, T, kWiderStage><<<static_cast<unsigned>(ntiles), kTileThreads, kWiderStage + 32, s>>>(
+                    static_cast<const T *>(content), offsets, n, bases, out_offsets, out_index, static_cast<T *>(out_value),
+                    status, static_cast<uint32_t>(ntiles));
+            return check_launch("segarg_direct_kernel<wider>");
+        }
         if (wide) {
             if (is_min)
                 segarg_direct_kernel<true, T, 32768><<<static_cast<unsigned>(ntiles), kTileThreads, 0, s>>>(

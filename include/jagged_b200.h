@@ -93,6 +93,8 @@ enum {
  * the hint 4-byte contents are staged 32 KB per 512-event tile instead of 16 KB, so such arrays stay on the
  * thread-per-event kernels instead of taking the long-tile path (ignored for other item sizes).                     */
 #define JG_WIDE_STAGE 0x100
+/* the same for a mean of 14 - 28 items: 64 KB per tile (dynamic shared memory, 3 resident CTAs per SM)               */
+#define JG_WIDER_STAGE 0x200
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int         jg_version(void);

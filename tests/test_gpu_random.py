@@ -24,6 +24,8 @@ def make_counts(kind, n, rng):
         return rng.poisson(5.0, n).astype(np.int64)
     if kind == "poisson10":                      # mean counts of 7 - 14: the event tile staged 32 KB at a time (JG_WIDE_STAGE)
         return rng.poisson(10.0, n).astype(np.int64)
+    if kind == "poisson20":                      # ... of 14 - 28: 64 KB at a time (JG_WIDER_STAGE)
+        return rng.poisson(20.0, n).astype(np.int64)
     if kind == "poisson40":
         return rng.poisson(40.0, n).astype(np.int64)
     if kind == "geometric":                      # heavy tail: mostly short, a few long events
@@ -40,7 +42,9 @@ CASES = [("poisson5", 300000, np.float32), ("poisson5", 300000, np.float64), ("p
          ("geometric", 3000, np.int64), ("poisson5", 20000, np.int8), ("geometric", 3000, np.int16),
          ("poisson5", 20000, np.uint16), ("poisson40", 2000, np.uint32), ("geometric", 3000, np.uint64),
          ("poisson5", 20000, np.uint8), ("poisson10", 60000, np.float32), ("poisson10", 30000, np.float64),
-         ("poisson10", 30000, np.int32), ("poisson10", 20000, np.uint32), ("poisson10", 20000, np.int16)]
+         ("poisson10", 30000, np.int32), ("poisson10", 20000, np.uint32), ("poisson10", 20000, np.int16),
+         ("poisson20", 40000, np.float32), ("poisson20", 20000, np.int32), ("poisson20", 20000, np.uint32),
+         ("poisson20", 20000, np.float64)]
 
 
 @pytest.mark.parametrize("kind,n,dtype", CASES)
