@@ -142,10 +142,13 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 // owner of every position (scatter + max-scan table, jg_tile.cuh) are kept in shared memory: the broadcast of
 // jagged.py:1003-1037 is never materialised.
 template <class F, typename C, bool TYPED>      // TYPED: both operands already have the compute type (no per-element dtype switch)
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 8)
 binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__restrict__ flat, int rhs_dt, int swap,
                      typename F::Out *__restrict__ out, const int64_t *__restrict__ offsets, int64_t n) {
-    constexpr int KM = 4096;
+    // (an owner table of 8192 positions: tiles of mean counts up to ~14 fit it; a longer run -- long events -- is swept
+    // in chunks, one table each.  Round 1 found the owner of every element of such a tile by a binary search, with an
+    // untyped load per operand: every tile of an array with a mean count above 8 took that path.)
+    constexpr int KM = 8192;
     __shared__ int64_t s_off[kTileEvents + 1];
     __shared__ __align__(16) uint16_t s_own[KM + 128];
     __shared__ C s_flat[kTileEvents];
@@ -153,13 +156,17 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
     tile.load(s_off, offsets, n, blockIdx.x);
     const int64_t o0 = __ldg(offsets);
     const int64_t e0 = tile.first_element(), e1 = tile.last_element();
-    if (e1 - e0 <= KM) {
-        const int L = static_cast<int>(e1 - e0);
+    const int64_t len = e1 - e0;
+    if (len <= 0) return;
 #pragma unroll 1
-        for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
-            s_flat[ev] = TYPED ? __ldg(static_cast<const C *>(flat) + tile.event0 + ev) : load_as<C>(flat, rhs_dt, tile.event0 + ev);
-        build_owner_table(s_own, tile, L);
-        const int64_t d0 = e0 - o0;
+    for (int ev = threadIdx.x; ev < tile.nev; ev += kTileThreads)
+        s_flat[ev] = TYPED ? __ldg(static_cast<const C *>(flat) + tile.event0 + ev) : load_as<C>(flat, rhs_dt, tile.event0 + ev);
+#pragma unroll 1
+    for (int64_t cs = 0; cs < len; cs += KM) {
+        const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
+        if (len <= KM) build_owner_table(s_own, tile, L);         // (both end with a barrier; the first one publishes s_flat)
+        else build_owner_range(s_own, tile, cs, L);
+        const int64_t d0 = e0 - o0 + cs;
         // 4 independent loads in flight per thread (the sweep is otherwise one dependent load per iteration)
 #pragma unroll 1
         for (int p = threadIdx.x; p < L; p += 4 * kTileThreads) {
@@ -182,13 +189,7 @@ binary_parent_kernel(const void *__restrict__ lhs, int lhs_dt, const void *__res
                 }
             }
         }
-        return;
-    }
-    for (int64_t j = e0 + threadIdx.x; j < e1; j += kTileThreads) {
-        const int ev = tile.find_event(j);
-        const C a = load_as<C>(lhs, lhs_dt, j - o0);
-        const C b = load_as<C>(flat, rhs_dt, tile.event0 + ev);
-        __stcs(out + (j - o0), swap ? F::apply(b, a) : F::apply(a, b));
+        if (len > KM) __syncthreads();                            // the table is rewritten by the next chunk
     }
 }
 
