@@ -139,7 +139,10 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
 
     # Count distribution -> kernel variant (north_star: "variants chosen by count distribution").  The event tile (512
     # events, 16 KB of staged content) fits mean counts up to ~7; beyond that -- Poisson(40), a few huge events -- the
-    # element-tiled kernels of csrc/jg_elem.cu split the work by CONTENT instead.  Both give the same results.
+    # element-tiled kernels of csrc/jg_elem.cu split the work by CONTENT instead.  In between the event-tiled kernels are
+    # kept where a larger tile pays (measured per operation: _stage_hint for the reductions, a factor of 2 for parents /
+    # localindex / broadcast, whose owner table covers 8192 positions).  Every variant gives the same results; a tile
+    # that does not fit after all (one long event among short ones) is handled on the device, per tile.
     LONG_EVENTS_MEAN = 7
 
     @classmethod

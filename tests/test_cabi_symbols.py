@@ -110,3 +110,29 @@ def test_ctypes_prototypes_have_the_header_types():
             if c != p and not any({c, p} <= s for s in same_width):
                 bad.append((name, i, c, p))
     assert not bad, bad
+
+
+def test_host_rule_for_the_count_distribution():
+    """Host logic, no GPU: which kernel family a reduction takes from (events, content length, dtype) --
+    JaggedArray._stage_hint: 16 KB event tile up to a mean count of 7, 32 KB (JG_WIDE_STAGE) up to 14 and 64 KB
+    (JG_WIDER_STAGE) up to 28 for 4-byte contents where measured to win, element tiles elsewhere; the hints are the
+    header's values."""
+    import re
+    import numpy
+    import awkward0_b200 as ak
+    from awkward0_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "jagged_b200.h")).read()
+    assert int(re.search(r"#define JG_WIDE_STAGE (0x[0-9a-f]+)", header).group(1), 16) == _lib.WIDE_STAGE
+    assert int(re.search(r"#define JG_WIDER_STAGE (0x[0-9a-f]+)", header).group(1), 16) == _lib.WIDER_STAGE
+    hint = ak.JaggedArray._stage_hint
+    n = 1000000
+    f32, f64, u32 = numpy.float32, numpy.float64, numpy.uint32
+    assert hint(n, 5 * n, f32) == (False, 0) and hint(n, 5 * n, f64) == (False, 0)
+    assert hint(n, 10 * n, f32) == (False, _lib.WIDE_STAGE) and hint(n, 10 * n, f32, arg=True) == (False, _lib.WIDE_STAGE)
+    assert hint(n, 10 * n, f64) == (True, 0)                                  # (its stage is 32 KB already)
+    assert hint(n, 17 * n, f32) == (True, 0) and hint(n, 17 * n, f32, arg=True) == (False, _lib.WIDER_STAGE)
+    assert hint(n, 24 * n, f32) == (False, _lib.WIDER_STAGE)
+    assert hint(n, 40 * n, f32) == (True, 0) and hint(n, 40 * n, f32, arg=True) == (True, 0)
+    assert hint(n, 40 * n, u32) == (False, _lib.WIDER_STAGE)                   # (no element-tiled kernels for this dtype)
+    assert hint(100, 1000, f32) == (False, 0)                                 # (tiny arrays: nothing to choose)
+    assert hint(0, 0, f32) == (False, 0)
