@@ -134,7 +134,7 @@ _KERNELS = {"jg_flat_reduce": 2, "jg_startsstops2parents": 2, "jg_validate_start
             "jg_compare_select_elem": 5, "jg_expand_elem": 2}
 
 
-_PHASED = {"jg_mask_select_phase": (3, 2, 1, 2), "jg_compare_select_phase": (3, 2, 1, 2)}      # launches of phase 0 / 1 / 2 / 3
+_PHASED = {"jg_mask_select_phase": (3, 2, 1, 2), "jg_compare_select_phase": (3, 2, 1, 2, 1)}   # launches of phase 0 / 1 / 2 / 3 (/ 4)
 
 
 def call(name, *args):

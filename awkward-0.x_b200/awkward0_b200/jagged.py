@@ -58,6 +58,8 @@ class _bothmethod(object):
 # Selection schedule of the event-tiled path: False = counting pass, scan of the tile totals, compaction (K is read back
 # while the compaction runs); True = ONE pass on published tile aggregates (include/jagged_b200.h, phase 3).
 SELECT_SINGLE_PASS = [os.environ.get("JG_SELECT_SINGLE", "0") == "1"]
+# the fifth single-pass form (ranges of 8 tiles per CTA, include/jagged_b200.h: phase 4), float32 compared columns only
+SELECT_RANGES = [os.environ.get("JG_SELECT_RANGES", "0") == "1"]
 
 
 class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
@@ -1261,7 +1263,8 @@ class JaggedArray(numpy.lib.mixins.NDArrayOperatorsMixin):
             else:
                 # the first column in two phases: count + scan, start reading K back, queue the compaction; the host
                 # then waits for K alone and the next operation is queued while the compaction is still running
-                for phase in ((3,) if SELECT_SINGLE_PASS[0] else ((1, 2) if not columns else (0,))):
+                ranges = SELECT_RANGES[0] and fused and same and col.itemsize == 4
+                for phase in ((4,) if ranges else (3,) if SELECT_SINGLE_PASS[0] else ((1, 2) if not columns else (0,))):
                     if fused:
                         call("jg_compare_select_phase", col.data_ptr(), col.itemsize, col.data_ptr() if same else key.data_ptr(),
                              jg_code(key.dtype), op, ctypes.c_double(scalar), 0 if same else mask_shift, off.data_ptr(), n,

@@ -109,6 +109,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     while (!mbar_try_wait(bar, phase)) {
     }
 }
+// generic-proxy accesses to shared memory (reads of the previous tile, head / tail bytes) must be ordered before the
+// async proxy (TMA) overwrites the same buffer: called by the thread that starts the next bulk copy into a stage that
+// has been read, after the barrier that ends those reads
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // global -> shared bulk copy; src, dst 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile(

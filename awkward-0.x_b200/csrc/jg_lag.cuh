@@ -161,12 +161,6 @@ __device__ __forceinline__ int64_t lag_prefix(const LagDesc &d, uint32_t tile) {
     return static_cast<int64_t>(warp_reduce_add(sum));
 }
 
-// generic-proxy accesses to shared memory (reads of the previous tile, head / tail bytes) must be ordered before the
-// async proxy (TMA) overwrites the same buffer in the next iteration
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 #endif  // __CUDACC__
 
 }  // namespace jg

@@ -165,8 +165,10 @@ segreduce_kernel(const T *__restrict__ content, const int64_t *__restrict__ offs
         __syncthreads();                                 // the stage is free (the previous group has been read)
         const T *sm = reinterpret_cast<const T *>(s_stage);
         if (nb > 0) {
-            if (threadIdx.x == 0)
+            if (threadIdx.x == 0) {
+                fence_proxy_async_smem();
                 stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb), &s_bar);
+            }
             const uint32_t shift = stage_edges<sizeof(T)>(
                 s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb));
             stage_wait(&s_bar, phase);
@@ -354,8 +356,10 @@ __device__ __noinline__ void segarg_long_tile(const T *__restrict__ content, con
         __syncthreads();                             // the stage is free (the previous group has been read)
         const T *sm = reinterpret_cast<const T *>(s_stage);
         if (nb > 0) {
-            if (threadIdx.x == 0)
+            if (threadIdx.x == 0) {
+                fence_proxy_async_smem();
                 stage_bulk(s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb), s_bar);
+            }
             const uint32_t shift = stage_edges<sizeof(T)>(
                 s_stage, reinterpret_cast<const unsigned char *>(content + start), static_cast<uint32_t>(nb));
             stage_wait(s_bar, phase);

@@ -279,6 +279,7 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
         const V *gc = content + e0 + cs;
         const E *gm = mask + e0 + mask_shift + cs;
         if (threadIdx.x == 0) {
+            fence_proxy_async_smem();          // (the previous chunk's reads of the stage, ended by the barrier above)
             if (!SAME) stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(gm), static_cast<uint32_t>(L * sizeof(E)), &s_bar[1]);
             stage_bulk(s_content, reinterpret_cast<const unsigned char *>(gc), static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
         }
@@ -330,6 +331,151 @@ mask_fill_kernel(const SEL sel, const V *__restrict__ content, const typename SE
             new_offsets[tile.event0 + ev] = base + s_new[ev];
             if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The fifth single-pass form (phase = 4, JG_SELECT_RANGES=1 for the Python host): one CTA owns a RANGE of kRangeTiles
+// consecutive event tiles.  Phase A: one warp per tile counts its run straight from global memory (a streaming read
+// that leaves the range in L2), the range total is published (jg_lag.cuh) and the range's base is the sum of what the
+// ranges before it published -- ONE wait per kRangeTiles tiles, for CTAs that were dispatched earlier and publish at
+// the very start of their life.  Phase B: the tiles of the range one after the other, each staged (an L2 hit a few
+// microseconds after phase A) and compacted like the chunks of an oversize tile, with the tile's base known on chip.
+// The column is read from HBM once; a CTA lives ~8 tiles long and holds one tile's shared memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kRangeTiles = 8;
+
+template <typename V, int KM, class SEL, bool SAME>
+__global__ void __launch_bounds__(kTileThreads, sizeof(V) == 8 ? 5 : (SAME ? 7 : 6))
+mask_range_kernel(const SEL sel, const V *__restrict__ content, const typename SEL::Elem *__restrict__ mask,
+                  int64_t mask_shift, const int64_t *__restrict__ offsets, int64_t n, V *__restrict__ out,
+                  int64_t *__restrict__ new_offsets, int64_t *__restrict__ new_counts, uint32_t ntiles,
+                  const LagDesc lag, int64_t *__restrict__ total_out) {
+    using E = typename SEL::Elem;
+    static_assert(!SAME || sizeof(E) == sizeof(V), "SAME needs the selector to read the content's own items");
+    static_assert(kRangeTiles <= kTileThreads / kWarp, "one warp per tile in the counting phase");
+    constexpr int NW = kTileThreads / kWarp;
+    __shared__ int64_t s_off[kTileEvents + 1];
+    __shared__ __align__(16) unsigned char s_content[KM * sizeof(V) + 32 + (SAME ? 32 * sizeof(V) : 0)];
+    __shared__ __align__(16) unsigned char s_mask[SAME ? 16 : KM * sizeof(E) + 32 + 32 * sizeof(E)];
+    __shared__ uint16_t s_pfx[KM + 2];
+    __shared__ uint64_t s_bar[2];
+    __shared__ int32_t s_scan[NW + 1];
+    __shared__ int64_t s_bound[kRangeTiles + 1];
+    __shared__ int64_t s_tilebase[kRangeTiles + 1];
+    __shared__ int64_t s_base;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t range = blockIdx.x;
+    const uint32_t t0 = range * kRangeTiles;
+    const int nt = static_cast<int>(min(static_cast<uint32_t>(kRangeTiles), ntiles - t0));
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (static_cast<int>(threadIdx.x) <= nt) {
+        const int64_t ev = min(n, static_cast<int64_t>(t0 + threadIdx.x) * kTileEvents);
+        s_bound[threadIdx.x] = __ldg(offsets + ev);
+    }
+    __syncthreads();
+    // ---- phase A: one warp per tile
+    if (warp < nt) {
+        const int64_t a = s_bound[warp], b = s_bound[warp + 1];
+        int64_t cnt = count_run<SEL, 4>(sel, mask + a + mask_shift, b - a, lane, kWarp);
+        cnt = warp_reduce_add(cnt);
+        if (lane == 0) s_tilebase[warp + 1] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int64_t total = 0;
+        if (lane == 0) {
+            s_tilebase[0] = 0;
+            for (int j = 1; j <= nt; ++j) {
+                total += s_tilebase[j];
+                s_tilebase[j] = total;              // -> exclusive bases of the tiles, [nt] = the range's total
+            }
+            lag_publish(lag, range, total);
+        }
+        const int64_t rb = lag_prefix(lag, range);
+        if (lane == 0) {
+            s_base = rb;
+            if (t0 + nt == ntiles) {
+                new_offsets[n] = rb + total;
+                *total_out = rb + total;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t range_base = s_base;
+    uint32_t phase = 0;
+    // ---- phase B: the tiles one after the other, each compacted chunk by chunk (one chunk unless events are long)
+#pragma unroll 1
+    for (int j = 0; j < nt; ++j) {
+        EventTile tile;
+        tile.load(s_off, offsets, n, t0 + j);
+        const int64_t base = range_base + s_tilebase[j];
+        const int64_t e0 = tile.first_element(), len = tile.last_element() - e0;
+        const int evA = threadIdx.x, evB = threadIdx.x + kTileThreads;
+        const int64_t stA = evA < tile.nev ? s_off[evA] - e0 : -1;
+        const int64_t stB = evB < tile.nev ? s_off[evB] - e0 : -1;
+        __syncthreads();          // every start is in its thread's registers: the offsets tile becomes the NEW offsets
+        int64_t *s_new = s_off;
+        int64_t run = 0;
+#pragma unroll 1
+        for (int64_t cs = 0; cs < len; cs += KM) {
+            const int L = static_cast<int>(min(static_cast<int64_t>(KM), len - cs));
+            const V *gc = content + e0 + cs;
+            const E *gm = mask + e0 + mask_shift + cs;
+            if (threadIdx.x == 0) {
+                fence_proxy_async_smem();
+                if (!SAME) stage_bulk(s_mask, reinterpret_cast<const unsigned char *>(gm), static_cast<uint32_t>(L * sizeof(E)), &s_bar[1]);
+                stage_bulk(s_content, reinterpret_cast<const unsigned char *>(gc), static_cast<uint32_t>(L * sizeof(V)), &s_bar[0]);
+            }
+            const uint32_t cshift = stage_edges<sizeof(V)>(s_content, reinterpret_cast<const unsigned char *>(gc), static_cast<uint32_t>(L * sizeof(V)));
+            const V *cv = reinterpret_cast<const V *>(s_content + cshift);
+            E *pad;
+            if (SAME) {
+                pad = reinterpret_cast<E *>(s_content + cshift);
+            } else {
+                const uint32_t ms = stage_edges<sizeof(E)>(s_mask, reinterpret_cast<const unsigned char *>(gm), static_cast<uint32_t>(L * sizeof(E)));
+                pad = reinterpret_cast<E *>(s_mask + ms);
+            }
+            const E *mv = pad;
+            if (warp == 1) rows_pad<SEL>(pad, L, lane);
+            mbar_wait(&s_bar[0], phase);
+            if (!SAME) mbar_wait(&s_bar[1], phase);
+            phase ^= 1u;
+            __syncthreads();
+            const int rows_total = (L + 31) >> 5;
+            const int rows_per_warp = (rows_total + NW - 1) / NW;
+            const int r_begin = min(rows_total, warp * rows_per_warp);
+            const int r_end = min(rows_total, r_begin + rows_per_warp);
+            const int cnt = rows_count(sel, mv, r_begin, r_end, lane);
+            if (lane == 0) s_scan[warp] = cnt;
+            __syncthreads();
+            uint32_t wrun = __reduce_add_sync(0xffffffffu, lane < warp ? s_scan[lane] : 0);
+            wrun = rows_compact<V, SEL, SAME>(sel, mv, cv, s_pfx, r_begin, r_end, lane, wrun, out + base + run);
+            if (warp == NW - 1 && lane == 0) s_pfx[rows_total << 5] = static_cast<uint16_t>(wrun);
+            __syncthreads();
+            if (stA >= cs && stA < cs + L) s_new[evA] = run + s_pfx[stA - cs];
+            if (stB >= cs && stB < cs + L) s_new[evB] = run + s_pfx[stB - cs];
+            run += s_pfx[L];
+            __syncthreads();      // the stage, s_pfx and s_scan are rewritten by the next chunk
+        }
+        if (stA >= len) s_new[evA] = run;       // empty events at the end of the tile (all of them when it is empty)
+        if (stB >= len) s_new[evB] = run;
+        if (threadIdx.x == 0) s_new[tile.nev] = run;
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ev = threadIdx.x + h * kTileThreads;
+            if (ev < tile.nev) {
+                new_offsets[tile.event0 + ev] = base + s_new[ev];
+                if (new_counts) new_counts[tile.event0 + ev] = s_new[ev + 1] - s_new[ev];
+            }
+        }
+        __syncthreads();          // the offsets tile is reloaded for the next tile of the range
     }
 }
 
@@ -544,6 +690,26 @@ static int launch_mask_select(const SEL &sel, const void *content, const typenam
     return check_launch("mask_fill_kernel");
 }
 
+// phase 4: ranges of kRangeTiles tiles per CTA (mask_range_kernel), ONE launch
+template <typename V, int KM, class SEL, bool SAME>
+static int launch_mask_ranges(const SEL &sel, const void *content, const typename SEL::Elem *mask, int64_t mask_shift,
+                              const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets, int64_t *new_counts,
+                              int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s) {
+    const int64_t ntiles = tile_grid(n);
+    const int64_t nranges = ceil_div(ntiles, kRangeTiles);
+    const size_t need = lag_ws_bytes(nranges);
+    JG_REQUIRE(ws != nullptr && ws_bytes >= need + 256, "jg_mask_select: workspace too small for the range descriptors");
+    if (cudaMemsetAsync(ws, 0, need, s) != cudaSuccess) {
+        set_error("jg_mask_select: cudaMemsetAsync failed");
+        return -3;
+    }
+    const LagDesc lag = lag_carve(ws, nranges);
+    mask_range_kernel<V, KM, SEL, SAME><<<static_cast<unsigned>(nranges), kTileThreads, 0, s>>>(
+        sel, static_cast<const V *>(content), mask, mask_shift, offsets, n, static_cast<V *>(out), new_offsets,
+        new_counts, static_cast<uint32_t>(ntiles), lag, total);
+    return check_launch("mask_range_kernel");
+}
+
 // staged positions per tile: content + selector + 16-bit prefix must leave room for ~6 CTAs per SM
 template <class SEL, bool SAME>
 static int dispatch_mask_select(const SEL &sel, const void *content, int itemsize, const typename SEL::Elem *mask,
@@ -551,7 +717,10 @@ static int dispatch_mask_select(const SEL &sel, const void *content, int itemsiz
                                 int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, cudaStream_t s, int phase) {
     constexpr int E = sizeof(typename SEL::Elem);
     if constexpr (SAME) {
-        if constexpr (E == 4) return launch_mask_select<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
+        if constexpr (E == 4) {
+            if (phase == 4) return launch_mask_ranges<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s);
+            return launch_mask_select<uint32_t, 4096, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
+        }
         else return launch_mask_select<uint64_t, 3584, SEL, true>(sel, content, mask, mask_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase);
     } else {
         constexpr int KM8 = E == 1 ? 3584 : (E == 4 ? 3072 : 2304);   // (f64 by another f64 column: the host keeps the mask path)
@@ -632,7 +801,7 @@ int jg_compare_select_phase(const void *content, int itemsize, const void *key, 
     JG_REQUIRE(n >= 0 && offsets && new_offsets && key, "jg_compare_select: bad arguments");
     JG_REQUIRE(op == JG_OP_GT || op == JG_OP_GE || op == JG_OP_LT || op == JG_OP_LE,
                "jg_compare_select: operator %d is not an ordering comparison", op);
-    JG_REQUIRE(phase >= 0 && phase <= 3, "jg_compare_select: phase must be 0 .. 3");
+    JG_REQUIRE(phase >= 0 && phase <= 4, "jg_compare_select: phase must be 0 .. 4");
     cudaStream_t s = as_stream(stream);
     const bool strict = (op == JG_OP_GT || op == JG_OP_LT);
 #define JG_CS(K, ST) compare_select<K, ST>(content, itemsize, key, op, scalar, key_shift, offsets, n, out, new_offsets, new_counts, total, ws, ws_bytes, s, phase)

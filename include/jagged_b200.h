@@ -210,7 +210,10 @@ int jg_compare_select(const void *content, int itemsize, const void *key, int ke
                       int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
                       int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, void *stream);
 
-/* jg_compare_select in two calls (see jg_mask_select_phase)                                                           */
+/* jg_compare_select in two calls (see jg_mask_select_phase).  phase 4 (float32 column compared with itself; like phase 0
+ * otherwise): the whole selection as ONE launch in which a CTA counts a range of 8 event tiles from global memory, takes
+ * the range's base from the published aggregates and then compacts its tiles from L2 -- the fifth single-pass form,
+ * bit-exact, measured slower than the three launches (1.96 vs 1.58 ms) and kept as that measured alternative.          */
 int jg_compare_select_phase(const void *content, int itemsize, const void *key, int key_dtype, int op, double scalar,
                             int64_t key_shift, const int64_t *offsets, int64_t n, void *out, int64_t *new_offsets,
                             int64_t *new_counts, int64_t *total, void *ws, size_t ws_bytes, int phase, void *stream);
