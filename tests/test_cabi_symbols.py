@@ -136,3 +136,36 @@ def test_host_rule_for_the_count_distribution():
     assert hint(n, 40 * n, u32) == (False, _lib.WIDER_STAGE)                   # (no element-tiled kernels for this dtype)
     assert hint(100, 1000, f32) == (False, 0)                                 # (tiny arrays: nothing to choose)
     assert hint(0, 0, f32) == (False, 0)
+
+
+def test_staged_tile_kernels_hold_tma_bulk_copies_for_sm100a():
+    """The library's device code is sm_100a only, and the kernels DESIGN.md section 3 describes as TMA-staged really
+    contain 1-D bulk copies (SASS `UBLKCP`) with their mbarriers (`SYNCS`); nothing is a tensor-core kernel.  Static
+    (cuobjdump on the built .so), so it runs without a GPU; `profiles/sass_evidence.py` prints the whole table."""
+    import shutil
+    import subprocess
+    import pytest
+    from awkward0_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump is not on PATH")
+    elfs = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    staged, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            staged[cur] = [False, False]
+        elif cur is not None:
+            if "UBLKCP" in line:
+                staged[cur][0] = True
+            elif "SYNCS" in line:
+                staged[cur][1] = True
+    assert len(staged) > 500
+    assert not re.search(r"\b(UTCHMMA|UTCMMA|HMMA|IMMA|DMMA)\b", sass)      # no contraction anywhere on this path
+    for family in ("segreduce_kernel", "segarg_direct_kernel", "mask_fill_kernel", "scan_win_kernel", "scan_tma_kernel",
+                   "segreduce_elem_kernel", "segarg_elem_kernel", "select_elem_fill_kernel", "argsort_kernel"):
+        members = [v for k, v in staged.items() if re.search(r"\d+%s[A-Z]" % family, k)]
+        assert members, family
+        assert all(bulk and mbar for bulk, mbar in members), family
